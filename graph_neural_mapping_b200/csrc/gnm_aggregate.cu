@@ -1,0 +1,242 @@
+// Neighbour aggregation over the block-diagonal CSR (reference: models/graphcnn.py:154-161, :178-182)
+// and the small row-wise helpers that go with it (eps gradient, layer-0 table gradient).
+#include "gnm_common.cuh"
+
+namespace {
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+    float4 v;
+    __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float4*>(p)); }
+    __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+    __device__ __forceinline__ void fma(float w, const Vec<4>& o) {
+        v.x = fmaf(w, o.v.x, v.x); v.y = fmaf(w, o.v.y, v.y); v.z = fmaf(w, o.v.z, v.z); v.w = fmaf(w, o.v.w, v.w);
+    }
+    __device__ __forceinline__ void div(float d) { v.x /= d; v.y /= d; v.z /= d; v.w /= d; }
+    __device__ __forceinline__ void xor_add(int o) {
+        v.x += __shfl_xor_sync(GNM_FULL_MASK, v.x, o); v.y += __shfl_xor_sync(GNM_FULL_MASK, v.y, o);
+        v.z += __shfl_xor_sync(GNM_FULL_MASK, v.z, o); v.w += __shfl_xor_sync(GNM_FULL_MASK, v.w, o);
+    }
+};
+template <>
+struct Vec<1> {
+    float v;
+    __device__ __forceinline__ void zero() { v = 0.f; }
+    __device__ __forceinline__ void load(const float* p) { v = __ldg(p); }
+    __device__ __forceinline__ void store(float* p) const { *p = v; }
+    __device__ __forceinline__ void fma(float w, const Vec<1>& o) { v = fmaf(w, o.v, v); }
+    __device__ __forceinline__ void div(float d) { v /= d; }
+    __device__ __forceinline__ void xor_add(int o) { v += __shfl_xor_sync(GNM_FULL_MASK, v, o); }
+};
+
+// Warp per destination row. The warp is split into G = 32/LPR groups of LPR lanes; each group
+// owns one neighbour at a time and its lanes cover LPR*VEC consecutive features of that
+// neighbour's row with one (128-bit when VEC == 4) coalesced load. Column indices are read
+// 32 at a time (coalesced) and broadcast with shuffles; four neighbours per group are in
+// flight per iteration. blockIdx.y tiles feature columns when F > LPR*VEC.
+template <int VEC, int LPR>
+__global__ void __launch_bounds__(256)
+aggregate_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n_rows,
+                 const float* __restrict__ src, int64_t ld_src, const int32_t* __restrict__ src_map,
+                 float* __restrict__ dst, int64_t ld_dst, int n_feat, int mode, const float* __restrict__ eps,
+                 const float* __restrict__ bias) {
+    constexpr int G = 32 / LPR;
+    const int row = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / LPR, sub = lane % LPR;
+    const int col = blockIdx.y * (LPR * VEC) + sub * VEC;
+    const bool active = col < n_feat;
+    const int cc = active ? col : 0;
+    const int s = rowptr[row], e = rowptr[row + 1];
+    Vec<VEC> acc;
+    acc.zero();
+    for (int k = s; k < e; k += 32) {
+        const int idx = (k + lane < e) ? colidx[k + lane] : -1;
+        const int cnt = min(32, e - k);
+        for (int t = 0; t < cnt; t += 4 * G) {
+            int j[4];
+            float w[4];
+            Vec<VEC> x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int sl = t + u * G + grp;
+                j[u] = __shfl_sync(GNM_FULL_MASK, idx, sl & 31);
+                if (sl >= 32) j[u] = -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int jj = max(j[u], 0);
+                w[u] = (j[u] >= 0) ? 1.f : 0.f;
+                if (mode == 2) {
+                    const int dj = rowptr[jj + 1] - rowptr[jj];
+                    w[u] = (j[u] >= 0) ? 1.f / (float)dj : 0.f;
+                }
+                const int64_t r = src_map ? (int64_t)src_map[jj] : (int64_t)jj;
+                x[u].load(src + r * ld_src + cc);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc.fma(w[u], x[u]);
+        }
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) acc.xor_add(o);
+    if (grp == 0 && active) {
+        if (mode == 1) acc.div((float)(e - s));
+        if (eps != nullptr) {
+            const float c = 1.f + __ldg(eps);
+            const int64_t r = src_map ? (int64_t)src_map[row] : (int64_t)row;
+            Vec<VEC> self;
+            self.load(src + r * ld_src + col);
+            acc.fma(c, self);
+        }
+        if (bias != nullptr) {
+            Vec<VEC> bv;
+            bv.load(bias + col);
+            acc.fma(1.f, bv);
+        }
+        acc.store(dst + (int64_t)row * ld_dst + col);
+    }
+}
+
+template <int VEC, int LPR>
+int launch_aggregate(const int32_t* rowptr, const int32_t* colidx, int n_rows, const float* src, int64_t ld_src,
+                     const int32_t* src_map, float* dst, int64_t ld_dst, int n_feat, int mode, const float* eps,
+                     const float* bias, cudaStream_t st) {
+    const int rows_per_block = 8;
+    dim3 grid((n_rows + rows_per_block - 1) / rows_per_block, (n_feat + LPR * VEC - 1) / (LPR * VEC));
+    aggregate_kernel<VEC, LPR><<<grid, rows_per_block * 32, 0, st>>>(rowptr, colidx, n_rows, src, ld_src, src_map, dst,
+                                                                      ld_dst, n_feat, mode, eps, bias);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+// sum_i <a[i], b[map(i)]>: one warp per row slice, block reduce, one double atomic per block.
+__global__ void __launch_bounds__(256)
+dot_rows_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
+                const int32_t* __restrict__ b_map, int n_rows, int n_feat, double* __restrict__ out) {
+    __shared__ double part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wg = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+    float acc = 0.f;
+    double dacc = 0.0;
+    for (int r = wg; r < n_rows; r += nw) {
+        const int64_t rb = b_map ? (int64_t)b_map[r] : (int64_t)r;
+        const float* pa = a + (int64_t)r * lda;
+        const float* pb = b + rb * ldb;
+        for (int c = lane; c < n_feat; c += 32) acc = fmaf(pa[c], __ldg(pb + c), acc);
+        dacc += (double)acc;   // flush the fp32 partial every row: keeps long sums accurate
+        acc = 0.f;
+    }
+    dacc = warp_sum_d(dacc);
+    if (lane == 0) part[warp] = dacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += part[i];
+        atomicAdd(out, t);
+    }
+}
+
+// table_grad[tags[r], :] += g[r, :]. Each CTA owns a contiguous slab of rows and a feature
+// chunk; it accumulates into a shared-memory copy of the (table rows x chunk) tile and then
+// flushes once with global atomics: (#CTAs x tile) atomics instead of one per element of g.
+__global__ void __launch_bounds__(256)
+scatter_rows_add_kernel(const float* __restrict__ g, int64_t ldg, const int32_t* __restrict__ tags, int n_rows,
+                        int n_feat, float* __restrict__ table_grad, int64_t ldt, int n_table_rows, int fchunk,
+                        int rows_per_cta) {
+    extern __shared__ float tile[];   // [n_table_rows][fchunk]
+    const int f0 = blockIdx.y * fchunk;
+    const int fw = min(fchunk, n_feat - f0);
+    for (int i = threadIdx.x; i < n_table_rows * fchunk; i += blockDim.x) tile[i] = 0.f;
+    __syncthreads();
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(n_rows, r0 + rows_per_cta);
+    // threads cover (row, feature) pairs with features fastest: coalesced reads of g
+    const int tpr = min(fw, (int)blockDim.x);          // threads per row
+    const int rstep = blockDim.x / tpr;
+    const int tf = threadIdx.x % tpr, tr = threadIdx.x / tpr;
+    if (tr < rstep) {
+        for (int r = r0 + tr; r < r1; r += rstep) {
+            const int t = tags[r];
+            if (t < 0 || t >= n_table_rows) continue;
+            for (int f = tf; f < fw; f += tpr) atomicAdd(&tile[t * fchunk + f], g[(int64_t)r * ldg + f0 + f]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_table_rows * fchunk; i += blockDim.x) {
+        const int t = i / fchunk, f = i % fchunk;
+        const float v = tile[i];
+        if (f < fw && v != 0.f) atomicAdd(&table_grad[(int64_t)t * ldt + f0 + f], v);
+    }
+}
+
+}  // namespace
+
+extern "C" int gnm_aggregate(const int32_t* rowptr, const int32_t* colidx, int n_rows, const float* src,
+                             int64_t ld_src, const int32_t* src_map, float* dst, int64_t ld_dst, int n_feat, int mode,
+                             const float* eps, const float* bias, gnm_stream_t stream) {
+    if (n_rows < 0 || n_feat < 0 || mode < 0 || mode > 2) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0 || n_feat == 0) return GNM_OK;
+    if (!rowptr || !src || !dst) return GNM_ERR_BAD_ARG;
+    cudaStream_t st = gnm_cast_stream(stream);
+    const bool vec4 = (n_feat % 4 == 0) && (ld_src % 4 == 0) && (ld_dst % 4 == 0) && gnm_aligned16(src) &&
+                      gnm_aligned16(dst) && (bias == nullptr || gnm_aligned16(bias));
+#define GNM_AGG(V, L) \
+    return launch_aggregate<V, L>(rowptr, colidx, n_rows, src, ld_src, src_map, dst, ld_dst, n_feat, mode, eps, bias, st)
+    if (vec4) {
+        const int q = n_feat / 4;
+        if (q <= 1) GNM_AGG(4, 1);
+        if (q <= 2) GNM_AGG(4, 2);
+        if (q <= 4) GNM_AGG(4, 4);
+        if (q <= 8) GNM_AGG(4, 8);
+        if (q <= 16) GNM_AGG(4, 16);
+        GNM_AGG(4, 32);
+    } else {
+        if (n_feat <= 2) GNM_AGG(1, 2);
+        if (n_feat <= 4) GNM_AGG(1, 4);
+        if (n_feat <= 8) GNM_AGG(1, 8);
+        if (n_feat <= 16) GNM_AGG(1, 16);
+        GNM_AGG(1, 32);
+    }
+#undef GNM_AGG
+}
+
+extern "C" int gnm_dot_rows(const float* a, int64_t lda, const float* b, int64_t ldb, const int32_t* b_map,
+                            int n_rows, int n_feat, double* out, gnm_stream_t stream) {
+    if (n_rows < 0 || n_feat < 0) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0 || n_feat == 0) return GNM_OK;
+    if (!a || !b || !out) return GNM_ERR_BAD_ARG;
+    int blocks = (n_rows + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    dot_rows_kernel<<<blocks, 256, 0, gnm_cast_stream(stream)>>>(a, lda, b, ldb, b_map, n_rows, n_feat, out);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_scatter_rows_add(const float* g, int64_t ldg, const int32_t* tags, int n_rows, int n_feat,
+                                    float* table_grad, int64_t ldt, int n_table_rows, gnm_stream_t stream) {
+    if (n_rows < 0 || n_feat < 0 || n_table_rows < 0) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0 || n_feat == 0 || n_table_rows == 0) return GNM_OK;
+    if (!g || !tags || !table_grad) return GNM_ERR_BAD_ARG;
+    // feature chunk so that the tile fits in ~96 KB of shared memory
+    int fchunk = n_feat;
+    while ((int64_t)n_table_rows * fchunk * 4 > 96 * 1024 && fchunk > 1) fchunk = (fchunk + 1) / 2;
+    if ((int64_t)n_table_rows * fchunk * 4 > 200 * 1024) return GNM_ERR_TOO_LARGE;
+    const int fparts = (n_feat + fchunk - 1) / fchunk;
+    int ctas = 148 * 2 / fparts;
+    if (ctas < 1) ctas = 1;
+    int rows_per_cta = (n_rows + ctas - 1) / ctas;
+    if (rows_per_cta < 64) rows_per_cta = 64;
+    ctas = (n_rows + rows_per_cta - 1) / rows_per_cta;
+    const size_t smem = (size_t)n_table_rows * fchunk * 4;
+    cudaError_t e = cudaFuncSetAttribute(scatter_rows_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid(ctas, fparts);
+    scatter_rows_add_kernel<<<grid, 256, smem, gnm_cast_stream(stream)>>>(g, ldg, tags, n_rows, n_feat, table_grad, ldt,
+                                                                          n_table_rows, fchunk, rows_per_cta);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}

@@ -1,0 +1,48 @@
+// Shared device helpers for libgnm (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gnm.h"
+
+#define GNM_FULL_MASK 0xffffffffu
+
+#define GNM_RETURN_IF_LAUNCH_FAILED()                 \
+    do {                                              \
+        cudaError_t e__ = cudaGetLastError();         \
+        if (e__ != cudaSuccess) return (int)e__;      \
+    } while (0)
+
+static inline cudaStream_t gnm_cast_stream(gnm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__host__ __device__ static inline bool gnm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(GNM_FULL_MASK, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(GNM_FULL_MASK, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int warp_inclusive_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(GNM_FULL_MASK, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// Streaming (read-once) 128-bit load that does not allocate in L1.
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}

@@ -1,0 +1,214 @@
+// DGI discriminator scoring (reference: models/discriminator.py:19-38, models/graphcnn.py:233-246)
+// as a fused segmented reduction: nn.Bilinear(n_h, n_h, 1) is h^T W c + b = <h, u_g> + b with
+// u_g = W c_g computed once per graph, instead of ATen's _trilinear expansion over all M rows.
+#include "gnm_common.cuh"
+
+namespace {
+
+constexpr int kMaxFeatPerLane = 32;   // n_h = L*F up to 1024
+
+__global__ void gather_nf_rows_kernel(const float* __restrict__ h_all, int64_t layer_stride, int n_layers, int n_feat,
+                                      int64_t ldh, int n_rows, float* __restrict__ table) {
+    const int nh = n_layers * n_feat;
+    const int64_t total = (int64_t)n_rows * nh;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / nh), c = (int)(i % nh);
+        const int l = c / n_feat, f = c % n_feat;
+        table[i] = h_all[l * layer_stride + (int64_t)r * ldh + f];
+    }
+}
+
+// One CTA (8 warps) per graph; u_g staged in shared memory; one warp per node row.
+__global__ void __launch_bounds__(256)
+dgi_score_fwd_kernel(const float* __restrict__ h_all, int64_t layer_stride, int n_layers, int n_feat, int64_t ldh,
+                     int n_rows, const float* __restrict__ u, const float* __restrict__ neg_table,
+                     const int32_t* __restrict__ neg_idx, const int32_t* __restrict__ node_off,
+                     const float* __restrict__ bias, float* __restrict__ out) {
+    extern __shared__ float us[];    // [n_layers * n_feat]
+    __shared__ float s_neg;
+    const int g = blockIdx.x;
+    const int nh = n_layers * n_feat;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) us[i] = u[(int64_t)g * nh + i];
+    __syncthreads();
+    const float b = bias ? __ldg(bias) : 0.f;
+    if (warp == 0) {
+        const float* nr = neg_table + (int64_t)neg_idx[g] * nh;
+        float a = 0.f;
+        for (int i = lane; i < nh; i += 32) a = fmaf(nr[i], us[i], a);
+        a = warp_sum(a);
+        if (lane == 0) s_neg = a + b;
+    }
+    __syncthreads();
+    const float sn = s_neg;
+    const int r0 = node_off[g], r1 = node_off[g + 1];
+    for (int r = r0 + warp; r < r1; r += 8) {
+        float a = 0.f;
+        for (int l = 0; l < n_layers; ++l) {
+            const float* hr = h_all + l * layer_stride + (int64_t)r * ldh;
+            const float* ul = us + l * n_feat;
+            for (int f = lane; f < n_feat; f += 32) a = fmaf(hr[f], ul[f], a);
+        }
+        a = warp_sum(a);
+        if (lane == 0) {
+            out[r] = a + b;
+            out[n_rows + r] = sn;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dgi_score_bwd_kernel(const float* __restrict__ h_all, int64_t layer_stride, int n_layers, int n_feat, int64_t ldh,
+                     int n_rows, const float* __restrict__ d_out, const float* __restrict__ neg_table,
+                     const int32_t* __restrict__ neg_idx, const int32_t* __restrict__ node_off,
+                     float* __restrict__ du, float* __restrict__ s2, double* __restrict__ d_bias) {
+    extern __shared__ float acc_s[];   // [8][nh] per-warp partial du
+    __shared__ float red[2][8];
+    const int g = blockIdx.x;
+    const int nh = n_layers * n_feat;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = node_off[g], r1 = node_off[g + 1];
+    float* mine = acc_s + warp * nh;
+    for (int i = lane; i < nh; i += 32) mine[i] = 0.f;
+    __syncwarp();
+    float sum1 = 0.f, sum2 = 0.f;
+    for (int r = r0 + warp; r < r1; r += 8) {
+        const float d1 = d_out[r];
+        if (lane == 0) { sum1 += d1; sum2 += d_out[n_rows + r]; }
+        for (int l = 0; l < n_layers; ++l) {
+            const float* hr = h_all + l * layer_stride + (int64_t)r * ldh;
+            float* ml = mine + l * n_feat;
+            for (int f = lane; f < n_feat; f += 32) ml[f] = fmaf(d1, hr[f], ml[f]);
+        }
+    }
+    sum1 = warp_sum(sum1);
+    sum2 = warp_sum(sum2);
+    if (lane == 0) { red[0][warp] = sum1; red[1][warp] = sum2; }
+    __syncthreads();
+    float t1 = 0.f, t2 = 0.f;
+    for (int w = 0; w < 8; ++w) { t1 += red[0][w]; t2 += red[1][w]; }
+    const float* nr = neg_table + (int64_t)neg_idx[g] * nh;
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) {
+        float a = 0.f;
+        for (int w = 0; w < 8; ++w) a += acc_s[w * nh + i];
+        du[(int64_t)g * nh + i] = fmaf(t2, nr[i], a);
+    }
+    if (threadIdx.x == 0) {
+        s2[g] = t2;
+        if (d_bias != nullptr) atomicAdd(d_bias, (double)t1 + (double)t2);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+rowdot_score_kernel(const float* __restrict__ h, int64_t ldh, int n_rows, int n_feat, const float* __restrict__ u,
+                    int64_t ldu, int rows_per_graph, const float* __restrict__ bias, const float* __restrict__ s_bias,
+                    float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int r = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    if (r >= n_rows) return;
+    const float* hr = h + (int64_t)r * ldh;
+    const float* ur = u + (int64_t)(r / rows_per_graph) * ldu;
+    float a = 0.f;
+    for (int f = lane; f < n_feat; f += 32) a = fmaf(hr[f], __ldg(ur + f), a);
+    a = warp_sum(a);
+    if (lane == 0) out[r] = a + (bias ? __ldg(bias) : 0.f) + (s_bias ? s_bias[r] : 0.f);
+}
+
+}  // namespace
+
+extern "C" int gnm_gather_nf_rows(const float* h_all, int64_t layer_stride, int n_layers, int n_feat, int64_t ldh,
+                                  int n_rows, float* table, gnm_stream_t stream) {
+    if (n_layers < 0 || n_feat < 0 || n_rows < 0) return GNM_ERR_BAD_ARG;
+    if (n_layers == 0 || n_feat == 0 || n_rows == 0) return GNM_OK;
+    if (!h_all || !table) return GNM_ERR_BAD_ARG;
+    const int64_t total = (int64_t)n_rows * n_layers * n_feat;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gather_nf_rows_kernel<<<(int)blocks, 256, 0, gnm_cast_stream(stream)>>>(h_all, layer_stride, n_layers, n_feat, ldh,
+                                                                            n_rows, table);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_dgi_score_fwd(const float* h_all, int64_t layer_stride, int n_layers, int n_feat, int64_t ldh,
+                                 int n_rows, const float* u, const float* neg_table, const int32_t* neg_idx,
+                                 const int32_t* node_off, int n_graphs, const float* bias, float* out,
+                                 gnm_stream_t stream) {
+    if (n_layers < 0 || n_feat < 0 || n_rows < 0 || n_graphs < 0) return GNM_ERR_BAD_ARG;
+    if (n_graphs == 0 || n_rows == 0) return GNM_OK;
+    if (!h_all || !u || !neg_table || !neg_idx || !node_off || !out) return GNM_ERR_BAD_ARG;
+    const size_t smem = (size_t)n_layers * n_feat * 4;
+    if (smem > 200 * 1024) return GNM_ERR_TOO_LARGE;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(dgi_score_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dgi_score_fwd_kernel<<<n_graphs, 256, smem, gnm_cast_stream(stream)>>>(h_all, layer_stride, n_layers, n_feat, ldh,
+                                                                           n_rows, u, neg_table, neg_idx, node_off,
+                                                                           bias, out);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_dgi_score_bwd(const float* h_all, int64_t layer_stride, int n_layers, int n_feat, int64_t ldh,
+                                 int n_rows, const float* d_out, const float* neg_table, const int32_t* neg_idx,
+                                 const int32_t* node_off, int n_graphs, float* du, float* s2, double* d_bias,
+                                 gnm_stream_t stream) {
+    if (n_layers < 0 || n_feat < 0 || n_rows < 0 || n_graphs < 0) return GNM_ERR_BAD_ARG;
+    if (n_graphs == 0 || n_rows == 0) return GNM_OK;
+    if (!h_all || !d_out || !neg_table || !neg_idx || !node_off || !du || !s2) return GNM_ERR_BAD_ARG;
+    const size_t smem = (size_t)8 * n_layers * n_feat * 4;
+    if (smem > 200 * 1024) return GNM_ERR_TOO_LARGE;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(dgi_score_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dgi_score_bwd_kernel<<<n_graphs, 256, smem, gnm_cast_stream(stream)>>>(h_all, layer_stride, n_layers, n_feat, ldh,
+                                                                           n_rows, d_out, neg_table, neg_idx, node_off,
+                                                                           du, s2, d_bias);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_rowdot_score(const float* h, int64_t ldh, int n_rows, int n_feat, const float* u, int64_t ldu,
+                                int rows_per_graph, const float* bias, const float* s_bias, float* out,
+                                gnm_stream_t stream) {
+    if (n_rows < 0 || n_feat < 0 || rows_per_graph <= 0) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0) return GNM_OK;
+    if (!h || !u || !out) return GNM_ERR_BAD_ARG;
+    const int blocks = (n_rows + 7) / 8;
+    rowdot_score_kernel<<<blocks, 256, 0, gnm_cast_stream(stream)>>>(h, ldh, n_rows, n_feat, u, ldu, rows_per_graph,
+                                                                     bias, s_bias, out);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+// ---- misc -------------------------------------------------------------------------------------
+
+extern "C" int gnm_abi_version(void) { return GNM_ABI_VERSION; }
+
+extern "C" const char* gnm_error_string(int code) {
+    switch (code) {
+        case GNM_OK: return "ok";
+        case GNM_ERR_BAD_ARG: return "gnm: bad argument";
+        case GNM_ERR_TOO_LARGE: return "gnm: problem too large for this kernel's shared-memory budget";
+        case GNM_ERR_ALIGN: return "gnm: misaligned pointer or leading dimension";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "gnm: unknown error";
+}
+
+extern "C" int gnm_set_device(int dev) { return (int)cudaSetDevice(dev); }
+
+extern "C" int gnm_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    int v = 0;
+    if (sm_count) { cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); *sm_count = v; }
+    if (cc_major) { cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev); *cc_major = v; }
+    if (cc_minor) { cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev); *cc_minor = v; }
+    if (smem_optin_bytes) { cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); *smem_optin_bytes = v; }
+    return GNM_OK;
+}

@@ -1,0 +1,491 @@
+// MLP pieces: Linear (+fused BatchNorm-apply/ReLU prologue, +fused batch-statistics epilogue),
+// weight gradient, BatchNorm statistics / finalize / backward.
+// Reference: models/mlp.py:40-49, models/graphcnn.py:162-166,185-190 (nn.Linear, nn.BatchNorm1d, ReLU).
+#include "gnm_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// y[m, n] = sum_k f(x[m, k]) * W(k, n) + bias[n]      fp32 FFMA, 128 x 64 x 16 tiles
+// ------------------------------------------------------------------------------------------
+constexpr int LBM = 128, LBN = 64, LBK = 16, LTHREADS = 256;
+
+__global__ void __launch_bounds__(LTHREADS)
+linear_kernel(const float* __restrict__ x, int64_t ldx, int n_rows, int n_in, const float* __restrict__ w,
+              int64_t ldw, int w_is_kn, const float* __restrict__ bias, const float* __restrict__ in_scale,
+              const float* __restrict__ in_shift, float* __restrict__ y, int64_t ldy, int n_out,
+              double* __restrict__ col_stats) {
+    __shared__ __align__(16) float xs[LBK][LBM + 4];
+    __shared__ __align__(16) float ws[LBK][LBN + 4];
+    __shared__ float cs[2][LBN];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads; thread tile 8 rows x 4 cols
+    const int m0 = blockIdx.x * LBM, n0 = blockIdx.y * LBN;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < n_in; k0 += LBK) {
+        // x tile: 128 rows x 16 k; thread loads k = tid & 15, rows (tid >> 4) + 16*i
+        {
+            const int kk = tid & 15;
+            const int k = k0 + kk;
+            float sc = 1.f, sh = 0.f;
+            const bool pro = in_scale != nullptr;
+            if (pro && k < n_in) { sc = in_scale[k]; sh = in_shift[k]; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int mm = (tid >> 4) + 16 * i;
+                const int m = m0 + mm;
+                float v = 0.f;
+                if (m < n_rows && k < n_in) {
+                    v = x[(int64_t)m * ldx + k];
+                    if (pro) v = fmaxf(fmaf(v, sc, sh), 0.f);
+                }
+                xs[kk][mm] = v;
+            }
+        }
+        // w tile: 16 k x 64 n
+        {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int e = tid + i * LTHREADS;    // 0..1023
+                int kk, nn;
+                if (w_is_kn) { nn = e & 63; kk = e >> 6; } else { kk = e & 15; nn = e >> 4; }
+                const int k = k0 + kk, n = n0 + nn;
+                float v = 0.f;
+                if (k < n_in && n < n_out) v = w_is_kn ? w[(int64_t)k * ldw + n] : w[(int64_t)n * ldw + k];
+                ws[kk][nn] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < LBK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&xs[kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&xs[kk][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&ws[kk][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    if (col_stats != nullptr) {
+        for (int i = tid; i < 2 * LBN; i += LTHREADS) (&cs[0][0])[i] = 0.f;
+        __syncthreads();
+    }
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        const float bv = (bias != nullptr && n < n_out) ? bias[n] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + ty * 8 + i;
+            const float v = acc[i][j] + bv;
+            acc[i][j] = v;
+            if (m < n_rows && n < n_out) { s1[j] += v; s2[j] = fmaf(v, v, s2[j]); }
+        }
+    }
+    const bool vec_ok = (ldy % 4 == 0) && gnm_aligned16(y) && (n0 + tx * 4 + 3 < n_out);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
+        if (m >= n_rows) continue;
+        float* yr = y + (int64_t)m * ldy + n0 + tx * 4;
+        if (vec_ok) {
+            *reinterpret_cast<float4*>(yr) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n0 + tx * 4 + j < n_out) yr[j] = acc[i][j];
+        }
+    }
+    if (col_stats != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&cs[0][tx * 4 + j], s1[j]);
+            atomicAdd(&cs[1][tx * 4 + j], s2[j]);
+        }
+        __syncthreads();
+        if (tid < 2 * LBN) {
+            const int which = tid / LBN, c = tid % LBN;
+            const int n = n0 + c;
+            if (n < n_out) atomicAdd(&col_stats[which * n_out + n], (double)cs[which][c]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// dw[o, i] += sum_m dz[m, o] * f(x[m, i]);  dbias[o] += sum_m dz[m, o]
+// 64 x 64 output tile per CTA, rows split over blockIdx.z slabs, fp32 atomics to merge slabs.
+// ------------------------------------------------------------------------------------------
+constexpr int WBO = 64, WBI = 64, WBR = 16;
+
+__global__ void __launch_bounds__(256)
+linear_wgrad_kernel(const float* __restrict__ dz, int64_t lddz, const float* __restrict__ x, int64_t ldx, int n_rows,
+                    int n_out, int n_in, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
+                    float* __restrict__ dw, int64_t lddw, float* __restrict__ dbias, int rows_per_slab) {
+    __shared__ __align__(16) float zs[WBR][WBO + 4];
+    __shared__ __align__(16) float xs[WBR][WBI + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;     // thread tile: o = ty*4.., i = tx*4..
+    const int o0 = blockIdx.x * WBO, i0 = blockIdx.y * WBI;
+    const int r0 = blockIdx.z * rows_per_slab, r1 = min(n_rows, r0 + rows_per_slab);
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    float bsum = 0.f;   // threads 0..63 accumulate dbias for column o0 + tid (only blockIdx.y == 0)
+    const bool pro = in_scale != nullptr;
+    for (int rb = r0; rb < r1; rb += WBR) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int e = tid + t * 256;       // 0..1023 = 16 rows x 64 cols
+            const int rr = e >> 6, c = e & 63;
+            const int r = rb + rr;
+            float vz = 0.f, vx = 0.f;
+            if (r < r1) {
+                if (o0 + c < n_out) vz = dz[(int64_t)r * lddz + o0 + c];
+                if (i0 + c < n_in) {
+                    vx = x[(int64_t)r * ldx + i0 + c];
+                    if (pro) vx = fmaxf(fmaf(vx, in_scale[i0 + c], in_shift[i0 + c]), 0.f);
+                }
+            }
+            zs[rr][c] = vz;
+            xs[rr][c] = vx;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < WBR; ++rr) {
+            const float4 a = *reinterpret_cast<const float4*>(&zs[rr][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&xs[rr][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
+        }
+        if (dbias != nullptr && blockIdx.y == 0 && tid < WBO) {
+#pragma unroll
+            for (int rr = 0; rr < WBR; ++rr) bsum += zs[rr][tid];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int o = o0 + ty * 4 + p;
+        if (o >= n_out) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + tx * 4 + q;
+            if (i < n_in) atomicAdd(&dw[(int64_t)o * lddw + i], acc[p][q]);
+        }
+    }
+    if (dbias != nullptr && blockIdx.y == 0 && tid < WBO && o0 + tid < n_out) atomicAdd(&dbias[o0 + tid], bsum);
+}
+
+// ------------------------------------------------------------------------------------------
+// column statistics
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+col_stats_kernel(const float* __restrict__ x, int64_t ldx, int n_rows, int n_feat, double* __restrict__ col_stats,
+                 int rows_per_cta) {
+    // thread -> column (tid % cw), row lane (tid / cw); cw = min(n_feat chunk, 256)
+    const int f0 = blockIdx.y * 256;
+    const int cw = min(256, n_feat - f0);
+    const int rl = 256 / cw;
+    const int c = threadIdx.x % cw, rr = threadIdx.x / cw;
+    __shared__ float sh1[256], sh2[256];
+    float s1 = 0.f, s2 = 0.f;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(n_rows, r0 + rows_per_cta);
+    if (rr < rl) {
+        for (int r = r0 + rr; r < r1; r += rl) {
+            const float v = x[(int64_t)r * ldx + f0 + c];
+            s1 += v;
+            s2 = fmaf(v, v, s2);
+        }
+    }
+    sh1[threadIdx.x] = s1;
+    sh2[threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.x < cw) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < rl; ++k) { a += (double)sh1[k * cw + threadIdx.x]; b += (double)sh2[k * cw + threadIdx.x]; }
+        atomicAdd(&col_stats[f0 + threadIdx.x], a);
+        atomicAdd(&col_stats[n_feat + f0 + threadIdx.x], b);
+    }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ col_stats, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   int64_t* __restrict__ nbt, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_o, float* __restrict__ rstd_o, int n_feat) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nbt != nullptr) *nbt += 1;
+    if (c >= n_feat) return;
+    const double mean = col_stats[c] / count;
+    double var = col_stats[n_feat + c] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    const float sc = g * rstd;
+    scale[c] = sc;
+    shift[c] = b - (float)mean * sc;
+    mean_o[c] = (float)mean;
+    rstd_o[c] = rstd;
+    if (running_mean != nullptr) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    if (running_var != nullptr) {
+        const double unb = count > 1.0 ? var * (count / (count - 1.0)) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+}
+
+__global__ void bn_eval_affine_kernel(const float* __restrict__ rm, const float* __restrict__ rv,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                      float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
+                                      float* __restrict__ rstd_o, int n_feat) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_feat) return;
+    const float rstd = 1.f / sqrtf(rv[c] + eps);
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    const float sc = g * rstd;
+    scale[c] = sc;
+    shift[c] = b - rm[c] * sc;
+    mean_o[c] = rm[c];
+    rstd_o[c] = rstd;
+}
+
+// ------------------------------------------------------------------------------------------
+// h = relu(z*scale + shift); pooled[g] = pool_scale[g] * sum_rows h        (one CTA per graph x column chunk)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_relu_readout_kernel(const float* __restrict__ z, int64_t ldz, int n_feat, const float* __restrict__ scale,
+                       const float* __restrict__ shift, float* __restrict__ h, int64_t ldh,
+                       const int32_t* __restrict__ node_off, const float* __restrict__ pool_scale,
+                       float* __restrict__ pooled, int64_t ld_pooled) {
+    const int g = blockIdx.x;
+    const int f0 = blockIdx.y * 256;
+    const int cw = min(256, n_feat - f0);
+    const int rl = 256 / cw;
+    const int c = threadIdx.x % cw, rr = threadIdx.x / cw;
+    __shared__ float red[256];
+    const int r0 = node_off[g], r1 = node_off[g + 1];
+    float s = 0.f;
+    if (rr < rl) {
+        const float sc = scale[f0 + c], sh = shift[f0 + c];
+        for (int r = r0 + rr; r < r1; r += rl) {
+            const float v = fmaxf(fmaf(z[(int64_t)r * ldz + f0 + c], sc, sh), 0.f);
+            if (h != nullptr) h[(int64_t)r * ldh + f0 + c] = v;
+            s += v;
+        }
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (pooled != nullptr && threadIdx.x < cw) {
+        float t = 0.f;
+        for (int k = 0; k < rl; ++k) t += red[k * cw + threadIdx.x];
+        if (pool_scale != nullptr) t *= pool_scale[g];
+        pooled[(int64_t)g * ld_pooled + f0 + threadIdx.x] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward of relu(bn(z)), pass 1: assemble the incoming gradient, mask, reduce
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+relu_bn_bwd_reduce_kernel(const float* __restrict__ z, int64_t ldz, int n_feat, const float* __restrict__ scale,
+                          const float* __restrict__ shift, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, const float* __restrict__ d_out, int64_t ld_dout,
+                          const float* __restrict__ d_pooled, int64_t ld_dpooled, const float* __restrict__ pool_scale,
+                          const float* __restrict__ d_score, const float* __restrict__ u, int64_t ldu,
+                          const float* __restrict__ d_neg, int64_t ld_dneg, int n_neg,
+                          const int32_t* __restrict__ node_off, float* __restrict__ dy, int64_t lddy,
+                          double* __restrict__ stats) {
+    const int g = blockIdx.x;
+    const int f0 = blockIdx.y * 256;
+    const int cw = min(256, n_feat - f0);
+    const int rl = 256 / cw;
+    const int c = threadIdx.x % cw, rr = threadIdx.x / cw;
+    __shared__ float sh1[256], sh2[256];
+    const int r0 = node_off[g], r1 = node_off[g + 1];
+    float s1 = 0.f, s2 = 0.f;
+    if (rr < rl) {
+        const int f = f0 + c;
+        const float sc = scale[f], sh = shift[f], mu = mean[f], rs = rstd[f];
+        float gp = 0.f, uu = 0.f;
+        if (d_pooled != nullptr) gp = d_pooled[(int64_t)g * ld_dpooled + f] * (pool_scale ? pool_scale[g] : 1.f);
+        if (d_score != nullptr) uu = u[(int64_t)g * ldu + f];
+        for (int r = r0 + rr; r < r1; r += rl) {
+            const float zv = z[(int64_t)r * ldz + f];
+            float gr = gp;
+            if (d_out != nullptr) gr += d_out[(int64_t)r * ld_dout + f];
+            if (d_score != nullptr) gr = fmaf(d_score[r], uu, gr);
+            if (d_neg != nullptr && r < n_neg) gr += d_neg[(int64_t)r * ld_dneg + f];
+            const float v = (fmaf(zv, sc, sh) > 0.f) ? gr : 0.f;
+            dy[(int64_t)r * lddy + f] = v;
+            s1 += v;
+            s2 = fmaf(v, (zv - mu) * rs, s2);
+        }
+    }
+    sh1[threadIdx.x] = s1;
+    sh2[threadIdx.x] = s2;
+    __syncthreads();
+    if (stats != nullptr && threadIdx.x < cw) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < rl; ++k) { a += (double)sh1[k * cw + threadIdx.x]; b += (double)sh2[k * cw + threadIdx.x]; }
+        atomicAdd(&stats[f0 + threadIdx.x], a);
+        atomicAdd(&stats[n_feat + f0 + threadIdx.x], b);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ z, int64_t ldz, int n_rows, int n_feat, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ gamma, const double* __restrict__ stats,
+                    double count, float* __restrict__ dy, int64_t lddy) {
+    const int64_t total = (int64_t)n_rows * n_feat;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / n_feat), f = (int)(i % n_feat);
+        const float gsc = (gamma ? gamma[f] : 1.f) * rstd[f];
+        float v = dy[(int64_t)r * lddy + f];
+        if (stats != nullptr) {
+            const float m1 = (float)(stats[f] / count), m2 = (float)(stats[n_feat + f] / count);
+            const float xh = (z[(int64_t)r * ldz + f] - mean[f]) * rstd[f];
+            v = v - m1 - xh * m2;
+        }
+        dy[(int64_t)r * lddy + f] = v * gsc;
+    }
+}
+
+}  // namespace
+
+extern "C" int gnm_linear(const float* x, int64_t ldx, int n_rows, int n_in, const float* w, int64_t ldw, int w_is_kn,
+                          const float* bias, const float* in_scale, const float* in_shift, float* y, int64_t ldy,
+                          int n_out, double* col_stats, gnm_stream_t stream) {
+    if (n_rows < 0 || n_in < 0 || n_out < 0) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0 || n_out == 0) return GNM_OK;
+    if (!x || !w || !y) return GNM_ERR_BAD_ARG;
+    if ((in_scale == nullptr) != (in_shift == nullptr)) return GNM_ERR_BAD_ARG;
+    dim3 grid((n_rows + LBM - 1) / LBM, (n_out + LBN - 1) / LBN);
+    linear_kernel<<<grid, LTHREADS, 0, gnm_cast_stream(stream)>>>(x, ldx, n_rows, n_in, w, ldw, w_is_kn, bias, in_scale,
+                                                                  in_shift, y, ldy, n_out, col_stats);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_linear_wgrad(const float* dz, int64_t lddz, const float* x, int64_t ldx, int n_rows, int n_out,
+                                int n_in, const float* in_scale, const float* in_shift, float* dw, int64_t lddw,
+                                float* dbias, gnm_stream_t stream) {
+    if (n_rows < 0 || n_in < 0 || n_out < 0) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0 || n_out == 0) return GNM_OK;
+    if (!dz || (n_in > 0 && (!x || !dw))) return GNM_ERR_BAD_ARG;
+    if ((in_scale == nullptr) != (in_shift == nullptr)) return GNM_ERR_BAD_ARG;
+    const int to = (n_out + WBO - 1) / WBO, ti = n_in > 0 ? (n_in + WBI - 1) / WBI : 1;
+    int slabs = (148 * 4) / (to * ti);
+    if (slabs < 1) slabs = 1;
+    int rows_per_slab = (n_rows + slabs - 1) / slabs;
+    rows_per_slab = ((rows_per_slab + WBR - 1) / WBR) * WBR;
+    if (rows_per_slab < 256) rows_per_slab = 256;
+    slabs = (n_rows + rows_per_slab - 1) / rows_per_slab;
+    dim3 grid(to, ti, slabs);
+    linear_wgrad_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(dz, lddz, x, ldx, n_rows, n_out, n_in, in_scale,
+                                                                   in_shift, dw, lddw, dbias, rows_per_slab);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_col_stats(const float* x, int64_t ldx, int n_rows, int n_feat, double* col_stats,
+                             gnm_stream_t stream) {
+    if (n_rows < 0 || n_feat < 0) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0 || n_feat == 0) return GNM_OK;
+    if (!x || !col_stats) return GNM_ERR_BAD_ARG;
+    const int fparts = (n_feat + 255) / 256;
+    int ctas = 148 * 4;
+    int rows_per_cta = (n_rows + ctas - 1) / ctas;
+    if (rows_per_cta < 32) rows_per_cta = 32;
+    ctas = (n_rows + rows_per_cta - 1) / rows_per_cta;
+    dim3 grid(ctas, fparts);
+    col_stats_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(x, ldx, n_rows, n_feat, col_stats, rows_per_cta);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_bn_finalize(const double* col_stats, double count, const float* gamma, const float* beta, float eps,
+                               float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                               float* scale, float* shift, float* mean, float* rstd, int n_feat, gnm_stream_t stream) {
+    if (n_feat < 0 || count <= 0.0) return GNM_ERR_BAD_ARG;
+    if (n_feat == 0) return GNM_OK;
+    if (!col_stats || !scale || !shift || !mean || !rstd) return GNM_ERR_BAD_ARG;
+    bn_finalize_kernel<<<(n_feat + 127) / 128, 128, 0, gnm_cast_stream(stream)>>>(
+        col_stats, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, scale, shift, mean,
+        rstd, n_feat);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma,
+                                  const float* beta, float eps, float* scale, float* shift, float* mean, float* rstd,
+                                  int n_feat, gnm_stream_t stream) {
+    if (n_feat < 0) return GNM_ERR_BAD_ARG;
+    if (n_feat == 0) return GNM_OK;
+    if (!running_mean || !running_var || !scale || !shift || !mean || !rstd) return GNM_ERR_BAD_ARG;
+    bn_eval_affine_kernel<<<(n_feat + 127) / 128, 128, 0, gnm_cast_stream(stream)>>>(
+        running_mean, running_var, gamma, beta, eps, scale, shift, mean, rstd, n_feat);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_bn_relu_readout(const float* z, int64_t ldz, int n_rows, int n_feat, const float* scale,
+                                   const float* shift, float* h, int64_t ldh, const int32_t* node_off, int n_graphs,
+                                   const float* pool_scale, float* pooled, int64_t ld_pooled, gnm_stream_t stream) {
+    if (n_rows < 0 || n_feat < 0 || n_graphs < 0) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0 || n_feat == 0 || n_graphs == 0) return GNM_OK;
+    if (!z || !scale || !shift || !node_off) return GNM_ERR_BAD_ARG;
+    dim3 grid(n_graphs, (n_feat + 255) / 256);
+    bn_relu_readout_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(z, ldz, n_feat, scale, shift, h, ldh, node_off,
+                                                                      pool_scale, pooled, ld_pooled);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_relu_bn_bwd_reduce(const float* z, int64_t ldz, int n_rows, int n_feat, const float* scale,
+                                      const float* shift, const float* mean, const float* rstd, const float* d_out,
+                                      int64_t ld_dout, const float* d_pooled, int64_t ld_dpooled,
+                                      const float* pool_scale, const float* d_score, const float* u, int64_t ldu,
+                                      const float* d_neg, int64_t ld_dneg, int n_neg, const int32_t* node_off,
+                                      int n_graphs, float* dy, int64_t lddy, double* stats, gnm_stream_t stream) {
+    if (n_rows < 0 || n_feat < 0 || n_graphs < 0) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0 || n_feat == 0 || n_graphs == 0) return GNM_OK;
+    if (!z || !scale || !shift || !mean || !rstd || !node_off || !dy) return GNM_ERR_BAD_ARG;
+    if (d_score != nullptr && u == nullptr) return GNM_ERR_BAD_ARG;
+    dim3 grid(n_graphs, (n_feat + 255) / 256);
+    relu_bn_bwd_reduce_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(
+        z, ldz, n_feat, scale, shift, mean, rstd, d_out, ld_dout, d_pooled, ld_dpooled, pool_scale, d_score, u, ldu,
+        d_neg, ld_dneg, n_neg, node_off, dy, lddy, stats);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_bn_bwd_apply(const float* z, int64_t ldz, int n_rows, int n_feat, const float* mean,
+                                const float* rstd, const float* gamma, const double* stats, double count, float* dy,
+                                int64_t lddy, gnm_stream_t stream) {
+    if (n_rows < 0 || n_feat < 0) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0 || n_feat == 0) return GNM_OK;
+    if (!rstd || !dy || (stats != nullptr && (!z || !mean || count <= 0.0))) return GNM_ERR_BAD_ARG;
+    const int64_t total = (int64_t)n_rows * n_feat;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    bn_bwd_apply_kernel<<<(int)blocks, 256, 0, gnm_cast_stream(stream)>>>(z, ldz, n_rows, n_feat, mean, rstd, gamma,
+                                                                          stats, count, dy, lddy);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}

@@ -1,0 +1,480 @@
+"""Host-side orchestration of the GIN + DGI hot path over the libgnm kernels.
+
+What lives here (all of it replaces per-step Python/ATen work of the reference's
+`GIN_InfoMaxReg.forward` / `compute_saliency`, models/graphcnn.py:194-299):
+
+* `GraphStore`     - device-resident per-graph CSR cache (built once per `S2VGraph` by
+                     `gnm_csr_build`), so a batch is assembled by offset arithmetic on the
+                     device instead of re-running graphcnn.py:84-134 and shipping the sparse
+                     index tensors H2D every step.
+* `BatchStructure` - the block-diagonal CSR (`Adj_block`), node offsets (`graph_pool`) and
+                     one-hot tags of one batch.
+* `GINFunction`    - one `torch.autograd.Function` for the whole encoder + DGI scorer:
+                     forward and a hand-derived backward, every M-sized tensor op is a
+                     libgnm kernel. Only [B, L*F]-sized glue (sigmoid, u = c W^T, the
+                     prediction heads) is left to torch.
+
+The kernels are reached through `ops` (ctypes over the C ABI). There is no CPU path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops as _ops
+from . import dist as _dist
+
+
+def require_cuda(dev):
+    if dev.type != "cuda":
+        raise RuntimeError("GIN_InfoMaxReg runs on the libgnm CUDA kernels only (no CPU fallback): "
+                           "call .to('cuda') first")
+
+
+# ------------------------------------------------------------------------------------------
+# graph store / batch structure
+# ------------------------------------------------------------------------------------------
+
+class _StoredGraph(object):
+    __slots__ = ("graph", "n", "nnz", "rp_addr", "ci_addr", "tag_addr", "onehot", "feat_dim", "keep")
+
+
+def _onehot_tags(feats, cache):
+    """Return int32 tags if `feats` ([N, D] float) is exactly one-hot per row, else None."""
+    key = (feats.data_ptr(), tuple(feats.shape), feats._version)
+    if key in cache:
+        return cache[key]
+    tags = None
+    if feats.dim() == 2 and feats.shape[1] > 0:
+        f = feats.detach()
+        if bool(((f == 0) | (f == 1)).all()) and bool((f.sum(1) == 1).all()):
+            tags = f.argmax(1).to(torch.int32)
+    cache[key] = tags
+    return tags
+
+
+class GraphStore(object):
+    """Device cache of per-graph local CSRs, keyed on the identity of the caller's graph
+    objects (the caller owns them and reuses them every step, main.py:26-28)."""
+
+    def __init__(self, device, add_self_loops):
+        self.device = device
+        self.add_self_loops = bool(add_self_loops)
+        self.entries = {}
+        self._tag_cache = {}
+        self.h2d_bytes = 0          # bytes shipped host->device by the last ensure()/assemble()
+
+    def clear(self):
+        self.entries.clear()
+        self._tag_cache.clear()
+
+    def __len__(self):
+        return len(self.entries)
+
+    def ensure(self, graphs):
+        new = []
+        seen = set()
+        for g in graphs:
+            k = id(g)
+            if k not in self.entries and k not in seen:
+                seen.add(k)
+                new.append(g)
+        if not new:
+            return
+        dev = self.device
+        counts = [len(g.g) for g in new]
+        ems = []
+        for g, n in zip(new, counts):
+            em = g.edge_mat
+            if not torch.is_tensor(em):                 # an edgeless graph keeps util.py:17's `0`
+                em = torch.zeros(2, 0, dtype=torch.int64)
+            ems.append(em.reshape(2, -1).to(torch.int64))
+        edge_counts = [int(e.shape[1]) for e in ems]
+        edges = torch.cat(ems, 1).contiguous() if ems else torch.zeros(2, 0, dtype=torch.int64)
+        edge_off = np.zeros(len(new) + 1, dtype=np.int64)
+        np.cumsum(edge_counts, out=edge_off[1:])
+        node_off = np.zeros(len(new) + 1, dtype=np.int64)
+        np.cumsum(counts, out=node_off[1:])
+        total_nodes = int(node_off[-1])
+        edges_d = edges.to(dev, non_blocking=True)
+        edge_off_d = torch.from_numpy(edge_off).to(dev)
+        node_off_d = torch.from_numpy(node_off.astype(np.int32)).to(dev)
+        self.h2d_bytes += edges.numel() * 8 + edge_off.nbytes + node_off.nbytes // 2
+        rowptr, colidx, status = _ops.csr_build(edges_d, edge_off_d, node_off_d, len(new), max(counts), total_nodes,
+                                                self.add_self_loops, True)
+        if int(status.item()) != 0:
+            raise IndexError("edge_mat holds a node index outside [0, len(graph.g))")
+        # one-hot tags of the node features (util.py:114-116), concatenated for the chunk
+        tag_list, onehot = [], []
+        for g in new:
+            t = _onehot_tags(g.node_features, self._tag_cache)
+            onehot.append(t is not None)
+            tag_list.append(t if t is not None else torch.zeros(len(g.g), dtype=torch.int32))
+        tags_d = torch.cat(tag_list).to(dev) if total_nodes > 0 else torch.zeros(0, dtype=torch.int32, device=dev)
+        self.h2d_bytes += total_nodes * 4
+        keep = (rowptr, colidx, tags_d)
+        rp0, ci0, tg0 = rowptr.data_ptr(), colidx.data_ptr(), tags_d.data_ptr()
+        for i, g in enumerate(new):
+            e = _StoredGraph()
+            e.graph = g                                  # pins the id
+            e.n = counts[i]
+            e.nnz = edge_counts[i] + (counts[i] if self.add_self_loops else 0)
+            nnz_base = int(edge_off[i]) + (int(node_off[i]) if self.add_self_loops else 0)
+            e.rp_addr = rp0 + 4 * int(node_off[i])
+            e.ci_addr = ci0 + 4 * nnz_base
+            e.tag_addr = tg0 + 4 * int(node_off[i])
+            e.onehot = onehot[i]
+            e.feat_dim = int(g.node_features.shape[1])
+            e.keep = keep
+            self.entries[id(g)] = e
+
+    def assemble(self, graphs):
+        self.ensure(graphs)
+        ent = [self.entries[id(g)] for g in graphs]
+        b = len(ent)
+        counts = np.fromiter((e.n for e in ent), dtype=np.int64, count=b)
+        nnzs = np.fromiter((e.nnz for e in ent), dtype=np.int64, count=b)
+        packed = np.empty(4 * b + 1, dtype=np.int64)
+        packed[0:b] = [e.rp_addr for e in ent]
+        packed[b:2 * b] = [e.ci_addr for e in ent]
+        packed[2 * b:3 * b] = [e.tag_addr for e in ent]
+        packed[3 * b] = 0
+        np.cumsum(nnzs, out=packed[3 * b + 1:4 * b + 1])
+        node_off = np.zeros(b + 1, dtype=np.int32)
+        np.cumsum(counts, out=node_off[1:])
+        m, nnz = int(node_off[-1]), int(packed[4 * b])
+        if nnz >= 2 ** 31:
+            raise RuntimeError("batch adjacency has %d entries; int32 CSR holds < 2^31" % nnz)
+        dev = self.device
+        packed_d = torch.from_numpy(packed).to(dev, non_blocking=True)
+        node_off_d = torch.from_numpy(node_off).to(dev, non_blocking=True)
+        self.h2d_bytes += packed.nbytes + node_off.nbytes
+        rowptr, colidx, tags = _ops.csr_batch_gather(packed_d[0:b], packed_d[b:2 * b], packed_d[2 * b:3 * b],
+                                                     node_off_d, packed_d[3 * b:4 * b + 1], b, m, nnz)
+        bs = BatchStructure()
+        bs.n_graphs, bs.n_rows, bs.nnz = b, m, nnz
+        bs.node_counts = counts
+        bs.node_off = node_off_d
+        bs.rowptr, bs.colidx = rowptr, colidx
+        bs.uniform_n = int(counts[0]) if b > 0 and bool((counts == counts[0]).all()) else None
+        bs.onehot = all(e.onehot for e in ent)
+        bs.tags = tags if bs.onehot else None
+        bs.feat_dim = ent[0].feat_dim if b > 0 else 0
+        return bs
+
+
+class BatchStructure(object):
+    """Adj_block (graphcnn.py:84-106) as int32 CSR + graph_pool (graphcnn.py:109-134) as node offsets."""
+
+    __slots__ = ("n_graphs", "n_rows", "nnz", "node_counts", "node_off", "rowptr", "colidx", "uniform_n", "onehot",
+                 "tags", "feat_dim", "pool_scale")
+
+    def set_pooling(self, graph_pooling_type, device):
+        if graph_pooling_type == "average":
+            self.pool_scale = torch.from_numpy((1.0 / self.node_counts).astype(np.float32)).to(device)
+        else:
+            self.pool_scale = None
+
+
+# ------------------------------------------------------------------------------------------
+# parameter plumbing
+# ------------------------------------------------------------------------------------------
+
+def layer_units(model, layer):
+    """The (Linear, BatchNorm1d) pairs of one GIN layer: mlp.py:27-38 + graphcnn.py:51."""
+    mlp = model.mlps[layer]
+    if mlp.linear_or_not:
+        return [(mlp.linear, model.batch_norms[layer])]
+    k = mlp.num_layers
+    units = [(mlp.linears[j], mlp.batch_norms[j]) for j in range(k - 1)]
+    units.append((mlp.linears[k - 1], model.batch_norms[layer]))
+    return units
+
+
+def flat_params(model):
+    ps = [model.eps, model.disc.f_k.weight, model.disc.f_k.bias]
+    for layer in range(model.num_layers):
+        for lin, bn in layer_units(model, layer):
+            ps.extend([lin.weight, lin.bias, bn.weight, bn.bias])
+    return ps
+
+
+class _Unit(object):
+    """Saved forward state of one Linear->BatchNorm->ReLU unit."""
+    __slots__ = ("w", "b", "gamma", "beta", "bn", "z", "scale", "shift", "mean", "rstd", "x_in", "count")
+
+
+class _Saved(object):
+    pass
+
+
+# ------------------------------------------------------------------------------------------
+# forward / backward
+# ------------------------------------------------------------------------------------------
+
+def _bn_affine(unit, stats, count, training, comm):
+    dev = unit.z.device
+    f = unit.z.shape[1]
+    buf = torch.empty(4, f, dtype=torch.float32, device=dev)
+    unit.scale, unit.shift, unit.mean, unit.rstd = buf[0], buf[1], buf[2], buf[3]
+    bn = unit.bn
+    use_batch = training or not bn.track_running_stats
+    if use_batch:
+        if comm.world > 1:
+            comm.all_reduce_sum(stats)
+        unit.count = float(count * comm.world)
+        track = bn.track_running_stats and training
+        if track and bn.momentum is None:
+            raise NotImplementedError("BatchNorm1d(momentum=None) is not used by the reference")
+        _ops.bn_finalize(stats, unit.count, unit.gamma, unit.beta, bn.eps, bn.momentum if track else 0.0,
+                         bn.running_mean if track else None, bn.running_var if track else None,
+                         bn.num_batches_tracked if track else None, unit.scale, unit.shift, unit.mean, unit.rstd)
+    else:
+        unit.count = 0.0
+        _ops.bn_eval_affine(bn.running_mean, bn.running_var, unit.gamma, unit.beta, bn.eps, unit.scale, unit.shift,
+                            unit.mean, unit.rstd)
+    return use_batch
+
+
+def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm):
+    """graphcnn.py:194-251 (and :254-294 when with_dgi is False). Returns (g_f, d_logit, saved)."""
+    dev = params[0].device
+    L, F = model.num_layers, model.hidden_dim
+    M, B = bs.n_rows, bs.n_graphs
+    learn_eps = model.learn_eps
+    average = model.neighbor_pooling_type == "average"
+    eps_p, disc_w, disc_b = params[0], params[1], params[2]
+    it = iter(params[3:])
+    sv = _Saved()
+    sv.layers = []
+    sv.bs = bs
+    sv.training = training
+    sv.with_dgi = with_dgi
+    sv.x_dense = x_dense
+    h_all = torch.empty(L, M, F, dtype=torch.float32, device=dev)
+    g_f = torch.empty(B, L * F, dtype=torch.float32, device=dev)
+    sv.h_all = h_all
+    use_gather0 = x_dense is None
+    if use_gather0 and not bs.onehot:
+        raise RuntimeError("internal: gather path needs one-hot node features")
+    sv.use_gather0 = use_gather0
+    sv.batch_stats = []
+    for layer in range(L):
+        units = []
+        for lin, bn in layer_units(model, layer):
+            u = _Unit()
+            u.w, u.b, u.gamma, u.beta = next(it), next(it), next(it), next(it)
+            u.bn = bn
+            units.append(u)
+        eps_l = eps_p[layer:layer + 1] if learn_eps else None
+        h_prev = h_all[layer - 1] if layer > 0 else None
+        pooled = None
+        for j, u in enumerate(units):
+            n_out = u.w.shape[0]
+            u.z = torch.empty(M, n_out, dtype=torch.float32, device=dev)
+            stats = torch.zeros(2 * n_out, dtype=torch.float64, device=dev)
+            if j == 0:
+                if layer == 0 and use_gather0:
+                    # first layer as a row gather of W1^T (X_concat is one-hot): no dense X, no GEMM
+                    w1t = u.w.detach().t().contiguous()
+                    sv.w1t = w1t
+                    _ops.aggregate(bs.rowptr, bs.colidx, w1t, bs.tags, u.z, 1 if average else 0, eps_l, u.b)
+                    _ops.col_stats(u.z, stats)
+                    u.x_in = None
+                else:
+                    src = x_dense if layer == 0 else h_prev
+                    pooled = torch.empty(M, src.shape[1], dtype=torch.float32, device=dev)
+                    _ops.aggregate(bs.rowptr, bs.colidx, src, None, pooled, 1 if average else 0, eps_l, None)
+                    _ops.linear(pooled, u.w, False, u.b, None, None, u.z, stats)
+                    u.x_in = pooled
+            else:
+                p = units[j - 1]
+                _ops.linear(p.z, u.w, False, u.b, p.scale, p.shift, u.z, stats)
+                u.x_in = None          # recomputed from p.z with p's affine + ReLU
+            _bn_affine(u, stats, M, training, comm)
+        last = units[-1]
+        _ops.bn_relu_readout(last.z, last.scale, last.shift, h_all[layer], bs.node_off, B, bs.pool_scale,
+                             g_f[:, layer * F:(layer + 1) * F])
+        sv.layers.append(units)
+    d_logit = None
+    if with_dgi:
+        # discriminator.py:19-38 refactored: sc = <h, u_g> + b with u_g = W c_g (c = sigmoid(g_f), graphcnn.py:238-239)
+        c = torch.sigmoid(g_f)
+        u_mat = c @ disc_w[0].t()
+        b_neg = neg_idx.shape[0]
+        if comm.world > 1:
+            # the negatives only ever read global rows [0, B_global) of n_f: rank 0 owns them
+            neg_table = _ops.gather_nf_rows(h_all, b_neg) if comm.rank == 0 else \
+                torch.empty(b_neg, L * F, dtype=torch.float32, device=dev)
+            comm.broadcast(neg_table, 0)
+            my_neg = neg_idx[comm.rank * B:(comm.rank + 1) * B].contiguous()
+        else:
+            neg_table = _ops.gather_nf_rows(h_all, b_neg)
+            my_neg = neg_idx
+        d_logit = torch.empty(2 * M, 1, dtype=torch.float32, device=dev)
+        _ops.dgi_score_fwd(h_all, u_mat, neg_table, my_neg, bs.node_off, B, disc_b, d_logit)
+        sv.c, sv.u_mat, sv.neg_table, sv.my_neg, sv.neg_idx = c, u_mat, neg_table, my_neg, neg_idx
+    sv.g_f = g_f
+    return g_f, d_logit, sv
+
+
+def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
+    """Hand-derived backward of `run_forward`. Returns (dX or None, [grad per flat param])."""
+    bs = sv.bs
+    dev = params[0].device
+    L = model.num_layers
+    M, B = bs.n_rows, bs.n_graphs
+    F = sv.h_all.shape[2]
+    learn_eps = model.learn_eps
+    average = model.neighbor_pooling_type == "average"
+    bwd_mode = 2 if average else 0
+    eps_p, disc_w, disc_b = params[0], params[1], params[2]
+    grads = [None] * len(params)
+    d_eps = torch.zeros(L, dtype=torch.float64, device=dev) if learn_eps else None
+
+    d_pooled = dg_f
+    d_score = u_mat = d_neg = None
+    n_neg = 0
+    if sv.with_dgi and dd_logit is not None:
+        dd = dd_logit.contiguous().view(-1)
+        du = torch.empty(B, L * F, dtype=torch.float32, device=dev)
+        s2 = torch.empty(B, dtype=torch.float32, device=dev)
+        d_bias = torch.zeros(1, dtype=torch.float64, device=dev)
+        _ops.dgi_score_bwd(sv.h_all, dd, sv.neg_table, sv.my_neg, bs.node_off, B, du, s2, d_bias)
+        # [B, L*F]-sized glue: u = c W^T, c = sigmoid(g_f)
+        grads[1] = (du.t() @ sv.c).unsqueeze(0)
+        grads[2] = d_bias.to(torch.float32)
+        dc = du @ disc_w[0]
+        dgs = dc * sv.c * (1.0 - sv.c)
+        d_pooled = dgs if d_pooled is None else d_pooled + dgs
+        n_neg = sv.neg_idx.shape[0]
+        d_neg = torch.zeros(n_neg, L * F, dtype=torch.float32, device=dev)
+        d_neg.index_add_(0, sv.my_neg.long(), s2.unsqueeze(1) * sv.u_mat)
+        if comm.world > 1:
+            comm.reduce_sum(d_neg, 0)
+            if comm.rank != 0:
+                d_neg, n_neg = None, 0
+        d_score = dd[:M]
+        u_mat = sv.u_mat
+    if d_pooled is None:
+        d_pooled = torch.zeros(B, L * F, dtype=torch.float32, device=dev)
+    d_pooled = d_pooled.contiguous()
+
+    d_h = None        # gradient reaching h_all[layer] from layer+1's aggregation
+    d_x = None
+    pidx = 3 + 4 * sum(len(u) for u in sv.layers)
+    for layer in range(L - 1, -1, -1):
+        units = sv.layers[layer]
+        pidx -= 4 * len(units)
+        sl = slice(layer * F, (layer + 1) * F)
+        eps_l = eps_p[layer:layer + 1] if learn_eps else None
+        h_prev = sv.h_all[layer - 1] if layer > 0 else None
+        dz = None
+        for j in range(len(units) - 1, -1, -1):
+            u = units[j]
+            n_out = u.w.shape[0]
+            dy = torch.empty(M, n_out, dtype=torch.float32, device=dev)
+            stats = torch.zeros(2 * n_out, dtype=torch.float64, device=dev)
+            if j == len(units) - 1:
+                _ops.relu_bn_bwd_reduce(u.z, u.scale, u.shift, u.mean, u.rstd, d_h, d_pooled[:, sl], bs.pool_scale,
+                                        d_score, u_mat[:, sl] if u_mat is not None else None,
+                                        d_neg[:, sl] if d_neg is not None else None, n_neg, bs.node_off, B, dy, stats)
+            else:
+                _ops.relu_bn_bwd_reduce(u.z, u.scale, u.shift, u.mean, u.rstd, dz, None, None, None, None, None, 0,
+                                        bs.node_off, B, dy, stats)
+            use_batch = u.count > 0.0
+            if use_batch and comm.world > 1:
+                comm.all_reduce_sum(stats)
+            gi = pidx + 4 * j
+            grads[gi + 3] = stats[:n_out].to(torch.float32)          # d beta  = sum dy
+            grads[gi + 2] = stats[n_out:].to(torch.float32)          # d gamma = sum dy * xhat
+            _ops.bn_bwd_apply(u.z, u.mean, u.rstd, u.gamma, stats if use_batch else None, u.count, dy)
+            dz_u = dy                                                # now d loss / d z_j
+            dw = torch.zeros_like(u.w)
+            db = torch.zeros_like(u.b)
+            if j > 0:
+                p = units[j - 1]
+                _ops.linear_wgrad(dz_u, p.z, p.scale, p.shift, dw, db)
+                dz = torch.empty(M, u.w.shape[1], dtype=torch.float32, device=dev)
+                _ops.linear(dz_u, u.w, True, None, None, None, dz, None)      # d a_{j-1} = dz_j @ W_j
+                grads[gi], grads[gi + 1] = dw, db
+                continue
+            # ---- first unit of the layer: input is the neighbour aggregation --------------------
+            if layer == 0 and sv.use_gather0:
+                # z0 = Agg(W1^T[tags]) + b:  dW1^T[t] = sum_{tags[r]=t} (Agg^T dz)[r]
+                g_agg = torch.empty(M, n_out, dtype=torch.float32, device=dev)
+                _ops.aggregate(bs.rowptr, bs.colidx, dz_u, None, g_agg, bwd_mode, eps_l, None)
+                dw1t = torch.zeros(u.w.shape[1], n_out, dtype=torch.float32, device=dev)
+                _ops.scatter_rows_add(g_agg, bs.tags, dw1t)
+                dw = dw1t.t().contiguous()
+                _ops.linear_wgrad(dz_u, None, None, None, None, db)
+                if learn_eps:
+                    _ops.dot_rows(dz_u, sv.w1t, bs.tags, d_eps[layer:layer + 1])
+                if need_x_grad:
+                    d_x = torch.empty(M, u.w.shape[1], dtype=torch.float32, device=dev)
+                    _ops.linear(g_agg, u.w, True, None, None, None, d_x, None)   # (Agg^T dz) @ W1
+            else:
+                _ops.linear_wgrad(dz_u, u.x_in, None, None, dw, db)
+                need_dp = layer > 0 or need_x_grad or learn_eps
+                if need_dp:
+                    src = sv.x_dense if layer == 0 else h_prev
+                    dp = torch.empty(M, u.w.shape[1], dtype=torch.float32, device=dev)
+                    _ops.linear(dz_u, u.w, True, None, None, None, dp, None)
+                    if learn_eps:
+                        _ops.dot_rows(dp, src, None, d_eps[layer:layer + 1])
+                    if layer > 0 or need_x_grad:
+                        d_prev = torch.empty(M, u.w.shape[1], dtype=torch.float32, device=dev)
+                        _ops.aggregate(bs.rowptr, bs.colidx, dp, None, d_prev, bwd_mode, eps_l, None)
+                        if layer > 0:
+                            d_h = d_prev
+                        else:
+                            d_x = d_prev
+            grads[gi], grads[gi + 1] = dw, db
+    if learn_eps:
+        grads[0] = d_eps.to(torch.float32)
+    return d_x, grads
+
+
+class GINFunction(torch.autograd.Function):
+    """(g_f, d_logit) = GIN encoder + DGI scorer; see run_forward / run_backward."""
+
+    @staticmethod
+    def forward(ctx, runner, x_dense, *params):
+        g_f, d_logit, sv = run_forward(runner.model, runner.bs, runner.neg_idx, runner.training, runner.with_dgi,
+                                       x_dense.detach() if x_dense is not None else None,
+                                       [p.detach() for p in params], runner.comm)
+        ctx.runner = runner
+        ctx.sv = sv
+        ctx.params = params
+        ctx.need_x = x_dense is not None and x_dense.requires_grad
+        if d_logit is None:
+            d_logit = torch.zeros(0, 1, dtype=torch.float32, device=g_f.device)
+        return g_f, d_logit
+
+    @staticmethod
+    def backward(ctx, dg_f, dd_logit):
+        runner, sv = ctx.runner, ctx.sv
+        if not sv.with_dgi:
+            dd_logit = None
+        need_x = ctx.need_x or runner.want_x_grad
+        d_x, grads = run_backward(runner.model, sv, [p.detach() for p in ctx.params], dg_f, dd_logit, need_x,
+                                  runner.comm)
+        runner.x_grad = d_x
+        out = []
+        for p, g in zip(ctx.params, grads):
+            out.append(g if (g is not None and p.requires_grad) else None)
+        return (None, d_x if ctx.need_x else None) + tuple(out)
+
+
+class Runner(object):
+    """Per-call context handed to GINFunction (non-tensor state)."""
+
+    def __init__(self, model, bs, neg_idx, training, with_dgi, comm, want_x_grad=False):
+        self.model = model
+        self.bs = bs
+        self.neg_idx = neg_idx
+        self.training = training
+        self.with_dgi = with_dgi
+        self.comm = comm
+        self.want_x_grad = want_x_grad
+        self.x_grad = None

@@ -1,0 +1,139 @@
+"""`GIN_InfoMaxReg` with the reference's constructor, `forward` / `compute_saliency`
+signatures and state_dict layout (reference: models/graphcnn.py:12-299), executed by the
+libgnm sm_100a kernels through `engine.GINFunction`.
+
+What stays in Python here is exactly what the reference driver relies on:
+  * one `np.random.permutation(len(batch_graph))` draw per forward (graphcnn.py:199),
+  * the `(c_logit, d_logit)` / `latent=True` return contract (graphcnn.py:248-251),
+  * `compute_saliency`'s side effects (`eval()`, `zero_grad()`, parameter `.grad`s).
+The prediction heads (`linears_prediction` + dropout on [B, F] rows, graphcnn.py:230) are
+[B, 2]-sized and stay in torch so the dropout mask comes from the same torch RNG stream as
+the reference's.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .mlp import MLP
+from .discriminator import Discriminator
+from .. import dist as _dist
+from .. import engine as _engine
+
+
+class GIN_InfoMaxReg(nn.Module):
+    def __init__(self, num_layers, num_mlp_layers, input_dim, hidden_dim, output_dim, final_dropout, learn_eps,
+                 graph_pooling_type, neighbor_pooling_type, device):
+        super().__init__()
+        # module creation order follows graphcnn.py:29-52 so torch.manual_seed(s) + constructor
+        # yields the reference's initial weights
+        self.disc = Discriminator(hidden_dim * num_layers)
+        self.sigm = nn.Sigmoid()
+        self.relu = nn.ReLU()
+
+        self.final_dropout = final_dropout
+        self.device = device
+        self.num_layers = num_layers
+        self.hidden_dim = hidden_dim
+        self.graph_pooling_type = graph_pooling_type
+        self.neighbor_pooling_type = neighbor_pooling_type
+        self.learn_eps = learn_eps
+        self.eps = nn.Parameter(torch.zeros(num_layers))
+
+        self.mlps = nn.ModuleList()
+        self.batch_norms = nn.ModuleList()
+        self.linears_prediction = nn.ModuleList()
+        for layer in range(num_layers):
+            self.mlps.append(MLP(num_mlp_layers, input_dim if layer == 0 else hidden_dim, hidden_dim, hidden_dim))
+            self.batch_norms.append(nn.BatchNorm1d(hidden_dim))
+            self.linears_prediction.append(nn.Linear(hidden_dim, output_dim))
+
+        self._store = None
+        self._comm = _dist.SINGLE
+        self.cache_graphs = True        # keep per-graph CSRs resident on the device between calls
+
+    # ---- data-parallel hook (new; the reference is single-process) -------------------------
+    def set_comm(self, comm):
+        """Engage data parallelism: `forward` then expects THIS rank's contiguous shard of the
+        global batch and synchronises BatchNorm statistics and the DGI negatives over `comm`."""
+        self._comm = comm if comm is not None else _dist.SINGLE
+
+    # ---- internals --------------------------------------------------------------------------
+    def _graph_store(self):
+        dev = self.eps.device
+        _engine.require_cuda(dev)
+        if self._store is None or self._store.device != dev or self._store.add_self_loops != (not self.learn_eps):
+            self._store = _engine.GraphStore(dev, add_self_loops=not self.learn_eps)
+        return self._store
+
+    def _structure(self, batch_graph):
+        if self.neighbor_pooling_type == "max":
+            raise NotImplementedError("neighbor_pooling_type='max' (graphcnn.py:55-81,137-143) is not on the "
+                                      "B200 hot path yet; use 'sum' or 'average'")
+        if self.neighbor_pooling_type not in ("sum", "average"):
+            raise ValueError("unknown neighbor_pooling_type %r" % (self.neighbor_pooling_type,))
+        store = self._graph_store()
+        if not self.cache_graphs:
+            store.clear()
+        bs = store.assemble(batch_graph)
+        bs.set_pooling(self.graph_pooling_type, self.eps.device)
+        return bs
+
+    def _dense_features(self, batch_graph, bs):
+        if bs.onehot:
+            return None                 # layer 0 runs as a row gather of W1^T
+        return torch.cat([g.node_features for g in batch_graph], 0).to(self.eps.device, torch.float32)
+
+    def _heads(self, g_f):
+        """graphcnn.py:228-231: sum over layers of dropout(Linear(pooled_h))."""
+        f = self.hidden_dim
+        score = 0
+        for layer in range(self.num_layers):
+            pooled_h = g_f[:, layer * f:(layer + 1) * f]
+            score = score + F.dropout(self.linears_prediction[layer](pooled_h), self.final_dropout,
+                                      training=self.training)
+        return score
+
+    # ---- reference API ------------------------------------------------------------------------
+    def forward(self, batch_graph, latent=False):
+        comm = self._comm
+        n_global = len(batch_graph) * comm.world
+        rand_seq = np.random.permutation(n_global)          # graphcnn.py:199 (one numpy draw per call)
+        bs = self._structure(batch_graph)
+        if bs.uniform_n is None:
+            # the reference's own DGI path needs equal-sized graphs (idx of graphcnn.py:198-201 and
+            # the expand of discriminator.py:23-26 both assume M == B * N)
+            raise RuntimeError("GIN_InfoMaxReg.forward needs graphs with the same number of nodes")
+        neg_idx = torch.from_numpy(rand_seq.astype(np.int32)).to(self.eps.device)
+        runner = _engine.Runner(self, bs, neg_idx, self.training, True, comm)
+        x = self._dense_features(batch_graph, bs)
+        g_f, d_logit = _engine.GINFunction.apply(runner, x, *_engine.flat_params(self))
+        c_logit = self._heads(g_f)
+        if latent:
+            return g_f.detach().cpu().numpy()
+        return c_logit, d_logit
+
+    def compute_saliency(self, batch_graph, cls):
+        assert len(batch_graph) == 1
+        return self.compute_saliency_batched(batch_graph, cls)
+
+    def compute_saliency_batched(self, batch_graph, cls):
+        """Gradient of the class-`cls` score wrt the (one-hot) input for a whole batch at once.
+        Exact in eval mode: BatchNorm uses running statistics and Adj_block is block-diagonal,
+        so each graph's rows equal its own `compute_saliency` result (graphcnn.py:254-299)."""
+        self.eval()
+        self.zero_grad()
+        bs = self._structure(batch_graph)
+        runner = _engine.Runner(self, bs, None, False, False, _dist.SINGLE, want_x_grad=True)
+        x = self._dense_features(batch_graph, bs)
+        if x is not None:
+            x.requires_grad_()
+        g_f, _ = _engine.GINFunction.apply(runner, x, *_engine.flat_params(self))
+        score_over_layer = self._heads(g_f)
+        predicting_class = torch.zeros([len(batch_graph), 2], device=g_f.device)     # graphcnn.py:263-264
+        predicting_class[:, cls] = 1
+        score_over_layer.backward(predicting_class)
+        return runner.x_grad if x is None else x.grad
+
+
+GraphCNN = GIN_InfoMaxReg      # the name BASELINE.json's north_star uses for this class

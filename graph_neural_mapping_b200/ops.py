@@ -1,0 +1,240 @@
+"""Thin tensor-level wrappers over the C ABI (include/gnm.h).
+
+Every function takes CUDA torch tensors (PyTorch is used for device memory and streams
+only), extracts raw pointers / leading dimensions, enqueues the kernel on torch's current
+stream and raises `RuntimeError` on a non-zero return code. There is no CPU path: a CPU
+tensor is rejected.
+"""
+import ctypes
+
+import torch
+
+from . import lib as _libmod
+
+_state = {"device": None}
+
+
+def _lib():
+    return _libmod.load()
+
+
+def _stream(t):
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if _state["device"] != dev:
+        _libmod.check(_lib().gnm_set_device(dev), "gnm_set_device")
+        _state["device"] = dev
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("libgnm ops need CUDA tensors (there is no CPU fallback); got a %s tensor" % t.device)
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("expected dtype %s, got %s" % (dtype, t.dtype))
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _mat(t):
+    """(pointer, leading dimension) of a 2-D fp32 tensor whose rows are contiguous."""
+    if t is None:
+        return None, 0
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise RuntimeError("expected a row-major 2-D tensor, got shape %s strides %s" % (tuple(t.shape), t.stride()))
+    return _ptr(t, torch.float32), int(t.stride(0))
+
+
+def device_info():
+    sm, ma, mi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    smem = ctypes.c_int64()
+    _libmod.check(_lib().gnm_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(smem)),
+                  "gnm_device_info")
+    return dict(sm_count=sm.value, cc=(ma.value, mi.value), smem_optin=smem.value)
+
+
+# ---- structure ---------------------------------------------------------------------------
+
+def csr_build(edges, edge_off, node_off, n_graphs, n_max, total_nodes, add_self_loops, local_cols):
+    """edges int64 [2, E] (local ids), edge_off int64 [B+1], node_off int32 [B+1] -> rowptr, colidx, status."""
+    e_total = int(edges.shape[1])
+    edges = edges.contiguous()
+    nnz = e_total + (total_nodes if add_self_loops else 0)
+    if nnz >= 2 ** 31:
+        raise RuntimeError("batch adjacency has %d entries; int32 CSR holds < 2^31" % nnz)
+    dev = edges.device
+    rowptr = torch.empty(total_nodes + 1, dtype=torch.int32, device=dev)
+    colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    _libmod.check(_lib().gnm_csr_build(_ptr(edges, torch.int64), e_total, _ptr(edge_off, torch.int64),
+                                       _ptr(node_off, torch.int32), n_graphs, n_max, int(add_self_loops),
+                                       int(local_cols), _ptr(rowptr), _ptr(colidx), _ptr(status), _stream(edges)),
+                  "gnm_csr_build")
+    return rowptr, colidx[:nnz], status
+
+
+def csr_batch_gather(rp_addr, ci_addr, tag_addr, node_off, nnz_off, n_graphs, total_nodes, total_nnz):
+    dev = node_off.device
+    rowptr = torch.empty(total_nodes + 1, dtype=torch.int32, device=dev)
+    colidx = torch.empty(max(total_nnz, 1), dtype=torch.int32, device=dev)
+    tags = torch.empty(total_nodes, dtype=torch.int32, device=dev) if tag_addr is not None else None
+    _libmod.check(_lib().gnm_csr_batch_gather(_ptr(rp_addr, torch.int64), _ptr(ci_addr, torch.int64),
+                                              _ptr(tag_addr, torch.int64) if tag_addr is not None else None,
+                                              _ptr(node_off, torch.int32), _ptr(nnz_off, torch.int64), n_graphs,
+                                              _ptr(rowptr), _ptr(colidx), _ptr(tags), _stream(node_off)),
+                  "gnm_csr_batch_gather")
+    return rowptr, colidx[:total_nnz], tags
+
+
+# ---- aggregation -------------------------------------------------------------------------
+
+def aggregate(rowptr, colidx, src, src_map, dst, mode, eps, bias=None):
+    sp, lds = _mat(src)
+    dp, ldd = _mat(dst)
+    _libmod.check(_lib().gnm_aggregate(_ptr(rowptr, torch.int32), _ptr(colidx, torch.int32), int(dst.shape[0]),
+                                       sp, lds, _ptr(src_map, torch.int32) if src_map is not None else None,
+                                       dp, ldd, int(dst.shape[1]), int(mode), _ptr(eps, torch.float32),
+                                       _ptr(bias, torch.float32), _stream(dst)), "gnm_aggregate")
+    return dst
+
+
+def dot_rows(a, b, b_map, out):
+    ap, lda = _mat(a)
+    bp, ldb = _mat(b)
+    _libmod.check(_lib().gnm_dot_rows(ap, lda, bp, ldb, _ptr(b_map, torch.int32) if b_map is not None else None,
+                                      int(a.shape[0]), int(a.shape[1]), _ptr(out, torch.float64), _stream(a)),
+                  "gnm_dot_rows")
+    return out
+
+
+def scatter_rows_add(g, tags, table_grad):
+    gp, ldg = _mat(g)
+    tp, ldt = _mat(table_grad)
+    _libmod.check(_lib().gnm_scatter_rows_add(gp, ldg, _ptr(tags, torch.int32), int(g.shape[0]), int(g.shape[1]),
+                                              tp, ldt, int(table_grad.shape[0]), _stream(g)), "gnm_scatter_rows_add")
+    return table_grad
+
+
+# ---- MLP -----------------------------------------------------------------------------------
+
+def linear(x, w, w_is_kn, bias, in_scale, in_shift, y, col_stats):
+    xp, ldx = _mat(x)
+    wp, ldw = _mat(w)
+    yp, ldy = _mat(y)
+    n_in = int(x.shape[1])
+    n_out = int(y.shape[1])
+    exp = (n_in, n_out) if w_is_kn else (n_out, n_in)
+    if tuple(w.shape) != exp:
+        raise RuntimeError("linear: weight shape %s does not match x %s -> y %s" % (tuple(w.shape), tuple(x.shape), tuple(y.shape)))
+    _libmod.check(_lib().gnm_linear(xp, ldx, int(x.shape[0]), n_in, wp, ldw, int(w_is_kn), _ptr(bias, torch.float32),
+                                    _ptr(in_scale, torch.float32), _ptr(in_shift, torch.float32), yp, ldy, n_out,
+                                    _ptr(col_stats, torch.float64), _stream(y)), "gnm_linear")
+    return y
+
+
+def linear_wgrad(dz, x, in_scale, in_shift, dw, dbias):
+    zp, ldz = _mat(dz)
+    xp, ldx = _mat(x)
+    wp, ldw = _mat(dw)
+    n_in = int(x.shape[1]) if x is not None else 0
+    _libmod.check(_lib().gnm_linear_wgrad(zp, ldz, xp, ldx, int(dz.shape[0]), int(dz.shape[1]), n_in,
+                                          _ptr(in_scale, torch.float32), _ptr(in_shift, torch.float32), wp, ldw,
+                                          _ptr(dbias, torch.float32), _stream(dz)), "gnm_linear_wgrad")
+
+
+def col_stats(x, stats):
+    xp, ldx = _mat(x)
+    _libmod.check(_lib().gnm_col_stats(xp, ldx, int(x.shape[0]), int(x.shape[1]), _ptr(stats, torch.float64),
+                                       _stream(x)), "gnm_col_stats")
+    return stats
+
+
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, nbt, scale, shift, mean, rstd):
+    _libmod.check(_lib().gnm_bn_finalize(_ptr(stats, torch.float64), float(count), _ptr(gamma, torch.float32),
+                                         _ptr(beta, torch.float32), float(eps), float(momentum),
+                                         _ptr(running_mean, torch.float32), _ptr(running_var, torch.float32),
+                                         _ptr(nbt, torch.int64), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd),
+                                         int(scale.shape[0]), _stream(scale)), "gnm_bn_finalize")
+
+
+def bn_eval_affine(running_mean, running_var, gamma, beta, eps, scale, shift, mean, rstd):
+    _libmod.check(_lib().gnm_bn_eval_affine(_ptr(running_mean, torch.float32), _ptr(running_var, torch.float32),
+                                            _ptr(gamma, torch.float32), _ptr(beta, torch.float32), float(eps),
+                                            _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), int(scale.shape[0]),
+                                            _stream(scale)), "gnm_bn_eval_affine")
+
+
+def bn_relu_readout(z, scale, shift, h, node_off, n_graphs, pool_scale, pooled):
+    zp, ldz = _mat(z)
+    hp, ldh = _mat(h)
+    pp, ldp = _mat(pooled)
+    _libmod.check(_lib().gnm_bn_relu_readout(zp, ldz, int(z.shape[0]), int(z.shape[1]), _ptr(scale), _ptr(shift),
+                                             hp, ldh, _ptr(node_off, torch.int32), n_graphs,
+                                             _ptr(pool_scale, torch.float32), pp, ldp, _stream(z)),
+                  "gnm_bn_relu_readout")
+
+
+def relu_bn_bwd_reduce(z, scale, shift, mean, rstd, d_out, d_pooled, pool_scale, d_score, u, d_neg, n_neg,
+                       node_off, n_graphs, dy, stats):
+    zp, ldz = _mat(z)
+    op, ldo = _mat(d_out)
+    gp, ldg = _mat(d_pooled)
+    up, ldu = _mat(u)
+    np_, ldn = _mat(d_neg)
+    yp, ldy = _mat(dy)
+    _libmod.check(_lib().gnm_relu_bn_bwd_reduce(zp, ldz, int(z.shape[0]), int(z.shape[1]), _ptr(scale), _ptr(shift),
+                                                _ptr(mean), _ptr(rstd), op, ldo, gp, ldg,
+                                                _ptr(pool_scale, torch.float32), _ptr(d_score, torch.float32), up, ldu,
+                                                np_, ldn, int(n_neg), _ptr(node_off, torch.int32), n_graphs, yp, ldy,
+                                                _ptr(stats, torch.float64), _stream(z)), "gnm_relu_bn_bwd_reduce")
+
+
+def bn_bwd_apply(z, mean, rstd, gamma, stats, count, dy):
+    zp, ldz = _mat(z)
+    yp, ldy = _mat(dy)
+    _libmod.check(_lib().gnm_bn_bwd_apply(zp, ldz, int(dy.shape[0]), int(dy.shape[1]), _ptr(mean), _ptr(rstd),
+                                          _ptr(gamma, torch.float32), _ptr(stats, torch.float64), float(count), yp, ldy,
+                                          _stream(dy)), "gnm_bn_bwd_apply")
+
+
+# ---- DGI -----------------------------------------------------------------------------------
+
+def _hall(h_all):
+    if h_all.dim() != 3 or h_all.stride(2) != 1:
+        raise RuntimeError("h_all must be [L, M, F] with contiguous rows")
+    return _ptr(h_all, torch.float32), int(h_all.stride(0)), int(h_all.shape[0]), int(h_all.shape[2]), int(h_all.stride(1))
+
+
+def gather_nf_rows(h_all, n_rows):
+    hp, ls, nl, nf, ldh = _hall(h_all)
+    table = torch.empty(n_rows, nl * nf, dtype=torch.float32, device=h_all.device)
+    _libmod.check(_lib().gnm_gather_nf_rows(hp, ls, nl, nf, ldh, n_rows, _ptr(table), _stream(h_all)),
+                  "gnm_gather_nf_rows")
+    return table
+
+
+def dgi_score_fwd(h_all, u, neg_table, neg_idx, node_off, n_graphs, bias, out):
+    hp, ls, nl, nf, ldh = _hall(h_all)
+    _libmod.check(_lib().gnm_dgi_score_fwd(hp, ls, nl, nf, ldh, int(h_all.shape[1]), _ptr(u.contiguous(), torch.float32),
+                                           _ptr(neg_table, torch.float32), _ptr(neg_idx, torch.int32),
+                                           _ptr(node_off, torch.int32), n_graphs, _ptr(bias, torch.float32),
+                                           _ptr(out, torch.float32), _stream(out)), "gnm_dgi_score_fwd")
+    return out
+
+
+def dgi_score_bwd(h_all, d_out, neg_table, neg_idx, node_off, n_graphs, du, s2, d_bias):
+    hp, ls, nl, nf, ldh = _hall(h_all)
+    _libmod.check(_lib().gnm_dgi_score_bwd(hp, ls, nl, nf, ldh, int(h_all.shape[1]), _ptr(d_out, torch.float32),
+                                           _ptr(neg_table, torch.float32), _ptr(neg_idx, torch.int32),
+                                           _ptr(node_off, torch.int32), n_graphs, _ptr(du, torch.float32),
+                                           _ptr(s2, torch.float32), _ptr(d_bias, torch.float64), _stream(du)),
+                  "gnm_dgi_score_bwd")
+
+
+def rowdot_score(h, u, rows_per_graph, bias, s_bias, out):
+    hp, ldh = _mat(h)
+    up, ldu = _mat(u)
+    _libmod.check(_lib().gnm_rowdot_score(hp, ldh, int(h.shape[0]), int(h.shape[1]), up, ldu, int(rows_per_graph),
+                                          _ptr(bias, torch.float32), _ptr(s_bias, torch.float32),
+                                          _ptr(out, torch.float32), _stream(out)), "gnm_rowdot_score")
+    return out

@@ -1,0 +1,194 @@
+/*
+ * gnm.h - C ABI of libgnm.so: the B200 (sm_100a) kernels behind graph-neural-mapping's GIN
+ * message-passing hot path (GIN_InfoMaxReg forward/backward + DGI Discriminator).
+ *
+ * The reference has no FFI of its own: every FLOP of this path is a PyTorch ATen call made
+ * from /root/reference/models/{graphcnn,mlp,discriminator}.py. Each entry point below names
+ * the reference lines (file:line under /root/reference) whose arithmetic it replaces; the
+ * Python classes in graph_neural_mapping_b200/models/ keep the reference's constructor and
+ * forward signatures and call these through ctypes.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked host;
+ *   - no hidden allocation, no internal synchronisation, no global state: work is enqueued
+ *     on `stream` (a cudaStream_t passed as void*, e.g. torch.cuda.current_stream().cuda_stream)
+ *     and the call returns immediately;
+ *   - return 0 on success, a negative GNM_ERR_* for rejected arguments, or a positive
+ *     cudaError_t if the launch failed. Never throws, never falls back to the CPU;
+ *   - matrices are fp32 row-major with an explicit leading dimension in ELEMENTS;
+ *   - "nullable" pointers may be NULL to disable the corresponding fused step.
+ */
+#ifndef GNM_H_
+#define GNM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNM_OK 0
+#define GNM_ERR_BAD_ARG (-1)
+#define GNM_ERR_TOO_LARGE (-2)
+#define GNM_ERR_ALIGN (-3)
+
+#define GNM_ABI_VERSION 3
+
+typedef void* gnm_stream_t;
+
+int gnm_abi_version(void);
+const char* gnm_error_string(int code);
+/* Bind this library's CUDA runtime to device `dev` (one process per GPU). */
+int gnm_set_device(int dev);
+int gnm_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes);
+
+/* ---- adjacency / readout structure ------------------------------------------------------ */
+
+/* graphcnn.py:84-106 (__preprocess_neighbors_sumavepool) + the coalesce that torch.spmm performs
+ * (graphcnn.py:154,178): block-diagonal CSR of a batch of B graphs from their edge lists.
+ *   edges      int64 [2][E_total]: row 0 sources, row 1 destinations, LOCAL node ids, graph after
+ *              graph (torch.cat(edge_mat_list, 1) without the start_idx shift);
+ *   edge_off   int64 [B+1] prefix of per-graph edge counts; node_off int32 [B+1] prefix of node counts;
+ *   add_self_loops = !learn_eps (graphcnn.py:97-102);
+ *   local_cols != 0 keeps column ids local to each graph (graph-store form), else global row ids;
+ *   n_max      largest node count in the batch (sizes the shared-memory histogram).
+ * Output: rowptr int32 [M+1], colidx int32 [E_total + (add_self_loops ? M : 0)], row-major sorted,
+ * duplicates kept (a duplicated edge counts twice, like the summed COO). For duplicate-free input it is
+ * bit-identical to Adj_block.coalesce().to_sparse_csr().{crow,col}_indices().
+ * status int32 [1]: bit 0 is set if any edge index was outside [0, N_g). */
+int gnm_csr_build(const int64_t* edges, int64_t e_total, const int64_t* edge_off, const int32_t* node_off,
+                  int n_graphs, int n_max, int add_self_loops, int local_cols,
+                  int32_t* rowptr, int32_t* colidx, int32_t* status, gnm_stream_t stream);
+
+/* Batch assembly from the device-resident graph store (replaces re-running graphcnn.py:84-106 and the
+ * H2D copy of Adj_block every step): slot b copies the stored local CSR of one graph, shifting row
+ * pointers by nnz_off[b] and column ids by node_off[b].
+ *   src_rowptr_addr / src_colidx_addr / src_tag_addr: int64 [B] device ADDRESSES of each graph's stored
+ *   int32 rowptr (N+1 entries), colidx and (nullable) one-hot tag array. */
+int gnm_csr_batch_gather(const int64_t* src_rowptr_addr, const int64_t* src_colidx_addr, const int64_t* src_tag_addr,
+                         const int32_t* node_off, const int64_t* nnz_off, int n_graphs,
+                         int32_t* rowptr, int32_t* colidx, int32_t* tags, gnm_stream_t stream);
+
+/* ---- neighbour aggregation -------------------------------------------------------------- */
+
+/* graphcnn.py:154-161 / :178-182: dst[i] = sum_{j in row i} src[map(j)] (/deg(i) for average)
+ *                                          + (1 + *eps) * src[map(i)] when eps != NULL.
+ * Also its backward (Adj_block is symmetric): mode 2 scales each gathered row by 1/deg(j), which is
+ * the transpose of the average. src_map (nullable int32 [M]) redirects row r to src[src_map[r]]: with
+ * src = W1^T and src_map = one-hot tags this is the first GIN layer as a row gather (graphcnn.py:195 +
+ * mlp.py:48: X_concat is one-hot, so spmm(Adj, X) @ W1^T == gather-sum of W1^T rows).
+ * mode: 0 sum, 1 average (0/0 = NaN for an isolated node, as the reference), 2 transpose-of-average.
+ * bias (nullable [n_feat]) is added to every output row (the Linear bias of the layer-0 gather path). */
+int gnm_aggregate(const int32_t* rowptr, const int32_t* colidx, int n_rows,
+                  const float* src, int64_t ld_src, const int32_t* src_map,
+                  float* dst, int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
+                  gnm_stream_t stream);
+
+/* d eps[layer] = sum_i <a[i], b[map(i)]> (autograd of graphcnn.py:161). out: double[1], accumulated. */
+int gnm_dot_rows(const float* a, int64_t lda, const float* b, int64_t ldb, const int32_t* b_map,
+                 int n_rows, int n_feat, double* out, gnm_stream_t stream);
+
+/* dW1^T[tag[r], :] += g[r, :] : gradient of the gathered table (layer-0 one-hot path). */
+int gnm_scatter_rows_add(const float* g, int64_t ldg, const int32_t* tags, int n_rows, int n_feat,
+                         float* table_grad, int64_t ldt, int n_table_rows, gnm_stream_t stream);
+
+/* ---- MLP: Linear + BatchNorm + ReLU ------------------------------------------------------ */
+
+/* mlp.py:48-49 / nn.Linear: y[m, n] = sum_k f(x[m, k]) * W(k, n) + bias[n], with
+ * W(k, n) = w[n*ldw + k] (w_is_kn == 0, nn.Linear layout [out, in]) or w[k*ldw + n] (w_is_kn == 1,
+ * used for dX = dY @ W). f is the fused BatchNorm-apply + ReLU of the PREVIOUS op:
+ * f(x) = max(0, x*in_scale[k] + in_shift[k]) when in_scale != NULL (mlp.py:48, graphcnn.py:163-166).
+ * col_stats (nullable double [2*n_out], +=): per-column sum and sum of squares of y, the BatchNorm batch
+ * statistics of the NEXT op (mlp.py:48, graphcnn.py:163). */
+int gnm_linear(const float* x, int64_t ldx, int n_rows, int n_in,
+               const float* w, int64_t ldw, int w_is_kn, const float* bias,
+               const float* in_scale, const float* in_shift,
+               float* y, int64_t ldy, int n_out, double* col_stats, gnm_stream_t stream);
+
+/* Weight gradient: dw[o, i] += sum_m dz[m, o] * f(x[m, i]); dbias[o] += sum_m dz[m, o] (nullable).
+ * f as in gnm_linear (recompute of the BatchNorm+ReLU activation instead of storing it). */
+int gnm_linear_wgrad(const float* dz, int64_t lddz, const float* x, int64_t ldx, int n_rows, int n_out, int n_in,
+                     const float* in_scale, const float* in_shift,
+                     float* dw, int64_t lddw, float* dbias, gnm_stream_t stream);
+
+/* Per-column sum / sum of squares (double [2F], +=) of a [M, F] matrix. */
+int gnm_col_stats(const float* x, int64_t ldx, int n_rows, int n_feat, double* col_stats, gnm_stream_t stream);
+
+/* nn.BatchNorm1d training statistics -> per-channel affine (mlp.py:38,48; graphcnn.py:51,163,187):
+ * mean = sum/count, var = sumsq/count - mean^2 (biased), rstd = 1/sqrt(var + eps);
+ * scale = gamma*rstd, shift = beta - mean*scale; running stats updated with momentum (unbiased variance,
+ * count/(count-1)) and *num_batches_tracked += 1 when those pointers are non-NULL.
+ * `count` is the GLOBAL row count (all ranks) - the caller all-reduces col_stats first. */
+int gnm_bn_finalize(const double* col_stats, double count, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var,
+                    int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* rstd,
+                    int n_feat, gnm_stream_t stream);
+
+/* Eval-mode BatchNorm (running statistics) as the same per-channel affine. */
+int gnm_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                       float eps, float* scale, float* shift, float* mean, float* rstd, int n_feat,
+                       gnm_stream_t stream);
+
+/* graphcnn.py:163-166 + :229: h = relu(z*scale + shift) written to h (nullable) and summed per graph into
+ * pooled[g, :] = pool_scale[g] * sum_{rows of g} h  (graph_pool SpMM, graphcnn.py:109-134,229;
+ * pool_scale NULL = sum pooling). pooled is OVERWRITTEN ([B, ld_pooled], already offset to the layer slice). */
+int gnm_bn_relu_readout(const float* z, int64_t ldz, int n_rows, int n_feat, const float* scale, const float* shift,
+                        float* h, int64_t ldh, const int32_t* node_off, int n_graphs, const float* pool_scale,
+                        float* pooled, int64_t ld_pooled, gnm_stream_t stream);
+
+/* Backward of relu(batchnorm(z)), pass 1. Assembles the gradient reaching h from up to four sources,
+ *   d_out[r, :]                       (nullable; gradient from the next layer's aggregation)
+ * + pool_scale[g] * d_pooled[g, :]    (nullable; readout/heads + DGI summary, graphcnn.py:229-239)
+ * + d_score[r] * u[g, :]              (nullable; positive DGI score, discriminator.py:28)
+ * + d_neg[r, :] for r < n_neg         (nullable; rows used as DGI negatives, graphcnn.py:241-242)
+ * masks it with the ReLU (z*scale+shift > 0), writes dy, and accumulates
+ * stats[0:F] += sum dy, stats[F:2F] += sum dy * xhat, xhat = (z - mean)*rstd  (double). */
+int gnm_relu_bn_bwd_reduce(const float* z, int64_t ldz, int n_rows, int n_feat,
+                           const float* scale, const float* shift, const float* mean, const float* rstd,
+                           const float* d_out, int64_t ld_dout,
+                           const float* d_pooled, int64_t ld_dpooled, const float* pool_scale,
+                           const float* d_score, const float* u, int64_t ldu,
+                           const float* d_neg, int64_t ld_dneg, int n_neg,
+                           const int32_t* node_off, int n_graphs,
+                           float* dy, int64_t lddy, double* stats, gnm_stream_t stream);
+
+/* Backward of batchnorm, pass 2 (in place on dy):
+ * training: dz = gamma*rstd*(dy - stats_sum/count - xhat*stats_dot/count); eval (stats == NULL): dz = dy*gamma*rstd. */
+int gnm_bn_bwd_apply(const float* z, int64_t ldz, int n_rows, int n_feat, const float* mean, const float* rstd,
+                     const float* gamma, const double* stats, double count, float* dy, int64_t lddy,
+                     gnm_stream_t stream);
+
+/* ---- DGI discriminator ------------------------------------------------------------------- */
+
+/* Copy rows [0, n_rows) of n_f = cat(hidden_rep, 1) (graphcnn.py:233) into a dense [n_rows, L*F] table:
+ * the only rows the "shuffled" negatives ever read (graphcnn.py:198-201,241-242). */
+int gnm_gather_nf_rows(const float* h_all, int64_t layer_stride, int n_layers, int n_feat, int64_t ldh,
+                       int n_rows, float* table, gnm_stream_t stream);
+
+/* discriminator.py:19-38 with f_k = nn.Bilinear(n_h, n_h, 1) refactored as sc = <h, u_g> + b, u_g = W c_g:
+ *   out[r]     = <n_f[r], u[g(r)]> + *bias                    (sc_1, positives)
+ *   out[M + r] = <neg_table[neg_idx[g(r)]], u[g(r)]> + *bias  (sc_2: one row per graph, broadcast)
+ * h_all holds the L hidden representations as [L][M, ldh]; n_f[r] is their concatenation. */
+int gnm_dgi_score_fwd(const float* h_all, int64_t layer_stride, int n_layers, int n_feat, int64_t ldh, int n_rows,
+                      const float* u, const float* neg_table, const int32_t* neg_idx,
+                      const int32_t* node_off, int n_graphs, const float* bias, float* out, gnm_stream_t stream);
+
+/* Backward of the scores wrt u, bias and the negative rows:
+ *   s2[g]   = sum_{r in g} d_out[M + r]
+ *   du[g]   = sum_{r in g} d_out[r] * n_f[r] + s2[g] * neg_table[neg_idx[g]]
+ *   d_bias += sum d_out  (double[1])
+ * (the gradient wrt n_f itself is fused into gnm_relu_bn_bwd_reduce via d_score/u/d_neg). */
+int gnm_dgi_score_bwd(const float* h_all, int64_t layer_stride, int n_layers, int n_feat, int64_t ldh, int n_rows,
+                      const float* d_out, const float* neg_table, const int32_t* neg_idx,
+                      const int32_t* node_off, int n_graphs, float* du, float* s2, double* d_bias,
+                      gnm_stream_t stream);
+
+/* Standalone Discriminator.forward on materialised tensors (discriminator.py:19-38):
+ * out[r] = <h[r], u[r / rows_per_graph]> + *bias (+ s_bias[r] if non-NULL). */
+int gnm_rowdot_score(const float* h, int64_t ldh, int n_rows, int n_feat, const float* u, int64_t ldu,
+                     int rows_per_graph, const float* bias, const float* s_bias, float* out, gnm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNM_H_ */

@@ -1,0 +1,245 @@
+"""A CPU stand-in for `graph_neural_mapping_b200.ops`, for HOST-LOGIC tests only.
+
+It lives under tests/ and is injected with monkeypatch; the product path cannot reach it.
+Each function follows the contract written in include/gnm.h (not the kernels' code), using
+plain torch CPU ops, so that the orchestration in `engine.py` (the hand-derived backward, the
+graph store, the data-parallel exchanges) can be checked against the golden fixtures without
+a GPU. The CUDA kernels themselves are checked by the `-m gpu` tests.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+
+def _i32_at(addr, n):
+    if n == 0:
+        return np.zeros(0, dtype=np.int32)
+    return np.ctypeslib.as_array(ctypes.cast(int(addr), ctypes.POINTER(ctypes.c_int32)), shape=(n,))
+
+
+def device_info():
+    return dict(sm_count=0, cc=(0, 0), smem_optin=0)
+
+
+def csr_build(edges, edge_off, node_off, n_graphs, n_max, total_nodes, add_self_loops, local_cols):
+    e = edges.numpy().reshape(2, -1)
+    eo, no = edge_off.numpy(), node_off.numpy().astype(np.int64)
+    rows, cols, bad = [], [], 0
+    for g in range(n_graphs):
+        s, d = e[0, eo[g]:eo[g + 1]], e[1, eo[g]:eo[g + 1]]
+        n = no[g + 1] - no[g]
+        ok = (s >= 0) & (s < n) & (d >= 0) & (d < n)
+        bad |= int((~ok).any())
+        s, d = s[ok], d[ok]
+        if add_self_loops:
+            s = np.concatenate([s, np.arange(n)])
+            d = np.concatenate([d, np.arange(n)])
+        order = np.lexsort((d, s))
+        rows.append(s[order] + no[g])
+        cols.append(d[order] + (0 if local_cols else no[g]))
+    rows = np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
+    cols = np.concatenate(cols) if cols else np.zeros(0, dtype=np.int64)
+    rowptr = np.zeros(total_nodes + 1, dtype=np.int64)
+    np.add.at(rowptr, rows + 1, 1)
+    rowptr = np.cumsum(rowptr)
+    return (torch.from_numpy(rowptr.astype(np.int32)), torch.from_numpy(cols.astype(np.int32)),
+            torch.tensor([bad], dtype=torch.int32))
+
+
+def csr_batch_gather(rp_addr, ci_addr, tag_addr, node_off, nnz_off, n_graphs, total_nodes, total_nnz):
+    no, zo = node_off.numpy(), nnz_off.numpy()
+    rowptr = np.zeros(total_nodes + 1, dtype=np.int32)
+    colidx = np.zeros(total_nnz, dtype=np.int32)
+    tags = np.zeros(total_nodes, dtype=np.int32) if tag_addr is not None else None
+    for g in range(n_graphs):
+        n = int(no[g + 1] - no[g])
+        rp = _i32_at(rp_addr[g], n + 1)
+        nnz = int(rp[n] - rp[0])
+        ci = _i32_at(ci_addr[g], nnz)
+        rowptr[no[g]:no[g] + n] = rp[:n] - rp[0] + zo[g]
+        colidx[zo[g]:zo[g] + nnz] = ci + no[g]
+        if tags is not None:
+            tags[no[g]:no[g] + n] = _i32_at(tag_addr[g], n)
+    rowptr[total_nodes] = total_nnz
+    return torch.from_numpy(rowptr), torch.from_numpy(colidx), (torch.from_numpy(tags) if tags is not None else None)
+
+
+def _csr(rowptr, colidx, m):
+    return torch.sparse_csr_tensor(rowptr.long(), colidx.long(), torch.ones(colidx.numel(), dtype=torch.float64),
+                                   size=(m, m)).to_dense()
+
+
+def aggregate(rowptr, colidx, src, src_map, dst, mode, eps, bias=None):
+    m = dst.shape[0]
+    a = _csr(rowptr, colidx, m)
+    s = src.double()
+    if src_map is not None:
+        s = s[src_map.long()]
+    deg = a.sum(1, keepdim=True)
+    if mode == 2:
+        out = a @ (s / deg)
+    else:
+        out = a @ s
+        if mode == 1:
+            out = out / deg
+    if eps is not None:
+        out = out + (1 + eps.double()) * s
+    if bias is not None:
+        out = out + bias.double()
+    dst.copy_(out.float())
+    return dst
+
+
+def dot_rows(a, b, b_map, out):
+    bb = b if b_map is None else b[b_map.long()]
+    out += (a.double() * bb.double()).sum()
+    return out
+
+
+def scatter_rows_add(g, tags, table_grad):
+    table_grad.index_add_(0, tags.long(), g)
+    return table_grad
+
+
+def _act(x, sc, sh):
+    return x if sc is None else torch.relu(x * sc + sh)
+
+
+def linear(x, w, w_is_kn, bias, in_scale, in_shift, y, col_stats):
+    a = _act(x, in_scale, in_shift).double()
+    out = a @ (w.double() if w_is_kn else w.double().t())
+    if bias is not None:
+        out = out + bias.double()
+    y.copy_(out.float())
+    if col_stats is not None:
+        n = y.shape[1]
+        col_stats[:n] += y.double().sum(0)
+        col_stats[n:] += (y.double() ** 2).sum(0)
+    return y
+
+
+def linear_wgrad(dz, x, in_scale, in_shift, dw, dbias):
+    if x is not None:
+        dw += (dz.double().t() @ _act(x, in_scale, in_shift).double()).float()
+    if dbias is not None:
+        dbias += dz.double().sum(0).float()
+
+
+def col_stats(x, stats):
+    n = x.shape[1]
+    stats[:n] += x.double().sum(0)
+    stats[n:] += (x.double() ** 2).sum(0)
+    return stats
+
+
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, nbt, scale, shift, mean, rstd):
+    n = scale.shape[0]
+    mu = stats[:n] / count
+    var = (stats[n:] / count - mu * mu).clamp_(min=0)
+    r = 1.0 / torch.sqrt(var + eps)
+    scale.copy_((gamma.double() * r).float())
+    shift.copy_(beta - mu.float() * scale)
+    mean.copy_(mu.float())
+    rstd.copy_(r.float())
+    if running_mean is not None:
+        running_mean.mul_(1 - momentum).add_(momentum * mu.float())
+    if running_var is not None:
+        unb = var * (count / (count - 1)) if count > 1 else var
+        running_var.mul_(1 - momentum).add_(momentum * unb.float())
+    if nbt is not None:
+        nbt += 1
+
+
+def bn_eval_affine(running_mean, running_var, gamma, beta, eps, scale, shift, mean, rstd):
+    r = 1.0 / torch.sqrt(running_var + eps)
+    scale.copy_(gamma * r)
+    shift.copy_(beta - running_mean * scale)
+    mean.copy_(running_mean)
+    rstd.copy_(r)
+
+
+def _graph_of_row(node_off, m):
+    no = node_off.long()
+    return torch.repeat_interleave(torch.arange(no.numel() - 1), no[1:] - no[:-1])
+
+
+def bn_relu_readout(z, scale, shift, h, node_off, n_graphs, pool_scale, pooled):
+    v = torch.relu(z * scale + shift)
+    if h is not None:
+        h.copy_(v)
+    if pooled is not None:
+        gid = _graph_of_row(node_off, z.shape[0])
+        out = torch.zeros(n_graphs, z.shape[1], dtype=torch.float64).index_add_(0, gid, v.double())
+        if pool_scale is not None:
+            out = out * pool_scale.double().unsqueeze(1)
+        pooled.copy_(out.float())
+
+
+def relu_bn_bwd_reduce(z, scale, shift, mean, rstd, d_out, d_pooled, pool_scale, d_score, u, d_neg, n_neg,
+                       node_off, n_graphs, dy, stats):
+    m, f = z.shape
+    gid = _graph_of_row(node_off, m)
+    g = torch.zeros(m, f, dtype=torch.float32)
+    if d_out is not None:
+        g = g + d_out
+    if d_pooled is not None:
+        gp = d_pooled if pool_scale is None else d_pooled * pool_scale.unsqueeze(1)
+        g = g + gp[gid]
+    if d_score is not None:
+        g = g + d_score.reshape(-1, 1) * u[gid]
+    if d_neg is not None and n_neg > 0:
+        k = min(n_neg, m)
+        g[:k] = g[:k] + d_neg[:k]
+    v = torch.where(z * scale + shift > 0, g, torch.zeros_like(g))
+    dy.copy_(v)
+    if stats is not None:
+        stats[:f] += v.double().sum(0)
+        stats[f:] += (v.double() * ((z - mean) * rstd).double()).sum(0)
+
+
+def bn_bwd_apply(z, mean, rstd, gamma, stats, count, dy):
+    f = dy.shape[1]
+    v = dy
+    if stats is not None:
+        m1 = (stats[:f] / count).float()
+        m2 = (stats[f:] / count).float()
+        v = v - m1 - (z - mean) * rstd * m2
+    dy.copy_(v * gamma * rstd)
+
+
+def gather_nf_rows(h_all, n_rows):
+    return torch.cat([h_all[l, :n_rows] for l in range(h_all.shape[0])], 1).contiguous()
+
+
+def dgi_score_fwd(h_all, u, neg_table, neg_idx, node_off, n_graphs, bias, out):
+    m = h_all.shape[1]
+    gid = _graph_of_row(node_off, m)
+    nf = torch.cat([h_all[l] for l in range(h_all.shape[0])], 1)
+    flat = out.view(-1)
+    flat[:m] = (nf * u[gid]).sum(1) + bias
+    s2 = (neg_table[neg_idx.long()] * u).sum(1) + bias
+    flat[m:] = s2[gid]
+    return out
+
+
+def dgi_score_bwd(h_all, d_out, neg_table, neg_idx, node_off, n_graphs, du, s2, d_bias):
+    m = h_all.shape[1]
+    gid = _graph_of_row(node_off, m)
+    nf = torch.cat([h_all[l] for l in range(h_all.shape[0])], 1)
+    d1, d2 = d_out[:m], d_out[m:]
+    s = torch.zeros(n_graphs).index_add_(0, gid, d2)
+    s2.copy_(s)
+    acc = torch.zeros(n_graphs, nf.shape[1]).index_add_(0, gid, d1.unsqueeze(1) * nf)
+    du.copy_(acc + s.unsqueeze(1) * neg_table[neg_idx.long()])
+    if d_bias is not None:
+        d_bias += d_out.double().sum()
+
+
+def rowdot_score(h, u, rows_per_graph, bias, s_bias, out):
+    gid = torch.arange(h.shape[0]) // rows_per_graph
+    v = (h * u[gid]).sum(1) + bias
+    if s_bias is not None:
+        v = v + s_bias.view(-1)
+    out.copy_(v)
+    return out

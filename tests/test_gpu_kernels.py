@@ -1,0 +1,338 @@
+"""GPU parity tests of each libgnm entry point (called through the C ABI via ops.py) against
+(a) the numpy CSR oracle and (b) the contract-level CPU stand-in (tests/emul_ops.py, fp64
+inside). Integer outputs must match bit-exactly; fp32 outputs within a scaled tolerance."""
+import numpy as np
+import pytest
+import torch
+
+import emul_ops
+from helpers import assert_close
+from oracle import csr_oracle
+from graph_neural_mapping_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 2e-5      # fp32 kernels vs fp64-accumulating stand-in, error scaled by the tensor's max-abs
+
+
+def rand_graph_edges(rng, n, p, dup=0):
+    a = np.triu(rng.random((n, n)) < p, 1)
+    i, j = np.nonzero(a)
+    src, dst = np.concatenate([i, j]), np.concatenate([j, i])
+    if dup and src.size:
+        k = rng.integers(0, src.size, size=dup)
+        src, dst = np.concatenate([src, src[k]]), np.concatenate([dst, dst[k]])
+    perm = rng.permutation(src.size)
+    return np.stack([src[perm], dst[perm]], 0).astype(np.int64)
+
+
+def build_inputs(edge_mats, counts):
+    edges = np.concatenate(edge_mats, 1) if edge_mats else np.zeros((2, 0), np.int64)
+    eo = np.cumsum([0] + [e.shape[1] for e in edge_mats]).astype(np.int64)
+    no = np.cumsum([0] + list(counts)).astype(np.int32)
+    return (torch.from_numpy(edges).to(DEV), torch.from_numpy(eo).to(DEV), torch.from_numpy(no).to(DEV))
+
+
+@pytest.mark.parametrize("self_loops", [False, True])
+@pytest.mark.parametrize("case", ["ragged", "dups", "empty_graph", "single", "n400"])
+def test_csr_build_bit_exact(case, self_loops):
+    rng = np.random.default_rng(7)
+    if case == "ragged":
+        counts = [5, 33, 1, 64, 17, 100]
+        ems = [rand_graph_edges(rng, n, 0.3) for n in counts]
+    elif case == "dups":
+        counts = [20, 31]
+        ems = [rand_graph_edges(rng, n, 0.4, dup=25) for n in counts]
+    elif case == "empty_graph":
+        counts = [6, 9, 4]
+        ems = [rand_graph_edges(rng, 6, 0.5), np.zeros((2, 0), np.int64), rand_graph_edges(rng, 4, 0.9)]
+    elif case == "single":
+        counts = [50]
+        ems = [rand_graph_edges(rng, 50, 0.3)]
+    else:
+        gs = synth.make_graphs(3, 400, 30, 300, seed0=5)
+        counts = [400] * 3
+        ems = [g.edge_mat.numpy() for g in gs]
+    e, eo, no = build_inputs(ems, counts)
+    m = int(sum(counts))
+    rp, ci, st = ops.csr_build(e, eo, no, len(counts), max(counts), m, self_loops, False)
+    assert int(st.item()) == 0
+    rp_o, ci_o = csr_oracle.multiset_csr(ems, counts, learn_eps=not self_loops)
+    assert np.array_equal(rp.cpu().numpy().astype(np.int64), rp_o)
+    assert np.array_equal(ci.cpu().numpy().astype(np.int64), ci_o)
+    # same indices as the reference's own coalesced sparse tensor (graphcnn.py:84-106 + spmm)
+    idx, _ = csr_oracle.block_diag_coo(ems, counts, learn_eps=not self_loops)
+    ref = torch.sparse_coo_tensor(torch.from_numpy(idx), torch.ones(idx.shape[1]), (m, m)).coalesce()
+    dense = torch.zeros(m, m)
+    rows = np.repeat(np.arange(m), np.diff(rp_o))
+    dense.index_put_((torch.from_numpy(rows), torch.from_numpy(ci_o)), torch.ones(len(ci_o)), accumulate=True)
+    assert torch.equal(dense, ref.to_dense())
+    if case != "dups":
+        refcsr = ref.to_sparse_csr()
+        assert np.array_equal(refcsr.crow_indices().numpy(), rp_o) and np.array_equal(refcsr.col_indices().numpy(), ci_o)
+    # local-column form + batch gather reproduces the global form for any slot order
+    rpl, cil, _ = ops.csr_build(e, eo, no, len(counts), max(counts), m, self_loops, True)
+    order = list(rng.permutation(len(counts)))
+    nnz_g = [ems[i].shape[1] + (counts[i] if self_loops else 0) for i in range(len(counts))]
+    nnz_base = np.cumsum([0] + nnz_g)
+    no_h = np.cumsum([0] + list(counts))
+    rp_addr = torch.tensor([rpl.data_ptr() + 4 * int(no_h[i]) for i in order], dtype=torch.int64, device=DEV)
+    ci_addr = torch.tensor([cil.data_ptr() + 4 * int(nnz_base[i]) for i in order], dtype=torch.int64, device=DEV)
+    no2 = torch.from_numpy(np.cumsum([0] + [counts[i] for i in order]).astype(np.int32)).to(DEV)
+    zo2 = torch.from_numpy(np.cumsum([0] + [nnz_g[i] for i in order]).astype(np.int64)).to(DEV)
+    rp2, ci2, _ = ops.csr_batch_gather(rp_addr, ci_addr, None, no2, zo2, len(order), m, int(sum(nnz_g)))
+    rp_o2, ci_o2 = csr_oracle.multiset_csr([ems[i] for i in order], [counts[i] for i in order], learn_eps=not self_loops)
+    assert np.array_equal(rp2.cpu().numpy().astype(np.int64), rp_o2)
+    assert np.array_equal(ci2.cpu().numpy().astype(np.int64), ci_o2)
+
+
+def test_csr_build_flags_bad_index():
+    em = np.array([[0, 1, 7], [1, 0, 2]], dtype=np.int64)
+    e, eo, no = build_inputs([em], [3])
+    _, _, st = ops.csr_build(e, eo, no, 1, 3, 3, False, False)
+    assert int(st.item()) == 1
+
+
+def _structure(rng, counts, p, self_loops):
+    ems = [rand_graph_edges(rng, n, p) for n in counts]
+    e, eo, no = build_inputs(ems, counts)
+    m = int(sum(counts))
+    rp, ci, _ = ops.csr_build(e, eo, no, len(counts), max(counts), m, self_loops, False)
+    return rp, ci, no, m
+
+
+@pytest.mark.parametrize("f", [1, 3, 8, 12, 64, 100, 128, 400])
+@pytest.mark.parametrize("mode,use_eps,use_map", [(0, True, False), (0, False, False), (1, True, False),
+                                                   (2, True, False), (0, True, True), (1, False, True)])
+def test_aggregate(f, mode, use_eps, use_map):
+    rng = np.random.default_rng(f * 10 + mode)
+    counts = [37, 64, 5, 90]
+    rp, ci, no, m = _structure(rng, counts, 0.3, not use_eps)
+    if mode != 1:
+        # avoid 0/0 in the stand-in's transpose path; isolated nodes are covered in test_aggregate_isolated_nan
+        pass
+    torch.manual_seed(f)
+    eps = torch.tensor([0.37], device=DEV) if use_eps else None
+    bias = torch.randn(f, device=DEV) if use_map else None
+    if use_map:
+        table = torch.randn(23, f, device=DEV)
+        smap = torch.randint(0, 23, (m,), dtype=torch.int32, device=DEV)
+        src = table
+    else:
+        src, smap = torch.randn(m, f, device=DEV), None
+    out = torch.empty(m, f, device=DEV)
+    ops.aggregate(rp, ci, src, smap, out, mode, eps, bias)
+    ref = torch.empty(m, f)
+    emul_ops.aggregate(rp.cpu(), ci.cpu(), src.cpu(), smap.cpu() if use_map else None, ref, mode,
+                       eps.cpu() if use_eps else None, bias.cpu() if use_map else None)
+    if mode == 2:
+        deg = (rp[1:] - rp[:-1]).cpu()
+        keep = torch.ones(m, dtype=torch.bool)
+        # rows whose neighbours all have deg > 0 (always true for symmetric graphs)
+        assert_close(out.cpu()[keep], ref[keep], TOL, "aggregate")
+    else:
+        assert_close(out, ref, TOL, "aggregate")
+
+
+def test_aggregate_isolated_nan_and_strided():
+    em = np.array([[0, 1], [1, 0]], dtype=np.int64)        # node 2 isolated
+    e, eo, no = build_inputs([em], [3])
+    rp, ci, _ = ops.csr_build(e, eo, no, 1, 3, 3, False, False)
+    src = torch.randn(3, 8, device=DEV)
+    out = torch.empty(3, 8, device=DEV)
+    ops.aggregate(rp, ci, src, None, out, 1, torch.tensor([0.0], device=DEV), None)   # graphcnn.py:157-158: 0/0
+    assert torch.isnan(out[2]).all() and not torch.isnan(out[:2]).any()
+    # strided views (a layer slice of a wider buffer)
+    big_s, big_d = torch.randn(3, 24, device=DEV), torch.zeros(3, 40, device=DEV)
+    ops.aggregate(rp, ci, big_s[:, 8:16], None, big_d[:, 16:24], 0, None, None)
+    assert torch.allclose(big_d[0, 16:24], big_s[1, 8:16]) and torch.all(big_d[:, :16] == 0) and torch.all(big_d[:, 24:] == 0)
+
+
+@pytest.mark.parametrize("m,k,n", [(1, 1, 1), (37, 10, 8), (300, 64, 64), (513, 400, 64), (257, 64, 400), (1000, 128, 128),
+                                   (129, 12, 12)])
+@pytest.mark.parametrize("kn,pro,stats", [(False, False, True), (False, True, True), (True, False, False)])
+def test_linear(m, k, n, kn, pro, stats):
+    torch.manual_seed(m + k + n)
+    x = torch.randn(m, k, device=DEV)
+    w = torch.randn((k, n) if kn else (n, k), device=DEV) * 0.3
+    b = torch.randn(n, device=DEV)
+    sc = torch.rand(k, device=DEV) + 0.5 if pro else None
+    sh = torch.randn(k, device=DEV) if pro else None
+    y = torch.empty(m, n, device=DEV)
+    st = torch.zeros(2 * n, dtype=torch.float64, device=DEV) if stats else None
+    ops.linear(x, w, kn, b, sc, sh, y, st)
+    yr = torch.empty(m, n)
+    sr = torch.zeros(2 * n, dtype=torch.float64) if stats else None
+    emul_ops.linear(x.cpu(), w.cpu(), kn, b.cpu(), sc.cpu() if pro else None, sh.cpu() if pro else None, yr, sr)
+    assert_close(y, yr, TOL, "linear")
+    if stats:
+        assert_close(st, sr, 1e-5, "linear col_stats")
+        st2 = torch.zeros(2 * n, dtype=torch.float64, device=DEV)
+        ops.col_stats(y, st2)
+        assert_close(st2, sr, 1e-5, "col_stats")
+
+
+@pytest.mark.parametrize("m,no,ni", [(1, 1, 1), (300, 8, 10), (5000, 64, 64), (1111, 64, 400), (2049, 128, 128), (700, 12, 0)])
+@pytest.mark.parametrize("pro", [False, True])
+def test_linear_wgrad(m, no, ni, pro):
+    torch.manual_seed(m)
+    dz = torch.randn(m, no, device=DEV)
+    x = torch.randn(m, ni, device=DEV) if ni > 0 else None
+    sc = torch.rand(ni, device=DEV) + 0.5 if (pro and ni > 0) else None
+    sh = torch.randn(ni, device=DEV) if (pro and ni > 0) else None
+    dw = torch.zeros(no, ni, device=DEV) if ni > 0 else None
+    db = torch.zeros(no, device=DEV)
+    ops.linear_wgrad(dz, x, sc, sh, dw, db)
+    dwr = torch.zeros(no, ni) if ni > 0 else None
+    dbr = torch.zeros(no)
+    emul_ops.linear_wgrad(dz.cpu(), x.cpu() if x is not None else None, sc.cpu() if sc is not None else None,
+                          sh.cpu() if sh is not None else None, dwr, dbr)
+    if ni > 0:
+        assert_close(dw, dwr, TOL, "dw")
+    assert_close(db, dbr, TOL, "db")
+
+
+@pytest.mark.parametrize("f", [8, 12, 64, 128, 300])
+def test_batchnorm_pieces(f):
+    torch.manual_seed(f)
+    counts = [40, 7, 129]
+    m = sum(counts)
+    no = torch.tensor(np.cumsum([0] + counts).astype(np.int32), device=DEV)
+    z = torch.randn(m, f, device=DEV) * 3 + 1
+    gamma, beta = torch.rand(f, device=DEV) + 0.5, torch.randn(f, device=DEV)
+    rm, rv = torch.randn(f, device=DEV), torch.rand(f, device=DEV) + 0.5
+    nbt = torch.tensor(3, dtype=torch.int64, device=DEV)
+    st = torch.zeros(2 * f, dtype=torch.float64, device=DEV)
+    ops.col_stats(z, st)
+    bufs = torch.empty(4, f, device=DEV)
+    rm_c, rv_c, nbt_c = rm.cpu().clone(), rv.cpu().clone(), nbt.cpu().clone()
+    ops.bn_finalize(st, float(m), gamma, beta, 1e-5, 0.1, rm, rv, nbt, bufs[0], bufs[1], bufs[2], bufs[3])
+    # against torch's own batch_norm (what the reference calls)
+    yr = torch.nn.functional.batch_norm(z.cpu(), rm_c, rv_c, gamma.cpu(), beta.cpu(), True, 0.1, 1e-5)
+    assert_close(z * bufs[0] + bufs[1], yr, TOL, "bn train affine")
+    assert_close(rm, rm_c, TOL, "running_mean")
+    assert_close(rv, rv_c, TOL, "running_var")
+    assert int(nbt) == int(nbt_c) + 1
+    ev = torch.empty(4, f, device=DEV)
+    ops.bn_eval_affine(rm, rv, gamma, beta, 1e-5, ev[0], ev[1], ev[2], ev[3])
+    ye = torch.nn.functional.batch_norm(z.cpu(), rm_c, rv_c, gamma.cpu(), beta.cpu(), False, 0.1, 1e-5)
+    assert_close(z * ev[0] + ev[1], ye, TOL, "bn eval affine")
+    # apply + readout
+    for ps in (None, torch.tensor([1.0 / c for c in counts], device=DEV)):
+        h = torch.empty(m, f, device=DEV)
+        wide = torch.zeros(3, 2 * f, device=DEV)
+        ops.bn_relu_readout(z, bufs[0], bufs[1], h, no, 3, ps, wide[:, f:])
+        hr, pr = torch.empty(m, f), torch.zeros(3, f)
+        emul_ops.bn_relu_readout(z.cpu(), bufs[0].cpu(), bufs[1].cpu(), hr, no.cpu(), 3, ps.cpu() if ps is not None else None, pr)
+        assert_close(h, hr, TOL, "h")
+        assert_close(wide[:, f:], pr, TOL, "pooled")
+        assert torch.all(wide[:, :f] == 0)
+    # backward pieces with every gradient source switched on
+    d_out = torch.randn(m, f, device=DEV)
+    d_pool = torch.randn(3, 2 * f, device=DEV)
+    d_score = torch.randn(m, device=DEV)
+    u = torch.randn(3, 3 * f, device=DEV)
+    d_neg = torch.randn(3, f, device=DEV)
+    ps = torch.tensor([1.0 / c for c in counts], device=DEV)
+    dy = torch.empty(m, f, device=DEV)
+    bst = torch.zeros(2 * f, dtype=torch.float64, device=DEV)
+    ops.relu_bn_bwd_reduce(z, bufs[0], bufs[1], bufs[2], bufs[3], d_out, d_pool[:, f:], ps, d_score, u[:, f:2 * f], d_neg, 3,
+                           no, 3, dy, bst)
+    dyr, bstr = torch.empty(m, f), torch.zeros(2 * f, dtype=torch.float64)
+    c = lambda t: t.cpu() if t is not None else None
+    emul_ops.relu_bn_bwd_reduce(c(z), c(bufs[0]), c(bufs[1]), c(bufs[2]), c(bufs[3]), c(d_out), c(d_pool)[:, f:], c(ps), c(d_score),
+                                c(u)[:, f:2 * f], c(d_neg), 3, c(no), 3, dyr, bstr)
+    assert_close(dy, dyr, TOL, "dy")
+    assert_close(bst, bstr, 1e-5, "bwd stats")
+    for use_stats in (True, False):
+        d1, d2 = dy.clone(), dyr.clone()
+        ops.bn_bwd_apply(z, bufs[2], bufs[3], gamma, bst if use_stats else None, float(m), d1)
+        emul_ops.bn_bwd_apply(c(z), c(bufs[2]), c(bufs[3]), c(gamma), bstr if use_stats else None, float(m), d2)
+        assert_close(d1, d2, TOL, "dz")
+    # full check of the two-pass BatchNorm backward against autograd of torch's batch_norm + relu
+    zz = z.cpu().clone().requires_grad_(True)
+    g_, b_ = gamma.cpu().clone().requires_grad_(True), beta.cpu().clone().requires_grad_(True)
+    out = torch.relu(torch.nn.functional.batch_norm(zz, None, None, g_, b_, True, 0.1, 1e-5))
+    gz, gg, gb = torch.autograd.grad(out, [zz, g_, b_], d_out.cpu())
+    dy2 = torch.empty(m, f, device=DEV)
+    st2 = torch.zeros(2 * f, dtype=torch.float64, device=DEV)
+    ops.relu_bn_bwd_reduce(z, bufs[0], bufs[1], bufs[2], bufs[3], d_out, None, None, None, None, None, 0, no, 3, dy2, st2)
+    ops.bn_bwd_apply(z, bufs[2], bufs[3], gamma, st2, float(m), dy2)
+    assert_close(dy2, gz, 1e-4, "bn+relu dz vs autograd")
+    assert_close(st2[:f], gb, 1e-4, "dbeta")
+    assert_close(st2[f:], gg, 1e-4, "dgamma")
+
+
+@pytest.mark.parametrize("L,f,n,b", [(3, 8, 12, 4), (5, 64, 48, 6), (2, 12, 16, 5), (5, 64, 400, 3)])
+def test_dgi_scores(L, f, n, b):
+    torch.manual_seed(L * f)
+    m = n * b
+    h_all = torch.randn(L, m, f, device=DEV)
+    u = torch.randn(b, L * f, device=DEV)
+    bias = torch.tensor([0.3], device=DEV)
+    perm = torch.randperm(b).to(torch.int32).to(DEV)
+    no = torch.arange(0, m + 1, n, dtype=torch.int32, device=DEV)
+    table = ops.gather_nf_rows(h_all, b)
+    tr = emul_ops.gather_nf_rows(h_all.cpu(), b)
+    assert torch.equal(table.cpu(), tr)
+    out = torch.empty(2 * m, 1, device=DEV)
+    ops.dgi_score_fwd(h_all, u, table, perm, no, b, bias, out)
+    outr = torch.empty(2 * m, 1)
+    emul_ops.dgi_score_fwd(h_all.cpu(), u.cpu(), tr, perm.cpu(), no.cpu(), b, bias.cpu(), outr)
+    assert_close(out, outr, TOL, "dgi fwd")
+    # literal reference formulation: nn.Bilinear on expanded c and n_f[idx] (graphcnn.py:198-201,241-246)
+    w = torch.randn(1, L * f, L * f) * 0.1
+    cvec = torch.rand(b, L * f)
+    uu = (cvec @ w[0].t()).to(DEV)
+    ops.dgi_score_fwd(h_all, uu, table, perm, no, b, bias, out)
+    nf = torch.cat([h_all[l].cpu() for l in range(L)], 1)
+    idx = np.repeat(perm.cpu().numpy(), n)
+    cx = cvec.repeat_interleave(n, 0)
+    lit = torch.cat([torch.nn.functional.bilinear(nf, cx, w, bias.cpu()),
+                     torch.nn.functional.bilinear(nf[idx], cx, w, bias.cpu())], 0)
+    assert_close(out, lit, 5e-5, "dgi fwd vs nn.Bilinear")
+    d = torch.randn(2 * m, device=DEV)
+    du, s2 = torch.empty(b, L * f, device=DEV), torch.empty(b, device=DEV)
+    db = torch.zeros(1, dtype=torch.float64, device=DEV)
+    ops.dgi_score_bwd(h_all, d, table, perm, no, b, du, s2, db)
+    dur, s2r, dbr = torch.empty(b, L * f), torch.empty(b), torch.zeros(1, dtype=torch.float64)
+    emul_ops.dgi_score_bwd(h_all.cpu(), d.cpu(), tr, perm.cpu(), no.cpu(), b, dur, s2r, dbr)
+    assert_close(du, dur, TOL, "du")
+    assert_close(s2, s2r, TOL, "s2")
+    assert_close(db, dbr, 1e-5, "dbias")
+    # standalone row-dot
+    o2 = torch.empty(m, device=DEV)
+    ops.rowdot_score(table.new_empty(0, 1) if False else torch.cat([h_all[l] for l in range(L)], 1).contiguous(), uu, n, bias, None, o2)
+    assert_close(o2, lit[:m, 0], 5e-5, "rowdot")
+
+
+def test_dot_rows_and_scatter():
+    torch.manual_seed(0)
+    m, f, t = 1234, 64, 50
+    a, b = torch.randn(m, f, device=DEV), torch.randn(t, f, device=DEV)
+    mp = torch.randint(0, t, (m,), dtype=torch.int32, device=DEV)
+    out = torch.zeros(1, dtype=torch.float64, device=DEV)
+    ops.dot_rows(a, b, mp, out)
+    assert_close(out, (a.double() * b[mp.long()].double()).sum().reshape(1), 1e-6, "dot_rows")
+    out.zero_()
+    c = torch.randn(m, f, device=DEV)
+    ops.dot_rows(a, c, None, out)
+    assert_close(out, (a.double() * c.double()).sum().reshape(1), 1e-6, "dot_rows nomap")
+    for tt, ff in [(50, 64), (400, 64), (1000, 128), (7, 12)]:
+        g = torch.randn(m, ff, device=DEV)
+        tags = torch.randint(0, tt, (m,), dtype=torch.int32, device=DEV)
+        tg = torch.zeros(tt, ff, device=DEV)
+        ops.scatter_rows_add(g, tags, tg)
+        ref = torch.zeros(tt, ff, dtype=torch.float64).index_add_(0, tags.cpu().long(), g.cpu().double())
+        assert_close(tg, ref, TOL, "scatter_rows_add")
+
+
+def test_no_cpu_fallback():
+    x = torch.randn(4, 4)
+    with pytest.raises(RuntimeError):
+        ops.col_stats(x, torch.zeros(8, dtype=torch.float64))
+    from graph_neural_mapping_b200.models import GIN_InfoMaxReg
+    m = GIN_InfoMaxReg(2, 2, 5, 4, 2, 0.0, True, "sum", "sum", torch.device("cpu"))
+    g = synth.make_graph(0, 5, 30, 32)
+    with pytest.raises(RuntimeError):
+        m([g])

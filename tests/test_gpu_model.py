@@ -1,0 +1,222 @@
+"""GPU parity of the whole drop-in path (GIN_InfoMaxReg on libgnm) against the golden fixtures
+written by the UNMODIFIED reference, and against the fp64 oracle (tolerance tie-breaker).
+
+Tolerances (scaled by each tensor's max-abs): logits/loss/latent 1e-4; gradients
+and saliency 2e-3 - the reference's own fp32 result differs from the fp64 oracle by up to 1e-3
+on some gradients at N=400 (tests/test_oracle_vs_golden.py), so nothing tighter is meaningful."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import Golden, assert_close, golden_names, grad_floor
+from oracle import gin_oracle
+from graph_neural_mapping_b200.models import GIN_InfoMaxReg, Discriminator, MLP
+from graph_neural_mapping_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda")
+NAMES = [n for n in golden_names() if "max" not in n]
+TOL, TOL_GRAD = 1e-4, 2e-3
+SEEDS = {"tiny_eps_sum": 100, "tiny_noeps_sum": 100, "tiny_eps_avg": 300, "tiny_noeps_avg": 300, "tiny_mlp1": 500,
+         "tiny_mlp3": 500, "mid_eps_sum_h64": 900, "schaefer400_noeps": 0, "schaefer400_eps": 10}
+
+
+def build_model(g, sd=None):
+    c = g.cfg
+    m = GIN_InfoMaxReg(c["num_layers"], c["num_mlp_layers"], c["input_dim"], c["hidden_dim"], c["output_dim"],
+                       c["final_dropout"], c["learn_eps"], c["graph_pooling_type"], c["neighbor_pooling_type"], DEV)
+    m.load_state_dict(sd if sd is not None else g.state_dict())
+    return m.to(DEV)
+
+
+def train_step(model, graphs, beta, seed):
+    model.train()
+    np.random.seed(seed)
+    c_logit, d_logit = model(graphs)
+    labels = torch.LongTensor([x.label for x in graphs]).to(DEV)
+    n = len(graphs) * graphs[0].node_features.shape[1]
+    d_labels = torch.cat([torch.ones(n, 1), torch.zeros(n, 1)], 0).to(DEV)          # main.py:32
+    loss = torch.nn.functional.cross_entropy(c_logit, labels) + beta * \
+        torch.nn.functional.binary_cross_entropy_with_logits(d_logit, d_labels)     # main.py:34-37
+    model.zero_grad()
+    loss.backward()
+    return c_logit, d_logit, loss
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_train_step_vs_reference_and_oracle(name):
+    g = Golden(name)
+    model = build_model(g)
+    graphs = g.graphs()
+    c_logit, d_logit, loss = train_step(model, graphs, g.cfg["beta"], 4242 + SEEDS[name])
+    assert_close(c_logit, g.z["train/c_logit"], TOL, "c_logit")
+    assert_close(d_logit, g.z["train/d_logit"], TOL, "d_logit")
+    assert_close(loss, g.z["train/loss"], TOL, "loss")
+    ref_grads = g.group("grad/")
+    floor = grad_floor(ref_grads)
+    for k, p in model.named_parameters():
+        if k in ref_grads:
+            assert p.grad is not None, k
+            assert_close(p.grad, ref_grads[k], TOL_GRAD, "grad " + k, floor=floor)
+        else:
+            assert p.grad is None, k
+    for k, v in g.group("buf_after/").items():
+        got = model.state_dict()[k]
+        if "num_batches" in k:
+            assert int(got) == int(v)
+        else:
+            assert_close(got, v, TOL, k)
+    # fp64 oracle as the tie-breaker: the CUDA path must be as close to it as the reference is
+    c = g.cfg
+    ocfg = gin_oracle.OracleConfig(c["num_layers"], c["num_mlp_layers"], c["input_dim"], c["hidden_dim"], c["output_dim"],
+                                   c["final_dropout"], c["learn_eps"], c["graph_pooling_type"], c["neighbor_pooling_type"])
+    r = gin_oracle.train_step_grads(g.state_dict(), graphs, g.perm, ocfg, c["beta"], torch.float64)
+    assert_close(c_logit, r["c_logit"], TOL, "c_logit vs fp64")
+    assert_close(d_logit, r["d_logit"], TOL, "d_logit vs fp64")
+    ograds = {k: (v.numpy() if v is not None else None) for k, v in r["grads"].items()}
+    floor = grad_floor(ograds)
+    for k, p in model.named_parameters():
+        if ograds.get(k) is not None:
+            assert_close(p.grad, ograds[k], TOL_GRAD, "grad vs fp64 " + k, floor=floor)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_eval_latent_saliency_vs_reference(name):
+    g = Golden(name)
+    model = build_model(g, g.state_after_train())
+    graphs = g.graphs()
+    model.eval()
+    np.random.seed(777)
+    c_e, d_e = model(graphs)
+    assert c_e.is_cuda and d_e.is_cuda and tuple(d_e.shape) == (2 * sum(g.node_counts), 1)
+    assert_close(c_e, g.z["eval/c_logit"], TOL, "eval c_logit")
+    assert_close(d_e, g.z["eval/d_logit"], TOL, "eval d_logit")
+    np.random.seed(1)
+    lat = model(graphs, latent=True)
+    assert isinstance(lat, np.ndarray) and lat.dtype == np.float32
+    assert_close(lat, g.z["eval/latent"], TOL, "latent")
+    np.random.seed(778)
+    c1, d1 = model([graphs[0]])
+    assert_close(c1, g.z["eval1/c_logit"], TOL, "eval1 c")
+    assert_close(d1, g.z["eval1/d_logit"], TOL, "eval1 d")
+    for k, v in g.group("saliency/").items():
+        gi, cls = int(k[1:k.index("_")]), int(k[-1])
+        s = model.compute_saliency([graphs[gi]], cls)
+        assert tuple(s.shape) == v.shape
+        assert_close(s, v, TOL_GRAD, "saliency " + k)
+        if gi == 0 and cls == 1:
+            ref = g.group("saliency_paramgrad/")
+            floor = grad_floor(ref) if ref else 0.0
+            for kk, p in model.named_parameters():
+                if kk in ref:
+                    assert_close(p.grad, ref[kk], TOL_GRAD, "saliency param grad " + kk, floor=floor)
+    # batched saliency == per-graph saliency (eval-mode BN, block-diagonal adjacency)
+    cls = 1
+    sb = model.compute_saliency_batched(graphs[:2], cls)
+    n0 = g.node_counts[0]
+    s0 = model.compute_saliency([graphs[0]], cls)
+    s1 = model.compute_saliency([graphs[1]], cls)
+    assert_close(sb[:n0], s0, 1e-6, "batched saliency g0")
+    assert_close(sb[n0:], s1, 1e-6, "batched saliency g1")
+    assert_close(s0, g.z["saliency/g0_c1"], TOL_GRAD, "saliency g0 vs reference")
+
+
+def test_dropout_training_uses_torch_rng_and_keeps_shapes():
+    g = Golden("tiny_eps_sum")
+    c = g.cfg
+    m = GIN_InfoMaxReg(c["num_layers"], c["num_mlp_layers"], c["input_dim"], c["hidden_dim"], 2, 0.5, True, "sum", "sum", DEV).to(DEV)
+    m.train()
+    graphs = g.graphs()
+    torch.manual_seed(0)
+    a, _ = m(graphs)
+    torch.manual_seed(0)
+    b, _ = m(graphs)
+    assert torch.equal(a, b) and tuple(a.shape) == (len(graphs), 2)
+
+
+def test_adam_training_follows_reference_for_a_few_steps():
+    """Three full main.py:25-41 steps (forward, loss, backward, Adam) against the fp32 oracle stepping the
+    same state with torch.optim.Adam: parameters stay within tolerance (errors do not compound visibly)."""
+    g = Golden("mid_eps_sum_h64")
+    c = g.cfg
+    model = build_model(g)
+    graphs = g.graphs()
+    opt = torch.optim.Adam(model.parameters(), lr=0.005)
+    ocfg = gin_oracle.OracleConfig(c["num_layers"], c["num_mlp_layers"], c["input_dim"], c["hidden_dim"], c["output_dim"],
+                                   0.0, c["learn_eps"], c["graph_pooling_type"], c["neighbor_pooling_type"])
+    sd = {k: v.clone() for k, v in g.state_dict().items()}
+    names = [k for k, _ in model.named_parameters()]
+    oparams = [sd[k].clone().double().requires_grad_(True) for k in names]
+    oopt = torch.optim.Adam(oparams, lr=0.005)
+    for step in range(3):
+        np.random.seed(100 + step)
+        perm = np.random.permutation(len(graphs))
+        _, _, loss = train_step(model, graphs, c["beta"], 100 + step)
+        opt.step()
+        state = dict(sd)
+        for k, p in zip(names, oparams):
+            state[k] = p.detach()
+        r = gin_oracle.train_step_grads(state, graphs, perm, ocfg, c["beta"], torch.float64)
+        assert_close(loss, r["loss"], 5e-4, "loss step %d" % step)
+        oopt.zero_grad()
+        for k, p in zip(names, oparams):
+            p.grad = r["grads"][k]
+        oopt.step()
+        for k, v in r["new_buffers"].items():
+            sd[k] = v
+    for k, p in zip(names, oparams):
+        assert_close(dict(model.named_parameters())[k], p.detach(), 5e-3, "param after 3 steps " + k)
+
+
+def test_standalone_modules_on_gpu():
+    torch.manual_seed(0)
+    mlp = MLP(2, 20, 16, 16).to(DEV)
+    x = torch.randn(300, 20, device=DEV, requires_grad=True)
+    y = mlp(x)
+    z = torch.nn.functional.batch_norm(x @ mlp.linears[0].weight.t() + mlp.linears[0].bias, None, None,
+                                       mlp.batch_norms[0].weight, mlp.batch_norms[0].bias, True)
+    yr = torch.relu(z) @ mlp.linears[1].weight.t() + mlp.linears[1].bias
+    assert_close(y, yr, 2e-5, "mlp fwd")
+    gy = torch.randn_like(y)
+    ps = [x, mlp.linears[0].weight, mlp.linears[1].weight, mlp.batch_norms[0].weight, mlp.batch_norms[0].bias, mlp.linears[1].bias]
+    g1 = torch.autograd.grad(y, ps, gy, retain_graph=True)
+    g2 = torch.autograd.grad(yr, ps, gy)
+    for a, b in zip(g1, g2):
+        assert_close(a, b, 2e-4, "mlp grads")
+    d = Discriminator(40).to(DEV)
+    c = torch.rand(5, 40, device=DEV)
+    hp, hm = torch.randn(60, 40, device=DEV, requires_grad=True), torch.randn(60, 40, device=DEV)
+    out = d(c, hp, hm)
+    cx = c.repeat_interleave(12, 0)
+    ref = torch.cat([torch.nn.functional.bilinear(hp, cx, d.f_k.weight, d.f_k.bias),
+                     torch.nn.functional.bilinear(hm, cx, d.f_k.weight, d.f_k.bias)], 0)
+    assert_close(out, ref, 2e-5, "disc fwd")
+    go = torch.randn_like(out)
+    g1 = torch.autograd.grad(out, [hp, d.f_k.weight, d.f_k.bias], go, retain_graph=True)
+    g2 = torch.autograd.grad(ref, [hp, d.f_k.weight, d.f_k.bias], go)
+    for a, b in zip(g1, g2):
+        assert_close(a, b, 2e-4, "disc grads")
+
+
+def test_full_size_properties():
+    """Size-independent checks at the benchmark's shape class (N=400, F=64, L=5; B=64 graphs here):
+    aggregation of ones gives the degrees, eval forward is order-equivariant, saliency batching is exact."""
+    torch.manual_seed(0)
+    graphs = synth.make_graphs_bulk(64, 400, 30, 128, seed0=3, device="cuda")
+    m = GIN_InfoMaxReg(5, 2, 400, 64, 2, 0.0, False, "sum", "sum", DEV).to(DEV).eval()
+    np.random.seed(0)
+    c, d = m(graphs)
+    assert torch.isfinite(c).all() and torch.isfinite(d).all()
+    bs = m._structure(graphs)
+    rp, ci = bs.rowptr.cpu().numpy(), bs.colidx.cpu().numpy()
+    assert rp[0] == 0 and rp[-1] == ci.size == 64 * (47600 + 400)
+    rows = np.repeat(np.arange(rp.size - 1), np.diff(rp))
+    assert np.all(ci // 400 == rows // 400)                                  # block diagonal
+    key = rows.astype(np.int64) * (64 * 400) + ci
+    assert np.all(np.diff(key) > 0)                                          # row-major sorted, no duplicates
+    np.random.seed(0)
+    c2, _ = m(list(reversed(graphs)))
+    assert_close(c2.flip(0), c, 1e-5, "order equivariance")
+    s_all = m.compute_saliency_batched(graphs[:3], 1)
+    s_one = m.compute_saliency([graphs[1]], 1)
+    assert_close(s_all[400:800], s_one, 1e-6, "batched saliency exact")

@@ -1,0 +1,217 @@
+"""Host-logic tests (CPU): the engine's orchestration - graph store, batch assembly, the
+hand-derived backward, saliency, data-parallel exchanges - run over a CPU stand-in for the
+kernels (tests/emul_ops.py, injected here only) and compared with the golden fixtures that the
+unmodified reference produced. The CUDA kernels are covered by the `-m gpu` tests."""
+import numpy as np
+import pytest
+import torch
+
+import emul_ops
+from helpers import Golden, assert_close, golden_names, grad_floor
+from graph_neural_mapping_b200 import engine
+from graph_neural_mapping_b200.models import graphcnn as gmod
+from graph_neural_mapping_b200.models import mlp as mlpmod
+from graph_neural_mapping_b200.models import discriminator as dmod
+
+NAMES = [n for n in golden_names() if "max" not in n]
+TOL = 1e-4
+TOL_GRAD = 2e-3
+
+
+@pytest.fixture(autouse=True)
+def cpu_backend(monkeypatch):
+    monkeypatch.setattr(engine, "_ops", emul_ops)
+    monkeypatch.setattr(mlpmod, "_ops", emul_ops)
+    monkeypatch.setattr(dmod, "_ops", emul_ops)
+    monkeypatch.setattr(engine, "require_cuda", lambda dev: None)
+
+
+def build_model(g, sd=None):
+    c = g.cfg
+    m = gmod.GIN_InfoMaxReg(c["num_layers"], c["num_mlp_layers"], c["input_dim"], c["hidden_dim"], c["output_dim"],
+                            c["final_dropout"], c["learn_eps"], c["graph_pooling_type"], c["neighbor_pooling_type"],
+                            torch.device("cpu"))
+    m.load_state_dict(sd if sd is not None else g.state_dict())
+    return m
+
+
+def train_step(model, graphs, g, seed):
+    model.train()
+    np.random.seed(seed)
+    c_logit, d_logit = model(graphs)
+    labels = torch.LongTensor([x.label for x in graphs])
+    n = len(graphs) * graphs[0].node_features.shape[1]
+    d_labels = torch.cat([torch.ones(n, 1), torch.zeros(n, 1)], 0)
+    loss = torch.nn.functional.cross_entropy(c_logit, labels) + g.cfg["beta"] * \
+        torch.nn.functional.binary_cross_entropy_with_logits(d_logit, d_labels)
+    model.zero_grad()
+    loss.backward()
+    return c_logit, d_logit, loss
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_state_dict_layout_matches_reference(name):
+    g = Golden(name)
+    m = build_model(g)
+    sd, ref = m.state_dict(), g.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape) and sd[k].dtype == ref[k].dtype, k
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_train_step_vs_reference(name):
+    g = Golden(name)
+    if g.cfg["N"] >= 400:
+        pytest.skip("dense CPU stand-in is too slow at N=400; covered on the GPU")
+    model = build_model(g)
+    graphs = g.graphs()
+    c_logit, d_logit, loss = train_step(model, graphs, g, 4242 + {"tiny_eps_sum": 100, "tiny_noeps_sum": 100, "tiny_eps_avg": 300,
+                                        "tiny_noeps_avg": 300, "tiny_mlp1": 500, "tiny_mlp3": 500,
+                                        "mid_eps_sum_h64": 900}[name])
+    assert_close(c_logit, g.z["train/c_logit"], TOL, "c_logit")
+    assert_close(d_logit, g.z["train/d_logit"], TOL, "d_logit")
+    assert_close(loss, g.z["train/loss"], TOL, "loss")
+    ref_grads = g.group("grad/")
+    floor = grad_floor(ref_grads)
+    for k, p in model.named_parameters():
+        if k in ref_grads:
+            assert p.grad is not None, k
+            assert_close(p.grad, ref_grads[k], TOL_GRAD, "grad " + k, floor=floor)
+        else:
+            assert p.grad is None, k
+    for k, v in g.group("buf_after/").items():
+        got = model.state_dict()[k]
+        if "num_batches" in k:
+            assert int(got) == int(v)
+        else:
+            assert_close(got, v, TOL, k)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_eval_latent_saliency_vs_reference(name):
+    g = Golden(name)
+    if g.cfg["N"] >= 400:
+        pytest.skip("dense CPU stand-in is too slow at N=400; covered on the GPU")
+    model = build_model(g, g.state_after_train())
+    graphs = g.graphs()
+    model.eval()
+    np.random.seed(777)
+    c_e, d_e = model(graphs)
+    assert_close(c_e, g.z["eval/c_logit"], TOL, "eval c_logit")
+    assert_close(d_e, g.z["eval/d_logit"], TOL, "eval d_logit")
+    np.random.seed(1)
+    lat = model(graphs, latent=True)
+    assert isinstance(lat, np.ndarray) and lat.dtype == np.float32
+    assert_close(lat, g.z["eval/latent"], TOL, "latent")
+    np.random.seed(778)
+    c1, d1 = model([graphs[0]])
+    assert_close(c1, g.z["eval1/c_logit"], TOL, "eval1 c")
+    assert_close(d1, g.z["eval1/d_logit"], TOL, "eval1 d")
+    for k, v in g.group("saliency/").items():
+        gi, cls = int(k[1:k.index("_")]), int(k[-1])
+        s = model.compute_saliency([graphs[gi]], cls)
+        assert tuple(s.shape) == v.shape
+        assert_close(s, v, TOL_GRAD, "saliency " + k)
+        if gi == 0 and cls == 1:
+            ref = g.group("saliency_paramgrad/")
+            floor = grad_floor(ref)
+            for kk, p in model.named_parameters():
+                if kk in ref:
+                    assert_close(p.grad, ref[kk], TOL_GRAD, "saliency param grad " + kk, floor=floor)
+                else:
+                    assert p.grad is None, kk
+    sb = model.compute_saliency_batched(graphs[:2], 1)
+    n0 = g.node_counts[0]
+    assert_close(sb[:n0], g.z["saliency/g0_c1"], TOL_GRAD, "batched saliency g0")
+    assert_close(sb[n0:], g.z["saliency/g1_c1"], TOL_GRAD, "batched saliency g1")
+
+
+def test_one_numpy_draw_per_forward():
+    g = Golden("tiny_eps_sum")
+    model = build_model(g).eval()
+    graphs = g.graphs()
+    np.random.seed(5)
+    model(graphs)
+    after = np.random.rand()
+    np.random.seed(5)
+    np.random.permutation(len(graphs))
+    assert after == np.random.rand()
+    np.random.seed(5)
+    model.compute_saliency([graphs[0]], 0)          # no numpy draw (graphcnn.py:254-299)
+    after = np.random.rand()
+    np.random.seed(5)
+    assert after == np.random.rand()
+
+
+def test_dense_feature_path_matches_gather_path():
+    """Non-one-hot node features take the dense layer-0 path; on one-hot input scaled by 1 they agree."""
+    g = Golden("tiny_eps_sum")
+    graphs = g.graphs()
+    m1, m2 = build_model(g), build_model(g)
+    for gr in graphs:
+        gr.node_features = gr.node_features.clone()
+    graphs2 = g.graphs()
+    for gr in graphs2:
+        gr.node_features = gr.node_features * 1.0 + 0.0
+        gr.node_features[0, 0] = 1.0000001   # not exactly one-hot any more -> dense path
+    c1, d1, _ = train_step(m1, graphs, g, 3)
+    c2, d2, _ = train_step(m2, graphs2, g, 3)
+    assert_close(c2, c1.detach(), 1e-5, "dense vs gather c_logit")
+    assert_close(d2, d1.detach(), 1e-5, "dense vs gather d_logit")
+    floor = grad_floor({k: p.grad.numpy() for k, p in m1.named_parameters() if p.grad is not None})
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert_close(p2.grad, p1.grad, 1e-4, "dense vs gather grad " + k, floor=floor)
+
+
+def test_graph_store_reuse_and_errors():
+    g = Golden("tiny_noeps_sum")
+    model = build_model(g).eval()
+    graphs = g.graphs()
+    np.random.seed(0)
+    a, _ = model(graphs)
+    n_before = len(model._store)
+    np.random.seed(0)
+    b, _ = model(list(reversed(graphs)))
+    assert len(model._store) == n_before == len(graphs)
+    assert_close(b.flip(0), a.detach(), 1e-6, "order")
+    bad = g.graphs()[0]
+    bad.edge_mat = bad.edge_mat.clone()
+    bad.edge_mat[0, 0] = 10 ** 6
+    with pytest.raises(IndexError):
+        model([bad])
+    with pytest.raises(AssertionError):
+        model.compute_saliency(graphs[:2], 0)
+
+
+def test_mlp_and_discriminator_standalone():
+    torch.manual_seed(0)
+    mlp = mlpmod.MLP(3, 6, 5, 4)
+    ref = torch.nn.Sequential()
+    x = torch.randn(37, 6, requires_grad=True)
+    y = mlp(x)
+    h = x
+    for j in range(2):
+        h = torch.relu(torch.nn.functional.batch_norm(h @ mlp.linears[j].weight.t() + mlp.linears[j].bias, None, None,
+                                                       mlp.batch_norms[j].weight, mlp.batch_norms[j].bias, True))
+    yr = h @ mlp.linears[2].weight.t() + mlp.linears[2].bias
+    assert_close(y, yr, 1e-5, "mlp fwd")
+    gy = torch.randn_like(y)
+    gx, = torch.autograd.grad(y, x, gy, retain_graph=True)
+    gxr, = torch.autograd.grad(yr, x, gy)
+    assert_close(gx, gxr, 1e-4, "mlp dx")
+    with pytest.raises(ValueError):
+        mlpmod.MLP(0, 3, 3, 3)
+    d = dmod.Discriminator(7)
+    c = torch.rand(3, 7)
+    hp, hm = torch.randn(12, 7, requires_grad=True), torch.randn(12, 7)
+    out = d(c, hp, hm)
+    cx = c.repeat_interleave(4, 0)
+    refo = torch.cat([torch.nn.functional.bilinear(hp, cx, d.f_k.weight, d.f_k.bias),
+                      torch.nn.functional.bilinear(hm, cx, d.f_k.weight, d.f_k.bias)], 0)
+    assert_close(out, refo, 1e-5, "disc fwd")
+    go = torch.randn_like(out)
+    g1 = torch.autograd.grad(out, [hp, d.f_k.weight, d.f_k.bias], go, retain_graph=True)
+    g2 = torch.autograd.grad(refo, [hp, d.f_k.weight, d.f_k.bias], go)
+    for a, b in zip(g1, g2):
+        assert_close(a, b, 1e-4, "disc grads")
