@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the GIN + DGI training hot path (BASELINE.json metric: GIN train graphs/sec @400 ROIs).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]             # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]        # the reference's CPU path (ATen port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...            # one rank per GPU, NCCL
+
+A "step" is one pass of main.py:25-41 over one batch: batch selection, forward (GIN encoder + DGI
+scores), CrossEntropy + beta*BCEWithLogits, zero_grad, backward, Adam step.
+Workload at N=1: BASELINE.json configs[1] - 5-layer GIN, hidden 64, 1024 synthetic Schaefer-400
+thresholded-FC graphs per batch. At N>1 every rank trains on its own 1024-graph batch (weak scaling,
+global batch 1024*N) with BatchNorm statistics, DGI negatives and gradients synchronised over NCCL.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "gin_train_graphs_per_sec_400roi"
+UNIT = "graphs/s"
+N_ROIS, HIDDEN, LAYERS, MLP_LAYERS, BETA, LR = 400, 64, 5, 2, 0.05, 0.005
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="graphs per GPU per step")
+    ap.add_argument("--learn-eps", action="store_true", help="graphcnn.py next_layer_eps path (default: main.py's default, False)")
+    ap.add_argument("--cpu-batch", type=int, default=32, help="graphs per step of the CPU baseline sample (configs[0])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="also print the per-kernel time table to stderr")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {"workload": "GIN 5-layer hidden 64 + DGI, synthetic Schaefer-400 top-30%% FC graphs, "
+                        "batch %d graphs/GPU, sum/sum pooling, learn_eps=%s, Adam" % (args.batch, args.learn_eps),
+            "graphs_per_gpu": args.batch, "global_batch": args.batch * world, "n_rois": N_ROIS,
+            "edges_per_graph": 47600, "hidden": HIDDEN, "layers": LAYERS, "parallelism": "dp%d" % world,
+            "l2_policy": "inputs_larger_than_l2 (per-step working set ~3 GB >> 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the reference's ATen path (oracle/aten_port.py), bounded sample
+# ------------------------------------------------------------------------------------------
+
+def cpu_reference_run(args, steps, warmup, graphs=None):
+    from oracle import aten_port
+    from graph_neural_mapping_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b = args.cpu_batch
+    if graphs is None:
+        graphs = synth.make_graphs_bulk(b, N_ROIS, 30, 256, seed0=99, device="cpu")
+    graphs = graphs[:b]
+    from graph_neural_mapping_b200.models import GIN_InfoMaxReg
+    torch.manual_seed(0)
+    init = GIN_InfoMaxReg(LAYERS, MLP_LAYERS, N_ROIS, HIDDEN, 2, 0.5, args.learn_eps, "sum", "sum", torch.device("cpu"))
+    st = aten_port.TrainState(init.state_dict(), lr=LR)
+    cfg = dict(num_layers=LAYERS, num_mlp_layers=MLP_LAYERS, learn_eps=args.learn_eps, graph_pooling_type="sum",
+               neighbor_pooling_type="sum")
+    np.random.seed(0)
+    for _ in range(warmup):
+        st.step(graphs, cfg, BETA, 0.5)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        st.step(graphs, cfg, BETA, 0.5)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return dict(value=b * steps / total, unit=UNIT, cores=cores, kind="port",
+                sample="%d steps of a %d-graph batch (BASELINE configs[0]) of the same synthetic Schaefer-400 graphs, "
+                       "oracle/aten_port.py = the reference's torch.spmm / nn.Bilinear / BatchNorm ATen path on CPU, "
+                       "%d threads" % (steps, b, cores)), total / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, sec_per_step = cpu_reference_run(args, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, max(1, args.gpus)), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# instrumentation
+# ------------------------------------------------------------------------------------------
+
+class OpTimer(object):
+    """Wraps the ops entry points with CUDA events on the launching stream."""
+
+    NAMES = ["csr_build", "csr_batch_gather", "aggregate", "dot_rows", "scatter_rows_add", "linear", "linear_wgrad",
+             "col_stats", "bn_finalize", "bn_eval_affine", "bn_relu_readout", "relu_bn_bwd_reduce", "bn_bwd_apply",
+             "gather_nf_rows", "dgi_score_fwd", "dgi_score_bwd", "rowdot_score"]
+
+    def __init__(self, ops):
+        self.ops = ops
+        self.orig = {}
+        self.records = []
+
+    def _wrap(self, name, fn):
+        def wrapped(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn(*a, **k)
+            e.record()
+            tag = name
+            if name == "aggregate":
+                tag = "aggregate[F=%d%s]" % (a[4].shape[1], ",gather0" if a[3] is not None else "")
+            elif name in ("linear", "linear_wgrad"):
+                tag = "%s[%dx%d]" % (name, a[0].shape[1], a[1].shape[1] if a[1] is not None else 0)
+            self.records.append((tag, s, e))
+            return out
+        return wrapped
+
+    def __enter__(self):
+        for n in self.NAMES:
+            self.orig[n] = getattr(self.ops, n)
+            setattr(self.ops, n, self._wrap(n, self.orig[n]))
+        return self
+
+    def __exit__(self, *exc):
+        for n, f in self.orig.items():
+            setattr(self.ops, n, f)
+
+    def table(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for tag, s, e in self.records:
+            t = s.elapsed_time(e)
+            c = agg.setdefault(tag, [0, 0.0])
+            c[0] += 1
+            c[1] += t
+        return agg
+
+
+class ClockSampler(object):
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------
+
+def run_b200(args):
+    from graph_neural_mapping_b200 import dist as gdist, ops, synth
+    from graph_neural_mapping_b200.models import GIN_InfoMaxReg
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    comm, local_rank = gdist.init_from_env()
+    world, rank = comm.world, comm.rank
+    if world != max(1, args.gpus) and world > 1:
+        raise RuntimeError("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    torch.manual_seed(0)
+    np.random.seed(1234)                     # same numpy stream on every rank (perm / batch selection)
+    pool = synth.make_graphs_bulk(B, N_ROIS, 30, 256, seed0=1000 * rank, device=dev)
+    model = GIN_InfoMaxReg(LAYERS, MLP_LAYERS, N_ROIS, HIDDEN, 2, 0.5, args.learn_eps, "sum", "sum", dev).to(dev)
+    model.set_comm(comm)
+    opt = torch.optim.Adam(model.parameters(), lr=LR)
+    c_crit, d_crit = torch.nn.CrossEntropyLoss(), torch.nn.BCEWithLogitsLoss()
+    labels_pool = torch.tensor([g.label for g in pool], device=dev)
+    d_labels_dev = torch.cat([torch.ones(B * N_ROIS, 1), torch.zeros(B * N_ROIS, 1)], 0).to(dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        """main.py:25-41 with every per-step input already on the device (warm graph store)."""
+        sel = np.random.permutation(len(pool))[:B]
+        batch = [pool[i] for i in sel]
+        c_logit, d_logit = model(batch)
+        c_labels = labels_pool[torch.from_numpy(sel).to(dev)]
+        loss = c_crit(c_logit, c_labels) + BETA * d_crit(d_logit, d_labels_dev)
+        opt.zero_grad()
+        loss.backward()
+        gdist.average_gradients(model, comm)
+        opt.step()
+        return loss
+
+    def step_e2e():
+        """The literal main.py:25-43 loop body: labels built on the host and copied every step, loss read back."""
+        sel = np.random.permutation(len(pool))[:B]
+        batch = [pool[i] for i in sel]
+        c_logit, d_logit = model(batch)
+        c_labels = torch.LongTensor([g.label for g in batch]).to(dev)
+        d_labels = torch.cat([torch.ones(B * N_ROIS, 1), torch.zeros(B * N_ROIS, 1)], 0).to(dev)
+        loss = c_crit(c_logit, c_labels) + BETA * d_crit(d_logit, d_labels)
+        opt.zero_grad()
+        loss.backward()
+        gdist.average_gradients(model, comm)
+        opt.step()
+        return float(loss.detach().cpu().numpy())
+
+    model.train()
+    # ---- value: device-resident inputs ---------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ops.LAUNCHES[0]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = ops.LAUNCHES[0] - launches0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = B * world * args.steps / (elapsed_ms / 1e3)
+
+    # ---- per-kernel times, live, on the launching stream ------------------------------------
+    with OpTimer(ops) as timer:
+        for _ in range(2):
+            step_resident()
+        table = timer.table()
+    n_prof = 2
+    bs = model._structure(pool)
+    m, nnz = bs.n_rows, bs.nnz
+    agg_key = "aggregate[F=%d]" % HIDDEN
+    agg_bytes = 4.0 * nnz + 4.0 * (m + 1) + 2 * 4.0 * m * HIDDEN          # AGG(l>=1)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    roof = None
+    if agg_key in table:
+        cnt, tot_ms = table[agg_key]
+        avg_s = tot_ms / cnt / 1e3
+        ach = agg_bytes / avg_s / 1e9
+        step_ms = sum(v[1] for v in table.values()) / n_prof
+        roof = {"bound": "hbm", "kernel": "aggregate_kernel<4,16> (neighbour SpMM, F=64)", "achieved": ach,
+                "peak": peak_gbs, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak_gbs, "traffic": None,
+                "algorithmic_bytes_per_launch": agg_bytes, "avg_launch_us": avg_s * 1e6, "launches_per_step": cnt / n_prof,
+                "share_of_kernel_time": (tot_ms / n_prof) / step_ms}
+    breakdown = {k: {"launches_per_step": v[0] / n_prof, "ms_per_step": v[1] / n_prof} for k, v in
+                 sorted(table.items(), key=lambda kv: -kv[1][1])}
+    if args.breakdown and rank == 0:
+        for k, v in breakdown.items():
+            sys.stderr.write("%-34s %6.1f launches  %9.3f ms/step\n" % (k, v["launches_per_step"], v["ms_per_step"]))
+
+    # ---- e2e: host graph lists through model(batch_graph), H2D/D2H inside the timed region -------
+    e2e = None
+    if not args.no_e2e:
+        def timed_e2e(cold, steps, warm):
+            model.cache_graphs = not cold
+            for _ in range(warm):
+                step_e2e()
+            barrier()
+            store = model._graph_store()
+            h0 = store.h2d_bytes
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                step_e2e()
+            barrier()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            h2d = (store.h2d_bytes - h0) / steps + 8 * B + 4 * 2 * B * N_ROIS
+            model.cache_graphs = True
+            return B * world * steps / float(tt.item()), int(h2d)
+        v_cold, h2d_cold = timed_e2e(True, max(2, min(args.steps, 5)), 1)
+        v_warm, h2d_warm = timed_e2e(False, args.steps, 2)
+        e2e = {"value": v_cold, "unit": UNIT, "h2d_bytes_per_step": h2d_cold, "d2h_bytes_per_step": 4,
+               "what": "model(batch_graph) on host S2VGraph lists with the device graph cache DISABLED: every step "
+                       "ships the batch's int64 edge lists, rebuilds the CSR, copies labels in and the loss out "
+                       "(what the reference does per step, graphcnn.py:195-206)",
+               "cached": {"value": v_warm, "unit": UNIT, "h2d_bytes_per_step": h2d_warm, "d2h_bytes_per_step": 4,
+                          "what": "same call with the per-graph CSR cache warm (steady state of main.py's epochs)"}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _ = cpu_reference_run(args, 3, 1, graphs=pool)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, world), "clocks": clocks, "gpu_launches": launches,
+                "e2e": e2e, "roofline": roof, "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -12,6 +12,7 @@ import torch
 from . import lib as _libmod
 
 _state = {"device": None}
+LAUNCHES = [0]      # kernels enqueued through this module (one per entry-point call)
 
 
 def _lib():
@@ -23,6 +24,7 @@ def _stream(t):
     if _state["device"] != dev:
         _libmod.check(_lib().gnm_set_device(dev), "gnm_set_device")
         _state["device"] = dev
+    LAUNCHES[0] += 1
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 

@@ -78,7 +78,8 @@ def aggregate(rowptr, colidx, src, src_map, dst, mode, eps, bias=None):
         s = s[src_map.long()]
     deg = a.sum(1, keepdim=True)
     if mode == 2:
-        out = a @ (s / deg)
+        # an isolated node (deg 0) is never gathered, so its scale is irrelevant
+        out = a @ (s / deg.clamp(min=1))
     else:
         out = a @ s
         if mode == 1:

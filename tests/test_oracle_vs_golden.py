@@ -101,3 +101,29 @@ def test_eval_and_saliency_match_reference(name):
         n0 = g.node_counts[0]
         assert_close(s[:n0], g.z["saliency/g0_c1"], TOL_GRAD, "batched saliency g0")
         assert_close(s[n0:], g.z["saliency/g1_c1"], TOL_GRAD, "batched saliency g1")
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "max" not in n])
+def test_aten_port_matches_reference(name):
+    """oracle/aten_port.py (the CPU baseline that bench.py times) against the reference's outputs."""
+    from oracle import aten_port
+    g = Golden(name)
+    sd = {}
+    for k, v in g.state_dict().items():
+        sd[k] = v.clone().requires_grad_(True) if (v.is_floating_point() and "running_" not in k) else v.clone()
+    seed = 4242 + {"tiny_eps_sum": 100, "tiny_noeps_sum": 100, "tiny_eps_avg": 300, "tiny_noeps_avg": 300, "tiny_mlp1": 500,
+                   "tiny_mlp3": 500, "mid_eps_sum_h64": 900, "schaefer400_noeps": 0, "schaefer400_eps": 10}[name]
+    np.random.seed(seed)
+    graphs = g.graphs()
+    c_logit, d_logit, g_f = aten_port.forward(sd, graphs, g.cfg, True)
+    assert_close(c_logit, g.z["train/c_logit"], 1e-6, "c_logit")
+    assert_close(d_logit, g.z["train/d_logit"], 1e-6, "d_logit")
+    labels = torch.LongTensor(g.labels)
+    n = len(graphs) * g.cfg["N"]
+    d_labels = torch.cat([torch.ones(n, 1), torch.zeros(n, 1)], 0)
+    loss = torch.nn.functional.cross_entropy(c_logit, labels) + g.cfg["beta"] * \
+        torch.nn.functional.binary_cross_entropy_with_logits(d_logit, d_labels)
+    loss.backward()
+    floor = grad_floor(g.group("grad/"))
+    for k, v in g.group("grad/").items():
+        assert_close(sd[k].grad, v, 1e-5, "grad " + k, floor=floor)
