@@ -25,6 +25,10 @@ from . import ops as _ops
 from . import dist as _dist
 
 
+DENSE_MIN_DENSITY = 0.04      # use the tensor-core block kernel when nnz >= this fraction of sum N_g^2
+FORCE_CSR_AGGREGATE = False    # test / A-B switch: always take the CSR gather kernel
+
+
 def require_cuda(dev):
     if dev.type != "cuda":
         raise RuntimeError("GIN_InfoMaxReg runs on the libgnm CUDA kernels only (no CPU fallback): "
@@ -36,7 +40,7 @@ def require_cuda(dev):
 # ------------------------------------------------------------------------------------------
 
 class _StoredGraph(object):
-    __slots__ = ("graph", "n", "nnz", "rp_addr", "ci_addr", "tag_addr", "onehot", "feat_dim", "keep")
+    __slots__ = ("graph", "n", "nnz", "rp_addr", "ci_addr", "tag_addr", "bm_addr", "onehot", "feat_dim", "keep")
 
 
 def _onehot_tags(feats, cache):
@@ -112,8 +116,16 @@ class GraphStore(object):
             tag_list.append(t if t is not None else torch.zeros(len(g.g), dtype=torch.int32))
         tags_d = torch.cat(tag_list).to(dev) if total_nodes > 0 else torch.zeros(0, dtype=torch.int32, device=dev)
         self.h2d_bytes += total_nodes * 4
-        keep = (rowptr, colidx, tags_d)
-        rp0, ci0, tg0 = rowptr.data_ptr(), colidx.data_ptr(), tags_d.data_ptr()
+        # adjacency bitmaps for the tensor-core aggregation (duplicate-free graphs only)
+        words = np.array([n * ((n + 31) // 32) for n in counts], dtype=np.int64)
+        bm_off = np.zeros(len(new) + 1, dtype=np.int64)
+        np.cumsum(words, out=bm_off[1:])
+        bm_off_d = torch.from_numpy(bm_off).to(dev)
+        bitmap, dup = _ops.bitmap_build(rowptr, colidx, node_off_d, bm_off_d, len(new), int(bm_off[-1]))
+        dup_h = dup.cpu().numpy()
+        self.h2d_bytes += bm_off.nbytes
+        keep = (rowptr, colidx, tags_d, bitmap)
+        rp0, ci0, tg0, bm0 = rowptr.data_ptr(), colidx.data_ptr(), tags_d.data_ptr(), bitmap.data_ptr()
         for i, g in enumerate(new):
             e = _StoredGraph()
             e.graph = g                                  # pins the id
@@ -123,6 +135,7 @@ class GraphStore(object):
             e.rp_addr = rp0 + 4 * int(node_off[i])
             e.ci_addr = ci0 + 4 * nnz_base
             e.tag_addr = tg0 + 4 * int(node_off[i])
+            e.bm_addr = (bm0 + 4 * int(bm_off[i])) if int(dup_h[i]) == 0 else 0
             e.onehot = onehot[i]
             e.feat_dim = int(g.node_features.shape[1])
             e.keep = keep
@@ -134,12 +147,13 @@ class GraphStore(object):
         b = len(ent)
         counts = np.fromiter((e.n for e in ent), dtype=np.int64, count=b)
         nnzs = np.fromiter((e.nnz for e in ent), dtype=np.int64, count=b)
-        packed = np.empty(4 * b + 1, dtype=np.int64)
+        packed = np.empty(5 * b + 1, dtype=np.int64)
         packed[0:b] = [e.rp_addr for e in ent]
         packed[b:2 * b] = [e.ci_addr for e in ent]
         packed[2 * b:3 * b] = [e.tag_addr for e in ent]
         packed[3 * b] = 0
         np.cumsum(nnzs, out=packed[3 * b + 1:4 * b + 1])
+        packed[4 * b + 1:5 * b + 1] = [e.bm_addr for e in ent]
         node_off = np.zeros(b + 1, dtype=np.int32)
         np.cumsum(counts, out=node_off[1:])
         m, nnz = int(node_off[-1]), int(packed[4 * b])
@@ -160,6 +174,13 @@ class GraphStore(object):
         bs.onehot = all(e.onehot for e in ent)
         bs.tags = tags if bs.onehot else None
         bs.feat_dim = ent[0].feat_dim if b > 0 else 0
+        bs.n_max = int(counts.max()) if b > 0 else 0
+        # tensor-core path: every graph has a bitmap (no duplicate edges) and the blocks are dense enough
+        # that N^2 tensor-core MACs beat gathering nnz rows through L2 (break-even ~3-4 % density)
+        has_bm = b > 0 and all(e.bm_addr != 0 for e in ent)
+        dense_enough = nnz >= DENSE_MIN_DENSITY * float((counts.astype(np.float64) ** 2).sum())
+        bs.bitmap_addr = packed_d[4 * b + 1:5 * b + 1] if (has_bm and dense_enough) else None
+        bs.has_isolated = None
         return bs
 
 
@@ -167,7 +188,20 @@ class BatchStructure(object):
     """Adj_block (graphcnn.py:84-106) as int32 CSR + graph_pool (graphcnn.py:109-134) as node offsets."""
 
     __slots__ = ("n_graphs", "n_rows", "nnz", "node_counts", "node_off", "rowptr", "colidx", "uniform_n", "onehot",
-                 "tags", "feat_dim", "pool_scale")
+                 "tags", "feat_dim", "pool_scale", "n_max", "bitmap_addr", "has_isolated")
+
+    def aggregate(self, src, src_map, dst, mode, eps, bias=None):
+        """graphcnn.py:154-161 / :178-182 (and the transpose for backward): tensor-core dense-block kernel when
+        the batch qualifies, CSR warp-per-row kernel otherwise."""
+        if self.bitmap_addr is not None and not FORCE_CSR_AGGREGATE and _ops.dense_aggregate_ok(src, dst, bias):
+            if mode != 0 and self.has_isolated is None:
+                # average pooling divides by the degree: an isolated node yields 0/0 = NaN in the reference, and a
+                # NaN row would poison its whole dense block (0 * NaN); keep such batches on the gather kernel
+                self.has_isolated = bool(((self.rowptr[1:] - self.rowptr[:-1]) == 0).any())
+            if mode == 0 or not self.has_isolated:
+                return _ops.aggregate_dense(self.bitmap_addr, self.node_off, self.rowptr, self.n_graphs, self.n_max,
+                                            src, src_map, dst, mode, eps, bias)
+        return _ops.aggregate(self.rowptr, self.colidx, src, src_map, dst, mode, eps, bias)
 
     def set_pooling(self, graph_pooling_type, device):
         if graph_pooling_type == "average":
@@ -278,13 +312,13 @@ def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm):
                     # first layer as a row gather of W1^T (X_concat is one-hot): no dense X, no GEMM
                     w1t = u.w.detach().t().contiguous()
                     sv.w1t = w1t
-                    _ops.aggregate(bs.rowptr, bs.colidx, w1t, bs.tags, u.z, 1 if average else 0, eps_l, u.b)
+                    bs.aggregate(w1t, bs.tags, u.z, 1 if average else 0, eps_l, u.b)
                     _ops.col_stats(u.z, stats)
                     u.x_in = None
                 else:
                     src = x_dense if layer == 0 else h_prev
                     pooled = torch.empty(M, src.shape[1], dtype=torch.float32, device=dev)
-                    _ops.aggregate(bs.rowptr, bs.colidx, src, None, pooled, 1 if average else 0, eps_l, None)
+                    bs.aggregate(src, None, pooled, 1 if average else 0, eps_l, None)
                     _ops.linear(pooled, u.w, False, u.b, None, None, u.z, stats)
                     u.x_in = pooled
             else:
@@ -403,7 +437,7 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
             if layer == 0 and sv.use_gather0:
                 # z0 = Agg(W1^T[tags]) + b:  dW1^T[t] = sum_{tags[r]=t} (Agg^T dz)[r]
                 g_agg = torch.empty(M, n_out, dtype=torch.float32, device=dev)
-                _ops.aggregate(bs.rowptr, bs.colidx, dz_u, None, g_agg, bwd_mode, eps_l, None)
+                bs.aggregate(dz_u, None, g_agg, bwd_mode, eps_l, None)
                 dw1t = torch.zeros(u.w.shape[1], n_out, dtype=torch.float32, device=dev)
                 _ops.scatter_rows_add(g_agg, bs.tags, dw1t)
                 dw = dw1t.t().contiguous()
@@ -424,7 +458,7 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                         _ops.dot_rows(dp, src, None, d_eps[layer:layer + 1])
                     if layer > 0 or need_x_grad:
                         d_prev = torch.empty(M, u.w.shape[1], dtype=torch.float32, device=dev)
-                        _ops.aggregate(bs.rowptr, bs.colidx, dp, None, d_prev, bwd_mode, eps_l, None)
+                        bs.aggregate(dp, None, d_prev, bwd_mode, eps_l, None)
                         if layer > 0:
                             d_h = d_prev
                         else:

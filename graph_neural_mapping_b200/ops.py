@@ -100,6 +100,34 @@ def aggregate(rowptr, colidx, src, src_map, dst, mode, eps, bias=None):
     return dst
 
 
+def bitmap_build(rowptr, colidx, node_off, bitmap_off, n_graphs, total_words):
+    """Chunk CSR (local column ids) -> per-graph bitmaps (uint32 words as int32) + per-graph duplicate flags."""
+    dev = rowptr.device
+    bitmap = torch.empty(max(total_words, 1), dtype=torch.int32, device=dev)
+    dup = torch.zeros(max(n_graphs, 1), dtype=torch.int32, device=dev)
+    _libmod.check(_lib().gnm_bitmap_build(_ptr(rowptr, torch.int32), _ptr(colidx, torch.int32),
+                                          _ptr(node_off, torch.int32), _ptr(bitmap_off, torch.int64), n_graphs,
+                                          _ptr(bitmap), _ptr(dup), _stream(rowptr)), "gnm_bitmap_build")
+    return bitmap, dup
+
+
+def aggregate_dense(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, src_map, dst, mode, eps, bias=None):
+    sp, lds = _mat(src)
+    dp, ldd = _mat(dst)
+    _libmod.check(_lib().gnm_aggregate_dense(_ptr(bitmap_addr, torch.int64), _ptr(node_off, torch.int32),
+                                             _ptr(rowptr, torch.int32), n_graphs, n_max, sp, lds,
+                                             _ptr(src_map, torch.int32) if src_map is not None else None, dp, ldd,
+                                             int(dst.shape[1]), int(mode), _ptr(eps, torch.float32),
+                                             _ptr(bias, torch.float32), _stream(dst)), "gnm_aggregate_dense")
+    return dst
+
+
+def dense_aggregate_ok(src, dst, bias=None):
+    """Alignment contract of gnm_aggregate_dense (float4 row loads, float2 stores)."""
+    return (dst.shape[1] % 4 == 0 and src.stride(0) % 4 == 0 and dst.stride(0) % 2 == 0 and
+            src.data_ptr() % 16 == 0 and dst.data_ptr() % 16 == 0 and (bias is None or bias.data_ptr() % 16 == 0))
+
+
 def dot_rows(a, b, b_map, out):
     ap, lda = _mat(a)
     bp, ldb = _mat(b)

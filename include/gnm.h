@@ -32,7 +32,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 3
+#define GNM_ABI_VERSION 4
 
 typedef void* gnm_stream_t;
 
@@ -83,6 +83,24 @@ int gnm_aggregate(const int32_t* rowptr, const int32_t* colidx, int n_rows,
                   const float* src, int64_t ld_src, const int32_t* src_map,
                   float* dst, int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
                   gnm_stream_t stream);
+
+/* Per-graph adjacency bitmaps for the tensor-core aggregation: for every graph of a store chunk, row r of
+ * its N x ceil(N/32)-word bitmap (at bitmap + bitmap_off[g], word offsets) gets bit c set for every listed
+ * neighbour c (rowptr/colidx: the chunk's CSR with LOCAL column ids from gnm_csr_build). dup_flags[g] is set
+ * to 1 if a column repeats within a row (a bitmap cannot hold multiplicity: such graphs stay on the CSR path). */
+int gnm_bitmap_build(const int32_t* rowptr, const int32_t* colidx, const int32_t* node_off,
+                     const int64_t* bitmap_off, int n_graphs, uint32_t* bitmap, int32_t* dup_flags,
+                     gnm_stream_t stream);
+
+/* Same contract as gnm_aggregate (graphcnn.py:154-161 / :178-182 and its transpose), computed per graph as a
+ * dense 0/1 block product on the tensor cores: dst_g = A_g . src_g with A_g expanded from the graph's bitmap
+ * (bitmap_addr[g]: device address) and src split into three bf16 planes (exact for fp32) with fp32
+ * accumulation. rowptr (batch CSR row pointers) supplies the degrees for mode 1 / 2 and may be NULL for mode 0.
+ * Needs n_feat % 4 == 0 and 16-byte aligned rows (else GNM_ERR_ALIGN: use gnm_aggregate). */
+int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr,
+                        int n_graphs, int n_max, const float* src, int64_t ld_src, const int32_t* src_map,
+                        float* dst, int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
+                        gnm_stream_t stream);
 
 /* d eps[layer] = sum_i <a[i], b[map(i)]> (autograd of graphcnn.py:161). out: double[1], accumulated. */
 int gnm_dot_rows(const float* a, int64_t lda, const float* b, int64_t ldb, const int32_t* b_map,

@@ -92,6 +92,55 @@ def aggregate(rowptr, colidx, src, src_map, dst, mode, eps, bias=None):
     return dst
 
 
+def bitmap_build(rowptr, colidx, node_off, bitmap_off, n_graphs, total_words):
+    rp, ci, no, bo = rowptr.numpy(), colidx.numpy(), node_off.numpy(), bitmap_off.numpy()
+    bm = np.zeros(max(total_words, 1), dtype=np.uint32)
+    dup = np.zeros(max(n_graphs, 1), dtype=np.int32)
+    for g in range(n_graphs):
+        n = int(no[g + 1] - no[g])
+        w = (n + 31) // 32
+        for r in range(n):
+            cols = ci[rp[no[g] + r]:rp[no[g] + r + 1]]
+            if len(np.unique(cols)) != len(cols):
+                dup[g] = 1
+            for c in cols:
+                bm[bo[g] + r * w + (c >> 5)] |= np.uint32(1) << np.uint32(c & 31)
+    return torch.from_numpy(bm.view(np.int32)), torch.from_numpy(dup)
+
+
+def dense_aggregate_ok(src, dst, bias=None):
+    return dst.shape[1] % 4 == 0
+
+
+def aggregate_dense(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, src_map, dst, mode, eps, bias=None):
+    """Contract of gnm_aggregate_dense: the adjacency is read from the per-graph bitmaps."""
+    no = node_off.numpy()
+    m = dst.shape[0]
+    a = torch.zeros(m, m, dtype=torch.float64)
+    for g in range(n_graphs):
+        n = int(no[g + 1] - no[g])
+        w = (n + 31) // 32
+        words = _i32_at(bitmap_addr[g], n * w).view(np.uint32).reshape(n, w)
+        bits = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(n, w * 32)[:, :n]
+        a[no[g]:no[g] + n, no[g]:no[g] + n] = torch.from_numpy(bits.astype(np.float64))
+    s = src.double()
+    if src_map is not None:
+        s = s[src_map.long()]
+    deg = a.sum(1, keepdim=True)
+    if mode == 2:
+        out = a @ (s / deg.clamp(min=1))
+    else:
+        out = a @ s
+        if mode == 1:
+            out = out / deg
+    if eps is not None:
+        out = out + (1 + eps.double()) * s
+    if bias is not None:
+        out = out + bias.double()
+    dst.copy_(out.float())
+    return dst
+
+
 def dot_rows(a, b, b_map, out):
     bb = b if b_map is None else b[b_map.long()]
     out += (a.double() * bb.double()).sum()

@@ -215,3 +215,17 @@ def test_mlp_and_discriminator_standalone():
     g2 = torch.autograd.grad(refo, [hp, d.f_k.weight, d.f_k.bias], go)
     for a, b in zip(g1, g2):
         assert_close(a, b, 1e-4, "disc grads")
+
+
+def test_csr_and_dense_aggregation_paths_agree(monkeypatch):
+    g = Golden("tiny_eps_avg")
+    graphs = g.graphs()
+    m1, m2 = build_model(g), build_model(g)
+    c1, d1, _ = train_step(m1, graphs, g, 9)
+    assert m1._structure(graphs).bitmap_addr is not None         # 30 % dense -> tensor-core path selected
+    monkeypatch.setattr(engine, "FORCE_CSR_AGGREGATE", True)
+    c2, d2, _ = train_step(m2, graphs, g, 9)
+    assert_close(c2, c1.detach(), 1e-5, "c_logit")
+    assert_close(d2, d1.detach(), 1e-5, "d_logit")
+    monkeypatch.setattr(engine, "DENSE_MIN_DENSITY", 0.9)
+    assert m2._structure(graphs).bitmap_addr is None             # sparse batches stay on the CSR kernel
