@@ -132,9 +132,9 @@ def test_dropout_training_uses_torch_rng_and_keeps_shapes():
     torch.manual_seed(0)
     b, _ = m(graphs)
     # same torch seed -> same dropout mask (exact zeros coincide); the BatchNorm statistics are merged with
-    # double-precision atomics, so the surviving values agree to rounding, not bitwise
+    # atomics (fp32 within a CTA, fp64 across CTAs), so the surviving values agree to rounding, not bitwise
     assert torch.equal(a == 0, b == 0) and bool((a == 0).any()) and tuple(a.shape) == (len(graphs), 2)
-    assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(a, b, rtol=1e-3, atol=1e-4)
 
 
 def test_adam_training_follows_reference_for_a_few_steps():
