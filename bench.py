@@ -285,10 +285,14 @@ def run_b200(args):
     value = B * world * args.steps / (elapsed_ms / 1e3)
 
     # ---- per-kernel times, live, on the launching stream ------------------------------------
+    graphs_on = model.use_cuda_graphs
+    model.use_cuda_graphs = False            # per-kernel events need the eager (kernel-by-kernel) path
+    step_resident()
     with OpTimer(ops) as timer:
         for _ in range(2):
             step_resident()
         table = timer.table()
+    model.use_cuda_graphs = graphs_on
     n_prof = 2
     bs = model._structure(pool)
     m, nnz = bs.n_rows, bs.nnz
@@ -358,7 +362,8 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(args, world), "clocks": clocks, "gpu_launches": launches,
+                "config": dict(workload_config(args, world), cuda_graphs=bool(model.use_cuda_graphs)),
+                "clocks": clocks, "gpu_launches": launches,
                 "e2e": e2e, "roofline": roof, "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown}
         print(json.dumps(line))
     if world > 1:

@@ -40,7 +40,8 @@ def require_cuda(dev):
 # ------------------------------------------------------------------------------------------
 
 class _StoredGraph(object):
-    __slots__ = ("graph", "n", "nnz", "rp_addr", "ci_addr", "tag_addr", "bm_addr", "onehot", "feat_dim", "keep")
+    __slots__ = ("graph", "n", "nnz", "rp_addr", "ci_addr", "tag_addr", "bm_addr", "onehot", "feat_dim", "keep",
+                 "isolated")
 
 
 def _onehot_tags(feats, cache):
@@ -123,6 +124,11 @@ class GraphStore(object):
         bm_off_d = torch.from_numpy(bm_off).to(dev)
         bitmap, dup = _ops.bitmap_build(rowptr, colidx, node_off_d, bm_off_d, len(new), int(bm_off[-1]))
         dup_h = dup.cpu().numpy()
+        # graphs holding a node without any neighbour (average pooling gives 0/0 there, graphcnn.py:157-158)
+        iso_h = np.zeros(len(new), dtype=bool)
+        zero_rows = torch.nonzero((rowptr[1:] - rowptr[:-1]) == 0).flatten().cpu().numpy()
+        if zero_rows.size:
+            iso_h[np.searchsorted(node_off, zero_rows, side="right") - 1] = True
         self.h2d_bytes += bm_off.nbytes
         keep = (rowptr, colidx, tags_d, bitmap)
         rp0, ci0, tg0, bm0 = rowptr.data_ptr(), colidx.data_ptr(), tags_d.data_ptr(), bitmap.data_ptr()
@@ -136,12 +142,14 @@ class GraphStore(object):
             e.ci_addr = ci0 + 4 * nnz_base
             e.tag_addr = tg0 + 4 * int(node_off[i])
             e.bm_addr = (bm0 + 4 * int(bm_off[i])) if int(dup_h[i]) == 0 else 0
+            e.isolated = bool(iso_h[i])
             e.onehot = onehot[i]
             e.feat_dim = int(g.node_features.shape[1])
             e.keep = keep
             self.entries[id(g)] = e
 
-    def assemble(self, graphs):
+    def assemble_host(self, graphs):
+        """Host half of batch assembly: per-slot addresses / offsets as numpy, plus batch-level flags."""
         self.ensure(graphs)
         ent = [self.entries[id(g)] for g in graphs]
         b = len(ent)
@@ -159,29 +167,52 @@ class GraphStore(object):
         m, nnz = int(node_off[-1]), int(packed[4 * b])
         if nnz >= 2 ** 31:
             raise RuntimeError("batch adjacency has %d entries; int32 CSR holds < 2^31" % nnz)
-        dev = self.device
-        packed_d = torch.from_numpy(packed).to(dev, non_blocking=True)
-        node_off_d = torch.from_numpy(node_off).to(dev, non_blocking=True)
-        self.h2d_bytes += packed.nbytes + node_off.nbytes
-        rowptr, colidx, tags = _ops.csr_batch_gather(packed_d[0:b], packed_d[b:2 * b], packed_d[2 * b:3 * b],
-                                                     node_off_d, packed_d[3 * b:4 * b + 1], b, m, nnz)
-        bs = BatchStructure()
-        bs.n_graphs, bs.n_rows, bs.nnz = b, m, nnz
-        bs.node_counts = counts
-        bs.node_off = node_off_d
-        bs.rowptr, bs.colidx = rowptr, colidx
-        bs.uniform_n = int(counts[0]) if b > 0 and bool((counts == counts[0]).all()) else None
-        bs.onehot = all(e.onehot for e in ent)
-        bs.tags = tags if bs.onehot else None
-        bs.feat_dim = ent[0].feat_dim if b > 0 else 0
-        bs.n_max = int(counts.max()) if b > 0 else 0
+        h = _HostBatch()
+        h.b, h.m, h.nnz, h.packed, h.node_off, h.counts = b, m, nnz, packed, node_off, counts
+        h.uniform_n = int(counts[0]) if b > 0 and bool((counts == counts[0]).all()) else None
+        h.onehot = all(e.onehot for e in ent)
+        h.feat_dim = ent[0].feat_dim if b > 0 else 0
+        h.n_max = int(counts.max()) if b > 0 else 0
         # tensor-core path: every graph has a bitmap (no duplicate edges) and the blocks are dense enough
         # that N^2 tensor-core MACs beat gathering nnz rows through L2 (break-even ~3-4 % density)
         has_bm = b > 0 and all(e.bm_addr != 0 for e in ent)
         dense_enough = nnz >= DENSE_MIN_DENSITY * float((counts.astype(np.float64) ** 2).sum())
-        bs.bitmap_addr = packed_d[4 * b + 1:5 * b + 1] if (has_bm and dense_enough) else None
-        bs.has_isolated = None
+        h.dense = bool(has_bm and dense_enough)
+        h.has_isolated = any(e.isolated for e in ent)
+        return h
+
+    def assemble_device(self, h, packed_d, node_off_d, nnz_capacity=None):
+        """Device half: gather the stored CSRs into the batch CSR (one kernel)."""
+        b = h.b
+        rowptr, colidx, tags = _ops.csr_batch_gather(packed_d[0:b], packed_d[b:2 * b], packed_d[2 * b:3 * b],
+                                                     node_off_d, packed_d[3 * b:4 * b + 1], b, h.m,
+                                                     h.nnz if nnz_capacity is None else nnz_capacity)
+        bs = BatchStructure()
+        bs.n_graphs, bs.n_rows, bs.nnz = b, h.m, h.nnz
+        bs.node_counts = h.counts
+        bs.node_off = node_off_d
+        bs.rowptr, bs.colidx = rowptr, colidx
+        bs.uniform_n = h.uniform_n
+        bs.onehot = h.onehot
+        bs.tags = tags if h.onehot else None
+        bs.feat_dim = h.feat_dim
+        bs.n_max = h.n_max
+        bs.bitmap_addr = packed_d[4 * b + 1:5 * b + 1] if h.dense else None
+        bs.has_isolated = h.has_isolated
         return bs
+
+    def assemble(self, graphs):
+        h = self.assemble_host(graphs)
+        dev = self.device
+        packed_d = torch.from_numpy(h.packed).to(dev, non_blocking=True)
+        node_off_d = torch.from_numpy(h.node_off).to(dev, non_blocking=True)
+        self.h2d_bytes += h.packed.nbytes + h.node_off.nbytes
+        return self.assemble_device(h, packed_d, node_off_d)
+
+
+class _HostBatch(object):
+    __slots__ = ("b", "m", "nnz", "packed", "node_off", "counts", "uniform_n", "onehot", "feat_dim", "n_max", "dense",
+                 "has_isolated")
 
 
 class BatchStructure(object):
@@ -194,10 +225,8 @@ class BatchStructure(object):
         """graphcnn.py:154-161 / :178-182 (and the transpose for backward): tensor-core dense-block kernel when
         the batch qualifies, CSR warp-per-row kernel otherwise."""
         if self.bitmap_addr is not None and not FORCE_CSR_AGGREGATE and _ops.dense_aggregate_ok(src, dst, bias):
-            if mode != 0 and self.has_isolated is None:
-                # average pooling divides by the degree: an isolated node yields 0/0 = NaN in the reference, and a
-                # NaN row would poison its whole dense block (0 * NaN); keep such batches on the gather kernel
-                self.has_isolated = bool(((self.rowptr[1:] - self.rowptr[:-1]) == 0).any())
+            # average pooling divides by the degree: an isolated node yields 0/0 = NaN in the reference, and a
+            # NaN row would poison its whole dense block (0 * NaN); keep such batches on the gather kernel
             if mode == 0 or not self.has_isolated:
                 return _ops.aggregate_dense(self.bitmap_addr, self.node_off, self.rowptr, self.n_graphs, self.n_max,
                                             src, src_map, dst, mode, eps, bias)

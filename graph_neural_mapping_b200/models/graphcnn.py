@@ -17,8 +17,11 @@ import torch.nn.functional as F
 
 from .mlp import MLP
 from .discriminator import Discriminator
+import os
+
 from .. import dist as _dist
 from .. import engine as _engine
+from .. import graphed as _graphed
 
 
 class GIN_InfoMaxReg(nn.Module):
@@ -51,6 +54,10 @@ class GIN_InfoMaxReg(nn.Module):
         self._store = None
         self._comm = _dist.SINGLE
         self.cache_graphs = True        # keep per-graph CSRs resident on the device between calls
+        # training steps of a repeated shape are captured into CUDA graphs (graphed.py) after one eager warm-up
+        self.use_cuda_graphs = os.environ.get("GNM_CUDA_GRAPHS", "1") != "0"
+        self._plans = {}
+        self._warm = set()
 
     # ---- data-parallel hook (new; the reference is single-process) -------------------------
     def set_comm(self, comm):
@@ -66,7 +73,7 @@ class GIN_InfoMaxReg(nn.Module):
             self._store = _engine.GraphStore(dev, add_self_loops=not self.learn_eps)
         return self._store
 
-    def _structure(self, batch_graph):
+    def _host_batch(self, batch_graph):
         if self.neighbor_pooling_type == "max":
             raise NotImplementedError("neighbor_pooling_type='max' (graphcnn.py:55-81,137-143) is not on the "
                                       "B200 hot path yet; use 'sum' or 'average'")
@@ -75,9 +82,39 @@ class GIN_InfoMaxReg(nn.Module):
         store = self._graph_store()
         if not self.cache_graphs:
             store.clear()
-        bs = store.assemble(batch_graph)
-        bs.set_pooling(self.graph_pooling_type, self.eps.device)
+        return store.assemble_host(batch_graph)
+
+    def _structure(self, batch_graph, host_batch=None):
+        h = host_batch if host_batch is not None else self._host_batch(batch_graph)
+        store = self._graph_store()
+        dev = self.eps.device
+        packed_d = torch.from_numpy(h.packed).to(dev, non_blocking=True)
+        node_off_d = torch.from_numpy(h.node_off).to(dev, non_blocking=True)
+        store.h2d_bytes += h.packed.nbytes + h.node_off.nbytes
+        bs = store.assemble_device(h, packed_d, node_off_d)
+        bs.set_pooling(self.graph_pooling_type, dev)
         return bs
+
+    def _step_plan(self, h, n_global):
+        """The CUDA-graph plan for this training-step shape, or None (first sighting runs eagerly: it warms up
+        cuBLAS / NCCL and the allocator before capture)."""
+        if not (self.use_cuda_graphs and self.training and torch.is_grad_enabled() and h.onehot
+                and self.eps.device.type == "cuda"):
+            return None
+        key = _graphed.StepPlan._signature(h) + (n_global, self._comm.world)
+        plan = self._plans.get(key)
+        if plan is not None and not plan.compatible(h, n_global):
+            del self._plans[key]
+            plan = None
+        if plan is None:
+            if key not in self._warm:
+                self._warm.add(key)
+                return None
+            while len(self._plans) >= 2:
+                self._plans.pop(next(iter(self._plans)))
+            plan = _graphed.StepPlan(self, h, n_global, self._comm)
+            self._plans[key] = plan
+        return plan
 
     def _dense_features(self, batch_graph, bs):
         if bs.onehot:
@@ -99,15 +136,21 @@ class GIN_InfoMaxReg(nn.Module):
         comm = self._comm
         n_global = len(batch_graph) * comm.world
         rand_seq = np.random.permutation(n_global)          # graphcnn.py:199 (one numpy draw per call)
-        bs = self._structure(batch_graph)
-        if bs.uniform_n is None:
+        h = self._host_batch(batch_graph)
+        if h.uniform_n is None:
             # the reference's own DGI path needs equal-sized graphs (idx of graphcnn.py:198-201 and
             # the expand of discriminator.py:23-26 both assume M == B * N)
             raise RuntimeError("GIN_InfoMaxReg.forward needs graphs with the same number of nodes")
-        neg_idx = torch.from_numpy(rand_seq.astype(np.int32)).to(self.eps.device)
-        runner = _engine.Runner(self, bs, neg_idx, self.training, True, comm)
-        x = self._dense_features(batch_graph, bs)
-        g_f, d_logit = _engine.GINFunction.apply(runner, x, *_engine.flat_params(self))
+        plan = self._step_plan(h, n_global)
+        if plan is not None:
+            self._graph_store().h2d_bytes += plan.load(h, rand_seq)
+            g_f, d_logit = _graphed.GraphedGINFunction.apply(plan, *_engine.flat_params(self))
+        else:
+            bs = self._structure(batch_graph, h)
+            neg_idx = torch.from_numpy(rand_seq.astype(np.int32)).to(self.eps.device)
+            runner = _engine.Runner(self, bs, neg_idx, self.training, True, comm)
+            x = self._dense_features(batch_graph, bs)
+            g_f, d_logit = _engine.GINFunction.apply(runner, x, *_engine.flat_params(self))
         c_logit = self._heads(g_f)
         if latent:
             return g_f.detach().cpu().numpy()

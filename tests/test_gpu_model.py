@@ -227,3 +227,44 @@ def test_full_size_properties():
     s_all = m.compute_saliency_batched(graphs[:3], 1)
     s_one = m.compute_saliency([graphs[1]], 1)
     assert_close(s_all[400:800], s_one, 1e-6, "batched saliency exact")
+
+
+def test_cuda_graph_steps_match_eager_steps():
+    """The captured forward/backward graphs (graphed.py) must reproduce the eager kernel-by-kernel path:
+    same losses, gradients and BatchNorm buffers over several optimiser steps, with a different batch order
+    and DGI permutation every step (those are the graphs' dynamic inputs)."""
+    g = Golden("mid_eps_sum_h64")
+    graphs = g.graphs()
+    m_eager, m_graph = build_model(g), build_model(g)
+    m_eager.use_cuda_graphs, m_graph.use_cuda_graphs = False, True
+    o1 = torch.optim.Adam(m_eager.parameters(), lr=0.005)
+    o2 = torch.optim.Adam(m_graph.parameters(), lr=0.005)
+    rng = np.random.default_rng(0)
+    for step in range(5):
+        order = rng.permutation(len(graphs))
+        batch = [graphs[i] for i in order]
+        _, _, l1 = train_step(m_eager, batch, g.cfg["beta"], 50 + step)
+        _, _, l2 = train_step(m_graph, batch, g.cfg["beta"], 50 + step)
+        assert_close(l2, l1.detach(), 1e-5, "loss step %d" % step)
+        floor = grad_floor({k: p.grad.cpu().numpy() for k, p in m_eager.named_parameters() if p.grad is not None})
+        for (k, p1), (_, p2) in zip(m_eager.named_parameters(), m_graph.named_parameters()):
+            if p1.grad is None:
+                assert p2.grad is None
+            else:
+                assert_close(p2.grad, p1.grad, 1e-4, "grad %s step %d" % (k, step), floor=floor)
+        o1.step()
+        o2.step()
+    assert len(m_graph._plans) == 1 and next(iter(m_graph._plans.values())).bwd_graph is not None
+    for (k, b1), (_, b2) in zip(m_eager.named_buffers(), m_graph.named_buffers()):
+        if b1.dtype.is_floating_point:
+            assert_close(b2, b1, 1e-4, k)
+        else:
+            assert int(b1) == int(b2) == 5
+    # a stale backward is refused instead of silently using overwritten activations
+    m_graph.train()
+    np.random.seed(1)
+    c_old, _ = m_graph(graphs)
+    np.random.seed(2)
+    m_graph(graphs)
+    with pytest.raises(RuntimeError):
+        c_old.sum().backward()
