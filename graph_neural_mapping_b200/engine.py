@@ -449,8 +449,12 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
             if use_batch and comm.world > 1:
                 comm.all_reduce_sum(stats)
             gi = pidx + 4 * j
-            grads[gi + 3] = stats[:n_out].to(torch.float32)          # d beta  = sum dy
-            grads[gi + 2] = stats[n_out:].to(torch.float32)          # d gamma = sum dy * xhat
+            # d beta = sum dy, d gamma = sum dy * xhat. After the all-reduce these are sums over ALL ranks of
+            # gradients of each rank's own mean loss; dividing by the world size makes them this rank's share,
+            # so that the gradient averaging after backward (dist.average_gradients) treats them like any other.
+            share = 1.0 / comm.world if (use_batch and comm.world > 1) else 1.0
+            grads[gi + 3] = (stats[:n_out] * share).to(torch.float32)
+            grads[gi + 2] = (stats[n_out:] * share).to(torch.float32)
             _ops.bn_bwd_apply(u.z, u.mean, u.rstd, u.gamma, stats if use_batch else None, u.count, dy)
             dz_u = dy                                                # now d loss / d z_j
             dw = torch.zeros_like(u.w)

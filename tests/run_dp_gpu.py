@@ -1,0 +1,93 @@
+"""Multi-GPU parity check, run as:  torchrun --nproc-per-node R tests/run_dp_gpu.py
+Each rank trains on its contiguous shard of a golden batch (NCCL sync-BatchNorm, broadcast DGI negatives,
+averaged gradients); rank 0 compares the gathered result with the single-process reference fixture, for the
+eager path and for the CUDA-graph path (several steps)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+from helpers import Golden, assert_close, grad_floor  # noqa: E402
+from graph_neural_mapping_b200 import dist as gdist  # noqa: E402
+from graph_neural_mapping_b200.models import GIN_InfoMaxReg  # noqa: E402
+
+
+def build(g, dev, comm, graphs_on):
+    c = g.cfg
+    m = GIN_InfoMaxReg(c["num_layers"], c["num_mlp_layers"], c["input_dim"], c["hidden_dim"], c["output_dim"],
+                       c["final_dropout"], c["learn_eps"], c["graph_pooling_type"], c["neighbor_pooling_type"], dev)
+    m.load_state_dict(g.state_dict())
+    m = m.to(dev)
+    m.set_comm(comm)
+    m.use_cuda_graphs = graphs_on
+    return m
+
+
+def step(model, graphs, beta, seed, dev, comm):
+    model.train()
+    np.random.seed(seed)
+    c_logit, d_logit = model(graphs)
+    labels = torch.LongTensor([x.label for x in graphs]).to(dev)
+    n = len(graphs) * graphs[0].node_features.shape[1]
+    d_labels = torch.cat([torch.ones(n, 1), torch.zeros(n, 1)], 0).to(dev)
+    loss = torch.nn.functional.cross_entropy(c_logit, labels) + beta * \
+        torch.nn.functional.binary_cross_entropy_with_logits(d_logit, d_labels)
+    model.zero_grad()
+    loss.backward()
+    gdist.average_gradients(model, comm)
+    return c_logit, d_logit, loss
+
+
+def gather(t, comm):
+    out = [torch.empty_like(t) for _ in range(comm.world)]
+    td.all_gather(out, t.contiguous())
+    return out
+
+
+def main():
+    comm, local_rank = gdist.init_from_env("nccl")
+    dev = torch.device("cuda", local_rank)
+    ok = True
+    for name, seed0 in [("mid_eps_sum_h64", 900), ("tiny_eps_sum", 100)]:
+        g = Golden(name)
+        if g.cfg["B"] % comm.world:
+            continue
+        graphs = gdist.shard(g.graphs(), comm)
+        for graphs_on in (False, True):
+            model = build(g, dev, comm, graphs_on)
+            reps = 3 if graphs_on else 1          # 1st sighting eager, then capture, then replay
+            for rep in range(reps):
+                model.load_state_dict(g.state_dict())
+                c_logit, d_logit, loss = step(model, graphs, g.cfg["beta"], 4242 + seed0, dev, comm)
+            cs, ds = gather(c_logit.detach(), comm), gather(d_logit.detach(), comm)
+            ls = gather(loss.detach().reshape(1), comm)
+            if comm.rank == 0:
+                m_local = ds[0].shape[0] // 2
+                d_all = torch.cat([x[:m_local] for x in ds] + [x[m_local:] for x in ds], 0)
+                assert_close(torch.cat(cs, 0), g.z["train/c_logit"], 1e-4, "c_logit")
+                assert_close(d_all, g.z["train/d_logit"], 1e-4, "d_logit")
+                assert_close(torch.stack(ls).mean(), g.z["train/loss"], 1e-4, "loss")
+                ref = g.group("grad/")
+                floor = grad_floor(ref)
+                for k, p in model.named_parameters():
+                    if k in ref:
+                        assert_close(p.grad, ref[k], 2e-3, "grad " + k, floor=floor)
+                if not graphs_on:
+                    for k, v in g.group("buf_after/").items():
+                        if "num_batches" not in k:
+                            assert_close(model.state_dict()[k], v, 1e-4, k)
+                print("DP parity OK: %s world=%d cuda_graphs=%s" % (name, comm.world, graphs_on), flush=True)
+    td.barrier()
+    td.destroy_process_group()
+    if comm.rank == 0:
+        print("DP_GPU_CHECK_PASSED" if ok else "DP_GPU_CHECK_FAILED", flush=True)
+
+
+if __name__ == "__main__":
+    main()

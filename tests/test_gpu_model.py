@@ -237,8 +237,12 @@ def test_cuda_graph_steps_match_eager_steps():
     graphs = g.graphs()
     m_eager, m_graph = build_model(g), build_model(g)
     m_eager.use_cuda_graphs, m_graph.use_cuda_graphs = False, True
-    o1 = torch.optim.Adam(m_eager.parameters(), lr=0.005)
-    o2 = torch.optim.Adam(m_graph.parameters(), lr=0.005)
+    # Linear biases that feed a train-mode BatchNorm have an exactly-zero true gradient; Adam would turn their
+    # rounding noise into +-lr random walks that show up in running_mean. Keep them out of the optimiser here.
+    def trainable(m):
+        return [p for k, p in m.named_parameters() if not (k.startswith("mlps.") and k.endswith(".bias"))]
+    o1 = torch.optim.Adam(trainable(m_eager), lr=0.005)
+    o2 = torch.optim.Adam(trainable(m_graph), lr=0.005)
     rng = np.random.default_rng(0)
     for step in range(5):
         order = rng.permutation(len(graphs))
@@ -268,3 +272,17 @@ def test_cuda_graph_steps_match_eager_steps():
     m_graph(graphs)
     with pytest.raises(RuntimeError):
         c_old.sum().backward()
+
+
+def test_two_gpu_data_parallel_matches_reference():
+    """Launches tests/run_dp_gpu.py under torchrun when the box has >= 2 GPUs (skipped on 1-GPU boxes)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29371", os.path.join(here, "run_dp_gpu.py")],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert "DP_GPU_CHECK_PASSED" in res.stdout, res.stdout[-3000:]
