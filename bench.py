@@ -367,8 +367,10 @@ def run_b200(args):
                 "e2e": e2e, "roofline": roof, "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown}
         print(json.dumps(line))
     if world > 1:
+        model.release_graphs()
+        torch.cuda.synchronize()
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        gdist.shutdown()
 
 
 def main():

@@ -97,3 +97,24 @@ def average_gradients(model, comm):
         n = p.numel()
         p.grad.copy_(flat[off:off + n].view_as(p.grad))
         off += n
+
+
+def shutdown():
+    """Tear the default process group down. Call `model.release_graphs()` first: CUDA graphs that captured NCCL
+    kernels keep the communicator alive and `destroy_process_group` would wait for them."""
+    import gc
+    import sys
+    import threading
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if td.is_available() and td.is_initialized():
+        # belt and braces: results are already printed when this runs; never let a stuck communicator
+        # teardown hold the job (and the GPUs) hostage
+        sys.stdout.flush()
+        sys.stderr.flush()
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        td.destroy_process_group()
+        watchdog.cancel()

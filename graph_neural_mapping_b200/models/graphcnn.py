@@ -65,6 +65,11 @@ class GIN_InfoMaxReg(nn.Module):
         global batch and synchronises BatchNorm statistics and the DGI negatives over `comm`."""
         self._comm = comm if comm is not None else _dist.SINGLE
 
+    def release_graphs(self):
+        """Drop the captured CUDA graphs (and their static buffers); they are re-captured on demand."""
+        self._plans.clear()
+        self._warm.clear()
+
     # ---- internals --------------------------------------------------------------------------
     def _graph_store(self):
         dev = self.eps.device

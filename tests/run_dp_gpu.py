@@ -83,10 +83,14 @@ def main():
                         if "num_batches" not in k:
                             assert_close(model.state_dict()[k], v, 1e-4, k)
                 print("DP parity OK: %s world=%d cuda_graphs=%s" % (name, comm.world, graphs_on), flush=True)
+            # captured graphs hold references on the NCCL communicator: drop them before tearing it down
+            model.release_graphs()
+            del model
+    torch.cuda.synchronize()
     td.barrier()
-    td.destroy_process_group()
     if comm.rank == 0:
         print("DP_GPU_CHECK_PASSED" if ok else "DP_GPU_CHECK_FAILED", flush=True)
+    gdist.shutdown()
 
 
 if __name__ == "__main__":
