@@ -16,7 +16,7 @@
 //    shared memory ([k][feature], 144-byte pitch: conflict-free for ldmatrix) and multiplied in
 //    three passes accumulating into the same fp32 accumulators. 0/1 x bf16 products are exact, so
 //    the only rounding is the fp32 accumulation, as in the reference's own summation.
-//  * One persistent CTA (8 warps = 4 along rows x 2 along features) per SM walks work items
+//  * One persistent CTA (16 warps = 4 along rows x 4 along features) per SM walks work items
 //    (graph, 448-row block, 64-feature slab); K is streamed in 128-row chunks, double buffered:
 //    the global loads of chunk c+1 are in flight while chunk c is in the MMA loop.
 //
@@ -30,12 +30,22 @@ namespace {
 
 constexpr int AD_KC = 128;                 // K rows per shared-memory chunk
 constexpr int AD_PITCH = 72;               // bf16 per smem row: 64 features + 8 pad = 144 B
-constexpr int AD_MT = 7;                   // m16 tiles per row-warp
-constexpr int AD_ROWS = 4 * AD_MT * 16;    // 448 rows per work item
 constexpr int AD_SLAB = 64;                // features per work item
-constexpr int AD_THREADS = 256;
 constexpr int AD_PLANE = AD_KC * AD_PITCH;                  // bf16 elements per split plane
 constexpr int AD_SMEM_BYTES = 2 * 3 * AD_PLANE * 2;         // two buffers x three planes
+
+// Warp grid of one CTA: WM warps along rows x WN warps along the 64 features; every warp owns MT m16 tiles
+// (rows) x NT = 8/WN n8 tiles (features). Rows per work item = WM * MT * 16.
+template <int WM_, int WN_, int MT_>
+struct AggDenseCfg {
+    static constexpr int WM = WM_, WN = WN_, MT = MT_;
+    static constexpr int NT = 8 / WN_;
+    static constexpr int THREADS = WM_ * WN_ * 32;
+    static constexpr int ROWS = WM_ * MT_ * 16;
+    static constexpr int STAGE = AD_KC * 16 / THREADS;      // float4 loads per thread per chunk
+    static_assert(NT >= 2 && (NT % 2) == 0, "ldmatrix.x4 covers two n-tiles");
+    static_assert(AD_KC * 16 % THREADS == 0, "chunk must divide evenly over the CTA");
+};
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                uint32_t b0, uint32_t b1) {
@@ -84,18 +94,21 @@ struct AggDenseParams {
     int n_graphs, n_feat, mode, n_rb, n_slabs;
 };
 
-__global__ void __launch_bounds__(AD_THREADS, 1) aggregate_dense_kernel(const AggDenseParams p) {
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) aggregate_dense_kernel(const AggDenseParams p) {
+    constexpr int AD_MT = Cfg::MT, AD_NT = Cfg::NT, AD_THREADS = Cfg::THREADS, AD_ROWS = Cfg::ROWS;
+    constexpr int AD_WN = Cfg::WN, AD_WM = Cfg::WM, AD_STAGE = Cfg::STAGE;
     extern __shared__ __align__(16) unsigned char ad_smem[];
     __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(ad_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int warp_m = warp >> 1, warp_n = warp & 1;
+    const int warp_m = warp / AD_WN, warp_n = warp % AD_WN;
     const int g = lane >> 2, t = lane & 3;
     const int n_items = p.n_graphs * p.n_rb * p.n_slabs;
     const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(sm);
     // ldmatrix lane address components: matrix q = lane / 8, row r = lane % 8
     const int lq = lane >> 3, lr = lane & 7;
     const int ld_row = (lq & 1) * 8 + lr;           // k offset inside the 16-row k-step
-    const int ld_col = warp_n * 32 + (lq >> 1) * 8; // feature offset of the first n-tile pair
+    const int ld_col = warp_n * (AD_NT * 8) + (lq >> 1) * 8; // feature offset of the first n-tile pair
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int slab = item % p.n_slabs;
@@ -110,18 +123,18 @@ __global__ void __launch_bounds__(AD_THREADS, 1) aggregate_dense_kernel(const Ag
         const uint32_t* __restrict__ bm = reinterpret_cast<const uint32_t*>(p.bitmap_addr[gi]);
         const int n_chunks = (n + AD_KC - 1) / AD_KC;
 
-        float acc[AD_MT][4][4];
+        float acc[AD_MT][AD_NT][4];
 #pragma unroll
         for (int i = 0; i < AD_MT; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < AD_NT; ++j)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
 
-        float4 stage[8];
+        float4 stage[AD_STAGE];
         auto load_chunk = [&](int c) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < AD_STAGE; ++j) {
                 const int i = tid + AD_THREADS * j;
                 const int row = i >> 4, c4 = i & 15;
                 const int krow = c * AD_KC + row;
@@ -142,7 +155,7 @@ __global__ void __launch_bounds__(AD_THREADS, 1) aggregate_dense_kernel(const Ag
         auto store_chunk = [&](int buf) {
             __nv_bfloat16* base = sm + (size_t)buf * 3 * AD_PLANE;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < AD_STAGE; ++j) {
                 const int i = tid + AD_THREADS * j;
                 const int row = i >> 4, c4 = i & 15;
                 float h[4], m[4], l[4];
@@ -170,7 +183,7 @@ __global__ void __launch_bounds__(AD_THREADS, 1) aggregate_dense_kernel(const Ag
                 uint32_t w_lo[AD_MT], w_hi[AD_MT];
 #pragma unroll
                 for (int i = 0; i < AD_MT; ++i) {
-                    const int r_lo = row0 + (warp_m + 4 * i) * 16 + g;
+                    const int r_lo = row0 + (warp_m + AD_WM * i) * 16 + g;
                     const int r_hi = r_lo + 8;
                     w_lo[i] = (r_lo < n) ? __ldg(bm + (size_t)r_lo * words + wi) : 0u;
                     w_hi[i] = (r_hi < n) ? __ldg(bm + (size_t)r_hi * words + wi) : 0u;
@@ -179,11 +192,11 @@ __global__ void __launch_bounds__(AD_THREADS, 1) aggregate_dense_kernel(const Ag
                 for (int half = 0; half < 2; ++half) {
                     const int ks = ws * 32 + half * 16;            // k offset inside the chunk
                     if (ks >= k_rows) break;                       // warp-uniform
-                    uint32_t b[3][4][2];
+                    uint32_t b[3][AD_NT][2];
 #pragma unroll
                     for (int sp = 0; sp < 3; ++sp)
 #pragma unroll
-                        for (int np = 0; np < 2; ++np) {
+                        for (int np = 0; np < AD_NT / 2; ++np) {
                             const uint32_t addr = buf_addr +
                                 (uint32_t)((sp * AD_PLANE + (ks + ld_row) * AD_PITCH + ld_col + np * 16) * 2);
                             ldmatrix_x4_trans(b[sp][2 * np][0], b[sp][2 * np][1], b[sp][2 * np + 1][0],
@@ -192,7 +205,7 @@ __global__ void __launch_bounds__(AD_THREADS, 1) aggregate_dense_kernel(const Ag
                     const int sh = half * 16 + 2 * t;
 #pragma unroll
                     for (int i = 0; i < AD_MT; ++i) {
-                        if (row0 + (warp_m + 4 * i) * 16 >= n) break;   // warp-uniform: no rows in this tile
+                        if (row0 + (warp_m + AD_WM * i) * 16 >= n) break;   // warp-uniform: no rows in this tile
                         const uint32_t a0 = bits_to_bf16x2(w_lo[i] >> sh);
                         const uint32_t a1 = bits_to_bf16x2(w_hi[i] >> sh);
                         const uint32_t a2 = bits_to_bf16x2(w_lo[i] >> (sh + 8));
@@ -200,7 +213,7 @@ __global__ void __launch_bounds__(AD_THREADS, 1) aggregate_dense_kernel(const Ag
 #pragma unroll
                         for (int sp = 0; sp < 3; ++sp)
 #pragma unroll
-                            for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[i][nt], a0, a1, a2, a3, b[sp][nt][0], b[sp][nt][1]);
+                            for (int nt = 0; nt < AD_NT; ++nt) mma_bf16_16816(acc[i][nt], a0, a1, a2, a3, b[sp][nt][0], b[sp][nt][1]);
                     }
                 }
             }
@@ -212,7 +225,7 @@ __global__ void __launch_bounds__(AD_THREADS, 1) aggregate_dense_kernel(const Ag
         const float self_c = p.eps ? 1.f + __ldg(p.eps) : 0.f;
 #pragma unroll
         for (int i = 0; i < AD_MT; ++i) {
-            const int rbase = row0 + (warp_m + 4 * i) * 16;
+            const int rbase = row0 + (warp_m + AD_WM * i) * 16;
             if (rbase >= n) break;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -224,8 +237,8 @@ __global__ void __launch_bounds__(AD_THREADS, 1) aggregate_dense_kernel(const Ag
                 if (p.mode == 1) { avg = true; inv = (float)(p.rowptr[gr + 1] - p.rowptr[gr]); }
                 const int64_t sr = p.src_map ? (int64_t)p.src_map[gr] : (int64_t)gr;
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    const int col = f0 + warp_n * 32 + nt * 8 + 2 * t;
+                for (int nt = 0; nt < AD_NT; ++nt) {
+                    const int col = f0 + warp_n * (AD_NT * 8) + nt * 8 + 2 * t;
                     if (col >= p.n_feat) continue;
                     float v0 = acc[i][nt][hh * 2], v1 = acc[i][nt][hh * 2 + 1];
                     if (avg) { v0 /= inv; v1 /= inv; }
@@ -301,16 +314,18 @@ extern "C" int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* no
     p.bitmap_addr = bitmap_addr; p.node_off = node_off; p.rowptr = rowptr; p.src = src; p.src_map = src_map;
     p.dst = dst; p.eps = eps; p.bias = bias; p.ld_src = ld_src; p.ld_dst = ld_dst; p.n_graphs = n_graphs;
     p.n_feat = n_feat; p.mode = mode;
-    p.n_rb = (n_max + AD_ROWS - 1) / AD_ROWS;
+    using Cfg = AggDenseCfg<4, 4, 7>;      // 16 warps: 4 per scheduler; 448 rows x 64 features per work item
+    p.n_rb = (n_max + Cfg::ROWS - 1) / Cfg::ROWS;
     p.n_slabs = (n_feat + AD_SLAB - 1) / AD_SLAB;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(aggregate_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AD_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(aggregate_dense_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         AD_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     const int64_t items = (int64_t)n_graphs * p.n_rb * p.n_slabs;
     const int grid = (int)(items < sms ? items : sms);
-    aggregate_dense_kernel<<<grid, AD_THREADS, AD_SMEM_BYTES, gnm_cast_stream(stream)>>>(p);
+    aggregate_dense_kernel<Cfg><<<grid, Cfg::THREADS, AD_SMEM_BYTES, gnm_cast_stream(stream)>>>(p);
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;
 }

@@ -27,6 +27,8 @@ from . import dist as _dist
 
 DENSE_MIN_DENSITY = 0.04      # use the tensor-core block kernel when nnz >= this fraction of sum N_g^2
 FORCE_CSR_AGGREGATE = False    # test / A-B switch: always take the CSR gather kernel
+FUSED_BWD_MAX = 64             # gnm_linear_bwd handles F_out, F_in <= 64; wider units take the unfused kernels
+FORCE_UNFUSED_BACKWARD = False # test / A-B switch
 
 
 def require_cuda(dev):
@@ -433,18 +435,24 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
         eps_l = eps_p[layer:layer + 1] if learn_eps else None
         h_prev = sv.h_all[layer - 1] if layer > 0 else None
         dz = None
+        pending = None        # (dy, stats) of the current unit when the previous fused call already produced them
         for j in range(len(units) - 1, -1, -1):
             u = units[j]
-            n_out = u.w.shape[0]
-            dy = torch.empty(M, n_out, dtype=torch.float32, device=dev)
-            stats = torch.zeros(2 * n_out, dtype=torch.float64, device=dev)
-            if j == len(units) - 1:
-                _ops.relu_bn_bwd_reduce(u.z, u.scale, u.shift, u.mean, u.rstd, d_h, d_pooled[:, sl], bs.pool_scale,
-                                        d_score, u_mat[:, sl] if u_mat is not None else None,
-                                        d_neg[:, sl] if d_neg is not None else None, n_neg, bs.node_off, B, dy, stats)
+            n_out, n_in = u.w.shape[0], u.w.shape[1]
+            if pending is not None:
+                dy, stats = pending
+                pending = None
             else:
-                _ops.relu_bn_bwd_reduce(u.z, u.scale, u.shift, u.mean, u.rstd, dz, None, None, None, None, None, 0,
-                                        bs.node_off, B, dy, stats)
+                dy = torch.empty(M, n_out, dtype=torch.float32, device=dev)
+                stats = torch.zeros(2 * n_out, dtype=torch.float64, device=dev)
+                if j == len(units) - 1:
+                    _ops.relu_bn_bwd_reduce(u.z, u.scale, u.shift, u.mean, u.rstd, d_h, d_pooled[:, sl],
+                                            bs.pool_scale, d_score, u_mat[:, sl] if u_mat is not None else None,
+                                            d_neg[:, sl] if d_neg is not None else None, n_neg, bs.node_off, B, dy,
+                                            stats)
+                else:
+                    _ops.relu_bn_bwd_reduce(u.z, u.scale, u.shift, u.mean, u.rstd, dz, None, None, None, None, None,
+                                            0, bs.node_off, B, dy, stats)
             use_batch = u.count > 0.0
             if use_batch and comm.world > 1:
                 comm.all_reduce_sum(stats)
@@ -455,42 +463,73 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
             share = 1.0 / comm.world if (use_batch and comm.world > 1) else 1.0
             grads[gi + 3] = (stats[:n_out] * share).to(torch.float32)
             grads[gi + 2] = (stats[n_out:] * share).to(torch.float32)
-            _ops.bn_bwd_apply(u.z, u.mean, u.rstd, u.gamma, stats if use_batch else None, u.count, dy)
-            dz_u = dy                                                # now d loss / d z_j
             dw = torch.zeros_like(u.w)
             db = torch.zeros_like(u.b)
+            gather0 = j == 0 and layer == 0 and sv.use_gather0
+            fused = (not gather0) and (not FORCE_UNFUSED_BACKWARD) and n_out <= FUSED_BWD_MAX and n_in <= FUSED_BWD_MAX
+            if fused:
+                # one pass: BatchNorm-backward apply (folded into the load as dz = A*dy + B*z + C), dW, db, dX and -
+                # for an inner unit - the ReLU mask + BatchNorm-backward reduction of the unit below
+                coef = torch.empty(3, n_out, dtype=torch.float32, device=dev)
+                _ops.bn_bwd_coeffs(stats if use_batch else None, u.count, u.gamma, u.mean, u.rstd, coef)
+                if j > 0:
+                    p = units[j - 1]
+                    dy_prev = torch.empty(M, n_in, dtype=torch.float32, device=dev)
+                    stats_prev = torch.zeros(2 * n_in, dtype=torch.float64, device=dev)
+                    _ops.linear_bwd(dy, u.z, coef, p.z, p.scale, p.shift, p.mean, p.rstd, u.w, dw, db, dy_prev,
+                                    stats_prev)
+                    pending = (dy_prev, stats_prev)
+                else:
+                    need_dp = layer > 0 or need_x_grad or learn_eps
+                    dp = torch.empty(M, n_in, dtype=torch.float32, device=dev) if need_dp else None
+                    _ops.linear_bwd(dy, u.z, coef, u.x_in, None, None, None, None, u.w, dw, db, dp, None)
+                    if need_dp:
+                        src = sv.x_dense if layer == 0 else h_prev
+                        if learn_eps:
+                            _ops.dot_rows(dp, src, None, d_eps[layer:layer + 1])
+                        if layer > 0 or need_x_grad:
+                            d_prev = torch.empty(M, n_in, dtype=torch.float32, device=dev)
+                            bs.aggregate(dp, None, d_prev, bwd_mode, eps_l, None)
+                            if layer > 0:
+                                d_h = d_prev
+                            else:
+                                d_x = d_prev
+                grads[gi], grads[gi + 1] = dw, db
+                continue
+            _ops.bn_bwd_apply(u.z, u.mean, u.rstd, u.gamma, stats if use_batch else None, u.count, dy)
+            dz_u = dy                                                # now d loss / d z_j
             if j > 0:
                 p = units[j - 1]
                 _ops.linear_wgrad(dz_u, p.z, p.scale, p.shift, dw, db)
-                dz = torch.empty(M, u.w.shape[1], dtype=torch.float32, device=dev)
+                dz = torch.empty(M, n_in, dtype=torch.float32, device=dev)
                 _ops.linear(dz_u, u.w, True, None, None, None, dz, None)      # d a_{j-1} = dz_j @ W_j
                 grads[gi], grads[gi + 1] = dw, db
                 continue
             # ---- first unit of the layer: input is the neighbour aggregation --------------------
-            if layer == 0 and sv.use_gather0:
+            if gather0:
                 # z0 = Agg(W1^T[tags]) + b:  dW1^T[t] = sum_{tags[r]=t} (Agg^T dz)[r]
                 g_agg = torch.empty(M, n_out, dtype=torch.float32, device=dev)
                 bs.aggregate(dz_u, None, g_agg, bwd_mode, eps_l, None)
-                dw1t = torch.zeros(u.w.shape[1], n_out, dtype=torch.float32, device=dev)
+                dw1t = torch.zeros(n_in, n_out, dtype=torch.float32, device=dev)
                 _ops.scatter_rows_add(g_agg, bs.tags, dw1t)
                 dw = dw1t.t().contiguous()
                 _ops.linear_wgrad(dz_u, None, None, None, None, db)
                 if learn_eps:
                     _ops.dot_rows(dz_u, sv.w1t, bs.tags, d_eps[layer:layer + 1])
                 if need_x_grad:
-                    d_x = torch.empty(M, u.w.shape[1], dtype=torch.float32, device=dev)
+                    d_x = torch.empty(M, n_in, dtype=torch.float32, device=dev)
                     _ops.linear(g_agg, u.w, True, None, None, None, d_x, None)   # (Agg^T dz) @ W1
             else:
                 _ops.linear_wgrad(dz_u, u.x_in, None, None, dw, db)
                 need_dp = layer > 0 or need_x_grad or learn_eps
                 if need_dp:
                     src = sv.x_dense if layer == 0 else h_prev
-                    dp = torch.empty(M, u.w.shape[1], dtype=torch.float32, device=dev)
+                    dp = torch.empty(M, n_in, dtype=torch.float32, device=dev)
                     _ops.linear(dz_u, u.w, True, None, None, None, dp, None)
                     if learn_eps:
                         _ops.dot_rows(dp, src, None, d_eps[layer:layer + 1])
                     if layer > 0 or need_x_grad:
-                        d_prev = torch.empty(M, u.w.shape[1], dtype=torch.float32, device=dev)
+                        d_prev = torch.empty(M, n_in, dtype=torch.float32, device=dev)
                         bs.aggregate(dp, None, d_prev, bwd_mode, eps_l, None)
                         if layer > 0:
                             d_h = d_prev

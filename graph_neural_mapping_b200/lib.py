@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libgnm.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _c_i32 = ctypes.c_int
 _c_i64 = ctypes.c_int64
@@ -33,6 +33,9 @@ SIGNATURES = {
     "gnm_scatter_rows_add": [_p, _c_i64, _p, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p],
     "gnm_linear": [_p, _c_i64, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p, _p, _p, _p, _c_i64, _c_i32, _p, _p],
     "gnm_linear_wgrad": [_p, _c_i64, _p, _c_i64, _c_i32, _c_i32, _c_i32, _p, _p, _p, _c_i64, _p, _p],
+    "gnm_bn_bwd_coeffs": [_p, _c_f64, _p, _p, _p, _p, _c_i32, _p],
+    "gnm_linear_bwd": [_p, _c_i64, _p, _c_i64, _p, _p, _c_i64, _p, _p, _p, _p, _p, _c_i64, _p, _c_i64, _p, _p, _c_i64,
+                       _p, _c_i32, _c_i32, _c_i32, _p],
     "gnm_col_stats": [_p, _c_i64, _c_i32, _c_i32, _p, _p],
     "gnm_bn_finalize": [_p, _c_f64, _p, _p, _c_f32, _c_f32, _p, _p, _p, _p, _p, _p, _p, _c_i32, _p],
     "gnm_bn_eval_affine": [_p, _p, _p, _p, _c_f32, _p, _p, _p, _p, _c_i32, _p],

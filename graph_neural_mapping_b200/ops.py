@@ -172,6 +172,27 @@ def linear_wgrad(dz, x, in_scale, in_shift, dw, dbias):
                                           _ptr(dbias, torch.float32), _stream(dz)), "gnm_linear_wgrad")
 
 
+def bn_bwd_coeffs(stats, count, gamma, mean, rstd, coef):
+    _libmod.check(_lib().gnm_bn_bwd_coeffs(_ptr(stats, torch.float64), float(count), _ptr(gamma, torch.float32),
+                                           _ptr(mean), _ptr(rstd), _ptr(coef, torch.float32), int(mean.shape[0]),
+                                           _stream(coef)), "gnm_bn_bwd_coeffs")
+    return coef
+
+
+def linear_bwd(dy, z, coef, x, in_scale, in_shift, in_mean, in_rstd, w, dw, dbias, dx, stats_in):
+    yp, ldy = _mat(dy)
+    zp, ldz = _mat(z)
+    xp, ldx = _mat(x)
+    wp, ldw = _mat(w)
+    gp, ldg = _mat(dw)
+    dp, ldd = _mat(dx)
+    _libmod.check(_lib().gnm_linear_bwd(yp, ldy, zp, ldz, _ptr(coef, torch.float32), xp, ldx, _ptr(in_scale),
+                                        _ptr(in_shift), _ptr(in_mean), _ptr(in_rstd), wp, ldw, gp, ldg,
+                                        _ptr(dbias, torch.float32), dp, ldd, _ptr(stats_in, torch.float64),
+                                        int(dy.shape[0]), int(w.shape[0]), int(w.shape[1]), _stream(dy)),
+                  "gnm_linear_bwd")
+
+
 def col_stats(x, stats):
     xp, ldx = _mat(x)
     _libmod.check(_lib().gnm_col_stats(xp, ldx, int(x.shape[0]), int(x.shape[1]), _ptr(stats, torch.float64),

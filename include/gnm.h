@@ -32,7 +32,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 4
+#define GNM_ABI_VERSION 5
 
 typedef void* gnm_stream_t;
 
@@ -128,6 +128,26 @@ int gnm_linear(const float* x, int64_t ldx, int n_rows, int n_in,
 int gnm_linear_wgrad(const float* dz, int64_t lddz, const float* x, int64_t ldx, int n_rows, int n_out, int n_in,
                      const float* in_scale, const float* in_shift,
                      float* dw, int64_t lddw, float* dbias, gnm_stream_t stream);
+
+/* BatchNorm backward as an affine map of (dy, z): dz = A*dy + B*z + C per channel, coef = [A | B | C] ([3*F]).
+ * Training (stats != NULL: sum dy, sum dy*xhat; count = global rows): A = g*rstd, B = -g*rstd^2*m2,
+ * C = g*rstd*(rstd*m2*mean - m1), m1 = stats[c]/count, m2 = stats[F+c]/count. Eval (stats == NULL): A = g*rstd. */
+int gnm_bn_bwd_coeffs(const double* stats, double count, const float* gamma, const float* mean, const float* rstd,
+                      float* coef, int n_feat, gnm_stream_t stream);
+
+/* Fused backward of one Linear -> BatchNorm (-> ReLU) unit (autograd of mlp.py:48-49, graphcnn.py:162-166) in one
+ * pass over the rows, F_out, F_in <= 64 (GNM_ERR_TOO_LARGE otherwise: use the unfused kernels):
+ *   dz = A*dy + B*z + C (coef from gnm_bn_bwd_coeffs);  dw[o,i] += sum_m dz[m,o]*a[m,i];  dbias[o] += sum_m dz[m,o]
+ *   a = relu(x*in_scale + in_shift) if in_scale != NULL else x          (the unit's input, recomputed)
+ *   dx[m,i] = (sum_o dz[m,o]*w[o,i]) * [a[m,i] > 0]                     (nullable; mask only with in_scale)
+ *   stats_in[i] += sum_m dx[m,i];  stats_in[F_in+i] += sum_m dx[m,i]*(x[m,i]-in_mean[i])*in_rstd[i]   (nullable)
+ * i.e. dx is already the ReLU-masked gradient at the previous unit's BatchNorm output and stats_in its
+ * BatchNorm-backward reduction. */
+int gnm_linear_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* coef,
+                   const float* x, int64_t ldx, const float* in_scale, const float* in_shift,
+                   const float* in_mean, const float* in_rstd, const float* w, int64_t ldw,
+                   float* dw, int64_t lddw, float* dbias, float* dx, int64_t lddx, double* stats_in,
+                   int n_rows, int n_out, int n_in, gnm_stream_t stream);
 
 /* Per-column sum / sum of squares (double [2F], +=) of a [M, F] matrix. */
 int gnm_col_stats(const float* x, int64_t ldx, int n_rows, int n_feat, double* col_stats, gnm_stream_t stream);

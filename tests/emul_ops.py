@@ -176,6 +176,38 @@ def linear_wgrad(dz, x, in_scale, in_shift, dw, dbias):
         dbias += dz.double().sum(0).float()
 
 
+def bn_bwd_coeffs(stats, count, gamma, mean, rstd, coef):
+    f = mean.shape[0]
+    g = gamma * rstd
+    coef[0] = g
+    if stats is None:
+        coef[1] = 0
+        coef[2] = 0
+    else:
+        m1, m2 = (stats[:f] / count).float(), (stats[f:] / count).float()
+        coef[1] = -g * rstd * m2
+        coef[2] = g * (rstd * m2 * mean - m1)
+    return coef
+
+
+def linear_bwd(dy, z, coef, x, in_scale, in_shift, in_mean, in_rstd, w, dw, dbias, dx, stats_in):
+    dz = (coef[0] * dy + coef[1] * z + coef[2]).double()
+    a = _act(x, in_scale, in_shift).double()
+    dw += (dz.t() @ a).float()
+    if dbias is not None:
+        dbias += dz.sum(0).float()
+    if dx is not None or stats_in is not None:
+        g = dz @ w.double()
+        if in_scale is not None:
+            g = torch.where(a > 0, g, torch.zeros_like(g))
+        if dx is not None:
+            dx.copy_(g.float())
+        if stats_in is not None:
+            n = x.shape[1]
+            stats_in[:n] += g.sum(0)
+            stats_in[n:] += (g * ((x - in_mean) * in_rstd).double()).sum(0)
+
+
 def col_stats(x, stats):
     n = x.shape[1]
     stats[:n] += x.double().sum(0)

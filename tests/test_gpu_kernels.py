@@ -424,3 +424,47 @@ def test_aggregate_dense_exactness_on_wide_dynamic_range():
     out = torch.empty(n, 64, device=DEV)
     ops.aggregate_dense(addr, no, rp, 1, n, src, None, out, 0, None, None)
     assert torch.equal(out, src.roll(-1, 0))
+
+
+@pytest.mark.parametrize("m,fo,fi", [(1, 1, 1), (300, 8, 12), (4097, 64, 64), (1000, 12, 64), (640, 64, 8), (129, 63, 37)])
+@pytest.mark.parametrize("act,train", [(True, True), (False, True), (True, False)])
+def test_linear_bwd_fused(m, fo, fi, act, train):
+    torch.manual_seed(m + fo)
+    dy, z = torch.randn(m, fo, device=DEV), torch.randn(m, fo, device=DEV) * 2 + 0.5
+    x = torch.randn(m, fi, device=DEV)
+    w = torch.randn(fo, fi, device=DEV) * 0.3
+    gamma, mean, rstd = torch.rand(fo, device=DEV) + 0.5, torch.randn(fo, device=DEV), torch.rand(fo, device=DEV) + 0.5
+    stats = torch.randn(2 * fo, dtype=torch.float64, device=DEV) * m if train else None
+    coef = torch.empty(3, fo, device=DEV)
+    ops.bn_bwd_coeffs(stats, float(m), gamma, mean, rstd, coef)
+    coef_r = torch.empty(3, fo)
+    c = lambda t: t.cpu() if t is not None else None
+    emul_ops.bn_bwd_coeffs(c(stats), float(m), c(gamma), c(mean), c(rstd), coef_r)
+    assert_close(coef, coef_r, 1e-5, "coef")
+    # the affine form equals the two-pass BatchNorm backward
+    if train:
+        dref = dy.clone()
+        ops.bn_bwd_apply(z, mean, rstd, gamma, stats, float(m), dref)
+        assert_close(coef[0] * dy + coef[1] * z + coef[2], dref, 2e-5, "dz affine form")
+    isc = torch.rand(fi, device=DEV) + 0.5 if act else None
+    ish = torch.randn(fi, device=DEV) if act else None
+    imu = torch.randn(fi, device=DEV) if act else None
+    irs = torch.rand(fi, device=DEV) + 0.5 if act else None
+    dw, db = torch.zeros(fo, fi, device=DEV), torch.zeros(fo, device=DEV)
+    dx = torch.full((m, fi), float("nan"), device=DEV)
+    st = torch.zeros(2 * fi, dtype=torch.float64, device=DEV) if act else None
+    ops.linear_bwd(dy, z, coef, x, isc, ish, imu, irs, w, dw, db, dx, st)
+    dwr, dbr, dxr = torch.zeros(fo, fi), torch.zeros(fo), torch.empty(m, fi)
+    str_ = torch.zeros(2 * fi, dtype=torch.float64) if act else None
+    emul_ops.linear_bwd(c(dy), c(z), c(coef), c(x), c(isc), c(ish), c(imu), c(irs), c(w), dwr, dbr, dxr, str_)
+    assert_close(dw, dwr, TOL, "dw")
+    assert_close(db, dbr, TOL, "db")
+    assert_close(dx, dxr, TOL, "dx")
+    if act:
+        assert_close(st, str_, 2e-5, "stats_in")
+    # dx == None (first unit of layer 0 in training) still produces dw / db
+    dw2, db2 = torch.zeros(fo, fi, device=DEV), torch.zeros(fo, device=DEV)
+    ops.linear_bwd(dy, z, coef, x, None, None, None, None, w, dw2, db2, None, None)
+    dwr2, dbr2 = torch.zeros(fo, fi), torch.zeros(fo)
+    emul_ops.linear_bwd(c(dy), c(z), c(coef), c(x), None, None, None, None, c(w), dwr2, dbr2, None, None)
+    assert_close(dw2, dwr2, TOL, "dw (no dx)")

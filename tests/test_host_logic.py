@@ -229,3 +229,16 @@ def test_csr_and_dense_aggregation_paths_agree(monkeypatch):
     assert_close(d2, d1.detach(), 1e-5, "d_logit")
     monkeypatch.setattr(engine, "DENSE_MIN_DENSITY", 0.9)
     assert m2._structure(graphs).bitmap_addr is None             # sparse batches stay on the CSR kernel
+
+
+def test_fused_and_unfused_backward_agree(monkeypatch):
+    g = Golden("tiny_mlp3")
+    graphs = g.graphs()
+    m1, m2 = build_model(g), build_model(g)
+    train_step(m1, graphs, g, 21)
+    monkeypatch.setattr(engine, "FORCE_UNFUSED_BACKWARD", True)
+    train_step(m2, graphs, g, 21)
+    floor = grad_floor({k: p.grad.numpy() for k, p in m1.named_parameters() if p.grad is not None})
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if p1.grad is not None:
+            assert_close(p2.grad, p1.grad, 1e-4, "grad " + k, floor=floor)
