@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256)
 scatter_rows_add_kernel(const float* __restrict__ g, int64_t ldg, const int32_t* __restrict__ tags, int n_rows,
                         int n_feat, float* __restrict__ table_grad, int64_t ldt, int n_table_rows, int fchunk,
                         int rows_per_cta) {
-    extern __shared__ float tile[];   // [n_table_rows][fchunk]
+    extern __shared__ __align__(16) float tile[];   // [n_table_rows][fchunk]
     const int f0 = blockIdx.y * fchunk;
     const int fw = min(fchunk, n_feat - f0);
     for (int i = threadIdx.x; i < n_table_rows * fchunk; i += blockDim.x) tile[i] = 0.f;
@@ -166,10 +166,23 @@ scatter_rows_add_kernel(const float* __restrict__ g, int64_t ldg, const int32_t*
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_table_rows * fchunk; i += blockDim.x) {
-        const int t = i / fchunk, f = i % fchunk;
-        const float v = tile[i];
-        if (f < fw && v != 0.f) atomicAdd(&table_grad[(int64_t)t * ldt + f0 + f], v);
+    const bool vec = (fchunk % 4 == 0) && (fw % 4 == 0) && (ldt % 4 == 0) && (f0 % 4 == 0) && gnm_aligned16(table_grad);
+    if (vec) {
+        // 128-bit vector reductions (sm_90+): a quarter of the atomic operations
+        const int q = fchunk >> 2;
+        for (int i = threadIdx.x; i < n_table_rows * q; i += blockDim.x) {
+            const int t = i / q, f = (i % q) * 4;
+            if (f >= fw) continue;
+            const float4 v = *reinterpret_cast<const float4*>(&tile[t * fchunk + f]);
+            if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+                atomicAdd(reinterpret_cast<float4*>(&table_grad[(int64_t)t * ldt + f0 + f]), v);
+        }
+    } else {
+        for (int i = threadIdx.x; i < n_table_rows * fchunk; i += blockDim.x) {
+            const int t = i / fchunk, f = i % fchunk;
+            const float v = tile[i];
+            if (f < fw && v != 0.f) atomicAdd(&table_grad[(int64_t)t * ldt + f0 + f], v);
+        }
     }
 }
 
@@ -226,7 +239,7 @@ extern "C" int gnm_scatter_rows_add(const float* g, int64_t ldg, const int32_t* 
     while ((int64_t)n_table_rows * fchunk * 4 > 96 * 1024 && fchunk > 1) fchunk = (fchunk + 1) / 2;
     if ((int64_t)n_table_rows * fchunk * 4 > 200 * 1024) return GNM_ERR_TOO_LARGE;
     const int fparts = (n_feat + fchunk - 1) / fchunk;
-    int ctas = 148 * 2 / fparts;
+    int ctas = 148 / fparts;
     if (ctas < 1) ctas = 1;
     int rows_per_cta = (n_rows + ctas - 1) / ctas;
     if (rows_per_cta < 64) rows_per_cta = 64;

@@ -18,13 +18,23 @@ __global__ void gather_nf_rows_kernel(const float* __restrict__ h_all, int64_t l
     }
 }
 
-// One CTA (8 warps) per graph; u_g staged in shared memory; one warp per node row.
+// One CTA (8 warps) per graph; u_g staged in shared memory. Vector path (F % 4 == 0): a group of F/4 lanes
+// covers one node row with 128-bit loads, 32/(F/4) rows per warp at a time, all L layer slices of a row in
+// flight together; scalar path otherwise (one warp per row).
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(GNM_FULL_MASK, v, o);
+    return v;
+}
+
+template <int LPR>   // lanes per row = F / 4 (power of two, <= 32); 0 = scalar path
 __global__ void __launch_bounds__(256)
 dgi_score_fwd_kernel(const float* __restrict__ h_all, int64_t layer_stride, int n_layers, int n_feat, int64_t ldh,
                      int n_rows, const float* __restrict__ u, const float* __restrict__ neg_table,
                      const int32_t* __restrict__ neg_idx, const int32_t* __restrict__ node_off,
                      const float* __restrict__ bias, float* __restrict__ out) {
-    extern __shared__ float us[];    // [n_layers * n_feat]
+    extern __shared__ __align__(16) float us[];    // [n_layers * n_feat]
     __shared__ float s_neg;
     const int g = blockIdx.x;
     const int nh = n_layers * n_feat;
@@ -42,17 +52,42 @@ dgi_score_fwd_kernel(const float* __restrict__ h_all, int64_t layer_stride, int 
     __syncthreads();
     const float sn = s_neg;
     const int r0 = node_off[g], r1 = node_off[g + 1];
-    for (int r = r0 + warp; r < r1; r += 8) {
-        float a = 0.f;
-        for (int l = 0; l < n_layers; ++l) {
-            const float* hr = h_all + l * layer_stride + (int64_t)r * ldh;
-            const float* ul = us + l * n_feat;
-            for (int f = lane; f < n_feat; f += 32) a = fmaf(hr[f], ul[f], a);
+    if (LPR > 0) {
+        constexpr int L = LPR > 0 ? LPR : 1;
+        constexpr int RPW = 32 / L;                 // rows per warp per iteration
+        const int sub = lane % L, grp = lane / L;
+        for (int rb = r0 + warp * RPW; rb < r1; rb += 8 * RPW) {
+            const int r = rb + grp;
+            float a = 0.f;
+            if (r < r1) {
+                const float* hr = h_all + (int64_t)r * ldh + sub * 4;
+                const float* ul = us + sub * 4;
+#pragma unroll 5
+                for (int l = 0; l < n_layers; ++l) {
+                    const float4 hv = ld_stream_f4(hr + l * layer_stride);
+                    const float4 uv = *reinterpret_cast<const float4*>(ul + l * n_feat);
+                    a = fmaf(hv.x, uv.x, a); a = fmaf(hv.y, uv.y, a); a = fmaf(hv.z, uv.z, a); a = fmaf(hv.w, uv.w, a);
+                }
+            }
+            a = group_sum<L>(a);
+            if (sub == 0 && r < r1) {
+                out[r] = a + b;
+                out[n_rows + r] = sn;
+            }
         }
-        a = warp_sum(a);
-        if (lane == 0) {
-            out[r] = a + b;
-            out[n_rows + r] = sn;
+    } else {
+        for (int r = r0 + warp; r < r1; r += 8) {
+            float a = 0.f;
+            for (int l = 0; l < n_layers; ++l) {
+                const float* hr = h_all + l * layer_stride + (int64_t)r * ldh;
+                const float* ul = us + l * n_feat;
+                for (int f = lane; f < n_feat; f += 32) a = fmaf(hr[f], ul[f], a);
+            }
+            a = warp_sum(a);
+            if (lane == 0) {
+                out[r] = a + b;
+                out[n_rows + r] = sn;
+            }
         }
     }
 }
@@ -138,14 +173,22 @@ extern "C" int gnm_dgi_score_fwd(const float* h_all, int64_t layer_stride, int n
     if (n_graphs == 0 || n_rows == 0) return GNM_OK;
     if (!h_all || !u || !neg_table || !neg_idx || !node_off || !out) return GNM_ERR_BAD_ARG;
     const size_t smem = (size_t)n_layers * n_feat * 4;
-    if (smem > 200 * 1024) return GNM_ERR_TOO_LARGE;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(dgi_score_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
-    dgi_score_fwd_kernel<<<n_graphs, 256, smem, gnm_cast_stream(stream)>>>(h_all, layer_stride, n_layers, n_feat, ldh,
-                                                                           n_rows, u, neg_table, neg_idx, node_off,
-                                                                           bias, out);
+    if (smem > 48 * 1024) return GNM_ERR_TOO_LARGE;
+    const int q = n_feat / 4;
+    const bool vec = (n_feat % 4 == 0) && (q & (q - 1)) == 0 && q <= 32 && (ldh % 4 == 0) && (layer_stride % 4 == 0) &&
+                     gnm_aligned16(h_all);
+#define GNM_DGI_FWD(LPR)                                                                                             \
+    dgi_score_fwd_kernel<LPR><<<n_graphs, 256, smem, gnm_cast_stream(stream)>>>(h_all, layer_stride, n_layers, n_feat, \
+                                                                                 ldh, n_rows, u, neg_table, neg_idx,   \
+                                                                                 node_off, bias, out)
+    if (!vec) GNM_DGI_FWD(0);
+    else if (q == 1) GNM_DGI_FWD(1);
+    else if (q == 2) GNM_DGI_FWD(2);
+    else if (q == 4) GNM_DGI_FWD(4);
+    else if (q == 8) GNM_DGI_FWD(8);
+    else if (q == 16) GNM_DGI_FWD(16);
+    else GNM_DGI_FWD(32);
+#undef GNM_DGI_FWD
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;
 }

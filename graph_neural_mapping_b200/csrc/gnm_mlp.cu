@@ -299,9 +299,137 @@ bn_relu_readout_kernel(const float* __restrict__ z, int64_t ldz, int n_feat, con
     }
 }
 
+// 128-bit version (F % 4 == 0, aligned): F/4 lanes cover a row, 256/(F/4) rows per pass, two passes in flight.
+__global__ void __launch_bounds__(256)
+bn_relu_readout_vec_kernel(const float* __restrict__ z, int64_t ldz, int n_feat, const float* __restrict__ scale,
+                           const float* __restrict__ shift, float* __restrict__ h, int64_t ldh,
+                           const int32_t* __restrict__ node_off, const float* __restrict__ pool_scale,
+                           float* __restrict__ pooled, int64_t ld_pooled) {
+    const int g = blockIdx.x;
+    const int lpr = n_feat >> 2;                 // lanes per row (<= 256)
+    const int rpp = 256 / lpr;                   // rows per pass
+    const int sub = threadIdx.x % lpr, rr = threadIdx.x / lpr;
+    __shared__ float4 red[256];
+    const int r0 = node_off[g], r1 = node_off[g + 1];
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rr < rpp) {
+        const float4 sc = *reinterpret_cast<const float4*>(scale + sub * 4);
+        const float4 sh = *reinterpret_cast<const float4*>(shift + sub * 4);
+        int r = r0 + rr;
+        for (; r + rpp < r1; r += 2 * rpp) {
+            const float4 a = ld_stream_f4(z + (int64_t)r * ldz + sub * 4);
+            const float4 b = ld_stream_f4(z + (int64_t)(r + rpp) * ldz + sub * 4);
+            float4 va, vb;
+            va.x = fmaxf(fmaf(a.x, sc.x, sh.x), 0.f); va.y = fmaxf(fmaf(a.y, sc.y, sh.y), 0.f);
+            va.z = fmaxf(fmaf(a.z, sc.z, sh.z), 0.f); va.w = fmaxf(fmaf(a.w, sc.w, sh.w), 0.f);
+            vb.x = fmaxf(fmaf(b.x, sc.x, sh.x), 0.f); vb.y = fmaxf(fmaf(b.y, sc.y, sh.y), 0.f);
+            vb.z = fmaxf(fmaf(b.z, sc.z, sh.z), 0.f); vb.w = fmaxf(fmaf(b.w, sc.w, sh.w), 0.f);
+            if (h != nullptr) {
+                *reinterpret_cast<float4*>(h + (int64_t)r * ldh + sub * 4) = va;
+                *reinterpret_cast<float4*>(h + (int64_t)(r + rpp) * ldh + sub * 4) = vb;
+            }
+            s.x += va.x + vb.x; s.y += va.y + vb.y; s.z += va.z + vb.z; s.w += va.w + vb.w;
+        }
+        for (; r < r1; r += rpp) {
+            const float4 a = ld_stream_f4(z + (int64_t)r * ldz + sub * 4);
+            float4 va;
+            va.x = fmaxf(fmaf(a.x, sc.x, sh.x), 0.f); va.y = fmaxf(fmaf(a.y, sc.y, sh.y), 0.f);
+            va.z = fmaxf(fmaf(a.z, sc.z, sh.z), 0.f); va.w = fmaxf(fmaf(a.w, sc.w, sh.w), 0.f);
+            if (h != nullptr) *reinterpret_cast<float4*>(h + (int64_t)r * ldh + sub * 4) = va;
+            s.x += va.x; s.y += va.y; s.z += va.z; s.w += va.w;
+        }
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (pooled != nullptr && threadIdx.x < lpr) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < rpp; ++k) {
+            const float4 v = red[k * lpr + threadIdx.x];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        const float ps = pool_scale ? pool_scale[g] : 1.f;
+        float* o = pooled + (int64_t)g * ld_pooled + threadIdx.x * 4;
+        o[0] = t.x * ps; o[1] = t.y * ps; o[2] = t.z * ps; o[3] = t.w * ps;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // backward of relu(bn(z)), pass 1: assemble the incoming gradient, mask, reduce
 // ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+relu_bn_bwd_reduce_vec_kernel(const float* __restrict__ z, int64_t ldz, int n_feat, const float* __restrict__ scale,
+                              const float* __restrict__ shift, const float* __restrict__ mean,
+                              const float* __restrict__ rstd, const float* __restrict__ d_out, int64_t ld_dout,
+                              const float* __restrict__ d_pooled, int64_t ld_dpooled,
+                              const float* __restrict__ pool_scale, const float* __restrict__ d_score,
+                              const float* __restrict__ u, int64_t ldu, const float* __restrict__ d_neg,
+                              int64_t ld_dneg, int n_neg, const int32_t* __restrict__ node_off,
+                              float* __restrict__ dy, int64_t lddy, double* __restrict__ stats) {
+    const int g = blockIdx.x;
+    const int lpr = n_feat >> 2;
+    const int rpp = 256 / lpr;
+    const int sub = threadIdx.x % lpr, rr = threadIdx.x / lpr;
+    __shared__ float4 red1[256], red2[256];
+    const int r0 = node_off[g], r1 = node_off[g + 1];
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+    if (rr < rpp) {
+        const int f = sub * 4;
+        const float4 sc = *reinterpret_cast<const float4*>(scale + f), sh = *reinterpret_cast<const float4*>(shift + f);
+        const float4 mu = *reinterpret_cast<const float4*>(mean + f), rs = *reinterpret_cast<const float4*>(rstd + f);
+        float4 gp = make_float4(0.f, 0.f, 0.f, 0.f), uu = gp;
+        if (d_pooled != nullptr) {
+            const float ps = pool_scale ? pool_scale[g] : 1.f;
+            const float* q = d_pooled + (int64_t)g * ld_dpooled + f;
+            gp = make_float4(q[0] * ps, q[1] * ps, q[2] * ps, q[3] * ps);
+        }
+        if (d_score != nullptr) {
+            const float* q = u + (int64_t)g * ldu + f;
+            uu = make_float4(q[0], q[1], q[2], q[3]);
+        }
+        for (int r = r0 + rr; r < r1; r += rpp) {
+            const float4 zv = ld_stream_f4(z + (int64_t)r * ldz + f);
+            float4 gr = gp;
+            if (d_out != nullptr) {
+                const float4 t = ld_stream_f4(d_out + (int64_t)r * ld_dout + f);
+                gr.x += t.x; gr.y += t.y; gr.z += t.z; gr.w += t.w;
+            }
+            if (d_score != nullptr) {
+                const float ds = d_score[r];
+                gr.x = fmaf(ds, uu.x, gr.x); gr.y = fmaf(ds, uu.y, gr.y); gr.z = fmaf(ds, uu.z, gr.z); gr.w = fmaf(ds, uu.w, gr.w);
+            }
+            if (d_neg != nullptr && r < n_neg) {
+                const float* q = d_neg + (int64_t)r * ld_dneg + f;
+                gr.x += q[0]; gr.y += q[1]; gr.z += q[2]; gr.w += q[3];
+            }
+            float4 v;
+            v.x = (fmaf(zv.x, sc.x, sh.x) > 0.f) ? gr.x : 0.f;
+            v.y = (fmaf(zv.y, sc.y, sh.y) > 0.f) ? gr.y : 0.f;
+            v.z = (fmaf(zv.z, sc.z, sh.z) > 0.f) ? gr.z : 0.f;
+            v.w = (fmaf(zv.w, sc.w, sh.w) > 0.f) ? gr.w : 0.f;
+            *reinterpret_cast<float4*>(dy + (int64_t)r * lddy + f) = v;
+            s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+            s2.x = fmaf(v.x, (zv.x - mu.x) * rs.x, s2.x); s2.y = fmaf(v.y, (zv.y - mu.y) * rs.y, s2.y);
+            s2.z = fmaf(v.z, (zv.z - mu.z) * rs.z, s2.z); s2.w = fmaf(v.w, (zv.w - mu.w) * rs.w, s2.w);
+        }
+    }
+    red1[threadIdx.x] = s1;
+    red2[threadIdx.x] = s2;
+    __syncthreads();
+    if (stats != nullptr && threadIdx.x < lpr) {
+        double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+        for (int k = 0; k < rpp; ++k) {
+            const float4 v = red1[k * lpr + threadIdx.x], w = red2[k * lpr + threadIdx.x];
+            a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+            b[0] += w.x; b[1] += w.y; b[2] += w.z; b[3] += w.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            atomicAdd(&stats[threadIdx.x * 4 + q], a[q]);
+            atomicAdd(&stats[n_feat + threadIdx.x * 4 + q], b[q]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 relu_bn_bwd_reduce_kernel(const float* __restrict__ z, int64_t ldz, int n_feat, const float* __restrict__ scale,
                           const float* __restrict__ shift, const float* __restrict__ mean,
@@ -450,6 +578,15 @@ extern "C" int gnm_bn_relu_readout(const float* z, int64_t ldz, int n_rows, int 
     if (n_rows < 0 || n_feat < 0 || n_graphs < 0) return GNM_ERR_BAD_ARG;
     if (n_rows == 0 || n_feat == 0 || n_graphs == 0) return GNM_OK;
     if (!z || !scale || !shift || !node_off) return GNM_ERR_BAD_ARG;
+    const bool vec = (n_feat % 4 == 0) && n_feat <= 1024 && (ldz % 4 == 0) && gnm_aligned16(z) && gnm_aligned16(scale) &&
+                     gnm_aligned16(shift) && (h == nullptr || ((ldh % 4 == 0) && gnm_aligned16(h)));
+    if (vec) {
+        bn_relu_readout_vec_kernel<<<n_graphs, 256, 0, gnm_cast_stream(stream)>>>(z, ldz, n_feat, scale, shift, h, ldh,
+                                                                                  node_off, pool_scale, pooled,
+                                                                                  ld_pooled);
+        GNM_RETURN_IF_LAUNCH_FAILED();
+        return GNM_OK;
+    }
     dim3 grid(n_graphs, (n_feat + 255) / 256);
     bn_relu_readout_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(z, ldz, n_feat, scale, shift, h, ldh, node_off,
                                                                       pool_scale, pooled, ld_pooled);
@@ -467,6 +604,16 @@ extern "C" int gnm_relu_bn_bwd_reduce(const float* z, int64_t ldz, int n_rows, i
     if (n_rows == 0 || n_feat == 0 || n_graphs == 0) return GNM_OK;
     if (!z || !scale || !shift || !mean || !rstd || !node_off || !dy) return GNM_ERR_BAD_ARG;
     if (d_score != nullptr && u == nullptr) return GNM_ERR_BAD_ARG;
+    const bool vec = (n_feat % 4 == 0) && n_feat <= 1024 && (ldz % 4 == 0) && (lddy % 4 == 0) && gnm_aligned16(z) &&
+                     gnm_aligned16(dy) && gnm_aligned16(scale) && gnm_aligned16(shift) && gnm_aligned16(mean) &&
+                     gnm_aligned16(rstd) && (d_out == nullptr || ((ld_dout % 4 == 0) && gnm_aligned16(d_out)));
+    if (vec) {
+        relu_bn_bwd_reduce_vec_kernel<<<n_graphs, 256, 0, gnm_cast_stream(stream)>>>(
+            z, ldz, n_feat, scale, shift, mean, rstd, d_out, ld_dout, d_pooled, ld_dpooled, pool_scale, d_score, u, ldu,
+            d_neg, ld_dneg, n_neg, node_off, dy, lddy, stats);
+        GNM_RETURN_IF_LAUNCH_FAILED();
+        return GNM_OK;
+    }
     dim3 grid(n_graphs, (n_feat + 255) / 256);
     relu_bn_bwd_reduce_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(
         z, ldz, n_feat, scale, shift, mean, rstd, d_out, ld_dout, d_pooled, ld_dpooled, pool_scale, d_score, u, ldu,

@@ -513,7 +513,9 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                 dw1t = torch.zeros(n_in, n_out, dtype=torch.float32, device=dev)
                 _ops.scatter_rows_add(g_agg, bs.tags, dw1t)
                 dw = dw1t.t().contiguous()
-                _ops.linear_wgrad(dz_u, None, None, None, None, db)
+                colsum = torch.zeros(2 * n_out, dtype=torch.float64, device=dev)
+                _ops.col_stats(dz_u, colsum)                      # d bias = column sums of dz
+                db = colsum[:n_out].to(torch.float32)
                 if learn_eps:
                     _ops.dot_rows(dz_u, sv.w1t, bs.tags, d_eps[layer:layer + 1])
                 if need_x_grad:
