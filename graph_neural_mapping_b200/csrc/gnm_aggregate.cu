@@ -147,7 +147,7 @@ dot_rows_kernel(const float* __restrict__ a, int64_t lda, const float* __restric
 __global__ void __launch_bounds__(256)
 scatter_rows_add_kernel(const float* __restrict__ g, int64_t ldg, const int32_t* __restrict__ tags, int n_rows,
                         int n_feat, float* __restrict__ table_grad, int64_t ldt, int n_table_rows, int fchunk,
-                        int rows_per_cta) {
+                        int rows_per_cta, float* __restrict__ workspace) {
     extern __shared__ __align__(16) float tile[];   // [n_table_rows][fchunk]
     const int f0 = blockIdx.y * fchunk;
     const int fw = min(fchunk, n_feat - f0);
@@ -166,23 +166,34 @@ scatter_rows_add_kernel(const float* __restrict__ g, int64_t ldg, const int32_t*
         }
     }
     __syncthreads();
-    const bool vec = (fchunk % 4 == 0) && (fw % 4 == 0) && (ldt % 4 == 0) && (f0 % 4 == 0) && gnm_aligned16(table_grad);
-    if (vec) {
-        // 128-bit vector reductions (sm_90+): a quarter of the atomic operations
-        const int q = fchunk >> 2;
-        for (int i = threadIdx.x; i < n_table_rows * q; i += blockDim.x) {
-            const int t = i / q, f = (i % q) * 4;
-            if (f >= fw) continue;
-            const float4 v = *reinterpret_cast<const float4*>(&tile[t * fchunk + f]);
-            if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
-                atomicAdd(reinterpret_cast<float4*>(&table_grad[(int64_t)t * ldt + f0 + f]), v);
-        }
-    } else {
-        for (int i = threadIdx.x; i < n_table_rows * fchunk; i += blockDim.x) {
-            const int t = i / fchunk, f = i % fchunk;
-            const float v = tile[i];
-            if (f < fw && v != 0.f) atomicAdd(&table_grad[(int64_t)t * ldt + f0 + f], v);
-        }
+    if (workspace != nullptr) {
+        // deterministic two-stage merge: this CTA's tile goes to its own workspace slice (plain stores)
+        float* mine = workspace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)n_table_rows * fchunk;
+        for (int i = threadIdx.x; i < n_table_rows * fchunk; i += blockDim.x) mine[i] = tile[i];
+        return;
+    }
+    for (int i = threadIdx.x; i < n_table_rows * fchunk; i += blockDim.x) {
+        const int t = i / fchunk, f = i % fchunk;
+        const float v = tile[i];
+        if (f < fw && v != 0.f) atomicAdd(&table_grad[(int64_t)t * ldt + f0 + f], v);
+    }
+}
+
+// second stage: table_grad[t, f0 + f] += sum over the CTAs' partial tiles (fixed order: deterministic)
+__global__ void __launch_bounds__(256)
+scatter_rows_merge_kernel(const float* __restrict__ workspace, int n_ctas, int n_table_rows, int fchunk, int n_feat,
+                          float* __restrict__ table_grad, int64_t ldt) {
+    const int fpart = blockIdx.y;
+    const int f0 = fpart * fchunk;
+    const int fw = min(fchunk, n_feat - f0);
+    const size_t tile = (size_t)n_table_rows * fchunk;
+    const float* base = workspace + (size_t)fpart * n_ctas * tile;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_table_rows * fchunk; i += gridDim.x * blockDim.x) {
+        const int t = i / fchunk, f = i % fchunk;
+        if (f >= fw) continue;
+        float a = 0.f;
+        for (int c = 0; c < n_ctas; ++c) a += base[(size_t)c * tile + i];
+        table_grad[(int64_t)t * ldt + f0 + f] += a;
     }
 }
 
@@ -230,7 +241,8 @@ extern "C" int gnm_dot_rows(const float* a, int64_t lda, const float* b, int64_t
 }
 
 extern "C" int gnm_scatter_rows_add(const float* g, int64_t ldg, const int32_t* tags, int n_rows, int n_feat,
-                                    float* table_grad, int64_t ldt, int n_table_rows, gnm_stream_t stream) {
+                                    float* table_grad, int64_t ldt, int n_table_rows, float* workspace,
+                                    int64_t workspace_floats, gnm_stream_t stream) {
     if (n_rows < 0 || n_feat < 0 || n_table_rows < 0) return GNM_ERR_BAD_ARG;
     if (n_rows == 0 || n_feat == 0 || n_table_rows == 0) return GNM_OK;
     if (!g || !tags || !table_grad) return GNM_ERR_BAD_ARG;
@@ -239,7 +251,7 @@ extern "C" int gnm_scatter_rows_add(const float* g, int64_t ldg, const int32_t* 
     while ((int64_t)n_table_rows * fchunk * 4 > 96 * 1024 && fchunk > 1) fchunk = (fchunk + 1) / 2;
     if ((int64_t)n_table_rows * fchunk * 4 > 200 * 1024) return GNM_ERR_TOO_LARGE;
     const int fparts = (n_feat + fchunk - 1) / fchunk;
-    int ctas = 148 / fparts;
+    int ctas = 148 * 2 / fparts;
     if (ctas < 1) ctas = 1;
     int rows_per_cta = (n_rows + ctas - 1) / ctas;
     if (rows_per_cta < 64) rows_per_cta = 64;
@@ -247,9 +259,33 @@ extern "C" int gnm_scatter_rows_add(const float* g, int64_t ldg, const int32_t* 
     const size_t smem = (size_t)n_table_rows * fchunk * 4;
     cudaError_t e = cudaFuncSetAttribute(scatter_rows_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    const int64_t need = (int64_t)ctas * fparts * n_table_rows * fchunk;
+    float* ws = (workspace != nullptr && workspace_floats >= need) ? workspace : nullptr;
     dim3 grid(ctas, fparts);
     scatter_rows_add_kernel<<<grid, 256, smem, gnm_cast_stream(stream)>>>(g, ldg, tags, n_rows, n_feat, table_grad, ldt,
-                                                                          n_table_rows, fchunk, rows_per_cta);
+                                                                          n_table_rows, fchunk, rows_per_cta, ws);
     GNM_RETURN_IF_LAUNCH_FAILED();
+    if (ws != nullptr) {
+        int mb = (n_table_rows * fchunk + 255) / 256;
+        if (mb > 148 * 4) mb = 148 * 4;
+        dim3 mgrid(mb, fparts);
+        scatter_rows_merge_kernel<<<mgrid, 256, 0, gnm_cast_stream(stream)>>>(ws, ctas, n_table_rows, fchunk, n_feat,
+                                                                              table_grad, ldt);
+        GNM_RETURN_IF_LAUNCH_FAILED();
+    }
     return GNM_OK;
+}
+
+/* Workspace size (floats) for the deterministic two-stage path of gnm_scatter_rows_add. */
+extern "C" int64_t gnm_scatter_rows_workspace(int n_rows, int n_feat, int n_table_rows) {
+    if (n_rows <= 0 || n_feat <= 0 || n_table_rows <= 0) return 0;
+    int fchunk = n_feat;
+    while ((int64_t)n_table_rows * fchunk * 4 > 96 * 1024 && fchunk > 1) fchunk = (fchunk + 1) / 2;
+    const int fparts = (n_feat + fchunk - 1) / fchunk;
+    int ctas = 148 * 2 / fparts;
+    if (ctas < 1) ctas = 1;
+    int rows_per_cta = (n_rows + ctas - 1) / ctas;
+    if (rows_per_cta < 64) rows_per_cta = 64;
+    ctas = (n_rows + rows_per_cta - 1) / rows_per_cta;
+    return (int64_t)ctas * fparts * n_table_rows * fchunk;
 }

@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libgnm.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _c_i32 = ctypes.c_int
 _c_i64 = ctypes.c_int64
@@ -30,7 +30,8 @@ SIGNATURES = {
     "gnm_bitmap_build": [_p, _p, _p, _p, _c_i32, _p, _p, _p],
     "gnm_aggregate_dense": [_p, _p, _p, _c_i32, _c_i32, _p, _c_i64, _p, _p, _c_i64, _c_i32, _c_i32, _p, _p, _p],
     "gnm_dot_rows": [_p, _c_i64, _p, _c_i64, _p, _c_i32, _c_i32, _p, _p],
-    "gnm_scatter_rows_add": [_p, _c_i64, _p, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p],
+    "gnm_scatter_rows_add": [_p, _c_i64, _p, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p, _c_i64, _p],
+    "gnm_scatter_rows_workspace": [_c_i32, _c_i32, _c_i32],
     "gnm_linear": [_p, _c_i64, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p, _p, _p, _p, _c_i64, _c_i32, _p, _p],
     "gnm_linear_wgrad": [_p, _c_i64, _p, _c_i64, _c_i32, _c_i32, _c_i32, _p, _p, _p, _c_i64, _p, _p],
     "gnm_bn_bwd_coeffs": [_p, _c_f64, _p, _p, _p, _p, _c_i32, _p],
@@ -76,6 +77,7 @@ def load():
         fn = getattr(lib, name)        # AttributeError if the symbol is missing
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int
+    lib.gnm_scatter_rows_workspace.restype = ctypes.c_int64
     lib.gnm_error_string.argtypes = [ctypes.c_int]
     lib.gnm_error_string.restype = ctypes.c_char_p
     got = lib.gnm_abi_version()

@@ -140,8 +140,11 @@ def dot_rows(a, b, b_map, out):
 def scatter_rows_add(g, tags, table_grad):
     gp, ldg = _mat(g)
     tp, ldt = _mat(table_grad)
+    need = int(_lib().gnm_scatter_rows_workspace(int(g.shape[0]), int(g.shape[1]), int(table_grad.shape[0])))
+    ws = torch.empty(max(need, 1), dtype=torch.float32, device=g.device)
     _libmod.check(_lib().gnm_scatter_rows_add(gp, ldg, _ptr(tags, torch.int32), int(g.shape[0]), int(g.shape[1]),
-                                              tp, ldt, int(table_grad.shape[0]), _stream(g)), "gnm_scatter_rows_add")
+                                              tp, ldt, int(table_grad.shape[0]), _ptr(ws), need, _stream(g)),
+                  "gnm_scatter_rows_add")
     return table_grad
 
 

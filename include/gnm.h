@@ -32,7 +32,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 5
+#define GNM_ABI_VERSION 6
 
 typedef void* gnm_stream_t;
 
@@ -106,9 +106,13 @@ int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* node_off, con
 int gnm_dot_rows(const float* a, int64_t lda, const float* b, int64_t ldb, const int32_t* b_map,
                  int n_rows, int n_feat, double* out, gnm_stream_t stream);
 
-/* dW1^T[tag[r], :] += g[r, :] : gradient of the gathered table (layer-0 one-hot path). */
+/* dW1^T[tag[r], :] += g[r, :] : gradient of the gathered table (layer-0 one-hot path).
+ * workspace (nullable, workspace_floats >= gnm_scatter_rows_workspace(...)) selects the deterministic two-stage
+ * merge (per-CTA partial tiles + fixed-order sum); without it partial tiles are merged with fp32 atomics. */
 int gnm_scatter_rows_add(const float* g, int64_t ldg, const int32_t* tags, int n_rows, int n_feat,
-                         float* table_grad, int64_t ldt, int n_table_rows, gnm_stream_t stream);
+                         float* table_grad, int64_t ldt, int n_table_rows, float* workspace,
+                         int64_t workspace_floats, gnm_stream_t stream);
+int64_t gnm_scatter_rows_workspace(int n_rows, int n_feat, int n_table_rows);
 
 /* ---- MLP: Linear + BatchNorm + ReLU ------------------------------------------------------ */
 
