@@ -300,16 +300,28 @@ extern "C" int gnm_bitmap_build(const int32_t* rowptr, const int32_t* colidx, co
     return GNM_OK;
 }
 
+// tcgen05 / TMEM implementation (gnm_aggregate_tc.cu); GNM_ERR_TOO_LARGE = does not fit, use the mma.sync kernel
+int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
+                            int n_max, const float* src, int64_t ld_src, const int32_t* src_map, float* dst,
+                            int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
+                            cudaStream_t stream);
+
 extern "C" int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr,
                                    int n_graphs, int n_max, const float* src, int64_t ld_src, const int32_t* src_map,
                                    float* dst, int64_t ld_dst, int n_feat, int mode, const float* eps,
-                                   const float* bias, gnm_stream_t stream) {
+                                   const float* bias, int impl, gnm_stream_t stream) {
     if (n_graphs < 0 || n_max < 0 || n_feat < 0 || mode < 0 || mode > 2) return GNM_ERR_BAD_ARG;
     if (n_graphs == 0 || n_max == 0 || n_feat == 0) return GNM_OK;
     if (!bitmap_addr || !node_off || !src || !dst || (mode != 0 && !rowptr)) return GNM_ERR_BAD_ARG;
     if ((n_feat % 4) || (ld_src % 4) || (ld_dst % 2) || !gnm_aligned16(src) || !gnm_aligned16(dst) ||
         (bias && !gnm_aligned16(bias)))
         return GNM_ERR_ALIGN;
+    if (impl < 0 || impl > 2) return GNM_ERR_BAD_ARG;
+    if (impl != 1) {
+        const int rc = gnm_launch_aggregate_tc(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, ld_src, src_map, dst,
+                                               ld_dst, n_feat, mode, eps, bias, gnm_cast_stream(stream));
+        if (rc == GNM_OK || impl == 2 || (rc != GNM_ERR_TOO_LARGE && rc != GNM_ERR_ALIGN)) return rc;
+    }
     AggDenseParams p;
     p.bitmap_addr = bitmap_addr; p.node_off = node_off; p.rowptr = rowptr; p.src = src; p.src_map = src_map;
     p.dst = dst; p.eps = eps; p.bias = bias; p.ld_src = ld_src; p.ld_dst = ld_dst; p.n_graphs = n_graphs;

@@ -1,0 +1,367 @@
+// Neighbour aggregation on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// Same contract as aggregate_dense_kernel (gnm_aggregate_dense.cu): per graph P_g = A_g . H_g with A_g a dense
+// 0/1 block expanded from the graph's bitmap and H_g (fp32) split exactly into three bf16 planes. The legacy
+// mma.sync path tops out near 200 TFLOP/s on this part (measured: 16 warps change nothing, ~0.35 kMAC/clk/SM);
+// tcgen05 runs the same bf16 MACs at 4 kMAC/clk/SM, which moves the kernel from tensor-bound to HBM-bound.
+//
+// One persistent CTA per SM, work item = (graph, 64-feature slab), N <= 416 nodes:
+//   * B operand = the three planes side by side as ONE [K x 192] MN-major matrix (no swizzle; core matrix
+//     = 8 k-rows x 16 B; n-cores at SBO, k-cores at LBO), resident in shared memory for the whole graph
+//     (154 KB). N = 192 per MMA reads the A tile once for all three planes and keeps shared-memory traffic
+//     under the MMA time: 2(M+N)/(MN) = 0.026 B/MAC.
+//   * A operand = 128-row x 64-column tiles of the adjacency, expanded from bitmap words into bf16 0/1
+//     K-major core matrices by 8 producer warps, 4-stage ring (16 KB per stage).
+//   * D = 128 lanes x 192 fp32 columns in TMEM, two slots: the 4 epilogue warps drain slot s (tcgen05.ld,
+//     hi+mid+lo summed in registers, average / eps self term / bias, fp32 stores) while the MMA thread fills
+//     slot s^1 with the next 128-row tile.
+//   * warp roles: 0-3 epilogue, 4 MMA issue + TMEM alloc, 5-12 producers; mbarriers: a_full/a_empty[4],
+//     acc_full/acc_empty[2], b_full, b_free. tcgen05.commit releases A stages / publishes accumulators.
+//   * every wait is bounded: on a timeout the kernel raises an abort flag and drains instead of hanging.
+#include <cuda_bf16.h>
+
+#include "gnm_common.cuh"
+
+namespace {
+
+constexpr int TC_KC = 64;                      // adjacency columns per A stage (4 MMAs of K = 16)
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_KCORE = 16 * 128;           // bytes between k-cores of an A stage ([k-core][row group][128 B])
+constexpr int TC_A_STAGE = (TC_KC / 8) * TC_A_KCORE;      // 16 KB
+constexpr int TC_N = 192;                      // three 64-feature planes side by side
+constexpr int TC_SLAB = 64;
+constexpr int TC_MAX_NODES = 416;
+constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 8;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;   // 416
+constexpr int TC_TMEM_COLS = 512;
+constexpr long long TC_TIMEOUT_CYCLES = 4000000000LL;
+
+__device__ int g_tc_abort = 0;
+
+struct AggTcParams {
+    const int64_t* bitmap_addr;
+    const int32_t* node_off;
+    const int32_t* rowptr;
+    const float* src;
+    const int32_t* src_map;
+    float* dst;
+    const float* eps;
+    const float* bias;
+    int64_t ld_src, ld_dst;
+    int n_graphs, n_feat, mode, n_slabs, kcores_max;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: false on timeout (the caller raises the abort flag and drains)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return true;
+        if (*abort_flag) return false;
+        if (clock64() - t0 > TC_TIMEOUT_CYCLES) {
+            *abort_flag = 1;
+            g_tc_abort = 1;
+            return false;
+        }
+    }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor, no swizzle (layout_type 0), version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
+__device__ __forceinline__ uint32_t bits2_bf16x2(uint32_t x) { return (x & 1u) * 0x3F80u + (x & 2u) * 0x1FC00000u; }
+
+__device__ __forceinline__ void split3_tc(float x, float& hi, float& mid, float& lo) {
+    hi = __bfloat162float(__float2bfloat16_rn(x));
+    const float r1 = x - hi;
+    mid = __bfloat162float(__float2bfloat16_rn(r1));
+    lo = r1 - mid;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTcParams p) {
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 6];
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_abort;
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + TC_STAGES;
+    uint64_t* acc_full = bars + 2 * TC_STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* b_full = acc_empty + 2;
+    uint64_t* b_free = b_full + 1;
+    const int b_ncore_stride = p.kcores_max * 128 + 16;            // SBO of B (padded: conflict-free plane fill)
+    unsigned char* sm_a = tc_smem;                                  // TC_STAGES x 16 KB
+    unsigned char* sm_b = tc_smem + TC_STAGES * TC_A_STAGE;         // 24 n-cores x b_ncore_stride
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    volatile int* abort_flag = &s_abort;
+    if (tid == 0) {
+        s_abort = 0;
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&a_full[i], TC_PROD_WARPS); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], TC_EPI_WARPS); }
+        mbar_init(b_full, TC_PROD_WARPS);
+        mbar_init(b_free, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TC_EPI_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const int n_items = p.n_graphs * p.n_slabs;
+
+    if (warp < TC_EPI_WARPS) {
+        // ================================ epilogue: TMEM -> registers -> global ==========================
+        uint32_t acc_it = 0;
+        const float self_c = p.eps ? 1.f + __ldg(p.eps) : 0.f;
+        for (int item = blockIdx.x; item < n_items && !*abort_flag; item += gridDim.x) {
+            const int gi = item / p.n_slabs, slab = item % p.n_slabs;
+            const int n0 = p.node_off[gi], n = p.node_off[gi + 1] - n0;
+            const int f0 = slab * TC_SLAB;
+            const int n_mt = (n + 127) >> 7;
+            for (int mt = 0; mt < n_mt; ++mt, ++acc_it) {
+                const uint32_t slot = acc_it & 1, ph = (acc_it >> 1) & 1;
+                if (!mbar_wait(&acc_full[slot], ph, abort_flag)) break;
+                tc_fence_after();
+                const int r = mt * 128 + warp * 32 + lane;
+                const bool row_ok = r < n;
+                const int gr = n0 + (row_ok ? r : 0);
+                float inv_deg = 1.f;
+                if (p.mode == 1) inv_deg = (float)(p.rowptr[gr + 1] - p.rowptr[gr]);
+                const int64_t sr = p.src_map ? (int64_t)p.src_map[gr] : (int64_t)gr;
+#pragma unroll
+                for (int c0 = 0; c0 < TC_SLAB; c0 += 32) {
+                    uint32_t hi[32], mid[32], lo[32];
+                    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + slot * TC_N + c0;
+                    tmem_ld32(taddr, hi);
+                    tmem_ld32(taddr + 64, mid);
+                    tmem_ld32(taddr + 128, lo);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (row_ok) {
+                        float* out = p.dst + (int64_t)gr * p.ld_dst + f0 + c0;
+                        const float* self = p.src + sr * p.ld_src + f0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (f0 + c0 + j >= p.n_feat) break;
+                            float v[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                v[q] = (__uint_as_float(lo[j + q]) + __uint_as_float(mid[j + q])) + __uint_as_float(hi[j + q]);
+                            if (p.mode == 1) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) v[q] /= inv_deg;
+                            }
+                            if (p.eps) {
+                                const float4 s = __ldg(reinterpret_cast<const float4*>(self + j));
+                                v[0] = fmaf(self_c, s.x, v[0]); v[1] = fmaf(self_c, s.y, v[1]);
+                                v[2] = fmaf(self_c, s.z, v[2]); v[3] = fmaf(self_c, s.w, v[3]);
+                            }
+                            if (p.bias) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + f0 + c0 + j));
+                                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+                            }
+                            *reinterpret_cast<float4*>(out + j) = make_float4(v[0], v[1], v[2], v[3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[slot]);
+            }
+        }
+    } else if (warp == TC_EPI_WARPS) {
+        // ================================ MMA issue (one thread) ==========================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(TC_N >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);   // f32 acc, bf16 x bf16, A K-major, B MN-major
+            const uint32_t a_base = smem_u32(sm_a), b_base = smem_u32(sm_b);
+            uint32_t a_it = 0, acc_it = 0, b_it = 0;
+            bool ok = true;
+            for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, ++b_it) {
+                const int gi = item / p.n_slabs;
+                const int n = p.node_off[gi + 1] - p.node_off[gi];
+                const int n_mt = (n + 127) >> 7;
+                const int ksteps_total = (n + 15) >> 4;
+                const int n_kc = (ksteps_total + 3) >> 2;
+                if (!(ok = mbar_wait(b_full, b_it & 1, abort_flag))) break;
+                tc_fence_after();
+                for (int mt = 0; mt < n_mt && ok; ++mt, ++acc_it) {
+                    const uint32_t slot = acc_it & 1, ph = (acc_it >> 1) & 1;
+                    if (!(ok = mbar_wait(&acc_empty[slot], ph ^ 1, abort_flag))) break;
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem + slot * TC_N;
+                    for (int kc = 0; kc < n_kc; ++kc, ++a_it) {
+                        const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
+                        if (!(ok = mbar_wait(&a_full[s], aph, abort_flag))) break;
+                        tc_fence_after();
+                        const int ks_n = min(4, ksteps_total - kc * 4);
+                        for (int ks = 0; ks < ks_n; ++ks) {
+                            const uint64_t da = umma_desc(a_base + s * TC_A_STAGE + ks * 2 * TC_A_KCORE, TC_A_KCORE, 128);
+                            const uint64_t db = umma_desc(b_base + (kc * 8 + ks * 2) * 128, 128, (uint32_t)b_ncore_stride);
+                            const uint32_t accum = (kc | ks) ? 1u : 0u;
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+                        }
+                        umma_commit(&a_empty[s]);          // frees the A stage when these MMAs retire
+                    }
+                    if (ok) umma_commit(&acc_full[slot]);  // accumulator complete -> epilogue
+                }
+                if (ok) umma_commit(b_free);               // all MMAs reading this graph's B planes are done
+            }
+        }
+    } else {
+        // ================================ producers: B planes once per item, A tiles per (row tile, k chunk) ====
+        const int ptid = tid - (TC_EPI_WARPS + 1) * 32;                  // 0..255
+        uint32_t a_it = 0, b_it = 0;
+        bool ok = true;
+        for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, ++b_it) {
+            const int gi = item / p.n_slabs, slab = item % p.n_slabs;
+            const int n0 = p.node_off[gi], n = p.node_off[gi + 1] - n0;
+            const int f0 = slab * TC_SLAB;
+            const int n_mt = (n + 127) >> 7;
+            const int ksteps_total = (n + 15) >> 4;
+            const int n_kc = (ksteps_total + 3) >> 2;
+            const int kpad = ksteps_total * 16;
+            const int words = (n + 31) >> 5;
+            const uint32_t* __restrict__ bm = reinterpret_cast<const uint32_t*>(p.bitmap_addr[gi]);
+            // ---- B planes: wait until the previous item's MMAs have retired
+            if (!(ok = mbar_wait(b_free, (b_it & 1) ^ 1, abort_flag))) break;
+            for (int idx = ptid; idx < kpad * 16; idx += TC_PROD_WARPS * 32) {
+                const int k = idx >> 4, c4 = idx & 15;
+                const int col = f0 + c4 * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < n && col < p.n_feat) {
+                    const int jr = n0 + k;
+                    const int64_t sr = p.src_map ? (int64_t)p.src_map[jr] : (int64_t)jr;
+                    v = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
+                    if (p.mode == 2) {
+                        const float w = 1.f / (float)(p.rowptr[jr + 1] - p.rowptr[jr]);
+                        v.x *= w; v.y *= w; v.z *= w; v.w *= w;
+                    }
+                }
+                float h[4], m[4], l[4];
+                split3_tc(v.x, h[0], m[0], l[0]);
+                split3_tc(v.y, h[1], m[1], l[1]);
+                split3_tc(v.z, h[2], m[2], l[2]);
+                split3_tc(v.w, h[3], m[3], l[3]);
+                unsigned char* dstp = sm_b + (size_t)(c4 >> 1) * b_ncore_stride + (k >> 3) * 128 + (k & 7) * 16 + (c4 & 1) * 8;
+                *reinterpret_cast<uint2*>(dstp) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+                *reinterpret_cast<uint2*>(dstp + 8 * (size_t)b_ncore_stride) = make_uint2(pack2(m[0], m[1]), pack2(m[2], m[3]));
+                *reinterpret_cast<uint2*>(dstp + 16 * (size_t)b_ncore_stride) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_full);
+            // ---- A tiles: thread = (row of the 128-row tile, one of the two bitmap words of the 64-column chunk)
+            const int arow = ptid & 127, aword = ptid >> 7;
+            for (int mt = 0; mt < n_mt && ok; ++mt) {
+                const int r = mt * 128 + arow;
+                const uint32_t* rowbits = bm + (size_t)(r < n ? r : 0) * words;
+                for (int kc = 0; kc < n_kc; ++kc, ++a_it) {
+                    const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
+                    const int wi = kc * 2 + aword;
+                    const uint32_t w = (r < n && wi < words) ? __ldg(rowbits + wi) : 0u;
+                    if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag))) break;
+                    unsigned char* st = sm_a + s * TC_A_STAGE + (aword * 4) * TC_A_KCORE + arow * 16;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t b8 = w >> (8 * q);
+                        *reinterpret_cast<uint4*>(st + q * TC_A_KCORE) =
+                            make_uint4(bits2_bf16x2(b8), bits2_bf16x2(b8 >> 2), bits2_bf16x2(b8 >> 4), bits2_bf16x2(b8 >> 6));
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[s]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_EPI_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace
+
+// Returns GNM_OK after launching, or GNM_ERR_TOO_LARGE when the batch does not fit this kernel (caller falls back).
+int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
+                            int n_max, const float* src, int64_t ld_src, const int32_t* src_map, float* dst,
+                            int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
+                            cudaStream_t stream) {
+    if (n_max > TC_MAX_NODES) return GNM_ERR_TOO_LARGE;
+    if ((ld_dst % 4) || (ld_src % 4) || (n_feat % 4)) return GNM_ERR_ALIGN;
+    int dev = 0, sms = 148, major = 0, smem_cap = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) return GNM_ERR_TOO_LARGE;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    AggTcParams p;
+    p.bitmap_addr = bitmap_addr; p.node_off = node_off; p.rowptr = rowptr; p.src = src; p.src_map = src_map;
+    p.dst = dst; p.eps = eps; p.bias = bias; p.ld_src = ld_src; p.ld_dst = ld_dst; p.n_graphs = n_graphs;
+    p.n_feat = n_feat; p.mode = mode;
+    p.n_slabs = (n_feat + TC_SLAB - 1) / TC_SLAB;
+    p.kcores_max = ((n_max + 15) / 16) * 2;
+    const int smem = TC_STAGES * TC_A_STAGE + 24 * (p.kcores_max * 128 + 16) + 1024;
+    if (smem > smem_cap - 1024) return GNM_ERR_TOO_LARGE;
+    cudaError_t e = cudaFuncSetAttribute(aggregate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t items = (int64_t)n_graphs * p.n_slabs;
+    const int grid = (int)(items < sms ? items : sms);
+    aggregate_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? GNM_OK : (int)e;
+}
+
+/* 1 if any tcgen05 aggregation launch since the last call hit a wait timeout (its output is then invalid).
+ * Synchronises the device; for tests and smoke checks. */
+extern "C" int gnm_aggregate_tc_status(int* aborted) {
+    int v = 0, zero = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&v, g_tc_abort, sizeof(int));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(g_tc_abort, &zero, sizeof(int));
+    if (aborted) *aborted = v;
+    return e == cudaSuccess ? GNM_OK : (int)e;
+}

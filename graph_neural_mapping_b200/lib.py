@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libgnm.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _c_i32 = ctypes.c_int
 _c_i64 = ctypes.c_int64
@@ -28,7 +28,8 @@ SIGNATURES = {
     "gnm_csr_batch_gather": [_p, _p, _p, _p, _p, _c_i32, _p, _p, _p, _p],
     "gnm_aggregate": [_p, _p, _c_i32, _p, _c_i64, _p, _p, _c_i64, _c_i32, _c_i32, _p, _p, _p],
     "gnm_bitmap_build": [_p, _p, _p, _p, _c_i32, _p, _p, _p],
-    "gnm_aggregate_dense": [_p, _p, _p, _c_i32, _c_i32, _p, _c_i64, _p, _p, _c_i64, _c_i32, _c_i32, _p, _p, _p],
+    "gnm_aggregate_dense": [_p, _p, _p, _c_i32, _c_i32, _p, _c_i64, _p, _p, _c_i64, _c_i32, _c_i32, _p, _p, _c_i32, _p],
+    "gnm_aggregate_tc_status": [_p],
     "gnm_dot_rows": [_p, _c_i64, _p, _c_i64, _p, _c_i32, _c_i32, _p, _p],
     "gnm_scatter_rows_add": [_p, _c_i64, _p, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p, _c_i64, _p],
     "gnm_scatter_rows_workspace": [_c_i32, _c_i32, _c_i32],

@@ -111,14 +111,25 @@ def bitmap_build(rowptr, colidx, node_off, bitmap_off, n_graphs, total_words):
     return bitmap, dup
 
 
-def aggregate_dense(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, src_map, dst, mode, eps, bias=None):
+DENSE_IMPL = [0]     # 0 auto, 1 mma.sync kernel, 2 tcgen05 kernel (A/B switch for tests and benchmarks)
+
+
+def aggregate_tc_status():
+    """True if a tcgen05 aggregation launch hit its bounded-wait timeout since the last call (device sync)."""
+    v = ctypes.c_int(0)
+    _libmod.check(_lib().gnm_aggregate_tc_status(ctypes.byref(v)), "gnm_aggregate_tc_status")
+    return bool(v.value)
+
+
+def aggregate_dense(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, src_map, dst, mode, eps, bias=None, impl=None):
     sp, lds = _mat(src)
     dp, ldd = _mat(dst)
     _libmod.check(_lib().gnm_aggregate_dense(_ptr(bitmap_addr, torch.int64), _ptr(node_off, torch.int32),
                                              _ptr(rowptr, torch.int32), n_graphs, n_max, sp, lds,
                                              _ptr(src_map, torch.int32) if src_map is not None else None, dp, ldd,
                                              int(dst.shape[1]), int(mode), _ptr(eps, torch.float32),
-                                             _ptr(bias, torch.float32), _stream(dst)), "gnm_aggregate_dense")
+                                             _ptr(bias, torch.float32), DENSE_IMPL[0] if impl is None else int(impl),
+                                             _stream(dst)), "gnm_aggregate_dense")
     return dst
 
 

@@ -32,7 +32,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 6
+#define GNM_ABI_VERSION 7
 
 typedef void* gnm_stream_t;
 
@@ -96,11 +96,16 @@ int gnm_bitmap_build(const int32_t* rowptr, const int32_t* colidx, const int32_t
  * dense 0/1 block product on the tensor cores: dst_g = A_g . src_g with A_g expanded from the graph's bitmap
  * (bitmap_addr[g]: device address) and src split into three bf16 planes (exact for fp32) with fp32
  * accumulation. rowptr (batch CSR row pointers) supplies the degrees for mode 1 / 2 and may be NULL for mode 0.
- * Needs n_feat % 4 == 0 and 16-byte aligned rows (else GNM_ERR_ALIGN: use gnm_aggregate). */
+ * Needs n_feat % 4 == 0 and 16-byte aligned rows (else GNM_ERR_ALIGN: use gnm_aggregate).
+ * impl: 0 = auto (tcgen05/TMEM kernel when every graph has <= 416 nodes, else the mma.sync kernel),
+ *       1 = mma.sync kernel, 2 = tcgen05 kernel only (GNM_ERR_TOO_LARGE if it does not fit). */
 int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr,
                         int n_graphs, int n_max, const float* src, int64_t ld_src, const int32_t* src_map,
                         float* dst, int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
-                        gnm_stream_t stream);
+                        int impl, gnm_stream_t stream);
+/* *aborted = 1 if a tcgen05 aggregation launch since the last call ran into a (bounded) barrier-wait timeout
+ * and drained without producing valid output. Synchronises the device; meant for tests / smoke checks. */
+int gnm_aggregate_tc_status(int* aborted);
 
 /* d eps[layer] = sum_i <a[i], b[map(i)]> (autograd of graphcnn.py:161). out: double[1], accumulated. */
 int gnm_dot_rows(const float* a, int64_t lda, const float* b, int64_t ldb, const int32_t* b_map,

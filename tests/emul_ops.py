@@ -112,7 +112,7 @@ def dense_aggregate_ok(src, dst, bias=None):
     return dst.shape[1] % 4 == 0
 
 
-def aggregate_dense(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, src_map, dst, mode, eps, bias=None):
+def aggregate_dense(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, src_map, dst, mode, eps, bias=None, impl=None):
     """Contract of gnm_aggregate_dense: the adjacency is read from the per-graph bitmaps."""
     no = node_off.numpy()
     m = dst.shape[0]
