@@ -16,7 +16,8 @@
 //     hi+mid+lo summed in registers, average / eps self term / bias, fp32 stores) while the MMA thread fills
 //     slot s^1 with the next 128-row tile.
 //   * warp roles: 0-3 epilogue, 4 MMA issue + TMEM alloc, 5-12 producers; mbarriers: a_full/a_empty[4],
-//     acc_full/acc_empty[2], b_full, b_free. tcgen05.commit releases A stages / publishes accumulators.
+//     acc_full/acc_empty[2], b_free. tcgen05.commit releases A stages / publishes accumulators. The B planes
+//     of an item are written chunk by chunk together with the A stages of its first row tile.
 //   * every wait is bounded: on a timeout the kernel raises an abort flag and drains instead of hanging.
 #include <cuda_bf16.h>
 
@@ -221,8 +222,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 const int n_mt = (n + 127) >> 7;
                 const int ksteps_total = (n + 15) >> 4;
                 const int n_kc = (ksteps_total + 3) >> 2;
-                if (!(ok = mbar_wait(b_full, b_it & 1, abort_flag))) break;
-                tc_fence_after();
                 for (int mt = 0; mt < n_mt && ok; ++mt, ++acc_it) {
                     const uint32_t slot = acc_it & 1, ph = (acc_it >> 1) & 1;
                     if (!(ok = mbar_wait(&acc_empty[slot], ph ^ 1, abort_flag))) break;
@@ -250,9 +249,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             }
         }
     } else {
-        // ================================ producers: B planes once per item, A tiles per (row tile, k chunk) ====
+        // ================================ producers ========================================================
+        // Stage (row tile mt, k chunk kc) = the 128 x 64 adjacency tile expanded from two bitmap words per row.
+        // During the FIRST row tile of an item the stage also carries the item's B planes for the same 64 nodes
+        // (fp32 rows -> three bf16 planes), so the B fill is pipelined with the MMAs instead of preceding them.
+        // Global loads for stage j+1 (bitmap word, 4 feature float4s) are issued before stage j is written.
         const int ptid = tid - (TC_EPI_WARPS + 1) * 32;                  // 0..255
+        const int arow = ptid & 127, aword = ptid >> 7;
         uint32_t a_it = 0, b_it = 0;
+        int prev_nkc = TC_STAGES;
         bool ok = true;
         for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, ++b_it) {
             const int gi = item / p.n_slabs, slab = item % p.n_slabs;
@@ -261,59 +266,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             const int n_mt = (n + 127) >> 7;
             const int ksteps_total = (n + 15) >> 4;
             const int n_kc = (ksteps_total + 3) >> 2;
-            const int kpad = ksteps_total * 16;
             const int words = (n + 31) >> 5;
             const uint32_t* __restrict__ bm = reinterpret_cast<const uint32_t*>(p.bitmap_addr[gi]);
-            // ---- B planes: wait until the previous item's MMAs have retired
-            if (!(ok = mbar_wait(b_free, (b_it & 1) ^ 1, abort_flag))) break;
-            for (int idx = ptid; idx < kpad * 16; idx += TC_PROD_WARPS * 32) {
-                const int k = idx >> 4, c4 = idx & 15;
-                const int col = f0 + c4 * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (k < n && col < p.n_feat) {
-                    const int jr = n0 + k;
-                    const int64_t sr = p.src_map ? (int64_t)p.src_map[jr] : (int64_t)jr;
-                    v = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
-                    if (p.mode == 2) {
-                        const float w = 1.f / (float)(p.rowptr[jr + 1] - p.rowptr[jr]);
-                        v.x *= w; v.y *= w; v.z *= w; v.w *= w;
-                    }
-                }
-                float h[4], m[4], l[4];
-                split3_tc(v.x, h[0], m[0], l[0]);
-                split3_tc(v.y, h[1], m[1], l[1]);
-                split3_tc(v.z, h[2], m[2], l[2]);
-                split3_tc(v.w, h[3], m[3], l[3]);
-                unsigned char* dstp = sm_b + (size_t)(c4 >> 1) * b_ncore_stride + (k >> 3) * 128 + (k & 7) * 16 + (c4 & 1) * 8;
-                *reinterpret_cast<uint2*>(dstp) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
-                *reinterpret_cast<uint2*>(dstp + 8 * (size_t)b_ncore_stride) = make_uint2(pack2(m[0], m[1]), pack2(m[2], m[3]));
-                *reinterpret_cast<uint2*>(dstp + 16 * (size_t)b_ncore_stride) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(b_full);
-            // ---- A tiles: thread = (row of the 128-row tile, one of the two bitmap words of the 64-column chunk)
-            const int arow = ptid & 127, aword = ptid >> 7;
-            for (int mt = 0; mt < n_mt && ok; ++mt) {
-                const int r = mt * 128 + arow;
-                const uint32_t* rowbits = bm + (size_t)(r < n ? r : 0) * words;
-                for (int kc = 0; kc < n_kc; ++kc, ++a_it) {
-                    const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
-                    const int wi = kc * 2 + aword;
-                    const uint32_t w = (r < n && wi < words) ? __ldg(rowbits + wi) : 0u;
-                    if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag))) break;
-                    unsigned char* st = sm_a + s * TC_A_STAGE + (aword * 4) * TC_A_KCORE + arow * 16;
+            const int n_st = n_mt * n_kc;
+
+            auto load_word = [&](int j) -> uint32_t {
+                const int mt = j / n_kc, kc = j - mt * n_kc;
+                const int r = mt * 128 + arow, wi = kc * 2 + aword;
+                return (j < n_st && r < n && wi < words) ? __ldg(bm + (size_t)r * words + wi) : 0u;
+            };
+            float4 bq[4];
+            auto load_b = [&](int kc) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t b8 = w >> (8 * q);
-                        *reinterpret_cast<uint4*>(st + q * TC_A_KCORE) =
-                            make_uint4(bits2_bf16x2(b8), bits2_bf16x2(b8 >> 2), bits2_bf16x2(b8 >> 4), bits2_bf16x2(b8 >> 6));
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = ptid + u * 256;                  // 64 nodes x 16 float4
+                    const int k = kc * TC_KC + (idx >> 4), c4 = idx & 15;
+                    const int col = f0 + c4 * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (kc < n_kc && k < n && col < p.n_feat) {
+                        const int jr = n0 + k;
+                        const int64_t sr = p.src_map ? (int64_t)p.src_map[jr] : (int64_t)jr;
+                        v = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
+                        if (p.mode == 2) {
+                            const float w = 1.f / (float)(p.rowptr[jr + 1] - p.rowptr[jr]);
+                            v.x *= w; v.y *= w; v.z *= w; v.w *= w;
+                        }
                     }
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_full[s]);
+                    bq[u] = v;
                 }
+            };
+            uint32_t w_next = load_word(0);
+            load_b(0);
+            for (int j = 0; j < n_st && ok; ++j, ++a_it) {
+                const int mt = j / n_kc, kc = j - mt * n_kc;
+                const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
+                const uint32_t w = w_next;
+                if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag))) break;
+                if (mt == 0) {
+                    // the previous item's MMAs on these B rows retired at least TC_STAGES stages ago, unless that
+                    // item had fewer stages than the ring: then wait for its explicit b_free commit
+                    if (kc == 0 && prev_nkc < TC_STAGES) {
+                        if (!(ok = mbar_wait(b_free, (b_it & 1) ^ 1, abort_flag))) break;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = ptid + u * 256;
+                        const int k = kc * TC_KC + (idx >> 4), c4 = idx & 15;
+                        if (k >= ksteps_total * 16) continue;
+                        float h[4], m[4], l[4];
+                        split3_tc(bq[u].x, h[0], m[0], l[0]);
+                        split3_tc(bq[u].y, h[1], m[1], l[1]);
+                        split3_tc(bq[u].z, h[2], m[2], l[2]);
+                        split3_tc(bq[u].w, h[3], m[3], l[3]);
+                        unsigned char* dstp = sm_b + (size_t)(c4 >> 1) * b_ncore_stride + (k >> 3) * 128 + (k & 7) * 16 + (c4 & 1) * 8;
+                        *reinterpret_cast<uint2*>(dstp) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+                        *reinterpret_cast<uint2*>(dstp + 8 * (size_t)b_ncore_stride) = make_uint2(pack2(m[0], m[1]), pack2(m[2], m[3]));
+                        *reinterpret_cast<uint2*>(dstp + 16 * (size_t)b_ncore_stride) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
+                    }
+                    if (kc + 1 < n_kc) load_b(kc + 1);
+                }
+                w_next = load_word(j + 1);
+                unsigned char* st = sm_a + s * TC_A_STAGE + (aword * 4) * TC_A_KCORE + arow * 16;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t b8 = w >> (8 * q);
+                    *reinterpret_cast<uint4*>(st + q * TC_A_KCORE) =
+                        make_uint4(bits2_bf16x2(b8), bits2_bf16x2(b8 >> 2), bits2_bf16x2(b8 >> 4), bits2_bf16x2(b8 >> 6));
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[s]);
             }
+            prev_nkc = n_kc;
         }
     }
     tc_fence_before();
