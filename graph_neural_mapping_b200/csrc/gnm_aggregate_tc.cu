@@ -268,15 +268,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             const int n_kc = (ksteps_total + 3) >> 2;
             const int words = (n + 31) >> 5;
             const uint32_t* __restrict__ bm = reinterpret_cast<const uint32_t*>(p.bitmap_addr[gi]);
-            const int n_st = n_mt * n_kc;
 
-            auto load_word = [&](int j) -> uint32_t {
-                const int mt = j / n_kc, kc = j - mt * n_kc;
-                const int r = mt * 128 + arow, wi = kc * 2 + aword;
-                return (j < n_st && r < n && wi < words) ? __ldg(bm + (size_t)r * words + wi) : 0u;
+            // bitmap words of this thread's row for a whole row tile (<= 7 words: N <= 416), all loads in flight at
+            // once; the next tile's words are fetched while the current tile's stages are produced
+            constexpr int MAXW = (TC_MAX_NODES / 32 + 1) / 2;          // 7
+            auto load_words = [&](int mt, uint32_t (&w)[MAXW]) {
+                const int r = mt * 128 + arow;
+                const bool rok = mt < n_mt && r < n;
+                const uint32_t* rowbits = bm + (size_t)(rok ? r : 0) * words;
+#pragma unroll
+                for (int q = 0; q < MAXW; ++q) {
+                    const int wi = q * 2 + aword;
+                    w[q] = (rok && wi < words) ? __ldg(rowbits + wi) : 0u;
+                }
             };
-            float4 bq[4];
-            auto load_b = [&](int kc) {
+            float4 bq[2][4];
+            auto load_b = [&](int kc, float4 (&dst4)[4]) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int idx = ptid + u * 256;                  // 64 nodes x 16 float4
@@ -292,50 +299,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                             v.x *= w; v.y *= w; v.z *= w; v.w *= w;
                         }
                     }
-                    bq[u] = v;
+                    dst4[u] = v;
                 }
             };
-            uint32_t w_next = load_word(0);
-            load_b(0);
-            for (int j = 0; j < n_st && ok; ++j, ++a_it) {
-                const int mt = j / n_kc, kc = j - mt * n_kc;
-                const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
-                const uint32_t w = w_next;
-                if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag))) break;
-                if (mt == 0) {
-                    // the previous item's MMAs on these B rows retired at least TC_STAGES stages ago, unless that
-                    // item had fewer stages than the ring: then wait for its explicit b_free commit
-                    if (kc == 0 && prev_nkc < TC_STAGES) {
-                        if (!(ok = mbar_wait(b_free, (b_it & 1) ^ 1, abort_flag))) break;
-                    }
+            uint32_t w_cur[MAXW], w_nxt[MAXW];
+            load_words(0, w_cur);
+            load_b(0, bq[0]);
+            load_b(1, bq[1]);
+            for (int mt = 0; mt < n_mt && ok; ++mt) {
+                load_words(mt + 1, w_nxt);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int idx = ptid + u * 256;
-                        const int k = kc * TC_KC + (idx >> 4), c4 = idx & 15;
-                        if (k >= ksteps_total * 16) continue;
-                        float h[4], m[4], l[4];
-                        split3_tc(bq[u].x, h[0], m[0], l[0]);
-                        split3_tc(bq[u].y, h[1], m[1], l[1]);
-                        split3_tc(bq[u].z, h[2], m[2], l[2]);
-                        split3_tc(bq[u].w, h[3], m[3], l[3]);
-                        unsigned char* dstp = sm_b + (size_t)(c4 >> 1) * b_ncore_stride + (k >> 3) * 128 + (k & 7) * 16 + (c4 & 1) * 8;
-                        *reinterpret_cast<uint2*>(dstp) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
-                        *reinterpret_cast<uint2*>(dstp + 8 * (size_t)b_ncore_stride) = make_uint2(pack2(m[0], m[1]), pack2(m[2], m[3]));
-                        *reinterpret_cast<uint2*>(dstp + 16 * (size_t)b_ncore_stride) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
-                    }
-                    if (kc + 1 < n_kc) load_b(kc + 1);
-                }
-                w_next = load_word(j + 1);
-                unsigned char* st = sm_a + s * TC_A_STAGE + (aword * 4) * TC_A_KCORE + arow * 16;
+                for (int kc = 0; kc < MAXW; ++kc) {
+                    if (kc >= n_kc) break;
+                    const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
+                    if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag))) break;
+                    if (mt == 0) {
+                        // the previous item's MMAs on these B rows retired at least TC_STAGES stages ago, unless
+                        // that item had fewer k chunks than the ring: then wait for its explicit b_free commit
+                        if (kc == 0 && prev_nkc < TC_STAGES) {
+                            if (!(ok = mbar_wait(b_free, (b_it & 1) ^ 1, abort_flag))) break;
+                        }
+                        float4 (&cur)[4] = bq[kc & 1];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t b8 = w >> (8 * q);
-                    *reinterpret_cast<uint4*>(st + q * TC_A_KCORE) =
-                        make_uint4(bits2_bf16x2(b8), bits2_bf16x2(b8 >> 2), bits2_bf16x2(b8 >> 4), bits2_bf16x2(b8 >> 6));
+                        for (int u = 0; u < 4; ++u) {
+                            const int idx = ptid + u * 256;
+                            const int k = kc * TC_KC + (idx >> 4), c4 = idx & 15;
+                            if (k >= ksteps_total * 16) continue;
+                            float h[4], m[4], l[4];
+                            split3_tc(cur[u].x, h[0], m[0], l[0]);
+                            split3_tc(cur[u].y, h[1], m[1], l[1]);
+                            split3_tc(cur[u].z, h[2], m[2], l[2]);
+                            split3_tc(cur[u].w, h[3], m[3], l[3]);
+                            unsigned char* dstp = sm_b + (size_t)(c4 >> 1) * b_ncore_stride + (k >> 3) * 128 + (k & 7) * 16 + (c4 & 1) * 8;
+                            *reinterpret_cast<uint2*>(dstp) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+                            *reinterpret_cast<uint2*>(dstp + 8 * (size_t)b_ncore_stride) = make_uint2(pack2(m[0], m[1]), pack2(m[2], m[3]));
+                            *reinterpret_cast<uint2*>(dstp + 16 * (size_t)b_ncore_stride) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
+                        }
+                        if (kc + 2 < n_kc) load_b(kc + 2, cur);
+                    }
+                    const uint32_t w = w_cur[kc];
+                    unsigned char* st = sm_a + s * TC_A_STAGE + (aword * 4) * TC_A_KCORE + arow * 16;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t b8 = w >> (8 * q);
+                        *reinterpret_cast<uint4*>(st + q * TC_A_KCORE) =
+                            make_uint4(bits2_bf16x2(b8), bits2_bf16x2(b8 >> 2), bits2_bf16x2(b8 >> 4), bits2_bf16x2(b8 >> 6));
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[s]);
+                    ++a_it;
                 }
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full[s]);
+#pragma unroll
+                for (int q = 0; q < MAXW; ++q) w_cur[q] = w_nxt[q];
             }
             prev_nkc = n_kc;
         }

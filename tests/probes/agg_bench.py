@@ -1,0 +1,53 @@
+"""Micro-benchmark / ncu target for the neighbour-aggregation kernels at the benchmark shape
+(B graphs x N=400 nodes, F=64): python tests/probes/agg_bench.py [B] [iters] [impl ...]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from graph_neural_mapping_b200 import engine, ops, synth  # noqa: E402
+
+
+def main():
+    b = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    impls = [int(x) for x in sys.argv[3:]] or [2, 1, 0]
+    dev = torch.device("cuda")
+    graphs = synth.make_graphs_bulk(b, 400, 30, 128, seed0=0, device=dev)
+    store = engine.GraphStore(dev, add_self_loops=True)
+    bs = store.assemble(graphs)
+    m, f = bs.n_rows, 64
+    torch.manual_seed(0)
+    src = torch.randn(m, f, device=dev)
+    dst = torch.empty(m, f, device=dev)
+    ref = torch.empty(m, f, device=dev)
+    ops.aggregate(bs.rowptr, bs.colidx, src, None, ref, 0, None, None)
+    alg_bytes = 4.0 * bs.nnz + 4.0 * (m + 1) + 8.0 * m * f
+    for impl in impls:
+        if impl == 0:
+            fn = lambda: ops.aggregate(bs.rowptr, bs.colidx, src, None, dst, 0, None, None)
+            name = "csr warp-per-row"
+        else:
+            fn = lambda: ops.aggregate_dense(bs.bitmap_addr, bs.node_off, bs.rowptr, bs.n_graphs, bs.n_max, src, None, dst, 0,
+                                             None, None, impl=impl)
+            name = "mma.sync dense" if impl == 1 else "tcgen05 dense"
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+        ev[0].record()
+        for i in range(iters):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ts = [ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(iters)]
+        err = float((dst - ref).abs().max() / ref.abs().max())
+        t = float(np.median(ts))
+        print("%-18s median %8.1f us  min %8.1f us  -> %7.1f GB/s algorithmic (%.3f of 6546)  max rel err vs csr %.2e  abort=%s"
+              % (name, t, min(ts), alg_bytes / t / 1e3, alg_bytes / t / 1e3 / 6546.2, err, ops.aggregate_tc_status()))
+
+
+if __name__ == "__main__":
+    main()
