@@ -50,6 +50,7 @@ struct AggTcParams {
     const float* bias;
     int64_t ld_src, ld_dst;
     int n_graphs, n_feat, mode, n_slabs, kcores_max;
+    long long* dbg;              // nullable: per-CTA wait/busy cycle counters (profiling aid)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,14 +62,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // bounded wait: false on timeout (the caller raises the abort flag and drains)
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag,
+                                          long long* waited = nullptr) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
     const long long t0 = clock64();
     while (true) {
         asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (done) return true;
+        if (done) {
+            if (waited) *waited += clock64() - t0;
+            return true;
+        }
         if (*abort_flag) return false;
         if (clock64() - t0 > TC_TIMEOUT_CYCLES) {
             *abort_flag = 1;
@@ -113,6 +118,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&v);
 }
+// exact fp32 -> (hi, mid, lo) bf16 split of two values at once (packed cvt.rn.bf16x2; bf16 -> fp32 is a shift / mask)
+__device__ __forceinline__ void split3x2(float x0, float x1, uint32_t& hi2, uint32_t& mid2, uint32_t& lo2) {
+    hi2 = pack2(x0, x1);
+    float r0 = x0 - __uint_as_float(hi2 << 16), r1 = x1 - __uint_as_float(hi2 & 0xffff0000u);
+    mid2 = pack2(r0, r1);
+    r0 -= __uint_as_float(mid2 << 16);
+    r1 -= __uint_as_float(mid2 & 0xffff0000u);
+    lo2 = pack2(r0, r1);
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTcParams p) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
@@ -128,8 +142,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     const int b_ncore_stride = p.kcores_max * 128 + 16;            // SBO of B (padded: conflict-free plane fill)
     unsigned char* sm_a = tc_smem;                                  // TC_STAGES x 16 KB
     unsigned char* sm_b = tc_smem + TC_STAGES * TC_A_STAGE;         // 24 n-cores x b_ncore_stride
+    // byte -> eight bf16 0/1 values (one 16-byte K-major core-matrix row): the whole A expansion is a table lookup
+    uint4* lut = reinterpret_cast<uint4*>(sm_b + (size_t)24 * b_ncore_stride);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 256) {
+        const uint32_t b8 = tid;
+        lut[tid] = make_uint4(bits2_bf16x2(b8), bits2_bf16x2(b8 >> 2), bits2_bf16x2(b8 >> 4), bits2_bf16x2(b8 >> 6));
+    }
     volatile int* abort_flag = &s_abort;
     if (tid == 0) {
         s_abort = 0;
@@ -152,6 +172,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     if (warp < TC_EPI_WARPS) {
         // ================================ epilogue: TMEM -> registers -> global ==========================
         uint32_t acc_it = 0;
+        long long w_acc = 0;
+        const long long t_role = clock64();
         const float self_c = p.eps ? 1.f + __ldg(p.eps) : 0.f;
         for (int item = blockIdx.x; item < n_items && !*abort_flag; item += gridDim.x) {
             const int gi = item / p.n_slabs, slab = item % p.n_slabs;
@@ -160,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             const int n_mt = (n + 127) >> 7;
             for (int mt = 0; mt < n_mt; ++mt, ++acc_it) {
                 const uint32_t slot = acc_it & 1, ph = (acc_it >> 1) & 1;
-                if (!mbar_wait(&acc_full[slot], ph, abort_flag)) break;
+                if (!mbar_wait(&acc_full[slot], ph, abort_flag, &w_acc)) break;
                 tc_fence_after();
                 const int r = mt * 128 + warp * 32 + lane;
                 const bool row_ok = r < n;
@@ -208,6 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 if (lane == 0) mbar_arrive(&acc_empty[slot]);
             }
         }
+        if (p.dbg && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_role; p.dbg[blockIdx.x * 16 + 1] = w_acc; }
     } else if (warp == TC_EPI_WARPS) {
         // ================================ MMA issue (one thread) ==========================================
         if (lane == 0) {
@@ -216,6 +239,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             const uint32_t a_base = smem_u32(sm_a), b_base = smem_u32(sm_b);
             uint32_t a_it = 0, acc_it = 0, b_it = 0;
             bool ok = true;
+            long long w_af = 0, w_ae = 0;
+            const long long t_role = clock64();
             for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, ++b_it) {
                 const int gi = item / p.n_slabs;
                 const int n = p.node_off[gi + 1] - p.node_off[gi];
@@ -224,12 +249,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 const int n_kc = (ksteps_total + 3) >> 2;
                 for (int mt = 0; mt < n_mt && ok; ++mt, ++acc_it) {
                     const uint32_t slot = acc_it & 1, ph = (acc_it >> 1) & 1;
-                    if (!(ok = mbar_wait(&acc_empty[slot], ph ^ 1, abort_flag))) break;
+                    if (!(ok = mbar_wait(&acc_empty[slot], ph ^ 1, abort_flag, &w_ae))) break;
                     tc_fence_after();
                     const uint32_t d_tmem = tmem + slot * TC_N;
                     for (int kc = 0; kc < n_kc; ++kc, ++a_it) {
                         const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
-                        if (!(ok = mbar_wait(&a_full[s], aph, abort_flag))) break;
+                        if (!(ok = mbar_wait(&a_full[s], aph, abort_flag, &w_af))) break;
                         tc_fence_after();
                         const int ks_n = min(4, ksteps_total - kc * 4);
                         for (int ks = 0; ks < ks_n; ++ks) {
@@ -247,6 +272,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 }
                 if (ok) umma_commit(b_free);               // all MMAs reading this graph's B planes are done
             }
+            if (p.dbg) { p.dbg[blockIdx.x * 16 + 2] = clock64() - t_role; p.dbg[blockIdx.x * 16 + 3] = w_af; p.dbg[blockIdx.x * 16 + 4] = w_ae; }
         }
     } else {
         // ================================ producers ========================================================
@@ -259,6 +285,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         uint32_t a_it = 0, b_it = 0;
         int prev_nkc = TC_STAGES;
         bool ok = true;
+        long long w_pe = 0;
+        const long long t_role = clock64();
         for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, ++b_it) {
             const int gi = item / p.n_slabs, slab = item % p.n_slabs;
             const int n0 = p.node_off[gi], n = p.node_off[gi + 1] - n0;
@@ -312,7 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 for (int kc = 0; kc < MAXW; ++kc) {
                     if (kc >= n_kc) break;
                     const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
-                    if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag))) break;
+                    if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag, &w_pe))) break;
                     if (mt == 0) {
                         // the previous item's MMAs on these B rows retired at least TC_STAGES stages ago, unless
                         // that item had fewer k chunks than the ring: then wait for its explicit b_free commit
@@ -325,26 +353,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                             const int idx = ptid + u * 256;
                             const int k = kc * TC_KC + (idx >> 4), c4 = idx & 15;
                             if (k >= ksteps_total * 16) continue;
-                            float h[4], m[4], l[4];
-                            split3_tc(cur[u].x, h[0], m[0], l[0]);
-                            split3_tc(cur[u].y, h[1], m[1], l[1]);
-                            split3_tc(cur[u].z, h[2], m[2], l[2]);
-                            split3_tc(cur[u].w, h[3], m[3], l[3]);
+                            uint32_t h0, m0, l0, h1, m1, l1;
+                            split3x2(cur[u].x, cur[u].y, h0, m0, l0);
+                            split3x2(cur[u].z, cur[u].w, h1, m1, l1);
                             unsigned char* dstp = sm_b + (size_t)(c4 >> 1) * b_ncore_stride + (k >> 3) * 128 + (k & 7) * 16 + (c4 & 1) * 8;
-                            *reinterpret_cast<uint2*>(dstp) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
-                            *reinterpret_cast<uint2*>(dstp + 8 * (size_t)b_ncore_stride) = make_uint2(pack2(m[0], m[1]), pack2(m[2], m[3]));
-                            *reinterpret_cast<uint2*>(dstp + 16 * (size_t)b_ncore_stride) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
+                            *reinterpret_cast<uint2*>(dstp) = make_uint2(h0, h1);
+                            *reinterpret_cast<uint2*>(dstp + 8 * (size_t)b_ncore_stride) = make_uint2(m0, m1);
+                            *reinterpret_cast<uint2*>(dstp + 16 * (size_t)b_ncore_stride) = make_uint2(l0, l1);
                         }
                         if (kc + 2 < n_kc) load_b(kc + 2, cur);
                     }
                     const uint32_t w = w_cur[kc];
                     unsigned char* st = sm_a + s * TC_A_STAGE + (aword * 4) * TC_A_KCORE + arow * 16;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t b8 = w >> (8 * q);
-                        *reinterpret_cast<uint4*>(st + q * TC_A_KCORE) =
-                            make_uint4(bits2_bf16x2(b8), bits2_bf16x2(b8 >> 2), bits2_bf16x2(b8 >> 4), bits2_bf16x2(b8 >> 6));
-                    }
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<uint4*>(st + q * TC_A_KCORE) = lut[(w >> (8 * q)) & 0xffu];
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&a_full[s]);
@@ -355,6 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             }
             prev_nkc = n_kc;
         }
+        if (p.dbg && ptid == 0) { p.dbg[blockIdx.x * 16 + 5] = clock64() - t_role; p.dbg[blockIdx.x * 16 + 6] = w_pe; }
     }
     tc_fence_before();
     __syncthreads();
@@ -364,6 +388,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
 }
 
 }  // namespace
+
+static long long* g_tc_dbg_host = nullptr;   // profiling aid, see gnm_aggregate_tc_set_debug
 
 // Returns GNM_OK after launching, or GNM_ERR_TOO_LARGE when the batch does not fit this kernel (caller falls back).
 int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
@@ -382,9 +408,10 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
     p.bitmap_addr = bitmap_addr; p.node_off = node_off; p.rowptr = rowptr; p.src = src; p.src_map = src_map;
     p.dst = dst; p.eps = eps; p.bias = bias; p.ld_src = ld_src; p.ld_dst = ld_dst; p.n_graphs = n_graphs;
     p.n_feat = n_feat; p.mode = mode;
+    p.dbg = g_tc_dbg_host;
     p.n_slabs = (n_feat + TC_SLAB - 1) / TC_SLAB;
     p.kcores_max = ((n_max + 15) / 16) * 2;
-    const int smem = TC_STAGES * TC_A_STAGE + 24 * (p.kcores_max * 128 + 16) + 1024;
+    const int smem = TC_STAGES * TC_A_STAGE + 24 * (p.kcores_max * 128 + 16) + 4096 + 1024;   // A ring + B planes + LUT
     if (smem > smem_cap - 1024) return GNM_ERR_TOO_LARGE;
     cudaError_t e = cudaFuncSetAttribute(aggregate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
@@ -404,4 +431,12 @@ extern "C" int gnm_aggregate_tc_status(int* aborted) {
     e = cudaMemcpyToSymbol(g_tc_abort, &zero, sizeof(int));
     if (aborted) *aborted = v;
     return e == cudaSuccess ? GNM_OK : (int)e;
+}
+
+/* Profiling aid: while non-NULL, every tcgen05 aggregation launch writes per-CTA cycle counters to buf
+ * (16 int64 per CTA: [0] epilogue role cycles, [1] waiting for accumulators, [2] MMA role cycles, [3] waiting
+ * for A stages, [4] waiting for free accumulator slots, [5] producer role cycles, [6] waiting for free stages). */
+extern "C" int gnm_aggregate_tc_set_debug(long long* buf) {
+    g_tc_dbg_host = buf;
+    return GNM_OK;
 }

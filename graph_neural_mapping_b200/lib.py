@@ -30,6 +30,7 @@ SIGNATURES = {
     "gnm_bitmap_build": [_p, _p, _p, _p, _c_i32, _p, _p, _p],
     "gnm_aggregate_dense": [_p, _p, _p, _c_i32, _c_i32, _p, _c_i64, _p, _p, _c_i64, _c_i32, _c_i32, _p, _p, _c_i32, _p],
     "gnm_aggregate_tc_status": [_p],
+    "gnm_aggregate_tc_set_debug": [_p],
     "gnm_dot_rows": [_p, _c_i64, _p, _c_i64, _p, _c_i32, _c_i32, _p, _p],
     "gnm_scatter_rows_add": [_p, _c_i64, _p, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p, _c_i64, _p],
     "gnm_scatter_rows_workspace": [_c_i32, _c_i32, _c_i32],

@@ -106,6 +106,9 @@ int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* node_off, con
 /* *aborted = 1 if a tcgen05 aggregation launch since the last call ran into a (bounded) barrier-wait timeout
  * and drained without producing valid output. Synchronises the device; meant for tests / smoke checks. */
 int gnm_aggregate_tc_status(int* aborted);
+/* Profiling aid: while buf != NULL every tcgen05 aggregation launch writes 16 int64 cycle counters per CTA to buf
+ * (device memory, >= 16 * #SMs entries): role cycles and barrier-wait cycles of the epilogue, MMA and producer warps. */
+int gnm_aggregate_tc_set_debug(long long* buf);
 
 /* d eps[layer] = sum_i <a[i], b[map(i)]> (autograd of graphcnn.py:161). out: double[1], accumulated. */
 int gnm_dot_rows(const float* a, int64_t lda, const float* b, int64_t ldb, const int32_t* b_map,
