@@ -10,9 +10,11 @@
 //     = 8 k-rows x 16 B; n-cores at SBO, k-cores at LBO), resident in shared memory for the whole graph
 //     (154 KB). N = 192 per MMA reads the A tile once for all three planes and keeps shared-memory traffic
 //     under the MMA time: 2(M+N)/(MN) = 0.026 B/MAC.
-//   * A operand = 128-row x 64-column tiles of the adjacency, expanded from bitmap words into bf16 0/1
-//     K-major core matrices by 8 producer warps, 4-stage ring (16 KB per stage).
-//   * D = 128 lanes x 192 fp32 columns in TMEM, two slots: the 4 epilogue warps drain slot s (tcgen05.ld,
+//   * A operand = 128-row x 64-column tiles of the adjacency, expanded from bitmap words into bf16 0/1 pairs in
+//     registers and written to TENSOR MEMORY (tcgen05.st, lane = row, 32 columns per stage, 4-stage ring); the
+//     MMA takes A from TMEM ([a_tmem] form). A in shared memory was measured first: MMA operand fetch (A 4 KB
+//     + B 6 KB per 96-cycle MMA = 107 B/clk of the 128 B/clk shared-memory pipe) starved the producers' stores.
+//   * D = 128 lanes x 192 fp32 columns in TMEM (columns 0-383: two slots; A ring in columns 384-511): the 4 epilogue warps drain slot s (tcgen05.ld,
 //     hi+mid+lo summed in registers, average / eps self term / bias, fp32 stores) while the MMA thread fills
 //     slot s^1 with the next 128-row tile.
 //   * warp roles: 0-3 epilogue, 4 MMA issue + TMEM alloc, 5-12 producers; mbarriers: a_full/a_empty[4],
@@ -27,8 +29,8 @@ namespace {
 
 constexpr int TC_KC = 64;                      // adjacency columns per A stage (4 MMAs of K = 16)
 constexpr int TC_STAGES = 4;
-constexpr int TC_A_KCORE = 16 * 128;           // bytes between k-cores of an A stage ([k-core][row group][128 B])
-constexpr int TC_A_STAGE = (TC_KC / 8) * TC_A_KCORE;      // 16 KB
+constexpr int TC_A_COLS = TC_KC / 2;           // TMEM columns per A stage (two bf16 per 32-bit column)
+constexpr int TC_A_TMEM0 = 384;                // first TMEM column of the A ring (after the two accumulator slots)
 constexpr int TC_N = 192;                      // three 64-feature planes side by side
 constexpr int TC_SLAB = 64;
 constexpr int TC_MAX_NODES = 416;
@@ -140,16 +142,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     uint64_t* b_full = acc_empty + 2;
     uint64_t* b_free = b_full + 1;
     const int b_ncore_stride = p.kcores_max * 128 + 16;            // SBO of B (padded: conflict-free plane fill)
-    unsigned char* sm_a = tc_smem;                                  // TC_STAGES x 16 KB
-    unsigned char* sm_b = tc_smem + TC_STAGES * TC_A_STAGE;         // 24 n-cores x b_ncore_stride
-    // byte -> eight bf16 0/1 values (one 16-byte K-major core-matrix row): the whole A expansion is a table lookup
-    uint4* lut = reinterpret_cast<uint4*>(sm_b + (size_t)24 * b_ncore_stride);
+    unsigned char* sm_b = tc_smem;                                  // 24 n-cores x b_ncore_stride
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid < 256) {
-        const uint32_t b8 = tid;
-        lut[tid] = make_uint4(bits2_bf16x2(b8), bits2_bf16x2(b8 >> 2), bits2_bf16x2(b8 >> 4), bits2_bf16x2(b8 >> 6));
-    }
     volatile int* abort_flag = &s_abort;
     if (tid == 0) {
         s_abort = 0;
@@ -236,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(TC_N >> 3) << 17) |
                                    ((uint32_t)(128 >> 4) << 24);   // f32 acc, bf16 x bf16, A K-major, B MN-major
-            const uint32_t a_base = smem_u32(sm_a), b_base = smem_u32(sm_b);
+            const uint32_t b_base = smem_u32(sm_b);
             uint32_t a_it = 0, acc_it = 0, b_it = 0;
             bool ok = true;
             long long w_af = 0, w_ae = 0;
@@ -258,13 +253,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                         tc_fence_after();
                         const int ks_n = min(4, ksteps_total - kc * 4);
                         for (int ks = 0; ks < ks_n; ++ks) {
-                            const uint64_t da = umma_desc(a_base + s * TC_A_STAGE + ks * 2 * TC_A_KCORE, TC_A_KCORE, 128);
+                            const uint32_t a_tmem = tmem + TC_A_TMEM0 + s * TC_A_COLS + ks * 8;   // 16 k = 8 columns
                             const uint64_t db = umma_desc(b_base + (kc * 8 + ks * 2) * 128, 128, (uint32_t)b_ncore_stride);
                             const uint32_t accum = (kc | ks) ? 1u : 0u;
                             asm volatile(
                                 "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                                ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+                                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                                ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(accum) : "memory");
                         }
                         umma_commit(&a_empty[s]);          // frees the A stage when these MMAs retire
                     }
@@ -276,16 +271,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         }
     } else {
         // ================================ producers ========================================================
-        // Stage (row tile mt, k chunk kc) = the 128 x 64 adjacency tile expanded from two bitmap words per row.
-        // During the FIRST row tile of an item the stage also carries the item's B planes for the same 64 nodes
-        // (fp32 rows -> three bf16 planes), so the B fill is pipelined with the MMAs instead of preceding them.
-        // Global loads for stage j+1 (bitmap word, 4 feature float4s) are issued before stage j is written.
+        // Stage (row tile mt, k chunk kc): the 128 x 64 adjacency tile as bf16 0/1, one row per thread, written to
+        // the TMEM A ring by the four warps of one group (warp % 4 selects the 32-lane quarter a warp may touch;
+        // the two groups alternate stages). During the FIRST row tile of an item every producer warp also
+        // converts the item's fp32 rows of the same 64 nodes into the three bf16 B planes in shared memory, so
+        // the B fill is pipelined with the MMAs. Global loads run one tile (bitmap) / two chunks (features) ahead.
         const int ptid = tid - (TC_EPI_WARPS + 1) * 32;                  // 0..255
-        const int arow = ptid & 127, aword = ptid >> 7;
+        const int grp = ptid >> 7;                                       // 0: warps 5-8, 1: warps 9-12
+        const int arow = (warp & 3) * 32 + lane;                         // row of the tile = TMEM lane
         uint32_t a_it = 0, b_it = 0;
         int prev_nkc = TC_STAGES;
         bool ok = true;
-        long long w_pe = 0;
+        long long w_pe = 0, c_st = 0, c_fence = 0, c_arr = 0;
         const long long t_role = clock64();
         for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, ++b_it) {
             const int gi = item / p.n_slabs, slab = item % p.n_slabs;
@@ -296,18 +293,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             const int n_kc = (ksteps_total + 3) >> 2;
             const int words = (n + 31) >> 5;
             const uint32_t* __restrict__ bm = reinterpret_cast<const uint32_t*>(p.bitmap_addr[gi]);
-
-            // bitmap words of this thread's row for a whole row tile (<= 7 words: N <= 416), all loads in flight at
-            // once; the next tile's words are fetched while the current tile's stages are produced
-            constexpr int MAXW = (TC_MAX_NODES / 32 + 1) / 2;          // 7
-            auto load_words = [&](int mt, uint32_t (&w)[MAXW]) {
+            constexpr int MAXC = (TC_MAX_NODES + TC_KC - 1) / TC_KC;      // 7 chunks of 64 columns
+            constexpr int MYC = (MAXC + 1) / 2;                           // chunks one group handles per tile
+            // bitmap words (two per chunk) of this thread's row for the chunks its group produces in row tile mt
+            auto load_words = [&](int mt, uint32_t it0, uint32_t (&w)[MYC][2]) {
                 const int r = mt * 128 + arow;
                 const bool rok = mt < n_mt && r < n;
                 const uint32_t* rowbits = bm + (size_t)(rok ? r : 0) * words;
+                const int first = ((it0 & 1) == (uint32_t)grp) ? 0 : 1;  // first chunk of the tile owned by this group
 #pragma unroll
-                for (int q = 0; q < MAXW; ++q) {
-                    const int wi = q * 2 + aword;
-                    w[q] = (rok && wi < words) ? __ldg(rowbits + wi) : 0u;
+                for (int c = 0; c < MYC; ++c) {
+                    const int kc = first + 2 * c;
+                    w[c][0] = (rok && kc < n_kc && 2 * kc < words) ? __ldg(rowbits + 2 * kc) : 0u;
+                    w[c][1] = (rok && kc < n_kc && 2 * kc + 1 < words) ? __ldg(rowbits + 2 * kc + 1) : 0u;
                 }
             };
             float4 bq[2][4];
@@ -330,14 +328,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                     dst4[u] = v;
                 }
             };
-            uint32_t w_cur[MAXW], w_nxt[MAXW];
-            load_words(0, w_cur);
+            uint32_t w_cur[MYC][2], w_nxt[MYC][2];
+            load_words(0, a_it, w_cur);
             load_b(0, bq[0]);
             load_b(1, bq[1]);
             for (int mt = 0; mt < n_mt && ok; ++mt) {
-                load_words(mt + 1, w_nxt);
+                load_words(mt + 1, a_it + n_kc, w_nxt);
+                const int first = ((a_it & 1) == (uint32_t)grp) ? 0 : 1;
 #pragma unroll
-                for (int kc = 0; kc < MAXW; ++kc) {
+                for (int kc = 0; kc < MAXC; ++kc) {
                     if (kc >= n_kc) break;
                     const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
                     if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag, &w_pe))) break;
@@ -362,23 +361,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                             *reinterpret_cast<uint2*>(dstp + 16 * (size_t)b_ncore_stride) = make_uint2(l0, l1);
                         }
                         if (kc + 2 < n_kc) load_b(kc + 2, cur);
+                        fence_async_smem();
                     }
-                    const uint32_t w = w_cur[kc];
-                    unsigned char* st = sm_a + s * TC_A_STAGE + (aword * 4) * TC_A_KCORE + arow * 16;
+                    const long long tq0 = p.dbg ? clock64() : 0;
+                    if (((kc - first) & 1) == 0) {
+                        // this group's stage: 64 bits -> 32 registers of bf16 pairs -> 32 TMEM columns of this row
+                        const int c = (kc - first) >> 1;
+                        uint32_t v[32];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<uint4*>(st + q * TC_A_KCORE) = lut[(w >> (8 * q)) & 0xffu];
-                    fence_async_smem();
+                        for (int j = 0; j < 16; ++j) {
+                            v[j] = bits2_bf16x2(w_cur[c][0] >> (2 * j));
+                            v[16 + j] = bits2_bf16x2(w_cur[c][1] >> (2 * j));
+                        }
+                        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TC_A_TMEM0 + s * TC_A_COLS;
+                        asm volatile(
+                            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+                            "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                            ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+                              "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
+                              "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+                              "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+                              "r"(v[31]) : "memory");
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    }
+                    const long long tq1 = p.dbg ? clock64() : 0;
+                    tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&a_full[s]);
+                    if (p.dbg) { const long long tq3 = clock64(); c_st += tq1 - tq0; c_arr += tq3 - tq1; }
                     ++a_it;
                 }
 #pragma unroll
-                for (int q = 0; q < MAXW; ++q) w_cur[q] = w_nxt[q];
+                for (int c = 0; c < MYC; ++c) { w_cur[c][0] = w_nxt[c][0]; w_cur[c][1] = w_nxt[c][1]; }
             }
             prev_nkc = n_kc;
         }
-        if (p.dbg && ptid == 0) { p.dbg[blockIdx.x * 16 + 5] = clock64() - t_role; p.dbg[blockIdx.x * 16 + 6] = w_pe; }
+        if (p.dbg && ptid == 0) {
+            p.dbg[blockIdx.x * 16 + 5] = clock64() - t_role; p.dbg[blockIdx.x * 16 + 6] = w_pe;
+            p.dbg[blockIdx.x * 16 + 7] = c_st; p.dbg[blockIdx.x * 16 + 8] = c_fence; p.dbg[blockIdx.x * 16 + 9] = c_arr;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -411,7 +432,7 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
     p.dbg = g_tc_dbg_host;
     p.n_slabs = (n_feat + TC_SLAB - 1) / TC_SLAB;
     p.kcores_max = ((n_max + 15) / 16) * 2;
-    const int smem = TC_STAGES * TC_A_STAGE + 24 * (p.kcores_max * 128 + 16) + 4096 + 1024;   // A ring + B planes + LUT
+    const int smem = 24 * (p.kcores_max * 128 + 16) + 1024;   // B planes (the A ring lives in tensor memory)
     if (smem > smem_cap - 1024) return GNM_ERR_TOO_LARGE;
     cudaError_t e = cudaFuncSetAttribute(aggregate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;

@@ -2,7 +2,7 @@
 // conventions used by gnm_aggregate_tc.cu on a single 128 x 192 x 64 bf16 GEMM.
 //   A: K-major, no swizzle   (core matrix = 8 rows x 16 B; k-cores at LBO, 8-row groups at SBO)
 //   B: MN-major, no swizzle  (core matrix = 8 k-rows x 16 B of n; n-cores at SBO, k-cores at LBO)
-// Tries both LBO/SBO role assignments for each operand and prints the max error of each combination.
+// Checks A from shared memory (SS) and A from tensor memory written with tcgen05.st (TS).
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tc_probe tc_probe.cu ; run: ./tc_probe
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -31,7 +31,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
 }
 
 __global__ void __launch_bounds__(128) probe_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
-                                                    float* __restrict__ d, int swap_a, int swap_b, int* status) {
+                                                    float* __restrict__ d, int ts_mode, int unused, int* status) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sa = smem;                                   // 16 KB
     unsigned char* sb = smem + 16384;                           // 24 * B_NCORE_STRIDE
@@ -61,19 +61,49 @@ __global__ void __launch_bounds__(128) probe_kernel(const __nv_bfloat16* __restr
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base;
+    if (ts_mode) {
+        // A operand in TMEM: lane = row, 32-bit column j of the A region holds k = 2j (low half) and 2j+1 (high half)
+        const int row = tid;                       // 128 threads = 128 rows; warp w owns lanes 32w..32w+31
+        uint32_t v[32];
+        for (int j = 0; j < 32; ++j) {
+            const uint16_t lo = *reinterpret_cast<const uint16_t*>(&a[row * K + 2 * j]);
+            const uint16_t hi = *reinterpret_cast<const uint16_t*>(&a[row * K + 2 * j + 1]);
+            v[j] = (uint32_t)lo | ((uint32_t)hi << 16);
+        }
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 192;
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+            "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+            ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+              "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+              "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+              "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
     if (tid == 0) {
         // instruction descriptor: F32 accum, BF16 x BF16, A K-major, B MN-major, N = 192, M = 128
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
         for (int ks = 0; ks < K / 16; ++ks) {
             const uint32_t a_addr = smem_u32(sa) + ks * 2 * A_KCORE_STRIDE;
             const uint32_t b_addr = smem_u32(sb) + ks * 2 * B_KCORE_STRIDE;
-            const uint64_t da = swap_a ? make_desc(a_addr, A_RGROUP_STRIDE, A_KCORE_STRIDE) : make_desc(a_addr, A_KCORE_STRIDE, A_RGROUP_STRIDE);
-            const uint64_t db = swap_b ? make_desc(b_addr, B_NCORE_STRIDE, B_KCORE_STRIDE) : make_desc(b_addr, B_KCORE_STRIDE, B_NCORE_STRIDE);
+            const uint64_t da = make_desc(a_addr, A_KCORE_STRIDE, A_RGROUP_STRIDE);
+            const uint64_t db = make_desc(b_addr, B_KCORE_STRIDE, B_NCORE_STRIDE);
             const uint32_t acc = ks > 0 ? 1u : 0u;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            if (ts_mode) {
+                const uint32_t a_tmem = tmem + 192 + ks * 8;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                    ::"r"(tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            } else {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                    ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     }
@@ -121,8 +151,8 @@ int main() {
     const int smem = 16384 + 24 * B_NCORE_STRIDE + 1024;
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int best = -1;
-    for (int combo = 0; combo < 4; ++combo) {
-        const int sa = combo & 1, sb = combo >> 1;
+    for (int combo = 0; combo < 2; ++combo) {
+        const int sa = combo, sb = 0;   // sa: 0 = A from shared memory, 1 = A from TMEM
         cudaMemset(dd, 0xff, M * N * 4); cudaMemset(ds, 0, 4);
         probe_kernel<<<1, 128, smem>>>(da, db, dd, sa, sb, ds);
         cudaError_t e = cudaDeviceSynchronize();
@@ -130,7 +160,7 @@ int main() {
         cudaMemcpy(out.data(), dd, M * N * 4, cudaMemcpyDeviceToHost);
         double maxerr = 0; int nan = 0;
         for (int i = 0; i < M * N; ++i) { if (out[i] != out[i]) { nan++; continue; } double d = fabs((double)out[i] - ref[i]); if (d > maxerr) maxerr = d; }
-        printf("swap_a=%d swap_b=%d : cuda=%s timeout=%d nan=%d max_abs_err=%.6f  (out[0]=%f ref[0]=%f out[last]=%f ref[last]=%f)\n", sa, sb,
+        printf("a_from_tmem=%d (%d) : cuda=%s timeout=%d nan=%d max_abs_err=%.6f  (out[0]=%f ref[0]=%f out[last]=%f ref[last]=%f)\n", sa, sb,
                cudaGetErrorString(e), st, nan, maxerr, out[0], ref[0], out[M * N - 1], ref[M * N - 1]);
         if (e == cudaSuccess && st == 0 && nan == 0 && maxerr < 1e-3) best = combo;
         if (e != cudaSuccess) break;
