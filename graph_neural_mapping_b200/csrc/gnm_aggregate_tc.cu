@@ -108,6 +108,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+
 __device__ __forceinline__ uint32_t bits2_bf16x2(uint32_t x) { return (x & 1u) * 0x3F80u + (x & 2u) * 0x1FC00000u; }
 
 __device__ __forceinline__ void split3_tc(float x, float& hi, float& mid, float& lo) {
@@ -185,19 +199,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 float inv_deg = 1.f;
                 if (p.mode == 1) inv_deg = (float)(p.rowptr[gr + 1] - p.rowptr[gr]);
                 const int64_t sr = p.src_map ? (int64_t)p.src_map[gr] : (int64_t)gr;
-#pragma unroll
-                for (int c0 = 0; c0 < TC_SLAB; c0 += 32) {
-                    uint32_t hi[32], mid[32], lo[32];
+#pragma unroll 1
+                for (int c0 = 0; c0 < TC_SLAB; c0 += 16) {
+                    uint32_t hi[16], mid[16], lo[16];
                     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + slot * TC_N + c0;
-                    tmem_ld32(taddr, hi);
-                    tmem_ld32(taddr + 64, mid);
-                    tmem_ld32(taddr + 128, lo);
+                    tmem_ld16(taddr, hi);
+                    tmem_ld16(taddr + 64, mid);
+                    tmem_ld16(taddr + 128, lo);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (row_ok) {
                         float* out = p.dst + (int64_t)gr * p.ld_dst + f0 + c0;
                         const float* self = p.src + sr * p.ld_src + f0 + c0;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
+                        for (int j = 0; j < 16; j += 4) {
                             if (f0 + c0 + j >= p.n_feat) break;
                             float v[4];
 #pragma unroll
@@ -367,21 +381,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                     if (((kc - first) & 1) == 0) {
                         // this group's stage: 64 bits -> 32 registers of bf16 pairs -> 32 TMEM columns of this row
                         const int c = (kc - first) >> 1;
-                        uint32_t v[32];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            v[j] = bits2_bf16x2(w_cur[c][0] >> (2 * j));
-                            v[16 + j] = bits2_bf16x2(w_cur[c][1] >> (2 * j));
-                        }
                         const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TC_A_TMEM0 + s * TC_A_COLS;
-                        asm volatile(
-                            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-                            "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-                            ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
-                              "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
-                              "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
-                              "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
-                              "r"(v[31]) : "memory");
+#pragma unroll
+                        for (int hw = 0; hw < 2; ++hw) {
+                            uint32_t v[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = bits2_bf16x2(w_cur[c][hw] >> (2 * j));
+                            tmem_st16(taddr + hw * 16, v);
+                        }
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     }
                     const long long tq1 = p.dbg ? clock64() : 0;
