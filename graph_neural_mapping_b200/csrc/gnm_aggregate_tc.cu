@@ -208,8 +208,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 float inv_deg = 1.f;
                 if (p.mode == 1) inv_deg = (float)(p.rowptr[gr + 1] - p.rowptr[gr]);
                 const int64_t sr = p.src_map ? (int64_t)p.src_map[gr] : (int64_t)gr;
+                // a warp whose 32 rows all lie beyond the graph (the tail of the last row tile) has nothing to drain
+                const int c_end = (mt * 128 + warp * 32 < n) ? TC_SLAB : 0;
 #pragma unroll 1
-                for (int c0 = 0; c0 < TC_SLAB; c0 += 16) {
+                for (int c0 = 0; c0 < c_end; c0 += 16) {
                     uint32_t hi[16], mid[16], lo[16];
                     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + slot * TC_N + c0;
                     tmem_ld16(taddr, hi);
@@ -394,7 +396,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                         if (DBG) c_bconv += clock64() - tb0;
                     }
                     const long long tq0 = DBG ? clock64() : 0;
-                    if (((kc - first) & 1) == 0) {
+                    // rows beyond the graph are never read back from the accumulator, so their A rows may hold
+                    // anything: a warp whose whole lane quarter is past the last node skips the expansion
+                    if (((kc - first) & 1) == 0 && mt * 128 + (warp & 3) * 32 < n) {
                         // this group's stage: 64 bits -> 32 registers of bf16 pairs -> 32 TMEM columns of this row
                         const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TC_A_TMEM0 + s * TC_A_COLS;
 #pragma unroll
