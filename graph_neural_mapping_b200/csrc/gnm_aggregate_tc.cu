@@ -17,7 +17,7 @@
 //   * D = 128 lanes x 192 fp32 columns in TMEM (columns 0-383: two slots; A ring in columns 384-511): the 4 epilogue warps drain slot s (tcgen05.ld,
 //     hi+mid+lo summed in registers, average / eps self term / bias, fp32 stores) while the MMA thread fills
 //     slot s^1 with the next 128-row tile.
-//   * warp roles: 0-3 epilogue, 4 MMA issue + TMEM alloc, 5-12 producers; mbarriers: a_full/a_empty[4],
+//   * warp roles: 0-3 epilogue, 4-11 producers, 12 MMA issue + TMEM alloc (highest warp id: issue priority); mbarriers: a_full/a_empty[4],
 //     acc_full/acc_empty[2], b_free. tcgen05.commit releases A stages / publishes accumulators. The B planes
 //     of an item are written chunk by chunk together with the A stages of its first row tile.
 //   * every wait is bounded: on a timeout the kernel raises an abort flag and drains instead of hanging.
@@ -36,6 +36,7 @@ constexpr int TC_SLAB = 64;
 constexpr int TC_MAX_NODES = 416;
 constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;   // 416
+constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;              // 12
 constexpr int TC_TMEM_COLS = 512;
 constexpr long long TC_TIMEOUT_CYCLES = 4000000000LL;
 
@@ -103,6 +104,14 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+
+// D[tmem] (+)= A[tmem] . B[smem descriptor]   (A operand from tensor memory)
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         mbar_init(b_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == TC_EPI_WARPS) {
+    if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -251,12 +260,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             }
         }
         if (DBG && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_role; p.dbg[blockIdx.x * 16 + 1] = w_acc; }
-    } else if (warp == TC_EPI_WARPS) {
+    } else if (warp == TC_MMA_WARP) {
         // ================================ MMA issue (one thread) ==========================================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(TC_N >> 3) << 17) |
                                    ((uint32_t)(128 >> 4) << 24);   // f32 acc, bf16 x bf16, A K-major, B MN-major
-            const uint32_t b_base = smem_u32(sm_b);
+            const uint64_t db_item = umma_desc(smem_u32(sm_b), 128, (uint32_t)b_ncore_stride);
             uint32_t a_it = 0, acc_it = 0, b_it = 0;
             bool ok = true;
             long long w_af = 0, w_ae = 0;
@@ -276,16 +285,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                         const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
                         if (!(ok = mbar_wait(&a_full[s], aph, abort_flag, DBG ? &w_af : nullptr))) break;
                         tc_fence_after();
+                        // lean issue path: the descriptor of k-step ks differs from the chunk's first one only in
+                        // its start-address field (+2 k-cores = 256 B = 16 units), the A operand by 8 TMEM columns
                         const int ks_n = min(4, ksteps_total - kc * 4);
-                        for (int ks = 0; ks < ks_n; ++ks) {
-                            const uint32_t a_tmem = tmem + TC_A_TMEM0 + s * TC_A_COLS + ks * 8;   // 16 k = 8 columns
-                            const uint64_t db = umma_desc(b_base + (kc * 8 + ks * 2) * 128, 128, (uint32_t)b_ncore_stride);
-                            const uint32_t accum = (kc | ks) ? 1u : 0u;
-                            asm volatile(
-                                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-                                ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(accum) : "memory");
-                        }
+                        const uint64_t db0 = db_item + (uint64_t)(kc * 8 * 128 >> 4);
+                        const uint32_t at0 = tmem + TC_A_TMEM0 + s * TC_A_COLS;
+                        umma_ts(d_tmem, at0, db0, idesc, kc ? 1u : 0u);
+                        if (ks_n > 1) umma_ts(d_tmem, at0 + 8, db0 + 16, idesc, 1u);
+                        if (ks_n > 2) umma_ts(d_tmem, at0 + 16, db0 + 32, idesc, 1u);
+                        if (ks_n > 3) umma_ts(d_tmem, at0 + 24, db0 + 48, idesc, 1u);
                         umma_commit(&a_empty[s]);          // frees the A stage when these MMAs retire
                     }
                     if (ok) umma_commit(&acc_full[slot]);  // accumulator complete -> epilogue
@@ -301,8 +309,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         // the two groups alternate stages). During the FIRST row tile of an item every producer warp also
         // converts the item's fp32 rows of the same 64 nodes into the three bf16 B planes in shared memory, so
         // the B fill is pipelined with the MMAs. Global loads run one tile (bitmap) / two chunks (features) ahead.
-        const int ptid = tid - (TC_EPI_WARPS + 1) * 32;                  // 0..255
-        const int grp = ptid >> 7;                                       // 0: warps 5-8, 1: warps 9-12
+        const int ptid = tid - TC_EPI_WARPS * 32;                        // 0..255
+        const int grp = ptid >> 7;                                       // 0: warps 4-7, 1: warps 8-11
         const int arow = (warp & 3) * 32 + lane;                         // row of the tile = TMEM lane
         uint32_t a_it = 0, b_it = 0;
         int prev_nkc = TC_STAGES;
@@ -432,7 +440,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == TC_EPI_WARPS) {
+    if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
     }
 }
