@@ -75,6 +75,21 @@ class GraphStore(object):
         self.entries.clear()
         self._tag_cache.clear()
 
+    def _staging(self, e_total):
+        """Pinned [2, E] int64 host buffer (grown geometrically, reused) for the edge lists of new graphs."""
+        cap = getattr(self, "_stage_cap", 0)
+        if cap < e_total or getattr(self, "_stage", None) is None:
+            cap = max(e_total, int(cap * 1.5), 1)
+            pin = self.device.type == "cuda"
+            self._stage = torch.empty(2 * cap, dtype=torch.int64, pin_memory=pin)
+            self._stage_cap = cap
+        if self.device.type == "cuda":
+            # the previous asynchronous copy out of this buffer must have finished before it is overwritten
+            ev = getattr(self, "_stage_event", None)
+            if ev is not None:
+                ev.synchronize()
+        return self._stage[:2 * e_total].view(2, e_total)
+
     def __len__(self):
         return len(self.entries)
 
@@ -97,16 +112,24 @@ class GraphStore(object):
                 em = torch.zeros(2, 0, dtype=torch.int64)
             ems.append(em.reshape(2, -1).to(torch.int64))
         edge_counts = [int(e.shape[1]) for e in ems]
-        edges = torch.cat(ems, 1).contiguous() if ems else torch.zeros(2, 0, dtype=torch.int64)
         edge_off = np.zeros(len(new) + 1, dtype=np.int64)
         np.cumsum(edge_counts, out=edge_off[1:])
         node_off = np.zeros(len(new) + 1, dtype=np.int64)
         np.cumsum(counts, out=node_off[1:])
         total_nodes = int(node_off[-1])
-        edges_d = edges.to(dev, non_blocking=True)
+        # stage the edge lists once in pinned memory (no torch.cat temporary, no pageable bounce buffer) and ship
+        # them with one asynchronous copy
+        e_total = int(edge_off[-1])
+        edges = self._staging(e_total)
+        for i, em in enumerate(ems):
+            edges[:, int(edge_off[i]):int(edge_off[i + 1])].copy_(em)
+        edges_d = edges.to(dev, non_blocking=True) if dev.type == "cuda" else edges.clone()
         edge_off_d = torch.from_numpy(edge_off).to(dev)
         node_off_d = torch.from_numpy(node_off.astype(np.int32)).to(dev)
         self.h2d_bytes += edges.numel() * 8 + edge_off.nbytes + node_off.nbytes // 2
+        if dev.type == "cuda":
+            self._stage_event = torch.cuda.Event()
+            self._stage_event.record()
         rowptr, colidx, status = _ops.csr_build(edges_d, edge_off_d, node_off_d, len(new), max(counts), total_nodes,
                                                 self.add_self_loops, True)
         if int(status.item()) != 0:
