@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also print the per-kernel time table to stderr")
+    ap.add_argument("--saliency", action="store_true",
+                    help="measure gradient-saliency extraction (graphcnn.py:254-299) throughput instead of training")
+    ap.add_argument("--saliency-batch", type=int, default=256, help="graphs per batched saliency call")
     return ap.parse_args()
 
 
@@ -380,8 +383,47 @@ def run_b200(args):
         gdist.shutdown()
 
 
+def run_saliency(args):
+    """BASELINE configs[4]: saliency maps (eval-mode forward + backward to the one-hot input) over this rank's
+    share of graphs, batched (exact). One step = one batched call writing a [B*N, N] fp32 map."""
+    from graph_neural_mapping_b200 import dist as gdist, synth
+    from graph_neural_mapping_b200.models import GIN_InfoMaxReg
+    comm, local_rank = gdist.init_from_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    b = args.saliency_batch
+    torch.manual_seed(0)
+    pool = synth.make_graphs_bulk(b, N_ROIS, 30, 256, seed0=1000 * comm.rank, device=dev)
+    model = GIN_InfoMaxReg(LAYERS, MLP_LAYERS, N_ROIS, HIDDEN, 2, 0.5, args.learn_eps, "sum", "sum", dev).to(dev)
+    for _ in range(max(args.warmup, 3)):
+        model.compute_saliency_batched(pool, 1)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if comm.world > 1:
+        torch.distributed.barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        sal = model.compute_saliency_batched(pool, 1)
+    ev1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if comm.world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    if comm.rank == 0:
+        print(json.dumps({"metric": "gin_saliency_graphs_per_sec_400roi", "value": b * comm.world * args.steps / (ms / 1e3),
+                          "unit": UNIT, "n_gpus": comm.world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
+                          "data": "synthetic", "config": {"workload": "gradient saliency, %d graphs per call, N=400, "
+                                                          "5-layer hidden 64" % b, "bytes_written_per_step": int(sal.numel() * 4)}}))
+    if comm.world > 1:
+        gdist.shutdown()
+
+
 def main():
     args = parse()
+    if args.saliency and args.impl != "reference":
+        return run_saliency(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -286,3 +286,33 @@ def test_two_gpu_data_parallel_matches_reference():
                           "--master-addr", "127.0.0.1", "--master-port", "29371", os.path.join(here, "run_dp_gpu.py")],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert "DP_GPU_CHECK_PASSED" in res.stdout, res.stdout[-3000:]
+
+
+def test_schaefer1000_hidden128_config_vs_oracle():
+    """BASELINE configs[3] shape class (N=1000 nodes, hidden 128): takes the general kernels - mma.sync block
+    aggregation (N > 416), 128-wide feature slabs, unfused backward, chunked table-gradient merge."""
+    torch.manual_seed(3)
+    graphs = synth.make_graphs(2, n_rois=1000, n_time=300, seed0=77)
+    for learn_eps in (True, False):
+        model = GIN_InfoMaxReg(2, 2, 1000, 128, 2, 0.0, learn_eps, "sum", "sum", DEV).to(DEV)
+        with torch.no_grad():
+            model.eps.copy_(torch.tensor([0.2, -0.1]))
+            for lin in model.linears_prediction:
+                lin.weight.mul_(0.01)
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        np.random.seed(5)
+        perm = np.random.permutation(2)
+        c_logit, d_logit, loss = train_step(model, graphs, 0.05, 5)
+        ocfg = gin_oracle.OracleConfig(2, 2, 1000, 128, 2, 0.0, learn_eps, "sum", "sum")
+        r = gin_oracle.train_step_grads(sd, graphs, perm, ocfg, 0.05, torch.float64)
+        assert_close(c_logit, r["c_logit"], TOL, "c_logit")
+        assert_close(d_logit, r["d_logit"], TOL, "d_logit")
+        assert_close(loss, r["loss"], TOL, "loss")
+        ograds = {k: (v.numpy() if v is not None else None) for k, v in r["grads"].items()}
+        floor = grad_floor(ograds)
+        for k, p in model.named_parameters():
+            if ograds.get(k) is not None:
+                assert_close(p.grad, ograds[k], TOL_GRAD, "grad " + k, floor=floor)
+        s = model.compute_saliency([graphs[0]], 0)
+        sref, _ = gin_oracle.saliency({k: v.detach().cpu() for k, v in model.state_dict().items()}, [graphs[0]], 0, ocfg)
+        assert_close(s, sref, TOL_GRAD, "saliency")
