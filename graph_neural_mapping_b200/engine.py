@@ -402,7 +402,6 @@ def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm):
         d_logit = torch.empty(2 * M, 1, dtype=torch.float32, device=dev)
         _ops.dgi_score_fwd(h_all, u_mat, neg_table, my_neg, bs.node_off, B, disc_b, d_logit)
         sv.c, sv.u_mat, sv.neg_table, sv.my_neg, sv.neg_idx = c, u_mat, neg_table, my_neg, neg_idx
-    sv.g_f = g_f
     return g_f, d_logit, sv
 
 
