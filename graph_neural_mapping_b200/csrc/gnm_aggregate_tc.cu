@@ -24,6 +24,7 @@
 #include <cuda_bf16.h>
 
 #include "gnm_common.cuh"
+#include "gnm_tc.cuh"
 
 namespace {
 
@@ -38,9 +39,6 @@ constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 8;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;   // 416
 constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;              // 12
 constexpr int TC_TMEM_COLS = 512;
-constexpr long long TC_TIMEOUT_CYCLES = 4000000000LL;
-
-__device__ int g_tc_abort = 0;
 
 struct AggTcParams {
     const int64_t* bitmap_addr;
@@ -55,111 +53,6 @@ struct AggTcParams {
     int n_graphs, n_feat, mode, n_slabs, kcores_max;
     long long* dbg;              // nullable: per-CTA wait/busy cycle counters (profiling aid)
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// bounded wait: false on timeout (the caller raises the abort flag and drains). The fast path is one try_wait;
-// the slow path lets the hardware suspend the thread (try_wait with a time hint) and only looks at the clock /
-// abort flag every 64 wake-ups, so waiting warps do not steal issue slots from the working ones.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag,
-                                          long long* waited = nullptr) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (done) return true;
-    const long long t0 = clock64();
-    int spins = 0;
-    while (true) {
-        asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, P;\n\t}"
-                     : "=r"(done) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
-        if (done) {
-            if (waited) *waited += clock64() - t0;
-            return true;
-        }
-        if ((++spins & 63) == 0) {
-            if (*abort_flag) return false;
-            if (clock64() - t0 > TC_TIMEOUT_CYCLES) {
-                *abort_flag = 1;
-                g_tc_abort = 1;
-                return false;
-            }
-        }
-    }
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// shared-memory matrix descriptor, no swizzle (layout_type 0), version 1
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
-}
-
-// D[tmem] (+)= A[tmem] . B[smem descriptor]   (A operand from tensor memory)
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-
-__device__ __forceinline__ uint32_t bits2_bf16x2(uint32_t x) { return (x & 1u) * 0x3F80u + (x & 2u) * 0x1FC00000u; }
-
-__device__ __forceinline__ void split3_tc(float x, float& hi, float& mid, float& lo) {
-    hi = __bfloat162float(__float2bfloat16_rn(x));
-    const float r1 = x - hi;
-    mid = __bfloat162float(__float2bfloat16_rn(r1));
-    lo = r1 - mid;
-}
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&v);
-}
-// exact fp32 -> (hi, mid, lo) bf16 split of two values at once (packed cvt.rn.bf16x2; bf16 -> fp32 is a shift / mask)
-__device__ __forceinline__ void split3x2(float x0, float x1, uint32_t& hi2, uint32_t& mid2, uint32_t& lo2) {
-    hi2 = pack2(x0, x1);
-    float r0 = x0 - __uint_as_float(hi2 << 16), r1 = x1 - __uint_as_float(hi2 & 0xffff0000u);
-    mid2 = pack2(r0, r1);
-    r0 -= __uint_as_float(mid2 << 16);
-    r1 -= __uint_as_float(mid2 & 0xffff0000u);
-    lo2 = pack2(r0, r1);
-}
 
 template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTcParams p) {
@@ -489,13 +382,16 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
 
 /* 1 if any tcgen05 aggregation launch since the last call hit a wait timeout (its output is then invalid).
  * Synchronises the device; for tests and smoke checks. */
+int gnm_linear_tc_abort_flag(int* aborted);     // gnm_linear_tc.cu
+
 extern "C" int gnm_aggregate_tc_status(int* aborted) {
     int v = 0, zero = 0;
     cudaError_t e = cudaMemcpyFromSymbol(&v, g_tc_abort, sizeof(int));
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpyToSymbol(g_tc_abort, &zero, sizeof(int));
+    if (e != cudaSuccess) return (int)e;
     if (aborted) *aborted = v;
-    return e == cudaSuccess ? GNM_OK : (int)e;
+    return gnm_linear_tc_abort_flag(aborted);
 }
 
 /* Profiling aid: while non-NULL, every tcgen05 aggregation launch writes per-CTA cycle counters to buf

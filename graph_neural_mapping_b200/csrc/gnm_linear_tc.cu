@@ -1,0 +1,318 @@
+// Linear layer on the 5th-generation tensor cores with fp32-level accuracy (reference: nn.Linear in
+// models/mlp.py:25,32-35,48-49, fused with the BatchNorm-apply + ReLU of the previous op and the batch
+// statistics of the next one, mlp.py:48 / graphcnn.py:163-166).
+//
+//   y[m, n] = sum_k f(x[m, k]) * W[n, k] + bias[n],   f(x) = relu(x*in_scale[k] + in_shift[k]) or x,  K, N <= 64
+//
+// fp32 operands are split exactly into three bf16 planes (hi + mid + lo, 8+8+8 significand bits). The products
+// kept are hi*hi, hi*mid, mid*hi, hi*lo, lo*hi, mid*mid - everything down to 2^-24 relative - six bf16 MMAs per
+// 16-wide k-step, all accumulating into the same 64 fp32 TMEM columns (the tensor pipe has ~20x headroom over the
+// HBM time of this op, so the 6x MMA count is free).
+//
+// One persistent CTA per SM, work item = 128-row tile:
+//   * producers (8 warps, two groups alternating tiles): one row per thread; 256 B of the row are loaded, f() applied,
+//     split, and the three planes written to TENSOR MEMORY (tcgen05.st; 96 columns per stage, 4-stage ring) - the A
+//     operand never touches shared memory;
+//   * B operand: the three W planes ([n][k], K-major core matrices) converted once per CTA into 24 KB of shared memory;
+//   * MMA thread: 24 x tcgen05.mma (M=128, N=64, K=16, A from TMEM) per tile, tcgen05.commit to free the stage and
+//     publish the accumulator (two 64-column slots);
+//   * epilogue (4 warps): tcgen05.ld, + bias, fp32 row stores, and the per-column sum / sum of squares of the tile
+//     by a shuffle transpose-reduction (31 shuffles per 32 columns instead of 5 per column), accumulated per lane
+//     across tiles and flushed once per CTA with fp64 atomics.
+#include "gnm_common.cuh"
+#include "gnm_tc.cuh"
+
+namespace {
+
+constexpr int LT_F = 64;                    // max K and N
+constexpr int LT_STAGES = 4;
+constexpr int LT_A_COLS = 96;               // TMEM columns per A stage: hi | mid | lo planes, 32 columns each
+constexpr int LT_D_COLS = 64;
+constexpr int LT_A_TMEM0 = 2 * LT_D_COLS;   // accumulator slots at columns [0,64) and [64,128)
+constexpr int LT_EPI_WARPS = 4, LT_PROD_WARPS = 8;
+constexpr int LT_THREADS = (LT_EPI_WARPS + LT_PROD_WARPS + 1) * 32;   // 416
+constexpr int LT_MMA_WARP = LT_EPI_WARPS + LT_PROD_WARPS;
+constexpr int LT_W_PLANE = LT_F * LT_F * 2;          // bytes of one bf16 W plane
+constexpr int LT_W_KCORE = 8 * 128;                  // [k-core][n-core][8 n-rows x 16 B]: bytes between k-cores
+constexpr int LT_SMEM = 3 * LT_W_PLANE + 2 * LT_F * 4 + 256;
+
+struct LinTcParams {
+    const float* x; int64_t ldx;
+    const float* w; int64_t ldw; int w_is_kn;
+    const float* bias; const float* in_scale; const float* in_shift;
+    float* y; int64_t ldy;
+    double* col_stats;
+    int n_rows, n_in, n_out;
+};
+
+// column sums over the 32 rows (lanes) of a warp for 32 columns: after the call lane l holds the total of column l in v[0]
+__device__ __forceinline__ void transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int step = 0; step < 5; ++step) {
+        const int off = 16 >> step;                 // lane distance 16, 8, 4, 2, 1
+        const int half = 16 >> step;                // columns kept per lane after this step
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const float send = upper ? v[j] : v[j + half];
+            const float keep = upper ? v[j + half] : v[j];
+            v[j] = keep + __shfl_xor_sync(GNM_FULL_MASK, send, off);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcParams p) {
+    extern __shared__ __align__(1024) unsigned char lt_smem[];
+    __shared__ __align__(8) uint64_t bars[2 * LT_STAGES + 4];
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_abort;
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + LT_STAGES;
+    uint64_t* acc_full = bars + 2 * LT_STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    unsigned char* sm_w = lt_smem;                                     // 3 planes x 8 KB
+    float* sm_sc = reinterpret_cast<float*>(lt_smem + 3 * LT_W_PLANE);  // in_scale[64] | in_shift[64]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    volatile int* abort_flag = &s_abort;
+    const int n_tiles = (p.n_rows + 127) >> 7;
+    const bool act = p.in_scale != nullptr;
+
+    // ---- one-time setup: W planes (K-major core matrices), prologue constants, barriers, tensor memory
+    for (int e = tid; e < LT_F * LT_F / 2; e += LT_THREADS) {
+        const int n = e >> 5, k = (e & 31) * 2;                       // element pair (n, k), (n, k+1)
+        float w0 = 0.f, w1 = 0.f;
+        if (n < p.n_out) {
+            if (k < p.n_in) w0 = p.w_is_kn ? p.w[(int64_t)k * p.ldw + n] : p.w[(int64_t)n * p.ldw + k];
+            if (k + 1 < p.n_in) w1 = p.w_is_kn ? p.w[(int64_t)(k + 1) * p.ldw + n] : p.w[(int64_t)n * p.ldw + k + 1];
+        }
+        uint32_t h, m, l;
+        split3x2(w0, w1, h, m, l);
+        const int off = (k >> 3) * LT_W_KCORE + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
+        *reinterpret_cast<uint32_t*>(sm_w + off) = h;
+        *reinterpret_cast<uint32_t*>(sm_w + LT_W_PLANE + off) = m;
+        *reinterpret_cast<uint32_t*>(sm_w + 2 * LT_W_PLANE + off) = l;
+    }
+    for (int k = tid; k < LT_F; k += LT_THREADS) {
+        sm_sc[k] = (act && k < p.n_in) ? p.in_scale[k] : 1.f;
+        sm_sc[LT_F + k] = (act && k < p.n_in) ? p.in_shift[k] : 0.f;
+    }
+    if (tid == 0) {
+        s_abort = 0;
+        for (int i = 0; i < LT_STAGES; ++i) { mbar_init(&a_full[i], LT_PROD_WARPS / 2); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], LT_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == LT_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    if (warp < LT_EPI_WARPS) {
+        // ================================ epilogue =========================================================
+        float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f};
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles && !*abort_flag; tile += gridDim.x, ++it) {
+            const uint32_t slot = it & 1, ph = (it >> 1) & 1;
+            if (!mbar_wait(&acc_full[slot], ph, abort_flag)) break;
+            tc_fence_after();
+            const int r = tile * 128 + warp * 32 + lane;
+            const bool row_ok = r < p.n_rows;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float v[32];
+#pragma unroll
+                for (int c0 = 0; c0 < 32; c0 += 16) {
+                    uint32_t t16[16];
+                    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + slot * LT_D_COLS + hf * 32 + c0, t16);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[c0 + j] = __uint_as_float(t16[j]);
+                }
+                if (hf == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[slot]);   // the accumulator is in registers: free the slot
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int c = hf * 32 + j;
+                    if (c >= p.n_out) break;
+                    if (p.bias != nullptr) {
+                        v[j] += __ldg(p.bias + c);
+                        if (c + 1 < p.n_out) v[j + 1] += __ldg(p.bias + c + 1);
+                        if (c + 2 < p.n_out) v[j + 2] += __ldg(p.bias + c + 2);
+                        if (c + 3 < p.n_out) v[j + 3] += __ldg(p.bias + c + 3);
+                    }
+                    if (row_ok) {
+                        float* out = p.y + (int64_t)r * p.ldy + c;
+                        if (c + 3 < p.n_out && (p.ldy & 3) == 0 && gnm_aligned16(p.y)) {
+                            *reinterpret_cast<float4*>(out) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (c + q < p.n_out) out[q] = v[j + q];
+                        }
+                    }
+                }
+                if (p.col_stats != nullptr) {
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = (row_ok && hf * 32 + j < p.n_out) ? v[j] : 0.f;
+                        v[j] = x;
+                        sq[j] = x * x;
+                    }
+                    transpose_reduce32(v, lane);
+                    transpose_reduce32(sq, lane);
+                    st1[hf] += v[0];
+                    st2[hf] += sq[0];
+                }
+            }
+        }
+        if (p.col_stats != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int c = q * 32 + lane;
+                if (c < p.n_out) {
+                    atomicAdd(&p.col_stats[c], (double)st1[q]);
+                    atomicAdd(&p.col_stats[p.n_out + c], (double)st2[q]);
+                }
+            }
+        }
+    } else if (warp == LT_MMA_WARP) {
+        // ================================ MMA issue (one thread) ============================================
+        if (lane == 0) {
+            // f32 accumulate, bf16 x bf16, B K-major, N = 64, M = 128 (A comes from tensor memory)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LT_F >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t dw_hi = umma_desc(smem_u32(sm_w), LT_W_KCORE, 128);
+            const uint64_t dw_mid = dw_hi + (uint64_t)(LT_W_PLANE >> 4);
+            const uint64_t dw_lo = dw_hi + (uint64_t)(2 * LT_W_PLANE >> 4);
+            const int ksteps = (p.n_in + 15) >> 4;
+            uint32_t it = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
+                const uint32_t s = it % LT_STAGES, aph = (it / LT_STAGES) & 1;
+                const uint32_t slot = it & 1, ph = (it >> 1) & 1;
+                if (!(ok = mbar_wait(&acc_empty[slot], ph ^ 1, abort_flag))) break;
+                if (!(ok = mbar_wait(&a_full[s], aph, abort_flag))) break;
+                tc_fence_after();
+                const uint32_t d = tmem + slot * LT_D_COLS;
+                const uint32_t a0 = tmem + LT_A_TMEM0 + s * LT_A_COLS;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint64_t kofs = (uint64_t)(ks * 2 * LT_W_KCORE >> 4);
+                    const uint32_t ah = a0 + ks * 8, am = ah + 32, al = ah + 64;
+                    umma_ts(d, ah, dw_hi + kofs, idesc, ks ? 1u : 0u);      // hi * hi
+                    umma_ts(d, ah, dw_mid + kofs, idesc, 1u);               // hi * mid
+                    umma_ts(d, am, dw_hi + kofs, idesc, 1u);                // mid * hi
+                    umma_ts(d, ah, dw_lo + kofs, idesc, 1u);                // hi * lo
+                    umma_ts(d, al, dw_hi + kofs, idesc, 1u);                // lo * hi
+                    umma_ts(d, am, dw_mid + kofs, idesc, 1u);               // mid * mid
+                }
+                umma_commit(&a_empty[s]);
+                umma_commit(&acc_full[slot]);
+            }
+        }
+    } else {
+        // ================================ producers: one row per thread, two warp groups alternate tiles =========
+        const int grp = (warp - LT_EPI_WARPS) >> 2;                       // 0: warps 4-7, 1: warps 8-11
+        const int arow = (warp & 3) * 32 + lane;                          // TMEM lane = row of the tile
+        uint32_t it = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
+            if ((it & 1) != (uint32_t)grp) continue;
+            const uint32_t s = it % LT_STAGES, aph = (it / LT_STAGES) & 1;
+            const int r = tile * 128 + arow;
+            const bool row_ok = r < p.n_rows;
+            const float* xr = p.x + (int64_t)(row_ok ? r : 0) * p.ldx;
+            const bool vec = (p.ldx & 3) == 0 && gnm_aligned16(p.x) && (p.n_in & 3) == 0;
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + LT_A_TMEM0 + s * LT_A_COLS;
+            bool waited = false;
+#pragma unroll
+            for (int k0 = 0; k0 < LT_F; k0 += 32) {
+                float xv[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int k = k0 + j;
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row_ok && k < p.n_in) {
+                        if (vec) {
+                            t = ld_stream_f4(xr + k);
+                        } else {
+                            t.x = xr[k];
+                            if (k + 1 < p.n_in) t.y = xr[k + 1];
+                            if (k + 2 < p.n_in) t.z = xr[k + 2];
+                            if (k + 3 < p.n_in) t.w = xr[k + 3];
+                        }
+                    }
+                    xv[j] = t.x; xv[j + 1] = t.y; xv[j + 2] = t.z; xv[j + 3] = t.w;
+                }
+                uint32_t hi[16], mid[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float a = xv[j], b = xv[j + 1];
+                    if (act) {
+                        a = (row_ok && k0 + j < p.n_in) ? fmaxf(fmaf(a, sm_sc[k0 + j], sm_sc[LT_F + k0 + j]), 0.f) : 0.f;
+                        b = (row_ok && k0 + j + 1 < p.n_in) ? fmaxf(fmaf(b, sm_sc[k0 + j + 1], sm_sc[LT_F + k0 + j + 1]), 0.f) : 0.f;
+                    }
+                    split3x2(a, b, hi[j >> 1], mid[j >> 1], lo[j >> 1]);
+                }
+                if (!waited) {
+                    // the global loads above are in flight while we wait for the ring slot
+                    if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag))) break;
+                    waited = true;
+                }
+                tmem_st16(taddr + (k0 >> 1), hi);
+                tmem_st16(taddr + 32 + (k0 >> 1), mid);
+                tmem_st16(taddr + 64 + (k0 >> 1), lo);
+            }
+            if (!ok) break;
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[s]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == LT_MMA_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+}  // namespace
+
+// GNM_OK after launching; GNM_ERR_TOO_LARGE when the shape does not fit this kernel (caller uses the FFMA kernel)
+int gnm_launch_linear_tc(const float* x, int64_t ldx, int n_rows, int n_in, const float* w, int64_t ldw, int w_is_kn,
+                         const float* bias, const float* in_scale, const float* in_shift, float* y, int64_t ldy,
+                         int n_out, double* col_stats, cudaStream_t stream) {
+    if (n_in > LT_F || n_out > LT_F || n_in < 1 || n_out < 1) return GNM_ERR_TOO_LARGE;
+    int dev = 0, sms = 148, major = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) return GNM_ERR_TOO_LARGE;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    LinTcParams p;
+    p.x = x; p.ldx = ldx; p.w = w; p.ldw = ldw; p.w_is_kn = w_is_kn; p.bias = bias; p.in_scale = in_scale;
+    p.in_shift = in_shift; p.y = y; p.ldy = ldy; p.col_stats = col_stats; p.n_rows = n_rows; p.n_in = n_in; p.n_out = n_out;
+    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    const int tiles = (n_rows + 127) / 128;
+    const int grid = tiles < sms ? tiles : sms;
+    linear_tc_kernel<<<grid, LT_THREADS, LT_SMEM, stream>>>(p);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? GNM_OK : (int)e;
+}
+
+int gnm_linear_tc_abort_flag(int* aborted) {
+    int v = 0, zero = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&v, g_tc_abort, sizeof(int));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(g_tc_abort, &zero, sizeof(int));
+    if (aborted) *aborted |= v;
+    return e == cudaSuccess ? GNM_OK : (int)e;
+}

@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libgnm.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _c_i32 = ctypes.c_int
 _c_i64 = ctypes.c_int64
@@ -35,6 +35,7 @@ SIGNATURES = {
     "gnm_scatter_rows_add": [_p, _c_i64, _p, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p, _c_i64, _p],
     "gnm_scatter_rows_workspace": [_c_i32, _c_i32, _c_i32],
     "gnm_linear": [_p, _c_i64, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p, _p, _p, _p, _c_i64, _c_i32, _p, _p],
+    "gnm_set_linear_impl": [_c_i32],
     "gnm_linear_wgrad": [_p, _c_i64, _p, _c_i64, _c_i32, _c_i32, _c_i32, _p, _p, _p, _c_i64, _p, _p],
     "gnm_bn_bwd_coeffs": [_p, _c_f64, _p, _p, _p, _p, _c_i32, _p],
     "gnm_linear_bwd": [_p, _c_i64, _p, _c_i64, _p, _p, _c_i64, _p, _p, _p, _p, _p, _c_i64, _p, _c_i64, _p, _p, _c_i64,

@@ -161,6 +161,11 @@ def scatter_rows_add(g, tags, table_grad):
 
 # ---- MLP -----------------------------------------------------------------------------------
 
+def set_linear_impl(impl):
+    """0 auto, 1 fp32 FFMA kernel, 2 tcgen05 kernel (process-wide A/B switch)."""
+    _libmod.check(_lib().gnm_set_linear_impl(int(impl)), "gnm_set_linear_impl")
+
+
 def linear(x, w, w_is_kn, bias, in_scale, in_shift, y, col_stats):
     xp, ldx = _mat(x)
     wp, ldw = _mat(w)

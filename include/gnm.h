@@ -32,7 +32,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 7
+#define GNM_ABI_VERSION 8
 
 typedef void* gnm_stream_t;
 
@@ -103,7 +103,7 @@ int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* node_off, con
                         int n_graphs, int n_max, const float* src, int64_t ld_src, const int32_t* src_map,
                         float* dst, int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
                         int impl, gnm_stream_t stream);
-/* *aborted = 1 if a tcgen05 aggregation launch since the last call ran into a (bounded) barrier-wait timeout
+/* *aborted = 1 if a tcgen05 kernel (aggregation or linear) launched since the last call ran into a (bounded) barrier-wait timeout
  * and drained without producing valid output. Synchronises the device; meant for tests / smoke checks. */
 int gnm_aggregate_tc_status(int* aborted);
 /* Profiling aid: while buf != NULL every tcgen05 aggregation launch writes 16 int64 cycle counters per CTA to buf
@@ -134,6 +134,11 @@ int gnm_linear(const float* x, int64_t ldx, int n_rows, int n_in,
                const float* w, int64_t ldw, int w_is_kn, const float* bias,
                const float* in_scale, const float* in_shift,
                float* y, int64_t ldy, int n_out, double* col_stats, gnm_stream_t stream);
+
+/* gnm_linear implementation switch (process-wide A/B aid; the only global setting of the library):
+ * 0 = auto (tcgen05 kernel for n_in, n_out <= 64 and n_rows >= 4096, fp32 FFMA kernel otherwise), 1 = FFMA only,
+ * 2 = tcgen05 only. The tcgen05 kernel keeps fp32-level accuracy by exact bf16x3 operand splits (six MMAs per k-step). */
+int gnm_set_linear_impl(int impl);
 
 /* Weight gradient: dw[o, i] += sum_m dz[m, o] * f(x[m, i]); dbias[o] += sum_m dz[m, o] (nullable).
  * f as in gnm_linear (recompute of the BatchNorm+ReLU activation instead of storing it). */

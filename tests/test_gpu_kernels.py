@@ -479,3 +479,35 @@ def test_linear_bwd_fused(m, fo, fi, act, train):
     dwr2, dbr2 = torch.zeros(fo, fi), torch.zeros(fo)
     emul_ops.linear_bwd(c(dy), c(z), c(coef), c(x), None, None, None, None, c(w), dwr2, dbr2, None, None)
     assert_close(dw2, dwr2, TOL, "dw (no dx)")
+
+
+@pytest.mark.parametrize("m,k,n", [(1, 1, 1), (37, 10, 8), (300, 64, 64), (5000, 64, 64), (129, 12, 12), (20000, 48, 64),
+                                   (4097, 64, 33), (40000, 64, 64)])
+@pytest.mark.parametrize("kn,pro,stats", [(False, False, True), (False, True, True), (True, False, False), (True, True, True)])
+def test_linear_tcgen05(m, k, n, kn, pro, stats):
+    """The tensor-core Linear (bf16x3 exact operand splits, six tcgen05 MMAs per k-step) against the fp64
+    stand-in at the same tolerance as the fp32 FFMA kernel, and against the FFMA kernel itself."""
+    torch.manual_seed(m + k + n)
+    x = torch.randn(m, k, device=DEV) * 3
+    w = torch.randn((k, n) if kn else (n, k), device=DEV) * 0.3
+    b = torch.randn(n, device=DEV)
+    sc = torch.rand(k, device=DEV) + 0.5 if pro else None
+    sh = torch.randn(k, device=DEV) if pro else None
+    try:
+        outs = []
+        for impl in (2, 1):
+            ops.set_linear_impl(impl)
+            y = torch.full((m, n), float("nan"), device=DEV)
+            st = torch.zeros(2 * n, dtype=torch.float64, device=DEV) if stats else None
+            ops.linear(x, w, kn, b, sc, sh, y, st)
+            outs.append((y, st))
+    finally:
+        ops.set_linear_impl(0)
+    assert not ops.aggregate_tc_status(), "tcgen05 kernel hit a barrier timeout"
+    yr = torch.empty(m, n)
+    sr = torch.zeros(2 * n, dtype=torch.float64) if stats else None
+    emul_ops.linear(x.cpu(), w.cpu(), kn, b.cpu(), sc.cpu() if pro else None, sh.cpu() if pro else None, yr, sr)
+    assert_close(outs[0][0], yr, TOL, "tcgen05 linear vs fp64")
+    assert_close(outs[0][0], outs[1][0], TOL, "tcgen05 vs FFMA")
+    if stats:
+        assert_close(outs[0][1], sr, 1e-5, "tcgen05 col_stats")
