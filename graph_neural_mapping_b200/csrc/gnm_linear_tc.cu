@@ -10,7 +10,7 @@
 // HBM time of this op, so the 6x MMA count is free).
 //
 // One persistent CTA per SM, work item = 128-row tile:
-//   * producers (8 warps, two groups alternating tiles): one row per thread; 256 B of the row are loaded, f() applied,
+//   * producers (16 warps = four groups taking tiles round-robin): one row per thread; 256 B of the row are loaded, f() applied,
 //     split, and the three planes written to TENSOR MEMORY (tcgen05.st; 96 columns per stage, 4-stage ring) - the A
 //     operand never touches shared memory;
 //   * B operand: the three W planes ([n][k], K-major core matrices) converted once per CTA into 24 KB of shared memory;
@@ -29,8 +29,8 @@ constexpr int LT_STAGES = 4;
 constexpr int LT_A_COLS = 96;               // TMEM columns per A stage: hi | mid | lo planes, 32 columns each
 constexpr int LT_D_COLS = 64;
 constexpr int LT_A_TMEM0 = 2 * LT_D_COLS;   // accumulator slots at columns [0,64) and [64,128)
-constexpr int LT_EPI_WARPS = 4, LT_PROD_WARPS = 8;
-constexpr int LT_THREADS = (LT_EPI_WARPS + LT_PROD_WARPS + 1) * 32;   // 416
+constexpr int LT_EPI_WARPS = 4, LT_PROD_WARPS = 16, LT_GROUPS = LT_PROD_WARPS / 4;
+constexpr int LT_THREADS = (LT_EPI_WARPS + LT_PROD_WARPS + 1) * 32;   // 672
 constexpr int LT_MMA_WARP = LT_EPI_WARPS + LT_PROD_WARPS;
 constexpr int LT_W_PLANE = LT_F * LT_F * 2;          // bytes of one bf16 W plane
 constexpr int LT_W_KCORE = 8 * 128;                  // [k-core][n-core][8 n-rows x 16 B]: bytes between k-cores
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
     }
     if (tid == 0) {
         s_abort = 0;
-        for (int i = 0; i < LT_STAGES; ++i) { mbar_init(&a_full[i], LT_PROD_WARPS / 2); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < LT_STAGES; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], LT_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -219,12 +219,14 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
         }
     } else {
         // ================================ producers: one row per thread, two warp groups alternate tiles =========
-        const int grp = (warp - LT_EPI_WARPS) >> 2;                       // 0: warps 4-7, 1: warps 8-11
+        // four warps (one per TMEM lane quarter) form a group; the groups take tiles round-robin, so the global-load
+        // latency of one group's tile is hidden behind the other groups' work (the loads are not software-pipelined)
+        const int grp = (warp - LT_EPI_WARPS) >> 2;
         const int arow = (warp & 3) * 32 + lane;                          // TMEM lane = row of the tile
         uint32_t it = 0;
         bool ok = true;
         for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
-            if ((it & 1) != (uint32_t)grp) continue;
+            if ((it % LT_GROUPS) != (uint32_t)grp) continue;
             const uint32_t s = it % LT_STAGES, aph = (it / LT_STAGES) & 1;
             const int r = tile * 128 + arow;
             const bool row_ok = r < p.n_rows;
