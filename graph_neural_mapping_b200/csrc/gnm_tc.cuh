@@ -23,9 +23,10 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// bounded wait: false on timeout (the caller raises the abort flag and drains). The fast path is one try_wait;
-// the slow path lets the hardware suspend the thread (try_wait with a time hint) and only looks at the clock /
-// abort flag every 64 wake-ups, so waiting warps do not steal issue slots from the working ones.
+// bounded wait: false on timeout (the caller raises the abort flag and drains). try_wait suspends the thread in
+// hardware for a short, implementation-defined time; the clock / abort flag are only consulted every 64 wake-ups.
+// (A try_wait with an explicit suspend-time hint was measured to sleep the WHOLE hint - 20 us per wait - instead of
+// waking on completion, which capped both tensor-core kernels; do not use it.)
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag,
                                           long long* waited = nullptr) {
     const uint32_t addr = smem_u32(bar);
@@ -36,8 +37,8 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
     const long long t0 = clock64();
     int spins = 0;
     while (true) {
-        asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, P;\n\t}"
-                     : "=r"(done) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+        asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) {
             if (waited) *waited += clock64() - t0;
             return true;
