@@ -10,13 +10,13 @@
 // HBM time of this op, so the 6x MMA count is free).
 //
 // One persistent CTA per SM, work item = 128-row tile:
-//   * producers (16 warps = four groups taking tiles round-robin): one row per thread; 256 B of the row are loaded, f() applied,
+//   * producers (8 warps = two groups taking tiles alternately): one row per thread; 256 B of the row are loaded, f() applied,
 //     split, and the three planes written to TENSOR MEMORY (tcgen05.st; 96 columns per stage, 4-stage ring) - the A
 //     operand never touches shared memory;
 //   * B operand: the three W planes ([n][k], K-major core matrices) converted once per CTA into 24 KB of shared memory;
 //   * MMA thread: 24 x tcgen05.mma (M=128, N=64, K=16, A from TMEM) per tile, tcgen05.commit to free the stage and
 //     publish the accumulator (two 64-column slots);
-//   * epilogue (4 warps): tcgen05.ld, + bias, fp32 row stores, and the per-column sum / sum of squares of the tile
+//   * epilogue (8 warps: one group of four per accumulator slot): tcgen05.ld, + bias, fp32 row stores, and the per-column sum / sum of squares of the tile
 //     by a shuffle transpose-reduction (31 shuffles per 32 columns instead of 5 per column), accumulated per lane
 //     across tiles and flushed once per CTA with fp64 atomics.
 #include "gnm_common.cuh"
@@ -29,12 +29,12 @@ constexpr int LT_STAGES = 4;
 constexpr int LT_A_COLS = 96;               // TMEM columns per A stage: hi | mid | lo planes, 32 columns each
 constexpr int LT_D_COLS = 64;
 constexpr int LT_A_TMEM0 = 2 * LT_D_COLS;   // accumulator slots at columns [0,64) and [64,128)
-constexpr int LT_EPI_WARPS = 4, LT_PROD_WARPS = 16, LT_GROUPS = LT_PROD_WARPS / 4;
-constexpr int LT_THREADS = (LT_EPI_WARPS + LT_PROD_WARPS + 1) * 32;   // 672
+constexpr int LT_EPI_WARPS = 8, LT_PROD_WARPS = 8, LT_GROUPS = LT_PROD_WARPS / 4;
+constexpr int LT_THREADS = (LT_EPI_WARPS + LT_PROD_WARPS + 1) * 32;   // 544
 constexpr int LT_MMA_WARP = LT_EPI_WARPS + LT_PROD_WARPS;
 constexpr int LT_W_PLANE = LT_F * LT_F * 2;          // bytes of one bf16 W plane
 constexpr int LT_W_KCORE = 8 * 128;                  // [k-core][n-core][8 n-rows x 16 B]: bytes between k-cores
-constexpr int LT_SMEM = 3 * LT_W_PLANE + 2 * LT_F * 4 + 256;
+constexpr int LT_SMEM = 3 * LT_W_PLANE + 3 * LT_F * 4 + 256;
 
 struct LinTcParams {
     const float* x; int64_t ldx;
@@ -95,11 +95,12 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
     for (int k = tid; k < LT_F; k += LT_THREADS) {
         sm_sc[k] = (act && k < p.n_in) ? p.in_scale[k] : 1.f;
         sm_sc[LT_F + k] = (act && k < p.n_in) ? p.in_shift[k] : 0.f;
+        sm_sc[2 * LT_F + k] = (p.bias != nullptr && k < p.n_out) ? p.bias[k] : 0.f;
     }
     if (tid == 0) {
         s_abort = 0;
         for (int i = 0; i < LT_STAGES; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], LT_EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == LT_MMA_WARP) {
@@ -114,13 +115,18 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
 
     if (warp < LT_EPI_WARPS) {
         // ================================ epilogue =========================================================
+        // A warp executes its instruction stream serially (well under one instruction per cycle), so one group of
+        // four warps per accumulator slot drains every other tile: twice the epilogue throughput of a single group.
         float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f};
+        const uint32_t my_slot = warp >> 2;
+        const int q = warp & 3;                       // TMEM lane quarter of this warp
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles && !*abort_flag; tile += gridDim.x, ++it) {
             const uint32_t slot = it & 1, ph = (it >> 1) & 1;
+            if (slot != my_slot) continue;
             if (!mbar_wait(&acc_full[slot], ph, abort_flag)) break;
             tc_fence_after();
-            const int r = tile * 128 + warp * 32 + lane;
+            const int r = tile * 128 + q * 32 + lane;
             const bool row_ok = r < p.n_rows;
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
 #pragma unroll
                 for (int c0 = 0; c0 < 32; c0 += 16) {
                     uint32_t t16[16];
-                    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + slot * LT_D_COLS + hf * 32 + c0, t16);
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + slot * LT_D_COLS + hf * 32 + c0, t16);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[c0 + j] = __uint_as_float(t16[j]);
@@ -142,11 +148,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
                 for (int j = 0; j < 32; j += 4) {
                     const int c = hf * 32 + j;
                     if (c >= p.n_out) break;
-                    if (p.bias != nullptr) {
-                        v[j] += __ldg(p.bias + c);
-                        if (c + 1 < p.n_out) v[j + 1] += __ldg(p.bias + c + 1);
-                        if (c + 2 < p.n_out) v[j + 2] += __ldg(p.bias + c + 2);
-                        if (c + 3 < p.n_out) v[j + 3] += __ldg(p.bias + c + 3);
+                    {
+                        const float4 b = *reinterpret_cast<const float4*>(sm_sc + 2 * LT_F + c);   // zero beyond n_out
+                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
                     }
                     if (row_ok) {
                         float* out = p.y + (int64_t)r * p.ldy + c;

@@ -11,7 +11,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
            ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
 }
 
-__global__ void __launch_bounds__(128) rate_kernel(int n, int a_swz, int b_swz, int reps, long long* cycles) {
+__global__ void __launch_bounds__(128) rate_kernel(int n, int a_swz, int b_swz, int reps, long long* cycles, int a_tmem_mode, int same_d) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base;
@@ -42,9 +42,16 @@ __global__ void __launch_bounds__(128) rate_kernel(int n, int a_swz, int b_swz, 
             else da = make_desc(smem_u32(sa) + ks * 2 * 2048, 2048, 128, 0);          // no swizzle
             if (b_swz) db = make_desc(smem_u32(sb) + ks * 2 * 1024, 8192, 1024, 2);   // SW128 MN-major: 64-wide n atoms at LBO, 8 k-rows at SBO
             else db = make_desc(smem_u32(sb) + ks * 2 * 128, 128, 8 * 128 + 16, 0);   // no swizzle
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                         ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
+            const uint32_t dcol = same_d ? 0u : (uint32_t)((r & 1) * 64);   // alternate accumulators (only valid for n <= 64)
+            if (a_tmem_mode) {
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                             ::"r"(tmem + dcol), "r"(tmem + 192 + ks * 8), "l"(db), "r"(idesc), "r"(1u) : "memory");
+            } else {
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(tmem + dcol), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
+            }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
         uint32_t done = 0;
@@ -65,14 +72,16 @@ int main() {
     cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int reps = 2048;
     const int ns[4] = {64, 128, 192, 256};
-    for (int grid : {1, 148})
+    for (int grid : {148})
         for (int cfg = 0; cfg < 4; ++cfg)
             for (int ni = 0; ni < 4; ++ni) {
-                rate_kernel<<<grid, 128, smem>>>(ns[ni], cfg & 1, cfg >> 1, reps, d);
+                const int a_tm = cfg & 1, same_d = (cfg >> 1) ? 0 : 1;
+                if (!same_d && ns[ni] > 64) continue;
+                rate_kernel<<<grid, 128, smem>>>(ns[ni], 0, 0, reps, d, a_tm, same_d);
                 cudaError_t e = cudaDeviceSynchronize();
                 long long h[148]; cudaMemcpy(h, d, grid * 8, cudaMemcpyDeviceToHost);
                 long long mx = 0; for (int i = 0; i < grid; ++i) if (h[i] > mx) mx = h[i];
-                printf("grid=%3d a_swz=%d b_swz=%d N=%3d : %s  %.1f cycles/MMA (floor %d)\n", grid, cfg & 1, cfg >> 1, ns[ni],
+                printf("grid=%3d A_from_tmem=%d same_accumulator=%d N=%3d : %s  %.1f cycles/MMA (floor %d)\n", grid, a_tm, same_d, ns[ni],
                        cudaGetErrorString(e), (double)mx / reps, 128 * ns[ni] / 256);
                 if (e != cudaSuccess) return 1;
             }
