@@ -34,7 +34,9 @@ constexpr int LT_THREADS = (LT_EPI_WARPS + LT_PROD_WARPS + 1) * 32;   // 544
 constexpr int LT_MMA_WARP = LT_EPI_WARPS + LT_PROD_WARPS;
 constexpr int LT_W_PLANE = LT_F * LT_F * 2;          // bytes of one bf16 W plane
 constexpr int LT_W_KCORE = 8 * 128;                  // [k-core][n-core][8 n-rows x 16 B]: bytes between k-cores
-constexpr int LT_SMEM = 3 * LT_W_PLANE + 3 * LT_F * 4 + 256;
+constexpr int LT_PITCH = LT_F + 4;                  // floats per staged row: 272 B, row-per-lane 128-bit accesses are conflict-optimal
+constexpr int LT_STG = 32 * LT_PITCH * 4;            // bytes of one warp's 32-row staging tile
+constexpr int LT_SMEM = 3 * LT_W_PLANE + 3 * LT_F * 4 + 256 + (LT_EPI_WARPS + LT_PROD_WARPS) * LT_STG;
 
 struct LinTcParams {
     const float* x; int64_t ldx;
@@ -71,7 +73,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
     uint64_t* acc_full = bars + 2 * LT_STAGES;
     uint64_t* acc_empty = acc_full + 2;
     unsigned char* sm_w = lt_smem;                                     // 3 planes x 8 KB
-    float* sm_sc = reinterpret_cast<float*>(lt_smem + 3 * LT_W_PLANE);  // in_scale[64] | in_shift[64]
+    float* sm_sc = reinterpret_cast<float*>(lt_smem + 3 * LT_W_PLANE);  // in_scale[64] | in_shift[64] | bias[64]
+    // per-warp staging tiles: global memory is only touched with coalesced 128-bit accesses (a row-per-lane access
+    // costs 32 L1 wavefronts per instruction and made the first version L1-bound)
+    float* sm_stg = reinterpret_cast<float*>(lt_smem + 3 * LT_W_PLANE + 3 * LT_F * 4 + 256);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     volatile int* abort_flag = &s_abort;
     const int n_tiles = (p.n_rows + 127) >> 7;
@@ -128,6 +133,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
             tc_fence_after();
             const int r = tile * 128 + q * 32 + lane;
             const bool row_ok = r < p.n_rows;
+            float* stg = sm_stg + warp * (32 * LT_PITCH);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 float v[32];
@@ -152,16 +158,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
                         const float4 b = *reinterpret_cast<const float4*>(sm_sc + 2 * LT_F + c);   // zero beyond n_out
                         v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
                     }
-                    if (row_ok) {
-                        float* out = p.y + (int64_t)r * p.ldy + c;
-                        if (c + 3 < p.n_out && (p.ldy & 3) == 0 && gnm_aligned16(p.y)) {
-                            *reinterpret_cast<float4*>(out) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (c + q < p.n_out) out[q] = v[j + q];
-                        }
-                    }
+                    *reinterpret_cast<float4*>(stg + lane * LT_PITCH + c) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
                 if (p.col_stats != nullptr) {
                     float sq[32];
@@ -177,6 +174,24 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
                     st2[hf] += sq[0];
                 }
             }
+            // copy the warp's 32 x 64 tile out with coalesced 128-bit stores (two rows per instruction)
+            __syncwarp();
+            const int row0 = tile * 128 + q * 32;
+            if (p.n_out == LT_F && (p.ldy & 3) == 0 && gnm_aligned16(p.y)) {
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) {
+                    const int rr = i * 2 + (lane >> 4), c4 = lane & 15;
+                    if (row0 + rr < p.n_rows)
+                        *reinterpret_cast<float4*>(p.y + (int64_t)(row0 + rr) * p.ldy + c4 * 4) =
+                            *reinterpret_cast<const float4*>(stg + rr * LT_PITCH + c4 * 4);
+                }
+            } else {
+                for (int e = lane; e < 32 * LT_F; e += 32) {
+                    const int rr = e >> 6, c = e & 63;
+                    if (row0 + rr < p.n_rows && c < p.n_out) p.y[(int64_t)(row0 + rr) * p.ldy + c] = stg[rr * LT_PITCH + c];
+                }
+            }
+            __syncwarp();
         }
         if (p.col_stats != nullptr) {
 #pragma unroll
@@ -223,52 +238,71 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
         }
     } else {
         // ================================ producers: one row per thread, two warp groups alternate tiles =========
-        // four warps (one per TMEM lane quarter) form a group; the groups take tiles round-robin, so the global-load
-        // latency of one group's tile is hidden behind the other groups' work (the loads are not software-pipelined)
+        // four warps (one per TMEM lane quarter) form a group; the groups take tiles alternately. A warp's 32 rows are
+        // fetched with cp.async one own-tile ahead into its staging tile, then read back one row per lane.
         const int grp = (warp - LT_EPI_WARPS) >> 2;
-        const int arow = (warp & 3) * 32 + lane;                          // TMEM lane = row of the tile
+        const int q = warp & 3;                                           // TMEM lane quarter = 32-row slice of the tile
+        float* stg = sm_stg + warp * (32 * LT_PITCH);
+        const uint32_t stg_u32 = smem_u32(stg);
+        const bool fast = p.n_in == LT_F && (p.ldx & 3) == 0 && gnm_aligned16(p.x);
+        // stage the warp's 32 rows of a tile: cp.async (coalesced 16-byte chunks, rows past the end zero-filled)
+        auto stage_rows = [&](int tile) {
+            const int row0 = tile * 128 + q * 32;
+            if (fast) {
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) {
+                    const int rr = i * 2 + (lane >> 4), c4 = lane & 15;
+                    const bool okr = row0 + rr < p.n_rows;
+                    const float* src = p.x + (int64_t)(okr ? row0 + rr : 0) * p.ldx + c4 * 4;
+                    const uint32_t dst = stg_u32 + (uint32_t)((rr * LT_PITCH + c4 * 4) * 4);
+                    const int nbytes = okr ? 16 : 0;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+                }
+            } else {
+                for (int e = lane; e < 32 * LT_F; e += 32) {
+                    const int rr = e >> 6, k = e & 63;
+                    stg[rr * LT_PITCH + k] = (row0 + rr < p.n_rows && k < p.n_in) ? p.x[(int64_t)(row0 + rr) * p.ldx + k] : 0.f;
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
         uint32_t it = 0;
         bool ok = true;
+        // first own tile
+        {
+            const int first_tile = blockIdx.x + grp * gridDim.x;
+            if (first_tile < n_tiles) stage_rows(first_tile);
+        }
         for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
             if ((it % LT_GROUPS) != (uint32_t)grp) continue;
             const uint32_t s = it % LT_STAGES, aph = (it / LT_STAGES) & 1;
-            const int r = tile * 128 + arow;
-            const bool row_ok = r < p.n_rows;
-            const float* xr = p.x + (int64_t)(row_ok ? r : 0) * p.ldx;
-            const bool vec = (p.ldx & 3) == 0 && gnm_aligned16(p.x) && (p.n_in & 3) == 0;
-            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + LT_A_TMEM0 + s * LT_A_COLS;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + LT_A_TMEM0 + s * LT_A_COLS;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
             bool waited = false;
 #pragma unroll
             for (int k0 = 0; k0 < LT_F; k0 += 32) {
-                float xv[32];
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int k = k0 + j;
-                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row_ok && k < p.n_in) {
-                        if (vec) {
-                            t = ld_stream_f4(xr + k);
-                        } else {
-                            t.x = xr[k];
-                            if (k + 1 < p.n_in) t.y = xr[k + 1];
-                            if (k + 2 < p.n_in) t.z = xr[k + 2];
-                            if (k + 3 < p.n_in) t.w = xr[k + 3];
-                        }
-                    }
-                    xv[j] = t.x; xv[j + 1] = t.y; xv[j + 2] = t.z; xv[j + 3] = t.w;
-                }
                 uint32_t hi[16], mid[16], lo[16];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float a = xv[j], b = xv[j + 1];
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(stg + lane * LT_PITCH + k0 + j);
+                    float a0 = t.x, a1 = t.y, a2 = t.z, a3 = t.w;
                     if (act) {
-                        a = (row_ok && k0 + j < p.n_in) ? fmaxf(fmaf(a, sm_sc[k0 + j], sm_sc[LT_F + k0 + j]), 0.f) : 0.f;
-                        b = (row_ok && k0 + j + 1 < p.n_in) ? fmaxf(fmaf(b, sm_sc[k0 + j + 1], sm_sc[LT_F + k0 + j + 1]), 0.f) : 0.f;
+                        const float4 sc = *reinterpret_cast<const float4*>(sm_sc + k0 + j);
+                        const float4 sh = *reinterpret_cast<const float4*>(sm_sc + LT_F + k0 + j);
+                        a0 = fmaxf(fmaf(a0, sc.x, sh.x), 0.f); a1 = fmaxf(fmaf(a1, sc.y, sh.y), 0.f);
+                        a2 = fmaxf(fmaf(a2, sc.z, sh.z), 0.f); a3 = fmaxf(fmaf(a3, sc.w, sh.w), 0.f);
                     }
-                    split3x2(a, b, hi[j >> 1], mid[j >> 1], lo[j >> 1]);
+                    split3x2(a0, a1, hi[j >> 1], mid[j >> 1], lo[j >> 1]);
+                    split3x2(a2, a3, hi[(j >> 1) + 1], mid[(j >> 1) + 1], lo[(j >> 1) + 1]);
+                }
+                if (k0 == 32) {
+                    // the staged rows are in registers now: start fetching this warp's next tile into the same buffer
+                    __syncwarp();
+                    const int next_tile = tile + LT_GROUPS * gridDim.x;
+                    if (next_tile < n_tiles) stage_rows(next_tile);
                 }
                 if (!waited) {
-                    // the global loads above are in flight while we wait for the ring slot
                     if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag))) break;
                     waited = true;
                 }
@@ -282,6 +316,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[s]);
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
