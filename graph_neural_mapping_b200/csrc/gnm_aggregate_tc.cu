@@ -17,7 +17,8 @@
 //   * D = 128 lanes x 192 fp32 columns in TMEM (columns 0-383: two slots; A ring in columns 384-511): the 4 epilogue warps drain slot s (tcgen05.ld,
 //     hi+mid+lo summed in registers, average / eps self term / bias, fp32 stores) while the MMA thread fills
 //     slot s^1 with the next 128-row tile.
-//   * warp roles: 0-3 epilogue, 4-11 producers, 12 MMA issue + TMEM alloc (highest warp id: issue priority); mbarriers: a_full/a_empty[4],
+//   * warp roles: 0-7 epilogue (two groups, one per accumulator slot), 8-15 producers, 16 MMA issue + TMEM alloc
+//     (highest warp id: issue priority); mbarriers: a_full/a_empty[4],
 //     acc_full/acc_empty[2], b_free. tcgen05.commit releases A stages / publishes accumulators. The B planes
 //     of an item are written chunk by chunk together with the A stages of its first row tile.
 //   * every wait is bounded: on a timeout the kernel raises an abort flag and drains instead of hanging.
@@ -35,8 +36,10 @@ constexpr int TC_A_TMEM0 = 384;                // first TMEM column of the A rin
 constexpr int TC_N = 192;                      // three 64-feature planes side by side
 constexpr int TC_SLAB = 64;
 constexpr int TC_MAX_NODES = 416;
-constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 8;
-constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;   // 416
+constexpr int TC_EPI_WARPS = 8, TC_PROD_WARPS = 8;       // epilogue: one group of four warps per accumulator slot
+constexpr int TC_PITCH = TC_SLAB + 4;                    // floats per staged output row (272 B: conflict-optimal)
+constexpr int TC_STG = 32 * TC_PITCH * 4;                // bytes of one epilogue warp's staging tile
+constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;   // 544
 constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;              // 12
 constexpr int TC_TMEM_COLS = 512;
 
@@ -68,13 +71,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     uint64_t* b_free = b_full + 1;
     const int b_ncore_stride = p.kcores_max * 128 + 16;            // SBO of B (padded: conflict-free plane fill)
     unsigned char* sm_b = tc_smem;                                  // 24 n-cores x b_ncore_stride
+    float* sm_stg = reinterpret_cast<float*>(tc_smem + (size_t)24 * b_ncore_stride);   // TC_EPI_WARPS staging tiles
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     volatile int* abort_flag = &s_abort;
     if (tid == 0) {
         s_abort = 0;
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&a_full[i], TC_PROD_WARPS); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], TC_EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         mbar_init(b_full, TC_PROD_WARPS);
         mbar_init(b_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -90,11 +94,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     const int n_items = p.n_graphs * p.n_slabs;
 
     if (warp < TC_EPI_WARPS) {
-        // ================================ epilogue: TMEM -> registers -> global ==========================
+        // ================================ epilogue: TMEM -> registers -> staging tile -> global ===========
+        // Two groups of four warps (group = accumulator slot) drain alternate row tiles. Each warp sums the three
+        // plane accumulators of its 32 rows, stages them in shared memory and copies them out with coalesced 128-bit
+        // stores (a row-per-lane store costs 32 L1 wavefronts per instruction); the eps self term and the bias are
+        // added during the copy-out, where the source rows are read coalesced as well.
         uint32_t acc_it = 0;
         long long w_acc = 0;
         const long long t_role = clock64();
         const float self_c = p.eps ? 1.f + __ldg(p.eps) : 0.f;
+        const uint32_t my_slot = warp >> 2;
+        const int q = warp & 3;
+        float* stg = sm_stg + warp * (32 * TC_PITCH);
         for (int item = blockIdx.x; item < n_items && !*abort_flag; item += gridDim.x) {
             const int gi = item / p.n_slabs, slab = item % p.n_slabs;
             const int n0 = p.node_off[gi], n = p.node_off[gi + 1] - n0;
@@ -102,54 +113,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             const int n_mt = (n + 127) >> 7;
             for (int mt = 0; mt < n_mt; ++mt, ++acc_it) {
                 const uint32_t slot = acc_it & 1, ph = (acc_it >> 1) & 1;
+                if (slot != my_slot) continue;
                 if (!mbar_wait(&acc_full[slot], ph, abort_flag, DBG ? &w_acc : nullptr)) break;
                 tc_fence_after();
-                const int r = mt * 128 + warp * 32 + lane;
-                const bool row_ok = r < n;
-                const int gr = n0 + (row_ok ? r : 0);
-                float inv_deg = 1.f;
-                if (p.mode == 1) inv_deg = (float)(p.rowptr[gr + 1] - p.rowptr[gr]);
-                const int64_t sr = p.src_map ? (int64_t)p.src_map[gr] : (int64_t)gr;
+                const int row0 = mt * 128 + q * 32;              // first row (within the graph) of this warp's slice
+                const int r = row0 + lane;
+                const int gr = n0 + (r < n ? r : 0);
+                float deg = 1.f;
+                if (p.mode == 1) deg = (float)(p.rowptr[gr + 1] - p.rowptr[gr]);
                 // a warp whose 32 rows all lie beyond the graph (the tail of the last row tile) has nothing to drain
-                const int c_end = (mt * 128 + warp * 32 < n) ? TC_SLAB : 0;
+                const bool any_rows = row0 < n;
+                if (any_rows) {
 #pragma unroll 1
-                for (int c0 = 0; c0 < c_end; c0 += 16) {
-                    uint32_t hi[16], mid[16], lo[16];
-                    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + slot * TC_N + c0;
-                    tmem_ld16(taddr, hi);
-                    tmem_ld16(taddr + 64, mid);
-                    tmem_ld16(taddr + 128, lo);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (row_ok) {
-                        float* out = p.dst + (int64_t)gr * p.ld_dst + f0 + c0;
-                        const float* self = p.src + sr * p.ld_src + f0 + c0;
+                    for (int c0 = 0; c0 < TC_SLAB; c0 += 16) {
+                        uint32_t hi[16], mid[16], lo[16];
+                        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * TC_N + c0;
+                        tmem_ld16(taddr, hi);
+                        tmem_ld16(taddr + 64, mid);
+                        tmem_ld16(taddr + 128, lo);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            if (f0 + c0 + j >= p.n_feat) break;
                             float v[4];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                v[q] = (__uint_as_float(lo[j + q]) + __uint_as_float(mid[j + q])) + __uint_as_float(hi[j + q]);
+                            for (int e = 0; e < 4; ++e)
+                                v[e] = (__uint_as_float(lo[j + e]) + __uint_as_float(mid[j + e])) + __uint_as_float(hi[j + e]);
                             if (p.mode == 1) {
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) v[q] /= inv_deg;
+                                for (int e = 0; e < 4; ++e) v[e] /= deg;
                             }
-                            if (p.eps) {
-                                const float4 s = __ldg(reinterpret_cast<const float4*>(self + j));
-                                v[0] = fmaf(self_c, s.x, v[0]); v[1] = fmaf(self_c, s.y, v[1]);
-                                v[2] = fmaf(self_c, s.z, v[2]); v[3] = fmaf(self_c, s.w, v[3]);
-                            }
-                            if (p.bias) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + f0 + c0 + j));
-                                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-                            }
-                            *reinterpret_cast<float4*>(out + j) = make_float4(v[0], v[1], v[2], v[3]);
+                            *reinterpret_cast<float4*>(stg + lane * TC_PITCH + c0 + j) = make_float4(v[0], v[1], v[2], v[3]);
                         }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[slot]);
+                if (lane == 0) mbar_arrive(&acc_empty[slot]);       // accumulator drained: the MMA may reuse the slot
+                if (any_rows) {
+                    const int c4 = lane & 15;
+                    const int col = f0 + c4 * 4;
+                    if (col < p.n_feat) {
+                        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll 4
+                        for (int i = 0; i < 16; ++i) {
+                            const int rr = i * 2 + (lane >> 4);
+                            if (row0 + rr >= n) continue;
+                            const int g2 = n0 + row0 + rr;
+                            float4 v = *reinterpret_cast<const float4*>(stg + rr * TC_PITCH + c4 * 4);
+                            if (p.eps) {
+                                const int64_t sr = p.src_map ? (int64_t)p.src_map[g2] : (int64_t)g2;
+                                const float4 sv = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
+                                v.x = fmaf(self_c, sv.x, v.x); v.y = fmaf(self_c, sv.y, v.y);
+                                v.z = fmaf(self_c, sv.z, v.z); v.w = fmaf(self_c, sv.w, v.w);
+                            }
+                            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                            *reinterpret_cast<float4*>(p.dst + (int64_t)g2 * p.ld_dst + col) = v;
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
         if (DBG && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_role; p.dbg[blockIdx.x * 16 + 1] = w_acc; }
@@ -203,7 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         // converts the item's fp32 rows of the same 64 nodes into the three bf16 B planes in shared memory, so
         // the B fill is pipelined with the MMAs. Global loads run one tile (bitmap) / two chunks (features) ahead.
         const int ptid = tid - TC_EPI_WARPS * 32;                        // 0..255
-        const int grp = ptid >> 7;                                       // 0: warps 4-7, 1: warps 8-11
+        const int grp = ptid >> 7;                                       // 0: warps 8-11, 1: warps 12-15
         const int arow = (warp & 3) * 32 + lane;                         // row of the tile = TMEM lane
         uint32_t a_it = 0, b_it = 0;
         int prev_nkc = TC_STAGES;
@@ -362,7 +385,7 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
     p.dbg = g_tc_dbg_host;
     p.n_slabs = (n_feat + TC_SLAB - 1) / TC_SLAB;
     p.kcores_max = ((n_max + 15) / 16) * 2;
-    const int smem = 24 * (p.kcores_max * 128 + 16) + 1024;   // B planes (the A ring lives in tensor memory)
+    const int smem = 24 * (p.kcores_max * 128 + 16) + TC_EPI_WARPS * TC_STG + 1024;   // B planes + epilogue staging
     if (smem > smem_cap - 1024) return GNM_ERR_TOO_LARGE;
     const int64_t items = (int64_t)n_graphs * p.n_slabs;
     const int grid = (int)(items < sms ? items : sms);
