@@ -36,7 +36,7 @@ constexpr int TC_A_TMEM0 = 384;                // first TMEM column of the A rin
 constexpr int TC_N = 192;                      // three 64-feature planes side by side
 constexpr int TC_SLAB = 64;
 constexpr int TC_MAX_NODES = 416;
-constexpr int TC_EPI_WARPS = 8, TC_PROD_WARPS = 8;       // epilogue: one group of four warps per accumulator slot
+constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 8;       // 4: one epilogue group drains both slots; 8: one group per slot
 constexpr int TC_PITCH = TC_SLAB + 4;                    // floats per staged output row (272 B: conflict-optimal)
 constexpr int TC_STG = 32 * TC_PITCH * 4;                // bytes of one epilogue warp's staging tile
 constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;   // 544
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     volatile int* abort_flag = &s_abort;
     if (tid == 0) {
         s_abort = 0;
-        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&a_full[i], TC_PROD_WARPS); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&a_full[i], TC_PROD_WARPS / 2); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         mbar_init(b_full, TC_PROD_WARPS);
         mbar_init(b_free, 1);
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             const int n_mt = (n + 127) >> 7;
             for (int mt = 0; mt < n_mt; ++mt, ++acc_it) {
                 const uint32_t slot = acc_it & 1, ph = (acc_it >> 1) & 1;
-                if (slot != my_slot) continue;
+                if (TC_EPI_WARPS == 8 && slot != my_slot) continue;
                 if (!mbar_wait(&acc_full[slot], ph, abort_flag, DBG ? &w_acc : nullptr)) break;
                 tc_fence_after();
                 const int row0 = mt * 128 + q * 32;              // first row (within the graph) of this warp's slice
@@ -258,11 +258,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                     w[c][1] = (rok && kc < n_kc && 2 * kc + 1 < words) ? __ldg(rowbits + 2 * kc + 1) : 0u;
                 }
             };
-            float4 bq[2][4];
-            auto load_b = [&](int kc, float4 (&dst4)[4]) {
+            // A stage belongs to ONE group of four warps (the groups alternate stages and run as two independent
+            // pipelines): the owner expands the adjacency tile and, during the first row tile, also converts the
+            // 64 feature rows of that chunk into the three B planes.
+            const int gtid = ptid & 127;
+            float4 bq[8];
+            auto load_b = [&](int kc) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int idx = ptid + u * 256;                  // 64 nodes x 16 float4
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = gtid + u * 128;                  // 64 nodes x 16 float4
                     const int k = kc * TC_KC + (idx >> 4), c4 = idx & 15;
                     const int col = f0 + c4 * 4;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -275,55 +279,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                             v.x *= w; v.y *= w; v.z *= w; v.w *= w;
                         }
                     }
-                    dst4[u] = v;
+                    bq[u] = v;
                 }
             };
-            // Code size matters here: three roles share a 32 KB instruction cache (an unrolled chunk loop made the
-            // kernel 120 KB of SASS and 26 % of all stall samples were instruction-fetch misses). The chunk loop is
-            // therefore NOT unrolled; register arrays are only indexed statically (word queue shifts down after
-            // each owned stage, the two B buffers swap roles by copy).
             uint32_t w_cur[MYC][2], w_nxt[MYC][2];
             load_words(0, a_it, w_cur);
-            load_b(0, bq[0]);
-            load_b(1, bq[1]);
+            load_b(((a_it & 1) == (uint32_t)grp) ? 0 : 1);
+            bool first_b = true;
             for (int mt = 0; mt < n_mt && ok; ++mt) {
                 load_words(mt + 1, a_it + n_kc, w_nxt);
                 const int first = ((a_it & 1) == (uint32_t)grp) ? 0 : 1;
 #pragma unroll 1
-                for (int kc = 0; kc < n_kc; ++kc) {
+                for (int kc = 0; kc < n_kc; ++kc, ++a_it) {
+                    if (((kc - first) & 1) != 0) continue;          // the other group's stage
                     const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
                     if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag, DBG ? &w_pe : nullptr))) break;
                     if (mt == 0) {
                         // the previous item's MMAs on these B rows retired at least TC_STAGES stages ago, unless
                         // that item had fewer k chunks than the ring: then wait for its explicit b_free commit
-                        if (kc == 0 && prev_nkc < TC_STAGES) {
+                        if (first_b && prev_nkc < TC_STAGES) {
                             if (!(ok = mbar_wait(b_free, (b_it & 1) ^ 1, abort_flag))) break;
                         }
+                        first_b = false;
                         const long long tb0 = DBG ? clock64() : 0;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int idx = ptid + u * 256;
+                        for (int u = 0; u < 8; ++u) {
+                            const int idx = gtid + u * 128;
                             const int k = kc * TC_KC + (idx >> 4), c4 = idx & 15;
                             if (k >= ksteps_total * 16) continue;
                             uint32_t h0, m0, l0, h1, m1, l1;
-                            split3x2(bq[0][u].x, bq[0][u].y, h0, m0, l0);
-                            split3x2(bq[0][u].z, bq[0][u].w, h1, m1, l1);
+                            split3x2(bq[u].x, bq[u].y, h0, m0, l0);
+                            split3x2(bq[u].z, bq[u].w, h1, m1, l1);
                             unsigned char* dstp = sm_b + (size_t)(c4 >> 1) * b_ncore_stride + (k >> 3) * 128 + (k & 7) * 16 + (c4 & 1) * 8;
                             *reinterpret_cast<uint2*>(dstp) = make_uint2(h0, h1);
                             *reinterpret_cast<uint2*>(dstp + 8 * (size_t)b_ncore_stride) = make_uint2(m0, m1);
                             *reinterpret_cast<uint2*>(dstp + 16 * (size_t)b_ncore_stride) = make_uint2(l0, l1);
                         }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) bq[0][u] = bq[1][u];      // chunk kc+1 moves to the front
-                        if (kc + 2 < n_kc) load_b(kc + 2, bq[1]);
+                        if (kc + 2 < n_kc) load_b(kc + 2);
                         fence_async_smem();
                         if (DBG) c_bconv += clock64() - tb0;
                     }
                     const long long tq0 = DBG ? clock64() : 0;
                     // rows beyond the graph are never read back from the accumulator, so their A rows may hold
                     // anything: a warp whose whole lane quarter is past the last node skips the expansion
-                    if (((kc - first) & 1) == 0 && mt * 128 + (warp & 3) * 32 < n) {
-                        // this group's stage: 64 bits -> 32 registers of bf16 pairs -> 32 TMEM columns of this row
+                    if (mt * 128 + (warp & 3) * 32 < n) {
+                        // 64 bits -> 32 registers of bf16 pairs -> 32 TMEM columns of this row
                         const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TC_A_TMEM0 + s * TC_A_COLS;
 #pragma unroll
                         for (int hw = 0; hw < 2; ++hw) {
@@ -341,7 +341,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&a_full[s]);
                     if (DBG) { const long long tq3 = clock64(); c_st += tq1 - tq0; c_arr += tq3 - tq1; }
-                    ++a_it;
                 }
 #pragma unroll
                 for (int c = 0; c < MYC; ++c) { w_cur[c][0] = w_nxt[c][0]; w_cur[c][1] = w_nxt[c][1]; }
