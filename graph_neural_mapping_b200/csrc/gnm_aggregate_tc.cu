@@ -72,8 +72,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     const int b_ncore_stride = p.kcores_max * 128 + 16;            // SBO of B (padded: conflict-free plane fill)
     unsigned char* sm_b = tc_smem;                                  // 24 n-cores x b_ncore_stride
     float* sm_stg = reinterpret_cast<float*>(tc_smem + (size_t)24 * b_ncore_stride);   // TC_EPI_WARPS staging tiles
+    // byte -> eight bf16 0/1 values (four 32-bit TMEM columns): the adjacency expansion is a table lookup
+    uint4* lut = reinterpret_cast<uint4*>(tc_smem + (size_t)24 * b_ncore_stride + TC_EPI_WARPS * TC_STG);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 256) {
+        const uint32_t b8 = tid;
+        lut[tid] = make_uint4(bits2_bf16x2(b8), bits2_bf16x2(b8 >> 2), bits2_bf16x2(b8 >> 4), bits2_bf16x2(b8 >> 6));
+    }
     volatile int* abort_flag = &s_abort;
     if (tid == 0) {
         s_abort = 0;
@@ -329,7 +335,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                         for (int hw = 0; hw < 2; ++hw) {
                             uint32_t v[16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = bits2_bf16x2(w_cur[0][hw] >> (2 * j));
+                            for (int b = 0; b < 4; ++b) {
+                                const uint4 t4 = lut[(w_cur[0][hw] >> (8 * b)) & 0xffu];
+                                v[4 * b] = t4.x; v[4 * b + 1] = t4.y; v[4 * b + 2] = t4.z; v[4 * b + 3] = t4.w;
+                            }
                             tmem_st16(taddr + hw * 16, v);
                         }
 #pragma unroll
@@ -384,7 +393,7 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
     p.dbg = g_tc_dbg_host;
     p.n_slabs = (n_feat + TC_SLAB - 1) / TC_SLAB;
     p.kcores_max = ((n_max + 15) / 16) * 2;
-    const int smem = 24 * (p.kcores_max * 128 + 16) + TC_EPI_WARPS * TC_STG + 1024;   // B planes + epilogue staging
+    const int smem = 24 * (p.kcores_max * 128 + 16) + TC_EPI_WARPS * TC_STG + 4096 + 1024;   // B planes + staging + LUT
     if (smem > smem_cap - 1024) return GNM_ERR_TOO_LARGE;
     const int64_t items = (int64_t)n_graphs * p.n_slabs;
     const int grid = (int)(items < sms ? items : sms);
