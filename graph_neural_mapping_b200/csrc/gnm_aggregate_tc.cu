@@ -414,6 +414,7 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
 /* 1 if any tcgen05 aggregation launch since the last call hit a wait timeout (its output is then invalid).
  * Synchronises the device; for tests and smoke checks. */
 int gnm_linear_tc_abort_flag(int* aborted);     // gnm_linear_tc.cu
+int gnm_linear_bwd_tc_abort_flag(int* aborted); // gnm_linear_bwd_tc.cu
 
 extern "C" int gnm_aggregate_tc_status(int* aborted) {
     int v = 0, zero = 0;
@@ -422,7 +423,8 @@ extern "C" int gnm_aggregate_tc_status(int* aborted) {
     e = cudaMemcpyToSymbol(g_tc_abort, &zero, sizeof(int));
     if (e != cudaSuccess) return (int)e;
     if (aborted) *aborted = v;
-    return gnm_linear_tc_abort_flag(aborted);
+    const int rc = gnm_linear_tc_abort_flag(aborted);
+    return rc != GNM_OK ? rc : gnm_linear_bwd_tc_abort_flag(aborted);
 }
 
 /* Profiling aid: while non-NULL, every tcgen05 aggregation launch writes per-CTA cycle counters to buf

@@ -1,0 +1,639 @@
+// Backward of one Linear -> BatchNorm (-> ReLU) unit on the 5th-generation tensor cores, input-gradient half
+// (reference: autograd of models/mlp.py:48-49 and models/graphcnn.py:162-166). Same contract as the dx / stats_in part
+// of gnm_linear_bwd (gnm_mlp_bwd.cu); the weight-gradient half is gnm_linear_wgrad_tc below.
+//
+//   dz = cA*dy + cB*z + cC (BatchNorm backward as an affine map of the two streams), so by linearity
+//   dx[m, i] = sum_o dy[m,o] * (cA[o] W[o,i]) + sum_o z[m,o] * (cB[o] W[o,i]) + sum_o cC[o] W[o,i]
+// i.e. two GEMMs into the same accumulator with the per-channel coefficients folded into two copies of W, plus a
+// constant row. dy and z are split exactly into three bf16 planes each (tensor memory, one row per lane), the two
+// scaled W copies into three planes each (shared memory), six MMAs per operand pair and 16-wide k-step.
+// Epilogue: + constant row, ReLU mask of the unit below (a = relu(x*in_scale + in_shift) > 0, x staged with cp.async),
+// its BatchNorm-backward reduction (sum dx, sum dx*xhat) by a shuffle transpose-reduce, coalesced stores through a
+// per-warp staging tile.
+#include "gnm_common.cuh"
+#include "gnm_tc.cuh"
+
+namespace {
+
+constexpr int BT_F = 64;
+constexpr int BT_STAGES = 2;
+constexpr int BT_A_COLS = 192;              // per stage: dy hi|mid|lo (96 columns) then z hi|mid|lo (96 columns)
+constexpr int BT_D_COLS = 64;
+constexpr int BT_A_TMEM0 = 2 * BT_D_COLS;
+constexpr int BT_EPI_WARPS = 8, BT_PROD_WARPS = 8;
+constexpr int BT_THREADS = (BT_EPI_WARPS + BT_PROD_WARPS + 1) * 32;
+constexpr int BT_MMA_WARP = BT_EPI_WARPS + BT_PROD_WARPS;
+constexpr int BT_W_PLANE = BT_F * BT_F * 2;
+constexpr int BT_W_KCORE = 8 * 128;
+constexpr int BT_PITCH = BT_F + 4;
+constexpr int BT_STG = 32 * BT_PITCH * 4;
+constexpr int BT_CONST_FLOATS = 5 * BT_F;   // c_row | in_scale | in_shift | in_mean | in_rstd
+constexpr int BT_SMEM = 6 * BT_W_PLANE + BT_CONST_FLOATS * 4 + 256 + (BT_EPI_WARPS + BT_PROD_WARPS) * BT_STG;
+
+struct LinBwdTcParams {
+    const float* dy; int64_t lddy;
+    const float* z; int64_t ldz;
+    const float* coef;                     // [3][n_out]
+    const float* w; int64_t ldw;           // [n_out][n_in]
+    const float* x; int64_t ldx;           // input of the unit: previous pre-BN tensor (with in_scale) or plain input
+    const float* in_scale; const float* in_shift; const float* in_mean; const float* in_rstd;
+    float* dx; int64_t lddx;
+    double* stats_in;
+    int n_rows, n_out, n_in;
+};
+
+__device__ __forceinline__ void transpose_reduce32_b(float (&v)[32], int lane) {
+#pragma unroll
+    for (int step = 0; step < 5; ++step) {
+        const int off = 16 >> step, half = 16 >> step;
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const float send = upper ? v[j] : v[j + half];
+            const float keep = upper ? v[j + half] : v[j];
+            v[j] = keep + __shfl_xor_sync(GNM_FULL_MASK, send, off);
+        }
+    }
+}
+
+// cp.async a warp's 32 rows x 64 floats (rows past n_rows zero-filled) into its padded staging tile
+__device__ __forceinline__ void stage_rows_async(const float* base, int64_t ld, int n_rows, int n_cols, int row0, float* stg,
+                                                 uint32_t stg_u32, int lane, bool fast) {
+    if (fast) {
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const int rr = i * 2 + (lane >> 4), c4 = lane & 15;
+            const bool okr = row0 + rr < n_rows;
+            const float* src = base + (int64_t)(okr ? row0 + rr : 0) * ld + c4 * 4;
+            const uint32_t dst = stg_u32 + (uint32_t)((rr * BT_PITCH + c4 * 4) * 4);
+            const int nbytes = okr ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+        }
+    } else {
+        for (int e = lane; e < 32 * BT_F; e += 32) {
+            const int rr = e >> 6, k = e & 63;
+            stg[rr * BT_PITCH + k] = (row0 + rr < n_rows && k < n_cols) ? base[(int64_t)(row0 + rr) * ld + k] : 0.f;
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const LinBwdTcParams p) {
+    extern __shared__ __align__(1024) unsigned char bt_smem[];
+    __shared__ __align__(8) uint64_t bars[2 * BT_STAGES + 4];
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_abort;
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + BT_STAGES;
+    uint64_t* acc_full = bars + 2 * BT_STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    unsigned char* sm_w = bt_smem;                                       // planes: WA hi|mid|lo, WB hi|mid|lo
+    float* sm_c = reinterpret_cast<float*>(bt_smem + 6 * BT_W_PLANE);
+    float* sm_stg = reinterpret_cast<float*>(bt_smem + 6 * BT_W_PLANE + BT_CONST_FLOATS * 4 + 256);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    volatile int* abort_flag = &s_abort;
+    const int n_tiles = (p.n_rows + 127) >> 7;
+    const bool act = p.in_scale != nullptr;
+
+    // ---- setup: B images. GEMM k = o (n_out), n = i (n_in); K-major core matrices: (n, k) -> (k/8)*1024 + (n/8)*128 + (n%8)*16 + (k%8)*2
+    for (int e = tid; e < BT_F * BT_F / 2; e += BT_THREADS) {
+        const int n = e >> 5, k = (e & 31) * 2;
+        float w0 = 0.f, w1 = 0.f;
+        if (n < p.n_in) {
+            if (k < p.n_out) w0 = p.w[(int64_t)k * p.ldw + n];
+            if (k + 1 < p.n_out) w1 = p.w[(int64_t)(k + 1) * p.ldw + n];
+        }
+        const float a0 = k < p.n_out ? p.coef[k] : 0.f, a1 = k + 1 < p.n_out ? p.coef[k + 1] : 0.f;
+        const float b0 = k < p.n_out ? p.coef[p.n_out + k] : 0.f, b1 = k + 1 < p.n_out ? p.coef[p.n_out + k + 1] : 0.f;
+        const int off = (k >> 3) * BT_W_KCORE + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
+        uint32_t h, m, l;
+        split3x2(a0 * w0, a1 * w1, h, m, l);
+        *reinterpret_cast<uint32_t*>(sm_w + off) = h;
+        *reinterpret_cast<uint32_t*>(sm_w + BT_W_PLANE + off) = m;
+        *reinterpret_cast<uint32_t*>(sm_w + 2 * BT_W_PLANE + off) = l;
+        split3x2(b0 * w0, b1 * w1, h, m, l);
+        *reinterpret_cast<uint32_t*>(sm_w + 3 * BT_W_PLANE + off) = h;
+        *reinterpret_cast<uint32_t*>(sm_w + 4 * BT_W_PLANE + off) = m;
+        *reinterpret_cast<uint32_t*>(sm_w + 5 * BT_W_PLANE + off) = l;
+    }
+    for (int i = tid; i < BT_F; i += BT_THREADS) {
+        float c = 0.f;
+        if (i < p.n_in)
+            for (int o = 0; o < p.n_out; ++o) c = fmaf(p.coef[2 * p.n_out + o], p.w[(int64_t)o * p.ldw + i], c);
+        sm_c[i] = c;
+        sm_c[BT_F + i] = (act && i < p.n_in) ? p.in_scale[i] : 1.f;
+        sm_c[2 * BT_F + i] = (act && i < p.n_in) ? p.in_shift[i] : 0.f;
+        sm_c[3 * BT_F + i] = (act && i < p.n_in) ? p.in_mean[i] : 0.f;
+        sm_c[4 * BT_F + i] = (act && i < p.n_in) ? p.in_rstd[i] : 0.f;
+    }
+    if (tid == 0) {
+        s_abort = 0;
+        for (int i = 0; i < BT_STAGES; ++i) { mbar_init(&a_full[i], BT_PROD_WARPS); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == BT_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    if (warp < BT_EPI_WARPS) {
+        // ================================ epilogue (two groups of four warps, one per accumulator slot) ============
+        float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f};
+        const uint32_t my_slot = warp >> 2;
+        const int q = warp & 3;
+        float* stg = sm_stg + warp * (32 * BT_PITCH);
+        const uint32_t stg_u32 = smem_u32(stg);
+        const bool fast_x = act && p.n_in == BT_F && (p.ldx & 3) == 0 && gnm_aligned16(p.x);
+        const bool fast_o = p.dx != nullptr && p.n_in == BT_F && (p.lddx & 3) == 0 && gnm_aligned16(p.dx);
+        // prefetch x for this group's first tile
+        if (act) {
+            const int t0 = blockIdx.x + (int)my_slot * gridDim.x;
+            if (t0 < n_tiles) stage_rows_async(p.x, p.ldx, p.n_rows, p.n_in, t0 * 128 + q * 32, stg, stg_u32, lane, fast_x);
+        }
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles && !*abort_flag; tile += gridDim.x, ++it) {
+            const uint32_t slot = it & 1, ph = (it >> 1) & 1;
+            if (slot != my_slot) continue;
+            if (!mbar_wait(&acc_full[slot], ph, abort_flag)) break;
+            tc_fence_after();
+            const int row0 = tile * 128 + q * 32;
+            const bool row_ok = row0 + lane < p.n_rows;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float v[32];
+#pragma unroll
+                for (int c0 = 0; c0 < 32; c0 += 16) {
+                    uint32_t t16[16];
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + slot * BT_D_COLS + hf * 32 + c0, t16);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[c0 + j] = __uint_as_float(t16[j]);
+                }
+                if (hf == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[slot]);
+                }
+                float xh[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int c = hf * 32 + j;
+                    const float4 cr = *reinterpret_cast<const float4*>(sm_c + c);
+                    v[j] += cr.x; v[j + 1] += cr.y; v[j + 2] += cr.z; v[j + 3] += cr.w;
+                    if (act) {
+                        const float4 xv = *reinterpret_cast<const float4*>(stg + lane * BT_PITCH + c);
+                        const float4 sc = *reinterpret_cast<const float4*>(sm_c + BT_F + c);
+                        const float4 sh = *reinterpret_cast<const float4*>(sm_c + 2 * BT_F + c);
+                        const float4 mu = *reinterpret_cast<const float4*>(sm_c + 3 * BT_F + c);
+                        const float4 rs = *reinterpret_cast<const float4*>(sm_c + 4 * BT_F + c);
+                        v[j] = (fmaf(xv.x, sc.x, sh.x) > 0.f) ? v[j] : 0.f;
+                        v[j + 1] = (fmaf(xv.y, sc.y, sh.y) > 0.f) ? v[j + 1] : 0.f;
+                        v[j + 2] = (fmaf(xv.z, sc.z, sh.z) > 0.f) ? v[j + 2] : 0.f;
+                        v[j + 3] = (fmaf(xv.w, sc.w, sh.w) > 0.f) ? v[j + 3] : 0.f;
+                        xh[j] = (xv.x - mu.x) * rs.x; xh[j + 1] = (xv.y - mu.y) * rs.y;
+                        xh[j + 2] = (xv.z - mu.z) * rs.z; xh[j + 3] = (xv.w - mu.w) * rs.w;
+                    }
+                    // the staging row is this lane's own: overwrite the consumed x values with the result
+                    *reinterpret_cast<float4*>(stg + lane * BT_PITCH + c) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+                if (act && p.stats_in != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float g = (row_ok && hf * 32 + j < p.n_in) ? v[j] : 0.f;
+                        v[j] = g;
+                        xh[j] = g * xh[j];
+                    }
+                    transpose_reduce32_b(v, lane);
+                    transpose_reduce32_b(xh, lane);
+                    st1[hf] += v[0];
+                    st2[hf] += xh[0];
+                }
+            }
+            __syncwarp();
+            if (p.dx != nullptr) {
+                if (fast_o) {
+#pragma unroll 4
+                    for (int i = 0; i < 16; ++i) {
+                        const int rr = i * 2 + (lane >> 4), c4 = lane & 15;
+                        if (row0 + rr < p.n_rows)
+                            *reinterpret_cast<float4*>(p.dx + (int64_t)(row0 + rr) * p.lddx + c4 * 4) =
+                                *reinterpret_cast<const float4*>(stg + rr * BT_PITCH + c4 * 4);
+                    }
+                } else {
+                    for (int e = lane; e < 32 * BT_F; e += 32) {
+                        const int rr = e >> 6, c = e & 63;
+                        if (row0 + rr < p.n_rows && c < p.n_in) p.dx[(int64_t)(row0 + rr) * p.lddx + c] = stg[rr * BT_PITCH + c];
+                    }
+                }
+            }
+            __syncwarp();
+            if (act) {
+                const int next_tile = tile + 2 * gridDim.x;
+                if (next_tile < n_tiles)
+                    stage_rows_async(p.x, p.ldx, p.n_rows, p.n_in, next_tile * 128 + q * 32, stg, stg_u32, lane, fast_x);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (act && p.stats_in != nullptr) {
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int c = h2 * 32 + lane;
+                if (c < p.n_in) {
+                    atomicAdd(&p.stats_in[c], (double)st1[h2]);
+                    atomicAdd(&p.stats_in[p.n_in + c], (double)st2[h2]);
+                }
+            }
+        }
+    } else if (warp == BT_MMA_WARP) {
+        // ================================ MMA issue ==============================================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BT_F >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t wa = umma_desc(smem_u32(sm_w), BT_W_KCORE, 128);
+            const uint64_t pl = (uint64_t)(BT_W_PLANE >> 4);
+            const int ksteps = (p.n_out + 15) >> 4;
+            uint32_t it = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
+                const uint32_t s = it % BT_STAGES, aph = (it / BT_STAGES) & 1;
+                const uint32_t slot = it & 1, ph = (it >> 1) & 1;
+                if (!(ok = mbar_wait(&acc_empty[slot], ph ^ 1, abort_flag))) break;
+                if (!(ok = mbar_wait(&a_full[s], aph, abort_flag))) break;
+                tc_fence_after();
+                const uint32_t d = tmem + slot * BT_D_COLS;
+                const uint32_t a0 = tmem + BT_A_TMEM0 + s * BT_A_COLS;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint64_t kofs = (uint64_t)(ks * 2 * BT_W_KCORE >> 4);
+#pragma unroll
+                    for (int op = 0; op < 2; ++op) {             // op 0: dy x (cA W), op 1: z x (cB W)
+                        const uint32_t ah = a0 + op * 96 + ks * 8, am = ah + 32, al = ah + 64;
+                        const uint64_t wh = wa + (uint64_t)op * 3 * pl + kofs, wm = wh + pl, wl = wh + 2 * pl;
+                        umma_ts(d, ah, wh, idesc, (ks | op) ? 1u : 0u);
+                        umma_ts(d, ah, wm, idesc, 1u);
+                        umma_ts(d, am, wh, idesc, 1u);
+                        umma_ts(d, ah, wl, idesc, 1u);
+                        umma_ts(d, al, wh, idesc, 1u);
+                        umma_ts(d, am, wm, idesc, 1u);
+                    }
+                }
+                umma_commit(&a_empty[s]);
+                umma_commit(&acc_full[slot]);
+            }
+        }
+    } else {
+        // ================================ producers: warps 8-11 stream dy, warps 12-15 stream z, every tile =========
+        const int grp = (warp - BT_EPI_WARPS) >> 2;
+        const int q = warp & 3;
+        float* stg = sm_stg + warp * (32 * BT_PITCH);
+        const uint32_t stg_u32 = smem_u32(stg);
+        const float* src = grp == 0 ? p.dy : p.z;
+        const int64_t ld = grp == 0 ? p.lddy : p.ldz;
+        const bool fast = p.n_out == BT_F && (ld & 3) == 0 && gnm_aligned16(src);
+        if ((int)blockIdx.x < n_tiles) stage_rows_async(src, ld, p.n_rows, p.n_out, blockIdx.x * 128 + q * 32, stg, stg_u32, lane, fast);
+        uint32_t it = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
+            const uint32_t s = it % BT_STAGES, aph = (it / BT_STAGES) & 1;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + BT_A_TMEM0 + s * BT_A_COLS + grp * 96;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            bool waited = false;
+#pragma unroll
+            for (int k0 = 0; k0 < BT_F; k0 += 32) {
+                uint32_t hi[16], mid[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(stg + lane * BT_PITCH + k0 + j);
+                    split3x2(t.x, t.y, hi[j >> 1], mid[j >> 1], lo[j >> 1]);
+                    split3x2(t.z, t.w, hi[(j >> 1) + 1], mid[(j >> 1) + 1], lo[(j >> 1) + 1]);
+                }
+                if (k0 == 32) {
+                    __syncwarp();
+                    const int next_tile = tile + gridDim.x;
+                    if (next_tile < n_tiles)
+                        stage_rows_async(src, ld, p.n_rows, p.n_out, next_tile * 128 + q * 32, stg, stg_u32, lane, fast);
+                }
+                if (!waited) {
+                    if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag))) break;
+                    waited = true;
+                }
+                tmem_st16(taddr + (k0 >> 1), hi);
+                tmem_st16(taddr + 32 + (k0 >> 1), mid);
+                tmem_st16(taddr + 64 + (k0 >> 1), lo);
+            }
+            if (!ok) break;
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[s]);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == BT_MMA_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight-gradient half: dW[o,i] = sum_m dz[m,o] a[m,i], db[o] = sum_m dz[m,o] with dz = cA*dy + cB*z + cC, i.e.
+//   dW = diag(cA) (dy^T a) + diag(cB) (z^T a) + cC (x) colsum(a),   db = cA*colsum(dy) + cB*colsum(z) + cC*n_rows
+// One "TN" GEMM with the rows as the reduction axis: A operand = [dy | z]^T (M = 128: dy channels then z channels),
+// B operand = a (N = 64), both MN-major in shared memory as three exact bf16 planes, 64 rows per stage. The B
+// planes sit side by side (hi | mid | lo, N = 192) so the six kept products take three MMAs per 16-row k-step:
+// A_hi x [hi|mid|lo], A_mid x [hi|mid], A_lo x [hi]; the three 64-column groups of the accumulator are summed in
+// the epilogue. Column sums are accumulated by the producers on the way.
+constexpr int WG_ROWS = 64;                          // rows (reduction length) per stage
+constexpr int WG_STAGES = 3;
+constexpr int WG_KCORES = WG_ROWS / 8;
+constexpr int WG_CORE_STRIDE = WG_KCORES * 128 + 16; // stride between 8-wide m / n cores (padded: conflict-free fill)
+constexpr int WG_A_PLANE = 16 * WG_CORE_STRIDE;      // 128 m = 16 cores
+constexpr int WG_B_BYTES = 24 * WG_CORE_STRIDE;      // 192 n = 24 cores (three planes side by side)
+constexpr int WG_STAGE_BYTES = 3 * WG_A_PLANE + WG_B_BYTES;
+constexpr int WG_PROD_WARPS = 8;
+constexpr int WG_THREADS = (WG_PROD_WARPS + 1) * 32;
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024;
+
+struct WgradTcParams {
+    const float* dy; int64_t lddy;
+    const float* z; int64_t ldz;
+    const float* coef;
+    const float* x; int64_t ldx;
+    const float* in_scale; const float* in_shift;
+    float* dw; int64_t lddw; float* db;
+    int n_rows, n_out, n_in;
+};
+
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) linear_wgrad_tc_kernel(const WgradTcParams p) {
+    extern __shared__ __align__(1024) unsigned char wg_smem[];
+    __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 1];
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_abort;
+    __shared__ float s_sum[3 * BT_F];                  // column sums: dy | z | a
+    uint64_t* full = bars;
+    uint64_t* empty = bars + WG_STAGES;
+    uint64_t* done = bars + 2 * WG_STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    volatile int* abort_flag = &s_abort;
+    const int n_chunks = (p.n_rows + WG_ROWS - 1) / WG_ROWS;
+    const bool act = p.in_scale != nullptr;
+
+    if (tid < 3 * BT_F) s_sum[tid] = 0.f;
+    if (tid == 0) {
+        s_abort = 0;
+        for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], WG_PROD_WARPS); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == WG_PROD_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    if (warp < WG_PROD_WARPS) {
+        // ================================ producers ============================================================
+        // thread -> (row k = e >> 4, float4 column c4 = e & 15) for e = tid + 256 j; c4 is fixed per thread
+        const int c4 = tid & 15, kr0 = tid >> 4;          // rows kr0, kr0+16, kr0+32, kr0+48 of the stage
+        const bool fast = p.n_out == BT_F && p.n_in == BT_F && ((p.lddy | p.ldz | p.ldx) & 3) == 0 &&
+                          gnm_aligned16(p.dy) && gnm_aligned16(p.z) && gnm_aligned16(p.x);
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) {
+            const int c = c4 * 4;
+            if (c < p.n_in) { sc.x = p.in_scale[c]; sh.x = p.in_shift[c]; }
+            if (c + 1 < p.n_in) { sc.y = p.in_scale[c + 1]; sh.y = p.in_shift[c + 1]; }
+            if (c + 2 < p.n_in) { sc.z = p.in_scale[c + 2]; sh.z = p.in_shift[c + 2]; }
+            if (c + 3 < p.n_in) { sc.w = p.in_scale[c + 3]; sh.w = p.in_shift[c + 3]; }
+        }
+        float4 s_dy = make_float4(0.f, 0.f, 0.f, 0.f), s_z = s_dy, s_a = s_dy;
+        float4 r_dy[4], r_z[4], r_x[4];
+        auto load_chunk = [&](int chunk) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = chunk * WG_ROWS + kr0 + 16 * j;
+                const bool okr = r < p.n_rows;
+                if (fast) {
+                    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                    r_dy[j] = okr ? __ldg(reinterpret_cast<const float4*>(p.dy + (int64_t)r * p.lddy) + c4) : zero;
+                    r_z[j] = okr ? __ldg(reinterpret_cast<const float4*>(p.z + (int64_t)r * p.ldz) + c4) : zero;
+                    r_x[j] = okr ? __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)r * p.ldx) + c4) : zero;
+                } else {
+                    float t[12];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = c4 * 4 + u;
+                        t[u] = (okr && c < p.n_out) ? p.dy[(int64_t)r * p.lddy + c] : 0.f;
+                        t[4 + u] = (okr && c < p.n_out) ? p.z[(int64_t)r * p.ldz + c] : 0.f;
+                        t[8 + u] = (okr && c < p.n_in) ? p.x[(int64_t)r * p.ldx + c] : 0.f;
+                    }
+                    r_dy[j] = make_float4(t[0], t[1], t[2], t[3]);
+                    r_z[j] = make_float4(t[4], t[5], t[6], t[7]);
+                    r_x[j] = make_float4(t[8], t[9], t[10], t[11]);
+                }
+            }
+        };
+        if ((int)blockIdx.x < n_chunks) load_chunk(blockIdx.x);
+        uint32_t it = 0;
+        bool ok = true;
+        for (int chunk = blockIdx.x; chunk < n_chunks && ok; chunk += gridDim.x, ++it) {
+            const uint32_t s = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
+            unsigned char* st = wg_smem + (size_t)s * WG_STAGE_BYTES;
+            if (!(ok = mbar_wait(&empty[s], ph ^ 1, abort_flag))) break;
+            float4 c_dy[4], c_z[4], c_a[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                c_dy[j] = r_dy[j];
+                c_z[j] = r_z[j];
+                float4 a = r_x[j];
+                if (act) {
+                    const bool okr = chunk * WG_ROWS + kr0 + 16 * j < p.n_rows;
+                    a.x = okr ? fmaxf(fmaf(a.x, sc.x, sh.x), 0.f) : 0.f;
+                    a.y = okr ? fmaxf(fmaf(a.y, sc.y, sh.y), 0.f) : 0.f;
+                    a.z = okr ? fmaxf(fmaf(a.z, sc.z, sh.z), 0.f) : 0.f;
+                    a.w = okr ? fmaxf(fmaf(a.w, sc.w, sh.w), 0.f) : 0.f;
+                }
+                c_a[j] = a;
+            }
+            if (chunk + (int)gridDim.x < n_chunks) load_chunk(chunk + gridDim.x);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = kr0 + 16 * j;
+                const int off = (c4 >> 1) * WG_CORE_STRIDE + (k >> 3) * 128 + (k & 7) * 16 + (c4 & 1) * 8;
+                uint32_t h0, m0, l0, h1, m1, l1;
+                split3x2(c_dy[j].x, c_dy[j].y, h0, m0, l0);
+                split3x2(c_dy[j].z, c_dy[j].w, h1, m1, l1);
+                *reinterpret_cast<uint2*>(st + off) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(st + WG_A_PLANE + off) = make_uint2(m0, m1);
+                *reinterpret_cast<uint2*>(st + 2 * WG_A_PLANE + off) = make_uint2(l0, l1);
+                split3x2(c_z[j].x, c_z[j].y, h0, m0, l0);
+                split3x2(c_z[j].z, c_z[j].w, h1, m1, l1);
+                const int offz = off + 8 * WG_CORE_STRIDE;                 // z channels: m = 64 + c
+                *reinterpret_cast<uint2*>(st + offz) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(st + WG_A_PLANE + offz) = make_uint2(m0, m1);
+                *reinterpret_cast<uint2*>(st + 2 * WG_A_PLANE + offz) = make_uint2(l0, l1);
+                split3x2(c_a[j].x, c_a[j].y, h0, m0, l0);
+                split3x2(c_a[j].z, c_a[j].w, h1, m1, l1);
+                unsigned char* sb = st + 3 * WG_A_PLANE + off;
+                *reinterpret_cast<uint2*>(sb) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(sb + 8 * WG_CORE_STRIDE) = make_uint2(m0, m1);
+                *reinterpret_cast<uint2*>(sb + 16 * WG_CORE_STRIDE) = make_uint2(l0, l1);
+                s_dy.x += c_dy[j].x; s_dy.y += c_dy[j].y; s_dy.z += c_dy[j].z; s_dy.w += c_dy[j].w;
+                s_z.x += c_z[j].x; s_z.y += c_z[j].y; s_z.z += c_z[j].z; s_z.w += c_z[j].w;
+                s_a.x += c_a[j].x; s_a.y += c_a[j].y; s_a.z += c_a[j].z; s_a.w += c_a[j].w;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+        }
+        // column sums: lanes l and l^16 share c4 -> fold, then one shared atomic per column and warp
+        float v[12] = {s_dy.x, s_dy.y, s_dy.z, s_dy.w, s_z.x, s_z.y, s_z.z, s_z.w, s_a.x, s_a.y, s_a.z, s_a.w};
+#pragma unroll
+        for (int u = 0; u < 12; ++u) v[u] += __shfl_xor_sync(GNM_FULL_MASK, v[u], 16);
+        if (lane < 16) {
+#pragma unroll
+            for (int u = 0; u < 12; ++u) atomicAdd(&s_sum[(u >> 2) * BT_F + c4 * 4 + (u & 3)], v[u]);
+        }
+    } else if (lane == 0) {
+        // ================================ MMA issue ==============================================================
+        const uint32_t id_base = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t id192 = id_base | ((uint32_t)(192 >> 3) << 17), id128 = id_base | ((uint32_t)(128 >> 3) << 17),
+                       id64 = id_base | ((uint32_t)(64 >> 3) << 17);
+        uint32_t it = 0;
+        bool ok = true;
+        for (int chunk = blockIdx.x; chunk < n_chunks && ok; chunk += gridDim.x, ++it) {
+            const uint32_t s = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
+            if (!(ok = mbar_wait(&full[s], ph, abort_flag))) break;
+            tc_fence_after();
+            const uint32_t base = smem_u32(wg_smem + (size_t)s * WG_STAGE_BYTES);
+            const uint64_t ah = umma_desc(base, 128, WG_CORE_STRIDE);
+            const uint64_t am = umma_desc(base + WG_A_PLANE, 128, WG_CORE_STRIDE);
+            const uint64_t al = umma_desc(base + 2 * WG_A_PLANE, 128, WG_CORE_STRIDE);
+            const uint64_t b = umma_desc(base + 3 * WG_A_PLANE, 128, WG_CORE_STRIDE);
+#pragma unroll
+            for (int ks = 0; ks < WG_ROWS / 16; ++ks) {
+                const uint64_t ko = (uint64_t)(ks * 256 >> 4);
+                umma_ss(tmem, ah + ko, b + ko, id192, (it | ks) ? 1u : 0u);
+                umma_ss(tmem, am + ko, b + ko, id128, 1u);
+                umma_ss(tmem, al + ko, b + ko, id64, 1u);
+            }
+            umma_commit(&empty[s]);
+        }
+        if (ok) umma_commit(done);
+    }
+    // ================================ epilogue (once per CTA) ====================================================
+    __syncwarp();
+    bool fin = mbar_wait(done, 0, abort_flag);
+    tc_fence_after();
+    __syncthreads();
+    float* tile = reinterpret_cast<float*>(wg_smem);                     // [128][65] floats, stage memory is free now
+    if (fin && warp < 4 && (int)blockIdx.x < n_chunks) {
+        const int m = warp * 32 + lane;
+        const int o = m & 63;
+        const float scale = o < p.n_out ? p.coef[(m >> 6) * p.n_out + o] : 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t g0[16], g1[16], g2[16];
+            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+            tmem_ld16(ta, g0);
+            tmem_ld16(ta + 64, g1);
+            tmem_ld16(ta + 128, g2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                tile[m * 65 + c0 + j] = scale * (__uint_as_float(g0[j]) + __uint_as_float(g1[j]) + __uint_as_float(g2[j]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (fin && (int)blockIdx.x < n_chunks) {
+        int my_rows = 0;
+        for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) my_rows += min(WG_ROWS, p.n_rows - chunk * WG_ROWS);
+        for (int e = tid; e < p.n_out * p.n_in; e += WG_THREADS) {
+            const int o = e / p.n_in, i = e - o * p.n_in;
+            const float v = tile[o * 65 + i] + tile[(64 + o) * 65 + i] + p.coef[2 * p.n_out + o] * s_sum[2 * BT_F + i];
+            atomicAdd(&p.dw[(int64_t)o * p.lddw + i], v);
+        }
+        if (p.db != nullptr) {
+            for (int o = tid; o < p.n_out; o += WG_THREADS)
+                atomicAdd(&p.db[o], p.coef[o] * s_sum[o] + p.coef[p.n_out + o] * s_sum[BT_F + o] +
+                                        p.coef[2 * p.n_out + o] * (float)my_rows);
+        }
+    }
+    if (warp == WG_PROD_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+    }
+}
+
+}  // namespace
+
+int gnm_launch_linear_bwd_dx_tc(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* coef,
+                                const float* x, int64_t ldx, const float* in_scale, const float* in_shift,
+                                const float* in_mean, const float* in_rstd, const float* w, int64_t ldw, float* dx,
+                                int64_t lddx, double* stats_in, int n_rows, int n_out, int n_in, cudaStream_t stream) {
+    if (n_in > BT_F || n_out > BT_F || n_in < 1 || n_out < 1) return GNM_ERR_TOO_LARGE;
+    int dev = 0, sms = 148, major = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) return GNM_ERR_TOO_LARGE;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    LinBwdTcParams p;
+    p.dy = dy; p.lddy = lddy; p.z = z; p.ldz = ldz; p.coef = coef; p.w = w; p.ldw = ldw; p.x = x; p.ldx = ldx;
+    p.in_scale = in_scale; p.in_shift = in_shift; p.in_mean = in_mean; p.in_rstd = in_rstd; p.dx = dx; p.lddx = lddx;
+    p.stats_in = stats_in; p.n_rows = n_rows; p.n_out = n_out; p.n_in = n_in;
+    cudaError_t e = cudaFuncSetAttribute(linear_bwd_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    const int tiles = (n_rows + 127) / 128;
+    const int grid = tiles < sms ? tiles : sms;
+    linear_bwd_dx_tc_kernel<<<grid, BT_THREADS, BT_SMEM, stream>>>(p);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? GNM_OK : (int)e;
+}
+
+int gnm_linear_bwd_tc_abort_flag(int* aborted) {
+    int v = 0, zero = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&v, g_tc_abort, sizeof(int));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(g_tc_abort, &zero, sizeof(int));
+    if (aborted) *aborted |= v;
+    return e == cudaSuccess ? GNM_OK : (int)e;
+}
+
+int gnm_launch_linear_wgrad_tc(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* coef,
+                               const float* x, int64_t ldx, const float* in_scale, const float* in_shift, float* dw,
+                               int64_t lddw, float* dbias, int n_rows, int n_out, int n_in, cudaStream_t stream) {
+    if (n_in > BT_F || n_out > BT_F || n_in < 1 || n_out < 1) return GNM_ERR_TOO_LARGE;
+    int dev = 0, sms = 148, major = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) return GNM_ERR_TOO_LARGE;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    WgradTcParams p;
+    p.dy = dy; p.lddy = lddy; p.z = z; p.ldz = ldz; p.coef = coef; p.x = x; p.ldx = ldx; p.in_scale = in_scale;
+    p.in_shift = in_shift; p.dw = dw; p.lddw = lddw; p.db = dbias; p.n_rows = n_rows; p.n_out = n_out; p.n_in = n_in;
+    cudaError_t e = cudaFuncSetAttribute(linear_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    const int chunks = (n_rows + WG_ROWS - 1) / WG_ROWS;
+    const int grid = chunks < sms ? chunks : sms;
+    linear_wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM, stream>>>(p);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? GNM_OK : (int)e;
+}

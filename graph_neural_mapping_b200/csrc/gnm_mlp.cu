@@ -502,6 +502,8 @@ int gnm_launch_linear_tc(const float* x, int64_t ldx, int n_rows, int n_in, cons
                          int n_out, double* col_stats, cudaStream_t stream);
 static int g_linear_impl = 0;     // 0 auto, 1 FFMA kernel, 2 tcgen05 kernel only (A/B switch, see gnm_set_linear_impl)
 
+int gnm_linear_impl_value() { return g_linear_impl; }
+
 extern "C" int gnm_set_linear_impl(int impl) {
     if (impl < 0 || impl > 2) return GNM_ERR_BAD_ARG;
     g_linear_impl = impl;

@@ -481,6 +481,66 @@ def test_linear_bwd_fused(m, fo, fi, act, train):
     assert_close(dw2, dwr2, TOL, "dw (no dx)")
 
 
+@pytest.mark.parametrize("m,fo,fi", [(1, 1, 1), (300, 8, 12), (4097, 64, 64), (40000, 64, 64), (20001, 48, 64), (9000, 64, 33),
+                                     (129, 63, 37), (64 * 148 * 3 + 5, 64, 64)])
+@pytest.mark.parametrize("act,train", [(True, True), (False, True), (True, False)])
+def test_linear_bwd_tcgen05(m, fo, fi, act, train):
+    """Tensor-core backward unit (input-gradient kernel + weight-gradient kernel, bf16x3 exact splits) against the
+    fp64 stand-in at the FFMA kernel's tolerance, and against the FFMA kernel itself."""
+    torch.manual_seed(m + fo + fi)
+    dy, z = torch.randn(m, fo, device=DEV), torch.randn(m, fo, device=DEV) * 2 + 0.5
+    x = torch.randn(m, fi, device=DEV)
+    w = torch.randn(fo, fi, device=DEV) * 0.3
+    gamma, mean, rstd = torch.rand(fo, device=DEV) + 0.5, torch.randn(fo, device=DEV), torch.rand(fo, device=DEV) + 0.5
+    stats = torch.randn(2 * fo, dtype=torch.float64, device=DEV) * m if train else None
+    coef = torch.empty(3, fo, device=DEV)
+    ops.bn_bwd_coeffs(stats, float(m), gamma, mean, rstd, coef)
+    isc = torch.rand(fi, device=DEV) + 0.5 if act else None
+    ish = torch.randn(fi, device=DEV) if act else None
+    imu = torch.randn(fi, device=DEV) if act else None
+    irs = torch.rand(fi, device=DEV) + 0.5 if act else None
+    outs = []
+    try:
+        for impl in (2, 1):
+            ops.set_linear_impl(impl)
+            dw, db = torch.zeros(fo, fi, device=DEV), torch.zeros(fo, device=DEV)
+            dx = torch.full((m, fi), float("nan"), device=DEV)
+            st = torch.zeros(2 * fi, dtype=torch.float64, device=DEV) if act else None
+            ops.linear_bwd(dy, z, coef, x, isc, ish, imu, irs, w, dw, db, dx, st)
+            dw2, db2 = torch.zeros(fo, fi, device=DEV), torch.zeros(fo, device=DEV)
+            ops.linear_bwd(dy, z, coef, x, None, None, None, None, w, dw2, db2, None, None)
+            outs.append((dw, db, dx, st, dw2, db2))
+    finally:
+        ops.set_linear_impl(0)
+    assert not ops.aggregate_tc_status(), "tcgen05 kernel hit a barrier timeout"
+    c = lambda t: t.cpu() if t is not None else None
+    dwr, dbr, dxr = torch.zeros(fo, fi), torch.zeros(fo), torch.empty(m, fi)
+    str_ = torch.zeros(2 * fi, dtype=torch.float64) if act else None
+    emul_ops.linear_bwd(c(dy), c(z), c(coef), c(x), c(isc), c(ish), c(imu), c(irs), c(w), dwr, dbr, dxr, str_)
+    dwr2, dbr2 = torch.zeros(fo, fi), torch.zeros(fo)
+    emul_ops.linear_bwd(c(dy), c(z), c(coef), c(x), None, None, None, None, c(w), dwr2, dbr2, None, None)
+    tc, ff = outs
+    if act:
+        # the ReLU mask is discontinuous: entries whose pre-activation is within rounding of zero may legitimately
+        # flip between the fp32 fmaf and the fp64 stand-in; they are compared against the FFMA kernel only
+        edge = (x.double() * isc.double() + ish.double()).abs() < 1e-5
+        assert int(edge.sum()) < 1e-4 * edge.numel() + 16
+        tc[2][edge] = 0.0
+        dxr[edge.cpu()] = 0.0
+        ff[2][edge] = 0.0
+    assert_close(tc[2], dxr, TOL, "dx vs fp64")
+    assert_close(tc[0], dwr, TOL, "dw vs fp64")
+    assert_close(tc[1], dbr, TOL, "db vs fp64")
+    assert_close(tc[4], dwr2, TOL, "dw (no dx, plain input) vs fp64")
+    assert_close(tc[5], dbr2, TOL, "db (no dx) vs fp64")
+    assert_close(tc[2], ff[2], TOL, "dx vs FFMA")
+    assert_close(tc[0], ff[0], TOL, "dw vs FFMA")
+    if act:
+        assert_close(tc[3], ff[3], 2e-5, "stats_in vs FFMA")
+        if not bool(edge.any()):
+            assert_close(tc[3], str_, 2e-5, "stats_in vs fp64")
+
+
 @pytest.mark.parametrize("m,k,n", [(1, 1, 1), (37, 10, 8), (300, 64, 64), (5000, 64, 64), (129, 12, 12), (20000, 48, 64),
                                    (4097, 64, 33), (40000, 64, 64)])
 @pytest.mark.parametrize("kn,pro,stats", [(False, False, True), (False, True, True), (True, False, False), (True, True, True)])
