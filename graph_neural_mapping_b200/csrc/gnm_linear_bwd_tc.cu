@@ -60,14 +60,27 @@ __device__ __forceinline__ void transpose_reduce32_b(float (&v)[32], int lane) {
 __device__ __forceinline__ void stage_rows_async(const float* base, int64_t ld, int n_rows, int n_cols, int row0, float* stg,
                                                  uint32_t stg_u32, int lane, bool fast) {
     if (fast) {
+        // lane -> (row pair member lane >> 4, float4 column lane & 15); rows advance by two per copy
+        const int nvalid = n_rows - row0 - (lane >> 4);          // copy i is in range iff 2 i < nvalid
+        const char* src = reinterpret_cast<const char*>(base + (int64_t)(row0 + (lane >> 4)) * ld + (lane & 15) * 4);
+        const int64_t step = 2 * ld * (int64_t)sizeof(float);
+        uint32_t dst = stg_u32 + (uint32_t)(((lane >> 4) * BT_PITCH + (lane & 15) * 4) * 4);
+        if (nvalid >= 31) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                src += step;
+                dst += 2 * BT_PITCH * 4;
+            }
+        } else {
 #pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-            const int rr = i * 2 + (lane >> 4), c4 = lane & 15;
-            const bool okr = row0 + rr < n_rows;
-            const float* src = base + (int64_t)(okr ? row0 + rr : 0) * ld + c4 * 4;
-            const uint32_t dst = stg_u32 + (uint32_t)((rr * BT_PITCH + c4 * 4) * 4);
-            const int nbytes = okr ? 16 : 0;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+            for (int i = 0; i < 16; ++i) {
+                const bool okr = 2 * i < nvalid;
+                const int nbytes = okr ? 16 : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(okr ? src : (const char*)base), "r"(nbytes) : "memory");
+                src += step;
+                dst += 2 * BT_PITCH * 4;
+            }
         }
     } else {
         for (int e = lane; e < 32 * BT_F; e += 32) {
@@ -160,7 +173,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
         for (int tile = blockIdx.x; tile < n_tiles && !*abort_flag; tile += gridDim.x, ++it) {
             const uint32_t slot = it & 1, ph = (it >> 1) & 1;
             if (slot != my_slot) continue;
-            if (!mbar_wait(&acc_full[slot], ph, abort_flag)) break;
+            if (!mbar_wait<32>(&acc_full[slot], ph, abort_flag)) break;
             tc_fence_after();
             const int row0 = tile * 128 + q * 32;
             const bool row_ok = row0 + lane < p.n_rows;
@@ -220,12 +233,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
             __syncwarp();
             if (p.dx != nullptr) {
                 if (fast_o) {
-#pragma unroll 4
+                    const int nvalid = p.n_rows - row0 - (lane >> 4);
+                    char* dstp = reinterpret_cast<char*>(p.dx + (int64_t)(row0 + (lane >> 4)) * p.lddx + (lane & 15) * 4);
+                    const int64_t step = 2 * p.lddx * (int64_t)sizeof(float);
+                    const float* sp = stg + (lane >> 4) * BT_PITCH + (lane & 15) * 4;
+#pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int rr = i * 2 + (lane >> 4), c4 = lane & 15;
-                        if (row0 + rr < p.n_rows)
-                            *reinterpret_cast<float4*>(p.dx + (int64_t)(row0 + rr) * p.lddx + c4 * 4) =
-                                *reinterpret_cast<const float4*>(stg + rr * BT_PITCH + c4 * 4);
+                        if (2 * i < nvalid) *reinterpret_cast<float4*>(dstp) = *reinterpret_cast<const float4*>(sp);
+                        dstp += step;
+                        sp += 2 * BT_PITCH;
                     }
                 } else {
                     for (int e = lane; e < 32 * BT_F; e += 32) {
@@ -321,7 +337,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
                         stage_rows_async(src, ld, p.n_rows, p.n_out, next_tile * 128 + q * 32, stg, stg_u32, lane, fast);
                 }
                 if (!waited) {
-                    if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag))) break;
+                    if (!(ok = mbar_wait<32>(&a_empty[s], aph ^ 1, abort_flag))) break;
                     waited = true;
                 }
                 tmem_st16(taddr + (k0 >> 1), hi);
@@ -425,84 +441,106 @@ __global__ void __launch_bounds__(WG_THREADS, 1) linear_wgrad_tc_kernel(const Wg
             if (c + 3 < p.n_in) { sc.w = p.in_scale[c + 3]; sh.w = p.in_shift[c + 3]; }
         }
         float4 s_dy = make_float4(0.f, 0.f, 0.f, 0.f), s_z = s_dy, s_a = s_dy;
-        float4 r_dy[4], r_z[4], r_x[4];
-        auto load_chunk = [&](int chunk) {
+        struct RowRegs { float4 dy[4], z[4], x[4]; };
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        // register prefetch, one chunk ahead. Deeper register rings (DEPTH 2, 3) were measured to gain nothing: the
+        // loads of all in-flight chunks share the warp's few scoreboards, so waiting for the oldest chunk drains them all.
+        auto load_chunk = [&](RowRegs& r, int chunk) {
+            const int r0 = chunk * WG_ROWS + kr0;
+            if (fast && r0 + 48 < p.n_rows) {
+                const float4* pdy = reinterpret_cast<const float4*>(p.dy + (int64_t)r0 * p.lddy) + c4;
+                const float4* pz = reinterpret_cast<const float4*>(p.z + (int64_t)r0 * p.ldz) + c4;
+                const float4* px = reinterpret_cast<const float4*>(p.x + (int64_t)r0 * p.ldx) + c4;
+                const int64_t sdy = 4 * p.lddy, sz = 4 * p.ldz, sx = 4 * p.ldx;     // 16 rows, in float4 units
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = chunk * WG_ROWS + kr0 + 16 * j;
-                const bool okr = r < p.n_rows;
-                if (fast) {
-                    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-                    r_dy[j] = okr ? __ldg(reinterpret_cast<const float4*>(p.dy + (int64_t)r * p.lddy) + c4) : zero;
-                    r_z[j] = okr ? __ldg(reinterpret_cast<const float4*>(p.z + (int64_t)r * p.ldz) + c4) : zero;
-                    r_x[j] = okr ? __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)r * p.ldx) + c4) : zero;
-                } else {
+                for (int j = 0; j < 4; ++j) {
+                    r.dy[j] = __ldg(pdy); pdy += sdy;
+                    r.z[j] = __ldg(pz); pz += sz;
+                    r.x[j] = __ldg(px); px += sx;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = r0 + 16 * j;
+                    const bool okr = rr < p.n_rows;
                     float t[12];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int c = c4 * 4 + u;
-                        t[u] = (okr && c < p.n_out) ? p.dy[(int64_t)r * p.lddy + c] : 0.f;
-                        t[4 + u] = (okr && c < p.n_out) ? p.z[(int64_t)r * p.ldz + c] : 0.f;
-                        t[8 + u] = (okr && c < p.n_in) ? p.x[(int64_t)r * p.ldx + c] : 0.f;
+                        t[u] = (okr && c < p.n_out) ? p.dy[(int64_t)rr * p.lddy + c] : 0.f;
+                        t[4 + u] = (okr && c < p.n_out) ? p.z[(int64_t)rr * p.ldz + c] : 0.f;
+                        t[8 + u] = (okr && c < p.n_in) ? p.x[(int64_t)rr * p.ldx + c] : 0.f;
                     }
-                    r_dy[j] = make_float4(t[0], t[1], t[2], t[3]);
-                    r_z[j] = make_float4(t[4], t[5], t[6], t[7]);
-                    r_x[j] = make_float4(t[8], t[9], t[10], t[11]);
+                    r.dy[j] = make_float4(t[0], t[1], t[2], t[3]);
+                    r.z[j] = make_float4(t[4], t[5], t[6], t[7]);
+                    r.x[j] = make_float4(t[8], t[9], t[10], t[11]);
                 }
             }
         };
-        if ((int)blockIdx.x < n_chunks) load_chunk(blockIdx.x);
-        uint32_t it = 0;
-        bool ok = true;
-        for (int chunk = blockIdx.x; chunk < n_chunks && ok; chunk += gridDim.x, ++it) {
-            const uint32_t s = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
-            unsigned char* st = wg_smem + (size_t)s * WG_STAGE_BYTES;
-            if (!(ok = mbar_wait(&empty[s], ph ^ 1, abort_flag))) break;
-            float4 c_dy[4], c_z[4], c_a[4];
+        auto convert_chunk = [&](const RowRegs& r, int chunk, unsigned char* st) {
+            const int nvalid = p.n_rows - chunk * WG_ROWS - kr0;              // row j of this thread is valid iff 16 j < nvalid
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                c_dy[j] = r_dy[j];
-                c_z[j] = r_z[j];
-                float4 a = r_x[j];
+                const float4 vdy = r.dy[j], vz = r.z[j];
+                float4 a = r.x[j];
                 if (act) {
-                    const bool okr = chunk * WG_ROWS + kr0 + 16 * j < p.n_rows;
+                    const bool okr = 16 * j < nvalid;
                     a.x = okr ? fmaxf(fmaf(a.x, sc.x, sh.x), 0.f) : 0.f;
                     a.y = okr ? fmaxf(fmaf(a.y, sc.y, sh.y), 0.f) : 0.f;
                     a.z = okr ? fmaxf(fmaf(a.z, sc.z, sh.z), 0.f) : 0.f;
                     a.w = okr ? fmaxf(fmaf(a.w, sc.w, sh.w), 0.f) : 0.f;
                 }
-                c_a[j] = a;
-            }
-            if (chunk + (int)gridDim.x < n_chunks) load_chunk(chunk + gridDim.x);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
                 const int k = kr0 + 16 * j;
                 const int off = (c4 >> 1) * WG_CORE_STRIDE + (k >> 3) * 128 + (k & 7) * 16 + (c4 & 1) * 8;
                 uint32_t h0, m0, l0, h1, m1, l1;
-                split3x2(c_dy[j].x, c_dy[j].y, h0, m0, l0);
-                split3x2(c_dy[j].z, c_dy[j].w, h1, m1, l1);
+                split3x2(vdy.x, vdy.y, h0, m0, l0);
+                split3x2(vdy.z, vdy.w, h1, m1, l1);
                 *reinterpret_cast<uint2*>(st + off) = make_uint2(h0, h1);
                 *reinterpret_cast<uint2*>(st + WG_A_PLANE + off) = make_uint2(m0, m1);
                 *reinterpret_cast<uint2*>(st + 2 * WG_A_PLANE + off) = make_uint2(l0, l1);
-                split3x2(c_z[j].x, c_z[j].y, h0, m0, l0);
-                split3x2(c_z[j].z, c_z[j].w, h1, m1, l1);
+                split3x2(vz.x, vz.y, h0, m0, l0);
+                split3x2(vz.z, vz.w, h1, m1, l1);
                 const int offz = off + 8 * WG_CORE_STRIDE;                 // z channels: m = 64 + c
                 *reinterpret_cast<uint2*>(st + offz) = make_uint2(h0, h1);
                 *reinterpret_cast<uint2*>(st + WG_A_PLANE + offz) = make_uint2(m0, m1);
                 *reinterpret_cast<uint2*>(st + 2 * WG_A_PLANE + offz) = make_uint2(l0, l1);
-                split3x2(c_a[j].x, c_a[j].y, h0, m0, l0);
-                split3x2(c_a[j].z, c_a[j].w, h1, m1, l1);
+                split3x2(a.x, a.y, h0, m0, l0);
+                split3x2(a.z, a.w, h1, m1, l1);
                 unsigned char* sb = st + 3 * WG_A_PLANE + off;
                 *reinterpret_cast<uint2*>(sb) = make_uint2(h0, h1);
                 *reinterpret_cast<uint2*>(sb + 8 * WG_CORE_STRIDE) = make_uint2(m0, m1);
                 *reinterpret_cast<uint2*>(sb + 16 * WG_CORE_STRIDE) = make_uint2(l0, l1);
-                s_dy.x += c_dy[j].x; s_dy.y += c_dy[j].y; s_dy.z += c_dy[j].z; s_dy.w += c_dy[j].w;
-                s_z.x += c_z[j].x; s_z.y += c_z[j].y; s_z.z += c_z[j].z; s_z.w += c_z[j].w;
-                s_a.x += c_a[j].x; s_a.y += c_a[j].y; s_a.z += c_a[j].z; s_a.w += c_a[j].w;
+                s_dy.x += vdy.x; s_dy.y += vdy.y; s_dy.z += vdy.z; s_dy.w += vdy.w;
+                s_z.x += vz.x; s_z.y += vz.y; s_z.z += vz.z; s_z.w += vz.w;
+                s_a.x += a.x; s_a.y += a.y; s_a.z += a.z; s_a.w += a.w;
             }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
+        };
+        constexpr int DEPTH = 1;
+        RowRegs rr[DEPTH];
+        const int G = gridDim.x;
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rr[d].dy[j] = rr[d].z[j] = rr[d].x[j] = zero4;
+            if ((int)blockIdx.x + d * G < n_chunks) load_chunk(rr[d], blockIdx.x + d * G);
+        }
+        uint32_t it = 0;
+        bool ok = true;
+        for (int chunk = blockIdx.x; chunk < n_chunks && ok; chunk += DEPTH * G) {
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) {
+                const int ch = chunk + d * G;
+                if (ch >= n_chunks) break;
+                const uint32_t s = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
+                unsigned char* st = wg_smem + (size_t)s * WG_STAGE_BYTES;
+                if (!(ok = mbar_wait<32>(&empty[s], ph ^ 1, abort_flag))) break;
+                convert_chunk(rr[d], ch, st);
+                if (ch + DEPTH * G < n_chunks) load_chunk(rr[d], ch + DEPTH * G);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+                ++it;
+            }
         }
         // column sums: lanes l and l^16 share c4 -> fold, then one shared atomic per column and warp
         float v[12] = {s_dy.x, s_dy.y, s_dy.z, s_dy.w, s_z.x, s_z.y, s_z.z, s_z.w, s_a.x, s_a.y, s_a.z, s_a.w};
@@ -541,7 +579,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) linear_wgrad_tc_kernel(const Wg
     }
     // ================================ epilogue (once per CTA) ====================================================
     __syncwarp();
-    bool fin = mbar_wait(done, 0, abort_flag);
+    bool fin = mbar_wait<64>(done, 0, abort_flag);
     tc_fence_after();
     __syncthreads();
     float* tile = reinterpret_cast<float*>(wg_smem);                     // [128][65] floats, stage memory is free now

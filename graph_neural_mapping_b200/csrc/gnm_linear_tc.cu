@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
         for (int tile = blockIdx.x; tile < n_tiles && !*abort_flag; tile += gridDim.x, ++it) {
             const uint32_t slot = it & 1, ph = (it >> 1) & 1;
             if (slot != my_slot) continue;
-            if (!mbar_wait(&acc_full[slot], ph, abort_flag)) break;
+            if (!mbar_wait<32>(&acc_full[slot], ph, abort_flag)) break;
             tc_fence_after();
             const int r = tile * 128 + q * 32 + lane;
             const bool row_ok = r < p.n_rows;
@@ -178,12 +178,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
             __syncwarp();
             const int row0 = tile * 128 + q * 32;
             if (p.n_out == LT_F && (p.ldy & 3) == 0 && gnm_aligned16(p.y)) {
-#pragma unroll 4
+                const int nvalid = p.n_rows - row0 - (lane >> 4);
+                char* dstp = reinterpret_cast<char*>(p.y + (int64_t)(row0 + (lane >> 4)) * p.ldy + (lane & 15) * 4);
+                const int64_t step = 2 * p.ldy * (int64_t)sizeof(float);
+                const float* sp = stg + (lane >> 4) * LT_PITCH + (lane & 15) * 4;
+#pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int rr = i * 2 + (lane >> 4), c4 = lane & 15;
-                    if (row0 + rr < p.n_rows)
-                        *reinterpret_cast<float4*>(p.y + (int64_t)(row0 + rr) * p.ldy + c4 * 4) =
-                            *reinterpret_cast<const float4*>(stg + rr * LT_PITCH + c4 * 4);
+                    if (2 * i < nvalid) *reinterpret_cast<float4*>(dstp) = *reinterpret_cast<const float4*>(sp);
+                    dstp += step;
+                    sp += 2 * LT_PITCH;
                 }
             } else {
                 for (int e = lane; e < 32 * LT_F; e += 32) {
@@ -249,14 +252,27 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
         auto stage_rows = [&](int tile) {
             const int row0 = tile * 128 + q * 32;
             if (fast) {
+                // lane -> (row pair member lane >> 4, float4 column lane & 15); rows advance by two per copy
+                const int nvalid = p.n_rows - row0 - (lane >> 4);        // copy i is in range iff 2 i < nvalid
+                const char* src = reinterpret_cast<const char*>(p.x + (int64_t)(row0 + (lane >> 4)) * p.ldx + (lane & 15) * 4);
+                const int64_t step = 2 * p.ldx * (int64_t)sizeof(float);
+                uint32_t dst = stg_u32 + (uint32_t)(((lane >> 4) * LT_PITCH + (lane & 15) * 4) * 4);
+                if (nvalid >= 31) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                        src += step;
+                        dst += 2 * LT_PITCH * 4;
+                    }
+                } else {
 #pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    const int rr = i * 2 + (lane >> 4), c4 = lane & 15;
-                    const bool okr = row0 + rr < p.n_rows;
-                    const float* src = p.x + (int64_t)(okr ? row0 + rr : 0) * p.ldx + c4 * 4;
-                    const uint32_t dst = stg_u32 + (uint32_t)((rr * LT_PITCH + c4 * 4) * 4);
-                    const int nbytes = okr ? 16 : 0;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+                    for (int i = 0; i < 16; ++i) {
+                        const bool okr = 2 * i < nvalid;
+                        const int nbytes = okr ? 16 : 0;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(okr ? src : (const char*)p.x), "r"(nbytes) : "memory");
+                        src += step;
+                        dst += 2 * LT_PITCH * 4;
+                    }
                 }
             } else {
                 for (int e = lane; e < 32 * LT_F; e += 32) {
@@ -303,7 +319,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
                     if (next_tile < n_tiles) stage_rows(next_tile);
                 }
                 if (!waited) {
-                    if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag))) break;
+                    if (!(ok = mbar_wait<32>(&a_empty[s], aph ^ 1, abort_flag))) break;
                     waited = true;
                 }
                 tmem_st16(taddr + (k0 >> 1), hi);

@@ -23,10 +23,12 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// bounded wait: false on timeout (the caller raises the abort flag and drains). try_wait suspends the thread in
-// hardware for a short, implementation-defined time; the clock / abort flag are only consulted every 64 wake-ups.
-// (A try_wait with an explicit suspend-time hint was measured to sleep the WHOLE hint - 20 us per wait - instead of
-// waking on completion, which capped both tensor-core kernels; do not use it.)
+// bounded wait: false on timeout (the caller raises the abort flag and drains). try_wait returns after a short,
+// implementation-defined time, so a waiting warp polls; the polls of a whole warp cost issue slots that the
+// conversion warps need (ncu: 10-17% of all executed instructions in the row-GEMM kernels), hence BACKOFF_NS > 0
+// parks the warp with nanosleep between polls. The single MMA-issuing thread polls without back-off (its wake-up
+// latency is on the critical path). The clock / abort flag are only consulted every 64 polls.
+template <int BACKOFF_NS = 0>
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag,
                                           long long* waited = nullptr) {
     const uint32_t addr = smem_u32(bar);
@@ -37,6 +39,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
     const long long t0 = clock64();
     int spins = 0;
     while (true) {
+        if (BACKOFF_NS > 0) __nanosleep(BACKOFF_NS);
         asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) {

@@ -11,7 +11,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
            ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
 }
 
-__global__ void __launch_bounds__(128) rate_kernel(int n, int a_swz, int b_swz, int reps, long long* cycles, int a_tmem_mode, int same_d) {
+__global__ void __launch_bounds__(128) rate_kernel(int n, int a_swz, int b_swz, int reps, long long* cycles, int a_tmem_mode, int same_d, int a_mn = 0) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base;
@@ -33,12 +33,14 @@ __global__ void __launch_bounds__(128) rate_kernel(int n, int a_swz, int b_swz, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base;
     if (tid == 0) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((a_mn ? 1u : 0u) << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const long long t0 = clock64();
         for (int r = 0; r < reps; ++r) {
             const int ks = r & 3;
             uint64_t da, db;
-            if (a_swz) da = make_desc(smem_u32(sa) + ks * 32, 16, 1024, 2);            // SW128 K-major: +32 B per k-step
+            if (a_mn == 1) da = make_desc(smem_u32(sa) + ks * 2 * 128, 128, 4 * 128 + 16, 0);   // MN-major no swizzle (64 k)
+            else if (a_mn == 2) da = make_desc(smem_u32(sa) + ks * 2 * 1024, 8192, 1024, 2);   // MN-major SW128: 64-wide m atoms
+            else if (a_swz) da = make_desc(smem_u32(sa) + ks * 32, 16, 1024, 2);            // SW128 K-major: +32 B per k-step
             else da = make_desc(smem_u32(sa) + ks * 2 * 2048, 2048, 128, 0);          // no swizzle
             if (b_swz) db = make_desc(smem_u32(sb) + ks * 2 * 1024, 8192, 1024, 2);   // SW128 MN-major: 64-wide n atoms at LBO, 8 k-rows at SBO
             else db = make_desc(smem_u32(sb) + ks * 2 * 128, 128, 8 * 128 + 16, 0);   // no swizzle
@@ -83,6 +85,18 @@ int main() {
                 long long mx = 0; for (int i = 0; i < grid; ++i) if (h[i] > mx) mx = h[i];
                 printf("grid=%3d A_from_tmem=%d same_accumulator=%d N=%3d : %s  %.1f cycles/MMA (floor %d)\n", grid, a_tm, same_d, ns[ni],
                        cudaGetErrorString(e), (double)mx / reps, 128 * ns[ni] / 256);
+                if (e != cudaSuccess) return 1;
+            }
+    // A operand MN-major from shared memory (weight-gradient kernel): no swizzle / 128-byte swizzle
+    for (int a_mn = 1; a_mn <= 2; ++a_mn)
+        for (int b_swz = 0; b_swz < 2; ++b_swz)
+            for (int ni = 0; ni < 3; ++ni) {
+                rate_kernel<<<148, 128, smem>>>(ns[ni], 0, b_swz, reps, d, 0, 1, a_mn);
+                cudaError_t e = cudaDeviceSynchronize();
+                long long h[148]; cudaMemcpy(h, d, 148 * 8, cudaMemcpyDeviceToHost);
+                long long mx = 0; for (int i = 0; i < 148; ++i) if (h[i] > mx) mx = h[i];
+                printf("A MN-major %s, B %s, N=%3d : %s  %.1f cycles/MMA (floor %d)\n", a_mn == 1 ? "no-swizzle" : "SW128", b_swz ? "SW128" : "no-swizzle",
+                       ns[ni], cudaGetErrorString(e), (double)mx / reps, 128 * ns[ni] / 256);
                 if (e != cudaSuccess) return 1;
             }
     return 0;
