@@ -41,11 +41,6 @@ def require_cuda(dev):
 # graph store / batch structure
 # ------------------------------------------------------------------------------------------
 
-class _StoredGraph(object):
-    __slots__ = ("graph", "n", "nnz", "rp_addr", "ci_addr", "tag_addr", "bm_addr", "onehot", "feat_dim", "keep",
-                 "isolated")
-
-
 def _onehot_tags(feats, cache):
     """Return int32 tags if `feats` ([N, D] float) is exactly one-hot per row, else None."""
     key = (feats.data_ptr(), tuple(feats.shape), feats._version)
@@ -67,12 +62,20 @@ class GraphStore(object):
     def __init__(self, device, add_self_loops):
         self.device = device
         self.add_self_loops = bool(add_self_loops)
-        self.entries = {}
+        self.entries = {}           # id(graph) -> slot
+        # slot table (one row per stored graph): rowptr / colidx / tag / bitmap addresses, n, nnz, onehot, isolated,
+        # feature width. A batch is assembled from it with a handful of numpy gathers instead of per-graph Python.
+        self._tab = np.zeros((0, 9), dtype=np.int64)
+        self._n_slots = 0
+        self._pins = []             # the graph objects (pins their ids) and the device buffers the addresses point into
         self._tag_cache = {}
         self.h2d_bytes = 0          # bytes shipped host->device by the last ensure()/assemble()
 
     def clear(self):
         self.entries.clear()
+        self._tab = np.zeros((0, 9), dtype=np.int64)
+        self._n_slots = 0
+        self._pins = []
         self._tag_cache.clear()
 
     def _staging(self, e_total):
@@ -157,36 +160,46 @@ class GraphStore(object):
         self.h2d_bytes += bm_off.nbytes
         keep = (rowptr, colidx, tags_d, bitmap)
         rp0, ci0, tg0, bm0 = rowptr.data_ptr(), colidx.data_ptr(), tags_d.data_ptr(), bitmap.data_ptr()
+        k = len(new)
+        if self._n_slots + k > self._tab.shape[0]:
+            grown = np.zeros((max(self._n_slots + k, 2 * self._tab.shape[0], 1024), 9), dtype=np.int64)
+            grown[:self._n_slots] = self._tab[:self._n_slots]
+            self._tab = grown
+        t = self._tab[self._n_slots:self._n_slots + k]
+        node_lo = np.asarray(node_off[:k], dtype=np.int64)
+        nnz_base = np.asarray(edge_off[:k], dtype=np.int64) + (node_lo if self.add_self_loops else 0)
+        t[:, 0] = rp0 + 4 * node_lo
+        t[:, 1] = ci0 + 4 * nnz_base
+        t[:, 2] = tg0 + 4 * node_lo
+        t[:, 3] = np.where(np.asarray(dup_h[:k]) == 0, bm0 + 4 * np.asarray(bm_off[:k], dtype=np.int64), 0)
+        t[:, 4] = counts
+        t[:, 5] = np.asarray(edge_counts, dtype=np.int64) + (np.asarray(counts, dtype=np.int64) if self.add_self_loops else 0)
+        t[:, 6] = np.asarray(onehot, dtype=np.int64)
+        t[:, 7] = iso_h.astype(np.int64)
+        t[:, 8] = [int(g.node_features.shape[1]) for g in new]
         for i, g in enumerate(new):
-            e = _StoredGraph()
-            e.graph = g                                  # pins the id
-            e.n = counts[i]
-            e.nnz = edge_counts[i] + (counts[i] if self.add_self_loops else 0)
-            nnz_base = int(edge_off[i]) + (int(node_off[i]) if self.add_self_loops else 0)
-            e.rp_addr = rp0 + 4 * int(node_off[i])
-            e.ci_addr = ci0 + 4 * nnz_base
-            e.tag_addr = tg0 + 4 * int(node_off[i])
-            e.bm_addr = (bm0 + 4 * int(bm_off[i])) if int(dup_h[i]) == 0 else 0
-            e.isolated = bool(iso_h[i])
-            e.onehot = onehot[i]
-            e.feat_dim = int(g.node_features.shape[1])
-            e.keep = keep
-            self.entries[id(g)] = e
+            self.entries[id(g)] = self._n_slots + i
+        self._n_slots += k
+        self._pins.append((new, keep))
 
     def assemble_host(self, graphs):
         """Host half of batch assembly: per-slot addresses / offsets as numpy, plus batch-level flags."""
-        self.ensure(graphs)
-        ent = [self.entries[id(g)] for g in graphs]
-        b = len(ent)
-        counts = np.fromiter((e.n for e in ent), dtype=np.int64, count=b)
-        nnzs = np.fromiter((e.nnz for e in ent), dtype=np.int64, count=b)
+        b = len(graphs)
+        getslot = self.entries.__getitem__
+        try:
+            idx = np.fromiter(map(getslot, map(id, graphs)), dtype=np.int64, count=b)
+        except KeyError:
+            self.ensure(graphs)
+            idx = np.fromiter(map(getslot, map(id, graphs)), dtype=np.int64, count=b)
+        t = self._tab[idx]                               # [b, 9]
+        counts = np.ascontiguousarray(t[:, 4])
         packed = np.empty(5 * b + 1, dtype=np.int64)
-        packed[0:b] = [e.rp_addr for e in ent]
-        packed[b:2 * b] = [e.ci_addr for e in ent]
-        packed[2 * b:3 * b] = [e.tag_addr for e in ent]
+        packed[0:b] = t[:, 0]
+        packed[b:2 * b] = t[:, 1]
+        packed[2 * b:3 * b] = t[:, 2]
         packed[3 * b] = 0
-        np.cumsum(nnzs, out=packed[3 * b + 1:4 * b + 1])
-        packed[4 * b + 1:5 * b + 1] = [e.bm_addr for e in ent]
+        np.cumsum(t[:, 5], out=packed[3 * b + 1:4 * b + 1])
+        packed[4 * b + 1:5 * b + 1] = t[:, 3]
         node_off = np.zeros(b + 1, dtype=np.int32)
         np.cumsum(counts, out=node_off[1:])
         m, nnz = int(node_off[-1]), int(packed[4 * b])
@@ -195,15 +208,15 @@ class GraphStore(object):
         h = _HostBatch()
         h.b, h.m, h.nnz, h.packed, h.node_off, h.counts = b, m, nnz, packed, node_off, counts
         h.uniform_n = int(counts[0]) if b > 0 and bool((counts == counts[0]).all()) else None
-        h.onehot = all(e.onehot for e in ent)
-        h.feat_dim = ent[0].feat_dim if b > 0 else 0
+        h.onehot = bool(t[:, 6].all())
+        h.feat_dim = int(t[0, 8]) if b > 0 else 0
         h.n_max = int(counts.max()) if b > 0 else 0
         # tensor-core path: every graph has a bitmap (no duplicate edges) and the blocks are dense enough
         # that N^2 tensor-core MACs beat gathering nnz rows through L2 (break-even ~3-4 % density)
-        has_bm = b > 0 and all(e.bm_addr != 0 for e in ent)
+        has_bm = b > 0 and bool((t[:, 3] != 0).all())
         dense_enough = nnz >= DENSE_MIN_DENSITY * float((counts.astype(np.float64) ** 2).sum())
         h.dense = bool(has_bm and dense_enough)
-        h.has_isolated = any(e.isolated for e in ent)
+        h.has_isolated = bool(t[:, 7].any())
         return h
 
     def assemble_device(self, h, packed_d, node_off_d, nnz_capacity=None):
@@ -300,6 +313,42 @@ class _Saved(object):
 # forward / backward
 # ------------------------------------------------------------------------------------------
 
+class _ZeroPool(object):
+    """Zero-initialised accumulators (BatchNorm statistics, dW / db, scalar sums) handed out as 16-byte aligned views
+    of a few large buffers: one fill kernel per buffer instead of one per accumulator (a training step has ~70)."""
+
+    def __init__(self, dev, n_f32=1 << 15, n_f64=1 << 12):
+        self.dev = dev
+        self.cap = {torch.float32: n_f32, torch.float64: n_f64}
+        self.buf = {torch.float32: None, torch.float64: None}
+        self.used = {torch.float32: 0, torch.float64: 0}
+        self.f64_chunks = []          # every float64 buffer handed out from (for batched post-processing)
+
+    def _take(self, dtype, n):
+        align = 4 if dtype == torch.float32 else 2
+        n_al = (n + align - 1) // align * align
+        if self.buf[dtype] is None or self.used[dtype] + n_al > self.buf[dtype].numel():
+            self.buf[dtype] = torch.zeros(max(self.cap[dtype], n_al), dtype=dtype, device=self.dev)
+            self.used[dtype] = 0
+            if dtype == torch.float64:
+                self.f64_chunks.append(self.buf[dtype])
+        off = self.used[dtype]
+        self.used[dtype] = off + n_al
+        return self.buf[dtype], off
+
+    def f32(self, *shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        buf, off = self._take(torch.float32, n)
+        return buf[off:off + n].view(*shape)
+
+    def f64(self, n):
+        """Returns (view, chunk index, offset) so that a caller can later address a converted copy of the chunk."""
+        buf, off = self._take(torch.float64, int(n))
+        return buf[off:off + int(n)], len(self.f64_chunks) - 1, off
+
+
 def _bn_affine(unit, stats, count, training, comm):
     dev = unit.z.device
     f = unit.z.shape[1]
@@ -347,6 +396,7 @@ def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm):
         raise RuntimeError("internal: gather path needs one-hot node features")
     sv.use_gather0 = use_gather0
     sv.batch_stats = []
+    zp = _ZeroPool(dev)
     for layer in range(L):
         units = []
         for lin, bn in layer_units(model, layer):
@@ -360,7 +410,7 @@ def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm):
         for j, u in enumerate(units):
             n_out = u.w.shape[0]
             u.z = torch.empty(M, n_out, dtype=torch.float32, device=dev)
-            stats = torch.zeros(2 * n_out, dtype=torch.float64, device=dev)
+            stats = zp.f64(2 * n_out)[0]
             if j == 0:
                 if layer == 0 and use_gather0:
                     # first layer as a row gather of W1^T (X_concat is one-hot): no dense X, no GEMM
@@ -417,7 +467,12 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
     bwd_mode = 2 if average else 0
     eps_p, disc_w, disc_b = params[0], params[1], params[2]
     grads = [None] * len(params)
-    d_eps = torch.zeros(L, dtype=torch.float64, device=dev) if learn_eps else None
+    zp = _ZeroPool(dev)
+    from_f64 = []         # (grad index, chunk, offset, length, scaled): float64 accumulators converted in one go at the end
+    d_eps = None
+    if learn_eps:
+        d_eps, c_, o_ = zp.f64(L)
+        from_f64.append((0, c_, o_, L, False))
 
     d_pooled = dg_f
     d_score = u_mat = d_neg = None
@@ -426,11 +481,11 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
         dd = dd_logit.contiguous().view(-1)
         du = torch.empty(B, L * F, dtype=torch.float32, device=dev)
         s2 = torch.empty(B, dtype=torch.float32, device=dev)
-        d_bias = torch.zeros(1, dtype=torch.float64, device=dev)
+        d_bias, c_, o_ = zp.f64(1)
+        from_f64.append((2, c_, o_, 1, False))
         _ops.dgi_score_bwd(sv.h_all, dd, sv.neg_table, sv.my_neg, bs.node_off, B, du, s2, d_bias)
         # [B, L*F]-sized glue: u = c W^T, c = sigmoid(g_f)
         grads[1] = (du.t() @ sv.c).unsqueeze(0)
-        grads[2] = d_bias.to(torch.float32)
         dc = du @ disc_w[0]
         dgs = dc * sv.c * (1.0 - sv.c)
         d_pooled = dgs if d_pooled is None else d_pooled + dgs
@@ -462,11 +517,11 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
             u = units[j]
             n_out, n_in = u.w.shape[0], u.w.shape[1]
             if pending is not None:
-                dy, stats = pending
+                dy, (stats, st_chunk, st_off) = pending
                 pending = None
             else:
                 dy = torch.empty(M, n_out, dtype=torch.float32, device=dev)
-                stats = torch.zeros(2 * n_out, dtype=torch.float64, device=dev)
+                stats, st_chunk, st_off = zp.f64(2 * n_out)
                 if j == len(units) - 1:
                     _ops.relu_bn_bwd_reduce(u.z, u.scale, u.shift, u.mean, u.rstd, d_h, d_pooled[:, sl],
                                             bs.pool_scale, d_score, u_mat[:, sl] if u_mat is not None else None,
@@ -479,14 +534,12 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
             if use_batch and comm.world > 1:
                 comm.all_reduce_sum(stats)
             gi = pidx + 4 * j
-            # d beta = sum dy, d gamma = sum dy * xhat. After the all-reduce these are sums over ALL ranks of
-            # gradients of each rank's own mean loss; dividing by the world size makes them this rank's share,
-            # so that the gradient averaging after backward (dist.average_gradients) treats them like any other.
-            share = 1.0 / comm.world if (use_batch and comm.world > 1) else 1.0
-            grads[gi + 3] = (stats[:n_out] * share).to(torch.float32)
-            grads[gi + 2] = (stats[n_out:] * share).to(torch.float32)
-            dw = torch.zeros_like(u.w)
-            db = torch.zeros_like(u.b)
+            # d beta = sum dy, d gamma = sum dy * xhat (converted, and scaled to this rank's share, at the end)
+            scaled = use_batch and comm.world > 1
+            from_f64.append((gi + 3, st_chunk, st_off, n_out, scaled))
+            from_f64.append((gi + 2, st_chunk, st_off + n_out, n_out, scaled))
+            dw = zp.f32(*u.w.shape)
+            db = zp.f32(*u.b.shape)
             gather0 = j == 0 and layer == 0 and sv.use_gather0
             fused = (not gather0) and (not FORCE_UNFUSED_BACKWARD) and n_out <= FUSED_BWD_MAX and n_in <= FUSED_BWD_MAX
             if fused:
@@ -497,9 +550,9 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                 if j > 0:
                     p = units[j - 1]
                     dy_prev = torch.empty(M, n_in, dtype=torch.float32, device=dev)
-                    stats_prev = torch.zeros(2 * n_in, dtype=torch.float64, device=dev)
+                    stats_prev = zp.f64(2 * n_in)
                     _ops.linear_bwd(dy, u.z, coef, p.z, p.scale, p.shift, p.mean, p.rstd, u.w, dw, db, dy_prev,
-                                    stats_prev)
+                                    stats_prev[0])
                     pending = (dy_prev, stats_prev)
                 else:
                     need_dp = layer > 0 or need_x_grad or learn_eps
@@ -532,12 +585,13 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                 # z0 = Agg(W1^T[tags]) + b:  dW1^T[t] = sum_{tags[r]=t} (Agg^T dz)[r]
                 g_agg = torch.empty(M, n_out, dtype=torch.float32, device=dev)
                 bs.aggregate(dz_u, None, g_agg, bwd_mode, eps_l, None)
-                dw1t = torch.zeros(n_in, n_out, dtype=torch.float32, device=dev)
+                dw1t = zp.f32(n_in, n_out)
                 _ops.scatter_rows_add(g_agg, bs.tags, dw1t)
                 dw = dw1t.t().contiguous()
-                colsum = torch.zeros(2 * n_out, dtype=torch.float64, device=dev)
+                colsum, c_, o_ = zp.f64(2 * n_out)
                 _ops.col_stats(dz_u, colsum)                      # d bias = column sums of dz
-                db = colsum[:n_out].to(torch.float32)
+                from_f64.append((gi + 1, c_, o_, n_out, False))
+                db = None
                 if learn_eps:
                     _ops.dot_rows(dz_u, sv.w1t, bs.tags, d_eps[layer:layer + 1])
                 if need_x_grad:
@@ -560,8 +614,15 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                         else:
                             d_x = d_prev
             grads[gi], grads[gi + 1] = dw, db
-    if learn_eps:
-        grads[0] = d_eps.to(torch.float32)
+    # float64 accumulators -> float32 gradients, one conversion per pool buffer (and one more for the shares of the
+    # synchronised BatchNorm reductions: after the all-reduce those are sums over ALL ranks of gradients of each
+    # rank's own mean loss; 1/world makes them this rank's share, so dist.average_gradients treats them like the rest)
+    plain = [c.to(torch.float32) for c in zp.f64_chunks]
+    if any(x[4] for x in from_f64):
+        shared = [(c * (1.0 / comm.world)).to(torch.float32) for c in zp.f64_chunks]
+    for gidx, c_, o_, n_, scaled in from_f64:
+        g = (shared if scaled else plain)[c_][o_:o_ + n_]
+        grads[gidx] = g.view(tuple(params[gidx].shape)) if gidx == 0 or gidx == 2 else g
     return d_x, grads
 
 

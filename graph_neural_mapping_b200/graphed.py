@@ -39,6 +39,8 @@ class StepPlan(object):
         self.bwd_graph = None
         self.generation = 0
         self.h = None
+        self._stage = [None, None, None]
+        self._stage_i = 0
         self.sig = self._signature(h)
         self.ptrs = self._pointers()
 
@@ -57,11 +59,27 @@ class StepPlan(object):
                 and self._pointers() == self.ptrs)
 
     def load(self, h, perm):
-        """Per-step host -> device traffic: slot addresses / offsets and the DGI permutation."""
+        """Per-step host -> device traffic: slot addresses / offsets and the DGI permutation, staged through a small
+        ring of pinned buffers and copied asynchronously, so the host never waits for the previous step's kernels and
+        can prepare (and enqueue) the next step while the GPU is still busy with this one."""
         self.h = h
-        self.packed.copy_(torch.from_numpy(h.packed))
-        self.node_off.copy_(torch.from_numpy(h.node_off))
-        self.neg_idx.copy_(torch.from_numpy(perm.astype(np.int32)))
+        i = self._stage_i
+        self._stage_i = (i + 1) % len(self._stage)
+        if self._stage[i] is None:
+            self._stage[i] = (torch.empty(self.packed.shape[0], dtype=torch.int64, pin_memory=True),
+                              torch.empty(self.node_off.shape[0], dtype=torch.int32, pin_memory=True),
+                              torch.empty(self.neg_idx.shape[0], dtype=torch.int32, pin_memory=True),
+                              torch.cuda.Event())
+        else:
+            self._stage[i][3].synchronize()           # the copies that last read this slot (three steps ago) are done
+        s_packed, s_off, s_neg, ev = self._stage[i]
+        s_packed.numpy()[:] = h.packed
+        s_off.numpy()[:] = h.node_off
+        s_neg.numpy()[:] = perm
+        self.packed.copy_(s_packed, non_blocking=True)
+        self.node_off.copy_(s_off, non_blocking=True)
+        self.neg_idx.copy_(s_neg, non_blocking=True)
+        ev.record()
         return h.packed.nbytes + h.node_off.nbytes + 4 * perm.size
 
     def _structure(self):
