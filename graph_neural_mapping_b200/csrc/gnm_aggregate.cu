@@ -197,6 +197,53 @@ scatter_rows_merge_kernel(const float* __restrict__ workspace, int n_ctas, int n
     }
 }
 
+// out[tag[t], :] += sum_k g[k * period + t, :]: the gathered-table gradient when every graph of the batch carries the
+// same injective tag sequence (util.py:106-116: one tag per ROI, the same ROI order in every subject). Two deterministic stages: each (row tile, split)
+// CTA sums its share of the graphs with 128-bit loads, eight rows in flight per thread; the splits are then added
+// in a fixed order.
+__global__ void __launch_bounds__(256)
+rows_period_sum_kernel(const float* __restrict__ g, int64_t ldg, int n_periods, int period, int n_feat4,
+                       float* __restrict__ partial) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;         // (t, c4)
+    if (e >= period * n_feat4) return;
+    const int t = e / n_feat4, c4 = e - t * n_feat4;
+    const int split = blockIdx.y, n_splits = gridDim.y;
+    const int k0 = (int)((int64_t)n_periods * split / n_splits), k1 = (int)((int64_t)n_periods * (split + 1) / n_splits);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* base = g + (int64_t)t * ldg + c4 * 4;
+    const int64_t step = (int64_t)period * ldg;
+    int k = k0;
+    for (; k + 8 <= k1; k += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(k + u) * step));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+    }
+    for (; k < k1; ++k) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)k * step));
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    reinterpret_cast<float4*>(partial)[(int64_t)split * period * n_feat4 + e] = a;
+}
+
+__global__ void __launch_bounds__(256)
+rows_period_merge_kernel(const float* __restrict__ partial, int n_splits, int period, int n_feat4,
+                         const int32_t* __restrict__ tags, int n_table_rows, float* __restrict__ out, int64_t ldo) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= period * n_feat4) return;
+    const int t = e / n_feat4, c4 = e - t * n_feat4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < n_splits; ++s) {
+        const float4 v = reinterpret_cast<const float4*>(partial)[(int64_t)s * period * n_feat4 + e];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    const int row = tags != nullptr ? tags[t] : t;
+    if (row < 0 || row >= n_table_rows) return;
+    float* o = out + (int64_t)row * ldo + c4 * 4;
+    o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+}
+
 }  // namespace
 
 extern "C" int gnm_aggregate(const int32_t* rowptr, const int32_t* colidx, int n_rows, const float* src,
@@ -288,4 +335,30 @@ extern "C" int64_t gnm_scatter_rows_workspace(int n_rows, int n_feat, int n_tabl
     if (rows_per_cta < 64) rows_per_cta = 64;
     ctas = (n_rows + rows_per_cta - 1) / rows_per_cta;
     return (int64_t)ctas * fparts * n_table_rows * fchunk;
+}
+
+/* Splits (workspace = splits * period * n_feat floats) used by gnm_rows_period_sum. */
+static int rows_period_splits(int n_periods) { return n_periods < 32 ? (n_periods < 1 ? 1 : n_periods) : 32; }
+
+extern "C" int64_t gnm_rows_period_workspace(int n_rows, int n_feat, int period) {
+    if (n_rows <= 0 || n_feat <= 0 || period <= 0) return 0;
+    return (int64_t)rows_period_splits(n_rows / period) * period * n_feat;
+}
+
+extern "C" int gnm_rows_period_sum(const float* g, int64_t ldg, int n_rows, int n_feat, int period, const int32_t* tags,
+                                   float* out, int64_t ldo, int n_table_rows, float* workspace,
+                                   int64_t workspace_floats, gnm_stream_t stream) {
+    if (n_rows < 0 || n_feat < 0 || period <= 0 || n_rows % period != 0 || n_table_rows < 0) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0 || n_feat == 0) return GNM_OK;
+    if (!g || !out || !workspace) return GNM_ERR_BAD_ARG;
+    if ((n_feat & 3) || (ldg & 3) || !gnm_aligned16(g) || !gnm_aligned16(workspace)) return GNM_ERR_ALIGN;
+    if (workspace_floats < gnm_rows_period_workspace(n_rows, n_feat, period)) return GNM_ERR_BAD_ARG;
+    const int n_periods = n_rows / period, splits = rows_period_splits(n_periods), f4 = n_feat / 4;
+    const int blocks = (period * f4 + 255) / 256;
+    rows_period_sum_kernel<<<dim3(blocks, splits), 256, 0, gnm_cast_stream(stream)>>>(g, ldg, n_periods, period, f4, workspace);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    rows_period_merge_kernel<<<blocks, 256, 0, gnm_cast_stream(stream)>>>(workspace, splits, period, f4, tags, n_table_rows, out,
+                                                                           ldo);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
 }

@@ -128,6 +128,7 @@ csr_batch_gather_kernel(const int64_t* __restrict__ src_rp_addr, const int64_t* 
             for (int i = threadIdx.x; i < n; i += blockDim.x) tags[n0 + i] = tg[i];
         }
     }
+    if (colidx == nullptr) return;       // structure-only gather: the dense-block kernels read the stored bitmaps
     const int chunk = (nnz + parts - 1) / parts;
     const int q0 = part * chunk, q1 = min(nnz, q0 + chunk);
     const int32_t* s = ci;   // address of this graph's own column segment
@@ -173,6 +174,7 @@ extern "C" int gnm_csr_batch_gather(const int64_t* src_rowptr_addr, const int64_
     int parts = 1;
     if (n_graphs < 1184) parts = (1184 + n_graphs - 1) / n_graphs;
     if (parts > 16) parts = 16;
+    if (colidx == nullptr) parts = 1;
     dim3 grid(n_graphs, parts);
     csr_batch_gather_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(src_rowptr_addr, src_colidx_addr, src_tag_addr,
                                                                        node_off, nnz_off, n_graphs, rowptr, colidx,

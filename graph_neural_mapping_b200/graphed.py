@@ -47,7 +47,7 @@ class StepPlan(object):
     # a captured graph bakes in kernel choices and pointers: anything that changes them is part of the key
     @staticmethod
     def _signature(h):
-        return (h.b, h.m, h.uniform_n, h.onehot, h.feat_dim, h.n_max, h.dense, h.has_isolated)
+        return (h.b, h.m, h.uniform_n, h.onehot, h.feat_dim, h.n_max, h.dense, h.has_isolated, h.same_tags)
 
     def _pointers(self):
         ps = [p.data_ptr() for p in _engine.flat_params(self.model)]

@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libgnm.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _c_i32 = ctypes.c_int
 _c_i64 = ctypes.c_int64
@@ -34,6 +34,8 @@ SIGNATURES = {
     "gnm_dot_rows": [_p, _c_i64, _p, _c_i64, _p, _c_i32, _c_i32, _p, _p],
     "gnm_scatter_rows_add": [_p, _c_i64, _p, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p, _c_i64, _p],
     "gnm_scatter_rows_workspace": [_c_i32, _c_i32, _c_i32],
+    "gnm_rows_period_sum": [_p, _c_i64, _c_i32, _c_i32, _c_i32, _p, _p, _c_i64, _c_i32, _p, _c_i64, _p],
+    "gnm_rows_period_workspace": [_c_i32, _c_i32, _c_i32],
     "gnm_linear": [_p, _c_i64, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p, _p, _p, _p, _c_i64, _c_i32, _p, _p],
     "gnm_set_linear_impl": [_c_i32],
     "gnm_linear_wgrad": [_p, _c_i64, _p, _c_i64, _c_i32, _c_i32, _c_i32, _p, _p, _p, _c_i64, _p, _p],
@@ -81,6 +83,7 @@ def load():
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int
     lib.gnm_scatter_rows_workspace.restype = ctypes.c_int64
+    lib.gnm_rows_period_workspace.restype = ctypes.c_int64
     lib.gnm_error_string.argtypes = [ctypes.c_int]
     lib.gnm_error_string.restype = ctypes.c_char_p
     got = lib.gnm_abi_version()

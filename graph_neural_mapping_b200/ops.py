@@ -75,17 +75,18 @@ def csr_build(edges, edge_off, node_off, n_graphs, n_max, total_nodes, add_self_
     return rowptr, colidx[:nnz], status
 
 
-def csr_batch_gather(rp_addr, ci_addr, tag_addr, node_off, nnz_off, n_graphs, total_nodes, total_nnz):
+def csr_batch_gather(rp_addr, ci_addr, tag_addr, node_off, nnz_off, n_graphs, total_nodes, total_nnz, with_colidx=True):
+    """with_colidx=False gathers row pointers (and tags) only and returns colidx = None."""
     dev = node_off.device
     rowptr = torch.empty(total_nodes + 1, dtype=torch.int32, device=dev)
-    colidx = torch.empty(max(total_nnz, 1), dtype=torch.int32, device=dev)
+    colidx = torch.empty(max(total_nnz, 1), dtype=torch.int32, device=dev) if with_colidx else None
     tags = torch.empty(total_nodes, dtype=torch.int32, device=dev) if tag_addr is not None else None
     _libmod.check(_lib().gnm_csr_batch_gather(_ptr(rp_addr, torch.int64), _ptr(ci_addr, torch.int64),
                                               _ptr(tag_addr, torch.int64) if tag_addr is not None else None,
                                               _ptr(node_off, torch.int32), _ptr(nnz_off, torch.int64), n_graphs,
                                               _ptr(rowptr), _ptr(colidx), _ptr(tags), _stream(node_off)),
                   "gnm_csr_batch_gather")
-    return rowptr, colidx[:total_nnz], tags
+    return rowptr, (colidx[:total_nnz] if with_colidx else None), tags
 
 
 # ---- aggregation -------------------------------------------------------------------------
@@ -156,6 +157,20 @@ def scatter_rows_add(g, tags, table_grad):
     _libmod.check(_lib().gnm_scatter_rows_add(gp, ldg, _ptr(tags, torch.int32), int(g.shape[0]), int(g.shape[1]),
                                               tp, ldt, int(table_grad.shape[0]), _ptr(ws), need, _stream(g)),
                   "gnm_scatter_rows_add")
+    return table_grad
+
+
+def rows_period_sum(g, period, tags, table_grad):
+    """table_grad[tags[t]] += sum_k g[k*period + t] - scatter_rows_add for batches whose graphs all carry the same
+    injective tag sequence (the caller checks that; tags = that sequence, or None for the identity)."""
+    gp, ldg = _mat(g)
+    tp, ldt = _mat(table_grad)
+    need = int(_lib().gnm_rows_period_workspace(int(g.shape[0]), int(g.shape[1]), int(period)))
+    ws = torch.empty(max(need, 1), dtype=torch.float32, device=g.device)
+    _libmod.check(_lib().gnm_rows_period_sum(gp, ldg, int(g.shape[0]), int(g.shape[1]), int(period),
+                                             _ptr(tags, torch.int32) if tags is not None else None, tp, ldt,
+                                             int(table_grad.shape[0]), _ptr(ws), need, _stream(g)),
+                  "gnm_rows_period_sum")
     return table_grad
 
 

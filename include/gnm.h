@@ -32,7 +32,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 8
+#define GNM_ABI_VERSION 9
 
 typedef void* gnm_stream_t;
 
@@ -64,7 +64,9 @@ int gnm_csr_build(const int64_t* edges, int64_t e_total, const int64_t* edge_off
  * H2D copy of Adj_block every step): slot b copies the stored local CSR of one graph, shifting row
  * pointers by nnz_off[b] and column ids by node_off[b].
  *   src_rowptr_addr / src_colidx_addr / src_tag_addr: int64 [B] device ADDRESSES of each graph's stored
- *   int32 rowptr (N+1 entries), colidx and (nullable) one-hot tag array. */
+ *   int32 rowptr (N+1 entries), colidx and (nullable) one-hot tag array.
+ *   colidx == NULL gathers row pointers and tags only (195 MB less traffic per step at B=1024, N=400): batches that
+ *   run on the dense-block kernels read the stored bitmaps and never touch the batch column indices. */
 int gnm_csr_batch_gather(const int64_t* src_rowptr_addr, const int64_t* src_colidx_addr, const int64_t* src_tag_addr,
                          const int32_t* node_off, const int64_t* nnz_off, int n_graphs,
                          int32_t* rowptr, int32_t* colidx, int32_t* tags, gnm_stream_t stream);
@@ -121,6 +123,14 @@ int gnm_scatter_rows_add(const float* g, int64_t ldg, const int32_t* tags, int n
                          float* table_grad, int64_t ldt, int n_table_rows, float* workspace,
                          int64_t workspace_floats, gnm_stream_t stream);
 int64_t gnm_scatter_rows_workspace(int n_rows, int n_feat, int n_table_rows);
+/* Same gradient when every graph of the batch carries the same injective tag sequence tags[0..period) (util.py:106-116
+ * gives every subject one tag per ROI in the same ROI order): out[tags[t], :] += sum_k g[k*period + t, :] (tags NULL =
+ * identity). A streaming column sum instead of a scatter; deterministic (per-split partial sums in workspace, merged in
+ * a fixed order). The CALLER guarantees the precondition; rows whose tag falls outside [0, n_table_rows) are dropped.
+ * n_rows % period == 0, n_feat % 4 == 0, 16-byte aligned rows; workspace_floats >= gnm_rows_period_workspace(...). */
+int gnm_rows_period_sum(const float* g, int64_t ldg, int n_rows, int n_feat, int period, const int32_t* tags, float* out,
+                        int64_t ldo, int n_table_rows, float* workspace, int64_t workspace_floats, gnm_stream_t stream);
+int64_t gnm_rows_period_workspace(int n_rows, int n_feat, int period);
 
 /* ---- MLP: Linear + BatchNorm + ReLU ------------------------------------------------------ */
 

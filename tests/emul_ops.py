@@ -47,7 +47,7 @@ def csr_build(edges, edge_off, node_off, n_graphs, n_max, total_nodes, add_self_
             torch.tensor([bad], dtype=torch.int32))
 
 
-def csr_batch_gather(rp_addr, ci_addr, tag_addr, node_off, nnz_off, n_graphs, total_nodes, total_nnz):
+def csr_batch_gather(rp_addr, ci_addr, tag_addr, node_off, nnz_off, n_graphs, total_nodes, total_nnz, with_colidx=True):
     no, zo = node_off.numpy(), nnz_off.numpy()
     rowptr = np.zeros(total_nodes + 1, dtype=np.int32)
     colidx = np.zeros(total_nnz, dtype=np.int32)
@@ -62,7 +62,8 @@ def csr_batch_gather(rp_addr, ci_addr, tag_addr, node_off, nnz_off, n_graphs, to
         if tags is not None:
             tags[no[g]:no[g] + n] = _i32_at(tag_addr[g], n)
     rowptr[total_nodes] = total_nnz
-    return torch.from_numpy(rowptr), torch.from_numpy(colidx), (torch.from_numpy(tags) if tags is not None else None)
+    return (torch.from_numpy(rowptr), torch.from_numpy(colidx) if with_colidx else None,
+            torch.from_numpy(tags) if tags is not None else None)
 
 
 def _csr(rowptr, colidx, m):
@@ -149,6 +150,14 @@ def dot_rows(a, b, b_map, out):
 
 def scatter_rows_add(g, tags, table_grad):
     table_grad.index_add_(0, tags.long(), g)
+    return table_grad
+
+
+def rows_period_sum(g, period, tags, table_grad):
+    s = g.view(-1, period, g.shape[1]).double().sum(0).to(g.dtype)
+    idx = torch.arange(period) if tags is None else tags[:period].long()
+    ok = (idx >= 0) & (idx < table_grad.shape[0])
+    table_grad.index_add_(0, idx[ok], s[ok])
     return table_grad
 
 

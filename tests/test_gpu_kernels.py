@@ -437,6 +437,44 @@ def test_aggregate_dense_exactness_on_wide_dynamic_range():
     assert not ops.aggregate_tc_status()
 
 
+@pytest.mark.parametrize("n_graphs,period,f,table", [(1, 5, 4, 5), (3, 7, 12, 9), (40, 400, 64, 400), (1024, 400, 64, 400),
+                                                     (33, 50, 8, 64)])
+def test_rows_period_sum(n_graphs, period, f, table):
+    """Layer-0 table gradient for batches that share one injective tag sequence: equals the scatter, is
+    deterministic, accumulates into the output, drops out-of-range tags."""
+    torch.manual_seed(n_graphs + period)
+    g = torch.randn(n_graphs * period, f, device=DEV)
+    seq = torch.randperm(table, device=DEV)[:period].to(torch.int32)
+    tags = seq.repeat(n_graphs)
+    base = torch.randn(table, f, device=DEV)
+    out = base.clone()
+    ops.rows_period_sum(g, period, tags, out)
+    ref = base.cpu().double().index_add_(0, tags.cpu().long(), g.cpu().double())
+    assert_close(out, ref, TOL, "rows_period_sum vs scatter reference")
+    out2 = base.clone()
+    ops.rows_period_sum(g, period, tags, out2)
+    assert torch.equal(out, out2), "deterministic"
+    sc = base.clone()
+    ops.scatter_rows_add(g, tags, sc)
+    assert_close(out, sc, TOL, "rows_period_sum vs scatter_rows_add")
+    if period <= table:
+        ident = torch.zeros(table, f, device=DEV)
+        ops.rows_period_sum(g, period, None, ident)
+        ref_i = torch.zeros(table, f, dtype=torch.float64)
+        ref_i[:period] = g.cpu().double().view(n_graphs, period, f).sum(0)
+        assert_close(ident, ref_i, TOL, "identity tags")
+    bad = tags.clone()
+    bad[:period][0] = table + 3                      # out-of-range tag of position 0: that position is dropped
+    out3 = torch.zeros(table, f, device=DEV)
+    ops.rows_period_sum(g, period, bad, out3)
+    ref3 = torch.zeros(table, f, dtype=torch.float64)
+    s = g.cpu().double().view(n_graphs, period, f).sum(0)
+    ref3.index_add_(0, seq.cpu().long()[1:], s[1:])
+    assert_close(out3, ref3, TOL, "out-of-range tag dropped")
+    with pytest.raises(Exception):
+        ops.rows_period_sum(g[:-1], period, tags, out) if period > 1 else (_ for _ in ()).throw(RuntimeError("n/a"))
+
+
 @pytest.mark.parametrize("m,fo,fi", [(1, 1, 1), (300, 8, 12), (4097, 64, 64), (1000, 12, 64), (640, 64, 8), (129, 63, 37)])
 @pytest.mark.parametrize("act,train", [(True, True), (False, True), (True, False)])
 def test_linear_bwd_fused(m, fo, fi, act, train):

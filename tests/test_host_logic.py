@@ -265,3 +265,37 @@ def test_no_reference_cycle_keeps_activations_alive():
         assert not leaked, [type(o).__name__ for o in leaked]
     finally:
         gc.enable()
+
+
+def test_shared_tag_sequence_takes_the_period_sum_path():
+    """util.py:106-116 gives every subject the same (arbitrary) injective tag sequence; the layer-0 table gradient is
+    then a sum over graphs (rows_period_sum). A batch whose graphs carry DIFFERENT tag orders must fall back to the
+    scatter, and both must agree with the dense layer-0 path (which does not look at tags at all)."""
+    g = Golden("tiny_eps_sum")
+    n = g.graphs()[0].node_features.shape[0]
+    perm = torch.from_numpy(np.random.RandomState(5).permutation(n))
+
+    def batch(per_graph_shift, dense):
+        graphs = g.graphs()
+        for i, gr in enumerate(graphs):
+            p = torch.roll(perm, i if per_graph_shift else 0)
+            f = torch.zeros_like(gr.node_features)
+            f[torch.arange(n), p] = 1.0
+            if dense:
+                f[0, p[0]] = 1.0000001                       # not exactly one-hot -> dense layer-0 path
+            gr.node_features = f
+        return graphs
+
+    grads = {}
+    for shift in (False, True):
+        for dense in (False, True):
+            m = build_model(g)
+            graphs = batch(shift, dense)
+            if not dense:
+                assert m._structure(graphs).same_tags == (not shift)
+            train_step(m, graphs, g, 17)
+            grads[(shift, dense)] = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    for shift in (False, True):
+        floor = grad_floor({k: v.numpy() for k, v in grads[(shift, True)].items()})
+        for k, v in grads[(shift, True)].items():
+            assert_close(grads[(shift, False)][k], v, 1e-4, "shift=%s grad %s" % (shift, k), floor=floor)
