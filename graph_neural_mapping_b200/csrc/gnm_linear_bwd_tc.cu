@@ -27,8 +27,10 @@ constexpr int BT_W_PLANE = BT_F * BT_F * 2;
 constexpr int BT_W_KCORE = 8 * 128;
 constexpr int BT_PITCH = BT_F + 4;
 constexpr int BT_STG = 32 * BT_PITCH * 4;
+constexpr int BT_OPITCH = 32 + 4;            // epilogue half tile: 32 rows x 32 columns, padded
+constexpr int BT_OSTG = 32 * BT_OPITCH * 4;
 constexpr int BT_CONST_FLOATS = 5 * BT_F;   // c_row | in_scale | in_shift | in_mean | in_rstd
-constexpr int BT_SMEM = 6 * BT_W_PLANE + BT_CONST_FLOATS * 4 + 256 + (BT_EPI_WARPS + BT_PROD_WARPS) * BT_STG;
+constexpr int BT_SMEM = 6 * BT_W_PLANE + BT_CONST_FLOATS * 4 + 256 + (BT_EPI_WARPS + BT_PROD_WARPS) * BT_STG + BT_EPI_WARPS * BT_OSTG;
 
 struct LinBwdTcParams {
     const float* dy; int64_t lddy;
@@ -42,19 +44,6 @@ struct LinBwdTcParams {
     int n_rows, n_out, n_in;
 };
 
-__device__ __forceinline__ void transpose_reduce32_b(float (&v)[32], int lane) {
-#pragma unroll
-    for (int step = 0; step < 5; ++step) {
-        const int off = 16 >> step, half = 16 >> step;
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int j = 0; j < half; ++j) {
-            const float send = upper ? v[j] : v[j + half];
-            const float keep = upper ? v[j + half] : v[j];
-            v[j] = keep + __shfl_xor_sync(GNM_FULL_MASK, send, off);
-        }
-    }
-}
 
 // cp.async a warp's 32 rows x 64 floats (rows past n_rows zero-filled) into its padded staging tile
 __device__ __forceinline__ void stage_rows_async(const float* base, int64_t ld, int n_rows, int n_cols, int row0, float* stg,
@@ -103,6 +92,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
     unsigned char* sm_w = bt_smem;                                       // planes: WA hi|mid|lo, WB hi|mid|lo
     float* sm_c = reinterpret_cast<float*>(bt_smem + 6 * BT_W_PLANE);
     float* sm_stg = reinterpret_cast<float*>(bt_smem + 6 * BT_W_PLANE + BT_CONST_FLOATS * 4 + 256);
+    float* sm_out = sm_stg + (BT_EPI_WARPS + BT_PROD_WARPS) * (32 * BT_PITCH);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     volatile int* abort_flag = &s_abort;
     const int n_tiles = (p.n_rows + 127) >> 7;
@@ -157,13 +147,19 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
 
     if (warp < BT_EPI_WARPS) {
         // ================================ epilogue (two groups of four warps, one per accumulator slot) ============
-        float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f};
+        // Row pass: the warp's 32 x 32 half of the accumulator goes TMEM -> registers -> a small shared tile, one row
+        // per lane. Column pass: the half is re-read eight lanes per row (float4 columns) next to the staged x tile:
+        // + constant row, ReLU mask, xhat, the two BatchNorm-backward column sums and the coalesced dx store all
+        // happen in that layout, so no cross-lane transposition is needed.
+        float cs1[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, cs2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         const uint32_t my_slot = warp >> 2;
         const int q = warp & 3;
         float* stg = sm_stg + warp * (32 * BT_PITCH);
+        float* obuf = sm_out + warp * (32 * BT_OPITCH);
         const uint32_t stg_u32 = smem_u32(stg);
         const bool fast_x = act && p.n_in == BT_F && (p.ldx & 3) == 0 && gnm_aligned16(p.x);
         const bool fast_o = p.dx != nullptr && p.n_in == BT_F && (p.lddx & 3) == 0 && gnm_aligned16(p.dx);
+        const int sub = lane >> 3, c4l = (lane & 7) * 4;
         // prefetch x for this group's first tile
         if (act) {
             const int t0 = blockIdx.x + (int)my_slot * gridDim.x;
@@ -176,81 +172,75 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
             if (!mbar_wait<32>(&acc_full[slot], ph, abort_flag)) break;
             tc_fence_after();
             const int row0 = tile * 128 + q * 32;
-            const bool row_ok = row0 + lane < p.n_rows;
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
-                float v[32];
 #pragma unroll
                 for (int c0 = 0; c0 < 32; c0 += 16) {
                     uint32_t t16[16];
                     tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + slot * BT_D_COLS + hf * 32 + c0, t16);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[c0 + j] = __uint_as_float(t16[j]);
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<uint4*>(obuf + lane * BT_OPITCH + c0 + j) = make_uint4(t16[j], t16[j + 1], t16[j + 2], t16[j + 3]);
                 }
                 if (hf == 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[slot]);
+                    if (lane == 0) mbar_arrive(&acc_empty[slot]);       // the accumulator has left TMEM: free the slot
                 }
-                float xh[32];
+                __syncwarp();
+                const int c = hf * 32 + c4l;
+                const float4 cr = *reinterpret_cast<const float4*>(sm_c + c);
+                const float4 sc = *reinterpret_cast<const float4*>(sm_c + BT_F + c);
+                const float4 sh = *reinterpret_cast<const float4*>(sm_c + 2 * BT_F + c);
+                const float4 mu = *reinterpret_cast<const float4*>(sm_c + 3 * BT_F + c);
+                const float4 rs = *reinterpret_cast<const float4*>(sm_c + 4 * BT_F + c);
+                const int nvalid = p.n_rows - row0 - sub;                  // row 4 i + sub is in range iff 4 i < nvalid
+                char* dstp = p.dx != nullptr ? reinterpret_cast<char*>(p.dx + (int64_t)(row0 + sub) * p.lddx + c) : nullptr;
+                const int64_t dstep = 4 * p.lddx * (int64_t)sizeof(float);
+                // loads first (a per-row branch in front of them would serialise the shared-memory latencies)
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int c = hf * 32 + j;
-                    const float4 cr = *reinterpret_cast<const float4*>(sm_c + c);
-                    v[j] += cr.x; v[j + 1] += cr.y; v[j + 2] += cr.z; v[j + 3] += cr.w;
+                for (int i0 = 0; i0 < 8; i0 += 4) {
+                float4 dd[4], xx[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    dd[i] = *reinterpret_cast<const float4*>(obuf + (4 * (i0 + i) + sub) * BT_OPITCH + c4l);
+                    if (act) xx[i] = *reinterpret_cast<const float4*>(stg + (4 * (i0 + i) + sub) * BT_PITCH + c);
+                }
+#pragma unroll
+                for (int i = i0; i < i0 + 4; ++i) {
+                    float4 d = dd[i - i0];
+                    const bool okr = 4 * i < nvalid;
+                    d.x += cr.x; d.y += cr.y; d.z += cr.z; d.w += cr.w;
                     if (act) {
-                        const float4 xv = *reinterpret_cast<const float4*>(stg + lane * BT_PITCH + c);
-                        const float4 sc = *reinterpret_cast<const float4*>(sm_c + BT_F + c);
-                        const float4 sh = *reinterpret_cast<const float4*>(sm_c + 2 * BT_F + c);
-                        const float4 mu = *reinterpret_cast<const float4*>(sm_c + 3 * BT_F + c);
-                        const float4 rs = *reinterpret_cast<const float4*>(sm_c + 4 * BT_F + c);
-                        v[j] = (fmaf(xv.x, sc.x, sh.x) > 0.f) ? v[j] : 0.f;
-                        v[j + 1] = (fmaf(xv.y, sc.y, sh.y) > 0.f) ? v[j + 1] : 0.f;
-                        v[j + 2] = (fmaf(xv.z, sc.z, sh.z) > 0.f) ? v[j + 2] : 0.f;
-                        v[j + 3] = (fmaf(xv.w, sc.w, sh.w) > 0.f) ? v[j + 3] : 0.f;
-                        xh[j] = (xv.x - mu.x) * rs.x; xh[j + 1] = (xv.y - mu.y) * rs.y;
-                        xh[j + 2] = (xv.z - mu.z) * rs.z; xh[j + 3] = (xv.w - mu.w) * rs.w;
+                        const float4 xv = xx[i - i0];
+                        d.x = (okr && fmaf(xv.x, sc.x, sh.x) > 0.f) ? d.x : 0.f;
+                        d.y = (okr && fmaf(xv.y, sc.y, sh.y) > 0.f) ? d.y : 0.f;
+                        d.z = (okr && fmaf(xv.z, sc.z, sh.z) > 0.f) ? d.z : 0.f;
+                        d.w = (okr && fmaf(xv.w, sc.w, sh.w) > 0.f) ? d.w : 0.f;
+                        cs1[hf][0] += d.x; cs1[hf][1] += d.y; cs1[hf][2] += d.z; cs1[hf][3] += d.w;
+                        cs2[hf][0] = fmaf(d.x, (xv.x - mu.x) * rs.x, cs2[hf][0]);
+                        cs2[hf][1] = fmaf(d.y, (xv.y - mu.y) * rs.y, cs2[hf][1]);
+                        cs2[hf][2] = fmaf(d.z, (xv.z - mu.z) * rs.z, cs2[hf][2]);
+                        cs2[hf][3] = fmaf(d.w, (xv.w - mu.w) * rs.w, cs2[hf][3]);
                     }
-                    // the staging row is this lane's own: overwrite the consumed x values with the result
-                    *reinterpret_cast<float4*>(stg + lane * BT_PITCH + c) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-                if (act && p.stats_in != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float g = (row_ok && hf * 32 + j < p.n_in) ? v[j] : 0.f;
-                        v[j] = g;
-                        xh[j] = g * xh[j];
+                    if (dstp != nullptr && okr) {
+                        if (fast_o) {
+                            *reinterpret_cast<float4*>(dstp + i * dstep) = d;
+                        } else {
+                            float* o = reinterpret_cast<float*>(dstp + i * dstep);
+                            if (c < p.n_in) o[0] = d.x;
+                            if (c + 1 < p.n_in) o[1] = d.y;
+                            if (c + 2 < p.n_in) o[2] = d.z;
+                            if (c + 3 < p.n_in) o[3] = d.w;
+                        }
                     }
-                    transpose_reduce32_b(v, lane);
-                    transpose_reduce32_b(xh, lane);
-                    st1[hf] += v[0];
-                    st2[hf] += xh[0];
                 }
+                }
+                __syncwarp();                                           // the half tile is reused by the next half
             }
-            __syncwarp();
-            if (p.dx != nullptr) {
-                if (fast_o) {
-                    const int nvalid = p.n_rows - row0 - (lane >> 4);
-                    char* dstp = reinterpret_cast<char*>(p.dx + (int64_t)(row0 + (lane >> 4)) * p.lddx + (lane & 15) * 4);
-                    const int64_t step = 2 * p.lddx * (int64_t)sizeof(float);
-                    const float* sp = stg + (lane >> 4) * BT_PITCH + (lane & 15) * 4;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (2 * i < nvalid) *reinterpret_cast<float4*>(dstp) = *reinterpret_cast<const float4*>(sp);
-                        dstp += step;
-                        sp += 2 * BT_PITCH;
-                    }
-                } else {
-                    for (int e = lane; e < 32 * BT_F; e += 32) {
-                        const int rr = e >> 6, c = e & 63;
-                        if (row0 + rr < p.n_rows && c < p.n_in) p.dx[(int64_t)(row0 + rr) * p.lddx + c] = stg[rr * BT_PITCH + c];
-                    }
-                }
-            }
-            __syncwarp();
             if (act) {
                 const int next_tile = tile + 2 * gridDim.x;
                 if (next_tile < n_tiles)
@@ -259,13 +249,32 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (act && p.stats_in != nullptr) {
+            // lanes with equal (lane & 7) hold the same columns for different rows: fold them, park the warp's 2 x 64
+            // partial sums in its (now free) staging tile, add the eight warps in a fixed order and issue ONE fp64
+            // atomic per column and CTA (same-address atomics serialise in L2)
+            __syncwarp();
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-                const int c = h2 * 32 + lane;
-                if (c < p.n_in) {
-                    atomicAdd(&p.stats_in[c], (double)st1[h2]);
-                    atomicAdd(&p.stats_in[p.n_in + c], (double)st2[h2]);
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float a1 = cs1[hf][u], a2 = cs2[hf][u];
+                    a1 += __shfl_xor_sync(GNM_FULL_MASK, a1, 8);
+                    a2 += __shfl_xor_sync(GNM_FULL_MASK, a2, 8);
+                    a1 += __shfl_xor_sync(GNM_FULL_MASK, a1, 16);
+                    a2 += __shfl_xor_sync(GNM_FULL_MASK, a2, 16);
+                    if (lane < 8) {
+                        stg[hf * 32 + c4l + u] = a1;
+                        stg[BT_F + hf * 32 + c4l + u] = a2;
+                    }
                 }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(BT_EPI_WARPS * 32) : "memory");
+            if (tid < 2 * BT_F) {
+                float a = 0.f;
+#pragma unroll
+                for (int w = 0; w < BT_EPI_WARPS; ++w) a += sm_stg[w * (32 * BT_PITCH) + tid];
+                const int c = tid & (BT_F - 1);
+                if (c < p.n_in) atomicAdd(&p.stats_in[(tid >> 6) * p.n_in + c], (double)a);
             }
         }
     } else if (warp == BT_MMA_WARP) {

@@ -47,22 +47,6 @@ struct LinTcParams {
     int n_rows, n_in, n_out;
 };
 
-// column sums over the 32 rows (lanes) of a warp for 32 columns: after the call lane l holds the total of column l in v[0]
-__device__ __forceinline__ void transpose_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int step = 0; step < 5; ++step) {
-        const int off = 16 >> step;                 // lane distance 16, 8, 4, 2, 1
-        const int half = 16 >> step;                // columns kept per lane after this step
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int j = 0; j < half; ++j) {
-            const float send = upper ? v[j] : v[j + half];
-            const float keep = upper ? v[j + half] : v[j];
-            v[j] = keep + __shfl_xor_sync(GNM_FULL_MASK, send, off);
-        }
-    }
-}
-
 __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcParams p) {
     extern __shared__ __align__(1024) unsigned char lt_smem[];
     __shared__ __align__(8) uint64_t bars[2 * LT_STAGES + 4];
@@ -122,7 +106,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
         // ================================ epilogue =========================================================
         // A warp executes its instruction stream serially (well under one instruction per cycle), so one group of
         // four warps per accumulator slot drains every other tile: twice the epilogue throughput of a single group.
-        float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f};
+        float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f};                      // generic-width path: columns lane, lane + 32
+        float cs1[4] = {0.f, 0.f, 0.f, 0.f}, cs2[4] = {0.f, 0.f, 0.f, 0.f};  // 64-wide path: columns 4 (lane & 15) ..
         const uint32_t my_slot = warp >> 2;
         const int q = warp & 3;                       // TMEM lane quarter of this warp
         uint32_t it = 0;
@@ -131,8 +116,6 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
             if (slot != my_slot) continue;
             if (!mbar_wait<32>(&acc_full[slot], ph, abort_flag)) break;
             tc_fence_after();
-            const int r = tile * 128 + q * 32 + lane;
-            const bool row_ok = r < p.n_rows;
             float* stg = sm_stg + warp * (32 * LT_PITCH);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
@@ -160,19 +143,6 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
                     }
                     *reinterpret_cast<float4*>(stg + lane * LT_PITCH + c) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
-                if (p.col_stats != nullptr) {
-                    float sq[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = (row_ok && hf * 32 + j < p.n_out) ? v[j] : 0.f;
-                        v[j] = x;
-                        sq[j] = x * x;
-                    }
-                    transpose_reduce32(v, lane);
-                    transpose_reduce32(sq, lane);
-                    st1[hf] += v[0];
-                    st2[hf] += sq[0];
-                }
             }
             // copy the warp's 32 x 64 tile out with coalesced 128-bit stores (two rows per instruction)
             __syncwarp();
@@ -182,28 +152,70 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
                 char* dstp = reinterpret_cast<char*>(p.y + (int64_t)(row0 + (lane >> 4)) * p.ldy + (lane & 15) * 4);
                 const int64_t step = 2 * p.ldy * (int64_t)sizeof(float);
                 const float* sp = stg + (lane >> 4) * LT_PITCH + (lane & 15) * 4;
+                // the batch statistics ride on the copy-out: this lane owns four columns of every other row.
+                // Loads are issued eight at a time ahead of their uses (a per-row branch would serialise them).
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (2 * i < nvalid) *reinterpret_cast<float4*>(dstp) = *reinterpret_cast<const float4*>(sp);
-                    dstp += step;
-                    sp += 2 * LT_PITCH;
+                for (int i0 = 0; i0 < 16; i0 += 8) {
+                    float4 t[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const float4*>(sp + (i0 + i) * 2 * LT_PITCH);
+                    if (nvalid >= 31) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(dstp + (i0 + i) * step) = t[i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (2 * (i0 + i) < nvalid) *reinterpret_cast<float4*>(dstp + (i0 + i) * step) = t[i];
+                            else t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        cs1[0] += t[i].x; cs1[1] += t[i].y; cs1[2] += t[i].z; cs1[3] += t[i].w;
+                        cs2[0] = fmaf(t[i].x, t[i].x, cs2[0]); cs2[1] = fmaf(t[i].y, t[i].y, cs2[1]);
+                        cs2[2] = fmaf(t[i].z, t[i].z, cs2[2]); cs2[3] = fmaf(t[i].w, t[i].w, cs2[3]);
+                    }
                 }
             } else {
                 for (int e = lane; e < 32 * LT_F; e += 32) {
-                    const int rr = e >> 6, c = e & 63;
-                    if (row0 + rr < p.n_rows && c < p.n_out) p.y[(int64_t)(row0 + rr) * p.ldy + c] = stg[rr * LT_PITCH + c];
+                    const int rr = e >> 6, c = e & 63;          // c = lane or lane + 32
+                    if (row0 + rr < p.n_rows && c < p.n_out) {
+                        const float t = stg[rr * LT_PITCH + c];
+                        p.y[(int64_t)(row0 + rr) * p.ldy + c] = t;
+                        st1[c >> 5] += t;
+                        st2[c >> 5] = fmaf(t, t, st2[c >> 5]);
+                    }
                 }
             }
             __syncwarp();
         }
         if (p.col_stats != nullptr) {
+            // per-warp partial sums -> shared memory -> one fixed-order sum per CTA -> ONE fp64 atomic per column and
+            // CTA (same-address atomics serialise in L2: eight times fewer of them is worth ~8 us per launch)
+            float* red = sm_stg + warp * (32 * LT_PITCH);          // this warp's staging tile is free now
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int c = q * 32 + lane;
-                if (c < p.n_out) {
-                    atomicAdd(&p.col_stats[c], (double)st1[q]);
-                    atomicAdd(&p.col_stats[p.n_out + c], (double)st2[q]);
+            for (int u = 0; u < 4; ++u) {
+                cs1[u] += __shfl_xor_sync(GNM_FULL_MASK, cs1[u], 16);
+                cs2[u] += __shfl_xor_sync(GNM_FULL_MASK, cs2[u], 16);
+            }
+            __syncwarp();
+            // generic-width path holds columns lane / lane + 32 in st1, st2; the 64-wide path 4 (lane & 15) + u in cs
+            red[lane] = st1[0]; red[32 + lane] = st1[1]; red[64 + lane] = st2[0]; red[96 + lane] = st2[1];
+            __syncwarp();
+            if (lane < 16) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    red[lane * 4 + u] += cs1[u];
+                    red[64 + lane * 4 + u] += cs2[u];
                 }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(LT_EPI_WARPS * 32) : "memory");
+            if (tid < 2 * LT_F) {
+                float a = 0.f;
+#pragma unroll
+                for (int w = 0; w < LT_EPI_WARPS; ++w) a += sm_stg[w * (32 * LT_PITCH) + tid];
+                const int c = tid & (LT_F - 1);
+                if (c < p.n_out) atomicAdd(&p.col_stats[(tid >> 6) * p.n_out + c], (double)a);
             }
         }
     } else if (warp == LT_MMA_WARP) {
