@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             for (int mt = 0; mt < n_mt; ++mt, ++acc_it) {
                 const uint32_t slot = acc_it & 1, ph = (acc_it >> 1) & 1;
                 if (TC_EPI_WARPS == 8 && slot != my_slot) continue;
-                if (!mbar_wait(&acc_full[slot], ph, abort_flag, DBG ? &w_acc : nullptr)) break;
+                if (!mbar_wait<32>(&acc_full[slot], ph, abort_flag, DBG ? &w_acc : nullptr)) break;
                 tc_fence_after();
                 const int row0 = mt * 128 + q * 32;              // first row (within the graph) of this warp's slice
                 const int r = row0 + lane;
@@ -240,71 +240,102 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         long long w_pe = 0, c_st = 0, c_fence = 0, c_arr = 0, c_bconv = 0, c_bload = 0;
         (void)c_fence; (void)c_bload;
         const long long t_role = clock64();
-        for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, ++b_it) {
-            const int gi = item / p.n_slabs, slab = item % p.n_slabs;
-            const int n0 = p.node_off[gi], n = p.node_off[gi + 1] - n0;
-            const int f0 = slab * TC_SLAB;
-            const int n_mt = (n + 127) >> 7;
-            const int ksteps_total = (n + 15) >> 4;
-            const int n_kc = (ksteps_total + 3) >> 2;
-            const int words = (n + 31) >> 5;
-            const uint32_t* __restrict__ bm = reinterpret_cast<const uint32_t*>(p.bitmap_addr[gi]);
-            constexpr int MAXC = (TC_MAX_NODES + TC_KC - 1) / TC_KC;      // 7 chunks of 64 columns
-            constexpr int MYC = (MAXC + 1) / 2;                           // chunks one group handles per tile
-            // bitmap words (two per chunk) of this thread's row for the chunks its group produces in row tile mt
-            auto load_words = [&](int mt, uint32_t it0, uint32_t (&w)[MYC][2]) {
-                const int r = mt * 128 + arow;
-                const bool rok = mt < n_mt && r < n;
-                const uint32_t* rowbits = bm + (size_t)(rok ? r : 0) * words;
-                const int first = ((it0 & 1) == (uint32_t)grp) ? 0 : 1;  // first chunk of the tile owned by this group
+        // Item parameters are fetched one item ahead (their dependent global loads - node offsets, bitmap address -
+        // would otherwise stall every item start), and the next item's first bitmap words and first feature chunk are
+        // requested during the current item's last row tile, when the B registers are idle.
+        struct ItemP { int n0, n, f0, n_mt, n_kc, ksteps_total, words; const uint32_t* bm; };
+        auto fetch_item = [&](int item, ItemP& q) {
+            if (item < n_items) {
+                const int gi = item / p.n_slabs, slab = item % p.n_slabs;
+                q.n0 = p.node_off[gi];
+                q.n = p.node_off[gi + 1] - q.n0;
+                q.f0 = slab * TC_SLAB;
+                q.bm = reinterpret_cast<const uint32_t*>(p.bitmap_addr[gi]);
+            } else {
+                q.n0 = 0; q.n = 0; q.f0 = 0; q.bm = nullptr;
+            }
+        };
+        auto derive_item = [&](ItemP& q) {
+            q.n_mt = (q.n + 127) >> 7;
+            q.ksteps_total = (q.n + 15) >> 4;
+            q.n_kc = (q.ksteps_total + 3) >> 2;
+            q.words = (q.n + 31) >> 5;
+        };
+        constexpr int MAXC = (TC_MAX_NODES + TC_KC - 1) / TC_KC;      // 7 chunks of 64 columns
+        constexpr int MYC = (MAXC + 1) / 2;                           // chunks one group handles per tile
+        // bitmap words (two per chunk) of this thread's row for the chunks its group produces in row tile mt
+        auto load_words = [&](const ItemP& q, int mt, uint32_t it0, uint32_t (&w)[MYC][2]) {
+            const int r = mt * 128 + arow;
+            const bool rok = mt < q.n_mt && r < q.n;
+            const uint32_t* rowbits = q.bm + (size_t)(rok ? r : 0) * q.words;
+            const int first = ((it0 & 1) == (uint32_t)grp) ? 0 : 1;  // first chunk of the tile owned by this group
 #pragma unroll
-                for (int c = 0; c < MYC; ++c) {
-                    const int kc = first + 2 * c;
-                    w[c][0] = (rok && kc < n_kc && 2 * kc < words) ? __ldg(rowbits + 2 * kc) : 0u;
-                    w[c][1] = (rok && kc < n_kc && 2 * kc + 1 < words) ? __ldg(rowbits + 2 * kc + 1) : 0u;
-                }
-            };
-            // A stage belongs to ONE group of four warps (the groups alternate stages and run as two independent
-            // pipelines): the owner expands the adjacency tile and, during the first row tile, also converts the
-            // 64 feature rows of that chunk into the three B planes.
-            const int gtid = ptid & 127;
-            float4 bq[8];
-            auto load_b = [&](int kc) {
+            for (int c = 0; c < MYC; ++c) {
+                const int kc = first + 2 * c;
+                w[c][0] = (rok && kc < q.n_kc && 2 * kc < q.words) ? __ldg(rowbits + 2 * kc) : 0u;
+                w[c][1] = (rok && kc < q.n_kc && 2 * kc + 1 < q.words) ? __ldg(rowbits + 2 * kc + 1) : 0u;
+            }
+        };
+        // A stage belongs to ONE group of four warps (the groups alternate stages and run as two independent
+        // pipelines): the owner expands the adjacency tile and, during the first row tile, also converts the
+        // 64 feature rows of that chunk into the three B planes.
+        const int gtid = ptid & 127;
+        float4 bq[8];
+        auto load_b = [&](const ItemP& q, int kc) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int idx = gtid + u * 128;                  // 64 nodes x 16 float4
-                    const int k = kc * TC_KC + (idx >> 4), c4 = idx & 15;
-                    const int col = f0 + c4 * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (kc < n_kc && k < n && col < p.n_feat) {
-                        const int jr = n0 + k;
-                        const int64_t sr = p.src_map ? (int64_t)p.src_map[jr] : (int64_t)jr;
-                        v = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
-                        if (p.mode == 2) {
-                            const float w = 1.f / (float)(p.rowptr[jr + 1] - p.rowptr[jr]);
-                            v.x *= w; v.y *= w; v.z *= w; v.w *= w;
-                        }
+            for (int u = 0; u < 8; ++u) {
+                const int idx = gtid + u * 128;                  // 64 nodes x 16 float4
+                const int k = kc * TC_KC + (idx >> 4), c4 = idx & 15;
+                const int col = q.f0 + c4 * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kc < q.n_kc && k < q.n && col < p.n_feat) {
+                    const int jr = q.n0 + k;
+                    const int64_t sr = p.src_map ? (int64_t)p.src_map[jr] : (int64_t)jr;
+                    v = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
+                    if (p.mode == 2) {
+                        const float w = 1.f / (float)(p.rowptr[jr + 1] - p.rowptr[jr]);
+                        v.x *= w; v.y *= w; v.z *= w; v.w *= w;
                     }
-                    bq[u] = v;
                 }
-            };
-            uint32_t w_cur[MYC][2], w_nxt[MYC][2];
-            load_words(0, a_it, w_cur);
-            load_b(((a_it & 1) == (uint32_t)grp) ? 0 : 1);
+                bq[u] = v;
+            }
+        };
+        ItemP cur, nxt;
+        fetch_item(blockIdx.x, cur);
+        derive_item(cur);
+        bool preloaded = false;                  // w_cur / bq already hold this item's first words / first chunk
+        uint32_t w_cur[MYC][2], w_nxt[MYC][2];
+        for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, ++b_it) {
+            fetch_item(item + gridDim.x, nxt);   // in flight during this whole item
+            const int n = cur.n, n_mt = cur.n_mt, n_kc = cur.n_kc, ksteps_total = cur.ksteps_total;
+            if (!preloaded) {
+                load_words(cur, 0, a_it, w_cur);
+                load_b(cur, ((a_it & 1) == (uint32_t)grp) ? 0 : 1);
+            }
+            preloaded = false;
             bool first_b = true;
             for (int mt = 0; mt < n_mt && ok; ++mt) {
-                load_words(mt + 1, a_it + n_kc, w_nxt);
+                if (mt == n_mt - 1 && mt > 0 && item + (int)gridDim.x < n_items) {
+                    // last row tile: the B registers are idle (conversion happens in tile 0 only)
+                    derive_item(nxt);
+                    const uint32_t it_next = a_it + n_kc;                 // ring position at the next item's start
+                    load_words(nxt, 0, it_next, w_nxt);
+                    load_b(nxt, ((it_next & 1) == (uint32_t)grp) ? 0 : 1);
+                    preloaded = true;
+                } else {
+                    load_words(cur, mt + 1, a_it + n_kc, w_nxt);
+                }
                 const int first = ((a_it & 1) == (uint32_t)grp) ? 0 : 1;
 #pragma unroll 1
                 for (int kc = 0; kc < n_kc; ++kc, ++a_it) {
                     if (((kc - first) & 1) != 0) continue;          // the other group's stage
                     const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
-                    if (!(ok = mbar_wait(&a_empty[s], aph ^ 1, abort_flag, DBG ? &w_pe : nullptr))) break;
+                    if (!(ok = mbar_wait<32>(&a_empty[s], aph ^ 1, abort_flag, DBG ? &w_pe : nullptr))) break;
                     if (mt == 0) {
                         // the previous item's MMAs on these B rows retired at least TC_STAGES stages ago, unless
                         // that item had fewer k chunks than the ring: then wait for its explicit b_free commit
                         if (first_b && prev_nkc < TC_STAGES) {
-                            if (!(ok = mbar_wait(b_free, (b_it & 1) ^ 1, abort_flag))) break;
+                            if (!(ok = mbar_wait<32>(b_free, (b_it & 1) ^ 1, abort_flag))) break;
                         }
                         first_b = false;
                         const long long tb0 = DBG ? clock64() : 0;
@@ -321,7 +352,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                             *reinterpret_cast<uint2*>(dstp + 8 * (size_t)b_ncore_stride) = make_uint2(m0, m1);
                             *reinterpret_cast<uint2*>(dstp + 16 * (size_t)b_ncore_stride) = make_uint2(l0, l1);
                         }
-                        if (kc + 2 < n_kc) load_b(kc + 2);
+                        if (kc + 2 < n_kc) load_b(cur, kc + 2);
                         fence_async_smem();
                         if (DBG) c_bconv += clock64() - tb0;
                     }
@@ -355,6 +386,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 for (int c = 0; c < MYC; ++c) { w_cur[c][0] = w_nxt[c][0]; w_cur[c][1] = w_nxt[c][1]; }
             }
             prev_nkc = n_kc;
+            if (!preloaded) derive_item(nxt);
+            cur = nxt;
         }
         if (DBG && ptid == 0) {
             p.dbg[blockIdx.x * 16 + 5] = clock64() - t_role; p.dbg[blockIdx.x * 16 + 6] = w_pe;
