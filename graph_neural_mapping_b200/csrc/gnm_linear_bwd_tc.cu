@@ -377,16 +377,20 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
 // planes sit side by side (hi | mid | lo, N = 192) so the six kept products take three MMAs per 16-row k-step:
 // A_hi x [hi|mid|lo], A_mid x [hi|mid], A_lo x [hi]; the three 64-column groups of the accumulator are summed in
 // the epilogue. Column sums are accumulated by the producers on the way.
-constexpr int WG_ROWS = 64;                          // rows (reduction length) per stage
+constexpr int WG_ROWS = 32;                          // rows (reduction length) per stage
 constexpr int WG_STAGES = 3;
+constexpr int WG_DEPTH = 4;                          // fp32 landing ring: chunks requested ahead of their conversion
 constexpr int WG_KCORES = WG_ROWS / 8;
 constexpr int WG_CORE_STRIDE = WG_KCORES * 128 + 16; // stride between 8-wide m / n cores (padded: conflict-free fill)
 constexpr int WG_A_PLANE = 16 * WG_CORE_STRIDE;      // 128 m = 16 cores
 constexpr int WG_B_BYTES = 24 * WG_CORE_STRIDE;      // 192 n = 24 cores (three planes side by side)
 constexpr int WG_STAGE_BYTES = 3 * WG_A_PLANE + WG_B_BYTES;
 constexpr int WG_PROD_WARPS = 8;
+constexpr int WG_RPT = WG_ROWS * 16 / (WG_PROD_WARPS * 32);   // rows per producer thread and chunk
+constexpr int WG_PT = WG_PROD_WARPS * 32;
 constexpr int WG_THREADS = (WG_PROD_WARPS + 1) * 32;
-constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024;
+constexpr int WG_LAND_CHUNK = 3 * WG_RPT * WG_PT * 16;      // per chunk: 3 float4 (three streams) per producer thread and row
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + WG_DEPTH * WG_LAND_CHUNK + 1024;
 
 struct WgradTcParams {
     const float* dy; int64_t lddy;
@@ -437,8 +441,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) linear_wgrad_tc_kernel(const Wg
 
     if (warp < WG_PROD_WARPS) {
         // ================================ producers ============================================================
-        // thread -> (row k = e >> 4, float4 column c4 = e & 15) for e = tid + 256 j; c4 is fixed per thread
-        const int c4 = tid & 15, kr0 = tid >> 4;          // rows kr0, kr0+16, kr0+32, kr0+48 of the stage
+        // thread -> WG_RPT rows (kr0 + j * WG_PT / 16) of the 32-row chunk, float4 column c4 (fixed per thread), three streams.
+        // Global -> shared "landing" slots with cp.async, WG_DEPTH - 1 chunks ahead of their conversion. Each thread
+        // reads back exactly the slots it requested, so the only synchronisation is its own cp.async group count -
+        // unlike a register prefetch, whose loads all share the warp's scoreboards (measured: a deeper register ring
+        // gained nothing), this keeps 3 chunks = 72 KB per SM genuinely in flight.
+        const int c4 = tid & 15, kr0 = tid >> 4;
         const bool fast = p.n_out == BT_F && p.n_in == BT_F && ((p.lddy | p.ldz | p.ldx) & 3) == 0 &&
                           gnm_aligned16(p.dy) && gnm_aligned16(p.z) && gnm_aligned16(p.x);
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -450,107 +458,108 @@ __global__ void __launch_bounds__(WG_THREADS, 1) linear_wgrad_tc_kernel(const Wg
             if (c + 3 < p.n_in) { sc.w = p.in_scale[c + 3]; sh.w = p.in_shift[c + 3]; }
         }
         float4 s_dy = make_float4(0.f, 0.f, 0.f, 0.f), s_z = s_dy, s_a = s_dy;
-        struct RowRegs { float4 dy[4], z[4], x[4]; };
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        // register prefetch, one chunk ahead. Deeper register rings (DEPTH 2, 3) were measured to gain nothing: the
-        // loads of all in-flight chunks share the warp's few scoreboards, so waiting for the oldest chunk drains them all.
-        auto load_chunk = [&](RowRegs& r, int chunk) {
-            const int r0 = chunk * WG_ROWS + kr0;
-            if (fast && r0 + 48 < p.n_rows) {
-                const float4* pdy = reinterpret_cast<const float4*>(p.dy + (int64_t)r0 * p.lddy) + c4;
-                const float4* pz = reinterpret_cast<const float4*>(p.z + (int64_t)r0 * p.ldz) + c4;
-                const float4* px = reinterpret_cast<const float4*>(p.x + (int64_t)r0 * p.ldx) + c4;
-                const int64_t sdy = 4 * p.lddy, sz = 4 * p.ldz, sx = 4 * p.ldx;     // 16 rows, in float4 units
+        unsigned char* land = wg_smem + (size_t)WG_STAGES * WG_STAGE_BYTES;
+        float4* my_land = reinterpret_cast<float4*>(land) + tid;                  // slot (d, q) at my_land[(d * 3 * WG_RPT + q) * WG_PT]
+        const uint32_t my_land_u32 = smem_u32(my_land);
+        const int G = gridDim.x;
+        auto request_chunk = [&](int chunk, int d) {
+            if (chunk < n_chunks) {
+                const int r0 = chunk * WG_ROWS + kr0;
+                if (fast) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    r.dy[j] = __ldg(pdy); pdy += sdy;
-                    r.z[j] = __ldg(pz); pz += sz;
-                    r.x[j] = __ldg(px); px += sx;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int rr = r0 + 16 * j;
-                    const bool okr = rr < p.n_rows;
-                    float t[12];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int c = c4 * 4 + u;
-                        t[u] = (okr && c < p.n_out) ? p.dy[(int64_t)rr * p.lddy + c] : 0.f;
-                        t[4 + u] = (okr && c < p.n_out) ? p.z[(int64_t)rr * p.ldz + c] : 0.f;
-                        t[8 + u] = (okr && c < p.n_in) ? p.x[(int64_t)rr * p.ldx + c] : 0.f;
+                    for (int j = 0; j < WG_RPT; ++j) {
+                        const int r = r0 + (WG_PT / 16) * j;
+                        const bool okr = r < p.n_rows;
+                        const int nbytes = okr ? 16 : 0;
+                        const int64_t rr = okr ? r : 0;
+                        const uint32_t dst = my_land_u32 + (uint32_t)((d * 3 * WG_RPT + j * 3) * WG_PT * 16);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst),
+                                     "l"(p.dy + rr * p.lddy + c4 * 4), "r"(nbytes) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + WG_PT * 16),
+                                     "l"(p.z + rr * p.ldz + c4 * 4), "r"(nbytes) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 2 * WG_PT * 16),
+                                     "l"(p.x + rr * p.ldx + c4 * 4), "r"(nbytes) : "memory");
                     }
-                    r.dy[j] = make_float4(t[0], t[1], t[2], t[3]);
-                    r.z[j] = make_float4(t[4], t[5], t[6], t[7]);
-                    r.x[j] = make_float4(t[8], t[9], t[10], t[11]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < WG_RPT; ++j) {
+                        const int r = r0 + (WG_PT / 16) * j;
+                        const bool okr = r < p.n_rows;
+                        float t[12];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int c = c4 * 4 + u;
+                            t[u] = (okr && c < p.n_out) ? p.dy[(int64_t)r * p.lddy + c] : 0.f;
+                            t[4 + u] = (okr && c < p.n_out) ? p.z[(int64_t)r * p.ldz + c] : 0.f;
+                            t[8 + u] = (okr && c < p.n_in) ? p.x[(int64_t)r * p.ldx + c] : 0.f;
+                        }
+                        my_land[(d * 3 * WG_RPT + j * 3) * WG_PT] = make_float4(t[0], t[1], t[2], t[3]);
+                        my_land[(d * 3 * WG_RPT + j * 3 + 1) * WG_PT] = make_float4(t[4], t[5], t[6], t[7]);
+                        my_land[(d * 3 * WG_RPT + j * 3 + 2) * WG_PT] = make_float4(t[8], t[9], t[10], t[11]);
+                    }
                 }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");      // one group per chunk slot, even when empty
         };
-        auto convert_chunk = [&](const RowRegs& r, int chunk, unsigned char* st) {
-            const int nvalid = p.n_rows - chunk * WG_ROWS - kr0;              // row j of this thread is valid iff 16 j < nvalid
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 vdy = r.dy[j], vz = r.z[j];
-                float4 a = r.x[j];
+        for (int d = 0; d < WG_DEPTH - 1; ++d) request_chunk(blockIdx.x + d * G, d);
+        uint32_t it = 0;
+        bool ok = true;
+        for (int chunk = blockIdx.x; chunk < n_chunks && ok; chunk += G, ++it) {
+            const uint32_t s = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
+            const int d = it % WG_DEPTH;
+            unsigned char* st = wg_smem + (size_t)s * WG_STAGE_BYTES;
+            // slot (it + DEPTH - 1) % DEPTH was consumed by this thread in the previous iteration: safe to refill
+            request_chunk(chunk + (WG_DEPTH - 1) * G, (it + WG_DEPTH - 1) % WG_DEPTH);
+            asm volatile("cp.async.wait_group %0;" ::"n"(WG_DEPTH - 1) : "memory");
+            float4 vdy[WG_RPT], vz[WG_RPT], va[WG_RPT];
+            const int nvalid = p.n_rows - chunk * WG_ROWS - kr0;              // row j of this thread is valid iff (WG_PT / 16) j < nvalid
+#pragma unroll
+            for (int j = 0; j < WG_RPT; ++j) {
+                vdy[j] = my_land[(d * 3 * WG_RPT + j * 3) * WG_PT];
+                vz[j] = my_land[(d * 3 * WG_RPT + j * 3 + 1) * WG_PT];
+                float4 a = my_land[(d * 3 * WG_RPT + j * 3 + 2) * WG_PT];
                 if (act) {
-                    const bool okr = 16 * j < nvalid;
+                    const bool okr = (WG_PT / 16) * j < nvalid;
                     a.x = okr ? fmaxf(fmaf(a.x, sc.x, sh.x), 0.f) : 0.f;
                     a.y = okr ? fmaxf(fmaf(a.y, sc.y, sh.y), 0.f) : 0.f;
                     a.z = okr ? fmaxf(fmaf(a.z, sc.z, sh.z), 0.f) : 0.f;
                     a.w = okr ? fmaxf(fmaf(a.w, sc.w, sh.w), 0.f) : 0.f;
                 }
-                const int k = kr0 + 16 * j;
+                va[j] = a;
+            }
+            if (!(ok = mbar_wait<32>(&empty[s], ph ^ 1, abort_flag))) break;
+#pragma unroll
+            for (int j = 0; j < WG_RPT; ++j) {
+                const int k = kr0 + (WG_PT / 16) * j;
                 const int off = (c4 >> 1) * WG_CORE_STRIDE + (k >> 3) * 128 + (k & 7) * 16 + (c4 & 1) * 8;
                 uint32_t h0, m0, l0, h1, m1, l1;
-                split3x2(vdy.x, vdy.y, h0, m0, l0);
-                split3x2(vdy.z, vdy.w, h1, m1, l1);
+                split3x2(vdy[j].x, vdy[j].y, h0, m0, l0);
+                split3x2(vdy[j].z, vdy[j].w, h1, m1, l1);
                 *reinterpret_cast<uint2*>(st + off) = make_uint2(h0, h1);
                 *reinterpret_cast<uint2*>(st + WG_A_PLANE + off) = make_uint2(m0, m1);
                 *reinterpret_cast<uint2*>(st + 2 * WG_A_PLANE + off) = make_uint2(l0, l1);
-                split3x2(vz.x, vz.y, h0, m0, l0);
-                split3x2(vz.z, vz.w, h1, m1, l1);
+                split3x2(vz[j].x, vz[j].y, h0, m0, l0);
+                split3x2(vz[j].z, vz[j].w, h1, m1, l1);
                 const int offz = off + 8 * WG_CORE_STRIDE;                 // z channels: m = 64 + c
                 *reinterpret_cast<uint2*>(st + offz) = make_uint2(h0, h1);
                 *reinterpret_cast<uint2*>(st + WG_A_PLANE + offz) = make_uint2(m0, m1);
                 *reinterpret_cast<uint2*>(st + 2 * WG_A_PLANE + offz) = make_uint2(l0, l1);
-                split3x2(a.x, a.y, h0, m0, l0);
-                split3x2(a.z, a.w, h1, m1, l1);
+                split3x2(va[j].x, va[j].y, h0, m0, l0);
+                split3x2(va[j].z, va[j].w, h1, m1, l1);
                 unsigned char* sb = st + 3 * WG_A_PLANE + off;
                 *reinterpret_cast<uint2*>(sb) = make_uint2(h0, h1);
                 *reinterpret_cast<uint2*>(sb + 8 * WG_CORE_STRIDE) = make_uint2(m0, m1);
                 *reinterpret_cast<uint2*>(sb + 16 * WG_CORE_STRIDE) = make_uint2(l0, l1);
-                s_dy.x += vdy.x; s_dy.y += vdy.y; s_dy.z += vdy.z; s_dy.w += vdy.w;
-                s_z.x += vz.x; s_z.y += vz.y; s_z.z += vz.z; s_z.w += vz.w;
-                s_a.x += a.x; s_a.y += a.y; s_a.z += a.z; s_a.w += a.w;
+                s_dy.x += vdy[j].x; s_dy.y += vdy[j].y; s_dy.z += vdy[j].z; s_dy.w += vdy[j].w;
+                s_z.x += vz[j].x; s_z.y += vz[j].y; s_z.z += vz[j].z; s_z.w += vz[j].w;
+                s_a.x += va[j].x; s_a.y += va[j].y; s_a.z += va[j].z; s_a.w += va[j].w;
             }
-        };
-        constexpr int DEPTH = 1;
-        RowRegs rr[DEPTH];
-        const int G = gridDim.x;
-#pragma unroll
-        for (int d = 0; d < DEPTH; ++d) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rr[d].dy[j] = rr[d].z[j] = rr[d].x[j] = zero4;
-            if ((int)blockIdx.x + d * G < n_chunks) load_chunk(rr[d], blockIdx.x + d * G);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
         }
-        uint32_t it = 0;
-        bool ok = true;
-        for (int chunk = blockIdx.x; chunk < n_chunks && ok; chunk += DEPTH * G) {
-#pragma unroll
-            for (int d = 0; d < DEPTH; ++d) {
-                const int ch = chunk + d * G;
-                if (ch >= n_chunks) break;
-                const uint32_t s = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
-                unsigned char* st = wg_smem + (size_t)s * WG_STAGE_BYTES;
-                if (!(ok = mbar_wait<32>(&empty[s], ph ^ 1, abort_flag))) break;
-                convert_chunk(rr[d], ch, st);
-                if (ch + DEPTH * G < n_chunks) load_chunk(rr[d], ch + DEPTH * G);
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
-                ++it;
-            }
-        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         // column sums: lanes l and l^16 share c4 -> fold, then one shared atomic per column and warp
         float v[12] = {s_dy.x, s_dy.y, s_dy.z, s_dy.w, s_z.x, s_z.y, s_z.z, s_z.w, s_a.x, s_a.y, s_a.z, s_a.w};
 #pragma unroll
