@@ -134,6 +134,63 @@ dgi_score_bwd_kernel(const float* __restrict__ h_all, int64_t layer_stride, int 
     }
 }
 
+// 64-wide fast path of the kernel above: register accumulators (one float4 per layer and lane), 128-bit streaming
+// loads, two rows per warp instruction; shared memory only for the final 16-way merge.
+template <int NL>
+__global__ void __launch_bounds__(256)
+dgi_score_bwd_vec_kernel(const float* __restrict__ h_all, int64_t layer_stride, int64_t ldh, int n_rows,
+                         const float* __restrict__ d_out, const float* __restrict__ neg_table,
+                         const int32_t* __restrict__ neg_idx, const int32_t* __restrict__ node_off,
+                         float* __restrict__ du, float* __restrict__ s2, double* __restrict__ d_bias) {
+    constexpr int F = 64, NH = NL * F;
+    __shared__ __align__(16) float part[8][NH];
+    __shared__ float red[2][8];
+    const int g = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, c4 = lane & 15;
+    const int r0 = node_off[g], r1 = node_off[g + 1];
+    float4 acc[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) acc[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sum1 = 0.f, sum2 = 0.f;
+    for (int r = r0 + warp * 2 + half; r < r1; r += 16) {
+        const float d1 = d_out[r];
+        if (c4 == 0) { sum1 += d1; sum2 += d_out[n_rows + r]; }
+        const float* hr = h_all + (int64_t)r * ldh + c4 * 4;
+        float4 hv[NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) hv[l] = ld_stream_f4(hr + l * layer_stride);
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            acc[l].x = fmaf(d1, hv[l].x, acc[l].x); acc[l].y = fmaf(d1, hv[l].y, acc[l].y);
+            acc[l].z = fmaf(d1, hv[l].z, acc[l].z); acc[l].w = fmaf(d1, hv[l].w, acc[l].w);
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        acc[l].x += __shfl_xor_sync(GNM_FULL_MASK, acc[l].x, 16); acc[l].y += __shfl_xor_sync(GNM_FULL_MASK, acc[l].y, 16);
+        acc[l].z += __shfl_xor_sync(GNM_FULL_MASK, acc[l].z, 16); acc[l].w += __shfl_xor_sync(GNM_FULL_MASK, acc[l].w, 16);
+        if (half == 0) *reinterpret_cast<float4*>(&part[warp][l * F + c4 * 4]) = acc[l];
+    }
+    sum1 = warp_sum(sum1);
+    sum2 = warp_sum(sum2);
+    if (lane == 0) { red[0][warp] = sum1; red[1][warp] = sum2; }
+    __syncthreads();
+    float t1 = 0.f, t2 = 0.f;
+    for (int w = 0; w < 8; ++w) { t1 += red[0][w]; t2 += red[1][w]; }
+    const float* nr = neg_table + (int64_t)neg_idx[g] * NH;
+    for (int i = threadIdx.x; i < NH; i += blockDim.x) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += part[w][i];
+        du[(int64_t)g * NH + i] = fmaf(t2, nr[i], a);
+    }
+    if (threadIdx.x == 0) {
+        s2[g] = t2;
+        if (d_bias != nullptr) atomicAdd(d_bias, (double)t1 + (double)t2);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 rowdot_score_kernel(const float* __restrict__ h, int64_t ldh, int n_rows, int n_feat, const float* __restrict__ u,
                     int64_t ldu, int rows_per_graph, const float* __restrict__ bias, const float* __restrict__ s_bias,
@@ -200,6 +257,21 @@ extern "C" int gnm_dgi_score_bwd(const float* h_all, int64_t layer_stride, int n
     if (n_layers < 0 || n_feat < 0 || n_rows < 0 || n_graphs < 0) return GNM_ERR_BAD_ARG;
     if (n_graphs == 0 || n_rows == 0) return GNM_OK;
     if (!h_all || !d_out || !neg_table || !neg_idx || !node_off || !du || !s2) return GNM_ERR_BAD_ARG;
+    if (n_feat == 64 && n_layers >= 1 && n_layers <= 5 && (ldh & 3) == 0 && (layer_stride & 3) == 0 && gnm_aligned16(h_all)) {
+#define GNM_DGI_BWD(NL) \
+    dgi_score_bwd_vec_kernel<NL><<<n_graphs, 256, 0, gnm_cast_stream(stream)>>>(h_all, layer_stride, ldh, n_rows, d_out, \
+                                                                             neg_table, neg_idx, node_off, du, s2, d_bias)
+        switch (n_layers) {
+            case 1: GNM_DGI_BWD(1); break;
+            case 2: GNM_DGI_BWD(2); break;
+            case 3: GNM_DGI_BWD(3); break;
+            case 4: GNM_DGI_BWD(4); break;
+            default: GNM_DGI_BWD(5); break;
+        }
+#undef GNM_DGI_BWD
+        GNM_RETURN_IF_LAUNCH_FAILED();
+        return GNM_OK;
+    }
     const size_t smem = (size_t)8 * n_layers * n_feat * 4;
     if (smem > 200 * 1024) return GNM_ERR_TOO_LARGE;
     if (smem > 48 * 1024) {

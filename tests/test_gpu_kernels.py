@@ -263,7 +263,8 @@ def test_batchnorm_pieces(f):
     assert_close(st2[f:], gg, 1e-4, "dgamma")
 
 
-@pytest.mark.parametrize("L,f,n,b", [(3, 8, 12, 4), (5, 64, 48, 6), (2, 12, 16, 5), (5, 64, 400, 3)])
+@pytest.mark.parametrize("L,f,n,b", [(3, 8, 12, 4), (5, 64, 48, 6), (2, 12, 16, 5), (5, 64, 400, 3), (3, 64, 37, 5), (1, 64, 5, 2),
+                                     (4, 64, 129, 2), (2, 64, 1, 3)])
 def test_dgi_scores(L, f, n, b):
     torch.manual_seed(L * f)
     m = n * b
