@@ -2,6 +2,7 @@
 // weight gradient, BatchNorm statistics / finalize / backward.
 // Reference: models/mlp.py:40-49, models/graphcnn.py:162-166,185-190 (nn.Linear, nn.BatchNorm1d, ReLU).
 #include "gnm_common.cuh"
+#include "gnm_p2p.cuh"
 
 namespace {
 
@@ -225,11 +226,13 @@ col_stats_kernel(const float* __restrict__ x, int64_t ldx, int n_rows, int n_fea
     }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ col_stats, double count, const float* __restrict__ gamma,
+__global__ void bn_finalize_kernel(double* col_stats, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    int64_t* __restrict__ nbt, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ mean_o, float* __restrict__ rstd_o, int n_feat) {
+                                   float* __restrict__ mean_o, float* __restrict__ rstd_o, int n_feat, const P2PArgs comm) {
+    // data parallel: the sums of all ranks are exchanged over peer memory right here (single-CTA launches only)
+    if (comm.world > 1) p2p_allreduce_block(col_stats, 2 * n_feat, comm);
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && nbt != nullptr) *nbt += 1;
     if (c >= n_feat) return;
@@ -567,15 +570,28 @@ extern "C" int gnm_col_stats(const float* x, int64_t ldx, int n_rows, int n_feat
     return GNM_OK;
 }
 
-extern "C" int gnm_bn_finalize(const double* col_stats, double count, const float* gamma, const float* beta, float eps,
+int gnm_p2p_abort_flag_mlp(int* aborted) {
+    int v = 0, zero = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&v, g_p2p_abort, sizeof(int));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(g_p2p_abort, &zero, sizeof(int));
+    if (aborted) *aborted |= v;
+    return e == cudaSuccess ? GNM_OK : (int)e;
+}
+
+extern "C" int gnm_bn_finalize(double* col_stats, double count, const float* gamma, const float* beta, float eps,
                                float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
-                               float* scale, float* shift, float* mean, float* rstd, int n_feat, gnm_stream_t stream) {
+                               float* scale, float* shift, float* mean, float* rstd, int n_feat,
+                               const gnm_p2p_comm* comm, gnm_stream_t stream) {
     if (n_feat < 0 || count <= 0.0) return GNM_ERR_BAD_ARG;
     if (n_feat == 0) return GNM_OK;
     if (!col_stats || !scale || !shift || !mean || !rstd) return GNM_ERR_BAD_ARG;
+    P2PArgs pa;
+    const int prc = p2p_args(comm, 2 * n_feat, &pa);      // 2 n_feat <= 256 doubles: the launch below is one CTA
+    if (prc < 0) return prc;
     bn_finalize_kernel<<<(n_feat + 127) / 128, 128, 0, gnm_cast_stream(stream)>>>(
         col_stats, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, scale, shift, mean,
-        rstd, n_feat);
+        rstd, n_feat, pa);
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;
 }

@@ -12,6 +12,7 @@
 // with m1 = sum(dy)/count, m2 = sum(dy*xhat)/count; eval: cA = g*rstd, cB = cC = 0).
 // fp32 FFMA; F_out, F_in <= 64 (zero padded); persistent CTAs keep their dW tile in registers across row tiles.
 #include "gnm_common.cuh"
+#include "gnm_p2p.cuh"
 
 namespace {
 
@@ -224,9 +225,11 @@ __global__ void __launch_bounds__(256, 2) linear_bwd_kernel(const LinBwdParams p
     }
 }
 
-__global__ void bn_bwd_coeffs_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
+__global__ void bn_bwd_coeffs_kernel(double* stats, double count, const float* __restrict__ gamma,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
-                                     float* __restrict__ coef, int n_feat) {
+                                     float* __restrict__ coef, int n_feat, const P2PArgs comm) {
+    // data parallel: [sum dy, sum dy*xhat] of all ranks, exchanged over peer memory right here (single-CTA launches only)
+    if (comm.world > 1 && stats != nullptr) p2p_allreduce_block(stats, 2 * n_feat, comm);
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_feat) return;
     const float g = (gamma ? gamma[c] : 1.f) * rstd[c];
@@ -243,13 +246,26 @@ __global__ void bn_bwd_coeffs_kernel(const double* __restrict__ stats, double co
 
 }  // namespace
 
-extern "C" int gnm_bn_bwd_coeffs(const double* stats, double count, const float* gamma, const float* mean,
-                                 const float* rstd, float* coef, int n_feat, gnm_stream_t stream) {
+int gnm_p2p_abort_flag_mlp_bwd(int* aborted) {
+    int v = 0, zero = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&v, g_p2p_abort, sizeof(int));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(g_p2p_abort, &zero, sizeof(int));
+    if (aborted) *aborted |= v;
+    return e == cudaSuccess ? GNM_OK : (int)e;
+}
+
+extern "C" int gnm_bn_bwd_coeffs(double* stats, double count, const float* gamma, const float* mean,
+                                 const float* rstd, float* coef, int n_feat, const gnm_p2p_comm* comm,
+                                 gnm_stream_t stream) {
     if (n_feat < 0 || (stats != nullptr && count <= 0.0)) return GNM_ERR_BAD_ARG;
     if (n_feat == 0) return GNM_OK;
     if (!rstd || !coef || (stats != nullptr && !mean)) return GNM_ERR_BAD_ARG;
+    P2PArgs pa;
+    const int prc = p2p_args(comm, 2 * n_feat, &pa);
+    if (prc < 0) return prc;
     bn_bwd_coeffs_kernel<<<(n_feat + 127) / 128, 128, 0, gnm_cast_stream(stream)>>>(stats, count, gamma, mean, rstd,
-                                                                                    coef, n_feat);
+                                                                                    coef, n_feat, pa);
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;
 }

@@ -22,6 +22,13 @@ class Comm(object):
         self.group = group
         self.world = int(world)
         self.rank = int(rank)
+        self.p2p = None            # ops.P2PComm once setup_p2p() succeeded on every rank
+
+    def p2p_for(self, t):
+        """The peer-memory communicator if it can carry tensor `t` (float64, small, on the GPU), else None."""
+        if self.p2p is not None and t.is_cuda and t.dtype == torch.float64 and t.numel() <= 256:
+            return self.p2p
+        return None
 
     def all_reduce_sum(self, t):
         if self.world > 1:
@@ -40,6 +47,7 @@ class Comm(object):
 
 
 SINGLE = Comm()
+_OPEN_P2P = []          # communicators whose peer buffers shutdown() has to unmap
 
 
 def from_env():
@@ -66,7 +74,51 @@ def init_from_env(backend=None):
         if backend == "nccl":
             kw["device_id"] = torch.device("cuda", local_rank)
         td.init_process_group(backend=backend, **kw)
-    return Comm(None, td.get_world_size(), td.get_rank()), local_rank
+    comm = Comm(None, td.get_world_size(), td.get_rank())
+    if backend == "nccl" and torch.cuda.is_available():
+        setup_p2p(comm, torch.device("cuda", local_rank))
+    return comm, local_rank
+
+
+def setup_p2p(comm, device):
+    """Map every rank's exchange buffer into every other rank (CUDA IPC over NVLink / NVSwitch) so that the
+    synchronised BatchNorm sums are exchanged by the consuming kernels themselves (include/gnm.h, data-parallel
+    section). All ranks must call this; if any rank fails (no peer access, GNM_P2P=0, ...) every rank stays on NCCL."""
+    if comm.world <= 1 or comm.p2p is not None:
+        return comm.p2p
+    from . import ops
+    ok, p2p, handle = True, None, b""
+    try:
+        if os.environ.get("GNM_P2P", "1") == "0" or comm.world > ops.P2P_MAX_WORLD or device.type != "cuda":
+            raise RuntimeError("disabled")
+        p2p = ops.P2PComm(comm.rank, comm.world, device)
+        handle = p2p.handle
+    except Exception:
+        ok = False
+    gathered = [None] * comm.world
+    td.all_gather_object(gathered, (ok, handle), group=comm.group)
+    if all(g[0] for g in gathered):
+        try:
+            p2p.connect([g[1] for g in gathered])
+        except Exception:
+            ok = False
+    else:
+        ok = False
+    flags = [None] * comm.world
+    td.all_gather_object(flags, ok, group=comm.group)
+    if all(flags):
+        # one exchange to prove the mapping works before anything depends on it
+        probe = torch.full((4,), float(comm.rank + 1), dtype=torch.float64, device=device)
+        p2p.allreduce(probe)
+        torch.cuda.synchronize(device)
+        good = (not p2p.status()) and float(probe[0]) == comm.world * (comm.world + 1) / 2.0
+        td.all_gather_object(flags, bool(good), group=comm.group)
+    if all(flags):
+        comm.p2p = p2p
+        _OPEN_P2P.append(comm)
+    elif p2p is not None:
+        p2p.close()
+    return comm.p2p
 
 
 def shard(batch_graph, comm):
@@ -89,14 +141,16 @@ def average_gradients(model, comm):
     ps = [p for p in model.parameters() if p.grad is not None]
     if not ps:
         return
-    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    grads = [p.grad for p in ps]
+    flat = torch.cat([g.reshape(-1) for g in grads])
     comm.all_reduce_sum(flat)
-    flat.div_(comm.world)
-    off = 0
-    for p in ps:
-        n = p.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+    flat.mul_(1.0 / comm.world)
+    views, off = [], 0
+    for g in grads:
+        n = g.numel()
+        views.append(flat[off:off + n].view_as(g))
         off += n
+    torch._foreach_copy_(grads, views)          # one multi-tensor kernel instead of one copy per parameter
 
 
 def shutdown():
@@ -116,5 +170,11 @@ def shutdown():
         watchdog = threading.Timer(30.0, lambda: os._exit(0))
         watchdog.daemon = True
         watchdog.start()
+        if _OPEN_P2P:
+            td.barrier()                  # nobody may still be writing into a buffer that is about to be unmapped
+            for c in _OPEN_P2P:
+                c.p2p.close()
+                c.p2p = None
+            del _OPEN_P2P[:]
         td.destroy_process_group()
         watchdog.cancel()

@@ -390,7 +390,10 @@ def _bn_affine(unit, stats, count, training, comm):
     bn = unit.bn
     use_batch = training or not bn.track_running_stats
     if use_batch:
-        if comm.world > 1:
+        # data parallel: the global-batch sums. Over NVLink peer memory inside bn_finalize itself when the ranks share
+        # a P2P communicator (dist.setup_p2p), else an NCCL / gloo all-reduce in front of it.
+        p2p = comm.p2p_for(stats) if comm.world > 1 else None
+        if comm.world > 1 and p2p is None:
             comm.all_reduce_sum(stats)
         unit.count = float(count * comm.world)
         track = bn.track_running_stats and training
@@ -398,7 +401,8 @@ def _bn_affine(unit, stats, count, training, comm):
             raise NotImplementedError("BatchNorm1d(momentum=None) is not used by the reference")
         _ops.bn_finalize(stats, unit.count, unit.gamma, unit.beta, bn.eps, bn.momentum if track else 0.0,
                          bn.running_mean if track else None, bn.running_var if track else None,
-                         bn.num_batches_tracked if track else None, unit.scale, unit.shift, unit.mean, unit.rstd)
+                         bn.num_batches_tracked if track else None, unit.scale, unit.shift, unit.mean, unit.rstd,
+                         p2p=p2p)
     else:
         unit.count = 0.0
         _ops.bn_eval_affine(bn.running_mean, bn.running_var, unit.gamma, unit.beta, bn.eps, unit.scale, unit.shift,
@@ -564,8 +568,18 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                     _ops.relu_bn_bwd_reduce(u.z, u.scale, u.shift, u.mean, u.rstd, dz, None, None, None, None, None,
                                             0, bs.node_off, B, dy, stats)
             use_batch = u.count > 0.0
+            gather0 = j == 0 and layer == 0 and sv.use_gather0
+            fused = (not gather0) and (not FORCE_UNFUSED_BACKWARD) and n_out <= FUSED_BWD_MAX and n_in <= FUSED_BWD_MAX
+            p2p = None
             if use_batch and comm.world > 1:
-                comm.all_reduce_sum(stats)
+                # global-batch [sum dy, sum dy*xhat]: exchanged inside bn_bwd_coeffs (fused path) or by the small
+                # peer-memory all-reduce kernel when the ranks share a P2P communicator, else NCCL / gloo
+                p2p = comm.p2p_for(stats)
+                if p2p is None:
+                    comm.all_reduce_sum(stats)
+                elif not fused:
+                    p2p.allreduce(stats)
+                    p2p = None
             gi = pidx + 4 * j
             # d beta = sum dy, d gamma = sum dy * xhat (converted, and scaled to this rank's share, at the end)
             scaled = use_batch and comm.world > 1
@@ -573,13 +587,11 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
             from_f64.append((gi + 2, st_chunk, st_off + n_out, n_out, scaled))
             dw = zp.f32(*u.w.shape)
             db = zp.f32(*u.b.shape)
-            gather0 = j == 0 and layer == 0 and sv.use_gather0
-            fused = (not gather0) and (not FORCE_UNFUSED_BACKWARD) and n_out <= FUSED_BWD_MAX and n_in <= FUSED_BWD_MAX
             if fused:
                 # one pass: BatchNorm-backward apply (folded into the load as dz = A*dy + B*z + C), dW, db, dX and -
                 # for an inner unit - the ReLU mask + BatchNorm-backward reduction of the unit below
                 coef = torch.empty(3, n_out, dtype=torch.float32, device=dev)
-                _ops.bn_bwd_coeffs(stats if use_batch else None, u.count, u.gamma, u.mean, u.rstd, coef)
+                _ops.bn_bwd_coeffs(stats if use_batch else None, u.count, u.gamma, u.mean, u.rstd, coef, p2p=p2p)
                 if j > 0:
                     p = units[j - 1]
                     dy_prev = torch.empty(M, n_in, dtype=torch.float32, device=dev)

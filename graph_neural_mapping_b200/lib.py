@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libgnm.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _c_i32 = ctypes.c_int
 _c_i64 = ctypes.c_int64
@@ -39,11 +39,17 @@ SIGNATURES = {
     "gnm_linear": [_p, _c_i64, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p, _p, _p, _p, _c_i64, _c_i32, _p, _p],
     "gnm_set_linear_impl": [_c_i32],
     "gnm_linear_wgrad": [_p, _c_i64, _p, _c_i64, _c_i32, _c_i32, _c_i32, _p, _p, _p, _c_i64, _p, _p],
-    "gnm_bn_bwd_coeffs": [_p, _c_f64, _p, _p, _p, _p, _c_i32, _p],
+    "gnm_bn_bwd_coeffs": [_p, _c_f64, _p, _p, _p, _p, _c_i32, _p, _p],
     "gnm_linear_bwd": [_p, _c_i64, _p, _c_i64, _p, _p, _c_i64, _p, _p, _p, _p, _p, _c_i64, _p, _c_i64, _p, _p, _c_i64,
                        _p, _c_i32, _c_i32, _c_i32, _p],
     "gnm_col_stats": [_p, _c_i64, _c_i32, _c_i32, _p, _p],
-    "gnm_bn_finalize": [_p, _c_f64, _p, _p, _c_f32, _c_f32, _p, _p, _p, _p, _p, _p, _p, _c_i32, _p],
+    "gnm_bn_finalize": [_p, _c_f64, _p, _p, _c_f32, _c_f32, _p, _p, _p, _p, _p, _p, _p, _c_i32, _p, _p],
+    "gnm_p2p_buffer_bytes": [],
+    "gnm_p2p_alloc": [_p, _p],
+    "gnm_p2p_open": [_p, _p],
+    "gnm_p2p_close": [_p, _c_i32],
+    "gnm_p2p_allreduce": [_p, _c_i32, _p, _p],
+    "gnm_p2p_status": [_p],
     "gnm_bn_eval_affine": [_p, _p, _p, _p, _c_f32, _p, _p, _p, _p, _c_i32, _p],
     "gnm_bn_relu_readout": [_p, _c_i64, _c_i32, _c_i32, _p, _p, _p, _c_i64, _p, _c_i32, _p, _p, _c_i64, _p],
     "gnm_relu_bn_bwd_reduce": [_p, _c_i64, _c_i32, _c_i32, _p, _p, _p, _p, _p, _c_i64, _p, _c_i64, _p, _p, _p,
@@ -84,6 +90,7 @@ def load():
         fn.restype = ctypes.c_int
     lib.gnm_scatter_rows_workspace.restype = ctypes.c_int64
     lib.gnm_rows_period_workspace.restype = ctypes.c_int64
+    lib.gnm_p2p_buffer_bytes.restype = ctypes.c_int64
     lib.gnm_error_string.argtypes = [ctypes.c_int]
     lib.gnm_error_string.restype = ctypes.c_char_p
     got = lib.gnm_abi_version()

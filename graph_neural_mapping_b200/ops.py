@@ -174,6 +174,68 @@ def rows_period_sum(g, period, tags, table_grad):
     return table_grad
 
 
+# ---- peer-memory exchange (data parallel) ----------------------------------------------------
+
+P2P_MAX_DOUBLES = 256
+P2P_MAX_WORLD = 16
+
+
+class _P2PStruct(ctypes.Structure):
+    _fields_ = [("peers", ctypes.c_void_p), ("counter", ctypes.c_void_p), ("rank", ctypes.c_int), ("world", ctypes.c_int)]
+
+
+class P2PComm(object):
+    """gnm_p2p_comm of include/gnm.h: this rank's exchange buffer, its peers' buffers mapped through CUDA IPC, the
+    device table of their addresses and the call counter. Built by dist.setup_p2p()."""
+
+    def __init__(self, rank, world, device):
+        self.rank, self.world, self.device = int(rank), int(world), device
+        self.local = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        _libmod.check(_lib().gnm_p2p_alloc(ctypes.byref(self.local), handle), "gnm_p2p_alloc")
+        self.handle = bytes(handle)
+        self.opened = []
+        self.peers = None
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.struct = None
+
+    def connect(self, handles):
+        addrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                addrs.append(self.local.value)
+                continue
+            ptr = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            _libmod.check(_lib().gnm_p2p_open(buf, ctypes.byref(ptr)), "gnm_p2p_open")
+            self.opened.append(ptr)
+            addrs.append(ptr.value)
+        self.peers = torch.tensor(addrs, dtype=torch.int64, device=self.device)
+        self.struct = _P2PStruct(self.peers.data_ptr(), self.counter.data_ptr(), self.rank, self.world)
+
+    def ref(self):
+        return ctypes.byref(self.struct)
+
+    def allreduce(self, t):
+        """In-place sum over all ranks of a float64 tensor of at most P2P_MAX_DOUBLES elements."""
+        _libmod.check(_lib().gnm_p2p_allreduce(_ptr(t, torch.float64), int(t.numel()), self.ref(), _stream(t)),
+                      "gnm_p2p_allreduce")
+        return t
+
+    def status(self):
+        v = ctypes.c_int(0)
+        _libmod.check(_lib().gnm_p2p_status(ctypes.byref(v)), "gnm_p2p_status")
+        return bool(v.value)
+
+    def close(self):
+        for ptr in self.opened:
+            _lib().gnm_p2p_close(ptr, 0)
+        self.opened = []
+        if self.local is not None and self.local.value:
+            _lib().gnm_p2p_close(self.local, 1)
+            self.local = None
+
+
 # ---- MLP -----------------------------------------------------------------------------------
 
 def set_linear_impl(impl):
@@ -206,9 +268,11 @@ def linear_wgrad(dz, x, in_scale, in_shift, dw, dbias):
                                           _ptr(dbias, torch.float32), _stream(dz)), "gnm_linear_wgrad")
 
 
-def bn_bwd_coeffs(stats, count, gamma, mean, rstd, coef):
+def bn_bwd_coeffs(stats, count, gamma, mean, rstd, coef, p2p=None):
+    """p2p: P2PComm - `stats` is all-reduced in place by the kernel before the coefficients are formed."""
     _libmod.check(_lib().gnm_bn_bwd_coeffs(_ptr(stats, torch.float64), float(count), _ptr(gamma, torch.float32),
                                            _ptr(mean), _ptr(rstd), _ptr(coef, torch.float32), int(mean.shape[0]),
+                                           p2p.ref() if (p2p is not None and stats is not None) else None,
                                            _stream(coef)), "gnm_bn_bwd_coeffs")
     return coef
 
@@ -234,12 +298,15 @@ def col_stats(x, stats):
     return stats
 
 
-def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, nbt, scale, shift, mean, rstd):
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, nbt, scale, shift, mean, rstd,
+                p2p=None):
+    """p2p: P2PComm whose ranks all call this in the same order - `stats` is then all-reduced in place by the kernel."""
     _libmod.check(_lib().gnm_bn_finalize(_ptr(stats, torch.float64), float(count), _ptr(gamma, torch.float32),
                                          _ptr(beta, torch.float32), float(eps), float(momentum),
                                          _ptr(running_mean, torch.float32), _ptr(running_var, torch.float32),
                                          _ptr(nbt, torch.int64), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd),
-                                         int(scale.shape[0]), _stream(scale)), "gnm_bn_finalize")
+                                         int(scale.shape[0]), p2p.ref() if p2p is not None else None,
+                                         _stream(scale)), "gnm_bn_finalize")
 
 
 def bn_eval_affine(running_mean, running_var, gamma, beta, eps, scale, shift, mean, rstd):

@@ -32,9 +32,23 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 9
+#define GNM_ABI_VERSION 10
 
 typedef void* gnm_stream_t;
+
+/* Peer-memory communicator of the data-parallel step (one process per GPU, GPUs of one NVLink / NVSwitch domain).
+ * Host-side POD; peers / counter are DEVICE pointers: peers[world] = every rank's exchange buffer (gnm_p2p_alloc on its
+ * owner, gnm_p2p_open elsewhere) as mapped in this process, counter = this rank's call counter (zero-initialised
+ * uint32). NULL (or world <= 1) wherever a `const gnm_p2p_comm*` is taken means "single process". */
+typedef struct gnm_p2p_comm {
+    void* const* peers;
+    unsigned int* counter;
+    int rank;
+    int world;
+} gnm_p2p_comm;
+#define GNM_P2P_MAX_WORLD 16
+#define GNM_P2P_MAX_DOUBLES 256
+#define GNM_P2P_HANDLE_BYTES 64
 
 int gnm_abi_version(void);
 const char* gnm_error_string(int code);
@@ -158,9 +172,10 @@ int gnm_linear_wgrad(const float* dz, int64_t lddz, const float* x, int64_t ldx,
 
 /* BatchNorm backward as an affine map of (dy, z): dz = A*dy + B*z + C per channel, coef = [A | B | C] ([3*F]).
  * Training (stats != NULL: sum dy, sum dy*xhat; count = global rows): A = g*rstd, B = -g*rstd^2*m2,
- * C = g*rstd*(rstd*m2*mean - m1), m1 = stats[c]/count, m2 = stats[F+c]/count. Eval (stats == NULL): A = g*rstd. */
-int gnm_bn_bwd_coeffs(const double* stats, double count, const float* gamma, const float* mean, const float* rstd,
-                      float* coef, int n_feat, gnm_stream_t stream);
+ * C = g*rstd*(rstd*m2*mean - m1), m1 = stats[c]/count, m2 = stats[F+c]/count. Eval (stats == NULL): A = g*rstd.
+ * With comm the kernel first all-reduces stats in place over peer memory (stats then holds the global sums). */
+int gnm_bn_bwd_coeffs(double* stats, double count, const float* gamma, const float* mean, const float* rstd,
+                      float* coef, int n_feat, const gnm_p2p_comm* comm, gnm_stream_t stream);
 
 /* Fused backward of one Linear -> BatchNorm (-> ReLU) unit (autograd of mlp.py:48-49, graphcnn.py:162-166) in one
  * pass over the rows, F_out, F_in <= 64 (GNM_ERR_TOO_LARGE otherwise: use the unfused kernels):
@@ -183,11 +198,12 @@ int gnm_col_stats(const float* x, int64_t ldx, int n_rows, int n_feat, double* c
  * mean = sum/count, var = sumsq/count - mean^2 (biased), rstd = 1/sqrt(var + eps);
  * scale = gamma*rstd, shift = beta - mean*scale; running stats updated with momentum (unbiased variance,
  * count/(count-1)) and *num_batches_tracked += 1 when those pointers are non-NULL.
- * `count` is the GLOBAL row count (all ranks) - the caller all-reduces col_stats first. */
-int gnm_bn_finalize(const double* col_stats, double count, const float* gamma, const float* beta,
+ * `count` is the GLOBAL row count (all ranks): either the caller all-reduces col_stats first (comm NULL) or the kernel
+ * does it in place over peer memory (comm, 2*n_feat <= GNM_P2P_MAX_DOUBLES; see the data-parallel section below). */
+int gnm_bn_finalize(double* col_stats, double count, const float* gamma, const float* beta,
                     float eps, float momentum, float* running_mean, float* running_var,
                     int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* rstd,
-                    int n_feat, gnm_stream_t stream);
+                    int n_feat, const gnm_p2p_comm* comm, gnm_stream_t stream);
 
 /* Eval-mode BatchNorm (running statistics) as the same per-channel affine. */
 int gnm_bn_eval_affine(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
@@ -252,6 +268,21 @@ int gnm_dgi_score_bwd(const float* h_all, int64_t layer_stride, int n_layers, in
  * out[r] = <h[r], u[r / rows_per_graph]> + *bias (+ s_bias[r] if non-NULL). */
 int gnm_rowdot_score(const float* h, int64_t ldh, int n_rows, int n_feat, const float* u, int64_t ldu,
                      int rows_per_graph, const float* bias, const float* s_bias, float* out, gnm_stream_t stream);
+
+/* ---- data parallel: synchronised BatchNorm sums over NVLink peer memory ------------------------------
+ * The reference is single-process; a global-batch BatchNorm needs the per-channel sums of all ranks before the next
+ * operator can run (20 exchanges per training step, each on the critical path). Instead of an NCCL launch per exchange
+ * the CONSUMING kernel does it: gnm_bn_finalize / gnm_bn_bwd_coeffs take a communicator and all-reduce their double[2F]
+ * input in place (remote stores into every peer's exchange buffer, system-scope release/acquire flags, fixed-order
+ * sum: bit-identical on all ranks) before using it. gnm_p2p_allreduce is the same exchange as a kernel of its own
+ * (n <= GNM_P2P_MAX_DOUBLES). All ranks must issue the same sequence of exchanges. Waits are bounded (~2 s):
+ * gnm_p2p_status reports a give-up. */
+int64_t gnm_p2p_buffer_bytes(void);
+int gnm_p2p_alloc(void** buf, unsigned char* handle /* [GNM_P2P_HANDLE_BYTES] out: CUDA IPC handle */);
+int gnm_p2p_open(const unsigned char* handle, void** buf);
+int gnm_p2p_close(void* buf, int owner);
+int gnm_p2p_allreduce(double* data, int n, const gnm_p2p_comm* comm, gnm_stream_t stream);
+int gnm_p2p_status(int* aborted);
 
 #ifdef __cplusplus
 }

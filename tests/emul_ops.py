@@ -185,7 +185,7 @@ def linear_wgrad(dz, x, in_scale, in_shift, dw, dbias):
         dbias += dz.double().sum(0).float()
 
 
-def bn_bwd_coeffs(stats, count, gamma, mean, rstd, coef):
+def bn_bwd_coeffs(stats, count, gamma, mean, rstd, coef, p2p=None):
     f = mean.shape[0]
     g = gamma * rstd
     coef[0] = g
@@ -224,7 +224,8 @@ def col_stats(x, stats):
     return stats
 
 
-def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, nbt, scale, shift, mean, rstd):
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, nbt, scale, shift, mean, rstd,
+                p2p=None):
     n = scale.shape[0]
     mu = stats[:n] / count
     var = (stats[n:] / count - mu * mu).clamp_(min=0)

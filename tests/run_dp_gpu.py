@@ -50,10 +50,51 @@ def gather(t, comm):
     return out
 
 
+def check_peer_exchange(comm, dev):
+    """The NVLink peer-memory all-reduce (include/gnm.h, data-parallel section) against NCCL: 200 back-to-back
+    exchanges of varying length, bit-identical results on every rank, no give-ups."""
+    p2p = comm.p2p
+    if p2p is None:
+        if os.environ.get("GNM_P2P", "1") != "0" and comm.rank == 0:
+            print("peer exchange NOT available on this box (falling back to NCCL)", flush=True)
+        return os.environ.get("GNM_P2P", "1") == "0"
+    gen = torch.Generator(device="cpu").manual_seed(1234 + comm.rank)
+    for it in range(200):
+        n = [1, 2, 128, 256, 37][it % 5]
+        x = (torch.randn(n, generator=gen, dtype=torch.float64) * 10.0 ** (it % 7 - 3)).to(dev)
+        got = p2p.allreduce(x.clone())
+        # the kernel adds the ranks' payloads in rank order: the same sequence of fp64 additions, done here by hand
+        # on the NCCL-gathered inputs, must give the same bits; NCCL's own all-reduce (another order) only nearly so
+        parts = gather(x, comm)
+        ref = torch.zeros_like(x)
+        for part in parts:
+            ref = ref + part
+        if not torch.equal(got, ref):
+            print("rank %d: peer exchange %d differs from the rank-ordered sum" % (comm.rank, it), flush=True)
+            return False
+        nccl = x.clone()
+        td.all_reduce(nccl)
+        scale = torch.stack([q.abs() for q in parts]).sum(0)
+        if not bool(((got - nccl).abs() <= 1e-14 * scale + 1e-300).all()):
+            print("rank %d: peer exchange %d differs from NCCL beyond rounding" % (comm.rank, it), flush=True)
+            return False
+        every = gather(got, comm)
+        if not all(torch.equal(every[0], e) for e in every):
+            print("rank %d: peer exchange %d not bit-identical across ranks" % (comm.rank, it), flush=True)
+            return False
+    torch.cuda.synchronize()
+    if p2p.status():
+        print("rank %d: a peer exchange gave up waiting" % comm.rank, flush=True)
+        return False
+    if comm.rank == 0:
+        print("peer exchange OK: world=%d, 200 exchanges, bit-identical on all ranks" % comm.world, flush=True)
+    return True
+
+
 def main():
     comm, local_rank = gdist.init_from_env("nccl")
     dev = torch.device("cuda", local_rank)
-    ok = True
+    ok = check_peer_exchange(comm, dev)
     for name, seed0 in [("mid_eps_sum_h64", 900), ("tiny_eps_sum", 100)]:
         g = Golden(name)
         if g.cfg["B"] % comm.world:
@@ -87,6 +128,12 @@ def main():
             model.release_graphs()
             del model
     torch.cuda.synchronize()
+    if comm.p2p is not None and comm.p2p.status():
+        print("rank %d: a peer exchange gave up waiting during the parity steps" % comm.rank, flush=True)
+        ok = False
+    flags = [None] * comm.world
+    td.all_gather_object(flags, bool(ok))
+    ok = all(flags)
     td.barrier()
     if comm.rank == 0:
         print("DP_GPU_CHECK_PASSED" if ok else "DP_GPU_CHECK_FAILED", flush=True)
