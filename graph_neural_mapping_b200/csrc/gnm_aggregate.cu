@@ -244,6 +244,114 @@ rows_period_merge_kernel(const float* __restrict__ partial, int n_splits, int pe
     o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
 }
 
+// ---- max pooling over neighbours (graphcnn.py:55-81, 137-143) ----------------------------------------------------
+// The reference gathers a padded neighbour list (pads point at a dummy row = column-wise minimum of h over the whole
+// batch) and takes torch.max over it. Equivalent here: maximum over the CSR row (which holds the self loop when the
+// reference appends the node itself, i.e. learn_eps == False); a row without any entry yields the dummy row. The
+// arg-max (source row, or n_rows for the dummy) is kept for the backward pass. Ties keep the lowest column id - they
+// only occur at exact zeros behind a ReLU (whose backward masks them) or on measure-zero inputs.
+
+__device__ __forceinline__ unsigned int float_order_key(float v) {
+    const unsigned int u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_key(unsigned int k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// packed[f] = min over rows of (order_key(h[r, f]) << 32 | r): column minimum and its first row. Caller presets ~0.
+__global__ void __launch_bounds__(128)
+col_min_kernel(const float* __restrict__ h, int64_t ldh, int n_rows, int n_feat, int rows_per_cta,
+               unsigned long long* __restrict__ packed) {
+    const int f = blockIdx.y * blockDim.x + threadIdx.x;
+    if (f >= n_feat) return;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(n_rows, r0 + rows_per_cta);
+    unsigned long long best = ~0ull;
+    for (int r = r0; r < r1; ++r) {
+        const unsigned long long k = ((unsigned long long)float_order_key(h[(int64_t)r * ldh + f]) << 32) | (unsigned int)r;
+        best = k < best ? k : best;
+    }
+    if (best != ~0ull) atomicMin(&packed[f], best);
+}
+
+__global__ void __launch_bounds__(256)
+aggregate_max_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n_rows,
+                     const float* __restrict__ h, int64_t ldh, int n_feat, const unsigned long long* __restrict__ col_min,
+                     const float* __restrict__ eps, float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argmax) {
+    const int row = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int s = rowptr[row], e = rowptr[row + 1];
+    const float self_c = eps != nullptr ? 1.f + __ldg(eps) : 0.f;
+    for (int f0 = 0; f0 < n_feat; f0 += 64) {
+        const int fa = f0 + lane, fb = f0 + lane + 32;
+        const bool oka = fa < n_feat, okb = fb < n_feat;
+        float ba = -INFINITY, bb = -INFINITY;
+        int ia = -1, ib = -1;
+        for (int k = s; k < e; ++k) {
+            const int j = colidx[k];
+            const float* hj = h + (int64_t)j * ldh;
+            const float va = oka ? hj[fa] : -INFINITY, vb = okb ? hj[fb] : -INFINITY;
+            if (va > ba || ia < 0) { if (oka) { ba = va; ia = j; } }
+            if (vb > bb || ib < 0) { if (okb) { bb = vb; ib = j; } }
+        }
+        if (oka) {
+            if (ia < 0) { ba = float_from_order_key((unsigned int)(col_min[fa] >> 32)); ia = n_rows; }
+            if (eps != nullptr) ba = fmaf(self_c, h[(int64_t)row * ldh + fa], ba);
+            out[(int64_t)row * ld_out + fa] = ba;
+            argmax[(int64_t)row * n_feat + fa] = ia;
+        }
+        if (okb) {
+            if (ib < 0) { bb = float_from_order_key((unsigned int)(col_min[fb] >> 32)); ib = n_rows; }
+            if (eps != nullptr) bb = fmaf(self_c, h[(int64_t)row * ldh + fb], bb);
+            out[(int64_t)row * ld_out + fb] = bb;
+            argmax[(int64_t)row * n_feat + fb] = ib;
+        }
+    }
+}
+
+// d_h[j, f] = sum over the rows i of CSR row j (symmetric structure: i lists j iff j lists i) whose arg-max at f is j,
+// + (1 + eps) d_out[j, f]. Pull form: deterministic, no atomics.
+__global__ void __launch_bounds__(256)
+aggregate_max_bwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int n_rows,
+                         const float* __restrict__ d_out, int64_t ld_dout, int n_feat,
+                         const int32_t* __restrict__ argmax, const float* __restrict__ eps, float* __restrict__ d_h,
+                         int64_t ld_dh) {
+    const int row = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int s = rowptr[row], e = rowptr[row + 1];
+    const float self_c = eps != nullptr ? 1.f + __ldg(eps) : 0.f;
+    for (int f0 = 0; f0 < n_feat; f0 += 64) {
+        const int fa = f0 + lane, fb = f0 + lane + 32;
+        const bool oka = fa < n_feat, okb = fb < n_feat;
+        float aa = 0.f, ab = 0.f;
+        for (int k = s; k < e; ++k) {
+            const int i = colidx[k];
+            const int32_t* am = argmax + (int64_t)i * n_feat;
+            const float* di = d_out + (int64_t)i * ld_dout;
+            if (oka && am[fa] == row) aa += di[fa];
+            if (okb && am[fb] == row) ab += di[fb];
+        }
+        if (oka) d_h[(int64_t)row * ld_dh + fa] = fmaf(self_c, d_out[(int64_t)row * ld_dout + fa], aa);
+        if (okb) d_h[(int64_t)row * ld_dh + fb] = fmaf(self_c, d_out[(int64_t)row * ld_dout + fb], ab);
+    }
+}
+
+// rows that took the dummy (no neighbour at all): their gradient belongs to the row that supplied the column minimum
+__global__ void __launch_bounds__(256)
+aggregate_max_dummy_bwd_kernel(int n_rows, const float* __restrict__ d_out, int64_t ld_dout, int n_feat,
+                               const int32_t* __restrict__ argmax, const unsigned long long* __restrict__ col_min,
+                               float* __restrict__ d_h, int64_t ld_dh) {
+    const int64_t total = (int64_t)n_rows * n_feat;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        if (argmax[idx] != n_rows) continue;
+        const int i = (int)(idx / n_feat), f = (int)(idx - (int64_t)i * n_feat);
+        const int r = (int)(col_min[f] & 0xffffffffull);
+        atomicAdd(&d_h[(int64_t)r * ld_dh + f], d_out[(int64_t)i * ld_dout + f]);
+    }
+}
+
 }  // namespace
 
 extern "C" int gnm_aggregate(const int32_t* rowptr, const int32_t* colidx, int n_rows, const float* src,
@@ -359,6 +467,46 @@ extern "C" int gnm_rows_period_sum(const float* g, int64_t ldg, int n_rows, int 
     GNM_RETURN_IF_LAUNCH_FAILED();
     rows_period_merge_kernel<<<blocks, 256, 0, gnm_cast_stream(stream)>>>(workspace, splits, period, f4, tags, n_table_rows, out,
                                                                            ldo);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_col_min(const float* h, int64_t ldh, int n_rows, int n_feat, unsigned long long* packed,
+                           gnm_stream_t stream) {
+    if (n_rows < 0 || n_feat < 0) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0 || n_feat == 0) return GNM_OK;
+    if (!h || !packed) return GNM_ERR_BAD_ARG;
+    const int rows_per_cta = 256;
+    dim3 grid((n_rows + rows_per_cta - 1) / rows_per_cta, (n_feat + 127) / 128);
+    col_min_kernel<<<grid, 128, 0, gnm_cast_stream(stream)>>>(h, ldh, n_rows, n_feat, rows_per_cta, packed);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_aggregate_max(const int32_t* rowptr, const int32_t* colidx, int n_rows, const float* h, int64_t ldh,
+                                 int n_feat, const unsigned long long* col_min, const float* eps, float* out,
+                                 int64_t ld_out, int32_t* argmax, gnm_stream_t stream) {
+    if (n_rows < 0 || n_feat < 0) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0 || n_feat == 0) return GNM_OK;
+    if (!rowptr || !h || !col_min || !out || !argmax) return GNM_ERR_BAD_ARG;     // colidx may be NULL when nnz == 0
+    aggregate_max_kernel<<<(n_rows + 7) / 8, 256, 0, gnm_cast_stream(stream)>>>(rowptr, colidx, n_rows, h, ldh, n_feat,
+                                                                               col_min, eps, out, ld_out, argmax);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_aggregate_max_bwd(const int32_t* rowptr, const int32_t* colidx, int n_rows, const float* d_out,
+                                     int64_t ld_dout, int n_feat, const int32_t* argmax,
+                                     const unsigned long long* col_min, const float* eps, float* d_h, int64_t ld_dh,
+                                     gnm_stream_t stream) {
+    if (n_rows < 0 || n_feat < 0) return GNM_ERR_BAD_ARG;
+    if (n_rows == 0 || n_feat == 0) return GNM_OK;
+    if (!rowptr || !d_out || !argmax || !col_min || !d_h) return GNM_ERR_BAD_ARG;   // colidx may be NULL when nnz == 0
+    aggregate_max_bwd_kernel<<<(n_rows + 7) / 8, 256, 0, gnm_cast_stream(stream)>>>(rowptr, colidx, n_rows, d_out, ld_dout,
+                                                                                   n_feat, argmax, eps, d_h, ld_dh);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    aggregate_max_dummy_bwd_kernel<<<148 * 4, 256, 0, gnm_cast_stream(stream)>>>(n_rows, d_out, ld_dout, n_feat, argmax,
+                                                                                col_min, d_h, ld_dh);
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;
 }

@@ -235,6 +235,9 @@ class GraphStore(object):
         h.has_isolated = bool(t[:, 7].any())
         # every graph carries the same injective tag sequence (and so the same node count)
         h.same_tags = bool(b > 0 and t[0, 9] != 0 and (t[:, 9] == t[0, 9]).all() and h.uniform_n is not None)
+        # max pooling of a one-hot layer-0 input is an OR of neighbour tags; when every graph's tags are injective and
+        # its adjacency duplicate-free that OR equals the SUM aggregation, so layer 0 keeps the row-gather path
+        h.max0_as_sum = bool(b > 0 and h.onehot and (t[:, 9] != 0).all() and has_bm)
         return h
 
     def assemble_device(self, h, packed_d, node_off_d, nnz_capacity=None):
@@ -262,6 +265,7 @@ class GraphStore(object):
         bs.bitmap_addr = packed_d[4 * b + 1:5 * b + 1] if h.dense else None
         bs.has_isolated = h.has_isolated
         bs.same_tags = h.same_tags
+        bs.max0_as_sum = h.max0_as_sum
         return bs
 
     def assemble(self, graphs):
@@ -275,7 +279,7 @@ class GraphStore(object):
 
 class _HostBatch(object):
     __slots__ = ("b", "m", "nnz", "packed", "node_off", "counts", "uniform_n", "onehot", "feat_dim", "n_max", "dense",
-                 "has_isolated", "same_tags")
+                 "has_isolated", "same_tags", "max0_as_sum")
 
 
 class BatchStructure(object):
@@ -283,7 +287,7 @@ class BatchStructure(object):
 
     __slots__ = ("n_graphs", "n_rows", "nnz", "node_counts", "node_off", "rowptr", "_colidx", "_gather_args",
                  "uniform_n", "onehot", "tags", "feat_dim", "pool_scale", "n_max", "bitmap_addr", "has_isolated",
-                 "same_tags")
+                 "same_tags", "max0_as_sum")
 
     @property
     def colidx(self):
@@ -431,7 +435,11 @@ def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm):
     use_gather0 = x_dense is None
     if use_gather0 and not bs.onehot:
         raise RuntimeError("internal: gather path needs one-hot node features")
+    maxpool = model.neighbor_pooling_type == "max"
+    if maxpool and use_gather0 and not bs.max0_as_sum:
+        raise RuntimeError("internal: max pooling keeps the layer-0 gather only for injective tags on duplicate-free graphs")
     sv.use_gather0 = use_gather0
+    sv.max_state = {}          # layer -> (argmax [M, F_in] int32, packed column minimum) under max pooling
     sv.batch_stats = []
     zp = _ZeroPool(dev)
     for layer in range(L):
@@ -459,7 +467,14 @@ def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm):
                 else:
                     src = x_dense if layer == 0 else h_prev
                     pooled = torch.empty(M, src.shape[1], dtype=torch.float32, device=dev)
-                    bs.aggregate(src, None, pooled, 1 if average else 0, eps_l, None)
+                    if maxpool:
+                        # graphcnn.py:137-143: max over the padded neighbour list, dummy row = column minimum of h
+                        cmin = _ops.col_min(src)
+                        amax = torch.empty(M, src.shape[1], dtype=torch.int32, device=dev)
+                        _ops.aggregate_max(bs.rowptr, bs.colidx, src, cmin, eps_l, pooled, amax)
+                        sv.max_state[layer] = (amax, cmin)
+                    else:
+                        bs.aggregate(src, None, pooled, 1 if average else 0, eps_l, None)
                     _ops.linear(pooled, u.w, False, u.b, None, None, u.z, stats)
                     u.x_in = pooled
             else:
@@ -609,7 +624,11 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                             _ops.dot_rows(dp, src, None, d_eps[layer:layer + 1])
                         if layer > 0 or need_x_grad:
                             d_prev = torch.empty(M, n_in, dtype=torch.float32, device=dev)
-                            bs.aggregate(dp, None, d_prev, bwd_mode, eps_l, None)
+                            if layer in sv.max_state:
+                                amax, cmin = sv.max_state[layer]
+                                _ops.aggregate_max_bwd(bs.rowptr, bs.colidx, dp, amax, cmin, eps_l, d_prev)
+                            else:
+                                bs.aggregate(dp, None, d_prev, bwd_mode, eps_l, None)
                             if layer > 0:
                                 d_h = d_prev
                             else:
@@ -643,6 +662,11 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                 if learn_eps:
                     _ops.dot_rows(dz_u, sv.w1t, bs.tags, d_eps[layer:layer + 1])
                 if need_x_grad:
+                    if model.neighbor_pooling_type == "max":
+                        raise NotImplementedError("input gradients (compute_saliency) under neighbor_pooling_type='max' "
+                                                  "with one-hot features: torch.max routes the gradient of every tied "
+                                                  "zero entry by the reference's neighbour-list order (graphcnn.py:141), "
+                                                  "which the device CSR does not keep")
                     d_x = torch.empty(M, n_in, dtype=torch.float32, device=dev)
                     _ops.linear(g_agg, u.w, True, None, None, None, d_x, None)   # (Agg^T dz) @ W1
             else:
@@ -656,7 +680,11 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                         _ops.dot_rows(dp, src, None, d_eps[layer:layer + 1])
                     if layer > 0 or need_x_grad:
                         d_prev = torch.empty(M, n_in, dtype=torch.float32, device=dev)
-                        bs.aggregate(dp, None, d_prev, bwd_mode, eps_l, None)
+                        if layer in sv.max_state:
+                            amax, cmin = sv.max_state[layer]
+                            _ops.aggregate_max_bwd(bs.rowptr, bs.colidx, dp, amax, cmin, eps_l, d_prev)
+                        else:
+                            bs.aggregate(dp, None, d_prev, bwd_mode, eps_l, None)
                         if layer > 0:
                             d_h = d_prev
                         else:

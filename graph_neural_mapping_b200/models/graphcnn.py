@@ -79,10 +79,7 @@ class GIN_InfoMaxReg(nn.Module):
         return self._store
 
     def _host_batch(self, batch_graph):
-        if self.neighbor_pooling_type == "max":
-            raise NotImplementedError("neighbor_pooling_type='max' (graphcnn.py:55-81,137-143) is not on the "
-                                      "B200 hot path yet; use 'sum' or 'average'")
-        if self.neighbor_pooling_type not in ("sum", "average"):
+        if self.neighbor_pooling_type not in ("sum", "average", "max"):
             raise ValueError("unknown neighbor_pooling_type %r" % (self.neighbor_pooling_type,))
         store = self._graph_store()
         if not self.cache_graphs:
@@ -104,7 +101,7 @@ class GIN_InfoMaxReg(nn.Module):
         """The CUDA-graph plan for this training-step shape, or None (first sighting runs eagerly: it warms up
         cuBLAS / NCCL and the allocator before capture)."""
         if not (self.use_cuda_graphs and self.training and torch.is_grad_enabled() and h.onehot
-                and self.eps.device.type == "cuda"):
+                and (self.neighbor_pooling_type != "max" or h.max0_as_sum) and self.eps.device.type == "cuda"):
             return None
         key = _graphed.StepPlan._signature(h) + (n_global, self._comm.world)
         plan = self._plans.get(key)
@@ -122,7 +119,7 @@ class GIN_InfoMaxReg(nn.Module):
         return plan
 
     def _dense_features(self, batch_graph, bs):
-        if bs.onehot:
+        if bs.onehot and (self.neighbor_pooling_type != "max" or bs.max0_as_sum):
             return None                 # layer 0 runs as a row gather of W1^T
         return torch.cat([g.node_features for g in batch_graph], 0).to(self.eps.device, torch.float32)
 

@@ -174,6 +174,35 @@ def rows_period_sum(g, period, tags, table_grad):
     return table_grad
 
 
+# ---- max pooling over neighbours ----------------------------------------------------------------
+
+def col_min(h):
+    """Packed (order-preserving key << 32 | first row) column minimum of h: the reference's dummy row (graphcnn.py:139-140)."""
+    hp, ldh = _mat(h)
+    packed = torch.full((int(h.shape[1]),), -1, dtype=torch.int64, device=h.device)       # all-ones
+    _libmod.check(_lib().gnm_col_min(hp, ldh, int(h.shape[0]), int(h.shape[1]), _ptr(packed), _stream(h)), "gnm_col_min")
+    return packed
+
+
+def aggregate_max(rowptr, colidx, h, cmin, eps, out, argmax):
+    hp, ldh = _mat(h)
+    op, ldo = _mat(out)
+    _libmod.check(_lib().gnm_aggregate_max(_ptr(rowptr, torch.int32), _ptr(colidx, torch.int32), int(h.shape[0]), hp, ldh,
+                                           int(h.shape[1]), _ptr(cmin, torch.int64), _ptr(eps, torch.float32), op, ldo,
+                                           _ptr(argmax, torch.int32), _stream(out)), "gnm_aggregate_max")
+    return out
+
+
+def aggregate_max_bwd(rowptr, colidx, d_out, argmax, cmin, eps, d_h):
+    gp, ldg = _mat(d_out)
+    dp, ldd = _mat(d_h)
+    _libmod.check(_lib().gnm_aggregate_max_bwd(_ptr(rowptr, torch.int32), _ptr(colidx, torch.int32), int(d_out.shape[0]),
+                                               gp, ldg, int(d_out.shape[1]), _ptr(argmax, torch.int32),
+                                               _ptr(cmin, torch.int64), _ptr(eps, torch.float32), dp, ldd,
+                                               _stream(d_h)), "gnm_aggregate_max_bwd")
+    return d_h
+
+
 # ---- peer-memory exchange (data parallel) ----------------------------------------------------
 
 P2P_MAX_DOUBLES = 256

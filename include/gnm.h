@@ -32,7 +32,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 10
+#define GNM_ABI_VERSION 11
 
 typedef void* gnm_stream_t;
 
@@ -268,6 +268,25 @@ int gnm_dgi_score_bwd(const float* h_all, int64_t layer_stride, int n_layers, in
  * out[r] = <h[r], u[r / rows_per_graph]> + *bias (+ s_bias[r] if non-NULL). */
 int gnm_rowdot_score(const float* h, int64_t ldh, int n_rows, int n_feat, const float* u, int64_t ldu,
                      int rows_per_graph, const float* bias, const float* s_bias, float* out, gnm_stream_t stream);
+
+/* ---- max pooling over neighbours (graphcnn.py:55-81 `__preprocess_neighbors_maxpool`, :137-143 `maxpool`) --------
+ * The reference gathers h through a padded neighbour list whose pads point at a dummy row (column-wise minimum of h
+ * over the batch, :139-140) and takes torch.max over dim 1. Here: maximum over the CSR row (it holds the self loop
+ * exactly when the reference appends the node itself, learn_eps == False); a row with no entry yields the dummy.
+ *   gnm_col_min: packed[f] = min_r (order_key(h[r,f]) << 32 | r), caller presets all-ones: the dummy row and, in the
+ *     low word, the row that supplied it (torch.min's gradient target).
+ *   gnm_aggregate_max: out[i,f] = max_{j in row i} h[j,f] (+ (1+eps) h[i,f]); argmax[i,f] = that j, or n_rows for the
+ *     dummy. Ties keep the lowest column id (they occur at exact zeros behind a ReLU, whose backward masks them).
+ *   gnm_aggregate_max_bwd: d_h[j,f] = sum_{i in row j, argmax[i,f] == j} d_out[i,f] (+ (1+eps) d_out[j,f]) - pull form
+ *     over the same CSR (symmetric structure, as util.py:99-103 builds it), deterministic; dummy hits go to the
+ *     column-minimum row. */
+int gnm_col_min(const float* h, int64_t ldh, int n_rows, int n_feat, unsigned long long* packed, gnm_stream_t stream);
+int gnm_aggregate_max(const int32_t* rowptr, const int32_t* colidx, int n_rows, const float* h, int64_t ldh, int n_feat,
+                      const unsigned long long* col_min, const float* eps, float* out, int64_t ld_out, int32_t* argmax,
+                      gnm_stream_t stream);
+int gnm_aggregate_max_bwd(const int32_t* rowptr, const int32_t* colidx, int n_rows, const float* d_out, int64_t ld_dout,
+                          int n_feat, const int32_t* argmax, const unsigned long long* col_min, const float* eps,
+                          float* d_h, int64_t ld_dh, gnm_stream_t stream);
 
 /* ---- data parallel: synchronised BatchNorm sums over NVLink peer memory ------------------------------
  * The reference is single-process; a global-batch BatchNorm needs the per-channel sums of all ranks before the next

@@ -153,6 +153,47 @@ def scatter_rows_add(g, tags, table_grad):
     return table_grad
 
 
+def col_min(h):
+    """Stand-in keeps (values, first argmin rows) as a tuple instead of the packed device words."""
+    v, _ = h.min(0)
+    first = (h == v.unsqueeze(0)).float().argmax(0)
+    return (v, first)
+
+
+def aggregate_max(rowptr, colidx, h, cmin, eps, out, argmax):
+    m, f = h.shape
+    rp, ci = rowptr.long(), colidx.long()
+    for i in range(m):
+        nb = ci[rp[i]:rp[i + 1]]
+        if nb.numel() == 0:
+            out[i] = cmin[0]
+            argmax[i] = m
+        else:
+            vals = h[nb]                                            # [deg, f], ascending column order
+            best = vals.max(0).values
+            first = (vals == best.unsqueeze(0)).float().argmax(0)   # lowest column id among ties
+            out[i] = best
+            argmax[i] = nb[first].to(argmax.dtype)
+        if eps is not None:
+            out[i] += (1.0 + eps[0]) * h[i]
+    return out
+
+
+def aggregate_max_bwd(rowptr, colidx, d_out, argmax, cmin, eps, d_h):
+    m, f = d_out.shape
+    d_h.zero_()
+    cols = torch.arange(f)
+    for i in range(m):
+        src = argmax[i].long()
+        real = src < m
+        d_h[src[real], cols[real]] += d_out[i, real]
+        if (~real).any():
+            d_h[cmin[1][~real], cols[~real]] += d_out[i, ~real]
+    if eps is not None:
+        d_h += (1.0 + eps[0]) * d_out
+    return d_h
+
+
 def rows_period_sum(g, period, tags, table_grad):
     s = g.view(-1, period, g.shape[1]).double().sum(0).to(g.dtype)
     idx = torch.arange(period) if tags is None else tags[:period].long()

@@ -438,6 +438,59 @@ def test_aggregate_dense_exactness_on_wide_dynamic_range():
     assert not ops.aggregate_tc_status()
 
 
+@pytest.mark.parametrize("sizes,f,p,self_loops,eps", [([12, 12, 12], 8, 0.3, False, True), ([40, 17, 1, 33], 64, 0.2, True, False),
+                                                      ([400, 400], 64, 0.3, False, True), ([9, 5], 70, 0.0, False, False),
+                                                      ([30], 3, 0.5, True, False)])
+def test_aggregate_max(sizes, f, p, self_loops, eps):
+    """Max pooling over neighbours (graphcnn.py:137-143): values, arg-max routing of the gradient, the dummy row
+    (column minimum) for nodes without any entry, the (1 + eps) self term; against the literal padded-list gather."""
+    rng = np.random.default_rng(sum(sizes) + f)
+    mats = [rand_graph_edges(rng, n, p) for n in sizes]
+    e, eo, no = build_inputs(mats, sizes)
+    m = sum(sizes)
+    rp, ci, _ = ops.csr_build(e, eo, no, len(sizes), max(sizes), m, self_loops, False)
+    torch.manual_seed(f)
+    h = torch.randn(m, f, device=DEV)
+    h[::3] = torch.relu(h[::3])                                  # exact zeros / ties like a post-ReLU layer
+    ep = torch.tensor([0.37], device=DEV) if eps else None
+    cmin = ops.col_min(h)
+    out = torch.empty(m, f, device=DEV)
+    amax = torch.empty(m, f, dtype=torch.int32, device=DEV)
+    ops.aggregate_max(rp, ci, h, cmin, ep, out, amax)
+    # literal reference: padded neighbour list, -1 pads -> dummy row = column minimum
+    hc = h.cpu().double().requires_grad_()
+    rpc, cic = rp.cpu().long(), ci.cpu().long()
+    deg = (rpc[1:] - rpc[:-1])
+    width = max(int(deg.max()), 1)
+    padded = torch.full((m, width), -1, dtype=torch.long)
+    for i in range(m):
+        padded[i, :int(deg[i])] = cic[rpc[i]:rpc[i + 1]]
+    dummy = hc.min(0)[0]
+    hw = torch.cat([hc, dummy.reshape(1, -1)], 0)
+    ref = hw[padded].max(1)[0]
+    if eps:
+        ref = ref + (1 + 0.37) * hc
+    assert_close(out, ref.detach(), 1e-6, "max pooling forward")
+    am = amax.cpu().long()
+    assert bool(((am == m) == (deg == 0).unsqueeze(1)).all()), "dummy exactly for empty rows"
+    d_out = torch.randn(m, f, device=DEV)
+    d_h = torch.full((m, f), float("nan"), device=DEV)
+    ops.aggregate_max_bwd(rp, ci, d_out, amax, cmin, ep, d_h)
+    ref.backward(d_out.cpu().double())
+    # ties (exact zeros) may be routed to another tied row than torch's choice: compare where the maximum is unique
+    vals = hw.detach()[padded]
+    n_at_max = (vals == vals.max(1, keepdim=True)[0]).sum(1)
+    unique_rows = (n_at_max <= 1).all(1) | (deg == 0)
+    if bool(unique_rows.all()):
+        assert_close(d_h, hc.grad, 1e-5, "max pooling backward")
+    # always: the gradient mass per column is conserved
+    assert_close(d_h.double().sum(0), hc.grad.sum(0), 1e-5, "column sums of the routed gradient")
+    d_h2 = torch.empty(m, f, device=DEV)
+    ops.aggregate_max_bwd(rp, ci, d_out, amax, cmin, ep, d_h2)
+    # pull form: bit-reproducible, except for the dummy hits of isolated nodes (fp32 atomics onto the column-minimum row)
+    assert torch.equal(d_h, d_h2) or bool((deg == 0).any()), "deterministic without dummy hits"
+
+
 @pytest.mark.parametrize("n_graphs,period,f,table", [(1, 5, 4, 5), (3, 7, 12, 9), (40, 400, 64, 400), (1024, 400, 64, 400),
                                                      (33, 50, 8, 64)])
 def test_rows_period_sum(n_graphs, period, f, table):

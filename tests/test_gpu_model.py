@@ -15,10 +15,11 @@ from graph_neural_mapping_b200 import synth
 
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda")
-NAMES = [n for n in golden_names() if "max" not in n]
+NAMES = golden_names()
 TOL, TOL_GRAD = 1e-4, 2e-3
 SEEDS = {"tiny_eps_sum": 100, "tiny_noeps_sum": 100, "tiny_eps_avg": 300, "tiny_noeps_avg": 300, "tiny_mlp1": 500,
-         "tiny_mlp3": 500, "mid_eps_sum_h64": 900, "schaefer400_noeps": 0, "schaefer400_eps": 10}
+         "tiny_mlp3": 500, "mid_eps_sum_h64": 900, "schaefer400_noeps": 0, "schaefer400_eps": 10, "tiny_eps_max": 700,
+         "tiny_noeps_max": 700}
 
 
 def build_model(g, sd=None):
@@ -99,6 +100,11 @@ def test_eval_latent_saliency_vs_reference(name):
     c1, d1 = model([graphs[0]])
     assert_close(c1, g.z["eval1/c_logit"], TOL, "eval1 c")
     assert_close(d1, g.z["eval1/d_logit"], TOL, "eval1 d")
+    if g.cfg["neighbor_pooling_type"] == "max":
+        # one-hot input gradients under max pooling depend on the reference's neighbour-list order at tied zeros
+        with pytest.raises(NotImplementedError):
+            model.compute_saliency([graphs[0]], 1)
+        return
     for k, v in g.group("saliency/").items():
         gi, cls = int(k[1:k.index("_")]), int(k[-1])
         s = model.compute_saliency([graphs[gi]], cls)

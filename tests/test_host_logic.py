@@ -13,7 +13,7 @@ from graph_neural_mapping_b200.models import graphcnn as gmod
 from graph_neural_mapping_b200.models import mlp as mlpmod
 from graph_neural_mapping_b200.models import discriminator as dmod
 
-NAMES = [n for n in golden_names() if "max" not in n]
+NAMES = golden_names()
 TOL = 1e-4
 TOL_GRAD = 2e-3
 
@@ -68,7 +68,7 @@ def test_train_step_vs_reference(name):
     graphs = g.graphs()
     c_logit, d_logit, loss = train_step(model, graphs, g, 4242 + {"tiny_eps_sum": 100, "tiny_noeps_sum": 100, "tiny_eps_avg": 300,
                                         "tiny_noeps_avg": 300, "tiny_mlp1": 500, "tiny_mlp3": 500,
-                                        "mid_eps_sum_h64": 900}[name])
+                                        "mid_eps_sum_h64": 900, "tiny_eps_max": 700, "tiny_noeps_max": 700}[name])
     assert_close(c_logit, g.z["train/c_logit"], TOL, "c_logit")
     assert_close(d_logit, g.z["train/d_logit"], TOL, "d_logit")
     assert_close(loss, g.z["train/loss"], TOL, "loss")
@@ -108,6 +108,11 @@ def test_eval_latent_saliency_vs_reference(name):
     c1, d1 = model([graphs[0]])
     assert_close(c1, g.z["eval1/c_logit"], TOL, "eval1 c")
     assert_close(d1, g.z["eval1/d_logit"], TOL, "eval1 d")
+    if g.cfg["neighbor_pooling_type"] == "max":
+        # one-hot input gradients under max pooling depend on the reference's neighbour-list order at tied zeros
+        with pytest.raises(NotImplementedError):
+            model.compute_saliency([graphs[0]], 1)
+        return
     for k, v in g.group("saliency/").items():
         gi, cls = int(k[1:k.index("_")]), int(k[-1])
         s = model.compute_saliency([graphs[gi]], cls)
