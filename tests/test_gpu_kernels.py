@@ -663,3 +663,84 @@ def test_linear_tcgen05(m, k, n, kn, pro, stats):
     assert_close(outs[0][0], outs[1][0], TOL, "tcgen05 vs FFMA")
     if stats:
         assert_close(outs[0][1], sr, 1e-5, "tcgen05 col_stats")
+
+
+def test_peer_exchange_protocol_two_ranks_on_one_gpu():
+    """The NVLink peer-memory all-reduce (include/gnm.h, data-parallel section) with both "ranks" on this GPU: two
+    exchange buffers, two communicators, the two kernels on two streams meet through the flag protocol. 100 exchanges
+    of varying length back to back (both slot parities, counter in device memory), then the fused users: bn_finalize
+    and bn_bwd_coeffs with a communicator must equal the same calls on pre-summed statistics."""
+    import ctypes
+    from graph_neural_mapping_b200 import lib as glib
+    L = glib.load()
+    world = 2
+    bufs = []
+    for _ in range(world):
+        ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        glib.check(L.gnm_p2p_alloc(ctypes.byref(ptr), handle), "gnm_p2p_alloc")
+        bufs.append(ptr)
+    try:
+        peers = torch.tensor([b.value for b in bufs], dtype=torch.int64, device=DEV)
+        counters = [torch.zeros(1, dtype=torch.int32, device=DEV) for _ in range(world)]
+        comms = [ops._P2PStruct(peers.data_ptr(), counters[r].data_ptr(), r, world) for r in range(world)]
+        streams = [torch.cuda.Stream() for _ in range(world)]
+        torch.manual_seed(3)
+        torch.cuda.synchronize()
+        for it in range(100):
+            n = [1, 2, 128, 256, 37][it % 5]
+            xs = [torch.randn(n, dtype=torch.float64, device=DEV) * 10.0 ** (it % 5 - 2) for _ in range(world)]
+            want = xs[0] + xs[1]
+            torch.cuda.synchronize()
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    glib.check(L.gnm_p2p_allreduce(ctypes.c_void_p(xs[r].data_ptr()), n, ctypes.byref(comms[r]),
+                                                   ctypes.c_void_p(streams[r].cuda_stream)), "gnm_p2p_allreduce")
+            torch.cuda.synchronize()
+            assert torch.equal(xs[0], want) and torch.equal(xs[1], want), "exchange %d" % it
+        aborted = ctypes.c_int(0)
+        glib.check(L.gnm_p2p_status(ctypes.byref(aborted)), "gnm_p2p_status")
+        assert aborted.value == 0, "a peer exchange gave up waiting"
+
+        class _C(object):                      # what ops.bn_finalize / bn_bwd_coeffs expect as p2p
+            def __init__(self, st):
+                self.st = st
+
+            def ref(self):
+                return ctypes.byref(self.st)
+
+        f, count = 64, 1000.0
+        parts = [torch.rand(2 * f, dtype=torch.float64, device=DEV) * 500 + torch.cat(
+            [torch.zeros(f, dtype=torch.float64, device=DEV), torch.full((f,), 400.0, dtype=torch.float64, device=DEV)])
+            for _ in range(world)]
+        gamma, beta = torch.rand(f, device=DEV) + 0.5, torch.randn(f, device=DEV)
+        ref_out = [torch.empty(f, device=DEV) for _ in range(4)]
+        ops.bn_finalize(parts[0] + parts[1], count, gamma, beta, 1e-5, 0.0, None, None, None, *ref_out)
+        outs = [[torch.empty(f, device=DEV) for _ in range(4)] for _ in range(world)]
+        work = [p.clone() for p in parts]
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                ops.bn_finalize(work[r], count, gamma, beta, 1e-5, 0.0, None, None, None, *outs[r], p2p=_C(comms[r]))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert torch.equal(work[r], parts[0] + parts[1]), "bn_finalize leaves the global sums in place"
+            for a, b in zip(outs[r], ref_out):
+                assert torch.equal(a, b), "fused bn_finalize == bn_finalize on pre-summed statistics"
+        mean, rstd = torch.randn(f, device=DEV), torch.rand(f, device=DEV) + 0.5
+        ref_coef = torch.empty(3, f, device=DEV)
+        ops.bn_bwd_coeffs(parts[0] + parts[1], count, gamma, mean, rstd, ref_coef)
+        coefs = [torch.empty(3, f, device=DEV) for _ in range(world)]
+        work = [p.clone() for p in parts]
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                ops.bn_bwd_coeffs(work[r], count, gamma, mean, rstd, coefs[r], p2p=_C(comms[r]))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert torch.equal(coefs[r], ref_coef), "fused bn_bwd_coeffs"
+        glib.check(L.gnm_p2p_status(ctypes.byref(aborted)), "gnm_p2p_status")
+        assert aborted.value == 0
+    finally:
+        torch.cuda.synchronize()
+        for b in bufs:
+            L.gnm_p2p_close(b, 1)
