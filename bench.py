@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=1024, help="graphs per GPU per step")
     ap.add_argument("--learn-eps", action="store_true", help="graphcnn.py next_layer_eps path (default: main.py's default, False)")
     ap.add_argument("--cpu-batch", type=int, default=32, help="graphs per step of the CPU baseline sample (configs[0])")
+    ap.add_argument("--driver", default="fused", choices=["fused", "loop"],
+                    help="device-resident arm (`value`): 'fused' = graph_neural_mapping_b200.driver.Trainer (the whole step "
+                         "as one CUDA graph, SURVEY 8(f) N2), 'loop' = the main.py loop body over the drop-in model")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also print the per-kernel time table to stderr")
@@ -278,6 +281,18 @@ def run_b200(args):
 
     model.train()
     # ---- value: device-resident inputs ---------------------------------------------------------
+    step_loop = step_resident
+    if args.driver == "fused":
+        from graph_neural_mapping_b200.driver import Trainer
+        # same model, same work per step (assembly, forward, heads, CE + beta*BCE, backward, gradient averaging, Adam)
+        # captured as ONE CUDA graph; the labels ride in the same pinned staging ring as the slot addresses
+        trainer = Trainer(model, lr=LR, beta=BETA, comm=comm)
+        labels_np = np.array([g.label for g in pool], dtype=np.int64)
+
+        def step_resident():
+            sel = np.random.permutation(len(pool))[:B]
+            return trainer.step([pool[i] for i in sel], labels_np[sel])
+
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
@@ -302,10 +317,10 @@ def run_b200(args):
     # ---- per-kernel times, live, on the launching stream ------------------------------------
     graphs_on = model.use_cuda_graphs
     model.use_cuda_graphs = False            # per-kernel events need the eager (kernel-by-kernel) path
-    step_resident()
+    step_loop()
     with OpTimer(ops) as timer:
         for _ in range(2):
-            step_resident()
+            step_loop()
         table = timer.table()
     model.use_cuda_graphs = graphs_on
     n_prof = 2
@@ -381,12 +396,17 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(args, world), cuda_graphs=bool(model.use_cuda_graphs)),
+                "config": dict(workload_config(args, world), cuda_graphs=bool(model.use_cuda_graphs),
+                               driver=("driver.Trainer: whole step (assembly, forward, heads, loss, backward, gradient "
+                                       "averaging, Adam) as one CUDA graph" if args.driver == "fused" else
+                                       "main.py loop body over the drop-in model (encoder forward / backward as CUDA graphs)")),
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": e2e, "roofline": roof, "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown}
         print(json.dumps(line))
     if world > 1:
         model.release_graphs()
+        if args.driver == "fused":
+            trainer.release()
         torch.cuda.synchronize()
         torch.distributed.barrier()
         gdist.shutdown()

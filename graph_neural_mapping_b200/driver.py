@@ -1,0 +1,163 @@
+"""Batched training driver beside the reference's frozen `main.py`.
+
+`main.py:25-43` per step: `model(batch_graph)`, labels built on the host, CrossEntropy + beta * BCEWithLogits,
+`zero_grad`, `backward`, `Adam.step`, `loss.cpu()`. Driven through the drop-in classes that loop already runs the
+encoder from two CUDA graphs; what is left between them - prediction heads, loss, autograd bookkeeping, gradient
+averaging, the optimizer - is ~100 small launches issued from Python every step.
+
+`Trainer.step(batch_graph)` runs the WHOLE step - batch assembly kernel, encoder + DGI forward, heads, loss, backward,
+data-parallel gradient averaging, Adam - as ONE captured CUDA graph per batch shape:
+
+  per step (host):  batch assembly arithmetic (numpy gathers over the graph store's slot table), one permutation draw,
+                    4 small asynchronous H2D copies through a pinned ring, one graph replay. No synchronisation: the
+                    loss stays on the device (`.item()` it when you want to look at it).
+
+Same arithmetic as the reference loop: the captured work is `engine.run_forward` / `run_backward` (the kernels of the
+drop-in model), torch's own loss functions and `torch.optim.Adam(capturable=True)`; dropout uses torch's CUDA-graph
+aware Philox generator. The first two steps of a new shape run eagerly (they warm up cuBLAS, the allocator and - data
+parallel - NCCL), the third captures.
+"""
+import numpy as np
+import torch
+
+from . import dist as _dist
+from . import engine as _engine
+from . import ops as _ops
+
+
+class _WholeStepPlan(object):
+    def __init__(self, trainer, h, n_global):
+        model = trainer.model
+        dev = model.eps.device
+        self.trainer, self.dev = trainer, dev
+        self.sig = trainer._signature(h, n_global)
+        self.nnz_cap = int(h.nnz * 1.02) + 4096
+        self.packed = torch.zeros(5 * h.b + 1, dtype=torch.int64, device=dev)
+        self.node_off = torch.zeros(h.b + 1, dtype=torch.int32, device=dev)
+        self.neg_idx = torch.zeros(n_global, dtype=torch.int32, device=dev)
+        self.labels = torch.zeros(h.b, dtype=torch.int64, device=dev)
+        self.d_labels = torch.cat([torch.ones(h.m, 1), torch.zeros(h.m, 1)], 0).to(dev)      # main.py:32-33
+        self.stage = [None, None, None]
+        self.stage_i = 0
+        self.graph = None
+        self.loss = None
+        self.h = h
+        self.launches = 0
+
+    def load(self, h, perm, labels):
+        """Host -> device traffic of one step, staged through a ring of pinned buffers (never waits for the GPU)."""
+        self.h = h
+        i = self.stage_i
+        self.stage_i = (i + 1) % len(self.stage)
+        if self.stage[i] is None:
+            self.stage[i] = (torch.empty(self.packed.shape[0], dtype=torch.int64, pin_memory=True),
+                             torch.empty(self.node_off.shape[0], dtype=torch.int32, pin_memory=True),
+                             torch.empty(self.neg_idx.shape[0], dtype=torch.int32, pin_memory=True),
+                             torch.empty(self.labels.shape[0], dtype=torch.int64, pin_memory=True),
+                             torch.cuda.Event())
+        else:
+            self.stage[i][4].synchronize()
+        s_packed, s_off, s_neg, s_lab, ev = self.stage[i]
+        s_packed.numpy()[:] = h.packed
+        s_off.numpy()[:] = h.node_off
+        s_neg.numpy()[:] = perm
+        s_lab.numpy()[:] = labels
+        self.packed.copy_(s_packed, non_blocking=True)
+        self.node_off.copy_(s_off, non_blocking=True)
+        self.neg_idx.copy_(s_neg, non_blocking=True)
+        self.labels.copy_(s_lab, non_blocking=True)
+        ev.record()
+        return h.packed.nbytes + h.node_off.nbytes + 4 * perm.size + 8 * len(labels)
+
+    def body(self):
+        """One training step on the static buffers (runs eagerly while warming up, then under capture)."""
+        tr = self.trainer
+        model = tr.model
+        store = model._graph_store()
+        bs = store.assemble_device(self.h, self.packed, self.node_off, nnz_capacity=self.nnz_cap)
+        bs.set_pooling(model.graph_pooling_type, self.dev)
+        runner = _engine.Runner(model, bs, self.neg_idx, True, True, tr.comm)
+        tr.optimizer.zero_grad(set_to_none=True)
+        g_f, d_logit = _engine.GINFunction.apply(runner, None, *_engine.flat_params(model))
+        c_logit = model._heads(g_f)
+        loss = tr.c_criterion(c_logit, self.labels) + tr.beta * tr.d_criterion(d_logit, self.d_labels)     # main.py:34-37
+        loss.backward()
+        _dist.average_gradients(model, tr.comm)
+        tr.optimizer.step()
+        return loss.detach()
+
+    def run(self):
+        if self.graph is None:
+            g = torch.cuda.CUDAGraph()
+            n0 = _ops.LAUNCHES[0]
+            with torch.cuda.graph(g):
+                self.loss = self.body()
+            self.launches = _ops.LAUNCHES[0] - n0
+            _ops.LAUNCHES[0] = n0                      # capture records, replay launches
+            self.graph = g
+        self.graph.replay()
+        _ops.LAUNCHES[0] += self.launches
+        return self.loss
+
+
+class Trainer(object):
+    """`main.py:25-43` as one CUDA graph per batch shape. `model` is a `GIN_InfoMaxReg` in train mode on a CUDA device
+    with one-hot node features; `comm` the data-parallel communicator (`dist.init_from_env()`), each rank passing its
+    own shard of the global batch. Adam only (the reference's optimizer, `main.py:137`)."""
+
+    def __init__(self, model, lr=0.01, beta=0.1, comm=None, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        dev = model.eps.device
+        _engine.require_cuda(dev)
+        self.model = model
+        self.beta = float(beta)
+        self.comm = comm if comm is not None else _dist.SINGLE
+        model.set_comm(self.comm)
+        self.optimizer = torch.optim.Adam(model.parameters(), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                          capturable=True)
+        self.c_criterion = torch.nn.CrossEntropyLoss()          # main.py:16
+        self.d_criterion = torch.nn.BCEWithLogitsLoss()         # main.py:17
+        self._plans = {}
+        self._seen = {}
+        self.h2d_bytes = 0
+
+    @staticmethod
+    def _signature(h, n_global):
+        return (h.b, h.m, h.uniform_n, h.onehot, h.feat_dim, h.n_max, h.dense, h.has_isolated, h.same_tags,
+                h.max0_as_sum, n_global)
+
+    def release(self):
+        """Drop the captured graphs (do this before tearing a process group down: they hold NCCL work)."""
+        self._plans.clear()
+        self._seen.clear()
+
+    def step(self, batch_graph, labels=None):
+        """One optimisation step on `batch_graph` (this rank's shard). Returns the loss as a 0-d device tensor that is
+        overwritten by the next step of the same shape; nothing synchronises."""
+        model = self.model
+        if not model.training:
+            raise RuntimeError("Trainer.step needs model.train()")
+        n_global = len(batch_graph) * self.comm.world
+        perm = np.random.permutation(n_global)                  # graphcnn.py:199: one numpy draw per step
+        h = model._host_batch(batch_graph)
+        if h.uniform_n is None:
+            raise RuntimeError("GIN_InfoMaxReg needs graphs with the same number of nodes (graphcnn.py:198-201)")
+        if not h.onehot or (model.neighbor_pooling_type == "max" and not h.max0_as_sum):
+            raise RuntimeError("Trainer runs the one-hot input path (util.py:114-116); use the model API for dense features")
+        if labels is None:
+            labels = [g.label for g in batch_graph]             # main.py:31
+        key = self._signature(h, n_global)
+        plan = self._plans.get(key)
+        if plan is not None and h.nnz > plan.nnz_cap:
+            del self._plans[key]
+            plan = None
+        if plan is None:
+            while len(self._plans) >= 2:
+                self._plans.pop(next(iter(self._plans)))
+            plan = _WholeStepPlan(self, h, n_global)
+            self._plans[key] = plan
+            self._seen[key] = 0
+        self.h2d_bytes += plan.load(h, perm, labels)
+        self._seen[key] += 1
+        if self._seen[key] <= 2:
+            return plan.body()                                   # warm-up: cuBLAS handles, allocator, NCCL
+        return plan.run()

@@ -309,7 +309,10 @@ class BatchStructure(object):
 
     def set_pooling(self, graph_pooling_type, device):
         if graph_pooling_type == "average":
-            self.pool_scale = torch.from_numpy((1.0 / self.node_counts).astype(np.float32)).to(device)
+            # graphcnn.py:118-120: 1 / len(graph.g) per graph - from the device node offsets (no host copy: this also
+            # runs under CUDA-graph capture)
+            no = self.node_off
+            self.pool_scale = 1.0 / (no[1:] - no[:-1]).to(torch.float32)
         else:
             self.pool_scale = None
 
