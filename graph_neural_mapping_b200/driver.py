@@ -161,3 +161,66 @@ class Trainer(object):
         if self._seen[key] <= 2:
             return plan.body()                                   # warm-up: cuBLAS handles, allocator, NCCL
         return plan.run()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Batched evaluation: main.py:49-82 runs its three evaluation loops one graph per forward (`model([g])`). In eval mode
+# BatchNorm uses the running statistics and Adj_block is block-diagonal, so class logits, the latent space and the
+# saliency maps of a graph do not depend on its batch companions: the loops below produce the same arrays, in the same
+# layout, from large batches.
+# ------------------------------------------------------------------------------------------------------------------
+
+def _batches(graphs, batch):
+    for i in range(0, len(graphs), batch):
+        yield graphs[i:i + batch]
+
+
+def class_logits(model, graphs, batch=256):
+    """`pass_data_iteratively(model, graphs)[0]` (main.py:49-57): [G, 2] class logits, eval mode, on the device."""
+    model.eval()
+    out = []
+    with torch.no_grad():
+        for chunk in _batches(graphs, batch):
+            if len({len(g.g) for g in chunk}) > 1:
+                out.extend(model([g])[0] for g in chunk)         # ragged node counts: the DGI path needs equal sizes
+            else:
+                out.append(model(chunk)[0])
+    return torch.cat(out, 0)
+
+
+def latent_space(model, graphs, batch=256):
+    """`get_latent_space` (main.py:71-82): (float32 [G, L*F] readout features, int [G, 1] labels)."""
+    model.eval()
+    feats = []
+    with torch.no_grad():
+        for chunk in _batches(graphs, batch):
+            if len({len(g.g) for g in chunk}) > 1:
+                feats.extend(model([g], latent=True) for g in chunk)
+            else:
+                feats.append(model(chunk, latent=True))
+    labels = np.stack([np.array([g.label]) for g in graphs], axis=0)
+    return np.concatenate(feats, axis=0), labels
+
+
+def saliency_maps(model, graphs, cls, batch=64):
+    """`get_saliency_map` (main.py:60-68): float32 [G, N, D] - one `compute_saliency` map per graph, computed in
+    batches (exact: `compute_saliency_batched`). All graphs must have the same number of nodes (np.stack)."""
+    maps = []
+    for chunk in _batches(graphs, batch):
+        s = model.compute_saliency_batched(chunk, cls).detach()
+        n = len(chunk[0].g)
+        maps.append(s.reshape(len(chunk), n, s.shape[1]).cpu().numpy())
+    return np.concatenate(maps, axis=0)
+
+
+def save_results(model, graphs, out_dir, batch=64):
+    """The arrays main.py:170-172 leaves for the evaluate/ scripts, same file names and layouts: latent_space.npy,
+    labels.npy, saliency_female.npy (class 0), saliency_male.npy (class 1)."""
+    import os
+    os.makedirs(out_dir, exist_ok=True)
+    lat, labels = latent_space(model, graphs, batch=max(batch, 1))
+    np.save(os.path.join(out_dir, "latent_space.npy"), lat)
+    np.save(os.path.join(out_dir, "labels.npy"), labels)
+    np.save(os.path.join(out_dir, "saliency_female.npy"), saliency_maps(model, graphs, 0, batch))
+    np.save(os.path.join(out_dir, "saliency_male.npy"), saliency_maps(model, graphs, 1, batch))
+    return out_dir

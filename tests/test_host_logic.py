@@ -304,3 +304,30 @@ def test_shared_tag_sequence_takes_the_period_sum_path():
         floor = grad_floor({k: v.numpy() for k, v in grads[(shift, True)].items()})
         for k, v in grads[(shift, True)].items():
             assert_close(grads[(shift, False)][k], v, 1e-4, "shift=%s grad %s" % (shift, k), floor=floor)
+
+
+def test_batched_evaluation_equals_the_one_graph_loops(tmp_path):
+    """driver.class_logits / latent_space / saliency_maps / save_results against main.py:49-82's one-graph-per-forward
+    loops over the same model, and against the reference's own per-graph outputs in the fixture."""
+    from graph_neural_mapping_b200 import driver
+    g = Golden("tiny_eps_sum")
+    model = build_model(g, g.state_after_train())
+    graphs = g.graphs()
+    model.eval()
+    loop_c = torch.cat([model([x])[0].detach() for x in graphs], 0)
+    loop_lat = np.concatenate([model([x], latent=True) for x in graphs], 0)
+    loop_s1 = np.stack([model.compute_saliency([x], 1).detach().cpu().numpy() for x in graphs], 0)
+    assert_close(driver.class_logits(model, graphs, batch=3), loop_c, 1e-6, "class logits")
+    lat, labels = driver.latent_space(model, graphs, batch=3)
+    assert lat.dtype == np.float32 and labels.shape == (len(graphs), 1)
+    assert_close(lat, loop_lat, 1e-6, "latent space")
+    assert [int(v) for v in labels[:, 0]] == [x.label for x in graphs]
+    s1 = driver.saliency_maps(model, graphs, 1, batch=3)
+    assert s1.shape == loop_s1.shape
+    assert_close(s1, loop_s1, 1e-6, "saliency maps")
+    assert_close(s1[0], g.z["saliency/g0_c1"], TOL_GRAD, "saliency of graph 0 vs the reference")
+    out = driver.save_results(model, graphs, str(tmp_path / "res"), batch=2)
+    import os
+    assert sorted(os.listdir(out)) == ["labels.npy", "latent_space.npy", "saliency_female.npy", "saliency_male.npy"]
+    assert_close(np.load(os.path.join(out, "saliency_male.npy")), loop_s1, 1e-6, "saved saliency")
+    assert np.load(os.path.join(out, "latent_space.npy")).shape == loop_lat.shape
