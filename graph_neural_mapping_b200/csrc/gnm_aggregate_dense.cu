@@ -304,7 +304,7 @@ extern "C" int gnm_bitmap_build(const int32_t* rowptr, const int32_t* colidx, co
 int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
                             int n_max, const float* src, int64_t ld_src, const int32_t* src_map, float* dst,
                             int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
-                            cudaStream_t stream);
+                            const float* aff_coef, const float* aff_z, int64_t ld_aff_z, cudaStream_t stream);
 
 extern "C" int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr,
                                    int n_graphs, int n_max, const float* src, int64_t ld_src, const int32_t* src_map,
@@ -319,7 +319,8 @@ extern "C" int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* no
     if (impl < 0 || impl > 2) return GNM_ERR_BAD_ARG;
     if (impl != 1) {
         const int rc = gnm_launch_aggregate_tc(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, ld_src, src_map, dst,
-                                               ld_dst, n_feat, mode, eps, bias, gnm_cast_stream(stream));
+                                               ld_dst, n_feat, mode, eps, bias, nullptr, nullptr, 0,
+                                               gnm_cast_stream(stream));
         if (rc == GNM_OK || impl == 2 || (rc != GNM_ERR_TOO_LARGE && rc != GNM_ERR_ALIGN)) return rc;
     }
     AggDenseParams p;
@@ -340,4 +341,20 @@ extern "C" int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* no
     aggregate_dense_kernel<Cfg><<<grid, Cfg::THREADS, AD_SMEM_BYTES, gnm_cast_stream(stream)>>>(p);
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;
+}
+
+/* Aggregation of a BatchNorm-backward result that is never materialised: dst = Agg(cA*dy + cB*z + cC) with the
+ * per-channel coefficients of gnm_bn_bwd_coeffs applied to the rows as they are loaded (tcgen05 kernel only:
+ * GNM_ERR_TOO_LARGE / GNM_ERR_ALIGN when the batch does not fit it - apply gnm_bn_bwd_apply and aggregate then).
+ * No (1 + eps) self term: the epilogue would add the raw dy row, not the transformed one. */
+extern "C" int gnm_aggregate_dense_affine(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr,
+                                          int n_graphs, int n_max, const float* dy, int64_t ld_dy, const float* z,
+                                          int64_t ld_z, const float* coef, float* dst, int64_t ld_dst, int n_feat,
+                                          int mode, gnm_stream_t stream) {
+    if (n_graphs < 0 || n_max < 0 || n_feat < 0 || mode < 0 || mode > 2) return GNM_ERR_BAD_ARG;
+    if (n_graphs == 0 || n_max == 0 || n_feat == 0) return GNM_OK;
+    if (!bitmap_addr || !node_off || !dy || !z || !coef || !dst || (mode != 0 && !rowptr)) return GNM_ERR_BAD_ARG;
+    if ((n_feat % 4) || (ld_dy % 4) || (ld_dst % 4) || !gnm_aligned16(dy) || !gnm_aligned16(dst)) return GNM_ERR_ALIGN;
+    return gnm_launch_aggregate_tc(bitmap_addr, node_off, rowptr, n_graphs, n_max, dy, ld_dy, nullptr, dst, ld_dst, n_feat,
+                                   mode, nullptr, nullptr, coef, z, ld_z, gnm_cast_stream(stream));
 }

@@ -54,6 +54,11 @@ struct AggTcParams {
     const float* bias;
     int64_t ld_src, ld_dst;
     int n_graphs, n_feat, mode, n_slabs, kcores_max;
+    // optional per-column affine of two streams applied to the rows on load: h = cA*src + cB*aff_z + cC (BatchNorm
+    // backward folded into the aggregation of its result; aff_coef = [cA | cB | cC], each n_feat long)
+    const float* aff_coef;
+    const float* aff_z;
+    int64_t ld_aff_z;
     long long* dbg;              // nullable: per-CTA wait/busy cycle counters (profiling aid)
 };
 
@@ -292,6 +297,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                     const int jr = q.n0 + k;
                     const int64_t sr = p.src_map ? (int64_t)p.src_map[jr] : (int64_t)jr;
                     v = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
+                    if (p.aff_coef != nullptr) {
+                        const float4 zv = __ldg(reinterpret_cast<const float4*>(p.aff_z + sr * p.ld_aff_z + col));
+                        const float4 ca = __ldg(reinterpret_cast<const float4*>(p.aff_coef + col));
+                        const float4 cb = __ldg(reinterpret_cast<const float4*>(p.aff_coef + p.n_feat + col));
+                        const float4 cc = __ldg(reinterpret_cast<const float4*>(p.aff_coef + 2 * p.n_feat + col));
+                        v.x = fmaf(ca.x, v.x, fmaf(cb.x, zv.x, cc.x)); v.y = fmaf(ca.y, v.y, fmaf(cb.y, zv.y, cc.y));
+                        v.z = fmaf(ca.z, v.z, fmaf(cb.z, zv.z, cc.z)); v.w = fmaf(ca.w, v.w, fmaf(cb.w, zv.w, cc.w));
+                    }
                     if (p.mode == 2) {
                         const float w = 1.f / (float)(p.rowptr[jr + 1] - p.rowptr[jr]);
                         v.x *= w; v.y *= w; v.z *= w; v.w *= w;
@@ -410,8 +423,10 @@ static long long* g_tc_dbg_host = nullptr;   // profiling aid, see gnm_aggregate
 int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
                             int n_max, const float* src, int64_t ld_src, const int32_t* src_map, float* dst,
                             int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
-                            cudaStream_t stream) {
+                            const float* aff_coef, const float* aff_z, int64_t ld_aff_z, cudaStream_t stream) {
     if (n_max > TC_MAX_NODES) return GNM_ERR_TOO_LARGE;
+    if (aff_coef != nullptr && (aff_z == nullptr || (ld_aff_z % 4) || !gnm_aligned16(aff_z) || !gnm_aligned16(aff_coef)))
+        return GNM_ERR_ALIGN;
     if ((ld_dst % 4) || (ld_src % 4) || (n_feat % 4)) return GNM_ERR_ALIGN;
     int dev = 0, sms = 148, major = 0, smem_cap = 0;
     cudaGetDevice(&dev);
@@ -423,6 +438,7 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
     p.bitmap_addr = bitmap_addr; p.node_off = node_off; p.rowptr = rowptr; p.src = src; p.src_map = src_map;
     p.dst = dst; p.eps = eps; p.bias = bias; p.ld_src = ld_src; p.ld_dst = ld_dst; p.n_graphs = n_graphs;
     p.n_feat = n_feat; p.mode = mode;
+    p.aff_coef = aff_coef; p.aff_z = aff_z; p.ld_aff_z = ld_aff_z;
     p.dbg = g_tc_dbg_host;
     p.n_slabs = (n_feat + TC_SLAB - 1) / TC_SLAB;
     p.kcores_max = ((n_max + 15) / 16) * 2;

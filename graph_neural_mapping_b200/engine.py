@@ -307,6 +307,16 @@ class BatchStructure(object):
                                             src, src_map, dst, mode, eps, bias)
         return _ops.aggregate(self.rowptr, self.colidx, src, src_map, dst, mode, eps, bias)
 
+    def aggregate_affine(self, dy, z, coef, dst, mode):
+        """dst = Agg(coef[0]*dy + coef[1]*z + coef[2]) when the batch runs on the tcgen05 dense-block kernel (the affine
+        is applied to the rows as they are loaded); False, with nothing launched, otherwise."""
+        if self.bitmap_addr is None or FORCE_CSR_AGGREGATE or not _ops.dense_aggregate_ok(dy, dst):
+            return False
+        if mode != 0 and self.has_isolated:
+            return False
+        return _ops.aggregate_dense_affine(self.bitmap_addr, self.node_off, self.rowptr, self.n_graphs, self.n_max, dy, z,
+                                           coef, dst, mode)
+
     def set_pooling(self, graph_pooling_type, device):
         if graph_pooling_type == "average":
             # graphcnn.py:118-120: 1 / len(graph.g) per graph - from the device node offsets (no host copy: this also
@@ -638,8 +648,18 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                                 d_x = d_prev
                 grads[gi], grads[gi + 1] = dw, db
                 continue
-            _ops.bn_bwd_apply(u.z, u.mean, u.rstd, u.gamma, stats if use_batch else None, u.count, dy)
-            dz_u = dy                                                # now d loss / d z_j
+            g_agg = coef0 = None
+            if gather0 and not learn_eps:
+                # layer-0 gather unit: dz is only ever aggregated, so the BatchNorm-backward apply rides on the
+                # aggregation kernel's row loads (dz = A*dy + B*z + C is never written); d bias follows in closed form
+                coef0 = torch.empty(3, n_out, dtype=torch.float32, device=dev)
+                _ops.bn_bwd_coeffs(stats if use_batch else None, u.count, u.gamma, u.mean, u.rstd, coef0)
+                g_try = torch.empty(M, n_out, dtype=torch.float32, device=dev)
+                if bs.aggregate_affine(dy, u.z, coef0, g_try, bwd_mode):
+                    g_agg = g_try
+            if g_agg is None:
+                _ops.bn_bwd_apply(u.z, u.mean, u.rstd, u.gamma, stats if use_batch else None, u.count, dy)
+            dz_u = dy                                                # now d loss / d z_j (unless g_agg is set)
             if j > 0:
                 p = units[j - 1]
                 _ops.linear_wgrad(dz_u, p.z, p.scale, p.shift, dw, db)
@@ -650,18 +670,26 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
             # ---- first unit of the layer: input is the neighbour aggregation --------------------
             if gather0:
                 # z0 = Agg(W1^T[tags]) + b:  dW1^T[t] = sum_{tags[r]=t} (Agg^T dz)[r]
-                g_agg = torch.empty(M, n_out, dtype=torch.float32, device=dev)
-                bs.aggregate(dz_u, None, g_agg, bwd_mode, eps_l, None)
+                folded = g_agg is not None
+                if not folded:
+                    g_agg = torch.empty(M, n_out, dtype=torch.float32, device=dev)
+                    bs.aggregate(dz_u, None, g_agg, bwd_mode, eps_l, None)
                 dw1t = zp.f32(n_in, n_out)
                 if bs.same_tags and n_out % 4 == 0:
                     _ops.rows_period_sum(g_agg, bs.uniform_n, bs.tags, dw1t)     # a streaming sum over the graphs
                 else:
                     _ops.scatter_rows_add(g_agg, bs.tags, dw1t)
                 dw = dw1t.t().contiguous()
-                colsum, c_, o_ = zp.f64(2 * n_out)
-                _ops.col_stats(dz_u, colsum)                      # d bias = column sums of dz
-                from_f64.append((gi + 1, c_, o_, n_out, False))
-                db = None
+                if folded:
+                    # d bias = column sums of dz = A*sum(dy) + B*sum(z) + C*M. Under batch statistics that is identically
+                    # zero (m1 = sum(dy)/M and sum(z) = M*mean cancel; the reference gets rounding noise); with running
+                    # statistics B = C = 0 and it is A * sum(dy)
+                    db = zp.f32(n_out) if use_batch else coef0[0] * stats[:n_out].to(torch.float32)
+                else:
+                    colsum, c_, o_ = zp.f64(2 * n_out)
+                    _ops.col_stats(dz_u, colsum)                      # d bias = column sums of dz
+                    from_f64.append((gi + 1, c_, o_, n_out, False))
+                    db = None
                 if learn_eps:
                     _ops.dot_rows(dz_u, sv.w1t, bs.tags, d_eps[layer:layer + 1])
                 if need_x_grad:

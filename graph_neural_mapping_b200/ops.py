@@ -134,6 +134,25 @@ def aggregate_dense(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, src_map
     return dst
 
 
+TC_MAX_NODES = 416          # largest graph the tcgen05 aggregation kernel takes (gnm_aggregate_tc.cu)
+
+
+def aggregate_dense_affine(bitmap_addr, node_off, rowptr, n_graphs, n_max, dy, z, coef, dst, mode):
+    """dst = Agg(coef[0]*dy + coef[1]*z + coef[2]) on the tcgen05 kernel; returns False (nothing launched) when the
+    batch does not fit that kernel - the caller then applies the affine with bn_bwd_apply and aggregates."""
+    yp, ldy = _mat(dy)
+    zp, ldz = _mat(z)
+    dp, ldd = _mat(dst)
+    rc = _lib().gnm_aggregate_dense_affine(_ptr(bitmap_addr, torch.int64), _ptr(node_off, torch.int32),
+                                           _ptr(rowptr, torch.int32), n_graphs, n_max, yp, ldy, zp, ldz,
+                                           _ptr(coef, torch.float32), dp, ldd, int(dst.shape[1]), int(mode), _stream(dst))
+    if rc in (-2, -3):                      # GNM_ERR_TOO_LARGE / GNM_ERR_ALIGN: not a tcgen05 batch
+        LAUNCHES[0] -= 1
+        return False
+    _libmod.check(rc, "gnm_aggregate_dense_affine")
+    return True
+
+
 def dense_aggregate_ok(src, dst, bias=None):
     """Alignment contract of gnm_aggregate_dense (float4 row loads, float2 stores)."""
     return (dst.shape[1] % 4 == 0 and src.stride(0) % 4 == 0 and dst.stride(0) % 2 == 0 and

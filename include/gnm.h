@@ -32,7 +32,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 11
+#define GNM_ABI_VERSION 12
 
 typedef void* gnm_stream_t;
 
@@ -119,6 +119,14 @@ int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* node_off, con
                         int n_graphs, int n_max, const float* src, int64_t ld_src, const int32_t* src_map,
                         float* dst, int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
                         int impl, gnm_stream_t stream);
+/* dst = Agg(cA*dy + cB*z + cC): the aggregation of a BatchNorm-backward result (autograd of graphcnn.py:162-166 feeding
+ * the transpose of :154-161 at layer 0) without materialising it - coef = [cA | cB | cC] from gnm_bn_bwd_coeffs is
+ * applied to the rows as the tcgen05 kernel loads them. Returns GNM_ERR_TOO_LARGE / GNM_ERR_ALIGN when the batch does
+ * not fit that kernel (n_max > 416, odd strides): use gnm_bn_bwd_apply + gnm_aggregate* then. No eps self term
+ * (learn_eps models take the two-pass route). */
+int gnm_aggregate_dense_affine(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
+                               int n_max, const float* dy, int64_t ld_dy, const float* z, int64_t ld_z, const float* coef,
+                               float* dst, int64_t ld_dst, int n_feat, int mode, gnm_stream_t stream);
 /* *aborted = 1 if a tcgen05 kernel (aggregation or linear) launched since the last call ran into a (bounded) barrier-wait timeout
  * and drained without producing valid output. Synchronises the device; meant for tests / smoke checks. */
 int gnm_aggregate_tc_status(int* aborted);

@@ -113,6 +113,14 @@ def dense_aggregate_ok(src, dst, bias=None):
     return dst.shape[1] % 4 == 0
 
 
+def aggregate_dense_affine(bitmap_addr, node_off, rowptr, n_graphs, n_max, dy, z, coef, dst, mode):
+    if n_max > 416:
+        return False
+    dz = (coef[0].double() * dy.double() + coef[1].double() * z.double() + coef[2].double()).to(dy.dtype)
+    aggregate_dense(bitmap_addr, node_off, rowptr, n_graphs, n_max, dz, None, dst, mode, None)
+    return True
+
+
 def aggregate_dense(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, src_map, dst, mode, eps, bias=None, impl=None):
     """Contract of gnm_aggregate_dense: the adjacency is read from the per-graph bitmaps."""
     no = node_off.numpy()

@@ -438,6 +438,50 @@ def test_aggregate_dense_exactness_on_wide_dynamic_range():
     assert not ops.aggregate_tc_status()
 
 
+@pytest.mark.parametrize("counts,f,mode", [([12, 12, 12], 8, 0), ([400, 400, 400], 64, 0), ([37, 64, 5, 90, 1], 64, 0),
+                                           ([416, 129, 128, 400] * 40, 64, 0), ([48, 48], 12, 2), ([1000], 64, 0)])
+def test_aggregate_dense_affine(counts, f, mode):
+    """Aggregation of a BatchNorm-backward result folded into the row loads: Agg(cA*dy + cB*z + cC) must equal
+    bn_bwd_apply followed by the aggregation, and the fp64 stand-in; batches the tcgen05 kernel cannot take return False
+    without launching anything."""
+    rng = np.random.default_rng(len(counts) * 7 + f)
+    ems = [rand_graph_edges(rng, n, 0.3) for n in counts]
+    if mode != 0:
+        ems = [np.concatenate([e, np.stack([np.arange(n), (np.arange(n) + 1) % n]), np.stack([(np.arange(n) + 1) % n, np.arange(n)])], 1)
+               for e, n in zip(ems, counts)]
+        ems = [np.unique(e, axis=1) for e in ems]
+        ems = [e[:, e[0] != e[1]] for e in ems]
+    e, eo, no = build_inputs(ems, counts)
+    m = int(sum(counts))
+    self_loops = True                        # the folded path serves learn_eps == False models (self loop in Adj_block)
+    rp, ci, _ = ops.csr_build(e, eo, no, len(counts), max(counts), m, self_loops, False)
+    rpl, cil, _ = ops.csr_build(e, eo, no, len(counts), max(counts), m, self_loops, True)
+    bm, dup, addr, _ = _bitmaps(rpl, cil, no, counts)
+    torch.manual_seed(f + m)
+    dy, z = torch.randn(m, f, device=DEV), torch.randn(m, f, device=DEV) * 2 + 0.3
+    gamma, mean, rstd = torch.rand(f, device=DEV) + 0.5, torch.randn(f, device=DEV), torch.rand(f, device=DEV) + 0.5
+    stats = torch.randn(2 * f, dtype=torch.float64, device=DEV) * m
+    coef = torch.empty(3, f, device=DEV)
+    ops.bn_bwd_coeffs(stats, float(m), gamma, mean, rstd, coef)
+    out = torch.full((m, f), float("nan"), device=DEV)
+    launched = ops.aggregate_dense_affine(addr, no, rp, len(counts), max(counts), dy, z, coef, out, mode)
+    if max(counts) > 416:
+        assert launched is False and bool(torch.isnan(out).all())
+        return
+    assert launched is True
+    assert not ops.aggregate_tc_status(), "tcgen05 kernel hit a barrier timeout"
+    dz = dy.clone()
+    ops.bn_bwd_apply(z, mean, rstd, gamma, stats, float(m), dz)
+    two_pass = torch.empty(m, f, device=DEV)
+    ops.aggregate_dense(addr, no, rp, len(counts), max(counts), dz, None, two_pass, mode, None, None, impl=2)
+    assert_close(out, two_pass, 2e-5, "folded vs bn_bwd_apply + aggregate")
+    if len(counts) <= 8:
+        ref = torch.empty(m, f)
+        dzr = (coef[0].double() * dy.double() + coef[1].double() * z.double() + coef[2].double()).cpu()
+        emul_ops.aggregate(rp.cpu(), ci.cpu(), dzr.float(), None, ref, mode, None, None)
+        assert_close(out, ref, 2e-5, "folded vs fp64")
+
+
 @pytest.mark.parametrize("sizes,f,p,self_loops,eps", [([12, 12, 12], 8, 0.3, False, True), ([40, 17, 1, 33], 64, 0.2, True, False),
                                                       ([400, 400], 64, 0.3, False, True), ([9, 5], 70, 0.0, False, False),
                                                       ([30], 3, 0.5, True, False)])
