@@ -118,7 +118,7 @@ def run_reference(args):
 class OpTimer(object):
     """Wraps the ops entry points with CUDA events on the launching stream."""
 
-    NAMES = ["csr_build", "csr_batch_gather", "bitmap_build", "aggregate_dense_affine", "aggregate_dense", "aggregate", "dot_rows", "scatter_rows_add", "rows_period_sum", "linear", "linear_wgrad",
+    NAMES = ["csr_build", "csr_batch_gather", "bitmap_build", "aggregate_dense_relu_bn_bwd", "aggregate_dense_affine", "aggregate_dense", "aggregate", "dot_rows", "scatter_rows_add", "rows_period_sum", "linear", "linear_wgrad",
              "col_stats", "bn_bwd_coeffs", "linear_bwd", "bn_finalize", "bn_eval_affine", "bn_relu_readout", "relu_bn_bwd_reduce", "bn_bwd_apply",
              "gather_nf_rows", "dgi_score_fwd", "dgi_score_bwd", "rowdot_score"]
 

@@ -304,7 +304,8 @@ extern "C" int gnm_bitmap_build(const int32_t* rowptr, const int32_t* colidx, co
 int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
                             int n_max, const float* src, int64_t ld_src, const int32_t* src_map, float* dst,
                             int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
-                            const float* aff_coef, const float* aff_z, int64_t ld_aff_z, cudaStream_t stream);
+                            const float* aff_coef, const float* aff_z, int64_t ld_aff_z, const GnmReluBnBwdFuse* fuse,
+                            cudaStream_t stream);
 
 extern "C" int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr,
                                    int n_graphs, int n_max, const float* src, int64_t ld_src, const int32_t* src_map,
@@ -319,7 +320,7 @@ extern "C" int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* no
     if (impl < 0 || impl > 2) return GNM_ERR_BAD_ARG;
     if (impl != 1) {
         const int rc = gnm_launch_aggregate_tc(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, ld_src, src_map, dst,
-                                               ld_dst, n_feat, mode, eps, bias, nullptr, nullptr, 0,
+                                               ld_dst, n_feat, mode, eps, bias, nullptr, nullptr, 0, nullptr,
                                                gnm_cast_stream(stream));
         if (rc == GNM_OK || impl == 2 || (rc != GNM_ERR_TOO_LARGE && rc != GNM_ERR_ALIGN)) return rc;
     }
@@ -356,5 +357,31 @@ extern "C" int gnm_aggregate_dense_affine(const int64_t* bitmap_addr, const int3
     if (!bitmap_addr || !node_off || !dy || !z || !coef || !dst || (mode != 0 && !rowptr)) return GNM_ERR_BAD_ARG;
     if ((n_feat % 4) || (ld_dy % 4) || (ld_dst % 4) || !gnm_aligned16(dy) || !gnm_aligned16(dst)) return GNM_ERR_ALIGN;
     return gnm_launch_aggregate_tc(bitmap_addr, node_off, rowptr, n_graphs, n_max, dy, ld_dy, nullptr, dst, ld_dst, n_feat,
-                                   mode, nullptr, nullptr, coef, z, ld_z, gnm_cast_stream(stream));
+                                   mode, nullptr, nullptr, coef, z, ld_z, nullptr, gnm_cast_stream(stream));
+}
+
+/* Backward aggregation fused with its consumer: dy = relu'(bn(z)) * (Agg(src) [+ (1+eps) src] + d_pooled[g]*pool_scale[g]
+ * + d_score[r]*u[g] + d_neg[r]) and stats += [sum dy, sum dy*xhat] - gnm_aggregate_dense followed by
+ * gnm_relu_bn_bwd_reduce, without the round trip of the aggregated gradient through HBM (tcgen05 kernel only, n_feat <= 64:
+ * GNM_ERR_TOO_LARGE / GNM_ERR_ALIGN otherwise, nothing launched - run the two kernels then). */
+extern "C" int gnm_aggregate_dense_relu_bn_bwd(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr,
+                                               int n_graphs, int n_max, const float* src, int64_t ld_src, int n_feat,
+                                               int mode, const float* eps, const float* z, int64_t ldz,
+                                               const float* scale, const float* shift, const float* mean,
+                                               const float* rstd, const float* d_pooled, int64_t ld_dpooled,
+                                               const float* pool_scale, const float* d_score, const float* u, int64_t ldu,
+                                               const float* d_neg, int64_t ld_dneg, int n_neg, float* dy, int64_t lddy,
+                                               double* stats, gnm_stream_t stream) {
+    if (n_graphs < 0 || n_max < 0 || n_feat < 0 || mode < 0 || mode > 2) return GNM_ERR_BAD_ARG;
+    if (n_graphs == 0 || n_max == 0 || n_feat == 0) return GNM_OK;
+    if (!bitmap_addr || !node_off || !src || !dy || !z || !scale || !shift || !mean || !rstd || (mode != 0 && !rowptr))
+        return GNM_ERR_BAD_ARG;
+    if (d_score != nullptr && u == nullptr) return GNM_ERR_BAD_ARG;
+    if ((n_feat % 4) || (ld_src % 4) || (lddy % 4) || !gnm_aligned16(src) || !gnm_aligned16(dy)) return GNM_ERR_ALIGN;
+    GnmReluBnBwdFuse f;
+    f.z = z; f.ldz = ldz; f.scale = scale; f.shift = shift; f.mean = mean; f.rstd = rstd; f.d_pooled = d_pooled;
+    f.ld_dpooled = ld_dpooled; f.pool_scale = pool_scale; f.d_score = d_score; f.u = u; f.ldu = ldu; f.d_neg = d_neg;
+    f.ld_dneg = ld_dneg; f.n_neg = n_neg; f.stats = stats;
+    return gnm_launch_aggregate_tc(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, ld_src, nullptr, dy, lddy, n_feat,
+                                   mode, eps, nullptr, nullptr, nullptr, 0, &f, gnm_cast_stream(stream));
 }

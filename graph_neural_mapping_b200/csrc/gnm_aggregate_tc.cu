@@ -59,6 +59,15 @@ struct AggTcParams {
     const float* aff_coef;
     const float* aff_z;
     int64_t ld_aff_z;
+    // optional fused consumer of the aggregated rows (backward pass): dst = relu'(bn(rz)) * (Agg + d_pooled[g]*pool_scale[g]
+    // + d_score[r]*u[g] + d_neg[r]) and its BatchNorm-backward reduction, i.e. gnm_relu_bn_bwd_reduce applied in the
+    // copy-out instead of a separate pass over a materialised d_h (rz == NULL: plain aggregation)
+    const float* rz; int64_t ld_rz;
+    const float* r_scale; const float* r_shift; const float* r_mean; const float* r_rstd;
+    const float* r_dpooled; int64_t ld_dpooled; const float* r_pool_scale;
+    const float* r_dscore; const float* r_u; int64_t ld_u;
+    const float* r_dneg; int64_t ld_dneg; int r_nneg;
+    double* r_stats;
     long long* dbg;              // nullable: per-CTA wait/busy cycle counters (profiling aid)
 };
 
@@ -79,6 +88,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     float* sm_stg = reinterpret_cast<float*>(tc_smem + (size_t)24 * b_ncore_stride);   // TC_EPI_WARPS staging tiles
     // byte -> eight bf16 0/1 values (four 32-bit TMEM columns): the adjacency expansion is a table lookup
     uint4* lut = reinterpret_cast<uint4*>(tc_smem + (size_t)24 * b_ncore_stride + TC_EPI_WARPS * TC_STG);
+    // fused relu / BatchNorm backward only: one more tile per epilogue warp, the z rows of its slice (cp.async)
+    float* sm_zst = reinterpret_cast<float*>(tc_smem + (size_t)24 * b_ncore_stride + TC_EPI_WARPS * TC_STG + 4096);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < 256) {
@@ -117,14 +128,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         const uint32_t my_slot = warp >> 2;
         const int q = warp & 3;
         float* stg = sm_stg + warp * (32 * TC_PITCH);
+        // fused relu/BatchNorm backward (single 64-wide slab only): this lane's four columns are fixed
+        const bool fuse = p.rz != nullptr;
+        float4 r_sc = make_float4(0.f, 0.f, 0.f, 0.f), r_sh = r_sc, r_mu = r_sc, r_rs = r_sc;
+        float rs1[4] = {0.f, 0.f, 0.f, 0.f}, rs2[4] = {0.f, 0.f, 0.f, 0.f};
+        if (fuse && (lane & 15) * 4 < p.n_feat) {
+            const int c = (lane & 15) * 4;
+            r_sc = __ldg(reinterpret_cast<const float4*>(p.r_scale + c));
+            r_sh = __ldg(reinterpret_cast<const float4*>(p.r_shift + c));
+            r_mu = __ldg(reinterpret_cast<const float4*>(p.r_mean + c));
+            r_rs = __ldg(reinterpret_cast<const float4*>(p.r_rstd + c));
+        }
         for (int item = blockIdx.x; item < n_items && !*abort_flag; item += gridDim.x) {
             const int gi = item / p.n_slabs, slab = item % p.n_slabs;
             const int n0 = p.node_off[gi], n = p.node_off[gi + 1] - n0;
             const int f0 = slab * TC_SLAB;
             const int n_mt = (n + 127) >> 7;
+            float4 r_gp = make_float4(0.f, 0.f, 0.f, 0.f), r_uu = r_gp;
+            if (fuse && (lane & 15) * 4 < p.n_feat) {
+                const int c = (lane & 15) * 4;
+                if (p.r_dpooled != nullptr) {
+                    const float ps = p.r_pool_scale ? __ldg(p.r_pool_scale + gi) : 1.f;
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(p.r_dpooled + (int64_t)gi * p.ld_dpooled + c));
+                    r_gp = make_float4(t.x * ps, t.y * ps, t.z * ps, t.w * ps);
+                }
+                if (p.r_dscore != nullptr) r_uu = __ldg(reinterpret_cast<const float4*>(p.r_u + (int64_t)gi * p.ld_u + c));
+            }
             for (int mt = 0; mt < n_mt; ++mt, ++acc_it) {
                 const uint32_t slot = acc_it & 1, ph = (acc_it >> 1) & 1;
                 if (TC_EPI_WARPS == 8 && slot != my_slot) continue;
+                float ds_row = 0.f;
+                if (fuse && mt * 128 + q * 32 < n) {
+                    // the rows this warp will mask with arrive while it waits for the accumulator: z through cp.async
+                    // into its second staging tile (two rows per instruction, coalesced), d_score one row per lane
+                    const int zr0 = mt * 128 + q * 32;
+                    float* zst = sm_zst + warp * (32 * TC_PITCH);
+                    const uint32_t zst_u32 = smem_u32(zst);
+#pragma unroll 4
+                    for (int i = 0; i < 16; ++i) {
+                        const int rr = i * 2 + (lane >> 4), c4z = lane & 15;
+                        const bool okz = zr0 + rr < n && c4z * 4 < p.n_feat;
+                        const float* srcz = p.rz + (int64_t)(n0 + (okz ? zr0 + rr : 0)) * p.ld_rz + (okz ? c4z * 4 : 0);
+                        const uint32_t dstz = zst_u32 + (uint32_t)((rr * TC_PITCH + c4z * 4) * 4);
+                        const int nbytes = okz ? 16 : 0;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dstz), "l"(srcz), "r"(nbytes) : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    if (p.r_dscore != nullptr && zr0 + lane < n) ds_row = __ldg(p.r_dscore + n0 + zr0 + lane);
+                }
                 if (!mbar_wait<32>(&acc_full[slot], ph, abort_flag, DBG ? &w_acc : nullptr)) break;
                 tc_fence_after();
                 const int row0 = mt * 128 + q * 32;              // first row (within the graph) of this warp's slice
@@ -157,19 +208,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                         }
                     }
                 }
+                if (fuse) asm volatile("cp.async.wait_group 0;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[slot]);       // accumulator drained: the MMA may reuse the slot
                 if (any_rows) {
                     const int c4 = lane & 15;
                     const int col = f0 + c4 * 4;
-                    if (col < p.n_feat) {
+                    const bool col_ok = col < p.n_feat;
+                    {
                         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                        if (p.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll 4
                         for (int i = 0; i < 16; ++i) {
                             const int rr = i * 2 + (lane >> 4);
-                            if (row0 + rr >= n) continue;
+                            // d_score of row rr lives in lane rr: EVERY lane takes part in the shuffle (narrow layers
+                            // leave lanes without a column, tail tiles leave lanes without a row)
+                            const float ds = fuse ? __shfl_sync(GNM_FULL_MASK, ds_row, rr) : 0.f;
+                            if (!col_ok || row0 + rr >= n) continue;
                             const int g2 = n0 + row0 + rr;
                             float4 v = *reinterpret_cast<const float4*>(stg + rr * TC_PITCH + c4 * 4);
                             if (p.eps) {
@@ -179,11 +235,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                                 v.z = fmaf(self_c, sv.z, v.z); v.w = fmaf(self_c, sv.w, v.w);
                             }
                             v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                            if (fuse) {
+                                // gnm_relu_bn_bwd_reduce on the fly: add the readout / DGI gradients of this row, mask by
+                                // the ReLU of the layer below, accumulate sum(dy) and sum(dy * xhat)
+                                const float4 zv = *reinterpret_cast<const float4*>(sm_zst + warp * (32 * TC_PITCH) + rr * TC_PITCH + c4 * 4);
+                                v.x += r_gp.x; v.y += r_gp.y; v.z += r_gp.z; v.w += r_gp.w;
+                                if (p.r_dscore != nullptr) {
+                                    v.x = fmaf(ds, r_uu.x, v.x); v.y = fmaf(ds, r_uu.y, v.y);
+                                    v.z = fmaf(ds, r_uu.z, v.z); v.w = fmaf(ds, r_uu.w, v.w);
+                                }
+                                if (p.r_dneg != nullptr && g2 < p.r_nneg) {
+                                    const float4 dn = __ldg(reinterpret_cast<const float4*>(p.r_dneg + (int64_t)g2 * p.ld_dneg + col));
+                                    v.x += dn.x; v.y += dn.y; v.z += dn.z; v.w += dn.w;
+                                }
+                                v.x = (fmaf(zv.x, r_sc.x, r_sh.x) > 0.f) ? v.x : 0.f;
+                                v.y = (fmaf(zv.y, r_sc.y, r_sh.y) > 0.f) ? v.y : 0.f;
+                                v.z = (fmaf(zv.z, r_sc.z, r_sh.z) > 0.f) ? v.z : 0.f;
+                                v.w = (fmaf(zv.w, r_sc.w, r_sh.w) > 0.f) ? v.w : 0.f;
+                                rs1[0] += v.x; rs1[1] += v.y; rs1[2] += v.z; rs1[3] += v.w;
+                                rs2[0] = fmaf(v.x, (zv.x - r_mu.x) * r_rs.x, rs2[0]);
+                                rs2[1] = fmaf(v.y, (zv.y - r_mu.y) * r_rs.y, rs2[1]);
+                                rs2[2] = fmaf(v.z, (zv.z - r_mu.z) * r_rs.z, rs2[2]);
+                                rs2[3] = fmaf(v.w, (zv.w - r_mu.w) * r_rs.w, rs2[3]);
+                            }
                             *reinterpret_cast<float4*>(p.dst + (int64_t)g2 * p.ld_dst + col) = v;
                         }
                     }
                     __syncwarp();
                 }
+            }
+        }
+        if (fuse && p.r_stats != nullptr) {
+            // lanes l and l ^ 16 hold the same columns: fold, park the warp's 2 x 64 partial sums in its staging tile,
+            // add the epilogue warps in a fixed order, ONE fp64 atomic per column and CTA
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                rs1[u] += __shfl_xor_sync(GNM_FULL_MASK, rs1[u], 16);
+                rs2[u] += __shfl_xor_sync(GNM_FULL_MASK, rs2[u], 16);
+                if (lane < 16) {
+                    stg[lane * 4 + u] = rs1[u];
+                    stg[64 + lane * 4 + u] = rs2[u];
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+            if (tid < 128) {
+                float a = 0.f;
+#pragma unroll
+                for (int w = 0; w < TC_EPI_WARPS; ++w) a += sm_stg[w * (32 * TC_PITCH) + tid];
+                const int c = tid & 63;
+                if (c < p.n_feat) atomicAdd(&p.r_stats[(tid >> 6) * p.n_feat + c], (double)a);
             }
         }
         if (DBG && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_role; p.dbg[blockIdx.x * 16 + 1] = w_acc; }
@@ -423,8 +524,18 @@ static long long* g_tc_dbg_host = nullptr;   // profiling aid, see gnm_aggregate
 int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
                             int n_max, const float* src, int64_t ld_src, const int32_t* src_map, float* dst,
                             int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
-                            const float* aff_coef, const float* aff_z, int64_t ld_aff_z, cudaStream_t stream) {
+                            const float* aff_coef, const float* aff_z, int64_t ld_aff_z, const GnmReluBnBwdFuse* fuse,
+                            cudaStream_t stream) {
     if (n_max > TC_MAX_NODES) return GNM_ERR_TOO_LARGE;
+    if (fuse != nullptr) {
+        if (n_feat > TC_SLAB) return GNM_ERR_TOO_LARGE;             // the fused reduction keeps one 64-wide slab per lane
+        if ((fuse->ldz % 4) || !gnm_aligned16(fuse->z) || !gnm_aligned16(fuse->scale) || !gnm_aligned16(fuse->shift) ||
+            !gnm_aligned16(fuse->mean) || !gnm_aligned16(fuse->rstd) ||
+            (fuse->d_pooled && ((fuse->ld_dpooled % 4) || !gnm_aligned16(fuse->d_pooled))) ||
+            (fuse->d_score && ((fuse->ldu % 4) || !gnm_aligned16(fuse->u))) ||
+            (fuse->d_neg && ((fuse->ld_dneg % 4) || !gnm_aligned16(fuse->d_neg))))
+            return GNM_ERR_ALIGN;
+    }
     if (aff_coef != nullptr && (aff_z == nullptr || (ld_aff_z % 4) || !gnm_aligned16(aff_z) || !gnm_aligned16(aff_coef)))
         return GNM_ERR_ALIGN;
     if ((ld_dst % 4) || (ld_src % 4) || (n_feat % 4)) return GNM_ERR_ALIGN;
@@ -439,10 +550,20 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
     p.dst = dst; p.eps = eps; p.bias = bias; p.ld_src = ld_src; p.ld_dst = ld_dst; p.n_graphs = n_graphs;
     p.n_feat = n_feat; p.mode = mode;
     p.aff_coef = aff_coef; p.aff_z = aff_z; p.ld_aff_z = ld_aff_z;
+    p.rz = nullptr; p.ld_rz = 0; p.r_scale = p.r_shift = p.r_mean = p.r_rstd = nullptr;
+    p.r_dpooled = nullptr; p.ld_dpooled = 0; p.r_pool_scale = nullptr; p.r_dscore = nullptr; p.r_u = nullptr; p.ld_u = 0;
+    p.r_dneg = nullptr; p.ld_dneg = 0; p.r_nneg = 0; p.r_stats = nullptr;
+    if (fuse != nullptr) {
+        p.rz = fuse->z; p.ld_rz = fuse->ldz; p.r_scale = fuse->scale; p.r_shift = fuse->shift; p.r_mean = fuse->mean;
+        p.r_rstd = fuse->rstd; p.r_dpooled = fuse->d_pooled; p.ld_dpooled = fuse->ld_dpooled;
+        p.r_pool_scale = fuse->pool_scale; p.r_dscore = fuse->d_score; p.r_u = fuse->u; p.ld_u = fuse->ldu;
+        p.r_dneg = fuse->d_neg; p.ld_dneg = fuse->ld_dneg; p.r_nneg = fuse->n_neg; p.r_stats = fuse->stats;
+    }
     p.dbg = g_tc_dbg_host;
     p.n_slabs = (n_feat + TC_SLAB - 1) / TC_SLAB;
     p.kcores_max = ((n_max + 15) / 16) * 2;
-    const int smem = 24 * (p.kcores_max * 128 + 16) + TC_EPI_WARPS * TC_STG + 4096 + 1024;   // B planes + staging + LUT
+    // B planes + staging + LUT (+ the z tiles of the fused relu / BatchNorm backward)
+    const int smem = 24 * (p.kcores_max * 128 + 16) + TC_EPI_WARPS * TC_STG + 4096 + 1024 + (fuse ? TC_EPI_WARPS * TC_STG : 0);
     if (smem > smem_cap - 1024) return GNM_ERR_TOO_LARGE;
     const int64_t items = (int64_t)n_graphs * p.n_slabs;
     const int grid = (int)(items < sms ? items : sms);

@@ -46,3 +46,14 @@ __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
                  : "l"(p));
     return r;
 }
+
+// Optional fused consumer of the tcgen05 aggregation's output rows (gnm_aggregate_dense_relu_bn_bwd): the arguments of
+// gnm_relu_bn_bwd_reduce other than the aggregated gradient itself.
+struct GnmReluBnBwdFuse {
+    const float* z; int64_t ldz;
+    const float* scale; const float* shift; const float* mean; const float* rstd;
+    const float* d_pooled; int64_t ld_dpooled; const float* pool_scale;
+    const float* d_score; const float* u; int64_t ldu;
+    const float* d_neg; int64_t ld_dneg; int n_neg;
+    double* stats;
+};

@@ -307,6 +307,17 @@ class BatchStructure(object):
                                             src, src_map, dst, mode, eps, bias)
         return _ops.aggregate(self.rowptr, self.colidx, src, src_map, dst, mode, eps, bias)
 
+    def aggregate_relu_bn_bwd(self, src, mode, eps, unit, d_pooled, d_score, u, d_neg, n_neg, dy, stats):
+        """Backward aggregation of `src` fused with the relu / BatchNorm backward reduction of `unit` (the last unit of
+        the layer below) when the batch runs on the tcgen05 dense-block kernel; False, nothing launched, otherwise."""
+        if self.bitmap_addr is None or FORCE_CSR_AGGREGATE or FORCE_UNFUSED_BACKWARD or not _ops.dense_aggregate_ok(src, dy):
+            return False
+        if mode != 0 and self.has_isolated:
+            return False
+        return _ops.aggregate_dense_relu_bn_bwd(self.bitmap_addr, self.node_off, self.rowptr, self.n_graphs, self.n_max,
+                                                src, mode, eps, unit.z, unit.scale, unit.shift, unit.mean, unit.rstd,
+                                                d_pooled, self.pool_scale, d_score, u, d_neg, n_neg, dy, stats)
+
     def aggregate_affine(self, dy, z, coef, dst, mode):
         """dst = Agg(coef[0]*dy + coef[1]*z + coef[2]) when the batch runs on the tcgen05 dense-block kernel (the affine
         is applied to the rows as they are loaded); False, with nothing launched, otherwise."""
@@ -568,7 +579,28 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
     d_pooled = d_pooled.contiguous()
 
     d_h = None        # gradient reaching h_all[layer] from layer+1's aggregation
+    carry = None      # (dy, stats) of this layer's last unit when layer+1's aggregation kernel already produced them
     d_x = None
+
+    def aggregate_into_layer_below(layer, dp, eps_l):
+        """d_h of layer-1 = Agg^T(dp); fused with layer-1's relu / BatchNorm backward reduction when possible."""
+        below = sv.layers[layer - 1][-1]
+        slb = slice((layer - 1) * F, layer * F)
+        if layer not in sv.max_state and below.z.shape[1] == dp.shape[1]:
+            dy_b = torch.empty(M, dp.shape[1], dtype=torch.float32, device=dev)
+            st_b = zp.f64(2 * dp.shape[1])
+            if bs.aggregate_relu_bn_bwd(dp, bwd_mode, eps_l, below, d_pooled[:, slb], d_score,
+                                        u_mat[:, slb] if u_mat is not None else None,
+                                        d_neg[:, slb] if d_neg is not None else None, n_neg, dy_b, st_b[0]):
+                return None, (dy_b, st_b)
+        d_prev = torch.empty(M, dp.shape[1], dtype=torch.float32, device=dev)
+        if layer in sv.max_state:
+            amax, cmin = sv.max_state[layer]
+            _ops.aggregate_max_bwd(bs.rowptr, bs.colidx, dp, amax, cmin, eps_l, d_prev)
+        else:
+            bs.aggregate(dp, None, d_prev, bwd_mode, eps_l, None)
+        return d_prev, None
+
     pidx = 3 + 4 * sum(len(u) for u in sv.layers)
     for layer in range(L - 1, -1, -1):
         units = sv.layers[layer]
@@ -584,6 +616,9 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
             if pending is not None:
                 dy, (stats, st_chunk, st_off) = pending
                 pending = None
+            elif j == len(units) - 1 and carry is not None:
+                dy, (stats, st_chunk, st_off) = carry
+                carry = None
             else:
                 dy = torch.empty(M, n_out, dtype=torch.float32, device=dev)
                 stats, st_chunk, st_off = zp.f64(2 * n_out)
@@ -635,17 +670,15 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                         src = sv.x_dense if layer == 0 else h_prev
                         if learn_eps:
                             _ops.dot_rows(dp, src, None, d_eps[layer:layer + 1])
-                        if layer > 0 or need_x_grad:
-                            d_prev = torch.empty(M, n_in, dtype=torch.float32, device=dev)
+                        if layer > 0:
+                            d_h, carry = aggregate_into_layer_below(layer, dp, eps_l)
+                        elif need_x_grad:
+                            d_x = torch.empty(M, n_in, dtype=torch.float32, device=dev)
                             if layer in sv.max_state:
                                 amax, cmin = sv.max_state[layer]
-                                _ops.aggregate_max_bwd(bs.rowptr, bs.colidx, dp, amax, cmin, eps_l, d_prev)
+                                _ops.aggregate_max_bwd(bs.rowptr, bs.colidx, dp, amax, cmin, eps_l, d_x)
                             else:
-                                bs.aggregate(dp, None, d_prev, bwd_mode, eps_l, None)
-                            if layer > 0:
-                                d_h = d_prev
-                            else:
-                                d_x = d_prev
+                                bs.aggregate(dp, None, d_x, bwd_mode, eps_l, None)
                 grads[gi], grads[gi + 1] = dw, db
                 continue
             g_agg = coef0 = None
@@ -709,17 +742,15 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                     _ops.linear(dz_u, u.w, True, None, None, None, dp, None)
                     if learn_eps:
                         _ops.dot_rows(dp, src, None, d_eps[layer:layer + 1])
-                    if layer > 0 or need_x_grad:
-                        d_prev = torch.empty(M, n_in, dtype=torch.float32, device=dev)
+                    if layer > 0:
+                        d_h, carry = aggregate_into_layer_below(layer, dp, eps_l)
+                    elif need_x_grad:
+                        d_x = torch.empty(M, n_in, dtype=torch.float32, device=dev)
                         if layer in sv.max_state:
                             amax, cmin = sv.max_state[layer]
-                            _ops.aggregate_max_bwd(bs.rowptr, bs.colidx, dp, amax, cmin, eps_l, d_prev)
+                            _ops.aggregate_max_bwd(bs.rowptr, bs.colidx, dp, amax, cmin, eps_l, d_x)
                         else:
-                            bs.aggregate(dp, None, d_prev, bwd_mode, eps_l, None)
-                        if layer > 0:
-                            d_h = d_prev
-                        else:
-                            d_x = d_prev
+                            bs.aggregate(dp, None, d_x, bwd_mode, eps_l, None)
             grads[gi], grads[gi + 1] = dw, db
     # float64 accumulators -> float32 gradients, one conversion per pool buffer (and one more for the shares of the
     # synchronised BatchNorm reductions: after the all-reduce those are sums over ALL ranks of gradients of each

@@ -153,6 +153,29 @@ def aggregate_dense_affine(bitmap_addr, node_off, rowptr, n_graphs, n_max, dy, z
     return True
 
 
+def aggregate_dense_relu_bn_bwd(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, mode, eps, z, scale, shift, mean, rstd,
+                                d_pooled, pool_scale, d_score, u, d_neg, n_neg, dy, stats):
+    """aggregate_dense(src) -> relu_bn_bwd_reduce(z, ...) in one tcgen05 kernel (the aggregated gradient is consumed in
+    the copy-out). Returns False, with nothing launched, when the batch does not fit that kernel."""
+    sp, lds = _mat(src)
+    zp, ldz = _mat(z)
+    gp, ldg = _mat(d_pooled)
+    up, ldu = _mat(u)
+    np_, ldn = _mat(d_neg)
+    yp, ldy = _mat(dy)
+    rc = _lib().gnm_aggregate_dense_relu_bn_bwd(_ptr(bitmap_addr, torch.int64), _ptr(node_off, torch.int32),
+                                                _ptr(rowptr, torch.int32), n_graphs, n_max, sp, lds, int(dy.shape[1]),
+                                                int(mode), _ptr(eps, torch.float32), zp, ldz, _ptr(scale), _ptr(shift),
+                                                _ptr(mean), _ptr(rstd), gp, ldg, _ptr(pool_scale, torch.float32),
+                                                _ptr(d_score, torch.float32), up, ldu, np_, ldn, int(n_neg), yp, ldy,
+                                                _ptr(stats, torch.float64), _stream(dy))
+    if rc in (-2, -3):                      # GNM_ERR_TOO_LARGE / GNM_ERR_ALIGN: not a tcgen05 batch
+        LAUNCHES[0] -= 1
+        return False
+    _libmod.check(rc, "gnm_aggregate_dense_relu_bn_bwd")
+    return True
+
+
 def dense_aggregate_ok(src, dst, bias=None):
     """Alignment contract of gnm_aggregate_dense (float4 row loads, float2 stores)."""
     return (dst.shape[1] % 4 == 0 and src.stride(0) % 4 == 0 and dst.stride(0) % 2 == 0 and

@@ -32,7 +32,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 12
+#define GNM_ABI_VERSION 13
 
 typedef void* gnm_stream_t;
 
@@ -127,6 +127,17 @@ int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* node_off, con
 int gnm_aggregate_dense_affine(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
                                int n_max, const float* dy, int64_t ld_dy, const float* z, int64_t ld_z, const float* coef,
                                float* dst, int64_t ld_dst, int n_feat, int mode, gnm_stream_t stream);
+/* Backward aggregation fused with its consumer (autograd of graphcnn.py:154-166 across two layers): what
+ * gnm_aggregate_dense(src -> d_h) followed by gnm_relu_bn_bwd_reduce(z, ..., d_h, ...) computes, with the ReLU mask, the
+ * readout / DGI gradient terms and the BatchNorm-backward reduction applied in the aggregation kernel's copy-out, so the
+ * aggregated gradient never makes the round trip through HBM. tcgen05 kernel only and n_feat <= 64: returns
+ * GNM_ERR_TOO_LARGE / GNM_ERR_ALIGN (nothing launched) otherwise - run the two kernels then. Arguments as in those two. */
+int gnm_aggregate_dense_relu_bn_bwd(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
+                                    int n_max, const float* src, int64_t ld_src, int n_feat, int mode, const float* eps,
+                                    const float* z, int64_t ldz, const float* scale, const float* shift, const float* mean,
+                                    const float* rstd, const float* d_pooled, int64_t ld_dpooled, const float* pool_scale,
+                                    const float* d_score, const float* u, int64_t ldu, const float* d_neg, int64_t ld_dneg,
+                                    int n_neg, float* dy, int64_t lddy, double* stats, gnm_stream_t stream);
 /* *aborted = 1 if a tcgen05 kernel (aggregation or linear) launched since the last call ran into a (bounded) barrier-wait timeout
  * and drained without producing valid output. Synchronises the device; meant for tests / smoke checks. */
 int gnm_aggregate_tc_status(int* aborted);

@@ -113,6 +113,17 @@ def dense_aggregate_ok(src, dst, bias=None):
     return dst.shape[1] % 4 == 0
 
 
+def aggregate_dense_relu_bn_bwd(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, mode, eps, z, scale, shift, mean, rstd,
+                                d_pooled, pool_scale, d_score, u, d_neg, n_neg, dy, stats):
+    if n_max > 416 or dy.shape[1] > 64:
+        return False
+    d_h = torch.empty_like(dy)
+    aggregate_dense(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, None, d_h, mode, eps)
+    relu_bn_bwd_reduce(z, scale, shift, mean, rstd, d_h, d_pooled, pool_scale, d_score, u, d_neg, n_neg, node_off, n_graphs,
+                       dy, stats)
+    return True
+
+
 def aggregate_dense_affine(bitmap_addr, node_off, rowptr, n_graphs, n_max, dy, z, coef, dst, mode):
     if n_max > 416:
         return False

@@ -438,6 +438,57 @@ def test_aggregate_dense_exactness_on_wide_dynamic_range():
     assert not ops.aggregate_tc_status()
 
 
+@pytest.mark.parametrize("counts,f,mode,eps_on,terms", [([12, 12, 12], 8, 0, True, "all"), ([400, 400, 400], 64, 0, False, "all"),
+                                                        ([37, 64, 5, 90, 1], 64, 0, True, "none"),
+                                                        ([400, 129, 128, 399] * 40, 64, 0, False, "all"), ([416, 100], 64, 0, False, "all"),
+                                                        ([48, 48], 12, 2, False, "pooled"), ([400] * 5, 128, 0, False, "all")])
+def test_aggregate_dense_relu_bn_bwd(counts, f, mode, eps_on, terms):
+    """The backward aggregation fused with relu / BatchNorm backward of the layer below must equal aggregate_dense
+    followed by relu_bn_bwd_reduce: dy, and the reduction [sum dy, sum dy*xhat]; wider layers return False untouched."""
+    rng = np.random.default_rng(len(counts) * 11 + f)
+    ems = [rand_graph_edges(rng, n, 0.3) for n in counts]
+    if mode != 0:
+        ems = [np.concatenate([e, np.stack([np.arange(n), (np.arange(n) + 1) % n]), np.stack([(np.arange(n) + 1) % n, np.arange(n)])], 1)
+               for e, n in zip(ems, counts)]
+        ems = [np.unique(e, axis=1) for e in ems]
+        ems = [e[:, e[0] != e[1]] for e in ems]
+    e, eo, no = build_inputs(ems, counts)
+    m, b = int(sum(counts)), len(counts)
+    rp, ci, _ = ops.csr_build(e, eo, no, b, max(counts), m, not eps_on, False)
+    rpl, cil, _ = ops.csr_build(e, eo, no, b, max(counts), m, not eps_on, True)
+    bm, dup, addr, _ = _bitmaps(rpl, cil, no, counts)
+    torch.manual_seed(f + m)
+    src, z = torch.randn(m, f, device=DEV), torch.randn(m, f, device=DEV)
+    scale, shift = torch.rand(f, device=DEV) + 0.5, torch.randn(f, device=DEV) * 0.3
+    mean, rstd = torch.randn(f, device=DEV), torch.rand(f, device=DEV) + 0.5
+    eps = torch.tensor([0.3], device=DEV) if eps_on else None
+    L = 3
+    d_pooled = torch.randn(b, L * f, device=DEV)[:, f:2 * f] if terms in ("all", "pooled") else None      # strided slice
+    pool_scale = torch.rand(b, device=DEV) + 0.5 if terms == "all" else None
+    d_score = torch.randn(m, device=DEV) if terms == "all" else None
+    u = torch.randn(b, L * f, device=DEV)[:, f:2 * f] if terms == "all" else None
+    n_neg = min(m, 7 * b) if terms == "all" else 0
+    d_neg = torch.randn(max(n_neg, 1), L * f, device=DEV)[:, f:2 * f] if terms == "all" else None
+    dy = torch.full((m, f), float("nan"), device=DEV)
+    st = torch.zeros(2 * f, dtype=torch.float64, device=DEV)
+    launched = ops.aggregate_dense_relu_bn_bwd(addr, no, rp, b, max(counts), src, mode, eps, z, scale, shift, mean, rstd,
+                                               d_pooled, pool_scale, d_score, u, d_neg, n_neg, dy, st)
+    if f > 64 or max(counts) > 400:
+        # wider layers / graphs above 400 nodes (no room for the z tiles next to the operand planes): untouched
+        assert launched is False and bool(torch.isnan(dy).all()) and float(st.abs().sum()) == 0.0
+        return
+    assert launched is True
+    assert not ops.aggregate_tc_status(), "tcgen05 kernel hit a barrier timeout"
+    d_h = torch.empty(m, f, device=DEV)
+    ops.aggregate_dense(addr, no, rp, b, max(counts), src, None, d_h, mode, eps, None, impl=2)
+    dy2 = torch.empty(m, f, device=DEV)
+    st2 = torch.zeros(2 * f, dtype=torch.float64, device=DEV)
+    ops.relu_bn_bwd_reduce(z, scale, shift, mean, rstd, d_h, d_pooled, pool_scale, d_score, u, d_neg, n_neg, no, b, dy2, st2)
+    assert_close(dy, dy2, 1e-6, "fused dy vs aggregate + relu_bn_bwd_reduce")
+    assert torch.equal(dy == 0, dy2 == 0), "same ReLU mask"
+    assert_close(st, st2, 1e-6, "fused BatchNorm-backward reduction")
+
+
 @pytest.mark.parametrize("counts,f,mode", [([12, 12, 12], 8, 0), ([400, 400, 400], 64, 0), ([37, 64, 5, 90, 1], 64, 0),
                                            ([416, 129, 128, 400] * 40, 64, 0), ([48, 48], 12, 2), ([1000], 64, 0)])
 def test_aggregate_dense_affine(counts, f, mode):
