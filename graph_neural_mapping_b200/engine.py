@@ -438,7 +438,24 @@ def _bn_affine(unit, stats, count, training, comm):
     return use_batch
 
 
-def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm):
+def first_argmax_from_padded(h, padded, cmin_values):
+    """Arg-max of `torch.max(h_with_dummy[padded], dim=1)` (graphcnn.py:139-142) with the reference's tie rule - the FIRST
+    entry of the padded neighbour list that attains the maximum - as source row ids ([M, F] int32, M = the dummy row).
+    Structurally equivalent nodes (same closed neighbourhood) carry identical features, so exact ties at positive values
+    do occur; parameter gradients do not care which of the tied nodes receives the gradient, the input gradient
+    (saliency) does. `padded` [M, W] int64 with -1 pads; torch glue, used for the small batches of compute_saliency."""
+    m = h.shape[0]
+    hw = torch.cat([h, cmin_values.reshape(1, -1).to(h.dtype)], 0)
+    idx = torch.where(padded >= 0, padded, torch.full_like(padded, m))
+    vals = hw[idx]                                                   # [M, W, F]
+    best = vals.max(1, keepdim=True)[0]
+    at_max = vals == best
+    first = at_max & (at_max.to(torch.int32).cumsum(1) == 1)         # exactly one True per (row, feature)
+    pos = first.to(torch.float32).argmax(1)                          # [M, F]
+    return idx.gather(1, pos).to(torch.int32)
+
+
+def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm, max_padded=None):
     """graphcnn.py:194-251 (and :254-294 when with_dgi is False). Returns (g_f, d_logit, saved)."""
     dev = params[0].device
     L, F = model.num_layers, model.hidden_dim
@@ -496,6 +513,9 @@ def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm):
                         cmin = _ops.col_min(src)
                         amax = torch.empty(M, src.shape[1], dtype=torch.int32, device=dev)
                         _ops.aggregate_max(bs.rowptr, bs.colidx, src, cmin, eps_l, pooled, amax)
+                        if max_padded is not None:
+                            # an input gradient is wanted: ties must go where torch.max sends them (list order)
+                            amax = first_argmax_from_padded(src, max_padded, _ops.col_min_values(cmin)).contiguous()
                         sv.max_state[layer] = (amax, cmin)
                     else:
                         bs.aggregate(src, None, pooled, 1 if average else 0, eps_l, None)
@@ -531,7 +551,36 @@ def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm):
     return g_f, d_logit, sv
 
 
-def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
+def max_pool_onehot_input_grad(bs, p, first, eps):
+    """Gradient of `maxpool(X) [+ (1 + eps) X]` (graphcnn.py:137-143 on the one-hot layer-0 input) wrt X, given
+    p = d loss / d pooled [M, D]. torch.max sends the gradient of entry (i, d) to ONE member of node i's padded
+    neighbour list: the member whose tag is d (value 1, unique for injective tags) if there is one, else - every
+    candidate ties at 0 - the FIRST entry of the list (`first[i]`, the reference's neighbour order; -1 = the list
+    holds pads only, the gradient then lands on the row that supplied the dummy row's minimum). [B, L*F]-style glue in
+    torch (saliency runs one graph, or a few, per call)."""
+    m, d = p.shape
+    dev = p.device
+    tags = bs.tags.long()
+    rp, ci = bs.rowptr.long(), bs.colidx.long()
+    rows = torch.repeat_interleave(torch.arange(m, device=dev), rp[1:] - rp[:-1])
+    hit_cols = tags[ci]                                              # list member ci holds a 1 in column tags[ci]
+    d_x = torch.zeros(m, d, dtype=p.dtype, device=dev)
+    d_x.index_put_((ci, hit_cols), p[rows, hit_cols], accumulate=True)
+    has_one = torch.zeros(m, d, dtype=torch.bool, device=dev)
+    has_one[rows, hit_cols] = True
+    rest = p.masked_fill(has_one, 0.0)                               # columns in which every candidate is 0
+    ok = first >= 0
+    d_x.index_add_(0, first[ok], rest[ok])
+    if bool((~ok).any()):
+        cols = torch.arange(d, device=dev)
+        r_min = torch.where(tags[0] == cols, 1, 0)                   # first row whose entry in column d is the minimum 0
+        d_x.index_put_((r_min, cols), rest[~ok].sum(0), accumulate=True)
+    if eps is not None:
+        d_x += (1.0 + eps) * p
+    return d_x
+
+
+def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm, max_first=None):
     """Hand-derived backward of `run_forward`. Returns (dX or None, [grad per flat param])."""
     bs = sv.bs
     dev = params[0].device
@@ -682,7 +731,7 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                 grads[gi], grads[gi + 1] = dw, db
                 continue
             g_agg = coef0 = None
-            if gather0 and not learn_eps:
+            if gather0 and not learn_eps and not (need_x_grad and model.neighbor_pooling_type == "max"):
                 # layer-0 gather unit: dz is only ever aggregated, so the BatchNorm-backward apply rides on the
                 # aggregation kernel's row loads (dz = A*dy + B*z + C is never written); d bias follows in closed form
                 coef0 = torch.empty(3, n_out, dtype=torch.float32, device=dev)
@@ -727,10 +776,14 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm):
                     _ops.dot_rows(dz_u, sv.w1t, bs.tags, d_eps[layer:layer + 1])
                 if need_x_grad:
                     if model.neighbor_pooling_type == "max":
-                        raise NotImplementedError("input gradients (compute_saliency) under neighbor_pooling_type='max' "
-                                                  "with one-hot features: torch.max routes the gradient of every tied "
-                                                  "zero entry by the reference's neighbour-list order (graphcnn.py:141), "
-                                                  "which the device CSR does not keep")
+                        if max_first is None:
+                            raise RuntimeError("input gradients under max pooling need the neighbour-list order "
+                                               "(use compute_saliency / compute_saliency_batched)")
+                        dp0 = torch.empty(M, n_in, dtype=torch.float32, device=dev)
+                        _ops.linear(dz_u, u.w, True, None, None, None, dp0, None)    # d loss / d pooled_0 = dz @ W1
+                        d_x = max_pool_onehot_input_grad(bs, dp0, max_first, eps_l)
+                        grads[gi], grads[gi + 1] = dw, db
+                        continue
                     d_x = torch.empty(M, n_in, dtype=torch.float32, device=dev)
                     _ops.linear(g_agg, u.w, True, None, None, None, d_x, None)   # (Agg^T dz) @ W1
             else:
@@ -771,7 +824,7 @@ class GINFunction(torch.autograd.Function):
     def forward(ctx, runner, x_dense, *params):
         g_f, d_logit, sv = run_forward(runner.model, runner.bs, runner.neg_idx, runner.training, runner.with_dgi,
                                        x_dense.detach() if x_dense is not None else None,
-                                       [p.detach() for p in params], runner.comm)
+                                       [p.detach() for p in params], runner.comm, max_padded=runner.max_padded)
         ctx.runner = runner
         ctx.sv = sv
         ctx.params = params
@@ -787,7 +840,7 @@ class GINFunction(torch.autograd.Function):
             dd_logit = None
         need_x = ctx.need_x or runner.want_x_grad
         d_x, grads = run_backward(runner.model, sv, [p.detach() for p in ctx.params], dg_f, dd_logit, need_x,
-                                  runner.comm)
+                                  runner.comm, max_first=runner.max_first)
         runner.x_grad = d_x
         out = []
         for p, g in zip(ctx.params, grads):
@@ -806,4 +859,6 @@ class Runner(object):
         self.with_dgi = with_dgi
         self.comm = comm
         self.want_x_grad = want_x_grad
+        self.max_first = None          # max pooling + input gradient: first neighbour-list entry per node (global ids)
+        self.max_padded = None         # ... and the padded neighbour lists themselves ([M, W] int64, -1 pads)
         self.x_grad = None

@@ -123,6 +123,45 @@ class GIN_InfoMaxReg(nn.Module):
             return None                 # layer 0 runs as a row gather of W1^T
         return torch.cat([g.node_features for g in batch_graph], 0).to(self.eps.device, torch.float32)
 
+    def _padded_neighbours(self, batch_graph):
+        """The padded neighbour lists of graphcnn.py:55-81 as global row ids ([M, W] int64, -1 pads; the node itself
+        appended when learn_eps is False) and their first entries ([M], -1 where the list starts with a pad).
+        torch.max breaks ties towards the first list entry, so input gradients under max pooling need the reference's
+        neighbour ORDER: `graph.neighbors` (util.py:86-90) when the graph carries it, else rebuilt from `edge_mat`,
+        whose first half lists the edges in the same order (util.py:99-103)."""
+        lists = []
+        for g in batch_graph:
+            n = len(g.g)
+            nb = getattr(g, "neighbors", None)
+            if nb is None or len(nb) != n or not any(len(x) for x in nb):
+                nb = [[] for _ in range(n)]
+                em = g.edge_mat
+                if torch.is_tensor(em) and em.numel() > 0:
+                    e = em.reshape(2, -1)
+                    e = e[:, :e.shape[1] // 2].cpu().numpy()
+                    for a, b in zip(e[0].tolist(), e[1].tolist()):
+                        nb[a].append(b)
+                        nb[b].append(a)
+            lists.append(nb)
+        max_deg = max((len(x) for nb in lists for x in nb), default=0)
+        width = max_deg + (0 if self.learn_eps else 1)
+        m = sum(len(nb) for nb in lists)
+        padded = np.full((m, max(width, 1)), -1, dtype=np.int64)
+        first = np.full(m, -1, dtype=np.int64)
+        row = 0
+        for nb in lists:
+            start = row
+            for j, x in enumerate(nb):
+                if x:
+                    padded[row, :len(x)] = np.asarray(x, dtype=np.int64) + start
+                    first[row] = x[0] + start
+                if not self.learn_eps:
+                    padded[row, max_deg] = start + j                    # graphcnn.py:73-75: the node itself, last
+                    if not x and max_deg == 0:
+                        first[row] = start + j
+                row += 1
+        return torch.from_numpy(padded), torch.from_numpy(first)
+
     def _heads(self, g_f):
         """graphcnn.py:228-231: sum over layers of dropout(Linear(pooled_h))."""
         f = self.hidden_dim
@@ -170,6 +209,11 @@ class GIN_InfoMaxReg(nn.Module):
         self.zero_grad()
         bs = self._structure(batch_graph)
         runner = _engine.Runner(self, bs, None, False, False, _dist.SINGLE, want_x_grad=True)
+        if self.neighbor_pooling_type == "max":
+            # input gradients under max pooling follow the reference's tie rule (first entry of the padded list)
+            padded, first = self._padded_neighbours(batch_graph)
+            runner.max_padded = padded.to(self.eps.device)
+            runner.max_first = first.to(self.eps.device)
         x = self._dense_features(batch_graph, bs)
         if x is not None:
             x.requires_grad_()

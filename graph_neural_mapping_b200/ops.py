@@ -226,6 +226,20 @@ def col_min(h):
     return packed
 
 
+def col_min_values(packed):
+    """The float32 column minima held in the high words of col_min()'s packed keys (inverse of the order key)."""
+    key = (packed >> 32) & 0xFFFFFFFF
+    bits = torch.where((key & 0x80000000) != 0, key & 0x7FFFFFFF, (~key) & 0xFFFFFFFF)
+    return _bits_to_float(bits)
+
+
+def _bits_to_float(bits_i64):
+    # int64 holding a 32-bit pattern -> float32 with that pattern
+    lo = (bits_i64 & 0x7FFFFFFF).to(torch.int32)
+    lo = torch.where((bits_i64 & 0x80000000) != 0, lo | torch.tensor(-0x80000000, dtype=torch.int32, device=bits_i64.device), lo)
+    return lo.view(torch.float32)
+
+
 def aggregate_max(rowptr, colidx, h, cmin, eps, out, argmax):
     hp, ldh = _mat(h)
     op, ldo = _mat(out)

@@ -179,6 +179,10 @@ def col_min(h):
     return (v, first)
 
 
+def col_min_values(cmin):
+    return cmin[0]
+
+
 def aggregate_max(rowptr, colidx, h, cmin, eps, out, argmax):
     m, f = h.shape
     rp, ci = rowptr.long(), colidx.long()

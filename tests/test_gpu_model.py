@@ -100,11 +100,6 @@ def test_eval_latent_saliency_vs_reference(name):
     c1, d1 = model([graphs[0]])
     assert_close(c1, g.z["eval1/c_logit"], TOL, "eval1 c")
     assert_close(d1, g.z["eval1/d_logit"], TOL, "eval1 d")
-    if g.cfg["neighbor_pooling_type"] == "max":
-        # one-hot input gradients under max pooling depend on the reference's neighbour-list order at tied zeros
-        with pytest.raises(NotImplementedError):
-            model.compute_saliency([graphs[0]], 1)
-        return
     for k, v in g.group("saliency/").items():
         gi, cls = int(k[1:k.index("_")]), int(k[-1])
         s = model.compute_saliency([graphs[gi]], cls)
@@ -116,6 +111,8 @@ def test_eval_latent_saliency_vs_reference(name):
             for kk, p in model.named_parameters():
                 if kk in ref:
                     assert_close(p.grad, ref[kk], TOL_GRAD, "saliency param grad " + kk, floor=floor)
+    if g.cfg["neighbor_pooling_type"] == "max":
+        return      # the dummy row of max pooling is the batch-wide minimum (graphcnn.py:140): isolated nodes couple graphs
     # batched saliency == per-graph saliency (eval-mode BN, block-diagonal adjacency)
     cls = 1
     sb = model.compute_saliency_batched(graphs[:2], cls)
