@@ -10,7 +10,8 @@
  *
  * Conventions (all entry points):
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked host;
- *   - no hidden allocation, no internal synchronisation, no global state: work is enqueued
+ *   - no hidden allocation, no internal synchronisation, no global state (except the explicitly named A/B switches,
+ *     status flags and the gnm_p2p_* buffers): work is enqueued
  *     on `stream` (a cudaStream_t passed as void*, e.g. torch.cuda.current_stream().cuda_stream)
  *     and the call returns immediately;
  *   - return 0 on success, a negative GNM_ERR_* for rejected arguments, or a positive
