@@ -3,24 +3,28 @@
 // Same contract as aggregate_dense_kernel (gnm_aggregate_dense.cu): per graph P_g = A_g . H_g with A_g a dense
 // 0/1 block expanded from the graph's bitmap and H_g (fp32) split exactly into three bf16 planes. The legacy
 // mma.sync path tops out near 200 TFLOP/s on this part (measured: 16 warps change nothing, ~0.35 kMAC/clk/SM);
-// tcgen05 runs the same bf16 MACs at 4 kMAC/clk/SM, which moves the kernel from tensor-bound to HBM-bound.
+// tcgen05 runs the same bf16 MACs at 4 kMAC/clk/SM: the MMAs need a third of the kernel's cycles, the rest is the
+// producers' instruction stream and the load latency in front of it (profiles/r1_aggregate_tcgen05*_ncu.txt).
 //
 // One persistent CTA per SM, work item = (graph, 64-feature slab), N <= 416 nodes:
 //   * B operand = the three planes side by side as ONE [K x 192] MN-major matrix (no swizzle; core matrix
 //     = 8 k-rows x 16 B; n-cores at SBO, k-cores at LBO), resident in shared memory for the whole graph
 //     (154 KB). N = 192 per MMA reads the A tile once for all three planes and keeps shared-memory traffic
 //     under the MMA time: 2(M+N)/(MN) = 0.026 B/MAC.
-//   * A operand = 128-row x 64-column tiles of the adjacency, expanded from bitmap words into bf16 0/1 pairs in
-//     registers and written to TENSOR MEMORY (tcgen05.st, lane = row, 32 columns per stage, 4-stage ring); the
-//     MMA takes A from TMEM ([a_tmem] form). A in shared memory was measured first: MMA operand fetch (A 4 KB
-//     + B 6 KB per 96-cycle MMA = 107 B/clk of the 128 B/clk shared-memory pipe) starved the producers' stores.
-//   * D = 128 lanes x 192 fp32 columns in TMEM (columns 0-383: two slots; A ring in columns 384-511): the 4 epilogue warps drain slot s (tcgen05.ld,
-//     hi+mid+lo summed in registers, average / eps self term / bias, fp32 stores) while the MMA thread fills
-//     slot s^1 with the next 128-row tile.
-//   * warp roles: 0-7 epilogue (two groups, one per accumulator slot), 8-15 producers, 16 MMA issue + TMEM alloc
-//     (highest warp id: issue priority); mbarriers: a_full/a_empty[4],
+//   * A operand = 128-row x 64-column tiles of the adjacency, expanded from bitmap bytes through a 256-entry
+//     byte -> 4 x bf16x2 table and written to TENSOR MEMORY (tcgen05.st, lane = row, 32 columns per stage, 4-stage
+//     ring); the MMA takes A from TMEM ([a_tmem] form). A in shared memory was measured first: MMA operand fetch
+//     (A 4 KB + B 6 KB per 96-cycle MMA = 107 B/clk of the 128 B/clk shared-memory pipe) starved the producers' stores.
+//   * D = 128 lanes x 192 fp32 columns in TMEM (columns 0-383: two slots; A ring in columns 384-511): the epilogue
+//     warps drain slot s (tcgen05.ld, hi+mid+lo summed in registers, staged through shared memory, coalesced
+//     stores with average / eps self term / bias applied on the way) while the MMA thread fills slot s^1.
+//   * warp roles: 0-3 epilogue, 4-11 producers (two independent groups of four; a stage belongs to one group),
+//     12 MMA issue + TMEM alloc (highest warp id: issue priority); mbarriers: a_full/a_empty[4],
 //     acc_full/acc_empty[2], b_free. tcgen05.commit releases A stages / publishes accumulators. The B planes
-//     of an item are written chunk by chunk together with the A stages of its first row tile.
+//     of an item are written chunk by chunk together with the A stages of its first row tile; item parameters and the
+//     next item's first loads are requested one item / one row tile ahead.
+//   * optional fusions on the same kernel: a per-column affine of two streams applied to the B rows on load
+//     (gnm_aggregate_dense_affine) and a consumer of the output rows in the copy-out (gnm_aggregate_dense_relu_bn_bwd).
 //   * every wait is bounded: on a timeout the kernel raises an abort flag and drains instead of hanging.
 #include <cuda_bf16.h>
 
@@ -39,7 +43,7 @@ constexpr int TC_MAX_NODES = 416;
 constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 8;       // 4: one epilogue group drains both slots; 8: one group per slot
 constexpr int TC_PITCH = TC_SLAB + 4;                    // floats per staged output row (272 B: conflict-optimal)
 constexpr int TC_STG = 32 * TC_PITCH * 4;                // bytes of one epilogue warp's staging tile
-constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;   // 544
+constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;   // 416
 constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;              // 12
 constexpr int TC_TMEM_COLS = 512;
 

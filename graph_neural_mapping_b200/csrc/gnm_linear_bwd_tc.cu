@@ -7,9 +7,10 @@
 // i.e. two GEMMs into the same accumulator with the per-channel coefficients folded into two copies of W, plus a
 // constant row. dy and z are split exactly into three bf16 planes each (tensor memory, one row per lane), the two
 // scaled W copies into three planes each (shared memory), six MMAs per operand pair and 16-wide k-step.
-// Epilogue: + constant row, ReLU mask of the unit below (a = relu(x*in_scale + in_shift) > 0, x staged with cp.async),
-// its BatchNorm-backward reduction (sum dx, sum dx*xhat) by a shuffle transpose-reduce, coalesced stores through a
-// per-warp staging tile.
+// Epilogue, per 32-column half: TMEM -> a small shared tile (one row per lane), then a column-layout pass (eight lanes
+// per row, float4 columns) next to the cp.async-staged x tile: + constant row, ReLU mask of the unit below
+// (a = relu(x*in_scale + in_shift) > 0), its BatchNorm-backward reduction (sum dx, sum dx*xhat) accumulated per lane -
+// no cross-lane transposition - and coalesced stores; one fp64 atomic per column and CTA at the end.
 #include "gnm_common.cuh"
 #include "gnm_tc.cuh"
 
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
 // Weight-gradient half: dW[o,i] = sum_m dz[m,o] a[m,i], db[o] = sum_m dz[m,o] with dz = cA*dy + cB*z + cC, i.e.
 //   dW = diag(cA) (dy^T a) + diag(cB) (z^T a) + cC (x) colsum(a),   db = cA*colsum(dy) + cB*colsum(z) + cC*n_rows
 // One "TN" GEMM with the rows as the reduction axis: A operand = [dy | z]^T (M = 128: dy channels then z channels),
-// B operand = a (N = 64), both MN-major in shared memory as three exact bf16 planes, 64 rows per stage. The B
+// B operand = a (N = 64), both MN-major in shared memory as three exact bf16 planes, 32 rows per stage. The B
 // planes sit side by side (hi | mid | lo, N = 192) so the six kept products take three MMAs per 16-row k-step:
 // A_hi x [hi|mid|lo], A_mid x [hi|mid], A_lo x [hi]; the three 64-column groups of the accumulator are summed in
 // the epilogue. Column sums are accumulated by the producers on the way.

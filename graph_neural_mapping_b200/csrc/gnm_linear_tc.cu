@@ -10,15 +10,17 @@
 // HBM time of this op, so the 6x MMA count is free).
 //
 // One persistent CTA per SM, work item = 128-row tile:
-//   * producers (8 warps = two groups taking tiles alternately): one row per thread; 256 B of the row are loaded, f() applied,
-//     split, and the three planes written to TENSOR MEMORY (tcgen05.st; 96 columns per stage, 4-stage ring) - the A
-//     operand never touches shared memory;
+//   * producers (8 warps = two groups taking tiles alternately): a warp's 32 rows arrive by cp.async one own-tile ahead in
+//     a padded staging tile (coalesced), are read back one row per lane, f() applied, split, and the three planes written
+//     to TENSOR MEMORY (tcgen05.st; 96 columns per stage, 4-stage ring) - the MMA's A operand costs no shared-memory
+//     bandwidth;
 //   * B operand: the three W planes ([n][k], K-major core matrices) converted once per CTA into 24 KB of shared memory;
 //   * MMA thread: 24 x tcgen05.mma (M=128, N=64, K=16, A from TMEM) per tile, tcgen05.commit to free the stage and
 //     publish the accumulator (two 64-column slots);
-//   * epilogue (8 warps: one group of four per accumulator slot): tcgen05.ld, + bias, fp32 row stores, and the per-column sum / sum of squares of the tile
-//     by a shuffle transpose-reduction (31 shuffles per 32 columns instead of 5 per column), accumulated per lane
-//     across tiles and flushed once per CTA with fp64 atomics.
+//   * epilogue (8 warps: one group of four per accumulator slot): tcgen05.ld, + bias, staged through shared memory and
+//     copied out with coalesced 128-bit stores; the per-column sum / sum of squares ride on that copy-out (each lane
+//     owns four columns), are added over the eight warps in a fixed order and flushed with ONE fp64 atomic per column
+//     and CTA (same-address atomics serialise in L2).
 #include "gnm_common.cuh"
 #include "gnm_tc.cuh"
 
