@@ -328,3 +328,29 @@ def test_batched_evaluation_equals_the_one_graph_loops(tmp_path):
     assert sorted(os.listdir(out)) == ["labels.npy", "latent_space.npy", "saliency_female.npy", "saliency_male.npy"]
     assert_close(np.load(os.path.join(out, "saliency_male.npy")), loop_s1, 1e-6, "saved saliency")
     assert np.load(os.path.join(out, "latent_space.npy")).shape == loop_lat.shape
+
+
+def test_padded_neighbour_lists_follow_the_reference_order():
+    """graphcnn.py:55-81: neighbours in `graph.neighbors` order, -1 pads up to the batch's max degree, the node itself
+    last when learn_eps is False; the same lists come out of `edge_mat` alone (util.py:86-103 builds both from one
+    edge iteration) when a graph object carries no `neighbors`."""
+    g = Golden("tiny_noeps_max")
+    with_nb = g.graphs()
+    without = g.graphs()
+    for x in without:
+        x.neighbors = []
+    for learn_eps in (False, True):
+        m = build_model(g)
+        m.learn_eps = learn_eps
+        p1, f1 = m._padded_neighbours(with_nb)
+        p2, f2 = m._padded_neighbours(without)
+        assert torch.equal(p1, p2) and torch.equal(f1, f2)
+        max_deg = max(x.max_neighbor for x in with_nb)
+        assert p1.shape == (sum(len(x.g) for x in with_nb), max_deg + (0 if learn_eps else 1))
+        start = 0
+        for x in with_nb:
+            for j, nb in enumerate(x.neighbors):
+                want = [v + start for v in nb] + [-1] * (max_deg - len(nb)) + ([] if learn_eps else [start + j])
+                assert p1[start + j].tolist() == want
+                assert int(f1[start + j]) == (want[0] if nb else -1)
+            start += len(x.g)
