@@ -308,6 +308,8 @@ def run_b200(args):
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ops.LAUNCHES[0] - launches0
     clocks = sampler.stop() if sampler else None
+    if comm.p2p is not None and comm.p2p.status():
+        raise RuntimeError("a peer-memory BatchNorm exchange gave up waiting for a peer: the timed steps are invalid")
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)

@@ -9,15 +9,16 @@
 // Call k (k = 1, 2, ... counted per rank in device memory, so CUDA-graph replays stay in step): rank r stores its
 // payload into slot[k&1][r] of EVERY rank (remote stores over NVLink), fences at system scope, stores k into the
 // matching flags, then waits until all its own flags of that parity show k and adds the slots in rank order - every
-// rank gets the bit-identical sum. Two parities suffice: a peer can only start call k+2 after it has seen my flag of
+// rank gets the bit-identical sum. The wait is bounded (~10 s: long enough for the rank-to-rank skew of a CUDA-graph
+// capture in front of the first replay, short enough never to hang a box). Two parities suffice: a peer can only start call k+2 after it has seen my flag of
 // call k+1, which I write after I finished reading call k.
 #pragma once
 #include "gnm_common.cuh"
 
 namespace {
 
-__device__ int g_p2p_abort = 0;      // raised when a peer did not show up within ~2 s (per translation unit)
-constexpr long long P2P_TIMEOUT_CYCLES = 4000000000LL;
+__device__ int g_p2p_abort = 0;      // raised when a peer did not show up within ~10 s (per translation unit)
+constexpr long long P2P_TIMEOUT_CYCLES = 20000000000LL;
 
 struct P2PArgs {
     void* const* peers;        // device array [world]: exchange buffer of every rank as mapped in THIS process

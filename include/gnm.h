@@ -314,7 +314,7 @@ int gnm_aggregate_max_bwd(const int32_t* rowptr, const int32_t* colidx, int n_ro
  * the CONSUMING kernel does it: gnm_bn_finalize / gnm_bn_bwd_coeffs take a communicator and all-reduce their double[2F]
  * input in place (remote stores into every peer's exchange buffer, system-scope release/acquire flags, fixed-order
  * sum: bit-identical on all ranks) before using it. gnm_p2p_allreduce is the same exchange as a kernel of its own
- * (n <= GNM_P2P_MAX_DOUBLES). All ranks must issue the same sequence of exchanges. Waits are bounded (~2 s):
+ * (n <= GNM_P2P_MAX_DOUBLES). All ranks must issue the same sequence of exchanges. Waits are bounded (~10 s):
  * gnm_p2p_status reports a give-up. */
 int64_t gnm_p2p_buffer_bytes(void);
 int gnm_p2p_alloc(void** buf, unsigned char* handle /* [GNM_P2P_HANDLE_BYTES] out: CUDA IPC handle */);
