@@ -361,6 +361,18 @@ def flat_params(model):
     return ps
 
 
+def flat_buffers(model):
+    """The BatchNorm buffers the kernels update in place (same set and order as `model.buffers()`, without walking the
+    module tree: this runs every step to check that a captured CUDA graph still points at the live tensors)."""
+    bs = []
+    for layer in range(model.num_layers):
+        for _, bn in layer_units(model, layer):
+            for t in (bn.running_mean, bn.running_var, bn.num_batches_tracked):
+                if t is not None:
+                    bs.append(t)
+    return bs
+
+
 class _Unit(object):
     """Saved forward state of one Linear->BatchNorm->ReLU unit."""
     __slots__ = ("w", "b", "gamma", "beta", "bn", "z", "scale", "shift", "mean", "rstd", "x_in", "count")

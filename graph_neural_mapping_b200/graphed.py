@@ -51,7 +51,7 @@ class StepPlan(object):
 
     def _pointers(self):
         ps = [p.data_ptr() for p in _engine.flat_params(self.model)]
-        ps += [b.data_ptr() for b in self.model.buffers()]
+        ps += [b.data_ptr() for b in _engine.flat_buffers(self.model)]
         return ps
 
     def compatible(self, h, n_neg):

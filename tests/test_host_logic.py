@@ -354,3 +354,16 @@ def test_padded_neighbour_lists_follow_the_reference_order():
                 assert p1[start + j].tolist() == want
                 assert int(f1[start + j]) == (want[0] if nb else -1)
             start += len(x.g)
+
+
+@pytest.mark.parametrize("name", ["tiny_eps_sum", "tiny_mlp1", "tiny_mlp3"])
+def test_flat_params_and_buffers_cover_the_module(name):
+    """engine.flat_params / flat_buffers (used to validate captured CUDA graphs every step) name exactly the tensors of
+    model.parameters() minus the prediction heads, and of model.buffers()."""
+    g = Golden(name)
+    m = build_model(g)
+    heads = {p.data_ptr() for p in m.linears_prediction.parameters()}
+    want = {p.data_ptr() for p in m.parameters()} - heads
+    assert {p.data_ptr() for p in engine.flat_params(m)} == want
+    assert {b.data_ptr() for b in engine.flat_buffers(m)} == {b.data_ptr() for b in m.buffers()}
+    assert len(engine.flat_buffers(m)) == len(list(m.buffers()))
