@@ -2,14 +2,17 @@
 """Benchmark of the GIN + DGI training hot path (BASELINE.json metric: GIN train graphs/sec @400 ROIs).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]             # this repo's CUDA path
-    python bench.py --impl reference [--steps K] [--warmup W]        # the reference's CPU path (ATen port)
+    python bench.py --impl reference [--steps K] [--warmup W]        # the UNMODIFIED reference on the host cores (oracle/_ref)
     torchrun --nproc-per-node N ... bench.py --gpus N ...            # one rank per GPU, NCCL
 
 A "step" is one pass of main.py:25-41 over one batch: batch selection, forward (GIN encoder + DGI
 scores), CrossEntropy + beta*BCEWithLogits, zero_grad, backward, Adam step.
 Workload at N=1: BASELINE.json configs[1] - 5-layer GIN, hidden 64, 1024 synthetic Schaefer-400
 thresholded-FC graphs per batch. At N>1 every rank trains on its own 1024-graph batch (weak scaling,
-global batch 1024*N) with BatchNorm statistics, DGI negatives and gradients synchronised over NCCL.
+global batch 1024*N: `value`) with BatchNorm statistics, DGI negatives and gradients synchronised; the same line
+carries a `strong` block (BASELINE configs[2]: ONE global batch of 1024 graphs sharded 1024/N per GPU) and
+`dp_parity_err` (an N-rank step against rank 0 recomputing the same global batch single-process, before timing).
+The timed region is K x `config.inner_repeats` steps (>= ~1 s of device time); ms_per_step is per step.
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -53,6 +56,11 @@ def parse():
     ap.add_argument("--saliency", action="store_true",
                     help="measure gradient-saliency extraction (graphcnn.py:254-299) throughput instead of training")
     ap.add_argument("--saliency-batch", type=int, default=256, help="graphs per batched saliency call")
+    ap.add_argument("--min-seconds", type=float, default=1.0,
+                    help="lower bound on the device time of the timed region: the K steps are repeated `inner_repeats` "
+                         "times (declared in config) so that clocks / throttling are sampled over >= this long")
+    ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling block (global batch fixed)")
+    ap.add_argument("--no-dp-parity", action="store_true", help="N>1: skip the data-parallel parity step before timing")
     return ap.parse_args()
 
 
@@ -68,34 +76,75 @@ def workload_config(args, world):
 # CPU baseline: the reference's ATen path (oracle/aten_port.py), bounded sample
 # ------------------------------------------------------------------------------------------
 
-def cpu_reference_run(args, steps, warmup, graphs=None):
-    from oracle import aten_port
+def _cpu_graphs(graphs, b):
+    """The CPU arm's graphs: host copies of the first b graphs (S2VGraph fields on the CPU, as util.py leaves them)."""
     from graph_neural_mapping_b200 import synth
+    if graphs is None:
+        return synth.make_graphs_bulk(b, N_ROIS, 30, 256, seed0=99, device="cpu")[:b]
+    out = []
+    for g in graphs[:b]:
+        out.append(synth.SynthGraph(len(g.g), g.label, g.edge_mat.cpu(), g.node_features.cpu()))
+    return out
+
+
+def cpu_reference_run(args, steps, warmup, graphs=None):
+    """The CPU arm: the reference's own GIN_InfoMaxReg (staged unmodified in oracle/_ref by oracle/make_ref.py) driven
+    by the body of main.py:25-43 on all host cores; kind "reference". Only if oracle/_ref is absent (a checkout that
+    never saw /root/reference) it falls back to oracle/aten_port.py, kind "port"."""
+    from oracle import ref_arm
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     b = args.cpu_batch
-    if graphs is None:
-        graphs = synth.make_graphs_bulk(b, N_ROIS, 30, 256, seed0=99, device="cpu")
-    graphs = graphs[:b]
-    from graph_neural_mapping_b200.models import GIN_InfoMaxReg
+    graphs = _cpu_graphs(graphs, b)
     torch.manual_seed(0)
-    init = GIN_InfoMaxReg(LAYERS, MLP_LAYERS, N_ROIS, HIDDEN, 2, 0.5, args.learn_eps, "sum", "sum", torch.device("cpu"))
-    st = aten_port.TrainState(init.state_dict(), lr=LR)
-    cfg = dict(num_layers=LAYERS, num_mlp_layers=MLP_LAYERS, learn_eps=args.learn_eps, graph_pooling_type="sum",
-               neighbor_pooling_type="sum")
     np.random.seed(0)
-    for _ in range(warmup):
-        st.step(graphs, cfg, BETA, 0.5)
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        st.step(graphs, cfg, BETA, 0.5)
-        times.append(time.perf_counter() - t0)
+    if ref_arm.available():
+        RefModel = ref_arm.reference_model_class()
+        cpu = torch.device("cpu")
+        model = RefModel(LAYERS, MLP_LAYERS, N_ROIS, HIDDEN, 2, 0.5, args.learn_eps, "sum", "sum", cpu).to(cpu)
+        opt = torch.optim.Adam(model.parameters(), lr=LR)                                   # main.py:136
+        c_crit, d_crit = torch.nn.CrossEntropyLoss(), torch.nn.BCEWithLogitsLoss()        # main.py:16-17
+        model.train()
+
+        def step():
+            sel = np.random.permutation(len(graphs))[:b]                                   # main.py:26
+            batch = [graphs[i] for i in sel]
+            c_logit, d_logit = model(batch)
+            c_labels = torch.LongTensor([g.label for g in batch])
+            d_labels = torch.cat([torch.ones(b * N_ROIS, 1), torch.zeros(b * N_ROIS, 1)], 0)
+            loss = c_crit(c_logit, c_labels) + BETA * d_crit(d_logit, d_labels)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return float(loss.detach().cpu().numpy())
+        kind = "reference"
+        what = "the UNMODIFIED reference (oracle/_ref: models/graphcnn.py GIN_InfoMaxReg driven by the body of main.py:25-43)"
+    else:
+        from oracle import aten_port
+        from graph_neural_mapping_b200.models import GIN_InfoMaxReg
+        init = GIN_InfoMaxReg(LAYERS, MLP_LAYERS, N_ROIS, HIDDEN, 2, 0.5, args.learn_eps, "sum", "sum", torch.device("cpu"))
+        st = aten_port.TrainState(init.state_dict(), lr=LR)
+        cfg = dict(num_layers=LAYERS, num_mlp_layers=MLP_LAYERS, learn_eps=args.learn_eps, graph_pooling_type="sum",
+                   neighbor_pooling_type="sum")
+
+        def step():
+            return st.step(graphs, cfg, BETA, 0.5)
+        kind = "port"
+        what = "oracle/aten_port.py (the reference's torch.spmm / nn.Bilinear / BatchNorm ATen path; oracle/_ref not staged)"
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(warmup):
+            step()
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            step()
+            times.append(time.perf_counter() - t0)
     total = sum(times)
-    return dict(value=b * steps / total, unit=UNIT, cores=cores, kind="port",
-                sample="%d steps of a %d-graph batch (BASELINE configs[0]) of the same synthetic Schaefer-400 graphs, "
-                       "oracle/aten_port.py = the reference's torch.spmm / nn.Bilinear / BatchNorm ATen path on CPU, "
-                       "%d threads" % (steps, b, cores)), total / steps
+    return dict(value=b * steps / total, unit=UNIT, cores=cores, kind=kind,
+                sample="%d steps of a %d-graph batch (BASELINE configs[0]) of the same synthetic Schaefer-400 graphs on the "
+                       "CPU, %s, %d threads" % (steps, b, what, cores)), total / steps
 
 
 def run_reference(args):
@@ -279,42 +328,88 @@ def run_b200(args):
         opt.step()
         return float(loss.detach().cpu().numpy())
 
+    def check_status(what):
+        """A tcgen05 pipeline or a peer exchange that ran into its bounded wait produced garbage: never report it."""
+        if ops.aggregate_tc_status():
+            raise RuntimeError("a tcgen05 kernel hit its bounded barrier wait during %s: the numbers are invalid" % what)
+        if comm.p2p is not None and comm.p2p.status():
+            raise RuntimeError("a peer-memory exchange gave up waiting for a peer during %s: the numbers are invalid" % what)
+
+    # ---- data-parallel parity, before anything is timed -----------------------------------------
+    dp_parity = None
+    if world > 1 and not args.no_dp_parity:
+        dp_parity = dp_parity_check(args, comm, dev)
+        check_status("the data-parallel parity step")
+
     model.train()
     # ---- value: device-resident inputs ---------------------------------------------------------
     step_loop = step_resident
+    trainer = None
+    labels_np = np.array([g.label for g in pool], dtype=np.int64)
     if args.driver == "fused":
         from graph_neural_mapping_b200.driver import Trainer
         # same model, same work per step (assembly, forward, heads, CE + beta*BCE, backward, gradient averaging, Adam)
         # captured as ONE CUDA graph; the labels ride in the same pinned staging ring as the slot addresses
-        trainer = Trainer(model, lr=LR, beta=BETA, comm=comm)
-        labels_np = np.array([g.label for g in pool], dtype=np.int64)
+        trainer = Trainer(model, lr=LR, beta=BETA, comm=comm, check_every=0)
 
-        def step_resident():
-            sel = np.random.permutation(len(pool))[:B]
+    def make_step(n_graphs):
+        if trainer is None:
+            return step_resident
+
+        def step():
+            sel = np.random.permutation(len(pool))[:n_graphs]
             return trainer.step([pool[i] for i in sel], labels_np[sel])
+        return step
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = ops.LAUNCHES[0]
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step_resident()
-    ev1.record()
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    launches = ops.LAUNCHES[0] - launches0
-    clocks = sampler.stop() if sampler else None
-    if comm.p2p is not None and comm.p2p.status():
-        raise RuntimeError("a peer-memory BatchNorm exchange gave up waiting for a peer: the timed steps are invalid")
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    value = B * world * args.steps / (elapsed_ms / 1e3)
+    def timed(step, n_graphs, steps, what):
+        """W warm-up steps, then `steps` x inner steps between two events, max over ranks. Returns (ms per step,
+        inner, clocks, libgnm kernels launched in the region)."""
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        est = torch.tensor([e0.elapsed_time(e1) / 3.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(est, op=torch.distributed.ReduceOp.MAX)
+        inner = max(1, int(np.ceil(args.min_seconds * 1e3 / (float(est.item()) * steps))))
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        k0 = ops.kernels_launched()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps * inner):
+            step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launched = ops.kernels_launched() - k0
+        clk = sampler.stop() if sampler else None
+        check_status(what)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item()) / (steps * inner), inner, clk, launched
+
+    step_resident = make_step(B)
+    ms_per_step, inner, clocks, launches = timed(step_resident, B, args.steps, "the timed steps")
+    elapsed_ms = ms_per_step * args.steps
+    value = B * world / (ms_per_step / 1e3)
+
+    # ---- strong scaling (BASELINE configs[2]): ONE global batch of `B` graphs, B / world per GPU ------
+    strong = None
+    if world > 1 and not args.no_strong and B % world == 0:
+        bs_local = B // world
+        ms_s, inner_s, clk_s, _ = timed(make_step(bs_local), bs_local, args.steps, "the strong-scaling steps")
+        strong = {"global_batch": B, "graphs_per_gpu": bs_local, "value": B / (ms_s / 1e3), "unit": UNIT,
+                  "ms_per_step": ms_s, "inner_repeats": inner_s, "clocks": clk_s,
+                  "what": "same step, the global batch held at %d graphs (main.py:26-41 at one global batch): each rank "
+                          "trains on %d graphs, BatchNorm over the global M = %d rows" % (B, bs_local, B * N_ROIS)}
 
     # ---- per-kernel times, live, on the launching stream ------------------------------------
     graphs_on = model.use_cuda_graphs
@@ -351,8 +446,23 @@ def run_b200(args):
                 "traffic": AGG_DRAM_TRAFFIC_BYTES if (B == 1024 and "dense" in agg_key) else None,
                 "algorithmic_bytes_per_launch": agg_bytes, "avg_launch_us": avg_s * 1e6, "launches_per_step": cnt / n_prof,
                 "share_of_kernel_time": (tot_ms / n_prof) / step_ms}
-    breakdown = {k: {"launches_per_step": v[0] / n_prof, "ms_per_step": v[1] / n_prof} for k, v in
-                 sorted(table.items(), key=lambda kv: -kv[1][1])}
+    # algorithmic bytes per launch of the ops whose formula does not depend on the call site
+    mf, bf = 4.0 * m * HIDDEN, 4.0 * B * HIDDEN
+    struct_bytes = 4.0 * nnz + 4.0 * (m + 1)
+    alg = {"aggregate_dense[F=%d]" % HIDDEN: agg_bytes, "aggregate[F=%d]" % HIDDEN: agg_bytes,
+           "aggregate_dense_relu_bn_bwd": agg_bytes + mf,                  # + the z rows of the unit below (dy replaces d_h)
+           "aggregate_dense_affine": struct_bytes + 3 * mf,                # dy, z in; Agg(..) out
+           "aggregate_dense[F=%d,gather0]" % HIDDEN: struct_bytes + 4.0 * N_ROIS * HIDDEN + mf,     # SURVEY AGG0
+           "linear[%dx%d]" % (HIDDEN, HIDDEN): 2 * mf, "linear_bwd": 4 * mf, "bn_relu_readout": 2 * mf + bf,
+           "dgi_score_fwd": LAYERS * mf + 2 * LAYERS * bf + 8.0 * m, "dgi_score_bwd": LAYERS * mf + 2 * LAYERS * bf + 8.0 * m,
+           "rows_period_sum": mf, "col_stats": mf}
+    breakdown = {}
+    for k, v in sorted(table.items(), key=lambda kv: -kv[1][1]):
+        ent = {"launches_per_step": v[0] / n_prof, "ms_per_step": v[1] / n_prof}
+        if k in alg and v[1] > 0:
+            ent["algorithmic_MB_per_launch"] = alg[k] / 1e6
+            ent["frac_of_hbm_peak"] = alg[k] / (v[1] / v[0] / 1e3) / 1e9 / peak_gbs
+        breakdown[k] = ent
     if args.breakdown and rank == 0:
         for k, v in breakdown.items():
             sys.stderr.write("%-34s %6.1f launches  %9.3f ms/step\n" % (k, v["launches_per_step"], v["ms_per_step"]))
@@ -379,7 +489,7 @@ def run_b200(args):
             model.cache_graphs = True
             return B * world * steps / float(tt.item()), int(h2d)
         v_cold, h2d_cold = timed_e2e(True, max(2, min(args.steps, 5)), 1)
-        v_warm, h2d_warm = timed_e2e(False, args.steps, 2)
+        v_warm, h2d_warm = timed_e2e(False, args.steps * inner, 2)
         e2e = {"value": v_warm, "unit": UNIT, "h2d_bytes_per_step": h2d_warm, "d2h_bytes_per_step": 4,
                "what": "the literal main.py:25-43 loop body: model(batch_graph) on host S2VGraph lists, labels and DGI "
                        "targets built on the host and copied in every step, loss.cpu() every step. Steady state of "
@@ -398,20 +508,107 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(args, world), cuda_graphs=bool(model.use_cuda_graphs),
+                "config": dict(workload_config(args, world), cuda_graphs=bool(model.use_cuda_graphs), inner_repeats=inner,
+                               steps_timed=args.steps * inner,
                                driver=("driver.Trainer: whole step (assembly, forward, heads, loss, backward, gradient "
                                        "averaging, Adam) as one CUDA graph" if args.driver == "fused" else
                                        "main.py loop body over the drop-in model (encoder forward / backward as CUDA graphs)")),
-                "clocks": clocks, "gpu_launches": launches,
-                "e2e": e2e, "roofline": roof, "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown}
+                "clocks": clocks, "gpu_launches": launches, "gpu_launches_per_step": launches / float(args.steps * inner),
+                "e2e": e2e, "roofline": roof, "cpu_baseline": cpu_baseline, "strong": strong, "dp_parity_err": dp_parity,
+                "kernel_breakdown": breakdown}
         print(json.dumps(line))
     if world > 1:
         model.release_graphs()
-        if args.driver == "fused":
+        if trainer is not None:
             trainer.release()
         torch.cuda.synchronize()
         torch.distributed.barrier()
         gdist.shutdown()
+
+
+def dp_parity_check(args, comm, dev, per_rank=16):
+    """One training step of main.py:25-41 on a global batch of 16 x N graphs, sharded over the N ranks (sync-BatchNorm,
+    DGI negatives, averaged gradients), against rank 0 recomputing the SAME global batch single-process from the same
+    state and permutation. 16 graphs per rank = 6400 rows: the tcgen05 kernel family of the timed run. Returns the
+    largest per-tensor scaled error (each tensor on its own max-abs; MLP Linear biases - true gradient zero in front
+    of a train-mode BatchNorm - on the largest gradient's scale)."""
+    import re
+    from graph_neural_mapping_b200 import dist as gdist, synth
+    from graph_neural_mapping_b200.models import GIN_InfoMaxReg
+    world, rank = comm.world, comm.rank
+    graphs = synth.make_graphs_bulk(per_rank * world, N_ROIS, 30, 256, seed0=4321, device="cpu")   # identical on all ranks
+    chk = torch.tensor([float(sum(int(g.edge_mat.sum()) % 1000003 for g in graphs))], dtype=torch.float64, device=dev)
+    lo, hi = chk.clone(), chk.clone()
+    torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+    torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+    if float(lo) != float(hi):
+        raise RuntimeError("dp_parity_check: the ranks generated different graphs")
+
+    def build(c):
+        torch.manual_seed(77)
+        m = GIN_InfoMaxReg(LAYERS, MLP_LAYERS, N_ROIS, HIDDEN, 2, 0.0, args.learn_eps, "sum", "sum", dev).to(dev)
+        with torch.no_grad():
+            m.eps.copy_(torch.linspace(-0.3, 0.4, LAYERS))
+            for lin in m.linears_prediction:
+                lin.weight.mul_(0.01)             # keeps the 2-class softmax off saturation (as tests/golden does)
+        m.set_comm(c)
+        m.train()
+        return m
+
+    def one_step(m, batch, c):
+        np.random.seed(2024)
+        c_logit, d_logit = m(batch)
+        labels = torch.tensor([g.label for g in batch], device=dev)
+        n = len(batch) * N_ROIS
+        d_labels = torch.cat([torch.ones(n, 1), torch.zeros(n, 1)], 0).to(dev)
+        loss = torch.nn.functional.cross_entropy(c_logit, labels) + BETA * \
+            torch.nn.functional.binary_cross_entropy_with_logits(d_logit, d_labels)
+        m.zero_grad()
+        loss.backward()
+        gdist.average_gradients(m, c)
+        return c_logit.detach(), d_logit.detach(), loss.detach()
+
+    model = build(comm)
+    c_l, d_l, loss = one_step(model, gdist.shard(graphs, comm), comm)
+    cs = [torch.empty_like(c_l) for _ in range(world)]
+    ds = [torch.empty_like(d_l) for _ in range(world)]
+    ls = [torch.empty_like(loss.reshape(1)) for _ in range(world)]
+    torch.distributed.all_gather(cs, c_l.contiguous())
+    torch.distributed.all_gather(ds, d_l.contiguous())
+    torch.distributed.all_gather(ls, loss.reshape(1))
+    out = None
+    if rank == 0:
+        single = build(gdist.SINGLE)
+        c_s, d_s, loss_s = one_step(single, graphs, gdist.SINGLE)
+        m_local = d_l.shape[0] // 2
+        d_all = torch.cat([x[:m_local] for x in ds] + [x[m_local:] for x in ds], 0)
+
+        def err(a, b, floor=0.0):
+            return float((a.double() - b.double()).abs().max() / max(float(b.double().abs().max()), floor, 1e-30))
+        errs = {"c_logit": err(torch.cat(cs, 0), c_s), "d_logit": err(d_all, d_s), "loss": err(torch.stack(ls).mean(), loss_s)}
+        gmax = max(float(p.grad.abs().max()) for p in single.parameters() if p.grad is not None)
+        zero_bias = re.compile(r"^mlps\.\d+\.(linear|linears\.\d+)\.bias$")
+        worst = ("", 0.0)
+        for (k, p), (_, q) in zip(model.named_parameters(), single.named_parameters()):
+            if q.grad is None:
+                continue
+            e = err(p.grad, q.grad, 1e-2 * gmax if zero_bias.match(k) else 0.0)
+            if e > worst[1]:
+                worst = (k, e)
+        for (k, b1), (_, b2) in zip(model.named_buffers(), single.named_buffers()):
+            if b1.dtype.is_floating_point:
+                errs["buffers"] = max(errs.get("buffers", 0.0), err(b1, b2))
+        errs["grad_worst"], errs["grad_worst_tensor"] = worst[1], worst[0]
+        out = {"value": max(errs["c_logit"], errs["d_logit"], errs["loss"], errs.get("buffers", 0.0), worst[1]),
+               "detail": errs, "global_batch": per_rank * world,
+               "what": "max per-tensor scaled error (own max-abs) of logits, loss, BatchNorm buffers and every parameter "
+                       "gradient: %d-rank step vs rank 0 recomputing the same global batch single-process" % world}
+        del single
+    model.release_graphs()
+    del model
+    torch.cuda.synchronize()
+    torch.distributed.barrier()
+    return out
 
 
 def run_saliency(args):

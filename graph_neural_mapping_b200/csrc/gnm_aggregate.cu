@@ -108,6 +108,7 @@ int launch_aggregate(const int32_t* rowptr, const int32_t* colidx, int n_rows, c
                      const float* bias, cudaStream_t st) {
     const int rows_per_block = 8;
     dim3 grid((n_rows + rows_per_block - 1) / rows_per_block, (n_feat + LPR * VEC - 1) / (LPR * VEC));
+    gnm_count_launch(GNM_K_AGG_CSR);
     aggregate_kernel<VEC, LPR><<<grid, rows_per_block * 32, 0, st>>>(rowptr, colidx, n_rows, src, ld_src, src_map, dst,
                                                                       ld_dst, n_feat, mode, eps, bias);
     GNM_RETURN_IF_LAUNCH_FAILED();
@@ -390,6 +391,7 @@ extern "C" int gnm_dot_rows(const float* a, int64_t lda, const float* b, int64_t
     if (!a || !b || !out) return GNM_ERR_BAD_ARG;
     int blocks = (n_rows + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
+    gnm_count_launch(GNM_K_OTHER);
     dot_rows_kernel<<<blocks, 256, 0, gnm_cast_stream(stream)>>>(a, lda, b, ldb, b_map, n_rows, n_feat, out);
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;
@@ -417,6 +419,7 @@ extern "C" int gnm_scatter_rows_add(const float* g, int64_t ldg, const int32_t* 
     const int64_t need = (int64_t)ctas * fparts * n_table_rows * fchunk;
     float* ws = (workspace != nullptr && workspace_floats >= need) ? workspace : nullptr;
     dim3 grid(ctas, fparts);
+    gnm_count_launch(GNM_K_OTHER);
     scatter_rows_add_kernel<<<grid, 256, smem, gnm_cast_stream(stream)>>>(g, ldg, tags, n_rows, n_feat, table_grad, ldt,
                                                                           n_table_rows, fchunk, rows_per_cta, ws);
     GNM_RETURN_IF_LAUNCH_FAILED();
@@ -424,6 +427,7 @@ extern "C" int gnm_scatter_rows_add(const float* g, int64_t ldg, const int32_t* 
         int mb = (n_table_rows * fchunk + 255) / 256;
         if (mb > 148 * 4) mb = 148 * 4;
         dim3 mgrid(mb, fparts);
+        gnm_count_launch(GNM_K_OTHER);
         scatter_rows_merge_kernel<<<mgrid, 256, 0, gnm_cast_stream(stream)>>>(ws, ctas, n_table_rows, fchunk, n_feat,
                                                                               table_grad, ldt);
         GNM_RETURN_IF_LAUNCH_FAILED();
@@ -463,8 +467,10 @@ extern "C" int gnm_rows_period_sum(const float* g, int64_t ldg, int n_rows, int 
     if (workspace_floats < gnm_rows_period_workspace(n_rows, n_feat, period)) return GNM_ERR_BAD_ARG;
     const int n_periods = n_rows / period, splits = rows_period_splits(n_periods), f4 = n_feat / 4;
     const int blocks = (period * f4 + 255) / 256;
+    gnm_count_launch(GNM_K_OTHER);
     rows_period_sum_kernel<<<dim3(blocks, splits), 256, 0, gnm_cast_stream(stream)>>>(g, ldg, n_periods, period, f4, workspace);
     GNM_RETURN_IF_LAUNCH_FAILED();
+    gnm_count_launch(GNM_K_OTHER);
     rows_period_merge_kernel<<<blocks, 256, 0, gnm_cast_stream(stream)>>>(workspace, splits, period, f4, tags, n_table_rows, out,
                                                                            ldo);
     GNM_RETURN_IF_LAUNCH_FAILED();
@@ -478,6 +484,7 @@ extern "C" int gnm_col_min(const float* h, int64_t ldh, int n_rows, int n_feat, 
     if (!h || !packed) return GNM_ERR_BAD_ARG;
     const int rows_per_cta = 256;
     dim3 grid((n_rows + rows_per_cta - 1) / rows_per_cta, (n_feat + 127) / 128);
+    gnm_count_launch(GNM_K_OTHER);
     col_min_kernel<<<grid, 128, 0, gnm_cast_stream(stream)>>>(h, ldh, n_rows, n_feat, rows_per_cta, packed);
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;
@@ -489,6 +496,7 @@ extern "C" int gnm_aggregate_max(const int32_t* rowptr, const int32_t* colidx, i
     if (n_rows < 0 || n_feat < 0) return GNM_ERR_BAD_ARG;
     if (n_rows == 0 || n_feat == 0) return GNM_OK;
     if (!rowptr || !h || !col_min || !out || !argmax) return GNM_ERR_BAD_ARG;     // colidx may be NULL when nnz == 0
+    gnm_count_launch(GNM_K_OTHER);
     aggregate_max_kernel<<<(n_rows + 7) / 8, 256, 0, gnm_cast_stream(stream)>>>(rowptr, colidx, n_rows, h, ldh, n_feat,
                                                                                col_min, eps, out, ld_out, argmax);
     GNM_RETURN_IF_LAUNCH_FAILED();
@@ -502,9 +510,11 @@ extern "C" int gnm_aggregate_max_bwd(const int32_t* rowptr, const int32_t* colid
     if (n_rows < 0 || n_feat < 0) return GNM_ERR_BAD_ARG;
     if (n_rows == 0 || n_feat == 0) return GNM_OK;
     if (!rowptr || !d_out || !argmax || !col_min || !d_h) return GNM_ERR_BAD_ARG;   // colidx may be NULL when nnz == 0
+    gnm_count_launch(GNM_K_OTHER);
     aggregate_max_bwd_kernel<<<(n_rows + 7) / 8, 256, 0, gnm_cast_stream(stream)>>>(rowptr, colidx, n_rows, d_out, ld_dout,
                                                                                    n_feat, argmax, eps, d_h, ld_dh);
     GNM_RETURN_IF_LAUNCH_FAILED();
+    gnm_count_launch(GNM_K_OTHER);
     aggregate_max_dummy_bwd_kernel<<<148 * 4, 256, 0, gnm_cast_stream(stream)>>>(n_rows, d_out, ld_dout, n_feat, argmax,
                                                                                 col_min, d_h, ld_dh);
     GNM_RETURN_IF_LAUNCH_FAILED();

@@ -294,6 +294,7 @@ extern "C" int gnm_bitmap_build(const int32_t* rowptr, const int32_t* colidx, co
     if (n_graphs < 0) return GNM_ERR_BAD_ARG;
     if (n_graphs == 0) return GNM_OK;
     if (!rowptr || !node_off || !bitmap_off || !bitmap || !dup_flags) return GNM_ERR_BAD_ARG;
+    gnm_count_launch(GNM_K_OTHER);
     bitmap_build_kernel<<<n_graphs, 256, 0, gnm_cast_stream(stream)>>>(rowptr, colidx, node_off, bitmap_off, n_graphs,
                                                                        bitmap, dup_flags);
     GNM_RETURN_IF_LAUNCH_FAILED();
@@ -339,6 +340,7 @@ extern "C" int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* no
     if (e != cudaSuccess) return (int)e;
     const int64_t items = (int64_t)n_graphs * p.n_rb * p.n_slabs;
     const int grid = (int)(items < sms ? items : sms);
+    gnm_count_launch(GNM_K_AGG_MMA_SYNC);
     aggregate_dense_kernel<Cfg><<<grid, Cfg::THREADS, AD_SMEM_BYTES, gnm_cast_stream(stream)>>>(p);
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;

@@ -575,10 +575,12 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
     if (p.dbg != nullptr) {
         e = cudaFuncSetAttribute(aggregate_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
+        gnm_count_launch(GNM_K_AGG_TC);
         aggregate_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p);
     } else {
         e = cudaFuncSetAttribute(aggregate_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
+        gnm_count_launch(GNM_K_AGG_TC);
         aggregate_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p);
     }
     e = cudaGetLastError();

@@ -13,6 +13,13 @@
         if (e__ != cudaSuccess) return (int)e__;      \
     } while (0)
 
+// kernel families counted by gnm_launch_counts (include/gnm.h); host-side, one increment per kernel enqueued
+enum GnmKernelFamily {
+    GNM_K_AGG_CSR = 0, GNM_K_AGG_MMA_SYNC, GNM_K_AGG_TC, GNM_K_LINEAR_FFMA, GNM_K_LINEAR_TC, GNM_K_LINEAR_BWD_FFMA,
+    GNM_K_LINEAR_BWD_DX_TC, GNM_K_LINEAR_WGRAD_TC, GNM_K_LINEAR_WGRAD_FFMA, GNM_K_OTHER, GNM_K_FAMILIES
+};
+void gnm_count_launch(int family);     // gnm_dgi.cu
+
 static inline cudaStream_t gnm_cast_stream(gnm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __host__ __device__ static inline bool gnm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

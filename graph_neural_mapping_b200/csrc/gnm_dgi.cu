@@ -216,6 +216,7 @@ extern "C" int gnm_gather_nf_rows(const float* h_all, int64_t layer_stride, int 
     const int64_t total = (int64_t)n_rows * n_layers * n_feat;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
+    gnm_count_launch(GNM_K_OTHER);
     gather_nf_rows_kernel<<<(int)blocks, 256, 0, gnm_cast_stream(stream)>>>(h_all, layer_stride, n_layers, n_feat, ldh,
                                                                             n_rows, table);
     GNM_RETURN_IF_LAUNCH_FAILED();
@@ -235,9 +236,10 @@ extern "C" int gnm_dgi_score_fwd(const float* h_all, int64_t layer_stride, int n
     const bool vec = (n_feat % 4 == 0) && (q & (q - 1)) == 0 && q <= 32 && (ldh % 4 == 0) && (layer_stride % 4 == 0) &&
                      gnm_aligned16(h_all);
 #define GNM_DGI_FWD(LPR)                                                                                             \
+    do { gnm_count_launch(GNM_K_OTHER); \
     dgi_score_fwd_kernel<LPR><<<n_graphs, 256, smem, gnm_cast_stream(stream)>>>(h_all, layer_stride, n_layers, n_feat, \
                                                                                  ldh, n_rows, u, neg_table, neg_idx,   \
-                                                                                 node_off, bias, out)
+                                                                                 node_off, bias, out); } while (0)
     if (!vec) GNM_DGI_FWD(0);
     else if (q == 1) GNM_DGI_FWD(1);
     else if (q == 2) GNM_DGI_FWD(2);
@@ -259,8 +261,9 @@ extern "C" int gnm_dgi_score_bwd(const float* h_all, int64_t layer_stride, int n
     if (!h_all || !d_out || !neg_table || !neg_idx || !node_off || !du || !s2) return GNM_ERR_BAD_ARG;
     if (n_feat == 64 && n_layers >= 1 && n_layers <= 5 && (ldh & 3) == 0 && (layer_stride & 3) == 0 && gnm_aligned16(h_all)) {
 #define GNM_DGI_BWD(NL) \
+    do { gnm_count_launch(GNM_K_OTHER); \
     dgi_score_bwd_vec_kernel<NL><<<n_graphs, 256, 0, gnm_cast_stream(stream)>>>(h_all, layer_stride, ldh, n_rows, d_out, \
-                                                                             neg_table, neg_idx, node_off, du, s2, d_bias)
+                                                                             neg_table, neg_idx, node_off, du, s2, d_bias); } while (0)
         switch (n_layers) {
             case 1: GNM_DGI_BWD(1); break;
             case 2: GNM_DGI_BWD(2); break;
@@ -278,6 +281,7 @@ extern "C" int gnm_dgi_score_bwd(const float* h_all, int64_t layer_stride, int n
         cudaError_t e = cudaFuncSetAttribute(dgi_score_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
+    gnm_count_launch(GNM_K_OTHER);
     dgi_score_bwd_kernel<<<n_graphs, 256, smem, gnm_cast_stream(stream)>>>(h_all, layer_stride, n_layers, n_feat, ldh,
                                                                            n_rows, d_out, neg_table, neg_idx, node_off,
                                                                            du, s2, d_bias);
@@ -292,6 +296,7 @@ extern "C" int gnm_rowdot_score(const float* h, int64_t ldh, int n_rows, int n_f
     if (n_rows == 0) return GNM_OK;
     if (!h || !u || !out) return GNM_ERR_BAD_ARG;
     const int blocks = (n_rows + 7) / 8;
+    gnm_count_launch(GNM_K_OTHER);
     rowdot_score_kernel<<<blocks, 256, 0, gnm_cast_stream(stream)>>>(h, ldh, n_rows, n_feat, u, ldu, rows_per_graph,
                                                                      bias, s_bias, out);
     GNM_RETURN_IF_LAUNCH_FAILED();
@@ -301,6 +306,16 @@ extern "C" int gnm_rowdot_score(const float* h, int64_t ldh, int n_rows, int n_f
 // ---- misc -------------------------------------------------------------------------------------
 
 extern "C" int gnm_abi_version(void) { return GNM_ABI_VERSION; }
+
+static int64_t g_launch_counts[GNM_K_FAMILIES] = {0};
+void gnm_count_launch(int family) {
+    if (family >= 0 && family < GNM_K_FAMILIES) __atomic_fetch_add(&g_launch_counts[family], 1, __ATOMIC_RELAXED);
+}
+extern "C" int gnm_launch_counts(int64_t* out, int n) {
+    if (!out || n < 0) return GNM_ERR_BAD_ARG;
+    for (int i = 0; i < n; ++i) out[i] = i < GNM_K_FAMILIES ? __atomic_load_n(&g_launch_counts[i], __ATOMIC_RELAXED) : 0;
+    return GNM_K_FAMILIES;
+}
 
 extern "C" const char* gnm_error_string(int code) {
     switch (code) {

@@ -660,6 +660,7 @@ int gnm_launch_linear_bwd_dx_tc(const float* dy, int64_t lddy, const float* z, i
     if (e != cudaSuccess) return (int)e;
     const int tiles = (n_rows + 127) / 128;
     const int grid = tiles < sms ? tiles : sms;
+    gnm_count_launch(GNM_K_LINEAR_BWD_DX_TC);
     linear_bwd_dx_tc_kernel<<<grid, BT_THREADS, BT_SMEM, stream>>>(p);
     e = cudaGetLastError();
     return e == cudaSuccess ? GNM_OK : (int)e;
@@ -690,6 +691,7 @@ int gnm_launch_linear_wgrad_tc(const float* dy, int64_t lddy, const float* z, in
     if (e != cudaSuccess) return (int)e;
     const int chunks = (n_rows + WG_ROWS - 1) / WG_ROWS;
     const int grid = chunks < sms ? chunks : sms;
+    gnm_count_launch(GNM_K_LINEAR_WGRAD_TC);
     linear_wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM, stream>>>(p);
     e = cudaGetLastError();
     return e == cudaSuccess ? GNM_OK : (int)e;

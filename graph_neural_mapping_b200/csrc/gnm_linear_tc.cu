@@ -374,6 +374,7 @@ int gnm_launch_linear_tc(const float* x, int64_t ldx, int n_rows, int n_in, cons
     if (e != cudaSuccess) return (int)e;
     const int tiles = (n_rows + 127) / 128;
     const int grid = tiles < sms ? tiles : sms;
+    gnm_count_launch(GNM_K_LINEAR_TC);
     linear_tc_kernel<<<grid, LT_THREADS, LT_SMEM, stream>>>(p);
     e = cudaGetLastError();
     return e == cudaSuccess ? GNM_OK : (int)e;

@@ -527,6 +527,7 @@ extern "C" int gnm_linear(const float* x, int64_t ldx, int n_rows, int n_in, con
         if (rc == GNM_OK || g_linear_impl == 2 || rc != GNM_ERR_TOO_LARGE) return rc;
     }
     dim3 grid((n_rows + LBM - 1) / LBM, (n_out + LBN - 1) / LBN);
+    gnm_count_launch(GNM_K_LINEAR_FFMA);
     linear_kernel<<<grid, LTHREADS, 0, gnm_cast_stream(stream)>>>(x, ldx, n_rows, n_in, w, ldw, w_is_kn, bias, in_scale,
                                                                   in_shift, y, ldy, n_out, col_stats);
     GNM_RETURN_IF_LAUNCH_FAILED();
@@ -548,6 +549,7 @@ extern "C" int gnm_linear_wgrad(const float* dz, int64_t lddz, const float* x, i
     if (rows_per_slab < 256) rows_per_slab = 256;
     slabs = (n_rows + rows_per_slab - 1) / rows_per_slab;
     dim3 grid(to, ti, slabs);
+    gnm_count_launch(GNM_K_LINEAR_WGRAD_FFMA);
     linear_wgrad_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(dz, lddz, x, ldx, n_rows, n_out, n_in, in_scale,
                                                                    in_shift, dw, lddw, dbias, rows_per_slab);
     GNM_RETURN_IF_LAUNCH_FAILED();
@@ -565,6 +567,7 @@ extern "C" int gnm_col_stats(const float* x, int64_t ldx, int n_rows, int n_feat
     if (rows_per_cta < 32) rows_per_cta = 32;
     ctas = (n_rows + rows_per_cta - 1) / rows_per_cta;
     dim3 grid(ctas, fparts);
+    gnm_count_launch(GNM_K_OTHER);
     col_stats_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(x, ldx, n_rows, n_feat, col_stats, rows_per_cta);
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;
@@ -589,6 +592,7 @@ extern "C" int gnm_bn_finalize(double* col_stats, double count, const float* gam
     P2PArgs pa;
     const int prc = p2p_args(comm, 2 * n_feat, &pa);      // 2 n_feat <= 256 doubles: the launch below is one CTA
     if (prc < 0) return prc;
+    gnm_count_launch(GNM_K_OTHER);
     bn_finalize_kernel<<<(n_feat + 127) / 128, 128, 0, gnm_cast_stream(stream)>>>(
         col_stats, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, scale, shift, mean,
         rstd, n_feat, pa);
@@ -602,6 +606,7 @@ extern "C" int gnm_bn_eval_affine(const float* running_mean, const float* runnin
     if (n_feat < 0) return GNM_ERR_BAD_ARG;
     if (n_feat == 0) return GNM_OK;
     if (!running_mean || !running_var || !scale || !shift || !mean || !rstd) return GNM_ERR_BAD_ARG;
+    gnm_count_launch(GNM_K_OTHER);
     bn_eval_affine_kernel<<<(n_feat + 127) / 128, 128, 0, gnm_cast_stream(stream)>>>(
         running_mean, running_var, gamma, beta, eps, scale, shift, mean, rstd, n_feat);
     GNM_RETURN_IF_LAUNCH_FAILED();
@@ -617,6 +622,7 @@ extern "C" int gnm_bn_relu_readout(const float* z, int64_t ldz, int n_rows, int 
     const bool vec = (n_feat % 4 == 0) && n_feat <= 1024 && (ldz % 4 == 0) && gnm_aligned16(z) && gnm_aligned16(scale) &&
                      gnm_aligned16(shift) && (h == nullptr || ((ldh % 4 == 0) && gnm_aligned16(h)));
     if (vec) {
+        gnm_count_launch(GNM_K_OTHER);
         bn_relu_readout_vec_kernel<<<n_graphs, 256, 0, gnm_cast_stream(stream)>>>(z, ldz, n_feat, scale, shift, h, ldh,
                                                                                   node_off, pool_scale, pooled,
                                                                                   ld_pooled);
@@ -624,6 +630,7 @@ extern "C" int gnm_bn_relu_readout(const float* z, int64_t ldz, int n_rows, int 
         return GNM_OK;
     }
     dim3 grid(n_graphs, (n_feat + 255) / 256);
+    gnm_count_launch(GNM_K_OTHER);
     bn_relu_readout_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(z, ldz, n_feat, scale, shift, h, ldh, node_off,
                                                                       pool_scale, pooled, ld_pooled);
     GNM_RETURN_IF_LAUNCH_FAILED();
@@ -644,6 +651,7 @@ extern "C" int gnm_relu_bn_bwd_reduce(const float* z, int64_t ldz, int n_rows, i
                      gnm_aligned16(dy) && gnm_aligned16(scale) && gnm_aligned16(shift) && gnm_aligned16(mean) &&
                      gnm_aligned16(rstd) && (d_out == nullptr || ((ld_dout % 4 == 0) && gnm_aligned16(d_out)));
     if (vec) {
+        gnm_count_launch(GNM_K_OTHER);
         relu_bn_bwd_reduce_vec_kernel<<<n_graphs, 256, 0, gnm_cast_stream(stream)>>>(
             z, ldz, n_feat, scale, shift, mean, rstd, d_out, ld_dout, d_pooled, ld_dpooled, pool_scale, d_score, u, ldu,
             d_neg, ld_dneg, n_neg, node_off, dy, lddy, stats);
@@ -651,6 +659,7 @@ extern "C" int gnm_relu_bn_bwd_reduce(const float* z, int64_t ldz, int n_rows, i
         return GNM_OK;
     }
     dim3 grid(n_graphs, (n_feat + 255) / 256);
+    gnm_count_launch(GNM_K_OTHER);
     relu_bn_bwd_reduce_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(
         z, ldz, n_feat, scale, shift, mean, rstd, d_out, ld_dout, d_pooled, ld_dpooled, pool_scale, d_score, u, ldu,
         d_neg, ld_dneg, n_neg, node_off, dy, lddy, stats);
@@ -667,6 +676,7 @@ extern "C" int gnm_bn_bwd_apply(const float* z, int64_t ldz, int n_rows, int n_f
     const int64_t total = (int64_t)n_rows * n_feat;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    gnm_count_launch(GNM_K_OTHER);
     bn_bwd_apply_kernel<<<(int)blocks, 256, 0, gnm_cast_stream(stream)>>>(z, ldz, n_rows, n_feat, mean, rstd, gamma,
                                                                           stats, count, dy, lddy);
     GNM_RETURN_IF_LAUNCH_FAILED();

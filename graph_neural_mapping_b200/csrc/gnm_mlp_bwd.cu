@@ -264,6 +264,7 @@ extern "C" int gnm_bn_bwd_coeffs(double* stats, double count, const float* gamma
     P2PArgs pa;
     const int prc = p2p_args(comm, 2 * n_feat, &pa);
     if (prc < 0) return prc;
+    gnm_count_launch(GNM_K_OTHER);
     bn_bwd_coeffs_kernel<<<(n_feat + 127) / 128, 128, 0, gnm_cast_stream(stream)>>>(stats, count, gamma, mean, rstd,
                                                                                     coef, n_feat, pa);
     GNM_RETURN_IF_LAUNCH_FAILED();
@@ -317,6 +318,7 @@ extern "C" int gnm_linear_bwd(const float* dy, int64_t lddy, const float* z, int
     const int tiles = (n_rows + FB_M - 1) / FB_M;
     int grid = sms * 2;
     if (grid > tiles) grid = tiles;
+    gnm_count_launch(GNM_K_LINEAR_BWD_FFMA);
     linear_bwd_kernel<<<grid, 256, smem, gnm_cast_stream(stream)>>>(p);
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;

@@ -51,6 +51,7 @@ extern "C" int gnm_p2p_allreduce(double* data, int n, const gnm_p2p_comm* comm, 
     const int rc = p2p_args(comm, n, &a);
     if (rc == 1) return GNM_OK;
     if (rc != GNM_OK) return rc;
+    gnm_count_launch(GNM_K_OTHER);
     p2p_allreduce_kernel<<<1, 256, 0, gnm_cast_stream(stream)>>>(data, n, a);
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;

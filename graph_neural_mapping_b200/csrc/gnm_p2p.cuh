@@ -53,8 +53,10 @@ __device__ __forceinline__ unsigned int* p2p_flag(void* base, int par, int src) 
 // Exactly ONE CTA per rank may execute it per call.
 __device__ __forceinline__ void p2p_allreduce_block(double* data, int n, const P2PArgs a) {
     __shared__ unsigned int s_seq;
+    __shared__ int s_gave_up;
     const int tid = threadIdx.x;
     if (tid == 0) {
+        s_gave_up = 0;
         s_seq = *a.counter + 1;
         *a.counter = s_seq;
     }
@@ -79,6 +81,7 @@ __device__ __forceinline__ void p2p_allreduce_block(double* data, int n, const P
                 __nanosleep(100);
                 if (clock64() - t0 > P2P_TIMEOUT_CYCLES) {      // bounded: never hang the GPU on a missing peer
                     g_p2p_abort = 1;
+                    s_gave_up = 1;
                     break;
                 }
             }
@@ -86,8 +89,11 @@ __device__ __forceinline__ void p2p_allreduce_block(double* data, int n, const P
     }
     __syncthreads();
     void* local = a.peers[a.rank];
+    // a peer that never showed up must not yield a plausible-looking partial sum: poison the result, so that the
+    // BatchNorm statistics, the loss and every gradient of this step turn NaN (and gnm_p2p_status reports why)
+    const bool gave_up = s_gave_up != 0;
     for (int e = tid; e < n; e += blockDim.x) {
-        double s = 0.0;
+        double s = gave_up ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
         for (int p = 0; p < a.world; ++p) {
             const volatile double* q = p2p_slot(local, par, p);
             s += q[e];

@@ -156,6 +156,7 @@ extern "C" int gnm_csr_build(const int64_t* edges, int64_t e_total, const int64_
     const size_t smem = (size_t)(fixed + (int64_t)sort_warps * n_max * 4);
     cudaError_t e = cudaFuncSetAttribute(csr_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    gnm_count_launch(GNM_K_OTHER);
     csr_build_kernel<<<n_graphs, kBuildThreads, smem, gnm_cast_stream(stream)>>>(
         edges, e_total, edge_off, node_off, n_graphs, n_max, add_self_loops, local_cols, sort_warps, rowptr, colidx,
         status);
@@ -176,6 +177,7 @@ extern "C" int gnm_csr_batch_gather(const int64_t* src_rowptr_addr, const int64_
     if (parts > 16) parts = 16;
     if (colidx == nullptr) parts = 1;
     dim3 grid(n_graphs, parts);
+    gnm_count_launch(GNM_K_OTHER);
     csr_batch_gather_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(src_rowptr_addr, src_colidx_addr, src_tag_addr,
                                                                        node_off, nnz_off, n_graphs, rowptr, colidx,
                                                                        tags);

@@ -153,7 +153,16 @@ def average_gradients(model, comm):
     torch._foreach_copy_(grads, views)          # one multi-tensor kernel instead of one copy per parameter
 
 
-def shutdown():
+def _teardown_timed_out(code):
+    import sys
+    sys.stderr.write("graph_neural_mapping_b200.dist.shutdown: process-group / peer-buffer teardown did not finish "
+                     "within 30 s; exiting with status %d\n" % code)
+    sys.stderr.flush()
+    sys.stdout.flush()
+    os._exit(code)
+
+
+def shutdown(timeout_exit_code=1):
     """Tear the default process group down. Call `model.release_graphs()` first: CUDA graphs that captured NCCL
     kernels keep the communicator alive and `destroy_process_group` would wait for them."""
     import gc
@@ -167,7 +176,8 @@ def shutdown():
         # teardown hold the job (and the GPUs) hostage
         sys.stdout.flush()
         sys.stderr.flush()
-        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        # a hung teardown is a FAILURE the launcher must see: non-zero exit status plus a message on stderr
+        watchdog = threading.Timer(30.0, _teardown_timed_out, args=(int(timeout_exit_code),))
         watchdog.daemon = True
         watchdog.start()
         if _OPEN_P2P:

@@ -89,14 +89,14 @@ class _WholeStepPlan(object):
     def run(self):
         if self.graph is None:
             g = torch.cuda.CUDAGraph()
-            n0 = _ops.LAUNCHES[0]
+            n0 = _ops.kernels_recorded()
             with torch.cuda.graph(g):
                 self.loss = self.body()
-            self.launches = _ops.LAUNCHES[0] - n0
-            _ops.LAUNCHES[0] = n0                      # capture records, replay launches
+            self.launches = _ops.kernels_recorded() - n0     # libgnm kernels inside the graph (C-side counters)
+            _ops.REPLAYED[0] -= self.launches                # capture records, replay launches
             self.graph = g
         self.graph.replay()
-        _ops.LAUNCHES[0] += self.launches
+        _ops.REPLAYED[0] += self.launches
         return self.loss
 
 
@@ -105,15 +105,23 @@ class Trainer(object):
     with one-hot node features; `comm` the data-parallel communicator (`dist.init_from_env()`), each rank passing its
     own shard of the global batch. Adam only (the reference's optimizer, `main.py:137`)."""
 
-    def __init__(self, model, lr=0.01, beta=0.1, comm=None, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, model, lr=0.005, beta=0.05, comm=None, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 check_every=100):
+        """Defaults follow main.py:113,118 (--lr 0.005, --beta 0.05). The learning rate lives in a DEVICE tensor, so
+        a scheduler (`torch.optim.lr_scheduler.StepLR(trainer.optimizer, ...)`, main.py:138,147) or `set_lr()` changes
+        what the captured step reads - a Python float would be baked into the CUDA graph at capture.
+        `check_every`: every that many steps (and in `finish()`) the kernels' bounded-wait flags are polled (one device
+        synchronisation); a tcgen05 pipeline or peer exchange that timed out raises instead of training on garbage."""
         dev = model.eps.device
         _engine.require_cuda(dev)
         self.model = model
         self.beta = float(beta)
         self.comm = comm if comm is not None else _dist.SINGLE
         model.set_comm(self.comm)
-        self.optimizer = torch.optim.Adam(model.parameters(), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
-                                          capturable=True)
+        self.optimizer = torch.optim.Adam(model.parameters(), lr=torch.tensor(float(lr), dtype=torch.float32, device=dev),
+                                          betas=betas, eps=eps, weight_decay=weight_decay, capturable=True)
+        self.check_every = int(check_every)
+        self.steps_done = 0
         self.c_criterion = torch.nn.CrossEntropyLoss()          # main.py:16
         self.d_criterion = torch.nn.BCEWithLogitsLoss()         # main.py:17
         self._plans = {}
@@ -124,6 +132,33 @@ class Trainer(object):
     def _signature(h, n_global):
         return (h.b, h.m, h.uniform_n, h.onehot, h.feat_dim, h.n_max, h.dense, h.has_isolated, h.same_tags,
                 h.max0_as_sum, n_global)
+
+    def set_lr(self, lr):
+        """Change the learning rate of every parameter group in place (visible to the captured CUDA graph)."""
+        for group in self.optimizer.param_groups:
+            if torch.is_tensor(group["lr"]):
+                group["lr"].fill_(float(lr))
+            else:
+                group["lr"] = float(lr)
+
+    def get_lr(self):
+        return float(self.optimizer.param_groups[0]["lr"])
+
+    def check(self):
+        """Poll the kernels' bounded-wait flags (synchronises the device). Raises if a tcgen05 kernel or a peer-memory
+        exchange gave up waiting since the last check: every step since then is invalid."""
+        if _ops.aggregate_tc_status():
+            raise RuntimeError("a tcgen05 kernel (aggregation / linear) hit its bounded barrier wait: the steps since "
+                               "the last check are invalid")
+        p2p = self.comm.p2p
+        if p2p is not None and p2p.status():
+            raise RuntimeError("a peer-memory exchange gave up waiting for a peer: BatchNorm statistics (and everything "
+                               "after them) were poisoned with NaN on this rank")
+
+    def finish(self):
+        """Call at the end of training / an epoch: drains the stream and checks the kernels' status flags."""
+        torch.cuda.synchronize(self.model.eps.device)
+        self.check()
 
     def release(self):
         """Drop the captured graphs (do this before tearing a process group down: they hold NCCL work)."""
@@ -158,6 +193,9 @@ class Trainer(object):
             self._seen[key] = 0
         self.h2d_bytes += plan.load(h, perm, labels)
         self._seen[key] += 1
+        self.steps_done += 1
+        if self.check_every > 0 and self.steps_done % self.check_every == 0:
+            self.check()
         if self._seen[key] <= 2:
             return plan.body()                                   # warm-up: cuBLAS handles, allocator, NCCL
         return plan.run()

@@ -59,9 +59,19 @@ class GraphStore(object):
     """Device cache of per-graph local CSRs, keyed on the identity of the caller's graph
     objects (the caller owns them and reuses them every step, main.py:26-28)."""
 
-    def __init__(self, device, add_self_loops):
+    def __init__(self, device, add_self_loops, max_bytes=None):
+        """`max_bytes`: device-memory budget of the cache (default: a quarter of the device's memory). When a new
+        chunk would exceed it the WHOLE store is dropped and the current batch re-built - callers that create fresh
+        graph objects every step (augmentation, re-thresholding) therefore run at first-touch speed with bounded
+        memory instead of leaking host and device memory. The key is the graph OBJECT: editing `graph.edge_mat` in
+        place after its first use is not seen (call `GIN_InfoMaxReg.forget_graphs()` after such an edit)."""
         self.device = device
         self.add_self_loops = bool(add_self_loops)
+        if max_bytes is None:
+            max_bytes = torch.cuda.get_device_properties(device).total_memory // 4 if device.type == "cuda" else 1 << 62
+        self.max_bytes = int(max_bytes)
+        self.bytes = 0              # device bytes held by the stored CSRs / tags / bitmaps
+        self.evictions = 0
         self.entries = {}           # id(graph) -> slot
         # slot table (one row per stored graph): rowptr / colidx / tag / bitmap addresses, n, nnz, onehot, isolated,
         # feature width, tag-sequence id. A batch is assembled from it with a handful of numpy gathers instead of per-graph Python.
@@ -91,6 +101,7 @@ class GraphStore(object):
         self._n_slots = 0
         self._pins = []
         self._tag_cache.clear()
+        self.bytes = 0
 
     def _staging(self, e_total):
         """Pinned [2, E] int64 host buffer (grown geometrically, reused) for the edge lists of new graphs."""
@@ -120,6 +131,12 @@ class GraphStore(object):
                 new.append(g)
         if not new:
             return
+        if self.bytes > self.max_bytes and self.entries:
+            # over budget: drop everything (buffers still referenced by enqueued kernels stay alive in torch's
+            # stream-ordered allocator) and re-build this batch
+            self.clear()
+            self.evictions += 1
+            return self.ensure(graphs)
         dev = self.device
         counts = [len(g.g) for g in new]
         ems = []
@@ -174,6 +191,7 @@ class GraphStore(object):
             iso_h[np.searchsorted(node_off, zero_rows, side="right") - 1] = True
         self.h2d_bytes += bm_off.nbytes
         keep = (rowptr, colidx, tags_d, bitmap)
+        self.bytes += sum(int(t.numel()) * t.element_size() for t in keep)
         rp0, ci0, tg0, bm0 = rowptr.data_ptr(), colidx.data_ptr(), tags_d.data_ptr(), bitmap.data_ptr()
         k = len(new)
         if self._n_slots + k > self._tab.shape[0]:

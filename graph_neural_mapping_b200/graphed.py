@@ -93,16 +93,16 @@ class StepPlan(object):
         if self.fwd_graph is None:
             g = torch.cuda.CUDAGraph()
             params = [p.detach() for p in _engine.flat_params(model)]
-            n0 = _ops.LAUNCHES[0]
+            n0 = _ops.kernels_recorded()
             with torch.cuda.graph(g, pool=self.pool):
                 bs = self._structure()
                 g_f, d_logit, sv = _engine.run_forward(model, bs, self.neg_idx, True, True, None, params, self.comm)
-            self.fwd_launches = _ops.LAUNCHES[0] - n0          # libgnm kernels inside the graph
-            _ops.LAUNCHES[0] = n0                              # capture records, replay launches
+            self.fwd_launches = _ops.kernels_recorded() - n0   # libgnm kernels inside the graph (C-side counters)
+            _ops.REPLAYED[0] -= self.fwd_launches              # capture records, replay launches
             self.fwd_graph, self.g_f, self.d_logit, self.sv, self.params = g, g_f, d_logit, sv, params
             self.bwd_graph = None
         self.fwd_graph.replay()
-        _ops.LAUNCHES[0] += self.fwd_launches
+        _ops.REPLAYED[0] += self.fwd_launches
         self.generation += 1
         return self.g_f.clone(), self.d_logit.clone()
 
@@ -113,20 +113,20 @@ class StepPlan(object):
             self.dg_in.copy_(dg_f)
             self.dd_in.copy_(dd_logit)
             g = torch.cuda.CUDAGraph()
-            n0 = _ops.LAUNCHES[0]
+            n0 = _ops.kernels_recorded()
             with torch.cuda.graph(g, pool=self.pool):
                 _, grads = _engine.run_backward(self.model, self.sv, self.params, self.dg_in, self.dd_in, False,
                                                 self.comm)
                 self.grad_shapes = [None if x is None else tuple(x.shape) for x in grads]
                 self.flat = torch.cat([x.reshape(-1) for x in grads if x is not None])
-            self.bwd_launches = _ops.LAUNCHES[0] - n0
-            _ops.LAUNCHES[0] = n0
+            self.bwd_launches = _ops.kernels_recorded() - n0
+            _ops.REPLAYED[0] -= self.bwd_launches
             self.bwd_graph = g
         else:
             self.dg_in.copy_(dg_f)
             self.dd_in.copy_(dd_logit)
         self.bwd_graph.replay()
-        _ops.LAUNCHES[0] += self.bwd_launches
+        _ops.REPLAYED[0] += self.bwd_launches
         flat = self.flat.clone()
         out, off = [], 0
         for shp in self.grad_shapes:

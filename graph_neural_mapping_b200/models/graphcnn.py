@@ -65,6 +65,12 @@ class GIN_InfoMaxReg(nn.Module):
         global batch and synchronises BatchNorm statistics and the DGI negatives over `comm`."""
         self._comm = comm if comm is not None else _dist.SINGLE
 
+    def forget_graphs(self):
+        """Drop the device-resident per-graph CSR cache (e.g. after editing a graph's `edge_mat` in place: the cache is
+        keyed on the graph objects, SURVEY 8(b) ownership)."""
+        if self._store is not None:
+            self._store.clear()
+
     def release_graphs(self):
         """Drop the captured CUDA graphs (and their static buffers); they are re-captured on demand."""
         self._plans.clear()
@@ -103,7 +109,7 @@ class GIN_InfoMaxReg(nn.Module):
         if not (self.use_cuda_graphs and self.training and torch.is_grad_enabled() and h.onehot
                 and (self.neighbor_pooling_type != "max" or h.max0_as_sum) and self.eps.device.type == "cuda"):
             return None
-        key = _graphed.StepPlan._signature(h) + (n_global, self._comm.world)
+        key = _graphed.StepPlan._signature(h) + (n_global, self._comm.world)      # training only: comm is self._comm
         plan = self._plans.get(key)
         if plan is not None and not plan.compatible(h, n_global):
             del self._plans[key]
@@ -174,7 +180,10 @@ class GIN_InfoMaxReg(nn.Module):
 
     # ---- reference API ------------------------------------------------------------------------
     def forward(self, batch_graph, latent=False):
-        comm = self._comm
+        # data parallel applies to TRAINING forwards only. In eval mode BatchNorm uses the running statistics and no
+        # exchange is needed, so a main.py-style test() on one rank (or with unequal chunk counts per rank) must not
+        # enter a collective: the call is then single-process, each rank treating its list as the whole batch.
+        comm = self._comm if self.training else _dist.SINGLE
         n_global = len(batch_graph) * comm.world
         rand_seq = np.random.permutation(n_global)          # graphcnn.py:199 (one numpy draw per call)
         h = self._host_batch(batch_graph)

@@ -12,7 +12,8 @@ import torch
 from . import lib as _libmod
 
 _state = {"device": None}
-LAUNCHES = [0]      # kernels enqueued through this module (one per entry-point call)
+LAUNCHES = [0]      # entry-point calls made through this module (an entry point may enqueue several kernels)
+REPLAYED = [0]      # kernels launched by CUDA-graph replays (driver.Trainer / graphed.StepPlan account for them here)
 
 
 def _lib():
@@ -53,6 +54,31 @@ def device_info():
     _libmod.check(_lib().gnm_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(smem)),
                   "gnm_device_info")
     return dict(sm_count=sm.value, cc=(ma.value, mi.value), smem_optin=smem.value)
+
+
+KERNEL_FAMILIES = ("aggregate_csr", "aggregate_mma_sync", "aggregate_tc", "linear_ffma", "linear_tc", "linear_bwd_ffma",
+                   "linear_bwd_dx_tc", "linear_wgrad_tc", "linear_wgrad_ffma", "other")
+
+
+def launch_counts():
+    """Kernels libgnm has enqueued so far, per family (gnm_launch_counts of include/gnm.h) - which kernel family a
+    code path really ran (tests) and how many kernels a step launches (bench.py). Host counters: a kernel recorded
+    under CUDA-graph capture counts once."""
+    buf = (ctypes.c_int64 * len(KERNEL_FAMILIES))()
+    n = _lib().gnm_launch_counts(buf, len(KERNEL_FAMILIES))
+    if n != len(KERNEL_FAMILIES):
+        raise RuntimeError("gnm_launch_counts: library reports %d kernel families, binding expects %d" % (n, len(KERNEL_FAMILIES)))
+    return {k: int(buf[i]) for i, k in enumerate(KERNEL_FAMILIES)}
+
+
+def kernels_recorded():
+    """Sum of libgnm's per-family launch counters: kernels ENQUEUED (or recorded under capture) so far."""
+    return sum(launch_counts().values())
+
+
+def kernels_launched():
+    """libgnm kernels that have run (or are queued to run) on the device: eager launches plus CUDA-graph replays."""
+    return kernels_recorded() + REPLAYED[0]
 
 
 # ---- structure ---------------------------------------------------------------------------

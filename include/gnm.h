@@ -33,7 +33,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 13
+#define GNM_ABI_VERSION 14
 
 typedef void* gnm_stream_t;
 
@@ -56,6 +56,13 @@ const char* gnm_error_string(int code);
 /* Bind this library's CUDA runtime to device `dev` (one process per GPU). */
 int gnm_set_device(int dev);
 int gnm_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes);
+/* Process-wide diagnostic counters (host pointer): out[i] = kernels this library has ENQUEUED so far in family i
+ * (a kernel recorded during CUDA-graph capture counts once, its replays are the caller's to count). Families:
+ * 0 aggregate (CSR warp-per-row), 1 aggregate (mma.sync dense blocks), 2 aggregate (tcgen05), 3 linear (FFMA),
+ * 4 linear (tcgen05), 5 linear_bwd (fused FFMA), 6 linear_bwd dX (tcgen05), 7 linear_bwd dW (tcgen05),
+ * 8 linear_wgrad (FFMA), 9 every other kernel. Returns the number of families (>= 0) or GNM_ERR_BAD_ARG.
+ * Tests use it to prove WHICH kernel family a code path ran; bench.py to count launches. */
+int gnm_launch_counts(int64_t* out, int n);
 
 /* ---- adjacency / readout structure ------------------------------------------------------ */
 

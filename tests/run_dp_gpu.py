@@ -118,7 +118,7 @@ def main():
                 floor = grad_floor(ref)
                 for k, p in model.named_parameters():
                     if k in ref:
-                        assert_close(p.grad, ref[k], 2e-3, "grad " + k, floor=floor)
+                        assert_close(p.grad, ref[k], 2e-3, "grad " + k, floor=floor(k))
                 if not graphs_on:
                     for k, v in g.group("buf_after/").items():
                         if "num_batches" not in k:

@@ -1,25 +1,27 @@
 """GPU parity of the whole drop-in path (GIN_InfoMaxReg on libgnm) against the golden fixtures
 written by the UNMODIFIED reference, and against the fp64 oracle (tolerance tie-breaker).
 
-Tolerances (scaled by each tensor's max-abs): logits/loss/latent 1e-4; gradients
-and saliency 2e-3 - the reference's own fp32 result differs from the fp64 oracle by up to 1e-3
-on some gradients at N=400 (tests/test_oracle_vs_golden.py), so nothing tighter is meaningful."""
+Tolerances, every tensor scaled by ITS OWN max-abs: logits / loss / latent / BatchNorm buffers 1e-4;
+every gradient tensor and saliency 2e-3. The gradient figure is the reference's own noise level: its fp32 result
+differs from the fp64 oracle by up to 1.1e-3 of a tensor's max-abs at N=400 (`mlps.3.linears.1.weight` of
+schaefer400_b16_eps, `mlps.0.linears.1.weight` of schaefer400_eps; <= 1e-5 on the small fixtures), so nothing tighter
+is meaningful against the fixture. Only the MLP Linear biases (true gradient exactly zero in front of a train-mode
+BatchNorm) are compared on a floor (helpers.grad_floor). The `schaefer400_b16_*` fixtures have M = 6400 rows >= 4096:
+they run the tcgen05 GEMM / aggregation kernels the benchmark runs, which the test asserts from libgnm's launch counters."""
 import numpy as np
 import pytest
 import torch
 
-from helpers import Golden, assert_close, golden_names, grad_floor
+from helpers import Golden, SEED0, assert_close, golden_names, grad_floor
 from oracle import gin_oracle
 from graph_neural_mapping_b200.models import GIN_InfoMaxReg, Discriminator, MLP
-from graph_neural_mapping_b200 import synth
+from graph_neural_mapping_b200 import ops, synth
 
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda")
 NAMES = golden_names()
 TOL, TOL_GRAD = 1e-4, 2e-3
-SEEDS = {"tiny_eps_sum": 100, "tiny_noeps_sum": 100, "tiny_eps_avg": 300, "tiny_noeps_avg": 300, "tiny_mlp1": 500,
-         "tiny_mlp3": 500, "mid_eps_sum_h64": 900, "schaefer400_noeps": 0, "schaefer400_eps": 10, "tiny_eps_max": 700,
-         "tiny_noeps_max": 700}
+SEEDS = SEED0
 
 
 def build_model(g, sd=None):
@@ -49,7 +51,16 @@ def test_train_step_vs_reference_and_oracle(name):
     g = Golden(name)
     model = build_model(g)
     graphs = g.graphs()
+    before = ops.launch_counts()
     c_logit, d_logit, loss = train_step(model, graphs, g.cfg["beta"], 4242 + SEEDS[name])
+    ran = {k: v - before[k] for k, v in ops.launch_counts().items()}
+    if "_b16_" in name:
+        # the benchmarked code path: tcgen05 aggregation, tcgen05 Linear forward, tcgen05 dX and dW backward - and
+        # none of the small-problem fallbacks
+        assert ran["aggregate_tc"] >= 9 and ran["linear_tc"] >= 9, ran
+        assert ran["linear_bwd_dx_tc"] >= 8 and ran["linear_wgrad_tc"] >= 9, ran
+        assert ran["linear_ffma"] == ran["linear_bwd_ffma"] == ran["aggregate_csr"] == ran["aggregate_mma_sync"] == 0, ran
+        assert not ops.aggregate_tc_status(), "a tcgen05 kernel hit its bounded wait"
     assert_close(c_logit, g.z["train/c_logit"], TOL, "c_logit")
     assert_close(d_logit, g.z["train/d_logit"], TOL, "d_logit")
     assert_close(loss, g.z["train/loss"], TOL, "loss")
@@ -58,7 +69,7 @@ def test_train_step_vs_reference_and_oracle(name):
     for k, p in model.named_parameters():
         if k in ref_grads:
             assert p.grad is not None, k
-            assert_close(p.grad, ref_grads[k], TOL_GRAD, "grad " + k, floor=floor)
+            assert_close(p.grad, ref_grads[k], TOL_GRAD, "grad " + k, floor=floor(k))
         else:
             assert p.grad is None, k
     for k, v in g.group("buf_after/").items():
@@ -78,7 +89,7 @@ def test_train_step_vs_reference_and_oracle(name):
     floor = grad_floor(ograds)
     for k, p in model.named_parameters():
         if ograds.get(k) is not None:
-            assert_close(p.grad, ograds[k], TOL_GRAD, "grad vs fp64 " + k, floor=floor)
+            assert_close(p.grad, ograds[k], TOL_GRAD, "grad vs fp64 " + k, floor=floor(k))
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -107,10 +118,10 @@ def test_eval_latent_saliency_vs_reference(name):
         assert_close(s, v, TOL_GRAD, "saliency " + k)
         if gi == 0 and cls == 1:
             ref = g.group("saliency_paramgrad/")
-            floor = grad_floor(ref) if ref else 0.0
+            floor = grad_floor(ref, training=False)
             for kk, p in model.named_parameters():
                 if kk in ref:
-                    assert_close(p.grad, ref[kk], TOL_GRAD, "saliency param grad " + kk, floor=floor)
+                    assert_close(p.grad, ref[kk], TOL_GRAD, "saliency param grad " + kk, floor=floor(kk))
     if g.cfg["neighbor_pooling_type"] == "max":
         return      # the dummy row of max pooling is the batch-wide minimum (graphcnn.py:140): isolated nodes couple graphs
     # batched saliency == per-graph saliency (eval-mode BN, block-diagonal adjacency)
@@ -258,7 +269,7 @@ def test_cuda_graph_steps_match_eager_steps():
             if p1.grad is None:
                 assert p2.grad is None
             else:
-                assert_close(p2.grad, p1.grad, 1e-4, "grad %s step %d" % (k, step), floor=floor)
+                assert_close(p2.grad, p1.grad, 1e-4, "grad %s step %d" % (k, step), floor=floor(k))
         o1.step()
         o2.step()
     assert len(m_graph._plans) == 1 and next(iter(m_graph._plans.values())).bwd_graph is not None
@@ -315,7 +326,7 @@ def test_schaefer1000_hidden128_config_vs_oracle():
         floor = grad_floor(ograds)
         for k, p in model.named_parameters():
             if ograds.get(k) is not None:
-                assert_close(p.grad, ograds[k], TOL_GRAD, "grad " + k, floor=floor)
+                assert_close(p.grad, ograds[k], TOL_GRAD, "grad " + k, floor=floor(k))
         s = model.compute_saliency([graphs[0]], 0)
         sref, _ = gin_oracle.saliency({k: v.detach().cpu() for k, v in model.state_dict().items()}, [graphs[0]], 0, ocfg)
         assert_close(s, sref, TOL_GRAD, "saliency")
@@ -394,3 +405,87 @@ def test_whole_step_trainer_with_dropout_is_reproducible():
         curves.append(np.array(losses))
     assert_close(curves[1], curves[0], 1e-4, "loss curve, run to run")
     assert abs(curves[0][-1] - curves[0][0]) > 1e-6, "parameters move"
+
+
+@pytest.mark.parametrize("name", ["schaefer400_b16_noeps", "schaefer400_b16_eps"])
+def test_whole_step_trainer_on_the_benchmarked_kernels_vs_reference(name):
+    """driver.Trainer at M = 6400 rows (tcgen05 kernel family, asserted) against the UNMODIFIED reference's fixture:
+    loss and every parameter gradient of the first step; then the captured CUDA graph (steps 3..) must reproduce the
+    eager steps' loss on the same batch / permutation when the parameters are put back."""
+    from graph_neural_mapping_b200.driver import Trainer
+    g = Golden(name)
+    graphs = g.graphs()
+    model = build_model(g)
+    model.final_dropout = 0.0
+    model.train()
+    tr = Trainer(model, lr=0.005, beta=g.cfg["beta"])
+    before = ops.launch_counts()
+    np.random.seed(4242 + SEEDS[name])
+    loss = float(tr.step(graphs))
+    ran = {k: v - before[k] for k, v in ops.launch_counts().items()}
+    assert ran["aggregate_tc"] >= 9 and ran["linear_tc"] >= 9 and ran["linear_bwd_dx_tc"] >= 8 and ran["linear_wgrad_tc"] >= 9, ran
+    assert ran["linear_ffma"] == ran["linear_bwd_ffma"] == 0, ran
+    assert_close(np.array(loss), g.z["train/loss"], TOL, "loss of the first Trainer step")
+    ref = g.group("grad/")
+    floor = grad_floor(ref)
+    for k, p in model.named_parameters():
+        if k in ref:
+            assert_close(p.grad, ref[k], TOL_GRAD, "Trainer grad " + k, floor=floor(k))
+    losses = []
+    for _ in range(4):                       # eager, capture, replay, replay - each from the fixture's state
+        model.load_state_dict(g.state_dict())
+        np.random.seed(4242 + SEEDS[name])
+        losses.append(float(tr.step(graphs)))
+    assert_close(np.array(losses), np.full(4, float(g.z["train/loss"])), TOL, "captured step vs reference loss")
+    tr.finish()                              # raises if a tcgen05 kernel timed out
+
+
+def test_trainer_learning_rate_schedule_reaches_the_captured_step():
+    """main.py:138,147 decays the learning rate with StepLR every epoch. The Trainer keeps lr in a device tensor, so a
+    scheduler step after capture changes the size of the next update (Adam's first-order step is ~lr per entry)."""
+    from graph_neural_mapping_b200.driver import Trainer
+    g = Golden("mid_eps_sum_h64")
+    graphs = g.graphs()
+    model = build_model(g)
+    model.final_dropout = 0.0
+    model.train()
+    tr = Trainer(model, lr=0.01, beta=g.cfg["beta"])
+    sched = torch.optim.lr_scheduler.StepLR(tr.optimizer, step_size=1, gamma=0.1)
+    w = model.mlps[1].linears[0].weight
+
+    def update_size():
+        w0 = w.detach().clone()
+        np.random.seed(5)
+        tr.step(graphs)
+        return float((w.detach() - w0).abs().max())
+
+    for _ in range(4):
+        big = update_size()                  # step 4 runs from the captured graph
+    assert len(tr._plans) == 1 and next(iter(tr._plans.values())).graph is not None
+    sched.step()                             # lr 0.01 -> 0.001
+    assert abs(tr.get_lr() - 0.001) < 1e-9
+    small = update_size()
+    assert small < 0.3 * big, (big, small)
+    tr.set_lr(0.01)
+    again = update_size()
+    assert again > 3.0 * small, (small, again)
+
+
+def test_graph_store_stays_within_its_byte_budget():
+    """Callers that build fresh graph objects every step must not leak device memory: the store drops its contents
+    when the budget is exceeded and the results do not change."""
+    g = Golden("mid_eps_sum_h64")
+    model = build_model(g)
+    model.eval()
+    graphs = g.graphs()
+    np.random.seed(0)
+    want, _ = model(graphs)
+    store = model._graph_store()
+    store.max_bytes = 3 * store.bytes // 2
+    for _ in range(6):
+        fresh = g.graphs()                   # new objects, same content
+        np.random.seed(0)
+        got, _ = model(fresh)
+        assert torch.equal(got, want)
+        assert store.bytes <= 2 * store.max_bytes
+    assert store.evictions >= 2 and len(store) <= 2 * len(graphs)

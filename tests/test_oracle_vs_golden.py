@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import csr_oracle, gin_oracle
-from helpers import Golden, assert_close, golden_names, grad_floor
+from helpers import Golden, SEED0, assert_close, golden_names, grad_floor
 
 # fp32 reference vs fp64 oracle: summation-order noise only. Scaled (max-abs) error.
 TOL64 = 1e-4
@@ -65,7 +65,7 @@ def test_train_step_matches_reference(name, dtype, tol):
     assert_close(r["loss"], g.z["train/loss"], tol, "loss")
     floor = grad_floor(g.group("grad/"))
     for k, v in g.group("grad/").items():
-        assert_close(r["grads"][k], v, TOL_GRAD, "grad " + k, floor=floor)
+        assert_close(r["grads"][k], v, TOL_GRAD, "grad " + k, floor=floor(k))
     for k in g.group("gradnone/"):
         assert r["grads"][k] is None, k
     for k, v in g.group("buf_after/").items():
@@ -111,8 +111,7 @@ def test_aten_port_matches_reference(name):
     sd = {}
     for k, v in g.state_dict().items():
         sd[k] = v.clone().requires_grad_(True) if (v.is_floating_point() and "running_" not in k) else v.clone()
-    seed = 4242 + {"tiny_eps_sum": 100, "tiny_noeps_sum": 100, "tiny_eps_avg": 300, "tiny_noeps_avg": 300, "tiny_mlp1": 500,
-                   "tiny_mlp3": 500, "mid_eps_sum_h64": 900, "schaefer400_noeps": 0, "schaefer400_eps": 10}[name]
+    seed = 4242 + SEED0[name]
     np.random.seed(seed)
     graphs = g.graphs()
     c_logit, d_logit, g_f = aten_port.forward(sd, graphs, g.cfg, True)
@@ -126,4 +125,4 @@ def test_aten_port_matches_reference(name):
     loss.backward()
     floor = grad_floor(g.group("grad/"))
     for k, v in g.group("grad/").items():
-        assert_close(sd[k].grad, v, 1e-5, "grad " + k, floor=floor)
+        assert_close(sd[k].grad, v, 1e-5, "grad " + k, floor=floor(k))
