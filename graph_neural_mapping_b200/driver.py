@@ -43,6 +43,14 @@ class _WholeStepPlan(object):
         self.loss = None
         self.h = h
         self.launches = 0
+        if trainer.fused:
+            heads = list(model.linears_prediction)
+            n_cls, n_feat = heads[0].weight.shape
+            self.loss_terms = torch.zeros(2, dtype=torch.float64, device=dev)
+            self.loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.heads_ws = torch.empty(_ops.heads_ce_workspace(h.b, len(heads), n_feat, n_cls), dtype=torch.float32, device=dev)
+            self.heads_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.c_logit = None
 
     def load(self, h, perm, labels):
         """Host -> device traffic of one step, staged through a ring of pinned buffers (never waits for the GPU)."""
@@ -70,6 +78,75 @@ class _WholeStepPlan(object):
         return h.packed.nbytes + h.node_off.nbytes + 4 * perm.size + 8 * len(labels)
 
     def body(self):
+        return self.body_fused() if self.trainer.fused else self.body_autograd()
+
+    def body_fused(self):
+        """One training step without torch autograd / torch.optim / torch loss kernels: encoder + DGI forward
+        (engine.run_forward), prediction heads + dropout + CrossEntropy forward and backward (gnm_heads_ce),
+        BCEWithLogits forward and backward (gnm_bce_logits), the hand-derived backward (engine.run_backward),
+        gradient averaging and Adam (gnm_adam_step). Same arithmetic as main.py:31-41."""
+        tr = self.trainer
+        model = tr.model
+        dev = self.dev
+        store = model._graph_store()
+        bs = store.assemble_device(self.h, self.packed, self.node_off, nnz_capacity=self.nnz_cap)
+        bs.set_pooling(model.graph_pooling_type, dev)
+        enc_params = _engine.flat_params(model)
+        params = [p.detach() for p in enc_params]
+        g_f, d_logit, sv = _engine.run_forward(model, bs, self.neg_idx, True, True, None, params, tr.comm)
+        b, m = bs.n_graphs, bs.n_rows
+        heads = list(model.linears_prediction)
+        n_layers, n_cls, n_feat = len(heads), heads[0].weight.shape[0], heads[0].weight.shape[1]
+        hw = [h.weight.detach() for h in heads]
+        hb = [h.bias.detach() for h in heads]
+        d_hw = [torch.empty_like(w) for w in hw]
+        d_hb = [torch.empty_like(x) for x in hb]
+        mask = None
+        if model.final_dropout > 0.0:
+            # F.dropout's keep mask (graphcnn.py:230), one draw for all layers from torch's (CUDA-graph aware) generator
+            keep = 1.0 - float(model.final_dropout)
+            mask = torch.empty(n_layers, b, n_cls, dtype=torch.float32, device=dev).bernoulli_(keep).mul_(1.0 / keep)
+        self.loss_terms.zero_()                     # [CE mean, beta * BCE mean], float64
+        c_logit = torch.empty(b, n_cls, dtype=torch.float32, device=dev)
+        d_gf = torch.empty_like(g_f)
+        _ops.heads_ce(g_f, hw, hb, mask, self.labels, 1.0 / b, c_logit, self.loss_terms[0:1], d_gf, d_hw, d_hb,
+                      self.heads_ws, self.heads_counter)
+        dd = torch.empty(2 * m, 1, dtype=torch.float32, device=dev)
+        w_bce = tr.beta / (2.0 * m)
+        _ops.bce_logits(d_logit.view(-1), m, w_bce, w_bce, self.loss_terms[1:2], dd.view(-1))       # main.py:32-37
+        _, enc_grads = _engine.run_backward(model, sv, params, d_gf, dd, False, tr.comm)
+        tensors, grads = [], []
+        for p, g in zip(enc_params, enc_grads):
+            if g is not None and p.requires_grad:
+                tensors.append(p)
+                grads.append(g.reshape(p.shape))
+        for h, gw, gb in zip(heads, d_hw, d_hb):
+            tensors += [h.weight, h.bias]
+            grads += [gw, gb]
+        grad_scale = 1.0
+        world = tr.comm.world
+        if world > 1:
+            # one flat all-reduce; each rank's loss is the mean over its own shard, so the average over ranks is the
+            # gradient of the global-batch mean loss (main.py:34-41 at the global batch)
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            tr.comm.all_reduce_sum(flat)
+            flat.mul_(1.0 / world)
+            views, off = [], 0
+            for g in grads:
+                views.append(flat[off:off + g.numel()].view(g.shape))
+                off += g.numel()
+            grads = views
+        state = tr.adam_state(tensors)
+        group = tr.optimizer.param_groups[0]
+        _ops.adam_step([p.detach() for p in tensors], [g.contiguous() for g in grads], state["offsets"], state["exp_avg"],
+                       state["exp_avg_sq"], state["step"], group["lr"], group["betas"][0], group["betas"][1], group["eps"],
+                       group["weight_decay"], grad_scale, loss_terms=self.loss_terms, loss_out=self.loss_out)
+        for p, g in zip(tensors, grads):
+            p.grad = g                                   # for inspection (aliases step-local / CUDA-graph memory)
+        self.c_logit = c_logit
+        return self.loss_out[0]
+
+    def body_autograd(self):
         """One training step on the static buffers (runs eagerly while warming up, then under capture)."""
         tr = self.trainer
         model = tr.model
@@ -106,7 +183,7 @@ class Trainer(object):
     own shard of the global batch. Adam only (the reference's optimizer, `main.py:137`)."""
 
     def __init__(self, model, lr=0.005, beta=0.05, comm=None, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                 check_every=100):
+                 check_every=100, fused=True):
         """Defaults follow main.py:113,118 (--lr 0.005, --beta 0.05). The learning rate lives in a DEVICE tensor, so
         a scheduler (`torch.optim.lr_scheduler.StepLR(trainer.optimizer, ...)`, main.py:138,147) or `set_lr()` changes
         what the captured step reads - a Python float would be baked into the CUDA graph at capture.
@@ -122,6 +199,12 @@ class Trainer(object):
                                           betas=betas, eps=eps, weight_decay=weight_decay, capturable=True)
         self.check_every = int(check_every)
         self.steps_done = 0
+        # fused=True: the step's [B, L*F]-sized remainder (heads, dropout, CE, BCE, Adam) runs on libgnm's own kernels
+        # (gnm_train.cu) and the backward is called directly - no torch autograd / loss / optimizer kernels in the
+        # step. fused=False: torch's loss functions, autograd and torch.optim.Adam(capturable=True) around the same
+        # encoder kernels (the round-1 driver; kept as the A/B reference of the fused path).
+        self.fused = bool(fused)
+        self._adam = None
         self.c_criterion = torch.nn.CrossEntropyLoss()          # main.py:16
         self.d_criterion = torch.nn.BCEWithLogitsLoss()         # main.py:17
         self._plans = {}
@@ -132,6 +215,30 @@ class Trainer(object):
     def _signature(h, n_global):
         return (h.b, h.m, h.uniform_n, h.onehot, h.feat_dim, h.n_max, h.dense, h.has_isolated, h.same_tags,
                 h.max0_as_sum, n_global)
+
+    def adam_state(self, tensors):
+        """Flat Adam moments shared with `self.optimizer.state` (so `optimizer.state_dict()` checkpoints them and a
+        later `optimizer.step()` would continue from them): created on first use for exactly the parameters that
+        receive gradients, like torch.optim.Adam's lazy state initialisation."""
+        ids = tuple(id(p) for p in tensors)
+        if self._adam is not None and self._adam["ids"] == ids:
+            return self._adam
+        if self._adam is not None:
+            raise RuntimeError("the set of parameters receiving gradients changed between steps")
+        dev = tensors[0].device
+        offsets, total = [], 0
+        for p in tensors:
+            offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        st = {"ids": ids, "offsets": offsets, "exp_avg": torch.zeros(total, dtype=torch.float32, device=dev),
+              "exp_avg_sq": torch.zeros(total, dtype=torch.float32, device=dev),
+              "step": torch.zeros(2, dtype=torch.float32, device=dev)}
+        for p, off in zip(tensors, offsets):
+            n = p.numel()
+            self.optimizer.state[p] = {"step": st["step"][0], "exp_avg": st["exp_avg"][off:off + n].view_as(p),
+                                       "exp_avg_sq": st["exp_avg_sq"][off:off + n].view_as(p)}
+        self._adam = st
+        return st
 
     def set_lr(self, lr):
         """Change the learning rate of every parameter group in place (visible to the captured CUDA graph)."""

@@ -563,8 +563,12 @@ def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm, m
     d_logit = None
     if with_dgi:
         # discriminator.py:19-38 refactored: sc = <h, u_g> + b with u_g = W c_g (c = sigmoid(g_f), graphcnn.py:238-239)
-        c = torch.sigmoid(g_f)
-        u_mat = c @ disc_w[0].t()
+        # c = sigmoid(g_f) and u = c W^T in one launch (W = disc.f_k.weight[0], [L*F, L*F] row-major: u[b,i] = sum_j c[b,j] W[i,j])
+        lf = L * F
+        c = torch.empty(B, lf, dtype=torch.float32, device=dev)
+        u_mat = torch.empty(B, lf, dtype=torch.float32, device=dev)
+        w_d = disc_w[0]
+        _ops.small_gemm(g_f, (g_f.stride(0), 1), w_d, (1, w_d.stride(0)), u_mat, B, lf, lf, sigmoid_a_out=c)
         b_neg = neg_idx.shape[0]
         if comm.world > 1:
             # the negatives only ever read global rows [0, B_global) of n_f: rank 0 owns them
@@ -639,14 +643,20 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm, max_first
         d_bias, c_, o_ = zp.f64(1)
         from_f64.append((2, c_, o_, 1, False))
         _ops.dgi_score_bwd(sv.h_all, dd, sv.neg_table, sv.my_neg, bs.node_off, B, du, s2, d_bias)
-        # [B, L*F]-sized glue: u = c W^T, c = sigmoid(g_f)
-        grads[1] = (du.t() @ sv.c).unsqueeze(0)
-        dc = du @ disc_w[0]
-        dgs = dc * sv.c * (1.0 - sv.c)
-        d_pooled = dgs if d_pooled is None else d_pooled + dgs
+        # [B, L*F]-sized glue of u = c W^T, c = sigmoid(g_f): dW[i,j] = sum_b du[b,i] c[b,j];
+        # d g_f = dg_f (heads) + (du W) c (1 - c); gradient reaching the shuffled rows n_f[perm[g]]
+        lf = L * F
+        w_d = disc_w[0]
+        d_w = torch.empty(1, lf, lf, dtype=torch.float32, device=dev)
+        _ops.small_gemm(du, (1, du.stride(0)), sv.c, (sv.c.stride(0), 1), d_w[0], lf, lf, B)
+        grads[1] = d_w
+        dgs = torch.empty(B, lf, dtype=torch.float32, device=dev)
+        dg_heads = d_pooled.contiguous() if d_pooled is not None else None
+        _ops.small_gemm(du, (du.stride(0), 1), w_d, (w_d.stride(0), 1), dgs, B, lf, lf, dsig_s=sv.c, dsig_add=dg_heads)
+        d_pooled = dgs
         n_neg = sv.neg_idx.shape[0]
-        d_neg = torch.zeros(n_neg, L * F, dtype=torch.float32, device=dev)
-        d_neg.index_add_(0, sv.my_neg.long(), s2.unsqueeze(1) * sv.u_mat)
+        d_neg = torch.empty(n_neg, lf, dtype=torch.float32, device=dev)
+        _ops.dgi_neg_grad(sv.my_neg, s2, sv.u_mat, d_neg)
         if comm.world > 1:
             comm.reduce_sum(d_neg, 0)
             if comm.rank != 0:

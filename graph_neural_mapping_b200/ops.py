@@ -501,3 +501,70 @@ def rowdot_score(h, u, rows_per_graph, bias, s_bias, out):
                                           _ptr(bias, torch.float32), _ptr(s_bias, torch.float32),
                                           _ptr(out, torch.float32), _stream(out)), "gnm_rowdot_score")
     return out
+
+
+# ---- the [B, L*F]-sized remainder of a training step (gnm_train.cu) ---------------------------
+
+def _ptr_array(tensors, dtype=torch.float32):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+            raise RuntimeError("expected contiguous CUDA %s tensors" % dtype)
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def heads_ce(g_f, weights, biases, mask, labels, inv_count, c_logit, loss_acc, d_gf, d_weights, d_biases, workspace, counter):
+    """graphcnn.py:228-231 + nn.CrossEntropyLoss forward and backward (see include/gnm.h: gnm_heads_ce)."""
+    gp, ldg = _mat(g_f)
+    dp, ldd = _mat(d_gf)
+    n_layers, n_classes, n_feat = len(weights), int(weights[0].shape[0]), int(weights[0].shape[1])
+    _libmod.check(_lib().gnm_heads_ce(gp, ldg, int(g_f.shape[0]), n_layers, n_feat, n_classes, _ptr_array(weights),
+                                      _ptr_array(biases), _ptr(mask, torch.float32), _ptr(labels, torch.int64),
+                                      float(inv_count), _ptr(c_logit, torch.float32), _ptr(loss_acc, torch.float64), dp, ldd,
+                                      _ptr_array(d_weights), _ptr_array(d_biases), _ptr(workspace, torch.float32),
+                                      int(workspace.numel()), _ptr(counter, torch.int32), _stream(g_f)), "gnm_heads_ce")
+
+
+def heads_ce_workspace(n_graphs, n_layers, n_feat, n_classes):
+    return int(_lib().gnm_heads_ce_workspace(int(n_graphs), int(n_layers), int(n_feat), int(n_classes)))
+
+
+def bce_logits(logits, n_pos, grad_scale, loss_scale, loss_acc, d_logits):
+    _libmod.check(_lib().gnm_bce_logits(_ptr(logits, torch.float32), int(logits.numel()), int(n_pos), float(grad_scale),
+                                        float(loss_scale), _ptr(loss_acc, torch.float64), _ptr(d_logits, torch.float32),
+                                        _stream(logits)), "gnm_bce_logits")
+
+
+def small_gemm(a, a_strides, b, b_strides, c, m, n, k, sigmoid_a_out=None, dsig_s=None, dsig_add=None):
+    """C[m,n] = sum_k A(m,k) B(k,n) with element strides (sam, sak) / (sbk, sbn); see include/gnm.h: gnm_small_gemm."""
+    cp, ldc = _mat(c)
+    ao, ldao = _mat(sigmoid_a_out)
+    sp, lds = _mat(dsig_s)
+    dp, ldadd = _mat(dsig_add)
+    _libmod.check(_lib().gnm_small_gemm(_ptr(a, torch.float32), int(a_strides[0]), int(a_strides[1]), _ptr(b, torch.float32),
+                                        int(b_strides[0]), int(b_strides[1]), cp, ldc, int(m), int(n), int(k),
+                                        1 if sigmoid_a_out is not None else 0, ao, ldao, sp, lds, dp, ldadd, _stream(c)),
+                  "gnm_small_gemm")
+    return c
+
+
+def dgi_neg_grad(neg_idx, s2, u, d_neg):
+    up, ldu = _mat(u)
+    dp, ldn = _mat(d_neg)
+    _libmod.check(_lib().gnm_dgi_neg_grad(_ptr(neg_idx, torch.int32), _ptr(s2, torch.float32), up, ldu, int(u.shape[0]),
+                                          int(u.shape[1]), dp, ldn, int(d_neg.shape[0]), _stream(d_neg)), "gnm_dgi_neg_grad")
+    return d_neg
+
+
+def adam_step(params, grads, state_off, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, weight_decay, grad_scale,
+              loss_terms=None, loss_out=None):
+    """torch.optim.Adam over a table of tensors in one launch (include/gnm.h: gnm_adam_step)."""
+    n = len(params)
+    numel = (ctypes.c_int32 * n)(*[int(p.numel()) for p in params])
+    offs = (ctypes.c_int32 * n)(*[int(o) for o in state_off])
+    _libmod.check(_lib().gnm_adam_step(_ptr_array(params), _ptr_array(grads), numel, offs, n, _ptr(exp_avg, torch.float32),
+                                       _ptr(exp_avg_sq, torch.float32), _ptr(step, torch.float32), _ptr(lr, torch.float32),
+                                       float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale),
+                                       _ptr(loss_terms, torch.float64), int(loss_terms.numel()) if loss_terms is not None else 0,
+                                       _ptr(loss_out, torch.float32), _stream(exp_avg)), "gnm_adam_step")

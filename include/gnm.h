@@ -33,7 +33,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 14
+#define GNM_ABI_VERSION 15
 
 typedef void* gnm_stream_t;
 
@@ -314,6 +314,50 @@ int gnm_aggregate_max(const int32_t* rowptr, const int32_t* colidx, int n_rows, 
 int gnm_aggregate_max_bwd(const int32_t* rowptr, const int32_t* colidx, int n_rows, const float* d_out, int64_t ld_dout,
                           int n_feat, const int32_t* argmax, const unsigned long long* col_min, const float* eps,
                           float* d_h, int64_t ld_dh, gnm_stream_t stream);
+
+/* ---- the [B, L*F]-sized remainder of a training step (gnm_train.cu) ---------------------------
+ * What main.py:31-41 does around the encoder, as a handful of launches instead of ~110 torch kernels.
+ *
+ * gnm_heads_ce: graphcnn.py:228-231 + main.py:35 forward AND backward in one pass over g_f [B, L*F]:
+ *   c_logit[b,c] = sum_l mask[l,b,c] * (<weights[l][c,:], g_f[b, l*F:(l+1)*F]> + biases[l][c])
+ *   (mask nullable [L,B,C] = F.dropout's keep mask scaled by 1/(1-p), drawn by the caller from torch's generator),
+ *   *loss_acc += inv_count * sum_b CrossEntropy(c_logit[b], labels[b]) (nn.CrossEntropyLoss, mean: inv_count = 1/B),
+ *   d_gf[b, :] = d loss / d g_f, d_weights[l] / d_biases[l] = the head gradients (written, deterministic).
+ *   weights / biases / d_weights / d_biases: HOST arrays of n_layers device pointers. workspace: at least
+ *   gnm_heads_ce_workspace(...) floats; counter: one zero-initialised uint32 (left zero). L <= 16, C <= 8.
+ * gnm_bce_logits: nn.BCEWithLogitsLoss (main.py:17,34) against the targets of main.py:32 (first n_pos rows 1, rest 0):
+ *   *loss_acc += loss_scale * sum_i bce(logits[i], y_i); d_logits[i] (nullable) = grad_scale * (sigmoid(logits[i]) - y_i).
+ * gnm_small_gemm: C[m,n] = sum_k A(m,k) B(k,n), A(m,k) = a[m*sam + k*sak], B(k,n) = b[k*sbk + n*sbn] (any of NT/TN/NN
+ *   without copies) for the Discriminator glue on [B, L*F] operands (graphcnn.py:238-239, discriminator.py:28-29
+ *   refactored as u_g = W c_g): sigmoid_a != 0 applies sigmoid to A on load and writes it to a_out (c = sigmoid(g_f),
+ *   u = c W^T in one launch); dsig_s != NULL makes the epilogue C = dsig_add (nullable) + acc * s * (1 - s)
+ *   (d g_f = d_heads + (du W) c (1 - c)).
+ * gnm_dgi_neg_grad: d_neg[j,:] = sum_{g: neg_idx[g] == j} s2[g] * u[g,:], j < n_neg - the gradient reaching the
+ *   "shuffled" rows n_f[perm[g]] of graphcnn.py:241-242; rows nobody names are zero. Deterministic.
+ * gnm_adam_step: torch.optim.Adam (main.py:39-41,136; defaults: no amsgrad) over a table of n_tensors tensors in one
+ *   launch: params / grads HOST arrays of device pointers, numel / state_off HOST int arrays (state_off = offset of the
+ *   tensor's moments in the flat exp_avg / exp_avg_sq buffers). step: DEVICE float[2], step[0] = steps done so far
+ *   (advanced by the call); lr: DEVICE float[1] (schedulers write it in place: visible to a captured CUDA graph).
+ *   Same operation order as torch's capturable implementation; grads are multiplied by grad_scale first (1/world
+ *   after a summed all-reduce). loss_out (nullable, DEVICE float[1]) = sum of the n_loss_terms doubles - the step's
+ *   loss terms accumulated by gnm_heads_ce / gnm_bce_logits - so that no extra launch forms the loss. */
+int gnm_heads_ce_workspace(int n_graphs, int n_layers, int n_feat, int n_classes);
+int gnm_heads_ce(const float* g_f, int64_t ldg, int n_graphs, int n_layers, int n_feat, int n_classes,
+                 const float* const* weights, const float* const* biases, const float* mask, const int64_t* labels,
+                 float inv_count, float* c_logit, double* loss_acc, float* d_gf, int64_t ldd, float* const* d_weights,
+                 float* const* d_biases, float* workspace, int64_t workspace_floats, unsigned int* counter,
+                 gnm_stream_t stream);
+int gnm_bce_logits(const float* logits, int64_t n, int64_t n_pos, float grad_scale, double loss_scale, double* loss_acc,
+                   float* d_logits, gnm_stream_t stream);
+int gnm_small_gemm(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbk, int64_t sbn, float* c,
+                   int64_t ldc, int m, int n, int k, int sigmoid_a, float* a_out, int64_t lda_out, const float* dsig_s,
+                   int64_t lds, const float* dsig_add, int64_t ldadd, gnm_stream_t stream);
+int gnm_dgi_neg_grad(const int32_t* neg_idx, const float* s2, const float* u, int64_t ldu, int n_graphs, int width,
+                     float* d_neg, int64_t ldn, int n_neg, gnm_stream_t stream);
+int gnm_adam_step(float* const* params, const float* const* grads, const int32_t* numel, const int32_t* state_off,
+                  int n_tensors, float* exp_avg, float* exp_avg_sq, float* step, const float* lr, float beta1, float beta2,
+                  float eps, float weight_decay, float grad_scale, const double* loss_terms, int n_loss_terms,
+                  float* loss_out, gnm_stream_t stream);
 
 /* ---- data parallel: synchronised BatchNorm sums over NVLink peer memory ------------------------------
  * The reference is single-process; a global-batch BatchNorm needs the per-channel sums of all ranks before the next

@@ -399,3 +399,27 @@ def rowdot_score(h, u, rows_per_graph, bias, s_bias, out):
         v = v + s_bias.view(-1)
     out.copy_(v)
     return out
+
+
+# ---- the [B, L*F]-sized remainder of a training step (contract of gnm_train.cu) ---------------
+
+def small_gemm(a, a_strides, b, b_strides, c, m, n, k, sigmoid_a_out=None, dsig_s=None, dsig_add=None):
+    am = torch.as_strided(a, (m, k), (int(a_strides[0]), int(a_strides[1]))).double()
+    bm = torch.as_strided(b, (k, n), (int(b_strides[0]), int(b_strides[1]))).double()
+    if sigmoid_a_out is not None:
+        am = torch.sigmoid(am)
+        sigmoid_a_out.copy_(am.to(sigmoid_a_out.dtype))
+    out = am @ bm
+    if dsig_s is not None:
+        s = dsig_s.double()
+        out = out * s * (1.0 - s)
+        if dsig_add is not None:
+            out = out + dsig_add.double()
+    c.copy_(out.to(c.dtype))
+    return c
+
+
+def dgi_neg_grad(neg_idx, s2, u, d_neg):
+    d_neg.zero_()
+    d_neg.index_add_(0, neg_idx.long(), s2.unsqueeze(1) * u)
+    return d_neg

@@ -489,3 +489,41 @@ def test_graph_store_stays_within_its_byte_budget():
         assert torch.equal(got, want)
         assert store.bytes <= 2 * store.max_bytes
     assert store.evictions >= 2 and len(store) <= 2 * len(graphs)
+
+
+@pytest.mark.parametrize("name", ["mid_eps_sum_h64", "tiny_noeps_avg", "schaefer400_b16_noeps"])
+def test_trainer_on_libgnm_step_kernels_matches_trainer_on_torch_ops(name):
+    """A/B of the two Trainer paths: heads / dropout-free CE / BCE / Adam on libgnm's own kernels with the backward called
+    directly (fused=True, no torch autograd in the step) against torch's loss functions, autograd and
+    torch.optim.Adam(capturable=True) around the same encoder kernels (fused=False): per-step losses and the state
+    after six steps (eager, eager, capture, three replays)."""
+    from graph_neural_mapping_b200.driver import Trainer
+    g = Golden(name)
+    graphs = g.graphs()
+    runs = []
+    for fused in (False, True):
+        m = build_model(g)
+        m.final_dropout = 0.0
+        m.train()
+        tr = Trainer(m, lr=0.005, beta=g.cfg["beta"], fused=fused)
+        losses = []
+        for sd in range(6):
+            np.random.seed(300 + sd)
+            losses.append(float(tr.step(graphs)))
+        tr.finish()
+        runs.append((m, tr, np.array(losses)))
+    assert_close(runs[1][2], runs[0][2], 1e-4, "per-step losses, libgnm step kernels vs torch ops")
+    sd0, sd1 = runs[0][0].state_dict(), runs[1][0].state_dict()
+    for k in sd0:
+        if "num_batches" in k:
+            assert int(sd0[k]) == int(sd1[k]) == 6, k
+        elif (k.startswith("mlps") and ".linear" in k and k.endswith("bias")) or k.endswith("running_mean"):
+            continue          # zero-gradient biases: Adam random-walks on rounding noise (see the test above)
+        else:
+            assert_close(sd1[k], sd0[k], 3e-3, "after 6 steps: " + k)
+    # the flat moments are the optimizer's state: a checkpoint taken from trainer.optimizer holds them
+    tr = runs[1][1]
+    osd = tr.optimizer.state_dict()
+    assert len(osd["state"]) == len(tr._adam["offsets"]) and float(tr._adam["step"][0]) == 6.0
+    st0 = next(iter(tr.optimizer.state.values()))
+    assert float(st0["step"]) == 6.0 and float(st0["exp_avg_sq"].abs().sum()) > 0.0
