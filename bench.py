@@ -36,6 +36,7 @@ AGG_DRAM_TRAFFIC_BYTES = 189.0e6
 METRIC = "gin_train_graphs_per_sec_400roi"
 UNIT = "graphs/s"
 N_ROIS, HIDDEN, LAYERS, MLP_LAYERS, BETA, LR = 400, 64, 5, 2, 0.05, 0.005
+EDGES_PER_GRAPH = 47600
 
 
 def parse():
@@ -44,7 +45,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="graphs per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="graphs per GPU per step (default 1024; 128 for --config c4)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4"],
+                    help="c2 = BASELINE configs[1]/[2] (Schaefer-400, hidden 64: the metric's workload); c4 = configs[3] "
+                         "(Schaefer-1000 top-30%% graphs, hidden 128; 128 graphs per GPU = a global batch of 1024 on 8 GPUs)")
+    ap.add_argument("--saliency-graphs", type=int, default=12500,
+                    help="--saliency: graphs per GPU (BASELINE configs[4]: 100k graphs sharded over 8 GPUs = 12,500 each)")
     ap.add_argument("--learn-eps", action="store_true", help="graphcnn.py next_layer_eps path (default: main.py's default, False)")
     ap.add_argument("--cpu-batch", type=int, default=32, help="graphs per step of the CPU baseline sample (configs[0])")
     ap.add_argument("--driver", default="fused", choices=["fused", "loop"],
@@ -61,14 +67,24 @@ def parse():
                          "times (declared in config) so that clocks / throttling are sampled over >= this long")
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling block (global batch fixed)")
     ap.add_argument("--no-dp-parity", action="store_true", help="N>1: skip the data-parallel parity step before timing")
-    return ap.parse_args()
+    ap.add_argument("--no-breakdown", action="store_true",
+                    help="skip the eager per-kernel timing pass (no `roofline` / `kernel_breakdown`): for ncu launch lists "
+                         "of the captured step")
+    args = ap.parse_args()
+    global N_ROIS, HIDDEN, EDGES_PER_GRAPH
+    if args.config == "c4":
+        N_ROIS, HIDDEN = 1000, 128
+    EDGES_PER_GRAPH = int(0.3 * N_ROIS * N_ROIS) - N_ROIS
+    if args.batch is None:
+        args.batch = 128 if args.config == "c4" else 1024
+    return args
 
 
 def workload_config(args, world):
-    return {"workload": "GIN 5-layer hidden 64 + DGI, synthetic Schaefer-400 top-30%% FC graphs, "
-                        "batch %d graphs/GPU, sum/sum pooling, learn_eps=%s, Adam" % (args.batch, args.learn_eps),
+    return {"workload": "GIN 5-layer hidden %d + DGI, synthetic Schaefer-%d top-30%% FC graphs, "
+                        "batch %d graphs/GPU, sum/sum pooling, learn_eps=%s, Adam" % (HIDDEN, N_ROIS, args.batch, args.learn_eps),
             "graphs_per_gpu": args.batch, "global_batch": args.batch * world, "n_rois": N_ROIS,
-            "edges_per_graph": 47600, "hidden": HIDDEN, "layers": LAYERS, "parallelism": "dp%d" % world,
+            "edges_per_graph": EDGES_PER_GRAPH, "hidden": HIDDEN, "layers": LAYERS, "parallelism": "dp%d" % world,
             "l2_policy": "inputs_larger_than_l2 (per-step working set ~3 GB >> 126 MB L2)"}
 
 
@@ -414,19 +430,26 @@ def run_b200(args):
     # ---- per-kernel times, live, on the launching stream ------------------------------------
     graphs_on = model.use_cuda_graphs
     model.use_cuda_graphs = False            # per-kernel events need the eager (kernel-by-kernel) path
-    step_loop()
-    with OpTimer(ops) as timer:
-        for _ in range(2):
-            step_loop()
-        table = timer.table()
+    table = {}
+    fam0 = ops.launch_counts()
+    if not args.no_breakdown:
+        step_loop()
+        with OpTimer(ops) as timer:
+            for _ in range(2):
+                step_loop()
+            table = timer.table()
     model.use_cuda_graphs = graphs_on
     n_prof = 2
     bs = model._structure(pool)
     m, nnz = bs.n_rows, bs.nnz
     agg_key = "aggregate_dense[F=%d]" % HIDDEN
-    agg_kernel = "aggregate_tc_kernel (tcgen05/TMEM block SpMM from bitmaps, bf16x3 exact split, F=64)"
+    fam = {k: v - fam0[k] for k, v in ops.launch_counts().items()}          # which kernel family really ran
+    if fam["aggregate_tc"] > 0:
+        agg_kernel = "aggregate_tc_kernel (tcgen05/TMEM block SpMM from bitmaps, bf16x3 exact split, F=%d)" % HIDDEN
+    else:
+        agg_kernel = "aggregate_dense_kernel (mma.sync block SpMM from bitmaps, bf16x3 exact split, F=%d)" % HIDDEN
     if agg_key not in table:
-        agg_key, agg_kernel = "aggregate[F=%d]" % HIDDEN, "aggregate_kernel<4,16> (CSR warp-per-row SpMM, F=64)"
+        agg_key, agg_kernel = "aggregate[F=%d]" % HIDDEN, "aggregate_kernel (CSR warp-per-row SpMM, F=%d)" % HIDDEN
     agg_bytes = 4.0 * nnz + 4.0 * (m + 1) + 2 * 4.0 * m * HIDDEN          # AGG(l>=1)
     peaks = {}
     try:
@@ -443,7 +466,7 @@ def run_b200(args):
         step_ms = sum(v[1] for v in table.values()) / n_prof
         roof = {"bound": "hbm", "kernel": agg_kernel, "achieved": ach,
                 "peak": peak_gbs, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak_gbs,
-                "traffic": AGG_DRAM_TRAFFIC_BYTES if (B == 1024 and "dense" in agg_key) else None,
+                "traffic": AGG_DRAM_TRAFFIC_BYTES if (B == 1024 and N_ROIS == 400 and fam["aggregate_tc"] > 0) else None,
                 "algorithmic_bytes_per_launch": agg_bytes, "avg_launch_us": avg_s * 1e6, "launches_per_step": cnt / n_prof,
                 "share_of_kernel_time": (tot_ms / n_prof) / step_ms}
     # algorithmic bytes per launch of the ops whose formula does not depend on the call site
@@ -505,7 +528,7 @@ def run_b200(args):
         cpu_baseline, _ = cpu_reference_run(args, 3, 1, graphs=pool)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": METRIC if N_ROIS == 400 else "gin_train_graphs_per_sec_%droi" % N_ROIS, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, world), cuda_graphs=bool(model.use_cuda_graphs), inner_repeats=inner,
@@ -612,38 +635,111 @@ def dp_parity_check(args, comm, dev, per_rank=16):
 
 
 def run_saliency(args):
-    """BASELINE configs[4]: saliency maps (eval-mode forward + backward to the one-hot input) over this rank's
-    share of graphs, batched (exact). One step = one batched call writing a [B*N, N] fp32 map."""
-    from graph_neural_mapping_b200 import dist as gdist, synth
+    """BASELINE configs[4]: gradient-saliency extraction (graphcnn.py:254-299: eval-mode forward + backward to the one-hot
+    input) over this rank's share of the 100k subject graphs - 12,500 per GPU, generated on the device with their edge
+    lists left there (synth.make_graphs_bulk(edges_on_device=True)), ingested into the graph store without a host trip,
+    processed in exact batches (SURVEY A10). One step = one batched call writing a [B*N, N] fp32 map to device memory;
+    `value` counts graphs/s over all ranks (pure sharding: no collective). `e2e` = the same maps streamed to pinned host
+    memory through driver.stream_saliency (asynchronous D2H, double buffer) - what main.py:60-68,170-172 needs."""
+    from graph_neural_mapping_b200 import dist as gdist, driver, ops, synth
     from graph_neural_mapping_b200.models import GIN_InfoMaxReg
     comm, local_rank = gdist.init_from_env()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    b = args.saliency_batch
+    b, n_graphs = args.saliency_batch, max(args.saliency_graphs, args.saliency_batch)
     torch.manual_seed(0)
-    pool = synth.make_graphs_bulk(b, N_ROIS, 30, 256, seed0=1000 * comm.rank, device=dev)
     model = GIN_InfoMaxReg(LAYERS, MLP_LAYERS, N_ROIS, HIDDEN, 2, 0.5, args.learn_eps, "sum", "sum", dev).to(dev)
-    for _ in range(max(args.warmup, 3)):
-        model.compute_saliency_batched(pool, 1)
+    store = model._graph_store()
+    t_gen = time.perf_counter()
+    pool = []
+    for c0 in range(0, n_graphs, 1024):                      # generate -> ingest -> drop the int64 edge lists, chunk-wise
+        chunk = synth.make_graphs_bulk(min(1024, n_graphs - c0), N_ROIS, 30, 256, seed0=100000 * comm.rank + c0, device=dev,
+                                       edges_on_device=True)
+        store.ensure(chunk)
+        synth.release_edges(chunk)
+        pool.extend(chunk)
     torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_gen = time.perf_counter() - t_gen
+    batches = [pool[i:i + b] for i in range(0, len(pool) - b + 1, b)]
+    state = {"i": 0}
+
+    def step():
+        s = model.compute_saliency_batched(batches[state["i"] % len(batches)], 1)
+        state["i"] += 1
+        return s
+
+    for _ in range(max(args.warmup, 3)):
+        sal = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    inner = max(1, int(np.ceil(args.min_seconds * 1e3 / (e0.elapsed_time(e1) / 3.0 * args.steps))))
     if comm.world > 1:
         torch.distributed.barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        sal = model.compute_saliency_batched(pool, 1)
-    ev1.record()
+    sampler = ClockSampler(local_rank) if comm.rank == 0 else None
+    k0 = ops.kernels_launched()
+    e0.record()
+    for _ in range(args.steps * inner):
+        sal = step()
+    e1.record()
     torch.cuda.synchronize()
-    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    launches = ops.kernels_launched() - k0
+    clocks = sampler.stop() if sampler else None
+    if ops.aggregate_tc_status():
+        raise RuntimeError("a tcgen05 kernel hit its bounded barrier wait: the numbers are invalid")
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if comm.world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = float(t.item()) / (args.steps * inner)
+    # e2e: maps land in pinned host memory (the sink touches every batch once, like a file writer would)
+    seen = {"bytes": 0}
+
+    def sink(first, arr):
+        seen["bytes"] += arr.nbytes
+    n_e2e = min(len(pool), max(4 * b, (args.steps * inner * b) // 4 // b * b))
+    driver.stream_saliency(model, pool[:2 * b], 1, sink, batch=b)          # warm the pinned buffers
+    torch.cuda.synchronize()
+    seen["bytes"] = 0
+    t0 = time.perf_counter()
+    driver.stream_saliency(model, pool[:n_e2e], 1, sink, batch=b)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if comm.world > 1:
+        torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
+    out_bytes = float(sal.numel() * 4)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_gbs = peaks.get("hbm_gbs", 6650.0)
     if comm.rank == 0:
-        print(json.dumps({"metric": "gin_saliency_graphs_per_sec_400roi", "value": b * comm.world * args.steps / (ms / 1e3),
-                          "unit": UNIT, "n_gpus": comm.world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
-                          "data": "synthetic", "config": {"workload": "gradient saliency, %d graphs per call, N=400, "
-                                                          "5-layer hidden 64" % b, "bytes_written_per_step": int(sal.numel() * 4)}}))
+        print(json.dumps({
+            "metric": "gin_saliency_graphs_per_sec_%droi" % N_ROIS, "value": b * comm.world / (ms / 1e3), "unit": UNIT,
+            "n_gpus": comm.world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "gradient saliency (graphcnn.py:254-299), %d graphs per GPU of BASELINE configs[4] (100k "
+                                   "graphs over 8 GPUs), %d graphs per batched call, N=%d, 5-layer hidden %d"
+                                   % (len(pool), b, N_ROIS, HIDDEN),
+                       "graphs_per_gpu": len(pool), "graphs_per_call": b, "inner_repeats": inner,
+                       "steps_timed": args.steps * inner, "bytes_written_per_step": int(out_bytes),
+                       "generate_and_ingest_s": t_gen, "parallelism": "shard%d (no collective)" % comm.world,
+                       "l2_policy": "inputs_larger_than_l2 (each call writes %d MB and cycles through %d batches)"
+                                    % (int(out_bytes / 1e6), len(batches))},
+            "clocks": clocks, "gpu_launches": launches, "gpu_launches_per_step": launches / float(args.steps * inner),
+            "e2e": {"value": n_e2e * comm.world / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": 41 * b,
+                    "d2h_bytes_per_step": int(seen["bytes"] / max(1, n_e2e // b)),
+                    "what": "driver.stream_saliency over %d graphs: every batch's [b, N, N] map copied to pinned host "
+                            "memory (asynchronous, double-buffered) and handed to a sink" % n_e2e},
+            "roofline": {"bound": "hbm", "kernel": "whole saliency call (output-write bound: 4*N*N bytes per graph)",
+                         "achieved": out_bytes / (ms / 1e3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": out_bytes / (ms / 1e3) / 1e9 / peak_gbs, "traffic": None,
+                         "algorithmic_bytes_per_launch": out_bytes}}))
     if comm.world > 1:
         gdist.shutdown()
 

@@ -347,25 +347,80 @@ def latent_space(model, graphs, batch=256):
     return np.concatenate(feats, axis=0), labels
 
 
+def stream_saliency(model, graphs, cls, sink, batch=64):
+    """Batched `compute_saliency` (exact) streamed to `sink(first_graph, array)`: the maps of one batch
+    ([b, N, D] float32 numpy view of a PINNED host buffer, valid until the call after next) are handed over while the
+    device already computes the next batch - two pinned buffers, asynchronous D2H, one event each. Nothing accumulates:
+    100k graphs x 640 KB never sit in host RAM unless the sink keeps them."""
+    dev = model.eps.device
+    bufs, events = [None, None], [None, None]
+    pending = None                          # (slot, first graph index, shape) of the batch whose copy is in flight
+    i0 = 0
+
+    def flush(p):
+        slot, first, shape = p
+        if events[slot] is not None:
+            events[slot].synchronize()
+        n_el = int(np.prod(shape))
+        sink(first, bufs[slot][:n_el].numpy().reshape(shape))
+
+    for k, chunk in enumerate(_batches(graphs, batch)):
+        s = model.compute_saliency_batched(chunk, cls).detach()
+        n = len(chunk[0].g)
+        shape = (len(chunk), n, int(s.shape[1]))
+        slot = k & 1
+        if bufs[slot] is None or bufs[slot].numel() < s.numel():
+            bufs[slot] = torch.empty(s.numel(), dtype=torch.float32, pin_memory=(dev.type == "cuda"))
+            events[slot] = torch.cuda.Event() if dev.type == "cuda" else None
+        bufs[slot][:s.numel()].copy_(s.reshape(-1), non_blocking=True)
+        if events[slot] is not None:
+            events[slot].record()
+        if pending is not None:
+            flush(pending)                  # the previous batch: its copy overlapped this batch's kernels
+        pending = (slot, i0, shape)
+        i0 += len(chunk)
+    if pending is not None:
+        flush(pending)
+    return i0
+
+
 def saliency_maps(model, graphs, cls, batch=64):
     """`get_saliency_map` (main.py:60-68): float32 [G, N, D] - one `compute_saliency` map per graph, computed in
     batches (exact: `compute_saliency_batched`). All graphs must have the same number of nodes (np.stack)."""
-    maps = []
-    for chunk in _batches(graphs, batch):
-        s = model.compute_saliency_batched(chunk, cls).detach()
-        n = len(chunk[0].g)
-        maps.append(s.reshape(len(chunk), n, s.shape[1]).cpu().numpy())
-    return np.concatenate(maps, axis=0)
+    out = {}
+
+    def sink(first, arr):
+        if "a" not in out:
+            out["a"] = np.empty((len(graphs),) + arr.shape[1:], dtype=np.float32)
+        out["a"][first:first + arr.shape[0]] = arr
+    stream_saliency(model, graphs, cls, sink, batch)
+    return out.get("a", np.zeros((0, 0, 0), dtype=np.float32))
+
+
+def saliency_maps_to_npy(model, graphs, cls, path, batch=64):
+    """`np.save(path, get_saliency_map(model, graphs, cls))` (main.py:168-172) without holding the array: the `.npy`
+    file is created as a memory map of its final shape [G, N, D] and filled batch by batch from the pinned double
+    buffer. Same bytes on disk as the reference's np.save (format 1.0/2.0 header + C-order float32)."""
+    n, d = len(graphs[0].g), int(graphs[0].node_features.shape[1])
+    mm = np.lib.format.open_memmap(path, mode="w+", dtype=np.float32, shape=(len(graphs), n, d))
+
+    def sink(first, arr):
+        mm[first:first + arr.shape[0]] = arr
+    stream_saliency(model, graphs, cls, sink, batch)
+    mm.flush()
+    del mm
+    return path
 
 
 def save_results(model, graphs, out_dir, batch=64):
     """The arrays main.py:170-172 leaves for the evaluate/ scripts, same file names and layouts: latent_space.npy,
-    labels.npy, saliency_female.npy (class 0), saliency_male.npy (class 1)."""
+    labels.npy, saliency_female.npy (class 0), saliency_male.npy (class 1). The saliency files are streamed
+    (saliency_maps_to_npy): host memory stays at two batches however many graphs there are."""
     import os
     os.makedirs(out_dir, exist_ok=True)
     lat, labels = latent_space(model, graphs, batch=max(batch, 1))
     np.save(os.path.join(out_dir, "latent_space.npy"), lat)
     np.save(os.path.join(out_dir, "labels.npy"), labels)
-    np.save(os.path.join(out_dir, "saliency_female.npy"), saliency_maps(model, graphs, 0, batch))
-    np.save(os.path.join(out_dir, "saliency_male.npy"), saliency_maps(model, graphs, 1, batch))
+    saliency_maps_to_npy(model, graphs, 0, os.path.join(out_dir, "saliency_female.npy"), batch)
+    saliency_maps_to_npy(model, graphs, 1, os.path.join(out_dir, "saliency_male.npy"), batch)
     return out_dir

@@ -137,6 +137,9 @@ class GraphStore(object):
             self.clear()
             self.evictions += 1
             return self.ensure(graphs)
+        if any(getattr(g, "_edges_released", False) for g in new):
+            raise RuntimeError("a graph whose edge list was released (synth.release_edges) is not in the store any more "
+                               "(evicted: raise GraphStore.max_bytes) - it cannot be rebuilt")
         dev = self.device
         counts = [len(g.g) for g in new]
         ems = []
@@ -154,13 +157,17 @@ class GraphStore(object):
         # stage the edge lists once in pinned memory (no torch.cat temporary, no pageable bounce buffer) and ship
         # them with one asynchronous copy
         e_total = int(edge_off[-1])
-        edges = self._staging(e_total)
-        for i, em in enumerate(ems):
-            edges[:, int(edge_off[i]):int(edge_off[i + 1])].copy_(em)
-        edges_d = edges.to(dev, non_blocking=True) if dev.type == "cuda" else edges.clone()
+        if dev.type == "cuda" and ems and all(e.is_cuda and e.device == dev for e in ems):
+            # edge lists that already live on the device (synth.make_graphs_bulk(edges_on_device=True)): no host trip
+            edges = edges_d = torch.cat(ems, 1) if len(ems) > 1 else ems[0].contiguous()
+        else:
+            edges = self._staging(e_total)
+            for i, em in enumerate(ems):
+                edges[:, int(edge_off[i]):int(edge_off[i + 1])].copy_(em)
+            edges_d = edges.to(dev, non_blocking=True) if dev.type == "cuda" else edges.clone()
         edge_off_d = torch.from_numpy(edge_off).to(dev)
         node_off_d = torch.from_numpy(node_off.astype(np.int32)).to(dev)
-        self.h2d_bytes += edges.numel() * 8 + edge_off.nbytes + node_off.nbytes // 2
+        self.h2d_bytes += (0 if edges is edges_d and dev.type == "cuda" else edges.numel() * 8) + edge_off.nbytes + node_off.nbytes // 2
         if dev.type == "cuda":
             self._stage_event = torch.cuda.Event()
             self._stage_event.record()

@@ -97,13 +97,19 @@ def make_graphs(n_graphs, n_rois=400, sparsity=30, n_time=1200, seed0=0, with_ne
 
 
 def make_graphs_bulk(n_graphs, n_rois=400, sparsity=30, n_time=256, seed0=0, device="cpu",
-                     share_features=True):
+                     share_features=True, edges_on_device=False):
     """Bulk generator for throughput runs (same recipe, batched in torch on `device`).
 
     Not bit-identical to `make_graph` (different RNG stream); use `make_graph` where a
     graph must be reproducible across machines. `share_features=True` makes every graph
     reference one identity matrix (as one subject list would after `util.py:114-116`
     only in value, here also in storage) to keep host memory bounded.
+
+    The whole recipe - time series, corrcoef, percentile threshold (`dataset.py:93-101`), upper-triangle edge
+    extraction and the mirrored edge list (`util.py:99-103`) - runs on `device`, vectorised over chunks of 64 graphs
+    (one `nonzero` per chunk, no per-graph work on the host). `edges_on_device=True` leaves each graph's `edge_mat` on
+    the device as well: `GraphStore.ensure` ingests such graphs without a host round trip (needed for
+    the 100k-graph saliency configuration, whose int64 edge lists alone are 76 GB).
     """
     gen = torch.Generator(device=device)
     gen.manual_seed(1234567 + seed0)
@@ -127,14 +133,30 @@ def make_graphs_bulk(n_graphs, n_rois=400, sparsity=30, n_time=256, seed0=0, dev
         # np.percentile's linear interpolation lies between order statistics k and k+1
         # (0-based, ascending); "fc > thr" therefore keeps exactly the entries ranked above k.
         thr = torch.kthvalue(flat, k + 1, dim=1).values
-        mask = fc > thr.view(c, 1, 1)
-        mask = torch.triu(mask, 1).cpu()
+        mask = torch.triu(fc > thr.view(c, 1, 1), 1)
+        # edge extraction on the device: one nonzero over the chunk (rows come out sorted by graph, then row-major
+        # within the graph = the upper-triangle order of edges_from_connectivity), split by per-graph counts
+        nz = torch.nonzero(mask)                                   # [E_chunk, 3]: graph, i, j
+        counts = torch.bincount(nz[:, 0], minlength=c)
+        offs = [0] + torch.cumsum(counts, 0).tolist()              # the only host synchronisation of the chunk
+        ij = nz[:, 1:].t().contiguous()                            # [2, E_chunk]
+        if not edges_on_device:
+            ij = ij.cpu()
         for b in range(c):
-            iu, ju = torch.nonzero(mask[b], as_tuple=True)
-            em = torch.stack([torch.cat([iu, ju]), torch.cat([ju, iu])], 0).contiguous()
+            half = ij[:, offs[b]:offs[b + 1]]
+            em = torch.cat([half, half.flip(0)], 1).contiguous()    # util.py:99-103: the same pairs, reversed, second
             feats = eye if share_features else eye.clone()
             graphs.append(SynthGraph(n_rois, (seed0 + c0 + b) % 2, em, feats))
     return graphs
+
+
+def release_edges(graphs):
+    """Drop the edge lists of graphs a GraphStore has already ingested (their device CSR / bitmap is what the kernels
+    read). The graph objects stay valid cache keys; a store that evicts them cannot rebuild them."""
+    empty = torch.zeros(2, 0, dtype=torch.int64)
+    for g in graphs:
+        g.edge_mat = empty
+        g._edges_released = True
 
 
 def to_networkx_route(graph):

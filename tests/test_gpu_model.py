@@ -512,7 +512,10 @@ def test_trainer_on_libgnm_step_kernels_matches_trainer_on_torch_ops(name):
             losses.append(float(tr.step(graphs)))
         tr.finish()
         runs.append((m, tr, np.array(losses)))
-    assert_close(runs[1][2], runs[0][2], 1e-4, "per-step losses, libgnm step kernels vs torch ops")
+    # step 1 starts from identical parameters: only the loss kernels differ. Later steps carry Adam's amplification of
+    # rounding noise on near-zero gradient entries (+-lr steps of random sign in either arm)
+    assert_close(runs[1][2][:1], runs[0][2][:1], 5e-6, "first-step loss, libgnm step kernels vs torch ops")
+    assert_close(runs[1][2], runs[0][2], 5e-4, "per-step losses, libgnm step kernels vs torch ops")
     sd0, sd1 = runs[0][0].state_dict(), runs[1][0].state_dict()
     for k in sd0:
         if "num_batches" in k:
@@ -527,3 +530,49 @@ def test_trainer_on_libgnm_step_kernels_matches_trainer_on_torch_ops(name):
     assert len(osd["state"]) == len(tr._adam["offsets"]) and float(tr._adam["step"][0]) == 6.0
     st0 = next(iter(tr.optimizer.state.values()))
     assert float(st0["step"]) == 6.0 and float(st0["exp_avg_sq"].abs().sum()) > 0.0
+
+
+def test_device_synth_and_streamed_result_files(tmp_path):
+    """SURVEY 8(f) N3 on the GPU: graphs generated on the device with their edge lists LEFT on the device are ingested
+    without a host trip and give the same model outputs as their host copies; `save_results` streams the saliency maps
+    into .npy files that equal main.py:60-82's one-graph-per-call loops."""
+    from graph_neural_mapping_b200 import driver
+    dev_graphs = synth.make_graphs_bulk(70, 48, 30, 96, seed0=5, device="cuda", edges_on_device=True)
+    host_graphs = synth.make_graphs_bulk(70, 48, 30, 96, seed0=5, device="cuda", edges_on_device=False)
+    assert dev_graphs[0].edge_mat.is_cuda and not host_graphs[0].edge_mat.is_cuda
+    for a, b in zip(dev_graphs, host_graphs):
+        assert torch.equal(a.edge_mat.cpu(), b.edge_mat)
+        e, half = b.edge_mat, b.edge_mat.shape[1] // 2
+        assert e.shape[1] == int(0.3 * 48 * 48) - 48 and torch.equal(e[:, half:], e[:, :half].flip(0))   # dataset.py:93-101
+    torch.manual_seed(1)
+    m1 = GIN_InfoMaxReg(3, 2, 48, 16, 2, 0.0, False, "sum", "sum", DEV).to(DEV).eval()
+    m2 = GIN_InfoMaxReg(3, 2, 48, 16, 2, 0.0, False, "sum", "sum", DEV).to(DEV).eval()
+    m2.load_state_dict(m1.state_dict())
+    h2d0 = m1._graph_store().h2d_bytes
+    np.random.seed(0)
+    c1, d1 = m1(dev_graphs)
+    assert m1._graph_store().h2d_bytes - h2d0 < 70 * 48 * 8 + 4096          # no edge list crossed PCIe
+    np.random.seed(0)
+    c2, d2 = m2(host_graphs)
+    assert torch.equal(c1, c2) and torch.equal(d1, d2)
+    synth.release_edges(dev_graphs)                                          # the store holds the CSR / bitmaps
+    np.random.seed(0)
+    c3, _ = m1(dev_graphs)
+    assert torch.equal(c3, c1)
+    m1.forget_graphs()
+    with pytest.raises(RuntimeError):
+        m1(dev_graphs)                                                       # released edge lists cannot be rebuilt
+    # result files (main.py:170-172), streamed
+    out = driver.save_results(m2, host_graphs, str(tmp_path / "res"), batch=16)
+    lat = np.load(out + "/latent_space.npy")
+    sal = {c: np.load(out + "/saliency_%s.npy" % n) for c, n in ((0, "female"), (1, "male"))}
+    labels = np.load(out + "/labels.npy")
+    assert lat.shape == (70, 48) and lat.dtype == np.float32 and labels.shape == (70, 1)
+    assert sal[0].shape == sal[1].shape == (70, 48, 48) and sal[0].dtype == np.float32
+    for gi in (0, 15, 16, 69):
+        for cls in (0, 1):
+            ref = m2.compute_saliency([host_graphs[gi]], cls)                # main.py:64
+            assert_close(sal[cls][gi], ref, 1e-6, "streamed saliency g%d c%d" % (gi, cls))
+        np.random.seed(3)
+        assert_close(lat[gi:gi + 1], m2([host_graphs[gi]], latent=True), 1e-5, "latent g%d" % gi)     # main.py:75-76
+    assert np.array_equal(labels[:, 0], np.array([g.label for g in host_graphs]))
