@@ -23,12 +23,66 @@ class Comm(object):
         self.world = int(world)
         self.rank = int(rank)
         self.p2p = None            # ops.P2PComm once setup_p2p() succeeded on every rank
+        self.regions = {}          # name -> ops.P2PRegion: peer-mapped bulk buffers (DGI rows, flat gradients)
+        self._token = None
 
     def p2p_for(self, t):
         """The peer-memory communicator if it can carry tensor `t` (float64, small, on the GPU), else None."""
         if self.p2p is not None and t.is_cuda and t.dtype == torch.float64 and t.numel() <= 256:
             return self.p2p
         return None
+
+    def region(self, name, nbytes):
+        """A peer-mapped region of at least `nbytes` on every rank (collective: every rank must ask for the same name
+        and size at the same point - the sizes derive from the global batch shape). Allocated (cudaMalloc + CUDA IPC
+        exchange over the process group) on first use or growth, never under CUDA-graph capture: the first, eager step
+        of a shape creates it. None when the ranks share no peer-memory communicator."""
+        if self.p2p is None:
+            return None
+        reg = self.regions.get(name)
+        if reg is not None and reg.nbytes >= nbytes:
+            return reg
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("peer region %r must be created before CUDA-graph capture (run one eager step first)" % name)
+        from . import ops
+        if reg is not None:
+            torch.cuda.synchronize()
+            td.barrier(group=self.group)
+            reg.close()
+        size = (int(nbytes) + (1 << 20) - 1) // (1 << 20) * (1 << 20)
+        reg = ops.P2PRegion(self.rank, self.world, self.p2p.device, size)
+        handles = [None] * self.world
+        td.all_gather_object(handles, reg.handle, group=self.group)
+        reg.connect(handles)
+        torch.cuda.synchronize()
+        td.barrier(group=self.group)
+        self.regions[name] = reg
+        return reg
+
+    def p2p_barrier(self):
+        """Every rank passes only after all ranks reached this point of their stream, and what they wrote before it
+        (to their own or to peer memory) is visible: one peer-memory all-reduce of a dummy value (gnm_p2p.cuh)."""
+        if self._token is None:
+            self._token = torch.zeros(1, dtype=torch.float64, device=self.p2p.device)
+        self.p2p.allreduce(self._token)
+
+    def all_reduce_mean_flat(self, flat):
+        """In-place mean over the ranks of a flat float32 vector (the parameter gradients). Over peer memory when
+        available: every rank pushes its vector into slot [rank] of every peer's region, a barrier, then each rank adds
+        the `world` slots in rank order (bit-identical everywhere, no NCCL kernel); NCCL / gloo all-reduce otherwise."""
+        n = flat.numel()
+        n4 = (n + 3) // 4 * 4
+        reg = self.region("grads", self.world * n4 * 4) if (self.p2p is not None and flat.is_cuda) else None
+        if reg is None:
+            td.all_reduce(flat, op=td.ReduceOp.SUM, group=self.group)
+            return flat.mul_(1.0 / self.world)
+        from . import ops
+        if flat.data_ptr() % 16 or not flat.is_contiguous():
+            raise RuntimeError("all_reduce_mean_flat needs a contiguous, 16-byte aligned vector")
+        reg.push(flat, self.rank * n4 * 4)
+        self.p2p_barrier()
+        ops.sum_slots(reg.tensor(self.rank, 0, (self.world * n4,)), self.world, n4, n, 1.0 / self.world, flat)
+        return flat
 
     def all_reduce_sum(self, t):
         if self.world > 1:
@@ -143,8 +197,7 @@ def average_gradients(model, comm):
         return
     grads = [p.grad for p in ps]
     flat = torch.cat([g.reshape(-1) for g in grads])
-    comm.all_reduce_sum(flat)
-    flat.mul_(1.0 / comm.world)
+    comm.all_reduce_mean_flat(flat)
     views, off = [], 0
     for g in grads:
         n = g.numel()
@@ -183,6 +236,10 @@ def shutdown(timeout_exit_code=1):
         if _OPEN_P2P:
             td.barrier()                  # nobody may still be writing into a buffer that is about to be unmapped
             for c in _OPEN_P2P:
+                for reg in c.regions.values():
+                    reg.close()
+                c.regions.clear()
+                c._token = None
                 c.p2p.close()
                 c.p2p = None
             del _OPEN_P2P[:]

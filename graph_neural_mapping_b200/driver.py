@@ -129,8 +129,7 @@ class _WholeStepPlan(object):
             # one flat all-reduce; each rank's loss is the mean over its own shard, so the average over ranks is the
             # gradient of the global-batch mean loss (main.py:34-41 at the global batch)
             flat = torch.cat([g.reshape(-1) for g in grads])
-            tr.comm.all_reduce_sum(flat)
-            flat.mul_(1.0 / world)
+            tr.comm.all_reduce_mean_flat(flat)
             views, off = [], 0
             for g in grads:
                 views.append(flat[off:off + g.numel()].view(g.shape))

@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libgnm.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 _c_i32 = ctypes.c_int
 _c_i64 = ctypes.c_int64
@@ -53,6 +53,10 @@ SIGNATURES = {
     "gnm_aggregate_max_bwd": [_p, _p, _c_i32, _p, _c_i64, _c_i32, _p, _p, _p, _p, _c_i64, _p],
     "gnm_p2p_buffer_bytes": [],
     "gnm_p2p_alloc": [_p, _p],
+    "gnm_p2p_alloc_bytes": [_p, _p, _c_i64],
+    "gnm_p2p_push": [_p, _c_i64, _p, _c_i32, _c_i64, _p],
+    "gnm_sum_slots": [_p, _c_i32, _c_i64, _c_i64, _c_f32, _p, _p],
+    "gnm_scatter_scaled_rows": [_p, _p, _p, _c_i64, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p],
     "gnm_p2p_open": [_p, _p],
     "gnm_p2p_close": [_p, _c_i32],
     "gnm_p2p_allreduce": [_p, _c_i32, _p, _p],

@@ -347,6 +347,88 @@ class P2PComm(object):
             self.local = None
 
 
+class _DevPtr(object):
+    """A raw device pointer exposed through __cuda_array_interface__ so that torch can wrap it without copying."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class P2PRegion(object):
+    """A peer-mapped memory region per rank (gnm_p2p_alloc_bytes + CUDA IPC): `tensor(r, ...)` is a torch view of rank
+    r's region as mapped in THIS process - kernels read / write it through ordinary pointers over NVLink."""
+
+    def __init__(self, rank, world, device, nbytes):
+        self.rank, self.world, self.device, self.nbytes = int(rank), int(world), device, int(nbytes)
+        self.local = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        _libmod.check(_lib().gnm_p2p_alloc_bytes(ctypes.byref(self.local), handle, self.nbytes), "gnm_p2p_alloc_bytes")
+        self.handle = bytes(handle)
+        self.opened = []
+        self.addrs = None
+        self.bases = None            # device int64[world]: the regions' base addresses (gnm_p2p_push)
+        self._views = {}
+
+    def connect(self, handles):
+        addrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                addrs.append(self.local.value)
+                continue
+            ptr = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            _libmod.check(_lib().gnm_p2p_open(buf, ctypes.byref(ptr)), "gnm_p2p_open")
+            self.opened.append(ptr)
+            addrs.append(ptr.value)
+        self.addrs = addrs
+        self.bases = torch.tensor(addrs, dtype=torch.int64, device=self.device)
+
+    def tensor(self, r, byte_offset, shape, dtype=torch.float32):
+        key = (r, byte_offset, tuple(shape), dtype)
+        t = self._views.get(key)
+        if t is None:
+            n = 1
+            for d in shape:
+                n *= int(d)
+            esz = torch.empty(0, dtype=dtype).element_size()
+            if byte_offset + n * esz > self.nbytes:
+                raise RuntimeError("P2PRegion view of %d bytes at %d exceeds the region (%d)" % (n * esz, byte_offset, self.nbytes))
+            typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4"}[dtype]
+            t = torch.as_tensor(_DevPtr(self.addrs[r] + byte_offset, shape, typestr), device=self.device)
+            self._views[key] = t
+        return t
+
+    def push(self, src, byte_offset):
+        """src (float32, contiguous, numel % 4 == 0) -> every rank's region at byte_offset."""
+        _libmod.check(_lib().gnm_p2p_push(_ptr(src, torch.float32), int(src.numel()), _ptr(self.bases, torch.int64), self.world,
+                                          int(byte_offset), _stream(src)), "gnm_p2p_push")
+
+    def close(self):
+        self._views.clear()
+        for ptr in self.opened:
+            _lib().gnm_p2p_close(ptr, 0)
+        self.opened = []
+        if self.local is not None and self.local.value:
+            _lib().gnm_p2p_close(self.local, 1)
+            self.local = None
+
+
+def sum_slots(base, world, stride, n, scale, out):
+    _libmod.check(_lib().gnm_sum_slots(_ptr(base, torch.float32), int(world), int(stride), int(n), float(scale),
+                                       _ptr(out, torch.float32), _stream(out)), "gnm_sum_slots")
+    return out
+
+
+def scatter_scaled_rows(idx, scale, src, dst):
+    sp, lds = _mat(src)
+    dp, ldd = _mat(dst)
+    _libmod.check(_lib().gnm_scatter_scaled_rows(_ptr(idx, torch.int32), _ptr(scale, torch.float32), sp, lds, int(src.shape[0]),
+                                                 int(src.shape[1]), dp, ldd, int(dst.shape[0]), _stream(src)),
+                  "gnm_scatter_scaled_rows")
+    return dst
+
+
 # ---- MLP -----------------------------------------------------------------------------------
 
 def set_linear_impl(impl):
@@ -468,9 +550,11 @@ def _hall(h_all):
     return _ptr(h_all, torch.float32), int(h_all.stride(0)), int(h_all.shape[0]), int(h_all.shape[2]), int(h_all.stride(1))
 
 
-def gather_nf_rows(h_all, n_rows):
+def gather_nf_rows(h_all, n_rows, out=None):
     hp, ls, nl, nf, ldh = _hall(h_all)
-    table = torch.empty(n_rows, nl * nf, dtype=torch.float32, device=h_all.device)
+    table = out if out is not None else torch.empty(n_rows, nl * nf, dtype=torch.float32, device=h_all.device)
+    if tuple(table.shape) != (n_rows, nl * nf) or not table.is_contiguous():
+        raise RuntimeError("gather_nf_rows: out must be a contiguous [%d, %d] tensor" % (n_rows, nl * nf))
     _libmod.check(_lib().gnm_gather_nf_rows(hp, ls, nl, nf, ldh, n_rows, _ptr(table), _stream(h_all)),
                   "gnm_gather_nf_rows")
     return table

@@ -33,7 +33,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 15
+#define GNM_ABI_VERSION 16
 
 typedef void* gnm_stream_t;
 
@@ -369,6 +369,23 @@ int gnm_adam_step(float* const* params, const float* const* grads, const int32_t
  * gnm_p2p_status reports a give-up. */
 int64_t gnm_p2p_buffer_bytes(void);
 int gnm_p2p_alloc(void** buf, unsigned char* handle /* [GNM_P2P_HANDLE_BYTES] out: CUDA IPC handle */);
+/* Larger peer-mapped regions for the two bulk exchanges of the data-parallel step - the rows of n_f that the DGI
+ * negatives read (graphcnn.py:241-242: rows perm[g] < B_global, all owned by rank 0) with their gradient, and the flat
+ * parameter gradients. gnm_p2p_alloc_bytes = gnm_p2p_alloc with a caller-chosen size (zero-filled; opened / closed
+ * with gnm_p2p_open / gnm_p2p_close). The data kernels read / write peer memory through ordinary pointers (e.g. the
+ * `neg_table` of gnm_dgi_score_fwd may point into rank 0's region); ordering between ranks comes from a
+ * gnm_p2p_allreduce of one dummy value used as a barrier (every rank passes it only after all ranks reached it).
+ *   gnm_p2p_push: every region r receives src[0..n) at byte_offset (regions: DEVICE array of `world` base pointers as
+ *     mapped in this process) - the all-gather half of the gradient all-reduce;
+ *   gnm_sum_slots: out = scale * sum_{r < world} base[r*stride .. r*stride + n) in rank order - the reduce half
+ *     (bit-identical on every rank); stride a multiple of 4 floats, 16-byte aligned pointers;
+ *   gnm_scatter_scaled_rows: dst[idx[g], :] = scale[g] * src[g, :] for injective idx (entries outside [0, n_dst) are
+ *     skipped) - each rank writes the gradient rows its permutation slice names straight into rank 0's region. */
+int gnm_p2p_alloc_bytes(void** buf, unsigned char* handle, int64_t bytes);
+int gnm_p2p_push(const float* src, int64_t n, void* const* regions, int world, int64_t byte_offset, gnm_stream_t stream);
+int gnm_sum_slots(const float* base, int world, int64_t stride, int64_t n, float scale, float* out, gnm_stream_t stream);
+int gnm_scatter_scaled_rows(const int32_t* idx, const float* scale, const float* src, int64_t lds, int n_src, int width,
+                            float* dst, int64_t ldd, int n_dst, gnm_stream_t stream);
 int gnm_p2p_open(const unsigned char* handle, void** buf);
 int gnm_p2p_close(void* buf, int owner);
 int gnm_p2p_allreduce(double* data, int n, const gnm_p2p_comm* comm, gnm_stream_t stream);

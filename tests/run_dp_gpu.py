@@ -82,20 +82,81 @@ def check_peer_exchange(comm, dev):
         if not all(torch.equal(every[0], e) for e in every):
             print("rank %d: peer exchange %d not bit-identical across ranks" % (comm.rank, it), flush=True)
             return False
+    # the flat gradient all-reduce over peer regions (push to every peer, barrier, rank-ordered sum): odd lengths,
+    # repeated calls (slot reuse), growth of the region
+    for it, n in enumerate([167435, 167435, 7, 690192, 64]):
+        x = torch.randn(n, generator=gen).to(dev) * (it + 1)
+        parts = gather(x, comm)
+        ref = torch.zeros_like(x)
+        for part in parts:
+            ref = ref + part                          # the kernel's order of additions
+        ref = ref * (1.0 / comm.world)
+        got = comm.all_reduce_mean_flat(x.clone())
+        if not torch.equal(got, ref):
+            print("rank %d: flat gradient all-reduce %d differs from the rank-ordered mean (max %.3e)"
+                  % (comm.rank, it, float((got - ref).abs().max())), flush=True)
+            return False
+        every = gather(got, comm)
+        if not all(torch.equal(every[0], e) for e in every):
+            print("rank %d: flat gradient all-reduce %d not bit-identical across ranks" % (comm.rank, it), flush=True)
+            return False
     torch.cuda.synchronize()
     if p2p.status():
         print("rank %d: a peer exchange gave up waiting" % comm.rank, flush=True)
         return False
     if comm.rank == 0:
-        print("peer exchange OK: world=%d, 200 exchanges, bit-identical on all ranks" % comm.world, flush=True)
+        print("peer exchange OK: world=%d, 200 exchanges + 5 flat all-reduces, bit-identical on all ranks" % comm.world, flush=True)
     return True
+
+
+def check_trainer(comm, dev, name, seed0):
+    """driver.Trainer (step on libgnm's own kernels, DGI rows and gradients over peer memory) on the sharded golden batch:
+    the mean of the ranks' losses must equal the single-process reference's loss, for the eager steps and the captured
+    CUDA graph; afterwards every rank must hold bit-identical parameters."""
+    from graph_neural_mapping_b200.driver import Trainer
+    g = Golden(name)
+    if g.cfg["B"] % comm.world:
+        return True
+    graphs = gdist.shard(g.graphs(), comm)
+    model = build(g, dev, comm, True)
+    model.final_dropout = 0.0
+    model.train()
+    tr = Trainer(model, lr=0.005, beta=g.cfg["beta"], comm=comm)
+    ok = True
+    for rep in range(4):
+        model.load_state_dict(g.state_dict())
+        np.random.seed(4242 + seed0)
+        loss = tr.step(graphs).detach().reshape(1).clone()
+        ls = gather(loss, comm)
+        if comm.rank == 0:
+            try:
+                assert_close(torch.stack(ls).mean(), g.z["train/loss"], 1e-4, "Trainer loss, step %d" % rep)
+            except AssertionError as e:
+                print(str(e), flush=True)
+                ok = False
+    tr.finish()
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    every = gather(flat, comm)
+    if not all(torch.equal(every[0], e) for e in every):
+        print("rank %d: parameters differ across ranks after Trainer steps" % comm.rank, flush=True)
+        ok = False
+    if comm.rank == 0 and ok:
+        print("DP Trainer OK: %s world=%d" % (name, comm.world), flush=True)
+    tr.release()
+    model.release_graphs()
+    return ok
 
 
 def main():
     comm, local_rank = gdist.init_from_env("nccl")
     dev = torch.device("cuda", local_rank)
     ok = check_peer_exchange(comm, dev)
-    for name, seed0 in [("mid_eps_sum_h64", 900), ("tiny_eps_sum", 100)]:
+    ok = check_trainer(comm, dev, "schaefer400_b16_noeps", 2000) and ok
+    ok = check_trainer(comm, dev, "mid_eps_sum_h64", 900) and ok
+    # B = 16 fixtures shard over 2, 4 and 8 ranks (M = 6400 rows: the tcgen05 kernel family at world <= 2 ... the
+    # small-problem kernels below 4096 rows per rank)
+    for name, seed0 in [("schaefer400_b16_noeps", 2000), ("schaefer400_b16_eps", 2100), ("mid_eps_sum_h64", 900),
+                        ("tiny_eps_sum", 100)]:
         g = Golden(name)
         if g.cfg["B"] % comm.world:
             continue

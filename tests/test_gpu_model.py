@@ -288,17 +288,20 @@ def test_cuda_graph_steps_match_eager_steps():
         c_old.sum().backward()
 
 
-def test_two_gpu_data_parallel_matches_reference():
-    """Launches tests/run_dp_gpu.py under torchrun when the box has >= 2 GPUs (skipped on 1-GPU boxes)."""
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_data_parallel_matches_reference(world):
+    """Launches tests/run_dp_gpu.py under torchrun with `world` ranks when the box has that many GPUs (skipped
+    otherwise): sharded steps (model API and driver.Trainer) against the single-process reference fixtures - the
+    B = 16 fixtures shard over 2, 4 and 8 ranks - plus the peer-memory exchange protocol."""
     import os
     import subprocess
     import sys
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     here = os.path.dirname(os.path.abspath(__file__))
-    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29371", os.path.join(here, "run_dp_gpu.py")],
-                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", str(29371 + world), os.path.join(here, "run_dp_gpu.py")],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert "DP_GPU_CHECK_PASSED" in res.stdout, res.stdout[-3000:]
 
 
