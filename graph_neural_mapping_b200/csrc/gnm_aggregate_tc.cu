@@ -72,6 +72,11 @@ struct AggTcParams {
     const float* r_dscore; const float* r_u; int64_t ld_u;
     const float* r_dneg; int64_t ld_dneg; int r_nneg;
     double* r_stats;
+    // layer-0 row gather with one table shared by every graph (all graphs carry the same tag sequence): src_map holds
+    // ONE graph's tags (indexed by the node's position in its graph), the B planes are converted once per CTA and
+    // stay resident; out_stats (nullable) += [sum, sum of squares] per column of the rows written (BatchNorm statistics)
+    int b_shared;
+    double* out_stats;
     long long* dbg;              // nullable: per-CTA wait/busy cycle counters (profiling aid)
 };
 
@@ -134,6 +139,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         float* stg = sm_stg + warp * (32 * TC_PITCH);
         // fused relu/BatchNorm backward (single 64-wide slab only): this lane's four columns are fixed
         const bool fuse = p.rz != nullptr;
+        const bool ostats = p.out_stats != nullptr;
         float4 r_sc = make_float4(0.f, 0.f, 0.f, 0.f), r_sh = r_sc, r_mu = r_sc, r_rs = r_sc;
         float rs1[4] = {0.f, 0.f, 0.f, 0.f}, rs2[4] = {0.f, 0.f, 0.f, 0.f};
         if (fuse && (lane & 15) * 4 < p.n_feat) {
@@ -233,12 +239,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                             const int g2 = n0 + row0 + rr;
                             float4 v = *reinterpret_cast<const float4*>(stg + rr * TC_PITCH + c4 * 4);
                             if (p.eps) {
-                                const int64_t sr = p.src_map ? (int64_t)p.src_map[g2] : (int64_t)g2;
+                                const int64_t sr = p.src_map ? (int64_t)p.src_map[p.b_shared ? row0 + rr : g2] : (int64_t)g2;
                                 const float4 sv = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
                                 v.x = fmaf(self_c, sv.x, v.x); v.y = fmaf(self_c, sv.y, v.y);
                                 v.z = fmaf(self_c, sv.z, v.z); v.w = fmaf(self_c, sv.w, v.w);
                             }
                             v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                            if (ostats) {
+                                rs1[0] += v.x; rs1[1] += v.y; rs1[2] += v.z; rs1[3] += v.w;
+                                rs2[0] = fmaf(v.x, v.x, rs2[0]); rs2[1] = fmaf(v.y, v.y, rs2[1]);
+                                rs2[2] = fmaf(v.z, v.z, rs2[2]); rs2[3] = fmaf(v.w, v.w, rs2[3]);
+                            }
                             if (fuse) {
                                 // gnm_relu_bn_bwd_reduce on the fly: add the readout / DGI gradients of this row, mask by
                                 // the ReLU of the layer below, accumulate sum(dy) and sum(dy * xhat)
@@ -269,7 +280,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 }
             }
         }
-        if (fuse && p.r_stats != nullptr) {
+        double* const stats_out = ostats ? p.out_stats : (fuse ? p.r_stats : nullptr);
+        if (stats_out != nullptr) {
             // lanes l and l ^ 16 hold the same columns: fold, park the warp's 2 x 64 partial sums in its staging tile,
             // add the epilogue warps in a fixed order, ONE fp64 atomic per column and CTA
             __syncwarp();
@@ -288,7 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
 #pragma unroll
                 for (int w = 0; w < TC_EPI_WARPS; ++w) a += sm_stg[w * (32 * TC_PITCH) + tid];
                 const int c = tid & 63;
-                if (c < p.n_feat) atomicAdd(&p.r_stats[(tid >> 6) * p.n_feat + c], (double)a);
+                if (c < p.n_feat) atomicAdd(&stats_out[(tid >> 6) * p.n_feat + c], (double)a);
             }
         }
         if (DBG && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_role; p.dbg[blockIdx.x * 16 + 1] = w_acc; }
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (kc < q.n_kc && k < q.n && col < p.n_feat) {
                     const int jr = q.n0 + k;
-                    const int64_t sr = p.src_map ? (int64_t)p.src_map[jr] : (int64_t)jr;
+                    const int64_t sr = p.src_map ? (int64_t)p.src_map[p.b_shared ? k : jr] : (int64_t)jr;
                     v = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
                     if (p.aff_coef != nullptr) {
                         const float4 zv = __ldg(reinterpret_cast<const float4*>(p.aff_z + sr * p.ld_aff_z + col));
@@ -426,9 +438,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, ++b_it) {
             fetch_item(item + gridDim.x, nxt);   // in flight during this whole item
             const int n = cur.n, n_mt = cur.n_mt, n_kc = cur.n_kc, ksteps_total = cur.ksteps_total;
+            // shared table: only this CTA's first item converts (and loads) the B planes
+            const bool do_b = !p.b_shared || item == (int)blockIdx.x;
             if (!preloaded) {
                 load_words(cur, 0, a_it, w_cur);
-                load_b(cur, ((a_it & 1) == (uint32_t)grp) ? 0 : 1);
+                if (do_b) load_b(cur, ((a_it & 1) == (uint32_t)grp) ? 0 : 1);
             }
             preloaded = false;
             bool first_b = true;
@@ -438,7 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                     derive_item(nxt);
                     const uint32_t it_next = a_it + n_kc;                 // ring position at the next item's start
                     load_words(nxt, 0, it_next, w_nxt);
-                    load_b(nxt, ((it_next & 1) == (uint32_t)grp) ? 0 : 1);
+                    if (!p.b_shared) load_b(nxt, ((it_next & 1) == (uint32_t)grp) ? 0 : 1);
                     preloaded = true;
                 } else {
                     load_words(cur, mt + 1, a_it + n_kc, w_nxt);
@@ -449,7 +463,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                     if (((kc - first) & 1) != 0) continue;          // the other group's stage
                     const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
                     if (!(ok = mbar_wait<32>(&a_empty[s], aph ^ 1, abort_flag, DBG ? &w_pe : nullptr))) break;
-                    if (mt == 0) {
+                    if (mt == 0 && do_b) {
                         // the previous item's MMAs on these B rows retired at least TC_STAGES stages ago, unless
                         // that item had fewer k chunks than the ring: then wait for its explicit b_free commit
                         if (first_b && prev_nkc < TC_STAGES) {
@@ -529,8 +543,11 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
                             int n_max, const float* src, int64_t ld_src, const int32_t* src_map, float* dst,
                             int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
                             const float* aff_coef, const float* aff_z, int64_t ld_aff_z, const GnmReluBnBwdFuse* fuse,
-                            cudaStream_t stream) {
+                            int b_shared, double* out_stats, cudaStream_t stream) {
     if (n_max > TC_MAX_NODES) return GNM_ERR_TOO_LARGE;
+    if ((out_stats != nullptr || b_shared) && (n_feat > TC_SLAB || fuse != nullptr || aff_coef != nullptr || mode == 2))
+        return GNM_ERR_TOO_LARGE;              // one 64-wide slab per lane; a shared table has no per-graph row weights
+    if (b_shared && src_map == nullptr) return GNM_ERR_BAD_ARG;
     if (fuse != nullptr) {
         if (n_feat > TC_SLAB) return GNM_ERR_TOO_LARGE;             // the fused reduction keeps one 64-wide slab per lane
         if ((fuse->ldz % 4) || !gnm_aligned16(fuse->z) || !gnm_aligned16(fuse->scale) || !gnm_aligned16(fuse->shift) ||
@@ -563,6 +580,7 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
         p.r_pool_scale = fuse->pool_scale; p.r_dscore = fuse->d_score; p.r_u = fuse->u; p.ld_u = fuse->ldu;
         p.r_dneg = fuse->d_neg; p.ld_dneg = fuse->ld_dneg; p.r_nneg = fuse->n_neg; p.r_stats = fuse->stats;
     }
+    p.b_shared = b_shared; p.out_stats = out_stats;
     p.dbg = g_tc_dbg_host;
     p.n_slabs = (n_feat + TC_SLAB - 1) / TC_SLAB;
     p.kcores_max = ((n_max + 15) / 16) * 2;

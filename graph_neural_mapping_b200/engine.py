@@ -343,6 +343,18 @@ class BatchStructure(object):
                                                 src, mode, eps, unit.z, unit.scale, unit.shift, unit.mean, unit.rstd,
                                                 d_pooled, self.pool_scale, d_score, u, d_neg, n_neg, dy, stats)
 
+    def aggregate_table(self, table, dst, mode, eps, bias, stats):
+        """Layer 0 as a row gather of `table` when every graph carries the same tag sequence: dst = Agg(table[tags]) (+ self
+        term) + bias and stats += its column statistics, the table staying resident in the kernel's shared memory
+        (ops.aggregate_dense_table); False, nothing launched, when the batch does not run on the tcgen05 kernel."""
+        if (self.bitmap_addr is None or FORCE_CSR_AGGREGATE or not self.same_tags or self.uniform_n is None or mode == 2
+                or not _ops.dense_aggregate_ok(table, dst, bias)):
+            return False
+        if mode != 0 and self.has_isolated:
+            return False
+        return _ops.aggregate_dense_table(self.bitmap_addr, self.node_off, self.rowptr, self.n_graphs, self.n_max, table,
+                                          self.tags[:self.uniform_n], dst, mode, eps, bias, stats)
+
     def aggregate_affine(self, dy, z, coef, dst, mode):
         """dst = Agg(coef[0]*dy + coef[1]*z + coef[2]) when the batch runs on the tcgen05 dense-block kernel (the affine
         is applied to the rows as they are loaded); False, with nothing launched, otherwise."""
@@ -539,8 +551,9 @@ def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm, m
                     # first layer as a row gather of W1^T (X_concat is one-hot): no dense X, no GEMM
                     w1t = u.w.detach().t().contiguous()
                     sv.w1t = w1t
-                    bs.aggregate(w1t, bs.tags, u.z, 1 if average else 0, eps_l, u.b)
-                    _ops.col_stats(u.z, stats)
+                    if not bs.aggregate_table(w1t, u.z, 1 if average else 0, eps_l, u.b, stats):
+                        bs.aggregate(w1t, bs.tags, u.z, 1 if average else 0, eps_l, u.b)
+                        _ops.col_stats(u.z, stats)
                     u.x_in = None
                 else:
                     src = x_dense if layer == 0 else h_prev

@@ -160,6 +160,22 @@ def aggregate_dense(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, src_map
     return dst
 
 
+def aggregate_dense_table(bitmap_addr, node_off, rowptr, n_graphs, n_max, table, tags, dst, mode, eps, bias, out_stats):
+    """z0 = Agg(table[tags]) (+ self term) + bias with one table shared by every graph, + column statistics of z0
+    (include/gnm.h: gnm_aggregate_dense_table). Returns False, nothing launched, when the batch does not fit it."""
+    tp, ldt = _mat(table)
+    dp, ldd = _mat(dst)
+    rc = _lib().gnm_aggregate_dense_table(_ptr(bitmap_addr, torch.int64), _ptr(node_off, torch.int32), _ptr(rowptr, torch.int32),
+                                          n_graphs, n_max, tp, ldt, _ptr(tags, torch.int32), dp, ldd, int(dst.shape[1]),
+                                          int(mode), _ptr(eps, torch.float32), _ptr(bias, torch.float32),
+                                          _ptr(out_stats, torch.float64), _stream(dst))
+    if rc in (-2, -3):
+        LAUNCHES[0] -= 1
+        return False
+    _libmod.check(rc, "gnm_aggregate_dense_table")
+    return True
+
+
 TC_MAX_NODES = 416          # largest graph the tcgen05 aggregation kernel takes (gnm_aggregate_tc.cu)
 
 

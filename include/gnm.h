@@ -33,7 +33,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 16
+#define GNM_ABI_VERSION 17
 
 typedef void* gnm_stream_t;
 
@@ -132,6 +132,18 @@ int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* node_off, con
  * applied to the rows as the tcgen05 kernel loads them. Returns GNM_ERR_TOO_LARGE / GNM_ERR_ALIGN when the batch does
  * not fit that kernel (n_max > 416, odd strides): use gnm_bn_bwd_apply + gnm_aggregate* then. No eps self term
  * (learn_eps models take the two-pass route). */
+/* Layer 0 on one-hot inputs when every graph of the batch carries the SAME injective tag sequence (util.py:106-116: one
+ * tag per ROI, same ROI order for every subject): z0 = Agg(table[tags]) [+ (1+eps) table[tags]] + bias - graphcnn.py:154-161
+ * + the first Linear of mlp.py:48 with X_concat = stacked identities - plus the BatchNorm statistics of z0
+ * (out_stats, nullable double[2*n_feat], += [sum | sum of squares] per column) taken in the copy-out. The table rows are
+ * converted to tensor-core operands once per CTA and stay resident for all its graphs. tcgen05 kernel only
+ * (n_max <= 416, n_feat <= 64, mode 0 / 1): GNM_ERR_TOO_LARGE / GNM_ERR_ALIGN otherwise, nothing launched - use
+ * gnm_aggregate_dense + gnm_col_stats then. tags: int32 [n_max], ONE graph's tag sequence; every graph has n_max nodes. */
+int gnm_aggregate_dense_table(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
+                              int n_max, const float* table, int64_t ld_table, const int32_t* tags, float* dst,
+                              int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias, double* out_stats,
+                              gnm_stream_t stream);
+
 int gnm_aggregate_dense_affine(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
                                int n_max, const float* dy, int64_t ld_dy, const float* z, int64_t ld_z, const float* coef,
                                float* dst, int64_t ld_dst, int n_feat, int mode, gnm_stream_t stream);

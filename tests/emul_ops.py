@@ -423,3 +423,7 @@ def dgi_neg_grad(neg_idx, s2, u, d_neg):
     d_neg.zero_()
     d_neg.index_add_(0, neg_idx.long(), s2.unsqueeze(1) * u)
     return d_neg
+
+
+def aggregate_dense_table(bitmap_addr, node_off, rowptr, n_graphs, n_max, table, tags, dst, mode, eps, bias, out_stats):
+    return False          # the stand-in has no shared-table kernel: the engine falls back to aggregate + col_stats

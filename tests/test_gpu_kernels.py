@@ -839,3 +839,50 @@ def test_peer_exchange_protocol_two_ranks_on_one_gpu():
         torch.cuda.synchronize()
         for b in bufs:
             L.gnm_p2p_close(b, 1)
+
+
+@pytest.mark.parametrize("n,b,f,mode,use_eps", [(400, 333, 64, 0, False), (400, 20, 64, 0, True), (48, 7, 32, 1, True),
+                                                (12, 3, 8, 0, False), (416, 150, 64, 1, False)])
+def test_aggregate_dense_table_shared_rows_and_column_stats(n, b, f, mode, use_eps):
+    """Layer 0 with one table shared by all graphs (gnm_aggregate_dense_table): the B planes are converted once per CTA
+    (b > 148 makes the persistent CTAs reuse them over several graphs); result and fused BatchNorm statistics against
+    the general kernels (gnm_aggregate_dense with a per-row map + gnm_col_stats) and the fp64 stand-in."""
+    rng = np.random.default_rng(n + b)
+    counts = [n] * b
+    ems = [rand_graph_edges(rng, n, 0.3) for _ in counts]
+    if mode != 0:
+        ring = np.stack([np.arange(n), (np.arange(n) + 1) % n])
+        ems = [np.unique(np.concatenate([e, ring, ring[::-1]], 1), axis=1) for e in ems]
+        ems = [e[:, e[0] != e[1]] for e in ems]
+    e, eo, no = build_inputs(ems, counts)
+    m = n * b
+    self_loops = not use_eps
+    rp, ci, _ = ops.csr_build(e, eo, no, b, n, m, self_loops, False)
+    rpl, cil, _ = ops.csr_build(e, eo, no, b, n, m, self_loops, True)
+    bm, dup, addr, _ = _bitmaps(rpl, cil, no, counts)
+    torch.manual_seed(f + b)
+    table = torch.randn(n + 5, f, device=DEV) * 3
+    tags1 = torch.randperm(n + 5)[:n].to(torch.int32).to(DEV)            # one graph's injective tag sequence
+    tags = tags1.repeat(b)
+    eps = torch.tensor([0.3], device=DEV) if use_eps else None
+    bias = torch.randn(f, device=DEV)
+    got = torch.full((m, f), float("nan"), device=DEV)
+    st = torch.zeros(2 * f, dtype=torch.float64, device=DEV)
+    assert ops.aggregate_dense_table(addr, no, rp, b, n, table, tags1, got, mode, eps, bias, st)
+    assert not ops.aggregate_tc_status(), "tcgen05 kernel hit a barrier timeout"
+    want = torch.empty(m, f, device=DEV)
+    ops.aggregate_dense(addr, no, rp, b, n, table, tags, want, mode, eps, bias, impl=2)
+    assert_close(got, want, 1e-6, "shared table vs per-row map")
+    st2 = torch.zeros(2 * f, dtype=torch.float64, device=DEV)
+    ops.col_stats(want, st2)
+    assert_close(st[:f], st2[:f], 1e-5, "fused column sums")
+    assert_close(st[f:], st2[f:], 1e-5, "fused column sums of squares")
+    ref = torch.empty(m, f)
+    emul_ops.aggregate(rp.cpu(), ci.cpu(), table.cpu(), tags.cpu(), ref, mode, eps.cpu() if use_eps else None, bias.cpu())
+    assert_close(got, ref, TOL, "shared table vs fp64")
+    assert_close(st[:f], ref.double().sum(0), 1e-5, "column sums vs fp64")
+    assert_close(st[f:], (ref.double() ** 2).sum(0), 1e-5, "column sums of squares vs fp64")
+    # without statistics
+    got2 = torch.empty(m, f, device=DEV)
+    assert ops.aggregate_dense_table(addr, no, rp, b, n, table, tags1, got2, mode, eps, bias, None)
+    assert torch.equal(got2, got)
