@@ -32,11 +32,16 @@ struct HeadsParams {
     float* ws;                                     // workspace: gridDim.x x (L*C*F + L*C) partial sums
     unsigned int* counter;                         // zero on entry; reset to zero by the last CTA
     int n_graphs, n_layers, n_feat, n_classes;
+    const float* d_logit_in;                       // HD_BWD only: d loss / d c_logit [B, C] from the caller's loss
 };
+
+// HD_FUSED: heads + CrossEntropy forward and backward; HD_FWD: c_logit only; HD_BWD: backward for a given d c_logit
+enum { HD_FUSED = 0, HD_FWD = 1, HD_BWD = 2 };
 
 // One warp per graph row; lanes own features f = lane, lane + 32, ... Per-warp gradient partials live in shared
 // memory (owner-lane updates, no atomics); CTAs write their partial to the workspace and the last CTA to finish adds
 // them in CTA order: deterministic, one launch, no pre-zeroed outputs.
+template <int MODE>
 __global__ void __launch_bounds__(HD_WARPS * 32) heads_ce_kernel(const HeadsParams p) {
     extern __shared__ float hd_smem[];
     __shared__ float s_logit[HD_WARPS][HD_MAX_CLASSES];
@@ -45,8 +50,10 @@ __global__ void __launch_bounds__(HD_WARPS * 32) heads_ce_kernel(const HeadsPara
     const int gsz = L * C * F + L * C;             // dW entries then db entries
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* acc = hd_smem + (size_t)warp * gsz;
-    for (int i = lane; i < gsz; i += 32) acc[i] = 0.f;
-    __syncwarp();
+    if (MODE != HD_FWD) {
+        for (int i = lane; i < gsz; i += 32) acc[i] = 0.f;
+        __syncwarp();
+    }
     double loss_w = 0.0;
     for (int row = blockIdx.x * HD_WARPS + warp; row < p.n_graphs; row += gridDim.x * HD_WARPS) {
         const float* g = p.g_f + (int64_t)row * p.ldg;
@@ -54,7 +61,7 @@ __global__ void __launch_bounds__(HD_WARPS * 32) heads_ce_kernel(const HeadsPara
         float logit[HD_MAX_CLASSES];
 #pragma unroll
         for (int c = 0; c < HD_MAX_CLASSES; ++c) logit[c] = 0.f;
-        for (int l = 0; l < L; ++l) {
+        for (int l = 0; l < L && MODE != HD_BWD; ++l) {
 #pragma unroll
             for (int c = 0; c < HD_MAX_CLASSES; ++c) {
                 if (c >= C) break;
@@ -65,6 +72,17 @@ __global__ void __launch_bounds__(HD_WARPS * 32) heads_ce_kernel(const HeadsPara
                 logit[c] += mk * d;
             }
         }
+        float dl[HD_MAX_CLASSES];
+        if (MODE == HD_FWD) {
+#pragma unroll
+            for (int c = 0; c < HD_MAX_CLASSES; ++c)
+                if (c < C && lane == 0) p.c_logit[(int64_t)row * C + c] = logit[c];
+            continue;
+        }
+        if (MODE == HD_BWD) {
+#pragma unroll
+            for (int c = 0; c < HD_MAX_CLASSES; ++c) dl[c] = c < C ? __ldg(p.d_logit_in + (int64_t)row * C + c) : 0.f;
+        } else {
         // ---- CrossEntropy (mean over the batch) and its gradient ------------------------------------------------
         float mx = logit[0];
 #pragma unroll
@@ -74,7 +92,6 @@ __global__ void __launch_bounds__(HD_WARPS * 32) heads_ce_kernel(const HeadsPara
         for (int c = 0; c < HD_MAX_CLASSES; ++c) if (c < C) se += expf(logit[c] - mx);
         const float lse = mx + logf(se);
         const int lab = (int)p.labels[row];
-        float dl[HD_MAX_CLASSES];
         float picked = 0.f;
 #pragma unroll
         for (int c = 0; c < HD_MAX_CLASSES; ++c) {
@@ -86,6 +103,7 @@ __global__ void __launch_bounds__(HD_WARPS * 32) heads_ce_kernel(const HeadsPara
             }
         }
         if (lane == 0) loss_w += (double)((lse - picked) * p.inv_count);
+        }
         // ---- backward: d g_f, dW, db --------------------------------------------------------------------------------
         for (int l = 0; l < L; ++l) {
             float dm[HD_MAX_CLASSES];
@@ -108,6 +126,7 @@ __global__ void __launch_bounds__(HD_WARPS * 32) heads_ce_kernel(const HeadsPara
             if (lane < C) acc[L * C * F + l * C + lane] += dm[lane];      // dm[] is warp-uniform
         }
     }
+    if (MODE == HD_FWD) return;
     __syncthreads();
     // CTA partial = sum of its warps (fixed order) -> workspace
     float* mine = p.ws + (size_t)blockIdx.x * gsz;
@@ -116,8 +135,10 @@ __global__ void __launch_bounds__(HD_WARPS * 32) heads_ce_kernel(const HeadsPara
         for (int w = 0; w < HD_WARPS; ++w) s += hd_smem[(size_t)w * gsz + i];
         mine[i] = s;
     }
-    loss_w = warp_sum_d(loss_w);
-    if (lane == 0 && loss_w != 0.0) atomicAdd(p.loss_acc, loss_w);
+    if (MODE == HD_FUSED) {
+        loss_w = warp_sum_d(loss_w);
+        if (lane == 0 && loss_w != 0.0) atomicAdd(p.loss_acc, loss_w);
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(p.counter, 1u) == gridDim.x - 1;
@@ -377,10 +398,62 @@ extern "C" int gnm_heads_ce(const float* g_f, int64_t ldg, int n_graphs, int n_l
         p.dw[l] = on ? d_weights[l] : nullptr; p.db[l] = on ? d_biases[l] : nullptr;
         if (on && (!p.w[l] || !p.b[l] || !p.dw[l] || !p.db[l])) return GNM_ERR_BAD_ARG;
     }
-    cudaError_t e = cudaFuncSetAttribute(heads_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    p.d_logit_in = nullptr;
+    cudaError_t e = cudaFuncSetAttribute(heads_ce_kernel<HD_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     gnm_count_launch(GNM_K_OTHER);
-    heads_ce_kernel<<<ctas, HD_WARPS * 32, smem, gnm_cast_stream(stream)>>>(p);
+    heads_ce_kernel<HD_FUSED><<<ctas, HD_WARPS * 32, smem, gnm_cast_stream(stream)>>>(p);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_heads_fwd(const float* g_f, int64_t ldg, int n_graphs, int n_layers, int n_feat, int n_classes,
+                             const float* const* weights, const float* const* biases, const float* mask, float* c_logit,
+                             gnm_stream_t stream) {
+    if (n_graphs < 0 || n_layers < 1 || n_feat < 1 || n_classes < 1) return GNM_ERR_BAD_ARG;
+    if (n_layers > HD_MAX_LAYERS || n_classes > HD_MAX_CLASSES) return GNM_ERR_TOO_LARGE;
+    if (n_graphs == 0) return GNM_OK;
+    if (!g_f || !weights || !biases || !c_logit) return GNM_ERR_BAD_ARG;
+    HeadsParams p = {};
+    p.g_f = g_f; p.ldg = ldg; p.mask = mask; p.c_logit = c_logit;
+    p.n_graphs = n_graphs; p.n_layers = n_layers; p.n_feat = n_feat; p.n_classes = n_classes;
+    for (int l = 0; l < n_layers; ++l) {
+        p.w[l] = weights[l]; p.b[l] = biases[l];
+        if (!p.w[l] || !p.b[l]) return GNM_ERR_BAD_ARG;
+    }
+    int ctas = (n_graphs + HD_WARPS - 1) / HD_WARPS;
+    if (ctas > 148 * 2) ctas = 148 * 2;
+    gnm_count_launch(GNM_K_OTHER);
+    heads_ce_kernel<HD_FWD><<<ctas, HD_WARPS * 32, 0, gnm_cast_stream(stream)>>>(p);
+    GNM_RETURN_IF_LAUNCH_FAILED();
+    return GNM_OK;
+}
+
+extern "C" int gnm_heads_bwd(const float* g_f, int64_t ldg, int n_graphs, int n_layers, int n_feat, int n_classes,
+                             const float* const* weights, const float* mask, const float* d_logit, float* d_gf, int64_t ldd,
+                             float* const* d_weights, float* const* d_biases, float* workspace, int64_t workspace_floats,
+                             unsigned int* counter, gnm_stream_t stream) {
+    if (n_graphs < 0 || n_layers < 1 || n_feat < 1 || n_classes < 1) return GNM_ERR_BAD_ARG;
+    if (n_layers > HD_MAX_LAYERS || n_classes > HD_MAX_CLASSES) return GNM_ERR_TOO_LARGE;
+    if (n_graphs == 0) return GNM_OK;
+    if (!g_f || !weights || !d_logit || !d_gf || !d_weights || !d_biases || !workspace || !counter) return GNM_ERR_BAD_ARG;
+    const int gsz = n_layers * n_classes * n_feat + n_layers * n_classes;
+    const size_t smem = (size_t)HD_WARPS * gsz * sizeof(float);
+    if (smem > 200 * 1024) return GNM_ERR_TOO_LARGE;
+    int ctas = (n_graphs + HD_WARPS - 1) / HD_WARPS;
+    if (ctas > 64) ctas = 64;
+    if (workspace_floats < (int64_t)ctas * gsz) return GNM_ERR_BAD_ARG;
+    HeadsParams p = {};
+    p.g_f = g_f; p.ldg = ldg; p.mask = mask; p.d_logit_in = d_logit; p.d_gf = d_gf; p.ldd = ldd; p.ws = workspace;
+    p.counter = counter; p.n_graphs = n_graphs; p.n_layers = n_layers; p.n_feat = n_feat; p.n_classes = n_classes;
+    for (int l = 0; l < n_layers; ++l) {
+        p.w[l] = weights[l]; p.dw[l] = d_weights[l]; p.db[l] = d_biases[l];
+        if (!p.w[l] || !p.dw[l] || !p.db[l]) return GNM_ERR_BAD_ARG;
+    }
+    cudaError_t e = cudaFuncSetAttribute(heads_ce_kernel<HD_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    gnm_count_launch(GNM_K_OTHER);
+    heads_ce_kernel<HD_BWD><<<ctas, HD_WARPS * 32, smem, gnm_cast_stream(stream)>>>(p);
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;
 }

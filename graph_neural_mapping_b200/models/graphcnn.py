@@ -24,6 +24,38 @@ from .. import engine as _engine
 from .. import graphed as _graphed
 
 
+class _HeadsFunction(torch.autograd.Function):
+    """c_logit = sum_l mask_l * (g_f[:, l] W_l^T + b_l) (graphcnn.py:228-231) on gnm_heads_fwd / gnm_heads_bwd."""
+
+    @staticmethod
+    def forward(ctx, g_f, mask, n_layers, *wb):
+        from .. import ops as _ops
+        ws = [w.detach().contiguous() for w in wb[:n_layers]]
+        bs = [b.detach().contiguous() for b in wb[n_layers:]]
+        g = g_f.detach()
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        c_logit = torch.empty(g.shape[0], ws[0].shape[0], dtype=torch.float32, device=g.device)
+        _ops.heads_fwd(g, ws, bs, mask, c_logit)
+        ctx.n_layers = n_layers
+        ctx.mask = mask
+        ctx.save_for_backward(g, *ws)
+        return c_logit
+
+    @staticmethod
+    def backward(ctx, d_logit):
+        from .. import ops as _ops
+        g, ws = ctx.saved_tensors[0], list(ctx.saved_tensors[1:])
+        n_cls, n_feat = ws[0].shape
+        d_gf = torch.empty_like(g)
+        dws = [torch.empty_like(w) for w in ws]
+        dbs = [torch.empty(n_cls, dtype=torch.float32, device=g.device) for _ in ws]
+        work = torch.empty(_ops.heads_ce_workspace(g.shape[0], ctx.n_layers, n_feat, n_cls), dtype=torch.float32, device=g.device)
+        counter = torch.zeros(1, dtype=torch.int32, device=g.device)
+        _ops.heads_bwd(g, ws, ctx.mask, d_logit.contiguous(), d_gf, dws, dbs, work, counter)
+        return (d_gf, None, None) + tuple(dws) + tuple(dbs)
+
+
 class GIN_InfoMaxReg(nn.Module):
     def __init__(self, num_layers, num_mlp_layers, input_dim, hidden_dim, output_dim, final_dropout, learn_eps,
                  graph_pooling_type, neighbor_pooling_type, device):
@@ -169,7 +201,19 @@ class GIN_InfoMaxReg(nn.Module):
         return torch.from_numpy(padded), torch.from_numpy(first)
 
     def _heads(self, g_f):
-        """graphcnn.py:228-231: sum over layers of dropout(Linear(pooled_h))."""
+        """graphcnn.py:228-231: sum over layers of dropout(Linear(pooled_h)). On the GPU: one libgnm launch forward, one
+        backward (_HeadsFunction) instead of ~15 + ~25 small torch kernels whose launch latency sat on the critical path
+        between the encoder's forward and backward graphs. The dropout masks are still drawn by L calls of F.dropout on
+        [B, C] tensors - the same consumption of torch's generator, hence the same masks, as the reference's
+        F.dropout(linear(pooled_h)) on that device."""
+        n_cls = self.linears_prediction[0].weight.shape[0]
+        if g_f.is_cuda and self.num_layers <= 16 and n_cls <= 8 and g_f.dtype == torch.float32:
+            mask = None
+            if self.training and self.final_dropout > 0.0:
+                ones = torch.ones(g_f.shape[0], n_cls, dtype=torch.float32, device=g_f.device)
+                mask = torch.stack([F.dropout(ones, self.final_dropout, training=True) for _ in range(self.num_layers)], 0)
+            wb = [lin.weight for lin in self.linears_prediction] + [lin.bias for lin in self.linears_prediction]
+            return _HeadsFunction.apply(g_f, mask, self.num_layers, *wb)
         f = self.hidden_dim
         score = 0
         for layer in range(self.num_layers):

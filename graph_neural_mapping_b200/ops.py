@@ -626,6 +626,25 @@ def heads_ce(g_f, weights, biases, mask, labels, inv_count, c_logit, loss_acc, d
                                       int(workspace.numel()), _ptr(counter, torch.int32), _stream(g_f)), "gnm_heads_ce")
 
 
+def heads_fwd(g_f, weights, biases, mask, c_logit):
+    gp, ldg = _mat(g_f)
+    n_layers, n_classes, n_feat = len(weights), int(weights[0].shape[0]), int(weights[0].shape[1])
+    _libmod.check(_lib().gnm_heads_fwd(gp, ldg, int(g_f.shape[0]), n_layers, n_feat, n_classes, _ptr_array(weights),
+                                       _ptr_array(biases), _ptr(mask, torch.float32), _ptr(c_logit, torch.float32),
+                                       _stream(g_f)), "gnm_heads_fwd")
+    return c_logit
+
+
+def heads_bwd(g_f, weights, mask, d_logit, d_gf, d_weights, d_biases, workspace, counter):
+    gp, ldg = _mat(g_f)
+    dp, ldd = _mat(d_gf)
+    n_layers, n_classes, n_feat = len(weights), int(weights[0].shape[0]), int(weights[0].shape[1])
+    _libmod.check(_lib().gnm_heads_bwd(gp, ldg, int(g_f.shape[0]), n_layers, n_feat, n_classes, _ptr_array(weights),
+                                       _ptr(mask, torch.float32), _ptr(d_logit, torch.float32), dp, ldd, _ptr_array(d_weights),
+                                       _ptr_array(d_biases), _ptr(workspace, torch.float32), int(workspace.numel()),
+                                       _ptr(counter, torch.int32), _stream(g_f)), "gnm_heads_bwd")
+
+
 def heads_ce_workspace(n_graphs, n_layers, n_feat, n_classes):
     return int(_lib().gnm_heads_ce_workspace(int(n_graphs), int(n_layers), int(n_feat), int(n_classes)))
 

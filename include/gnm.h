@@ -33,7 +33,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 17
+#define GNM_ABI_VERSION 18
 
 typedef void* gnm_stream_t;
 
@@ -359,6 +359,16 @@ int gnm_heads_ce(const float* g_f, int64_t ldg, int n_graphs, int n_layers, int 
                  float inv_count, float* c_logit, double* loss_acc, float* d_gf, int64_t ldd, float* const* d_weights,
                  float* const* d_biases, float* workspace, int64_t workspace_floats, unsigned int* counter,
                  gnm_stream_t stream);
+/* The two halves of gnm_heads_ce for callers that compute their own loss on c_logit (the reference's driver does,
+ * main.py:35): gnm_heads_fwd writes c_logit only; gnm_heads_bwd takes d loss / d c_logit [B, C] and writes d_gf and the
+ * head gradients (same workspace / counter contract as gnm_heads_ce). */
+int gnm_heads_fwd(const float* g_f, int64_t ldg, int n_graphs, int n_layers, int n_feat, int n_classes,
+                  const float* const* weights, const float* const* biases, const float* mask, float* c_logit,
+                  gnm_stream_t stream);
+int gnm_heads_bwd(const float* g_f, int64_t ldg, int n_graphs, int n_layers, int n_feat, int n_classes,
+                  const float* const* weights, const float* mask, const float* d_logit, float* d_gf, int64_t ldd,
+                  float* const* d_weights, float* const* d_biases, float* workspace, int64_t workspace_floats,
+                  unsigned int* counter, gnm_stream_t stream);
 int gnm_bce_logits(const float* logits, int64_t n, int64_t n_pos, float grad_scale, double loss_scale, double* loss_acc,
                    float* d_logits, gnm_stream_t stream);
 int gnm_small_gemm(const float* a, int64_t sam, int64_t sak, const float* b, int64_t sbk, int64_t sbn, float* c,

@@ -154,3 +154,29 @@ def test_adam_step_matches_torch_adam_over_several_steps_and_lr_changes():
     ops.adam_step(a, [g * 4.0], [0], ma, va, sa, lr, 0.9, 0.999, 1e-8, 0.0, 0.25)
     ops.adam_step(b2, [g], [0], mb, vb, sb, lr, 0.9, 0.999, 1e-8, 0.0, 1.0)
     assert_close(a[0], b2[0], 1e-6, "grad_scale")
+
+
+@pytest.mark.parametrize("b,layers,feat,classes,drop", [(1024, 5, 64, 2, 0.5), (3, 2, 8, 2, 0.0), (77, 3, 128, 4, 0.25)])
+def test_heads_forward_backward_halves_match_torch(b, layers, feat, classes, drop):
+    """gnm_heads_fwd / gnm_heads_bwd (the model's _HeadsFunction: the caller's own loss sits in between) against
+    nn.Linear + masks + autograd, and the module-level function against the reference's per-layer loop."""
+    from graph_neural_mapping_b200.models.graphcnn import _HeadsFunction
+    torch.manual_seed(b)
+    g_f = (torch.randn(b, layers * feat, device=DEV) * 2.0).requires_grad_(True)
+    ws = [torch.randn(classes, feat, device=DEV).mul_(0.2).requires_grad_(True) for _ in range(layers)]
+    bs = [torch.randn(classes, device=DEV).requires_grad_(True) for _ in range(layers)]
+    mask = torch.empty(layers, b, classes, device=DEV).bernoulli_(1 - drop).mul_(1 / (1 - drop)) if drop > 0 else None
+    score = 0
+    for l in range(layers):
+        y = torch.nn.functional.linear(g_f[:, l * feat:(l + 1) * feat], ws[l], bs[l])
+        score = score + (y * mask[l] if mask is not None else y)
+    go = torch.randn(b, classes, device=DEV)
+    ref = torch.autograd.grad(score, [g_f] + ws + bs, go)
+    g2 = g_f.detach().clone().requires_grad_(True)
+    ws2 = [w.detach().clone().requires_grad_(True) for w in ws]
+    bs2 = [x.detach().clone().requires_grad_(True) for x in bs]
+    out = _HeadsFunction.apply(g2, mask, layers, *(ws2 + bs2))
+    assert_close(out, score.detach(), 2e-5, "c_logit")
+    got = torch.autograd.grad(out, [g2] + ws2 + bs2, go)
+    for a, r, nm in zip(got, ref, ["d g_f"] + ["dW"] * layers + ["db"] * layers):
+        assert_close(a, r, 5e-5, nm)
