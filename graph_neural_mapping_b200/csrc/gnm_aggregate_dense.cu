@@ -306,7 +306,7 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
                             int n_max, const float* src, int64_t ld_src, const int32_t* src_map, float* dst,
                             int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
                             const float* aff_coef, const float* aff_z, int64_t ld_aff_z, const GnmReluBnBwdFuse* fuse,
-                            int b_shared, double* out_stats, cudaStream_t stream);
+                            int b_shared, double* out_stats, const gnm_bn_tail* tail, cudaStream_t stream);
 
 extern "C" int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr,
                                    int n_graphs, int n_max, const float* src, int64_t ld_src, const int32_t* src_map,
@@ -322,7 +322,7 @@ extern "C" int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* no
     if (impl != 1) {
         const int rc = gnm_launch_aggregate_tc(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, ld_src, src_map, dst,
                                                ld_dst, n_feat, mode, eps, bias, nullptr, nullptr, 0, nullptr, 0, nullptr,
-                                               gnm_cast_stream(stream));
+                                               nullptr, gnm_cast_stream(stream));
         if (rc == GNM_OK || impl == 2 || (rc != GNM_ERR_TOO_LARGE && rc != GNM_ERR_ALIGN)) return rc;
     }
     AggDenseParams p;
@@ -359,7 +359,7 @@ extern "C" int gnm_aggregate_dense_affine(const int64_t* bitmap_addr, const int3
     if (!bitmap_addr || !node_off || !dy || !z || !coef || !dst || (mode != 0 && !rowptr)) return GNM_ERR_BAD_ARG;
     if ((n_feat % 4) || (ld_dy % 4) || (ld_dst % 4) || !gnm_aligned16(dy) || !gnm_aligned16(dst)) return GNM_ERR_ALIGN;
     return gnm_launch_aggregate_tc(bitmap_addr, node_off, rowptr, n_graphs, n_max, dy, ld_dy, nullptr, dst, ld_dst, n_feat,
-                                   mode, nullptr, nullptr, coef, z, ld_z, nullptr, 0, nullptr, gnm_cast_stream(stream));
+                                   mode, nullptr, nullptr, coef, z, ld_z, nullptr, 0, nullptr, nullptr, gnm_cast_stream(stream));
 }
 
 /* Layer 0 on one-hot inputs when every graph of the batch carries the SAME injective tag sequence (util.py:106-116: one
@@ -372,7 +372,8 @@ extern "C" int gnm_aggregate_dense_affine(const int64_t* bitmap_addr, const int3
 extern "C" int gnm_aggregate_dense_table(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr,
                                          int n_graphs, int n_max, const float* table, int64_t ld_table,
                                          const int32_t* tags, float* dst, int64_t ld_dst, int n_feat, int mode,
-                                         const float* eps, const float* bias, double* out_stats, gnm_stream_t stream) {
+                                         const float* eps, const float* bias, double* out_stats, const gnm_bn_tail* tail,
+                                         gnm_stream_t stream) {
     if (n_graphs < 0 || n_max < 0 || n_feat < 0 || mode < 0 || mode > 1) return GNM_ERR_BAD_ARG;
     if (n_graphs == 0 || n_max == 0 || n_feat == 0) return GNM_OK;
     if (!bitmap_addr || !node_off || !table || !tags || !dst || (mode != 0 && !rowptr)) return GNM_ERR_BAD_ARG;
@@ -380,7 +381,7 @@ extern "C" int gnm_aggregate_dense_table(const int64_t* bitmap_addr, const int32
         (bias && !gnm_aligned16(bias)))
         return GNM_ERR_ALIGN;
     return gnm_launch_aggregate_tc(bitmap_addr, node_off, rowptr, n_graphs, n_max, table, ld_table, tags, dst, ld_dst,
-                                   n_feat, mode, eps, bias, nullptr, nullptr, 0, nullptr, 1, out_stats,
+                                   n_feat, mode, eps, bias, nullptr, nullptr, 0, nullptr, 1, out_stats, tail,
                                    gnm_cast_stream(stream));
 }
 
@@ -407,5 +408,5 @@ extern "C" int gnm_aggregate_dense_relu_bn_bwd(const int64_t* bitmap_addr, const
     f.ld_dpooled = ld_dpooled; f.pool_scale = pool_scale; f.d_score = d_score; f.u = u; f.ldu = ldu; f.d_neg = d_neg;
     f.ld_dneg = ld_dneg; f.n_neg = n_neg; f.stats = stats;
     return gnm_launch_aggregate_tc(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, ld_src, nullptr, dy, lddy, n_feat,
-                                   mode, eps, nullptr, nullptr, nullptr, 0, &f, 0, nullptr, gnm_cast_stream(stream));
+                                   mode, eps, nullptr, nullptr, nullptr, 0, &f, 0, nullptr, nullptr, gnm_cast_stream(stream));
 }

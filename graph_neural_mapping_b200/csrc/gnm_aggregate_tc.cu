@@ -30,6 +30,7 @@
 
 #include "gnm_common.cuh"
 #include "gnm_tc.cuh"
+#include "gnm_bn_tail.cuh"
 
 namespace {
 
@@ -77,6 +78,7 @@ struct AggTcParams {
     // stay resident; out_stats (nullable) += [sum, sum of squares] per column of the rows written (BatchNorm statistics)
     int b_shared;
     double* out_stats;
+    BnTailDev tail;              // BatchNorm tail on out_stats (forward) or r_stats (fused backward); kind 0: none
     long long* dbg;              // nullable: per-CTA wait/busy cycle counters (profiling aid)
 };
 
@@ -532,6 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
     }
+    bn_tail_run(p.tail);
 }
 
 }  // namespace
@@ -543,8 +546,9 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
                             int n_max, const float* src, int64_t ld_src, const int32_t* src_map, float* dst,
                             int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
                             const float* aff_coef, const float* aff_z, int64_t ld_aff_z, const GnmReluBnBwdFuse* fuse,
-                            int b_shared, double* out_stats, cudaStream_t stream) {
+                            int b_shared, double* out_stats, const gnm_bn_tail* tail, cudaStream_t stream) {
     if (n_max > TC_MAX_NODES) return GNM_ERR_TOO_LARGE;
+    if (tail != nullptr && out_stats == nullptr && (fuse == nullptr || fuse->stats == nullptr)) return GNM_ERR_BAD_ARG;
     if ((out_stats != nullptr || b_shared) && (n_feat > TC_SLAB || fuse != nullptr || aff_coef != nullptr || mode == 2))
         return GNM_ERR_TOO_LARGE;              // one 64-wide slab per lane; a shared table has no per-graph row weights
     if (b_shared && src_map == nullptr) return GNM_ERR_BAD_ARG;
@@ -581,6 +585,8 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
         p.r_dneg = fuse->d_neg; p.ld_dneg = fuse->ld_dneg; p.r_nneg = fuse->n_neg; p.r_stats = fuse->stats;
     }
     p.b_shared = b_shared; p.out_stats = out_stats;
+    const int trc = bn_tail_args(tail, out_stats != nullptr ? out_stats : (fuse ? fuse->stats : nullptr), n_feat, &p.tail);
+    if (trc != GNM_OK) return trc;
     p.dbg = g_tc_dbg_host;
     p.n_slabs = (n_feat + TC_SLAB - 1) / TC_SLAB;
     p.kcores_max = ((n_max + 15) / 16) * 2;

@@ -23,6 +23,7 @@
 //     and CTA (same-address atomics serialise in L2).
 #include "gnm_common.cuh"
 #include "gnm_tc.cuh"
+#include "gnm_bn_tail.cuh"
 
 namespace {
 
@@ -46,6 +47,7 @@ struct LinTcParams {
     const float* bias; const float* in_scale; const float* in_shift;
     float* y; int64_t ldy;
     double* col_stats;
+    BnTailDev tail;              // BatchNorm finalisation of col_stats by the last CTA (kind 0: none)
     int n_rows, n_in, n_out;
 };
 
@@ -353,6 +355,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
     if (warp == LT_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }
+    bn_tail_run(p.tail);
 }
 
 }  // namespace
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
 // GNM_OK after launching; GNM_ERR_TOO_LARGE when the shape does not fit this kernel (caller uses the FFMA kernel)
 int gnm_launch_linear_tc(const float* x, int64_t ldx, int n_rows, int n_in, const float* w, int64_t ldw, int w_is_kn,
                          const float* bias, const float* in_scale, const float* in_shift, float* y, int64_t ldy,
-                         int n_out, double* col_stats, cudaStream_t stream) {
+                         int n_out, double* col_stats, const gnm_bn_tail* tail, cudaStream_t stream) {
     if (n_in > LT_F || n_out > LT_F || n_in < 1 || n_out < 1) return GNM_ERR_TOO_LARGE;
     int dev = 0, sms = 148, major = 0;
     cudaGetDevice(&dev);
@@ -370,6 +373,8 @@ int gnm_launch_linear_tc(const float* x, int64_t ldx, int n_rows, int n_in, cons
     LinTcParams p;
     p.x = x; p.ldx = ldx; p.w = w; p.ldw = ldw; p.w_is_kn = w_is_kn; p.bias = bias; p.in_scale = in_scale;
     p.in_shift = in_shift; p.y = y; p.ldy = ldy; p.col_stats = col_stats; p.n_rows = n_rows; p.n_in = n_in; p.n_out = n_out;
+    const int trc = bn_tail_args(tail, col_stats, n_out, &p.tail);
+    if (trc != GNM_OK) return trc;
     cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
     if (e != cudaSuccess) return (int)e;
     const int tiles = (n_rows + 127) / 128;

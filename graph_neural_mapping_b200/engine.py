@@ -343,7 +343,7 @@ class BatchStructure(object):
                                                 src, mode, eps, unit.z, unit.scale, unit.shift, unit.mean, unit.rstd,
                                                 d_pooled, self.pool_scale, d_score, u, d_neg, n_neg, dy, stats)
 
-    def aggregate_table(self, table, dst, mode, eps, bias, stats):
+    def aggregate_table(self, table, dst, mode, eps, bias, stats, tail=None):
         """Layer 0 as a row gather of `table` when every graph carries the same tag sequence: dst = Agg(table[tags]) (+ self
         term) + bias and stats += its column statistics, the table staying resident in the kernel's shared memory
         (ops.aggregate_dense_table); False, nothing launched, when the batch does not run on the tcgen05 kernel."""
@@ -353,7 +353,7 @@ class BatchStructure(object):
         if mode != 0 and self.has_isolated:
             return False
         return _ops.aggregate_dense_table(self.bitmap_addr, self.node_off, self.rowptr, self.n_graphs, self.n_max, table,
-                                          self.tags[:self.uniform_n], dst, mode, eps, bias, stats)
+                                          self.tags[:self.uniform_n], dst, mode, eps, bias, stats, tail)
 
     def aggregate_affine(self, dy, z, coef, dst, mode):
         """dst = Agg(coef[0]*dy + coef[1]*z + coef[2]) when the batch runs on the tcgen05 dense-block kernel (the affine
@@ -391,22 +391,32 @@ def layer_units(model, layer):
 
 
 def flat_params(model):
-    ps = [model.eps, model.disc.f_k.weight, model.disc.f_k.bias]
-    for layer in range(model.num_layers):
-        for lin, bn in layer_units(model, layer):
-            ps.extend([lin.weight, lin.bias, bn.weight, bn.bias])
+    """The encoder / discriminator parameters in kernel order. The list of Parameter OBJECTS is cached on the model
+    (walking the module tree costs ~0.1 ms and this runs several times per step on the host's critical path);
+    `.to()` / `load_state_dict` keep the objects, assigning a new nn.Parameter to a submodule needs
+    `model.release_graphs()` (which also drops this cache)."""
+    ps = model.__dict__.get("_gnm_flat_params")
+    if ps is None:
+        ps = [model.eps, model.disc.f_k.weight, model.disc.f_k.bias]
+        for layer in range(model.num_layers):
+            for lin, bn in layer_units(model, layer):
+                ps.extend([lin.weight, lin.bias, bn.weight, bn.bias])
+        model.__dict__["_gnm_flat_params"] = ps
     return ps
 
 
 def flat_buffers(model):
     """The BatchNorm buffers the kernels update in place (same set and order as `model.buffers()`, without walking the
     module tree: this runs every step to check that a captured CUDA graph still points at the live tensors)."""
+    bns = model.__dict__.get("_gnm_flat_bns")
+    if bns is None:
+        bns = [bn for layer in range(model.num_layers) for _, bn in layer_units(model, layer)]
+        model.__dict__["_gnm_flat_bns"] = bns
     bs = []
-    for layer in range(model.num_layers):
-        for _, bn in layer_units(model, layer):
-            for t in (bn.running_mean, bn.running_var, bn.num_batches_tracked):
-                if t is not None:
-                    bs.append(t)
+    for bn in bns:               # buffers are re-read every time: load_state_dict / .to() may replace the tensors
+        for t in (bn.running_mean, bn.running_var, bn.num_batches_tracked):
+            if t is not None:
+                bs.append(t)
     return bs
 
 
@@ -459,13 +469,45 @@ class _ZeroPool(object):
         return buf[off:off + int(n)], len(self.f64_chunks) - 1, off
 
 
-def _bn_affine(unit, stats, count, training, comm):
+FOLD_BN_TAILS = True           # A/B switch: BatchNorm finalisation in the last CTA of the kernel producing the statistics
+
+
+def _bn_forward_tail(unit, stats, count, training, comm):
+    """Prepare the BatchNorm of `unit` (its Linear's output z is about to be produced together with `stats`): allocates
+    scale / shift / mean / rstd and returns the ops.BnTail the producer kernel may run in its last CTA - or None when
+    this BatchNorm uses running statistics or the exchange needs NCCL. `_bn_affine(..., done=taken)` completes it."""
     dev = unit.z.device
     f = unit.z.shape[1]
     buf = torch.empty(4, f, dtype=torch.float32, device=dev)
     unit.scale, unit.shift, unit.mean, unit.rstd = buf[0], buf[1], buf[2], buf[3]
     bn = unit.bn
     use_batch = training or not bn.track_running_stats
+    if not (FOLD_BN_TAILS and use_batch and hasattr(_ops, "BnTail")):
+        return None
+    p2p = comm.p2p_for(stats) if comm.world > 1 else None
+    if comm.world > 1 and p2p is None:
+        return None                   # the sums go through NCCL / gloo first
+    track = bn.track_running_stats and training
+    if track and bn.momentum is None:
+        return None
+    return _ops.BnTail(_ops.BnTail.FINALIZE, float(count * comm.world), unit.gamma, unit.mean, unit.rstd, beta=unit.beta,
+                       eps=bn.eps, momentum=bn.momentum if track else 0.0, running_mean=bn.running_mean if track else None,
+                       running_var=bn.running_var if track else None, nbt=bn.num_batches_tracked if track else None,
+                       scale=unit.scale, shift=unit.shift, p2p=p2p)
+
+
+def _bn_affine(unit, stats, count, training, comm, done=False):
+    dev = unit.z.device
+    f = unit.z.shape[1]
+    if getattr(unit, "scale", None) is None:
+        buf = torch.empty(4, f, dtype=torch.float32, device=dev)
+        unit.scale, unit.shift, unit.mean, unit.rstd = buf[0], buf[1], buf[2], buf[3]
+    bn = unit.bn
+    use_batch = training or not bn.track_running_stats
+    if done:
+        # the kernel that produced `stats` already ran gnm_bn_finalize's arithmetic in its last CTA
+        unit.count = float(count * comm.world)
+        return use_batch
     if use_batch:
         # data parallel: the global-batch sums. Over NVLink peer memory inside bn_finalize itself when the ranks share
         # a P2P communicator (dist.setup_p2p), else an NCCL / gloo all-reduce in front of it.
@@ -545,13 +587,17 @@ def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm, m
         for j, u in enumerate(units):
             n_out = u.w.shape[0]
             u.z = torch.empty(M, n_out, dtype=torch.float32, device=dev)
+            u.scale = None
             stats = zp.f64(2 * n_out)[0]
+            tail = _bn_forward_tail(u, stats, M, training, comm)
+            done = False
             if j == 0:
                 if layer == 0 and use_gather0:
                     # first layer as a row gather of W1^T (X_concat is one-hot): no dense X, no GEMM
                     w1t = u.w.detach().t().contiguous()
                     sv.w1t = w1t
-                    if not bs.aggregate_table(w1t, u.z, 1 if average else 0, eps_l, u.b, stats):
+                    done = tail is not None and bs.aggregate_table(w1t, u.z, 1 if average else 0, eps_l, u.b, stats, tail)
+                    if not done and not bs.aggregate_table(w1t, u.z, 1 if average else 0, eps_l, u.b, stats):
                         bs.aggregate(w1t, bs.tags, u.z, 1 if average else 0, eps_l, u.b)
                         _ops.col_stats(u.z, stats)
                     u.x_in = None
@@ -569,13 +615,13 @@ def run_forward(model, bs, neg_idx, training, with_dgi, x_dense, params, comm, m
                         sv.max_state[layer] = (amax, cmin)
                     else:
                         bs.aggregate(src, None, pooled, 1 if average else 0, eps_l, None)
-                    _ops.linear(pooled, u.w, False, u.b, None, None, u.z, stats)
+                    done = bool(_ops.linear(pooled, u.w, False, u.b, None, None, u.z, stats, tail))
                     u.x_in = pooled
             else:
                 p = units[j - 1]
-                _ops.linear(p.z, u.w, False, u.b, p.scale, p.shift, u.z, stats)
+                done = bool(_ops.linear(p.z, u.w, False, u.b, p.scale, p.shift, u.z, stats, tail))
                 u.x_in = None          # recomputed from p.z with p's affine + ReLU
-            _bn_affine(u, stats, M, training, comm)
+            _bn_affine(u, stats, M, training, comm, done=done)
         last = units[-1]
         _ops.bn_relu_readout(last.z, last.scale, last.shift, h_all[layer], bs.node_off, B, bs.pool_scale,
                              g_f[:, layer * F:(layer + 1) * F])

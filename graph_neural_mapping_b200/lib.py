@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libgnm.so")
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 _c_i32 = ctypes.c_int
 _c_i64 = ctypes.c_int64
@@ -30,7 +30,7 @@ SIGNATURES = {
     "gnm_aggregate": [_p, _p, _c_i32, _p, _c_i64, _p, _p, _c_i64, _c_i32, _c_i32, _p, _p, _p],
     "gnm_bitmap_build": [_p, _p, _p, _p, _c_i32, _p, _p, _p],
     "gnm_aggregate_dense": [_p, _p, _p, _c_i32, _c_i32, _p, _c_i64, _p, _p, _c_i64, _c_i32, _c_i32, _p, _p, _c_i32, _p],
-    "gnm_aggregate_dense_table": [_p, _p, _p, _c_i32, _c_i32, _p, _c_i64, _p, _p, _c_i64, _c_i32, _c_i32, _p, _p, _p, _p],
+    "gnm_aggregate_dense_table": [_p, _p, _p, _c_i32, _c_i32, _p, _c_i64, _p, _p, _c_i64, _c_i32, _c_i32, _p, _p, _p, _p, _p],
     "gnm_aggregate_tc_status": [_p],
     "gnm_aggregate_tc_set_debug": [_p],
     "gnm_dot_rows": [_p, _c_i64, _p, _c_i64, _p, _c_i32, _c_i32, _p, _p],
@@ -38,7 +38,7 @@ SIGNATURES = {
     "gnm_scatter_rows_workspace": [_c_i32, _c_i32, _c_i32],
     "gnm_rows_period_sum": [_p, _c_i64, _c_i32, _c_i32, _c_i32, _p, _p, _c_i64, _c_i32, _p, _c_i64, _p],
     "gnm_rows_period_workspace": [_c_i32, _c_i32, _c_i32],
-    "gnm_linear": [_p, _c_i64, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p, _p, _p, _p, _c_i64, _c_i32, _p, _p],
+    "gnm_linear": [_p, _c_i64, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p, _p, _p, _p, _c_i64, _c_i32, _p, _p, _p],
     "gnm_set_linear_impl": [_c_i32],
     "gnm_linear_wgrad": [_p, _c_i64, _p, _c_i64, _c_i32, _c_i32, _c_i32, _p, _p, _p, _c_i64, _p, _p],
     "gnm_bn_bwd_coeffs": [_p, _c_f64, _p, _p, _p, _p, _c_i32, _p, _p],

@@ -107,6 +107,13 @@ class GIN_InfoMaxReg(nn.Module):
         """Drop the captured CUDA graphs (and their static buffers); they are re-captured on demand."""
         self._plans.clear()
         self._warm.clear()
+        self.__dict__.pop("_gnm_flat_params", None)
+        self.__dict__.pop("_gnm_flat_bns", None)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_gnm_flat_params", None)
+        self.__dict__.pop("_gnm_flat_bns", None)
+        return super()._apply(fn, *args, **kwargs)
 
     # ---- internals --------------------------------------------------------------------------
     def _graph_store(self):

@@ -81,6 +81,51 @@ def kernels_launched():
     return kernels_recorded() + REPLAYED[0]
 
 
+class _BnTailStruct(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("count", ctypes.c_double), ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+                ("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("running_mean", ctypes.c_void_p),
+                ("running_var", ctypes.c_void_p), ("num_batches_tracked", ctypes.c_void_p), ("scale", ctypes.c_void_p),
+                ("shift", ctypes.c_void_p), ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p), ("coef", ctypes.c_void_p),
+                ("comm", ctypes.c_void_p), ("counter", ctypes.c_void_p)]
+
+
+_TAIL_COUNTERS = {}
+
+
+def _tail_counter(device):
+    """One zero-initialised ticket per device: kernels of one stream run one after the other and leave it zero."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    t = _TAIL_COUNTERS.get(key)
+    if t is None:
+        t = _TAIL_COUNTERS[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return t
+
+
+class BnTail(object):
+    """gnm_bn_tail of include/gnm.h: the BatchNorm finalisation a stats-producing kernel runs in its last CTA."""
+
+    FINALIZE, BWD_COEFFS = 1, 2
+
+    def __init__(self, kind, count, gamma, mean, rstd, beta=None, eps=0.0, momentum=0.0, running_mean=None, running_var=None,
+                 nbt=None, scale=None, shift=None, coef=None, p2p=None):
+        dev = mean.device
+        self.keep = (gamma, beta, running_mean, running_var, nbt, scale, shift, mean, rstd, coef, p2p, _tail_counter(dev))
+
+        def a(t):
+            return t.data_ptr() if t is not None else None
+        self.struct = _BnTailStruct(int(kind), float(count), a(gamma), a(beta), float(eps), float(momentum), a(running_mean),
+                                    a(running_var), a(nbt), a(scale), a(shift), a(mean), a(rstd), a(coef),
+                                    ctypes.addressof(p2p.struct) if p2p is not None else None,
+                                    _tail_counter(dev).data_ptr())
+
+    def ref(self):
+        return ctypes.byref(self.struct)
+
+
+def _tail_ref(tail):
+    return tail.ref() if tail is not None else None
+
+
 # ---- structure ---------------------------------------------------------------------------
 
 def csr_build(edges, edge_off, node_off, n_graphs, n_max, total_nodes, add_self_loops, local_cols):
@@ -160,7 +205,8 @@ def aggregate_dense(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, src_map
     return dst
 
 
-def aggregate_dense_table(bitmap_addr, node_off, rowptr, n_graphs, n_max, table, tags, dst, mode, eps, bias, out_stats):
+def aggregate_dense_table(bitmap_addr, node_off, rowptr, n_graphs, n_max, table, tags, dst, mode, eps, bias, out_stats,
+                          tail=None):
     """z0 = Agg(table[tags]) (+ self term) + bias with one table shared by every graph, + column statistics of z0
     (include/gnm.h: gnm_aggregate_dense_table). Returns False, nothing launched, when the batch does not fit it."""
     tp, ldt = _mat(table)
@@ -168,7 +214,7 @@ def aggregate_dense_table(bitmap_addr, node_off, rowptr, n_graphs, n_max, table,
     rc = _lib().gnm_aggregate_dense_table(_ptr(bitmap_addr, torch.int64), _ptr(node_off, torch.int32), _ptr(rowptr, torch.int32),
                                           n_graphs, n_max, tp, ldt, _ptr(tags, torch.int32), dp, ldd, int(dst.shape[1]),
                                           int(mode), _ptr(eps, torch.float32), _ptr(bias, torch.float32),
-                                          _ptr(out_stats, torch.float64), _stream(dst))
+                                          _ptr(out_stats, torch.float64), _tail_ref(tail), _stream(dst))
     if rc in (-2, -3):
         LAUNCHES[0] -= 1
         return False
@@ -452,7 +498,9 @@ def set_linear_impl(impl):
     _libmod.check(_lib().gnm_set_linear_impl(int(impl)), "gnm_set_linear_impl")
 
 
-def linear(x, w, w_is_kn, bias, in_scale, in_shift, y, col_stats):
+def linear(x, w, w_is_kn, bias, in_scale, in_shift, y, col_stats, tail=None):
+    """tail: BnTail(FINALIZE) run by the kernel's last CTA on col_stats. Returns True when the tail was taken; False
+    when the shape runs on a kernel without tails (the Linear itself was still computed: call bn_finalize)."""
     xp, ldx = _mat(x)
     wp, ldw = _mat(w)
     yp, ldy = _mat(y)
@@ -461,10 +509,17 @@ def linear(x, w, w_is_kn, bias, in_scale, in_shift, y, col_stats):
     exp = (n_in, n_out) if w_is_kn else (n_out, n_in)
     if tuple(w.shape) != exp:
         raise RuntimeError("linear: weight shape %s does not match x %s -> y %s" % (tuple(w.shape), tuple(x.shape), tuple(y.shape)))
-    _libmod.check(_lib().gnm_linear(xp, ldx, int(x.shape[0]), n_in, wp, ldw, int(w_is_kn), _ptr(bias, torch.float32),
-                                    _ptr(in_scale, torch.float32), _ptr(in_shift, torch.float32), yp, ldy, n_out,
-                                    _ptr(col_stats, torch.float64), _stream(y)), "gnm_linear")
-    return y
+    args = (xp, ldx, int(x.shape[0]), n_in, wp, ldw, int(w_is_kn), _ptr(bias, torch.float32),
+            _ptr(in_scale, torch.float32), _ptr(in_shift, torch.float32), yp, ldy, n_out, _ptr(col_stats, torch.float64))
+    if tail is not None:
+        rc = _lib().gnm_linear(*args, tail.ref(), _stream(y))
+        if rc == 0:
+            return True
+        if rc != -2:
+            _libmod.check(rc, "gnm_linear")
+        LAUNCHES[0] -= 1                    # GNM_ERR_TOO_LARGE: nothing was launched, run without the tail
+    _libmod.check(_lib().gnm_linear(*args, None, _stream(y)), "gnm_linear")
+    return False
 
 
 def linear_wgrad(dz, x, in_scale, in_shift, dw, dbias):

@@ -33,7 +33,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 18
+#define GNM_ABI_VERSION 19
 
 typedef void* gnm_stream_t;
 
@@ -50,6 +50,38 @@ typedef struct gnm_p2p_comm {
 #define GNM_P2P_MAX_WORLD 16
 #define GNM_P2P_MAX_DOUBLES 256
 #define GNM_P2P_HANDLE_BYTES 64
+
+/* BatchNorm finalisation folded into the kernel that PRODUCES the batch statistics ("tail"): host-side POD passed by
+ * pointer (nullable = no tail) to gnm_linear / gnm_aggregate_dense_table (forward sums -> gnm_bn_finalize's outputs) and
+ * to gnm_relu_bn_bwd_reduce / gnm_aggregate_dense_relu_bn_bwd / gnm_linear_bwd (backward sums -> gnm_bn_bwd_coeffs' output).
+ * The last CTA of the producer to finish does the arithmetic of the separate kernel - including, data parallel, the
+ * peer-memory all-reduce of the sums - so 20 few-microsecond kernels per training step, each a serial link between
+ * two big ones, leave the launch list. Only the tcgen05 / vectorised producers honour a tail; an entry point that
+ * cannot returns GNM_ERR_TOO_LARGE before launching anything when one is passed (call the separate kernel then).
+ *   kind FINALIZE: count, gamma, beta (nullable), eps, momentum, running_mean / running_var / num_batches_tracked
+ *     (nullable), outputs scale, shift, mean, rstd - exactly gnm_bn_finalize;
+ *   kind BWD_COEFFS: count, gamma, inputs mean, rstd, output coef [3 * n_feat] - exactly gnm_bn_bwd_coeffs;
+ *   comm: nullable peer-memory communicator; counter: DEVICE uint32, zero on entry, left zero. */
+#define GNM_BN_TAIL_FINALIZE 1
+#define GNM_BN_TAIL_BWD_COEFFS 2
+typedef struct gnm_bn_tail {
+    int kind;
+    double count;
+    const float* gamma;
+    const float* beta;
+    float eps;
+    float momentum;
+    float* running_mean;
+    float* running_var;
+    int64_t* num_batches_tracked;
+    float* scale;
+    float* shift;
+    float* mean;
+    float* rstd;
+    float* coef;
+    const gnm_p2p_comm* comm;
+    unsigned int* counter;
+} gnm_bn_tail;
 
 int gnm_abi_version(void);
 const char* gnm_error_string(int code);
@@ -142,7 +174,7 @@ int gnm_aggregate_dense(const int64_t* bitmap_addr, const int32_t* node_off, con
 int gnm_aggregate_dense_table(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
                               int n_max, const float* table, int64_t ld_table, const int32_t* tags, float* dst,
                               int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias, double* out_stats,
-                              gnm_stream_t stream);
+                              const gnm_bn_tail* tail, gnm_stream_t stream);
 
 int gnm_aggregate_dense_affine(const int64_t* bitmap_addr, const int32_t* node_off, const int32_t* rowptr, int n_graphs,
                                int n_max, const float* dy, int64_t ld_dy, const float* z, int64_t ld_z, const float* coef,
@@ -196,7 +228,7 @@ int64_t gnm_rows_period_workspace(int n_rows, int n_feat, int period);
 int gnm_linear(const float* x, int64_t ldx, int n_rows, int n_in,
                const float* w, int64_t ldw, int w_is_kn, const float* bias,
                const float* in_scale, const float* in_shift,
-               float* y, int64_t ldy, int n_out, double* col_stats, gnm_stream_t stream);
+               float* y, int64_t ldy, int n_out, double* col_stats, const gnm_bn_tail* tail, gnm_stream_t stream);
 
 /* gnm_linear implementation switch (process-wide A/B aid; the only global setting of the library):
  * 0 = auto (tcgen05 kernel for n_in, n_out <= 64 and n_rows >= 4096, fp32 FFMA kernel otherwise), 1 = FFMA only,

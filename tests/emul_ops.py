@@ -229,7 +229,7 @@ def _act(x, sc, sh):
     return x if sc is None else torch.relu(x * sc + sh)
 
 
-def linear(x, w, w_is_kn, bias, in_scale, in_shift, y, col_stats):
+def linear(x, w, w_is_kn, bias, in_scale, in_shift, y, col_stats, tail=None):
     a = _act(x, in_scale, in_shift).double()
     out = a @ (w.double() if w_is_kn else w.double().t())
     if bias is not None:
@@ -239,7 +239,7 @@ def linear(x, w, w_is_kn, bias, in_scale, in_shift, y, col_stats):
         n = y.shape[1]
         col_stats[:n] += y.double().sum(0)
         col_stats[n:] += (y.double() ** 2).sum(0)
-    return y
+    return False            # no BatchNorm tail taken (ops.linear's contract)
 
 
 def linear_wgrad(dz, x, in_scale, in_shift, dw, dbias):
@@ -425,5 +425,5 @@ def dgi_neg_grad(neg_idx, s2, u, d_neg):
     return d_neg
 
 
-def aggregate_dense_table(bitmap_addr, node_off, rowptr, n_graphs, n_max, table, tags, dst, mode, eps, bias, out_stats):
+def aggregate_dense_table(bitmap_addr, node_off, rowptr, n_graphs, n_max, table, tags, dst, mode, eps, bias, out_stats, tail=None):
     return False          # the stand-in has no shared-table kernel: the engine falls back to aggregate + col_stats

@@ -886,3 +886,47 @@ def test_aggregate_dense_table_shared_rows_and_column_stats(n, b, f, mode, use_e
     got2 = torch.empty(m, f, device=DEV)
     assert ops.aggregate_dense_table(addr, no, rp, b, n, table, tags1, got2, mode, eps, bias, None)
     assert torch.equal(got2, got)
+
+
+@pytest.mark.parametrize("m,n_in,n_out,pro", [(8192, 64, 64, True), (40000, 64, 64, False), (5000, 32, 48, True)])
+def test_linear_with_batchnorm_tail_equals_linear_then_bn_finalize(m, n_in, n_out, pro):
+    """gnm_linear's BatchNorm tail (last CTA of the tcgen05 kernel runs gnm_bn_finalize's arithmetic on the statistics it
+    just produced) against the two separate kernels: affine, saved statistics, running buffers, num_batches_tracked."""
+    torch.manual_seed(m)
+    x = torch.randn(m, n_in, device=DEV) * 2 + 0.3
+    w = torch.randn(n_out, n_in, device=DEV) * 0.2
+    b = torch.randn(n_out, device=DEV)
+    sc = (torch.rand(n_in, device=DEV) + 0.5) if pro else None
+    sh = torch.randn(n_in, device=DEV) if pro else None
+    gamma, beta = torch.rand(n_out, device=DEV) + 0.5, torch.randn(n_out, device=DEV)
+
+    def fresh():
+        return (torch.zeros(2 * n_out, dtype=torch.float64, device=DEV), torch.empty(m, n_out, device=DEV),
+                torch.empty(4, n_out, device=DEV), torch.full((n_out,), 0.25, device=DEV), torch.full((n_out,), 1.5, device=DEV),
+                torch.tensor(3, dtype=torch.int64, device=DEV))
+    st1, y1, o1, rm1, rv1, nbt1 = fresh()
+    ops.linear(x, w, False, b, sc, sh, y1, st1)
+    ops.bn_finalize(st1, float(m), gamma, beta, 1e-5, 0.1, rm1, rv1, nbt1, o1[0], o1[1], o1[2], o1[3])
+    st2, y2, o2, rm2, rv2, nbt2 = fresh()
+    tail = ops.BnTail(ops.BnTail.FINALIZE, float(m), gamma, o2[2], o2[3], beta=beta, eps=1e-5, momentum=0.1, running_mean=rm2,
+                      running_var=rv2, nbt=nbt2, scale=o2[0], shift=o2[1])
+    before = ops.launch_counts()
+    assert ops.linear(x, w, False, b, sc, sh, y2, st2, tail) is True
+    ran = {k: v - before[k] for k, v in ops.launch_counts().items()}
+    assert ran["linear_tc"] == 1 and ran["other"] == 0, ran            # one kernel, no separate finalize
+    assert torch.equal(y1, y2)
+    assert_close(o2, o1, 1e-6, "scale / shift / mean / rstd")
+    assert_close(rm2, rm1, 1e-6, "running_mean")
+    assert_close(rv2, rv1, 1e-6, "running_var")
+    assert int(nbt2) == int(nbt1) == 4
+    # the ticket counter is left at zero: a second launch behaves the same
+    st3, y3, o3, rm3, rv3, nbt3 = fresh()
+    tail3 = ops.BnTail(ops.BnTail.FINALIZE, float(m), gamma, o3[2], o3[3], beta=beta, eps=1e-5, momentum=0.1, running_mean=rm3,
+                       running_var=rv3, nbt=nbt3, scale=o3[0], shift=o3[1])
+    assert ops.linear(x, w, False, b, sc, sh, y3, st3, tail3) is True
+    assert_close(o3, o1, 1e-6, "second launch")
+    # small problems run on the FFMA kernel, which has no tail: the call reports it and the Linear is still computed
+    xs = x[:100].contiguous()
+    st4, y4 = torch.zeros(2 * n_out, dtype=torch.float64, device=DEV), torch.empty(100, n_out, device=DEV)
+    assert ops.linear(xs, w, False, b, sc, sh, y4, st4, tail3) is False
+    assert_close(y4, y1[:100], 2e-5, "fallback result")
