@@ -307,6 +307,16 @@ extern "C" int gnm_rowdot_score(const float* h, int64_t ldh, int n_rows, int n_f
 
 extern "C" int gnm_abi_version(void) { return GNM_ABI_VERSION; }
 
+/* 0 = the stream is not capturing, 1 = capturing, 2 = its capture was invalidated (by an operation that is not permitted
+ * under capture); debugging aid for CUDA-graph capture of the step. */
+extern "C" int gnm_stream_capture_status(gnm_stream_t stream, int* status) {
+    cudaStreamCaptureStatus s = cudaStreamCaptureStatusNone;
+    cudaError_t e = cudaStreamIsCapturing(gnm_cast_stream(stream), &s);
+    if (status) *status = (int)s;
+    if (e != cudaSuccess) { cudaGetLastError(); if (status && e == cudaErrorStreamCaptureInvalidated) *status = 2; }
+    return GNM_OK;
+}
+
 static int64_t g_launch_counts[GNM_K_FAMILIES] = {0};
 void gnm_count_launch(int family) {
     if (family >= 0 && family < GNM_K_FAMILIES) __atomic_fetch_add(&g_launch_counts[family], 1, __ATOMIC_RELAXED);

@@ -191,44 +191,67 @@ __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict
 //   SIGMOID_A: pro = sigmoid (and the activated A is also written to a_out, row-major [M, K]);
 //   DSIG_EPI:  C = add[m,n] (nullable) + acc * s[m,n] * (1 - s[m,n])   (backward through c = sigmoid(g_f)).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int SG_T = 64, SG_K = 16;
+constexpr int SG_T = 64, SG_K = 16, SG_P = SG_T + 4;      // 64 x 64 tile, 16-deep k slices, rows padded to 68 floats
 
+// One operand tile (SG_K x SG_T, k-major in shared memory) from a strided matrix: element (i, k) at p[i*si + k*sk],
+// i = row of A / column of B. 128-bit loads along whichever axis is contiguous when the tile is interior and aligned.
+template <bool SIGMOID>
+__device__ __forceinline__ void sg_load_tile(float (*dst)[SG_P], const float* __restrict__ p, int64_t si, int64_t sk, int i0,
+                                             int k0, int n_i, int n_k, float* __restrict__ act_out, int64_t ld_act,
+                                             bool write_act) {
+    const int t = threadIdx.x;
+    const bool interior = i0 + SG_T <= n_i && k0 + SG_K <= n_k;
+    if (sk == 1 && interior && (si & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        const int i = t >> 2, k4 = (t & 3) * 4;                    // 64 rows x 4 float4 along k
+        float4 v = *reinterpret_cast<const float4*>(p + (int64_t)(i0 + i) * si + k0 + k4);
+        if (SIGMOID) {
+            v.x = 1.f / (1.f + expf(-v.x)); v.y = 1.f / (1.f + expf(-v.y));
+            v.z = 1.f / (1.f + expf(-v.z)); v.w = 1.f / (1.f + expf(-v.w));
+            if (write_act) *reinterpret_cast<float4*>(act_out + (int64_t)(i0 + i) * ld_act + k0 + k4) = v;
+        }
+        dst[k4][i] = v.x; dst[k4 + 1][i] = v.y; dst[k4 + 2][i] = v.z; dst[k4 + 3][i] = v.w;
+    } else if (si == 1 && interior && (sk & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && !SIGMOID) {
+        const int k = t >> 4, i4 = (t & 15) * 4;                   // 16 k x 16 float4 along i
+        *reinterpret_cast<float4*>(&dst[k][i4]) = *reinterpret_cast<const float4*>(p + (int64_t)(k0 + k) * sk + i0 + i4);
+    } else {
+        for (int e = t; e < SG_K * SG_T; e += 256) {
+            int k, i;
+            if (sk == 1) { k = e % SG_K; i = e / SG_K; } else { i = e % SG_T; k = e / SG_T; }
+            float v = 0.f;
+            if (i0 + i < n_i && k0 + k < n_k) {
+                v = p[(int64_t)(i0 + i) * si + (int64_t)(k0 + k) * sk];
+                if (SIGMOID) {
+                    v = 1.f / (1.f + expf(-v));
+                    if (write_act) act_out[(int64_t)(i0 + i) * ld_act + k0 + k] = v;
+                }
+            }
+            dst[k][i] = v;
+        }
+    }
+}
+
+// grid = (n tiles, m tiles, k splits); with more than one k split the partial products are added with atomics into a
+// C that the host entry zeroed (the epilogue variants run unsplit).
 template <bool SIGMOID_A, bool DSIG_EPI>
 __global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict__ a, int64_t sam, int64_t sak,
                                                          const float* __restrict__ b, int64_t sbk, int64_t sbn,
                                                          float* __restrict__ c, int64_t ldc, int m_tot, int n_tot, int k_tot,
-                                                         float* __restrict__ a_out, int64_t lda_out,
+                                                         int k_per_split, float* __restrict__ a_out, int64_t lda_out,
                                                          const float* __restrict__ epi_s, int64_t lds,
                                                          const float* __restrict__ epi_add, int64_t ldadd) {
-    __shared__ float sa[SG_K][SG_T + 1];
-    __shared__ float sb[SG_K][SG_T + 1];
+    __shared__ __align__(16) float sa[SG_K][SG_P];
+    __shared__ __align__(16) float sb[SG_K][SG_P];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.y * SG_T, n0 = blockIdx.x * SG_T;
+    const int k_begin = blockIdx.z * k_per_split, k_end = min(k_tot, k_begin + k_per_split);
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < k_tot; k0 += SG_K) {
-        for (int i = threadIdx.x; i < SG_K * SG_T; i += 256) {
-            // pick the faster-varying index along the unit-stride axis of each operand
-            int kk, mm;
-            if (sak == 1) { kk = i % SG_K; mm = i / SG_K; } else { mm = i % SG_T; kk = i / SG_T; }
-            float v = 0.f;
-            if (m0 + mm < m_tot && k0 + kk < k_tot) {
-                v = a[(int64_t)(m0 + mm) * sam + (int64_t)(k0 + kk) * sak];
-                if (SIGMOID_A) {
-                    v = 1.f / (1.f + expf(-v));
-                    if (blockIdx.x == 0 && a_out) a_out[(int64_t)(m0 + mm) * lda_out + k0 + kk] = v;
-                }
-            }
-            sa[kk][mm] = v;
-            int kb, nn;
-            if (sbk == 1) { kb = i % SG_K; nn = i / SG_K; } else { nn = i % SG_T; kb = i / SG_T; }
-            float w = 0.f;
-            if (n0 + nn < n_tot && k0 + kb < k_tot) w = b[(int64_t)(k0 + kb) * sbk + (int64_t)(n0 + nn) * sbn];
-            sb[kb][nn] = w;
-        }
+    for (int k0 = k_begin; k0 < k_end; k0 += SG_K) {
+        sg_load_tile<SIGMOID_A>(sa, a, sam, sak, m0, k0, m_tot, k_end, a_out, lda_out, blockIdx.x == 0);
+        sg_load_tile<false>(sb, b, sbn, sbk, n0, k0, n_tot, k_end, nullptr, 0, false);
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < SG_K; ++kk) {
@@ -258,7 +281,8 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict
                 v = v * s * (1.f - s);
                 if (epi_add) v += epi_add[(int64_t)m * ldadd + n];
             }
-            c[(int64_t)m * ldc + n] = v;
+            if (gridDim.z > 1) atomicAdd(&c[(int64_t)m * ldc + n], v);
+            else c[(int64_t)m * ldc + n] = v;
         }
     }
 }
@@ -314,18 +338,27 @@ struct AdamTable {
 };
 
 __global__ void __launch_bounds__(256) adam_kernel(const AdamTable t, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
-                                                   float* __restrict__ step, const float* __restrict__ lr, float beta1,
-                                                   float beta2, float eps, float weight_decay, float grad_scale,
+                                                   float* __restrict__ step, const float* __restrict__ lr, double beta1_d,
+                                                   double beta2_d, float eps, float weight_decay, float grad_scale,
                                                    const double* __restrict__ loss_terms, int n_loss_terms,
                                                    float* __restrict__ loss_out) {
     // every CTA derives the same step number from the (not yet incremented) device counter; the LAST chunk's CTA
     // would race with readers if it incremented in place, so the counter is double-buffered: step[0] is read,
     // step[1] receives step[0] + 1 and a tiny tail of this kernel's launch (CTA 0 of the next launch) copies it back
+    // scalar arithmetic in double, as torch's Python-side bias corrections (1 - beta ** step, lr / bc1, sqrt(bc2)) and
+    // its `1 - beta` weights are: (float)(1 - 0.999) and 1.f - 0.999f differ by 5e-5 relative
+    __shared__ float s_sc[6];
     const float t_new = step[0] + 1.f;
-    const float bc1 = 1.f - powf(beta1, t_new);
-    const float bc2 = 1.f - powf(beta2, t_new);
-    const float step_size = lr[0] / bc1;
-    const float bc2_sqrt = sqrtf(bc2);
+    if (threadIdx.x == 0) {
+        const double bc1 = 1.0 - pow(beta1_d, (double)t_new), bc2 = 1.0 - pow(beta2_d, (double)t_new);
+        s_sc[0] = (float)((double)lr[0] / bc1);
+        s_sc[1] = (float)sqrt(bc2);
+        s_sc[2] = (float)(1.0 - beta1_d);
+        s_sc[3] = (float)(1.0 - beta2_d);
+        s_sc[4] = (float)beta2_d;
+    }
+    __syncthreads();
+    const float step_size = s_sc[0], bc2_sqrt = s_sc[1], omb1 = s_sc[2], omb2 = s_sc[3], beta2 = s_sc[4];
     const int total_chunks = t.chunk0[t.n_tensors];
     for (int item = blockIdx.x; item < total_chunks; item += gridDim.x) {
         int ti = 0;
@@ -341,8 +374,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTable t, float* __r
             const float w = pp[e];
             if (weight_decay != 0.f) g = fmaf(weight_decay, w, g);
             // torch: exp_avg.lerp_(grad, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-            const float mm = m[e] + (g - m[e]) * (1.f - beta1);
-            const float vv = fmaf(1.f - beta2, g * g, v[e] * beta2);
+            const float mm = m[e] + (g - m[e]) * omb1;
+            const float vv = fmaf(omb2, g * g, v[e] * beta2);
             m[e] = mm;
             v[e] = vv;
             // torch (capturable): denom = exp_avg_sq.sqrt() / bias_correction2_sqrt + eps; param.addcdiv_(exp_avg, denom, -step_size)
@@ -479,17 +512,39 @@ extern "C" int gnm_small_gemm(const float* a, int64_t sam, int64_t sak, const fl
     if (m == 0 || n == 0) return GNM_OK;
     if (!a || !b || !c) return GNM_ERR_BAD_ARG;
     if (sigmoid_a && dsig_s) return GNM_ERR_BAD_ARG;
-    dim3 grid((n + SG_T - 1) / SG_T, (m + SG_T - 1) / SG_T);
+    cudaStream_t st = gnm_cast_stream(stream);
+    const int tiles = ((n + SG_T - 1) / SG_T) * ((m + SG_T - 1) / SG_T);
+    // few output tiles and a long reduction (dW = du^T c: 25 tiles, K = B): split k across CTAs, partials merged by atomics
+    int splits = 1;
+    if (!sigmoid_a && !dsig_s && tiles < 74 && k >= 8 * SG_K) {
+        splits = 148 / tiles;
+        const int max_splits = k / (4 * SG_K);
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    }
+    int k_per_split = ((k + splits - 1) / splits + SG_K - 1) / SG_K * SG_K;
+    splits = (k + k_per_split - 1) / k_per_split;
+    if (splits < 1) { splits = 1; k_per_split = SG_K; }
+    if (splits > 1) {
+        if (ldc != n) {
+            cudaError_t e = cudaMemset2DAsync(c, (size_t)ldc * 4, 0, (size_t)n * 4, (size_t)m, st);
+            if (e != cudaSuccess) return (int)e;
+        } else {
+            cudaError_t e = cudaMemsetAsync(c, 0, (size_t)m * n * 4, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    dim3 grid((n + SG_T - 1) / SG_T, (m + SG_T - 1) / SG_T, splits);
     gnm_count_launch(GNM_K_OTHER);
     if (sigmoid_a)
-        small_gemm_kernel<true, false><<<grid, 256, 0, gnm_cast_stream(stream)>>>(a, sam, sak, b, sbk, sbn, c, ldc, m, n, k, a_out,
-                                                                                  lda_out, nullptr, 0, nullptr, 0);
+        small_gemm_kernel<true, false><<<grid, 256, 0, st>>>(a, sam, sak, b, sbk, sbn, c, ldc, m, n, k, k_per_split, a_out, lda_out,
+                                                             nullptr, 0, nullptr, 0);
     else if (dsig_s)
-        small_gemm_kernel<false, true><<<grid, 256, 0, gnm_cast_stream(stream)>>>(a, sam, sak, b, sbk, sbn, c, ldc, m, n, k, nullptr,
-                                                                                  0, dsig_s, lds, dsig_add, ldadd);
+        small_gemm_kernel<false, true><<<grid, 256, 0, st>>>(a, sam, sak, b, sbk, sbn, c, ldc, m, n, k, k_per_split, nullptr, 0,
+                                                             dsig_s, lds, dsig_add, ldadd);
     else
-        small_gemm_kernel<false, false><<<grid, 256, 0, gnm_cast_stream(stream)>>>(a, sam, sak, b, sbk, sbn, c, ldc, m, n, k,
-                                                                                   nullptr, 0, nullptr, 0, nullptr, 0);
+        small_gemm_kernel<false, false><<<grid, 256, 0, st>>>(a, sam, sak, b, sbk, sbn, c, ldc, m, n, k, k_per_split, nullptr, 0,
+                                                              nullptr, 0, nullptr, 0);
     GNM_RETURN_IF_LAUNCH_FAILED();
     return GNM_OK;
 }
@@ -506,8 +561,8 @@ extern "C" int gnm_dgi_neg_grad(const int32_t* neg_idx, const float* s2, const f
 }
 
 extern "C" int gnm_adam_step(float* const* params, const float* const* grads, const int32_t* numel, const int32_t* state_off,
-                             int n_tensors, float* exp_avg, float* exp_avg_sq, float* step, const float* lr, float beta1,
-                             float beta2, float eps, float weight_decay, float grad_scale, const double* loss_terms,
+                             int n_tensors, float* exp_avg, float* exp_avg_sq, float* step, const float* lr, double beta1,
+                             double beta2, float eps, float weight_decay, float grad_scale, const double* loss_terms,
                              int n_loss_terms, float* loss_out, gnm_stream_t stream) {
     if (n_tensors < 0 || n_loss_terms < 0) return GNM_ERR_BAD_ARG;
     if (!step || !lr || (n_tensors > 0 && (!params || !grads || !numel || !state_off || !exp_avg || !exp_avg_sq)))

@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libgnm.so")
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 _c_i32 = ctypes.c_int
 _c_i64 = ctypes.c_int64
@@ -25,6 +25,7 @@ SIGNATURES = {
     "gnm_set_device": [_c_i32],
     "gnm_device_info": [_p, _p, _p, _p],
     "gnm_launch_counts": [_p, _c_i32],
+    "gnm_stream_capture_status": [_p, _p],
     "gnm_csr_build": [_p, _c_i64, _p, _p, _c_i32, _c_i32, _c_i32, _c_i32, _p, _p, _p, _p],
     "gnm_csr_batch_gather": [_p, _p, _p, _p, _p, _c_i32, _p, _p, _p, _p],
     "gnm_aggregate": [_p, _p, _c_i32, _p, _c_i64, _p, _p, _c_i64, _c_i32, _c_i32, _p, _p, _p],
@@ -79,7 +80,7 @@ SIGNATURES = {
     "gnm_small_gemm": [_p, _c_i64, _c_i64, _p, _c_i64, _c_i64, _p, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32, _p, _c_i64, _p,
                        _c_i64, _p, _c_i64, _p],
     "gnm_dgi_neg_grad": [_p, _p, _p, _c_i64, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p],
-    "gnm_adam_step": [_p, _p, _p, _p, _c_i32, _p, _p, _p, _p, _c_f32, _c_f32, _c_f32, _c_f32, _c_f32, _p, _c_i32, _p, _p],
+    "gnm_adam_step": [_p, _p, _p, _p, _c_i32, _p, _p, _p, _p, _c_f64, _c_f64, _c_f32, _c_f32, _c_f32, _p, _c_i32, _p, _p],
     "gnm_rowdot_score": [_p, _c_i64, _c_i32, _c_i32, _p, _c_i64, _c_i32, _p, _p, _p, _p],
 }
 

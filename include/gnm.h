@@ -33,7 +33,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 19
+#define GNM_ABI_VERSION 20
 
 typedef void* gnm_stream_t;
 
@@ -95,6 +95,8 @@ int gnm_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_o
  * 8 linear_wgrad (FFMA), 9 every other kernel. Returns the number of families (>= 0) or GNM_ERR_BAD_ARG.
  * Tests use it to prove WHICH kernel family a code path ran; bench.py to count launches. */
 int gnm_launch_counts(int64_t* out, int n);
+/* Debugging aid for CUDA-graph capture: *status = 0 (stream not capturing), 1 (capturing), 2 (capture invalidated). */
+int gnm_stream_capture_status(gnm_stream_t stream, int* status);
 
 /* ---- adjacency / readout structure ------------------------------------------------------ */
 
@@ -409,7 +411,7 @@ int gnm_small_gemm(const float* a, int64_t sam, int64_t sak, const float* b, int
 int gnm_dgi_neg_grad(const int32_t* neg_idx, const float* s2, const float* u, int64_t ldu, int n_graphs, int width,
                      float* d_neg, int64_t ldn, int n_neg, gnm_stream_t stream);
 int gnm_adam_step(float* const* params, const float* const* grads, const int32_t* numel, const int32_t* state_off,
-                  int n_tensors, float* exp_avg, float* exp_avg_sq, float* step, const float* lr, float beta1, float beta2,
+                  int n_tensors, float* exp_avg, float* exp_avg_sq, float* step, const float* lr, double beta1, double beta2,
                   float eps, float weight_decay, float grad_scale, const double* loss_terms, int n_loss_terms,
                   float* loss_out, gnm_stream_t stream);
 
