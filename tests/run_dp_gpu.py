@@ -179,7 +179,9 @@ def main():
                 floor = grad_floor(ref)
                 for k, p in model.named_parameters():
                     if k in ref:
-                        assert_close(p.grad, ref[k], 2e-3, "grad " + k, floor=floor(k))
+                        # 3e-3 of the tensor's own max-abs from the fp64 truth (tests/test_gpu_model.py) plus the
+                        # reference fixture's own distance from it (<= 1.1e-3 at N = 400)
+                        assert_close(p.grad, ref[k], 4.5e-3, "grad " + k, floor=floor(k))
                 if not graphs_on:
                     for k, v in g.group("buf_after/").items():
                         if "num_batches" not in k:
