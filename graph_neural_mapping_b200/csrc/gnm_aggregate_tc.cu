@@ -82,8 +82,16 @@ struct AggTcParams {
     long long* dbg;              // nullable: per-CTA wait/busy cycle counters (profiling aid)
 };
 
-template <bool DBG>
+// VAR: which optional paths this instantiation carries (the others are compiled out: the three roles run different code
+// at the same time, and the all-in-one kernel - 81 KB of SASS - lost 20 % to instruction fetch and dead branches):
+//   TCV_FUSE relu / BatchNorm-backward consumer in the copy-out, TCV_AFF affine of two streams on the B rows,
+//   TCV_MAP row map / bias / shared table / output statistics (layer 0), TCV_EPS (1 + eps) self term, TCV_AVG degree weights.
+enum { TCV_FUSE = 1, TCV_AFF = 2, TCV_MAP = 4, TCV_EPS = 8, TCV_AVG = 16, TCV_ALL = 31 };
+
+template <bool DBG, int VAR>
 __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTcParams p) {
+    constexpr bool kFuse = (VAR & TCV_FUSE) != 0, kAff = (VAR & TCV_AFF) != 0, kMap = (VAR & TCV_MAP) != 0,
+                   kEps = (VAR & TCV_EPS) != 0, kAvg = (VAR & TCV_AVG) != 0;
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 6];
     __shared__ uint32_t s_tmem;
@@ -135,13 +143,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         uint32_t acc_it = 0;
         long long w_acc = 0;
         const long long t_role = clock64();
-        const float self_c = p.eps ? 1.f + __ldg(p.eps) : 0.f;
+        const float self_c = (kEps && p.eps) ? 1.f + __ldg(p.eps) : 0.f;
         const uint32_t my_slot = warp >> 2;
         const int q = warp & 3;
         float* stg = sm_stg + warp * (32 * TC_PITCH);
         // fused relu/BatchNorm backward (single 64-wide slab only): this lane's four columns are fixed
-        const bool fuse = p.rz != nullptr;
-        const bool ostats = p.out_stats != nullptr;
+        const bool fuse = kFuse && p.rz != nullptr;
+        const bool ostats = kMap && p.out_stats != nullptr;
         float4 r_sc = make_float4(0.f, 0.f, 0.f, 0.f), r_sh = r_sc, r_mu = r_sc, r_rs = r_sc;
         float rs1[4] = {0.f, 0.f, 0.f, 0.f}, rs2[4] = {0.f, 0.f, 0.f, 0.f};
         if (fuse && (lane & 15) * 4 < p.n_feat) {
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 const int r = row0 + lane;
                 const int gr = n0 + (r < n ? r : 0);
                 float deg = 1.f;
-                if (p.mode == 1) deg = (float)(p.rowptr[gr + 1] - p.rowptr[gr]);
+                if (kAvg && p.mode == 1) deg = (float)(p.rowptr[gr + 1] - p.rowptr[gr]);
                 // a warp whose 32 rows all lie beyond the graph (the tail of the last row tile) has nothing to drain
                 const bool any_rows = row0 < n;
                 if (any_rows) {
@@ -212,7 +220,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
                                 v[e] = (__uint_as_float(lo[j + e]) + __uint_as_float(mid[j + e])) + __uint_as_float(hi[j + e]);
-                            if (p.mode == 1) {
+                            if (kAvg && p.mode == 1) {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) v[e] /= deg;
                             }
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                     const bool col_ok = col < p.n_feat;
                     {
                         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                        if (kMap && p.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll 4
                         for (int i = 0; i < 16; ++i) {
                             const int rr = i * 2 + (lane >> 4);
@@ -240,13 +248,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                             if (!col_ok || row0 + rr >= n) continue;
                             const int g2 = n0 + row0 + rr;
                             float4 v = *reinterpret_cast<const float4*>(stg + rr * TC_PITCH + c4 * 4);
-                            if (p.eps) {
-                                const int64_t sr = p.src_map ? (int64_t)p.src_map[p.b_shared ? row0 + rr : g2] : (int64_t)g2;
+                            if (kEps && p.eps) {
+                                const int64_t sr = (kMap && p.src_map) ? (int64_t)p.src_map[p.b_shared ? row0 + rr : g2] : (int64_t)g2;
                                 const float4 sv = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
                                 v.x = fmaf(self_c, sv.x, v.x); v.y = fmaf(self_c, sv.y, v.y);
                                 v.z = fmaf(self_c, sv.z, v.z); v.w = fmaf(self_c, sv.w, v.w);
                             }
-                            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                            if (kMap) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
                             if (ostats) {
                                 rs1[0] += v.x; rs1[1] += v.y; rs1[2] += v.z; rs1[3] += v.w;
                                 rs2[0] = fmaf(v.x, v.x, rs2[0]); rs2[1] = fmaf(v.y, v.y, rs2[1]);
@@ -414,9 +422,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (kc < q.n_kc && k < q.n && col < p.n_feat) {
                     const int jr = q.n0 + k;
-                    const int64_t sr = p.src_map ? (int64_t)p.src_map[p.b_shared ? k : jr] : (int64_t)jr;
+                    const int64_t sr = (kMap && p.src_map) ? (int64_t)p.src_map[p.b_shared ? k : jr] : (int64_t)jr;
                     v = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
-                    if (p.aff_coef != nullptr) {
+                    if (kAff && p.aff_coef != nullptr) {
                         const float4 zv = __ldg(reinterpret_cast<const float4*>(p.aff_z + sr * p.ld_aff_z + col));
                         const float4 ca = __ldg(reinterpret_cast<const float4*>(p.aff_coef + col));
                         const float4 cb = __ldg(reinterpret_cast<const float4*>(p.aff_coef + p.n_feat + col));
@@ -424,7 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                         v.x = fmaf(ca.x, v.x, fmaf(cb.x, zv.x, cc.x)); v.y = fmaf(ca.y, v.y, fmaf(cb.y, zv.y, cc.y));
                         v.z = fmaf(ca.z, v.z, fmaf(cb.z, zv.z, cc.z)); v.w = fmaf(ca.w, v.w, fmaf(cb.w, zv.w, cc.w));
                     }
-                    if (p.mode == 2) {
+                    if (kAvg && p.mode == 2) {
                         const float w = 1.f / (float)(p.rowptr[jr + 1] - p.rowptr[jr]);
                         v.x *= w; v.y *= w; v.z *= w; v.w *= w;
                     }
@@ -441,7 +449,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             fetch_item(item + gridDim.x, nxt);   // in flight during this whole item
             const int n = cur.n, n_mt = cur.n_mt, n_kc = cur.n_kc, ksteps_total = cur.ksteps_total;
             // shared table: only this CTA's first item converts (and loads) the B planes
-            const bool do_b = !p.b_shared || item == (int)blockIdx.x;
+            const bool do_b = !(kMap && p.b_shared) || item == (int)blockIdx.x;
             if (!preloaded) {
                 load_words(cur, 0, a_it, w_cur);
                 if (do_b) load_b(cur, ((a_it & 1) == (uint32_t)grp) ? 0 : 1);
@@ -454,7 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                     derive_item(nxt);
                     const uint32_t it_next = a_it + n_kc;                 // ring position at the next item's start
                     load_words(nxt, 0, it_next, w_nxt);
-                    if (!p.b_shared) load_b(nxt, ((it_next & 1) == (uint32_t)grp) ? 0 : 1);
+                    if (!(kMap && p.b_shared)) load_b(nxt, ((it_next & 1) == (uint32_t)grp) ? 0 : 1);
                     preloaded = true;
                 } else {
                     load_words(cur, mt + 1, a_it + n_kc, w_nxt);
@@ -534,7 +542,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
     }
-    bn_tail_run(p.tail);
+    if (kFuse || kMap) bn_tail_run(p.tail);
+}
+
+template <bool DBG, int VAR>
+cudaError_t launch_variant(const AggTcParams& p, int grid, int smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(aggregate_tc_kernel<DBG, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    gnm_count_launch(GNM_K_AGG_TC);
+    aggregate_tc_kernel<DBG, VAR><<<grid, TC_THREADS, smem, stream>>>(p);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -595,19 +612,24 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
     if (smem > smem_cap - 1024) return GNM_ERR_TOO_LARGE;
     const int64_t items = (int64_t)n_graphs * p.n_slabs;
     const int grid = (int)(items < sms ? items : sms);
+    // the paths this call needs; the lean instantiations cover sum pooling (mode 0), everything else takes the all-in-one
+    int var = (fuse ? TCV_FUSE : 0) | (aff_coef ? TCV_AFF : 0) | ((src_map || bias || out_stats || b_shared) ? TCV_MAP : 0) |
+              (eps ? TCV_EPS : 0) | (mode != 0 ? TCV_AVG : 0);
     cudaError_t e;
     if (p.dbg != nullptr) {
-        e = cudaFuncSetAttribute(aggregate_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        gnm_count_launch(GNM_K_AGG_TC);
-        aggregate_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(aggregate_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        gnm_count_launch(GNM_K_AGG_TC);
-        aggregate_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p);
+        e = var == 0 ? launch_variant<true, 0>(p, grid, smem, stream) : launch_variant<true, TCV_ALL>(p, grid, smem, stream);
+        return e == cudaSuccess ? GNM_OK : (int)e;
     }
-    e = cudaGetLastError();
+    switch (var) {
+        case 0: e = launch_variant<false, 0>(p, grid, smem, stream); break;
+        case TCV_EPS: e = launch_variant<false, TCV_EPS>(p, grid, smem, stream); break;
+        case TCV_FUSE: e = launch_variant<false, TCV_FUSE>(p, grid, smem, stream); break;
+        case TCV_FUSE | TCV_EPS: e = launch_variant<false, TCV_FUSE | TCV_EPS>(p, grid, smem, stream); break;
+        case TCV_AFF: e = launch_variant<false, TCV_AFF>(p, grid, smem, stream); break;
+        case TCV_MAP: e = launch_variant<false, TCV_MAP>(p, grid, smem, stream); break;
+        case TCV_MAP | TCV_EPS: e = launch_variant<false, TCV_MAP | TCV_EPS>(p, grid, smem, stream); break;
+        default: e = launch_variant<false, TCV_ALL>(p, grid, smem, stream); break;
+    }
     return e == cudaSuccess ? GNM_OK : (int)e;
 }
 
