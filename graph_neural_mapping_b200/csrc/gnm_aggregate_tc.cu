@@ -105,15 +105,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     const int b_ncore_stride = p.kcores_max * 128 + 16;            // SBO of B (padded: conflict-free plane fill)
     unsigned char* sm_b = tc_smem;                                  // 24 n-cores x b_ncore_stride
     float* sm_stg = reinterpret_cast<float*>(tc_smem + (size_t)24 * b_ncore_stride);   // TC_EPI_WARPS staging tiles
-    // byte -> eight bf16 0/1 values (four 32-bit TMEM columns): the adjacency expansion is a table lookup
-    uint4* lut = reinterpret_cast<uint4*>(tc_smem + (size_t)24 * b_ncore_stride + TC_EPI_WARPS * TC_STG);
+    // nibble -> four bf16 0/1 values (two 32-bit TMEM columns): the adjacency expansion is a table lookup. The table is
+    // replicated per LANE (entry e of lane l at e * 256 + l * 8 bytes): whatever nibbles the 32 rows of a warp hold,
+    // lane l always reads banks 2l, 2l + 1 - two wavefronts per LDS.64, never a conflict. (A 256-entry byte table read
+    // with LDS.128 took 2.7 wavefronts per ideal one: 4.8 M of the kernel's 10.5 M shared-memory wavefronts were its
+    // bank conflicts, profiles/r2_aggregate_tc_lines.txt.)
+    uint2* lut = reinterpret_cast<uint2*>(tc_smem + (size_t)24 * b_ncore_stride + TC_EPI_WARPS * TC_STG);
     // fused relu / BatchNorm backward only: one more tile per epilogue warp, the z rows of its slice (cp.async)
     float* sm_zst = reinterpret_cast<float*>(tc_smem + (size_t)24 * b_ncore_stride + TC_EPI_WARPS * TC_STG + 4096);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid < 256) {
-        const uint32_t b8 = tid;
-        lut[tid] = make_uint4(bits2_bf16x2(b8), bits2_bf16x2(b8 >> 2), bits2_bf16x2(b8 >> 4), bits2_bf16x2(b8 >> 6));
+    for (int i = tid; i < 16 * 32; i += TC_THREADS) {
+        const uint32_t e = (uint32_t)i >> 5;
+        lut[i] = make_uint2(bits2_bf16x2(e), bits2_bf16x2(e >> 2));
     }
     volatile int* abort_flag = &s_abort;
     if (tid == 0) {
@@ -412,27 +416,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         // pipelines): the owner expands the adjacency tile and, during the first row tile, also converts the
         // 64 feature rows of that chunk into the three B planes.
         const int gtid = ptid & 127;
+        const int lb_c4 = gtid & 15, lb_kr = gtid >> 4;      // this thread's float4 column / first node of a 64-node chunk
         float4 bq[8];
+        // affine variant: this thread's column never changes within a slab - its coefficients live in registers
+        float4 aff_a = make_float4(0.f, 0.f, 0.f, 0.f), aff_b = aff_a, aff_c = aff_a;
+        int aff_col = -1;
         auto load_b = [&](const ItemP& q, int kc) {
+            const int col = q.f0 + lb_c4 * 4;
+            const bool ok0 = kc < q.n_kc && col < p.n_feat;
+            const int kbase = kc * TC_KC + lb_kr;             // rows kbase, kbase + 8, ... of the graph
+            if (kAff && ok0 && p.aff_coef != nullptr && aff_col != col) {
+                aff_a = __ldg(reinterpret_cast<const float4*>(p.aff_coef + col));
+                aff_b = __ldg(reinterpret_cast<const float4*>(p.aff_coef + p.n_feat + col));
+                aff_c = __ldg(reinterpret_cast<const float4*>(p.aff_coef + 2 * p.n_feat + col));
+                aff_col = col;
+            }
+            const float* rowp = p.src + (int64_t)(q.n0 + kbase) * p.ld_src + col;
+            const float* zrow = kAff ? p.aff_z + (int64_t)(q.n0 + kbase) * p.ld_aff_z + col : nullptr;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int idx = gtid + u * 128;                  // 64 nodes x 16 float4
-                const int k = kc * TC_KC + (idx >> 4), c4 = idx & 15;
-                const int col = q.f0 + c4 * 4;
+                const int k = kbase + u * 8;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (kc < q.n_kc && k < q.n && col < p.n_feat) {
-                    const int jr = q.n0 + k;
-                    const int64_t sr = (kMap && p.src_map) ? (int64_t)p.src_map[p.b_shared ? k : jr] : (int64_t)jr;
-                    v = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
+                if (ok0 && k < q.n) {
+                    if (kMap && p.src_map) {
+                        const int64_t sr = (int64_t)p.src_map[p.b_shared ? k : q.n0 + k];
+                        v = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
+                    } else {
+                        v = __ldg(reinterpret_cast<const float4*>(rowp + (int64_t)(u * 8) * p.ld_src));
+                    }
                     if (kAff && p.aff_coef != nullptr) {
-                        const float4 zv = __ldg(reinterpret_cast<const float4*>(p.aff_z + sr * p.ld_aff_z + col));
-                        const float4 ca = __ldg(reinterpret_cast<const float4*>(p.aff_coef + col));
-                        const float4 cb = __ldg(reinterpret_cast<const float4*>(p.aff_coef + p.n_feat + col));
-                        const float4 cc = __ldg(reinterpret_cast<const float4*>(p.aff_coef + 2 * p.n_feat + col));
-                        v.x = fmaf(ca.x, v.x, fmaf(cb.x, zv.x, cc.x)); v.y = fmaf(ca.y, v.y, fmaf(cb.y, zv.y, cc.y));
-                        v.z = fmaf(ca.z, v.z, fmaf(cb.z, zv.z, cc.z)); v.w = fmaf(ca.w, v.w, fmaf(cb.w, zv.w, cc.w));
+                        const float4 zv = __ldg(reinterpret_cast<const float4*>(zrow + (int64_t)(u * 8) * p.ld_aff_z));
+                        v.x = fmaf(aff_a.x, v.x, fmaf(aff_b.x, zv.x, aff_c.x)); v.y = fmaf(aff_a.y, v.y, fmaf(aff_b.y, zv.y, aff_c.y));
+                        v.z = fmaf(aff_a.z, v.z, fmaf(aff_b.z, zv.z, aff_c.z)); v.w = fmaf(aff_a.w, v.w, fmaf(aff_b.w, zv.w, aff_c.w));
                     }
                     if (kAvg && p.mode == 2) {
+                        const int jr = q.n0 + k;
                         const float w = 1.f / (float)(p.rowptr[jr + 1] - p.rowptr[jr]);
                         v.x *= w; v.y *= w; v.z *= w; v.w *= w;
                     }
@@ -483,8 +501,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                         const long long tb0 = DBG ? clock64() : 0;
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const int idx = gtid + u * 128;
-                            const int k = kc * TC_KC + (idx >> 4), c4 = idx & 15;
+                            const int k = kc * TC_KC + lb_kr + u * 8, c4 = lb_c4;
                             if (k >= ksteps_total * 16) continue;
                             uint32_t h0, m0, l0, h1, m1, l1;
                             split3x2(bq[u].x, bq[u].y, h0, m0, l0);
@@ -505,12 +522,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                         // 64 bits -> 32 registers of bf16 pairs -> 32 TMEM columns of this row
                         const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TC_A_TMEM0 + s * TC_A_COLS;
 #pragma unroll
+                        const uint2* my_lut = lut + lane;
                         for (int hw = 0; hw < 2; ++hw) {
                             uint32_t v[16];
+                            const uint32_t w32 = w_cur[0][hw];
 #pragma unroll
-                            for (int b = 0; b < 4; ++b) {
-                                const uint4 t4 = lut[(w_cur[0][hw] >> (8 * b)) & 0xffu];
-                                v[4 * b] = t4.x; v[4 * b + 1] = t4.y; v[4 * b + 2] = t4.z; v[4 * b + 3] = t4.w;
+                            for (int b = 0; b < 8; ++b) {
+                                const uint2 t2 = my_lut[((w32 >> (4 * b)) & 15u) * 32];
+                                v[2 * b] = t2.x; v[2 * b + 1] = t2.y;
                             }
                             tmem_st16(taddr + hw * 16, v);
                         }
