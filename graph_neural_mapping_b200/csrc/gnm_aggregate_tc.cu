@@ -88,6 +88,13 @@ struct AggTcParams {
 //   TCV_MAP row map / bias / shared table / output statistics (layer 0), TCV_EPS (1 + eps) self term, TCV_AVG degree weights.
 enum { TCV_FUSE = 1, TCV_AFF = 2, TCV_MAP = 4, TCV_EPS = 8, TCV_AVG = 16, TCV_ALL = 31 };
 
+// bulk prefetch of [ptr, ptr + bytes) into L2 (no destination, no completion tracking); 16-byte granularity
+__device__ __forceinline__ void l2_prefetch(const void* ptr, int64_t bytes) {
+    const uint32_t n = (uint32_t)(bytes & ~(int64_t)15);
+    if (n == 0 || (reinterpret_cast<uintptr_t>(ptr) & 15)) return;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(n) : "memory");
+}
+
 template <bool DBG, int VAR>
 __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTcParams p) {
     constexpr bool kFuse = (VAR & TCV_FUSE) != 0, kAff = (VAR & TCV_AFF) != 0, kMap = (VAR & TCV_MAP) != 0,
@@ -475,6 +482,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             preloaded = false;
             bool first_b = true;
             for (int mt = 0; mt < n_mt && ok; ++mt) {
+                const long long tt0 = DBG ? clock64() : 0;
+                if (ptid == 0 && mt == (n_mt > 1 ? 1 : 0) && item + (int)gridDim.x < n_items) {
+                    // The NEXT item's feature rows and bitmap are pulled into L2 now, two to three row tiles before its
+                    // first loads: one bulk L2 prefetch per stream (the rows of a graph are contiguous), so that the
+                    // register loads in front of the B conversion (only one chunk ahead - there are no registers for
+                    // more) and the bitmap word loads hit L2 instead of waiting for DRAM. `nxt` was requested at the
+                    // start of this item and has arrived by now.
+                    if (!(kMap && p.b_shared) && !(kMap && p.src_map) && p.ld_src == p.n_feat) {
+                        l2_prefetch(p.src + (int64_t)nxt.n0 * p.ld_src, (int64_t)nxt.n * p.n_feat * 4);
+                        if (kAff && p.aff_z != nullptr && p.ld_aff_z == p.n_feat)
+                            l2_prefetch(p.aff_z + (int64_t)nxt.n0 * p.ld_aff_z, (int64_t)nxt.n * p.n_feat * 4);
+                    }
+                    if (nxt.bm != nullptr) l2_prefetch(nxt.bm, (int64_t)nxt.n * ((nxt.n + 31) >> 5) * 4);
+                }
                 if (mt == n_mt - 1 && mt > 0 && item + (int)gridDim.x < n_items) {
                     // last row tile: the B registers are idle (conversion happens in tile 0 only)
                     derive_item(nxt);
@@ -486,11 +507,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                     load_words(cur, mt + 1, a_it + n_kc, w_nxt);
                 }
                 const int first = ((a_it & 1) == (uint32_t)grp) ? 0 : 1;
+                if (DBG) c_bload += clock64() - tt0;                // tile head: next tile's / next item's loads issued
 #pragma unroll 1
                 for (int kc = 0; kc < n_kc; ++kc, ++a_it) {
                     if (((kc - first) & 1) != 0) continue;          // the other group's stage
                     const uint32_t s = a_it % TC_STAGES, aph = (a_it / TC_STAGES) & 1;
+                    const long long tw0 = DBG ? clock64() : 0;
                     if (!(ok = mbar_wait<32>(&a_empty[s], aph ^ 1, abort_flag, DBG ? &w_pe : nullptr))) break;
+                    if (DBG) c_fence += clock64() - tw0;            // whole wait call, fast path included
                     if (mt == 0 && do_b) {
                         // the previous item's MMAs on these B rows retired at least TC_STAGES stages ago, unless
                         // that item had fewer k chunks than the ring: then wait for its explicit b_free commit
@@ -543,8 +567,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                     if (lane == 0) mbar_arrive(&a_full[s]);
                     if (DBG) { const long long tq3 = clock64(); c_st += tq1 - tq0; c_arr += tq3 - tq1; }
                 }
+                const long long tt1 = DBG ? clock64() : 0;
 #pragma unroll
                 for (int c = 0; c < MYC; ++c) { w_cur[c][0] = w_nxt[c][0]; w_cur[c][1] = w_nxt[c][1]; }
+                if (DBG) c_bload += clock64() - tt1;                // tile tail: the prefetched words must have arrived
             }
             prev_nkc = n_kc;
             if (!preloaded) derive_item(nxt);

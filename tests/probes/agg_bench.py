@@ -52,7 +52,7 @@ def main():
             lib.load().gnm_aggregate_tc_set_debug(None)
             d = dbg.view(148, 16).double().mean(0).tolist()
             print("  tcgen05 role cycles (mean over CTAs): epilogue %.0f (waiting acc_full %.0f) | mma %.0f (waiting a_full %.0f, "
-                  "acc_empty %.0f) | producer %.0f (waiting a_empty %.0f; A expand+store %.0f, B wait-for-loads %.0f, syncwarp+arrive %.0f, B convert+store %.0f, B issue loads+fence %.0f)" % tuple(d[:12]))
+                  "acc_empty %.0f) | producer %.0f (a_empty slow-path wait %.0f; A expand+store %.0f, a_empty wait call incl. fast path %.0f, syncwarp+arrive %.0f, B convert+store+next loads %.0f, tile head/tail (word loads, item switch) %.0f)" % tuple(d[:12]))
         err = float((dst - ref).abs().max() / ref.abs().max())
         t = float(np.median(ts))
         print("%-18s median %8.1f us  min %8.1f us  -> %7.1f GB/s algorithmic (%.3f of 6546)  max rel err vs csr %.2e  abort=%s"
