@@ -81,6 +81,9 @@ __device__ __forceinline__ void stage_rows_async(const float* base, int64_t ld, 
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// ACT: the unit below is Linear -> BatchNorm -> ReLU (mask + its backward reduction in the epilogue); FAST: 64 x 64,
+// aligned, dx requested - the general paths are compiled out (see linear_tc_kernel).
+template <bool ACT, bool FAST>
 __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const LinBwdTcParams p) {
     extern __shared__ __align__(1024) unsigned char bt_smem[];
     __shared__ __align__(8) uint64_t bars[2 * BT_STAGES + 4];
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     volatile int* abort_flag = &s_abort;
     const int n_tiles = (p.n_rows + 127) >> 7;
-    const bool act = p.in_scale != nullptr;
+    constexpr bool act = ACT;
 
     // ---- setup: B images. GEMM k = o (n_out), n = i (n_in); K-major core matrices: (n, k) -> (k/8)*1024 + (n/8)*128 + (n%8)*16 + (k%8)*2
     for (int e = tid; e < BT_F * BT_F / 2; e += BT_THREADS) {
@@ -158,8 +161,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
         float* stg = sm_stg + warp * (32 * BT_PITCH);
         float* obuf = sm_out + warp * (32 * BT_OPITCH);
         const uint32_t stg_u32 = smem_u32(stg);
-        const bool fast_x = act && p.n_in == BT_F && (p.ldx & 3) == 0 && gnm_aligned16(p.x);
-        const bool fast_o = p.dx != nullptr && p.n_in == BT_F && (p.lddx & 3) == 0 && gnm_aligned16(p.dx);
+        const bool fast_x = act && (FAST || (p.n_in == BT_F && (p.ldx & 3) == 0 && gnm_aligned16(p.x)));
+        const bool fast_o = FAST || (p.dx != nullptr && p.n_in == BT_F && (p.lddx & 3) == 0 && gnm_aligned16(p.dx));
         const int sub = lane >> 3, c4l = (lane & 7) * 4;
         // prefetch x for this group's first tile
         if (act) {
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
         const uint32_t stg_u32 = smem_u32(stg);
         const float* src = grp == 0 ? p.dy : p.z;
         const int64_t ld = grp == 0 ? p.lddy : p.ldz;
-        const bool fast = p.n_out == BT_F && (ld & 3) == 0 && gnm_aligned16(src);
+        const bool fast = FAST || (p.n_out == BT_F && (ld & 3) == 0 && gnm_aligned16(src));
         if ((int)blockIdx.x < n_tiles) stage_rows_async(src, ld, p.n_rows, p.n_out, blockIdx.x * 128 + q * 32, stg, stg_u32, lane, fast);
         uint32_t it = 0;
         bool ok = true;
@@ -410,6 +413,7 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+template <bool ACT, bool FAST>
 __global__ void __launch_bounds__(WG_THREADS, 1) linear_wgrad_tc_kernel(const WgradTcParams p) {
     extern __shared__ __align__(1024) unsigned char wg_smem[];
     __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 1];
@@ -422,7 +426,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) linear_wgrad_tc_kernel(const Wg
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     volatile int* abort_flag = &s_abort;
     const int n_chunks = (p.n_rows + WG_ROWS - 1) / WG_ROWS;
-    const bool act = p.in_scale != nullptr;
+    constexpr bool act = ACT;
 
     if (tid < 3 * BT_F) s_sum[tid] = 0.f;
     if (tid == 0) {
@@ -448,8 +452,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) linear_wgrad_tc_kernel(const Wg
         // unlike a register prefetch, whose loads all share the warp's scoreboards (measured: a deeper register ring
         // gained nothing), this keeps 3 chunks = 72 KB per SM genuinely in flight.
         const int c4 = tid & 15, kr0 = tid >> 4;
-        const bool fast = p.n_out == BT_F && p.n_in == BT_F && ((p.lddy | p.ldz | p.ldx) & 3) == 0 &&
-                          gnm_aligned16(p.dy) && gnm_aligned16(p.z) && gnm_aligned16(p.x);
+        const bool fast = FAST || (p.n_out == BT_F && p.n_in == BT_F && ((p.lddy | p.ldz | p.ldx) & 3) == 0 &&
+                                   gnm_aligned16(p.dy) && gnm_aligned16(p.z) && gnm_aligned16(p.x));
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) {
             const int c = c4 * 4;
@@ -656,12 +660,24 @@ int gnm_launch_linear_bwd_dx_tc(const float* dy, int64_t lddy, const float* z, i
     p.dy = dy; p.lddy = lddy; p.z = z; p.ldz = ldz; p.coef = coef; p.w = w; p.ldw = ldw; p.x = x; p.ldx = ldx;
     p.in_scale = in_scale; p.in_shift = in_shift; p.in_mean = in_mean; p.in_rstd = in_rstd; p.dx = dx; p.lddx = lddx;
     p.stats_in = stats_in; p.n_rows = n_rows; p.n_out = n_out; p.n_in = n_in;
-    cudaError_t e = cudaFuncSetAttribute(linear_bwd_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM);
-    if (e != cudaSuccess) return (int)e;
     const int tiles = (n_rows + 127) / 128;
     const int grid = tiles < sms ? tiles : sms;
-    gnm_count_launch(GNM_K_LINEAR_BWD_DX_TC);
-    linear_bwd_dx_tc_kernel<<<grid, BT_THREADS, BT_SMEM, stream>>>(p);
+    const bool act = in_scale != nullptr;
+    const bool fast = n_in == BT_F && n_out == BT_F && dx != nullptr && ((lddy | ldz | lddx) & 3) == 0 && gnm_aligned16(dy) &&
+                      gnm_aligned16(z) && gnm_aligned16(dx) && (!act || ((ldx & 3) == 0 && gnm_aligned16(x)));
+    cudaError_t e;
+#define GNM_BT_LAUNCH(A, F)                                                                                                  \
+    do {                                                                                                                     \
+        e = cudaFuncSetAttribute(linear_bwd_dx_tc_kernel<A, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM);       \
+        if (e != cudaSuccess) return (int)e;                                                                                 \
+        gnm_count_launch(GNM_K_LINEAR_BWD_DX_TC);                                                                            \
+        linear_bwd_dx_tc_kernel<A, F><<<grid, BT_THREADS, BT_SMEM, stream>>>(p);                                             \
+    } while (0)
+    if (act && fast) GNM_BT_LAUNCH(true, true);
+    else if (fast) GNM_BT_LAUNCH(false, true);
+    else if (act) GNM_BT_LAUNCH(true, false);
+    else GNM_BT_LAUNCH(false, false);
+#undef GNM_BT_LAUNCH
     e = cudaGetLastError();
     return e == cudaSuccess ? GNM_OK : (int)e;
 }
@@ -687,12 +703,24 @@ int gnm_launch_linear_wgrad_tc(const float* dy, int64_t lddy, const float* z, in
     WgradTcParams p;
     p.dy = dy; p.lddy = lddy; p.z = z; p.ldz = ldz; p.coef = coef; p.x = x; p.ldx = ldx; p.in_scale = in_scale;
     p.in_shift = in_shift; p.dw = dw; p.lddw = lddw; p.db = dbias; p.n_rows = n_rows; p.n_out = n_out; p.n_in = n_in;
-    cudaError_t e = cudaFuncSetAttribute(linear_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
-    if (e != cudaSuccess) return (int)e;
     const int chunks = (n_rows + WG_ROWS - 1) / WG_ROWS;
     const int grid = chunks < sms ? chunks : sms;
-    gnm_count_launch(GNM_K_LINEAR_WGRAD_TC);
-    linear_wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM, stream>>>(p);
+    const bool act = in_scale != nullptr;
+    const bool fast = n_out == BT_F && n_in == BT_F && ((lddy | ldz | ldx) & 3) == 0 && gnm_aligned16(dy) && gnm_aligned16(z) &&
+                      gnm_aligned16(x);
+    cudaError_t e;
+#define GNM_WG_LAUNCH(A, F)                                                                                                 \
+    do {                                                                                                                    \
+        e = cudaFuncSetAttribute(linear_wgrad_tc_kernel<A, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);       \
+        if (e != cudaSuccess) return (int)e;                                                                                \
+        gnm_count_launch(GNM_K_LINEAR_WGRAD_TC);                                                                            \
+        linear_wgrad_tc_kernel<A, F><<<grid, WG_THREADS, WG_SMEM, stream>>>(p);                                             \
+    } while (0)
+    if (act && fast) GNM_WG_LAUNCH(true, true);
+    else if (fast) GNM_WG_LAUNCH(false, true);
+    else if (act) GNM_WG_LAUNCH(true, false);
+    else GNM_WG_LAUNCH(false, false);
+#undef GNM_WG_LAUNCH
     e = cudaGetLastError();
     return e == cudaSuccess ? GNM_OK : (int)e;
 }
