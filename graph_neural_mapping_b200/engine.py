@@ -72,6 +72,8 @@ class GraphStore(object):
         self.max_bytes = int(max_bytes)
         self.bytes = 0              # device bytes held by the stored CSRs / tags / bitmaps
         self.evictions = 0
+        if hasattr(_ops, "prepare_device"):
+            _ops.prepare_device(device)
         self.entries = {}           # id(graph) -> slot
         # slot table (one row per stored graph): rowptr / colidx / tag / bitmap addresses, n, nnz, onehot, isolated,
         # feature width, tag-sequence id. A batch is assembled from it with a handful of numpy gathers instead of per-graph Python.

@@ -97,8 +97,17 @@ def _tail_counter(device):
     key = device.index if device.index is not None else torch.cuda.current_device()
     t = _TAIL_COUNTERS.get(key)
     if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            # memory allocated under capture belongs to that graph's private pool and dies with it
+            raise RuntimeError("the BatchNorm-tail ticket must exist before CUDA-graph capture (GraphStore creates it)")
         t = _TAIL_COUNTERS[key] = torch.zeros(1, dtype=torch.int32, device=device)
     return t
+
+
+def prepare_device(device):
+    """Per-device state that must exist before any CUDA-graph capture (called by engine.GraphStore)."""
+    if device.type == "cuda":
+        _tail_counter(device)
 
 
 class BnTail(object):
