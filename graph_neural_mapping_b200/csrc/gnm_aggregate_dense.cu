@@ -396,7 +396,7 @@ extern "C" int gnm_aggregate_dense_relu_bn_bwd(const int64_t* bitmap_addr, const
                                                const float* rstd, const float* d_pooled, int64_t ld_dpooled,
                                                const float* pool_scale, const float* d_score, const float* u, int64_t ldu,
                                                const float* d_neg, int64_t ld_dneg, int n_neg, float* dy, int64_t lddy,
-                                               double* stats, gnm_stream_t stream) {
+                                               double* stats, const gnm_bn_tail* tail, gnm_stream_t stream) {
     if (n_graphs < 0 || n_max < 0 || n_feat < 0 || mode < 0 || mode > 2) return GNM_ERR_BAD_ARG;
     if (n_graphs == 0 || n_max == 0 || n_feat == 0) return GNM_OK;
     if (!bitmap_addr || !node_off || !src || !dy || !z || !scale || !shift || !mean || !rstd || (mode != 0 && !rowptr))
@@ -408,5 +408,5 @@ extern "C" int gnm_aggregate_dense_relu_bn_bwd(const int64_t* bitmap_addr, const
     f.ld_dpooled = ld_dpooled; f.pool_scale = pool_scale; f.d_score = d_score; f.u = u; f.ldu = ldu; f.d_neg = d_neg;
     f.ld_dneg = ld_dneg; f.n_neg = n_neg; f.stats = stats;
     return gnm_launch_aggregate_tc(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, ld_src, nullptr, dy, lddy, n_feat,
-                                   mode, eps, nullptr, nullptr, nullptr, 0, &f, 0, nullptr, nullptr, gnm_cast_stream(stream));
+                                   mode, eps, nullptr, nullptr, nullptr, 0, &f, 0, nullptr, tail, gnm_cast_stream(stream));
 }

@@ -13,6 +13,7 @@
 // no cross-lane transposition - and coalesced stores; one fp64 atomic per column and CTA at the end.
 #include "gnm_common.cuh"
 #include "gnm_tc.cuh"
+#include "gnm_bn_tail.cuh"
 
 namespace {
 
@@ -43,6 +44,7 @@ struct LinBwdTcParams {
     float* dx; int64_t lddx;
     double* stats_in;
     int n_rows, n_out, n_in;
+    BnTailDev tail;                        // BatchNorm-backward coefficients of the unit below from stats_in (kind 0: none)
 };
 
 
@@ -370,6 +372,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
     if (warp == BT_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }
+    if (ACT) bn_tail_run(p.tail);
 }
 
 
@@ -649,8 +652,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) linear_wgrad_tc_kernel(const Wg
 int gnm_launch_linear_bwd_dx_tc(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* coef,
                                 const float* x, int64_t ldx, const float* in_scale, const float* in_shift,
                                 const float* in_mean, const float* in_rstd, const float* w, int64_t ldw, float* dx,
-                                int64_t lddx, double* stats_in, int n_rows, int n_out, int n_in, cudaStream_t stream) {
+                                int64_t lddx, double* stats_in, int n_rows, int n_out, int n_in, const gnm_bn_tail* tail,
+                                cudaStream_t stream) {
     if (n_in > BT_F || n_out > BT_F || n_in < 1 || n_out < 1) return GNM_ERR_TOO_LARGE;
+    if (tail != nullptr && (stats_in == nullptr || in_scale == nullptr)) return GNM_ERR_BAD_ARG;
     int dev = 0, sms = 148, major = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
@@ -660,6 +665,8 @@ int gnm_launch_linear_bwd_dx_tc(const float* dy, int64_t lddy, const float* z, i
     p.dy = dy; p.lddy = lddy; p.z = z; p.ldz = ldz; p.coef = coef; p.w = w; p.ldw = ldw; p.x = x; p.ldx = ldx;
     p.in_scale = in_scale; p.in_shift = in_shift; p.in_mean = in_mean; p.in_rstd = in_rstd; p.dx = dx; p.lddx = lddx;
     p.stats_in = stats_in; p.n_rows = n_rows; p.n_out = n_out; p.n_in = n_in;
+    const int trc = bn_tail_args(tail, stats_in, n_in, &p.tail);
+    if (trc != GNM_OK) return trc;
     const int tiles = (n_rows + 127) / 128;
     const int grid = tiles < sms ? tiles : sms;
     const bool act = in_scale != nullptr;

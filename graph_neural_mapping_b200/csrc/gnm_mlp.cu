@@ -3,6 +3,7 @@
 // Reference: models/mlp.py:40-49, models/graphcnn.py:162-166,185-190 (nn.Linear, nn.BatchNorm1d, ReLU).
 #include "gnm_common.cuh"
 #include "gnm_p2p.cuh"
+#include "gnm_bn_tail.cuh"
 
 namespace {
 
@@ -367,7 +368,7 @@ relu_bn_bwd_reduce_vec_kernel(const float* __restrict__ z, int64_t ldz, int n_fe
                               const float* __restrict__ pool_scale, const float* __restrict__ d_score,
                               const float* __restrict__ u, int64_t ldu, const float* __restrict__ d_neg,
                               int64_t ld_dneg, int n_neg, const int32_t* __restrict__ node_off,
-                              float* __restrict__ dy, int64_t lddy, double* __restrict__ stats) {
+                              float* __restrict__ dy, int64_t lddy, double* __restrict__ stats, const BnTailDev tail) {
     const int g = blockIdx.x;
     const int lpr = n_feat >> 2;
     const int rpp = 256 / lpr;
@@ -431,6 +432,7 @@ relu_bn_bwd_reduce_vec_kernel(const float* __restrict__ z, int64_t ldz, int n_fe
             atomicAdd(&stats[n_feat + threadIdx.x * 4 + q], b[q]);
         }
     }
+    bn_tail_run(tail);
 }
 
 __global__ void __launch_bounds__(256)
@@ -643,7 +645,8 @@ extern "C" int gnm_relu_bn_bwd_reduce(const float* z, int64_t ldz, int n_rows, i
                                       int64_t ld_dout, const float* d_pooled, int64_t ld_dpooled,
                                       const float* pool_scale, const float* d_score, const float* u, int64_t ldu,
                                       const float* d_neg, int64_t ld_dneg, int n_neg, const int32_t* node_off,
-                                      int n_graphs, float* dy, int64_t lddy, double* stats, gnm_stream_t stream) {
+                                      int n_graphs, float* dy, int64_t lddy, double* stats, const gnm_bn_tail* tail,
+                                      gnm_stream_t stream) {
     if (n_rows < 0 || n_feat < 0 || n_graphs < 0) return GNM_ERR_BAD_ARG;
     if (n_rows == 0 || n_feat == 0 || n_graphs == 0) return GNM_OK;
     if (!z || !scale || !shift || !mean || !rstd || !node_off || !dy) return GNM_ERR_BAD_ARG;
@@ -651,14 +654,18 @@ extern "C" int gnm_relu_bn_bwd_reduce(const float* z, int64_t ldz, int n_rows, i
     const bool vec = (n_feat % 4 == 0) && n_feat <= 1024 && (ldz % 4 == 0) && (lddy % 4 == 0) && gnm_aligned16(z) &&
                      gnm_aligned16(dy) && gnm_aligned16(scale) && gnm_aligned16(shift) && gnm_aligned16(mean) &&
                      gnm_aligned16(rstd) && (d_out == nullptr || ((ld_dout % 4 == 0) && gnm_aligned16(d_out)));
+    BnTailDev td;
+    const int trc = bn_tail_args(tail, stats, n_feat, &td);
+    if (trc != GNM_OK) return trc;
     if (vec) {
         gnm_count_launch(GNM_K_OTHER);
         relu_bn_bwd_reduce_vec_kernel<<<n_graphs, 256, 0, gnm_cast_stream(stream)>>>(
             z, ldz, n_feat, scale, shift, mean, rstd, d_out, ld_dout, d_pooled, ld_dpooled, pool_scale, d_score, u, ldu,
-            d_neg, ld_dneg, n_neg, node_off, dy, lddy, stats);
+            d_neg, ld_dneg, n_neg, node_off, dy, lddy, stats, td);
         GNM_RETURN_IF_LAUNCH_FAILED();
         return GNM_OK;
     }
+    if (tail != nullptr) return GNM_ERR_TOO_LARGE;      // the scalar kernel has no tail: nothing launched
     dim3 grid(n_graphs, (n_feat + 255) / 256);
     gnm_count_launch(GNM_K_OTHER);
     relu_bn_bwd_reduce_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(

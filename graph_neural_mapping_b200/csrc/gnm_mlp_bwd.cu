@@ -275,7 +275,8 @@ extern "C" int gnm_bn_bwd_coeffs(double* stats, double count, const float* gamma
 int gnm_launch_linear_bwd_dx_tc(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* coef,
                                 const float* x, int64_t ldx, const float* in_scale, const float* in_shift,
                                 const float* in_mean, const float* in_rstd, const float* w, int64_t ldw, float* dx,
-                                int64_t lddx, double* stats_in, int n_rows, int n_out, int n_in, cudaStream_t stream);
+                                int64_t lddx, double* stats_in, int n_rows, int n_out, int n_in, const gnm_bn_tail* tail,
+                                cudaStream_t stream);
 int gnm_launch_linear_wgrad_tc(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* coef,
                                const float* x, int64_t ldx, const float* in_scale, const float* in_shift, float* dw,
                                int64_t lddw, float* dbias, int n_rows, int n_out, int n_in, cudaStream_t stream);
@@ -285,8 +286,9 @@ extern "C" int gnm_linear_bwd(const float* dy, int64_t lddy, const float* z, int
                               const float* x, int64_t ldx, const float* in_scale, const float* in_shift,
                               const float* in_mean, const float* in_rstd, const float* w, int64_t ldw, float* dw,
                               int64_t lddw, float* dbias, float* dx, int64_t lddx, double* stats_in, int n_rows,
-                              int n_out, int n_in, gnm_stream_t stream) {
+                              int n_out, int n_in, const gnm_bn_tail* tail, gnm_stream_t stream) {
     if (n_rows < 0 || n_out <= 0 || n_in <= 0) return GNM_ERR_BAD_ARG;
+    if (tail != nullptr && (dx == nullptr || stats_in == nullptr)) return GNM_ERR_BAD_ARG;
     if (n_out > FB_T || n_in > FB_T) return GNM_ERR_TOO_LARGE;
     if (n_rows == 0) return GNM_OK;
     if (!dy || !z || !coef || !x || !w || !dw) return GNM_ERR_BAD_ARG;
@@ -303,12 +305,13 @@ extern "C" int gnm_linear_bwd(const float* dy, int64_t lddy, const float* z, int
         int rc = GNM_OK;
         if (dx != nullptr)
             rc = gnm_launch_linear_bwd_dx_tc(dy, lddy, z, ldz, coef, x, ldx, in_scale, in_shift, in_mean, in_rstd, w, ldw,
-                                             dx, lddx, stats_in, n_rows, n_out, n_in, gnm_cast_stream(stream));
+                                             dx, lddx, stats_in, n_rows, n_out, n_in, tail, gnm_cast_stream(stream));
         if (rc == GNM_OK)
             rc = gnm_launch_linear_wgrad_tc(dy, lddy, z, ldz, coef, x, ldx, in_scale, in_shift, dw, lddw, dbias, n_rows,
                                             n_out, n_in, gnm_cast_stream(stream));
         if (rc == GNM_OK || impl == 2 || rc != GNM_ERR_TOO_LARGE) return rc;
     }
+    if (tail != nullptr) return GNM_ERR_TOO_LARGE;      // the fused FFMA kernel has no tail: nothing launched
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

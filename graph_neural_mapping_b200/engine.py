@@ -334,7 +334,7 @@ class BatchStructure(object):
                                             src, src_map, dst, mode, eps, bias)
         return _ops.aggregate(self.rowptr, self.colidx, src, src_map, dst, mode, eps, bias)
 
-    def aggregate_relu_bn_bwd(self, src, mode, eps, unit, d_pooled, d_score, u, d_neg, n_neg, dy, stats):
+    def aggregate_relu_bn_bwd(self, src, mode, eps, unit, d_pooled, d_score, u, d_neg, n_neg, dy, stats, tail=None):
         """Backward aggregation of `src` fused with the relu / BatchNorm backward reduction of `unit` (the last unit of
         the layer below) when the batch runs on the tcgen05 dense-block kernel; False, nothing launched, otherwise."""
         if self.bitmap_addr is None or FORCE_CSR_AGGREGATE or FORCE_UNFUSED_BACKWARD or not _ops.dense_aggregate_ok(src, dy):
@@ -343,7 +343,7 @@ class BatchStructure(object):
             return False
         return _ops.aggregate_dense_relu_bn_bwd(self.bitmap_addr, self.node_off, self.rowptr, self.n_graphs, self.n_max,
                                                 src, mode, eps, unit.z, unit.scale, unit.shift, unit.mean, unit.rstd,
-                                                d_pooled, self.pool_scale, d_score, u, d_neg, n_neg, dy, stats)
+                                                d_pooled, self.pool_scale, d_score, u, d_neg, n_neg, dy, stats, tail)
 
     def aggregate_table(self, table, dst, mode, eps, bias, stats, tail=None):
         """Layer 0 as a row gather of `table` when every graph carries the same tag sequence: dst = Agg(table[tags]) (+ self
@@ -496,6 +496,19 @@ def _bn_forward_tail(unit, stats, count, training, comm):
                        eps=bn.eps, momentum=bn.momentum if track else 0.0, running_mean=bn.running_mean if track else None,
                        running_var=bn.running_var if track else None, nbt=bn.num_batches_tracked if track else None,
                        scale=unit.scale, shift=unit.shift, p2p=p2p)
+
+
+def _bn_backward_tail(unit, stats, comm):
+    """(coef, tail) for the BatchNorm backward of `unit`, whose [sum dy, sum dy*xhat] are about to be produced into `stats`:
+    the producer kernel's last CTA all-reduces them (data parallel, peer memory) and writes gnm_bn_bwd_coeffs' output.
+    (None, None) when this BatchNorm ran on running statistics or the exchange needs NCCL."""
+    if not (FOLD_BN_TAILS and unit.count > 0.0 and hasattr(_ops, "BnTail")):
+        return None, None
+    p2p = comm.p2p_for(stats) if comm.world > 1 else None
+    if comm.world > 1 and p2p is None:
+        return None, None
+    coef = torch.empty(3, unit.z.shape[1], dtype=torch.float32, device=unit.z.device)
+    return coef, _ops.BnTail(_ops.BnTail.BWD_COEFFS, unit.count, unit.gamma, unit.mean, unit.rstd, coef=coef, p2p=p2p)
 
 
 def _bn_affine(unit, stats, count, training, comm, done=False):
@@ -768,10 +781,11 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm, max_first
         if layer not in sv.max_state and below.z.shape[1] == dp.shape[1]:
             dy_b = torch.empty(M, dp.shape[1], dtype=torch.float32, device=dev)
             st_b = zp.f64(2 * dp.shape[1])
+            coef_b, tail_b = _bn_backward_tail(below, st_b[0], comm)
             if bs.aggregate_relu_bn_bwd(dp, bwd_mode, eps_l, below, d_pooled[:, slb], d_score,
                                         u_mat[:, slb] if u_mat is not None else None,
-                                        d_neg[:, slb] if d_neg is not None else None, n_neg, dy_b, st_b[0]):
-                return None, (dy_b, st_b)
+                                        d_neg[:, slb] if d_neg is not None else None, n_neg, dy_b, st_b[0], tail_b):
+                return None, (dy_b, st_b, coef_b)
         d_prev = torch.empty(M, dp.shape[1], dtype=torch.float32, device=dev)
         if layer in sv.max_state:
             amax, cmin = sv.max_state[layer]
@@ -792,30 +806,35 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm, max_first
         for j in range(len(units) - 1, -1, -1):
             u = units[j]
             n_out, n_in = u.w.shape[0], u.w.shape[1]
+            coef_ready = None      # gnm_bn_bwd_coeffs' output when the kernel that produced `stats` already ran it (tail)
             if pending is not None:
-                dy, (stats, st_chunk, st_off) = pending
+                dy, (stats, st_chunk, st_off), coef_ready = pending
                 pending = None
             elif j == len(units) - 1 and carry is not None:
-                dy, (stats, st_chunk, st_off) = carry
+                dy, (stats, st_chunk, st_off), coef_ready = carry
                 carry = None
             else:
                 dy = torch.empty(M, n_out, dtype=torch.float32, device=dev)
                 stats, st_chunk, st_off = zp.f64(2 * n_out)
+                coef_t, tail_t = _bn_backward_tail(u, stats, comm)
                 if j == len(units) - 1:
-                    _ops.relu_bn_bwd_reduce(u.z, u.scale, u.shift, u.mean, u.rstd, d_h, d_pooled[:, sl],
-                                            bs.pool_scale, d_score, u_mat[:, sl] if u_mat is not None else None,
-                                            d_neg[:, sl] if d_neg is not None else None, n_neg, bs.node_off, B, dy,
-                                            stats)
+                    took = _ops.relu_bn_bwd_reduce(u.z, u.scale, u.shift, u.mean, u.rstd, d_h, d_pooled[:, sl],
+                                                   bs.pool_scale, d_score, u_mat[:, sl] if u_mat is not None else None,
+                                                   d_neg[:, sl] if d_neg is not None else None, n_neg, bs.node_off, B, dy,
+                                                   stats, tail=tail_t)
                 else:
-                    _ops.relu_bn_bwd_reduce(u.z, u.scale, u.shift, u.mean, u.rstd, dz, None, None, None, None, None,
-                                            0, bs.node_off, B, dy, stats)
+                    took = _ops.relu_bn_bwd_reduce(u.z, u.scale, u.shift, u.mean, u.rstd, dz, None, None, None, None, None,
+                                                   0, bs.node_off, B, dy, stats, tail=tail_t)
+                if took is True:
+                    coef_ready = coef_t
             use_batch = u.count > 0.0
             gather0 = j == 0 and layer == 0 and sv.use_gather0
             fused = (not gather0) and (not FORCE_UNFUSED_BACKWARD) and n_out <= FUSED_BWD_MAX and n_in <= FUSED_BWD_MAX
             p2p = None
-            if use_batch and comm.world > 1:
+            if use_batch and comm.world > 1 and coef_ready is None:
                 # global-batch [sum dy, sum dy*xhat]: exchanged inside bn_bwd_coeffs (fused path) or by the small
-                # peer-memory all-reduce kernel when the ranks share a P2P communicator, else NCCL / gloo
+                # peer-memory all-reduce kernel when the ranks share a P2P communicator, else NCCL / gloo (a tail has
+                # already done the exchange, in place, when coef_ready is set)
                 p2p = comm.p2p_for(stats)
                 if p2p is None:
                     comm.all_reduce_sum(stats)
@@ -832,15 +851,19 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm, max_first
             if fused:
                 # one pass: BatchNorm-backward apply (folded into the load as dz = A*dy + B*z + C), dW, db, dX and -
                 # for an inner unit - the ReLU mask + BatchNorm-backward reduction of the unit below
-                coef = torch.empty(3, n_out, dtype=torch.float32, device=dev)
-                _ops.bn_bwd_coeffs(stats if use_batch else None, u.count, u.gamma, u.mean, u.rstd, coef, p2p=p2p)
+                if coef_ready is not None:
+                    coef = coef_ready
+                else:
+                    coef = torch.empty(3, n_out, dtype=torch.float32, device=dev)
+                    _ops.bn_bwd_coeffs(stats if use_batch else None, u.count, u.gamma, u.mean, u.rstd, coef, p2p=p2p)
                 if j > 0:
                     p = units[j - 1]
                     dy_prev = torch.empty(M, n_in, dtype=torch.float32, device=dev)
                     stats_prev = zp.f64(2 * n_in)
-                    _ops.linear_bwd(dy, u.z, coef, p.z, p.scale, p.shift, p.mean, p.rstd, u.w, dw, db, dy_prev,
-                                    stats_prev[0])
-                    pending = (dy_prev, stats_prev)
+                    coef_p, tail_p = _bn_backward_tail(p, stats_prev[0], comm)
+                    took = _ops.linear_bwd(dy, u.z, coef, p.z, p.scale, p.shift, p.mean, p.rstd, u.w, dw, db, dy_prev,
+                                           stats_prev[0], tail=tail_p)
+                    pending = (dy_prev, stats_prev, coef_p if took is True else None)
                 else:
                     need_dp = layer > 0 or need_x_grad or learn_eps
                     dp = torch.empty(M, n_in, dtype=torch.float32, device=dev) if need_dp else None
@@ -864,8 +887,11 @@ def run_backward(model, sv, params, dg_f, dd_logit, need_x_grad, comm, max_first
             if gather0 and not learn_eps and not (need_x_grad and model.neighbor_pooling_type == "max"):
                 # layer-0 gather unit: dz is only ever aggregated, so the BatchNorm-backward apply rides on the
                 # aggregation kernel's row loads (dz = A*dy + B*z + C is never written); d bias follows in closed form
-                coef0 = torch.empty(3, n_out, dtype=torch.float32, device=dev)
-                _ops.bn_bwd_coeffs(stats if use_batch else None, u.count, u.gamma, u.mean, u.rstd, coef0)
+                if coef_ready is not None:
+                    coef0 = coef_ready
+                else:
+                    coef0 = torch.empty(3, n_out, dtype=torch.float32, device=dev)
+                    _ops.bn_bwd_coeffs(stats if use_batch else None, u.count, u.gamma, u.mean, u.rstd, coef0)
                 g_try = torch.empty(M, n_out, dtype=torch.float32, device=dev)
                 if bs.aggregate_affine(dy, u.z, coef0, g_try, bwd_mode):
                     g_agg = g_try

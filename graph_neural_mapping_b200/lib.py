@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libgnm.so")
-ABI_VERSION = 20
+ABI_VERSION = 21
 
 _c_i32 = ctypes.c_int
 _c_i64 = ctypes.c_int64
@@ -44,12 +44,12 @@ SIGNATURES = {
     "gnm_linear_wgrad": [_p, _c_i64, _p, _c_i64, _c_i32, _c_i32, _c_i32, _p, _p, _p, _c_i64, _p, _p],
     "gnm_bn_bwd_coeffs": [_p, _c_f64, _p, _p, _p, _p, _c_i32, _p, _p],
     "gnm_linear_bwd": [_p, _c_i64, _p, _c_i64, _p, _p, _c_i64, _p, _p, _p, _p, _p, _c_i64, _p, _c_i64, _p, _p, _c_i64,
-                       _p, _c_i32, _c_i32, _c_i32, _p],
+                       _p, _c_i32, _c_i32, _c_i32, _p, _p],
     "gnm_col_stats": [_p, _c_i64, _c_i32, _c_i32, _p, _p],
     "gnm_bn_finalize": [_p, _c_f64, _p, _p, _c_f32, _c_f32, _p, _p, _p, _p, _p, _p, _p, _c_i32, _p, _p],
     "gnm_aggregate_dense_affine": [_p, _p, _p, _c_i32, _c_i32, _p, _c_i64, _p, _c_i64, _p, _p, _c_i64, _c_i32, _c_i32, _p],
     "gnm_aggregate_dense_relu_bn_bwd": [_p, _p, _p, _c_i32, _c_i32, _p, _c_i64, _c_i32, _c_i32, _p, _p, _c_i64, _p, _p, _p, _p,
-                                        _p, _c_i64, _p, _p, _p, _c_i64, _p, _c_i64, _c_i32, _p, _c_i64, _p, _p],
+                                        _p, _c_i64, _p, _p, _p, _c_i64, _p, _c_i64, _c_i32, _p, _c_i64, _p, _p, _p],
     "gnm_col_min": [_p, _c_i64, _c_i32, _c_i32, _p, _p],
     "gnm_aggregate_max": [_p, _p, _c_i32, _p, _c_i64, _c_i32, _p, _p, _p, _c_i64, _p, _p],
     "gnm_aggregate_max_bwd": [_p, _p, _c_i32, _p, _c_i64, _c_i32, _p, _p, _p, _p, _c_i64, _p],
@@ -66,7 +66,7 @@ SIGNATURES = {
     "gnm_bn_eval_affine": [_p, _p, _p, _p, _c_f32, _p, _p, _p, _p, _c_i32, _p],
     "gnm_bn_relu_readout": [_p, _c_i64, _c_i32, _c_i32, _p, _p, _p, _c_i64, _p, _c_i32, _p, _p, _c_i64, _p],
     "gnm_relu_bn_bwd_reduce": [_p, _c_i64, _c_i32, _c_i32, _p, _p, _p, _p, _p, _c_i64, _p, _c_i64, _p, _p, _p,
-                               _c_i64, _p, _c_i64, _c_i32, _p, _c_i32, _p, _c_i64, _p, _p],
+                               _c_i64, _p, _c_i64, _c_i32, _p, _c_i32, _p, _c_i64, _p, _p, _p],
     "gnm_bn_bwd_apply": [_p, _c_i64, _c_i32, _c_i32, _p, _p, _p, _p, _c_f64, _p, _c_i64, _p],
     "gnm_gather_nf_rows": [_p, _c_i64, _c_i32, _c_i32, _c_i64, _c_i32, _p, _p],
     "gnm_dgi_score_fwd": [_p, _c_i64, _c_i32, _c_i32, _c_i64, _c_i32, _p, _p, _p, _p, _c_i32, _p, _p, _p],

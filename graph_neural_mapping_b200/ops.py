@@ -251,7 +251,7 @@ def aggregate_dense_affine(bitmap_addr, node_off, rowptr, n_graphs, n_max, dy, z
 
 
 def aggregate_dense_relu_bn_bwd(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, mode, eps, z, scale, shift, mean, rstd,
-                                d_pooled, pool_scale, d_score, u, d_neg, n_neg, dy, stats):
+                                d_pooled, pool_scale, d_score, u, d_neg, n_neg, dy, stats, tail=None):
     """aggregate_dense(src) -> relu_bn_bwd_reduce(z, ...) in one tcgen05 kernel (the aggregated gradient is consumed in
     the copy-out). Returns False, with nothing launched, when the batch does not fit that kernel."""
     sp, lds = _mat(src)
@@ -265,7 +265,7 @@ def aggregate_dense_relu_bn_bwd(bitmap_addr, node_off, rowptr, n_graphs, n_max, 
                                                 int(mode), _ptr(eps, torch.float32), zp, ldz, _ptr(scale), _ptr(shift),
                                                 _ptr(mean), _ptr(rstd), gp, ldg, _ptr(pool_scale, torch.float32),
                                                 _ptr(d_score, torch.float32), up, ldu, np_, ldn, int(n_neg), yp, ldy,
-                                                _ptr(stats, torch.float64), _stream(dy))
+                                                _ptr(stats, torch.float64), _tail_ref(tail), _stream(dy))
     if rc in (-2, -3):                      # GNM_ERR_TOO_LARGE / GNM_ERR_ALIGN: not a tcgen05 batch
         LAUNCHES[0] -= 1
         return False
@@ -550,18 +550,27 @@ def bn_bwd_coeffs(stats, count, gamma, mean, rstd, coef, p2p=None):
     return coef
 
 
-def linear_bwd(dy, z, coef, x, in_scale, in_shift, in_mean, in_rstd, w, dw, dbias, dx, stats_in):
+def linear_bwd(dy, z, coef, x, in_scale, in_shift, in_mean, in_rstd, w, dw, dbias, dx, stats_in, tail=None):
+    """tail: BnTail(BWD_COEFFS) of the unit below, run on stats_in by the dx kernel's last CTA. Returns True when the tail
+    was taken, False when the shape runs on the kernel without tails (the backward was still computed)."""
     yp, ldy = _mat(dy)
     zp, ldz = _mat(z)
     xp, ldx = _mat(x)
     wp, ldw = _mat(w)
     gp, ldg = _mat(dw)
     dp, ldd = _mat(dx)
-    _libmod.check(_lib().gnm_linear_bwd(yp, ldy, zp, ldz, _ptr(coef, torch.float32), xp, ldx, _ptr(in_scale),
-                                        _ptr(in_shift), _ptr(in_mean), _ptr(in_rstd), wp, ldw, gp, ldg,
-                                        _ptr(dbias, torch.float32), dp, ldd, _ptr(stats_in, torch.float64),
-                                        int(dy.shape[0]), int(w.shape[0]), int(w.shape[1]), _stream(dy)),
-                  "gnm_linear_bwd")
+    args = (yp, ldy, zp, ldz, _ptr(coef, torch.float32), xp, ldx, _ptr(in_scale), _ptr(in_shift), _ptr(in_mean), _ptr(in_rstd),
+            wp, ldw, gp, ldg, _ptr(dbias, torch.float32), dp, ldd, _ptr(stats_in, torch.float64), int(dy.shape[0]),
+            int(w.shape[0]), int(w.shape[1]))
+    if tail is not None:
+        rc = _lib().gnm_linear_bwd(*args, tail.ref(), _stream(dy))
+        if rc == 0:
+            return True
+        if rc != -2:
+            _libmod.check(rc, "gnm_linear_bwd")
+        LAUNCHES[0] -= 1
+    _libmod.check(_lib().gnm_linear_bwd(*args, None, _stream(dy)), "gnm_linear_bwd")
+    return False
 
 
 def col_stats(x, stats):
@@ -600,18 +609,26 @@ def bn_relu_readout(z, scale, shift, h, node_off, n_graphs, pool_scale, pooled):
 
 
 def relu_bn_bwd_reduce(z, scale, shift, mean, rstd, d_out, d_pooled, pool_scale, d_score, u, d_neg, n_neg,
-                       node_off, n_graphs, dy, stats):
+                       node_off, n_graphs, dy, stats, tail=None):
+    """Returns True when `tail` (BnTail BWD_COEFFS) was run by the kernel's last CTA."""
     zp, ldz = _mat(z)
     op, ldo = _mat(d_out)
     gp, ldg = _mat(d_pooled)
     up, ldu = _mat(u)
     np_, ldn = _mat(d_neg)
     yp, ldy = _mat(dy)
-    _libmod.check(_lib().gnm_relu_bn_bwd_reduce(zp, ldz, int(z.shape[0]), int(z.shape[1]), _ptr(scale), _ptr(shift),
-                                                _ptr(mean), _ptr(rstd), op, ldo, gp, ldg,
-                                                _ptr(pool_scale, torch.float32), _ptr(d_score, torch.float32), up, ldu,
-                                                np_, ldn, int(n_neg), _ptr(node_off, torch.int32), n_graphs, yp, ldy,
-                                                _ptr(stats, torch.float64), _stream(z)), "gnm_relu_bn_bwd_reduce")
+    args = (zp, ldz, int(z.shape[0]), int(z.shape[1]), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), op, ldo, gp, ldg,
+            _ptr(pool_scale, torch.float32), _ptr(d_score, torch.float32), up, ldu, np_, ldn, int(n_neg),
+            _ptr(node_off, torch.int32), n_graphs, yp, ldy, _ptr(stats, torch.float64))
+    if tail is not None:
+        rc = _lib().gnm_relu_bn_bwd_reduce(*args, tail.ref(), _stream(z))
+        if rc == 0:
+            return True
+        if rc != -2:
+            _libmod.check(rc, "gnm_relu_bn_bwd_reduce")
+        LAUNCHES[0] -= 1
+    _libmod.check(_lib().gnm_relu_bn_bwd_reduce(*args, None, _stream(z)), "gnm_relu_bn_bwd_reduce")
+    return False
 
 
 def bn_bwd_apply(z, mean, rstd, gamma, stats, count, dy):

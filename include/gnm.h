@@ -33,7 +33,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 20
+#define GNM_ABI_VERSION 21
 
 typedef void* gnm_stream_t;
 
@@ -191,7 +191,7 @@ int gnm_aggregate_dense_relu_bn_bwd(const int64_t* bitmap_addr, const int32_t* n
                                     const float* z, int64_t ldz, const float* scale, const float* shift, const float* mean,
                                     const float* rstd, const float* d_pooled, int64_t ld_dpooled, const float* pool_scale,
                                     const float* d_score, const float* u, int64_t ldu, const float* d_neg, int64_t ld_dneg,
-                                    int n_neg, float* dy, int64_t lddy, double* stats, gnm_stream_t stream);
+                                    int n_neg, float* dy, int64_t lddy, double* stats, const gnm_bn_tail* tail, gnm_stream_t stream);
 /* *aborted = 1 if a tcgen05 kernel (aggregation or linear) launched since the last call ran into a (bounded) barrier-wait timeout
  * and drained without producing valid output. Synchronises the device; meant for tests / smoke checks. */
 int gnm_aggregate_tc_status(int* aborted);
@@ -262,7 +262,7 @@ int gnm_linear_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, c
                    const float* x, int64_t ldx, const float* in_scale, const float* in_shift,
                    const float* in_mean, const float* in_rstd, const float* w, int64_t ldw,
                    float* dw, int64_t lddw, float* dbias, float* dx, int64_t lddx, double* stats_in,
-                   int n_rows, int n_out, int n_in, gnm_stream_t stream);
+                   int n_rows, int n_out, int n_in, const gnm_bn_tail* tail, gnm_stream_t stream);
 
 /* Per-column sum / sum of squares (double [2F], +=) of a [M, F] matrix. */
 int gnm_col_stats(const float* x, int64_t ldx, int n_rows, int n_feat, double* col_stats, gnm_stream_t stream);
@@ -304,7 +304,7 @@ int gnm_relu_bn_bwd_reduce(const float* z, int64_t ldz, int n_rows, int n_feat,
                            const float* d_score, const float* u, int64_t ldu,
                            const float* d_neg, int64_t ld_dneg, int n_neg,
                            const int32_t* node_off, int n_graphs,
-                           float* dy, int64_t lddy, double* stats, gnm_stream_t stream);
+                           float* dy, int64_t lddy, double* stats, const gnm_bn_tail* tail, gnm_stream_t stream);
 
 /* Backward of batchnorm, pass 2 (in place on dy):
  * training: dz = gamma*rstd*(dy - stats_sum/count - xhat*stats_dot/count); eval (stats == NULL): dz = dy*gamma*rstd. */

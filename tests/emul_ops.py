@@ -114,7 +114,7 @@ def dense_aggregate_ok(src, dst, bias=None):
 
 
 def aggregate_dense_relu_bn_bwd(bitmap_addr, node_off, rowptr, n_graphs, n_max, src, mode, eps, z, scale, shift, mean, rstd,
-                                d_pooled, pool_scale, d_score, u, d_neg, n_neg, dy, stats):
+                                d_pooled, pool_scale, d_score, u, d_neg, n_neg, dy, stats, tail=None):
     if n_max > 416 or dy.shape[1] > 64:
         return False
     d_h = torch.empty_like(dy)
@@ -263,7 +263,7 @@ def bn_bwd_coeffs(stats, count, gamma, mean, rstd, coef, p2p=None):
     return coef
 
 
-def linear_bwd(dy, z, coef, x, in_scale, in_shift, in_mean, in_rstd, w, dw, dbias, dx, stats_in):
+def linear_bwd(dy, z, coef, x, in_scale, in_shift, in_mean, in_rstd, w, dw, dbias, dx, stats_in, tail=None):
     dz = (coef[0] * dy + coef[1] * z + coef[2]).double()
     a = _act(x, in_scale, in_shift).double()
     dw += (dz.t() @ a).float()
@@ -333,7 +333,7 @@ def bn_relu_readout(z, scale, shift, h, node_off, n_graphs, pool_scale, pooled):
 
 
 def relu_bn_bwd_reduce(z, scale, shift, mean, rstd, d_out, d_pooled, pool_scale, d_score, u, d_neg, n_neg,
-                       node_off, n_graphs, dy, stats):
+                       node_off, n_graphs, dy, stats, tail=None):
     m, f = z.shape
     gid = _graph_of_row(node_off, m)
     g = torch.zeros(m, f, dtype=torch.float32)

@@ -44,4 +44,4 @@ def test_argument_checks_need_no_gpu():
     assert l.gnm_aggregate(None, None, 0, None, 0, None, None, 0, 4, 0, None, None, None) == 0
     assert l.gnm_linear(None, 0, 0, 4, None, 0, 0, None, None, None, None, 0, 4, None, None, None) == 0
     assert l.gnm_linear_bwd(None, 0, None, 0, None, None, 0, None, None, None, None, None, 0, None, 0, None, None, 0,
-                            None, 10, 100, 4, None) == -2
+                            None, 10, 100, 4, None, None) == -2
