@@ -1,9 +1,10 @@
 """Per-source-line digest of an `ncu --set full --import-source on` report: stall samples, executed warp instructions,
-dominant stall reasons, shared-memory wavefront excess. usage: ncu_src_lines.py report.ncu-rep [top]"""
+dominant stall reasons, shared-memory wavefront excess.
+usage: ncu_src_lines.py report.ncu-rep [top] [extra `ncu -i` filters, e.g. --kernel-name regex:aggregate_tc --launch-count 1]"""
 import csv, io, subprocess, sys
 from collections import defaultdict
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv", "--print-source", "cuda,sass"],
+out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv", "--print-source", "cuda,sass"] + sys.argv[3:],
                      capture_output=True, text=True).stdout
 path, hdr = None, None
 lines = []
