@@ -367,19 +367,23 @@ relu_bn_bwd_reduce_vec_kernel(const float* __restrict__ z, int64_t ldz, int n_fe
                               const float* __restrict__ d_pooled, int64_t ld_dpooled,
                               const float* __restrict__ pool_scale, const float* __restrict__ d_score,
                               const float* __restrict__ u, int64_t ldu, const float* __restrict__ d_neg,
-                              int64_t ld_dneg, int n_neg, const int32_t* __restrict__ node_off,
+                              int64_t ld_dneg, int n_neg, const int32_t* __restrict__ node_off, int n_graphs,
                               float* __restrict__ dy, int64_t lddy, double* __restrict__ stats, const BnTailDev tail) {
-    const int g = blockIdx.x;
+    // persistent over graphs: a thread owns the same four columns for every graph, so the column sums stay in
+    // registers and each CTA issues ONE set of fp64 atomics (same-address atomics of a CTA per graph serialised in L2)
     const int lpr = n_feat >> 2;
     const int rpp = 256 / lpr;
     const int sub = threadIdx.x % lpr, rr = threadIdx.x / lpr;
     __shared__ float4 red1[256], red2[256];
-    const int r0 = node_off[g], r1 = node_off[g + 1];
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+    const int f = sub * 4;
+    float4 sc = s1, sh = s1, mu = s1, rs = s1;
     if (rr < rpp) {
-        const int f = sub * 4;
-        const float4 sc = *reinterpret_cast<const float4*>(scale + f), sh = *reinterpret_cast<const float4*>(shift + f);
-        const float4 mu = *reinterpret_cast<const float4*>(mean + f), rs = *reinterpret_cast<const float4*>(rstd + f);
+        sc = *reinterpret_cast<const float4*>(scale + f); sh = *reinterpret_cast<const float4*>(shift + f);
+        mu = *reinterpret_cast<const float4*>(mean + f); rs = *reinterpret_cast<const float4*>(rstd + f);
+    }
+    for (int g = blockIdx.x; g < n_graphs && rr < rpp; g += gridDim.x) {
+        const int r0 = node_off[g], r1 = node_off[g + 1];
         float4 gp = make_float4(0.f, 0.f, 0.f, 0.f), uu = gp;
         if (d_pooled != nullptr) {
             const float ps = pool_scale ? pool_scale[g] : 1.f;
@@ -390,6 +394,7 @@ relu_bn_bwd_reduce_vec_kernel(const float* __restrict__ z, int64_t ldz, int n_fe
             const float* q = u + (int64_t)g * ldu + f;
             uu = make_float4(q[0], q[1], q[2], q[3]);
         }
+#pragma unroll 2
         for (int r = r0 + rr; r < r1; r += rpp) {
             const float4 zv = ld_stream_f4(z + (int64_t)r * ldz + f);
             float4 gr = gp;
@@ -659,9 +664,10 @@ extern "C" int gnm_relu_bn_bwd_reduce(const float* z, int64_t ldz, int n_rows, i
     if (trc != GNM_OK) return trc;
     if (vec) {
         gnm_count_launch(GNM_K_OTHER);
-        relu_bn_bwd_reduce_vec_kernel<<<n_graphs, 256, 0, gnm_cast_stream(stream)>>>(
+        const int grid = n_graphs < 148 * 4 ? n_graphs : 148 * 4;
+        relu_bn_bwd_reduce_vec_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(
             z, ldz, n_feat, scale, shift, mean, rstd, d_out, ld_dout, d_pooled, ld_dpooled, pool_scale, d_score, u, ldu,
-            d_neg, ld_dneg, n_neg, node_off, dy, lddy, stats, td);
+            d_neg, ld_dneg, n_neg, node_off, n_graphs, dy, lddy, stats, td);
         GNM_RETURN_IF_LAUNCH_FAILED();
         return GNM_OK;
     }
