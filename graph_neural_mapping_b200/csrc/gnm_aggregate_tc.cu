@@ -40,7 +40,8 @@ constexpr int TC_A_COLS = TC_KC / 2;           // TMEM columns per A stage (two 
 constexpr int TC_A_TMEM0 = 384;                // first TMEM column of the A ring (after the two accumulator slots)
 constexpr int TC_N = 192;                      // three 64-feature planes side by side
 constexpr int TC_SLAB = 64;
-constexpr int TC_MAX_NODES = 416;
+constexpr int TC_MAX_NODES = 416;               // largest graph whose planes fit shared memory in ONE pass
+constexpr int TC_K_PASS = 448;                  // larger graphs: passes over K ranges of this many nodes, dst accumulated
 constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 8;       // 4: one epilogue group drains both slots; 8: one group per slot
 constexpr int TC_PITCH = TC_SLAB + 4;                    // floats per staged output row (272 B: conflict-optimal)
 constexpr int TC_STG = 32 * TC_PITCH * 4;                // bytes of one epilogue warp's staging tile
@@ -78,6 +79,9 @@ struct AggTcParams {
     // stay resident; out_stats (nullable) += [sum, sum of squares] per column of the rows written (BatchNorm statistics)
     int b_shared;
     double* out_stats;
+    // graphs of more than TC_MAX_NODES nodes (TCV_KSPLIT variants): this launch covers adjacency columns / feature rows
+    // [k_lo, k_lo + k_pass) of every graph; accumulate != 0 adds the result to what dst already holds
+    int k_lo, k_pass, accumulate;
     BnTailDev tail;              // BatchNorm tail on out_stats (forward) or r_stats (fused backward); kind 0: none
     long long* dbg;              // nullable: per-CTA wait/busy cycle counters (profiling aid)
 };
@@ -86,7 +90,7 @@ struct AggTcParams {
 // at the same time, and the all-in-one kernel - 81 KB of SASS - lost 20 % to instruction fetch and dead branches):
 //   TCV_FUSE relu / BatchNorm-backward consumer in the copy-out, TCV_AFF affine of two streams on the B rows,
 //   TCV_MAP row map / bias / shared table / output statistics (layer 0), TCV_EPS (1 + eps) self term, TCV_AVG degree weights.
-enum { TCV_FUSE = 1, TCV_AFF = 2, TCV_MAP = 4, TCV_EPS = 8, TCV_AVG = 16, TCV_ALL = 31 };
+enum { TCV_FUSE = 1, TCV_AFF = 2, TCV_MAP = 4, TCV_EPS = 8, TCV_AVG = 16, TCV_ALL = 31, TCV_KSPLIT = 32 };
 
 // bulk prefetch of [ptr, ptr + bytes) into L2 (no destination, no completion tracking); 16-byte granularity
 __device__ __forceinline__ void l2_prefetch(const void* ptr, int64_t bytes) {
@@ -98,7 +102,8 @@ __device__ __forceinline__ void l2_prefetch(const void* ptr, int64_t bytes) {
 template <bool DBG, int VAR>
 __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTcParams p) {
     constexpr bool kFuse = (VAR & TCV_FUSE) != 0, kAff = (VAR & TCV_AFF) != 0, kMap = (VAR & TCV_MAP) != 0,
-                   kEps = (VAR & TCV_EPS) != 0, kAvg = (VAR & TCV_AVG) != 0;
+                   kEps = (VAR & TCV_EPS) != 0, kAvg = (VAR & TCV_AVG) != 0, kSplit = (VAR & TCV_KSPLIT) != 0;
+    const int k_lo = kSplit ? p.k_lo : 0;
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 6];
     __shared__ uint32_t s_tmem;
@@ -175,6 +180,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             const int n0 = p.node_off[gi], n = p.node_off[gi + 1] - n0;
             const int f0 = slab * TC_SLAB;
             const int n_mt = (n + 127) >> 7;
+            // K-split pass without columns for this graph: the MMA thread publishes an untouched accumulator; keep the
+            // barrier protocol going but neither read it nor write dst
+            const bool have_k = !kSplit || n > k_lo;
             float4 r_gp = make_float4(0.f, 0.f, 0.f, 0.f), r_uu = r_gp;
             if (fuse && (lane & 15) * 4 < p.n_feat) {
                 const int c = (lane & 15) * 4;
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 float deg = 1.f;
                 if (kAvg && p.mode == 1) deg = (float)(p.rowptr[gr + 1] - p.rowptr[gr]);
                 // a warp whose 32 rows all lie beyond the graph (the tail of the last row tile) has nothing to drain
-                const bool any_rows = row0 < n;
+                const bool any_rows = row0 < n && have_k;
                 if (any_rows) {
 #pragma unroll 1
                     for (int c0 = 0; c0 < TC_SLAB; c0 += 16) {
@@ -259,6 +267,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                             if (!col_ok || row0 + rr >= n) continue;
                             const int g2 = n0 + row0 + rr;
                             float4 v = *reinterpret_cast<const float4*>(stg + rr * TC_PITCH + c4 * 4);
+                            if (kSplit && p.accumulate) {
+                                const float4 o = *reinterpret_cast<const float4*>(p.dst + (int64_t)g2 * p.ld_dst + col);
+                                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                            }
                             if (kEps && p.eps) {
                                 const int64_t sr = (kMap && p.src_map) ? (int64_t)p.src_map[p.b_shared ? row0 + rr : g2] : (int64_t)g2;
                                 const float4 sv = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
@@ -339,7 +351,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 const int gi = item / p.n_slabs;
                 const int n = p.node_off[gi + 1] - p.node_off[gi];
                 const int n_mt = (n + 127) >> 7;
-                const int ksteps_total = (n + 15) >> 4;
+                const int nk = kSplit ? max(0, min(p.k_pass, n - k_lo)) : n;
+                const int ksteps_total = (nk + 15) >> 4;
                 const int n_kc = (ksteps_total + 3) >> 2;
                 for (int mt = 0; mt < n_mt && ok; ++mt, ++acc_it) {
                     const uint32_t slot = acc_it & 1, ph = (acc_it >> 1) & 1;
@@ -386,7 +399,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         // Item parameters are fetched one item ahead (their dependent global loads - node offsets, bitmap address -
         // would otherwise stall every item start), and the next item's first bitmap words and first feature chunk are
         // requested during the current item's last row tile, when the B registers are idle.
-        struct ItemP { int n0, n, f0, n_mt, n_kc, ksteps_total, words; const uint32_t* bm; };
+        struct ItemP { int n0, n, nk, f0, n_mt, n_kc, ksteps_total, words; const uint32_t* bm; };
         auto fetch_item = [&](int item, ItemP& q) {
             if (item < n_items) {
                 const int gi = item / p.n_slabs, slab = item % p.n_slabs;
@@ -400,7 +413,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         };
         auto derive_item = [&](ItemP& q) {
             q.n_mt = (q.n + 127) >> 7;
-            q.ksteps_total = (q.n + 15) >> 4;
+            q.nk = kSplit ? max(0, min(p.k_pass, q.n - k_lo)) : q.n;      // K extent of this pass
+            q.ksteps_total = (q.nk + 15) >> 4;
             q.n_kc = (q.ksteps_total + 3) >> 2;
             q.words = (q.n + 31) >> 5;
         };
@@ -410,13 +424,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         auto load_words = [&](const ItemP& q, int mt, uint32_t it0, uint32_t (&w)[MYC][2]) {
             const int r = mt * 128 + arow;
             const bool rok = mt < q.n_mt && r < q.n;
-            const uint32_t* rowbits = q.bm + (size_t)(rok ? r : 0) * q.words;
+            const int wo = k_lo >> 5;                                 // first bitmap word of this pass's column range
+            const uint32_t* rowbits = q.bm + (size_t)(rok ? r : 0) * q.words + wo;
             const int first = ((it0 & 1) == (uint32_t)grp) ? 0 : 1;  // first chunk of the tile owned by this group
 #pragma unroll
             for (int c = 0; c < MYC; ++c) {
                 const int kc = first + 2 * c;
-                w[c][0] = (rok && kc < q.n_kc && 2 * kc < q.words) ? __ldg(rowbits + 2 * kc) : 0u;
-                w[c][1] = (rok && kc < q.n_kc && 2 * kc + 1 < q.words) ? __ldg(rowbits + 2 * kc + 1) : 0u;
+                w[c][0] = (rok && kc < q.n_kc && wo + 2 * kc < q.words) ? __ldg(rowbits + 2 * kc) : 0u;
+                w[c][1] = (rok && kc < q.n_kc && wo + 2 * kc + 1 < q.words) ? __ldg(rowbits + 2 * kc + 1) : 0u;
             }
         };
         // A stage belongs to ONE group of four warps (the groups alternate stages and run as two independent
@@ -438,15 +453,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 aff_c = __ldg(reinterpret_cast<const float4*>(p.aff_coef + 2 * p.n_feat + col));
                 aff_col = col;
             }
-            const float* rowp = p.src + (int64_t)(q.n0 + kbase) * p.ld_src + col;
-            const float* zrow = kAff ? p.aff_z + (int64_t)(q.n0 + kbase) * p.ld_aff_z + col : nullptr;
+            const float* rowp = p.src + (int64_t)(q.n0 + k_lo + kbase) * p.ld_src + col;
+            const float* zrow = kAff ? p.aff_z + (int64_t)(q.n0 + k_lo + kbase) * p.ld_aff_z + col : nullptr;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int k = kbase + u * 8;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok0 && k < q.n) {
+                if (ok0 && k < q.nk) {
                     if (kMap && p.src_map) {
-                        const int64_t sr = (int64_t)p.src_map[p.b_shared ? k : q.n0 + k];
+                        const int64_t sr = (int64_t)p.src_map[p.b_shared ? k : q.n0 + k_lo + k];
                         v = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
                     } else {
                         v = __ldg(reinterpret_cast<const float4*>(rowp + (int64_t)(u * 8) * p.ld_src));
@@ -457,7 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                         v.z = fmaf(aff_a.z, v.z, fmaf(aff_b.z, zv.z, aff_c.z)); v.w = fmaf(aff_a.w, v.w, fmaf(aff_b.w, zv.w, aff_c.w));
                     }
                     if (kAvg && p.mode == 2) {
-                        const int jr = q.n0 + k;
+                        const int jr = q.n0 + k_lo + k;
                         const float w = 1.f / (float)(p.rowptr[jr + 1] - p.rowptr[jr]);
                         v.x *= w; v.y *= w; v.z *= w; v.w *= w;
                     }
@@ -609,7 +624,12 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
                             int64_t ld_dst, int n_feat, int mode, const float* eps, const float* bias,
                             const float* aff_coef, const float* aff_z, int64_t ld_aff_z, const GnmReluBnBwdFuse* fuse,
                             int b_shared, double* out_stats, const gnm_bn_tail* tail, cudaStream_t stream) {
-    if (n_max > TC_MAX_NODES) return GNM_ERR_TOO_LARGE;
+    // graphs above TC_MAX_NODES nodes: K-split passes (plain / eps / row-map variants of sum pooling and of the transposed
+    // average, mode 2); the fused consumers, the shared table and the forward average (division of the TOTAL) stay single-pass
+    const bool ksplit = n_max > TC_MAX_NODES;
+    if (ksplit && (n_max > 8192 || fuse != nullptr || aff_coef != nullptr || out_stats != nullptr || b_shared || mode == 1 ||
+                   tail != nullptr))
+        return GNM_ERR_TOO_LARGE;
     if (tail != nullptr && out_stats == nullptr && (fuse == nullptr || fuse->stats == nullptr)) return GNM_ERR_BAD_ARG;
     if ((out_stats != nullptr || b_shared) && (n_feat > TC_SLAB || fuse != nullptr || aff_coef != nullptr || mode == 2))
         return GNM_ERR_TOO_LARGE;              // one 64-wide slab per lane; a shared table has no per-graph row weights
@@ -647,11 +667,12 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
         p.r_dneg = fuse->d_neg; p.ld_dneg = fuse->ld_dneg; p.r_nneg = fuse->n_neg; p.r_stats = fuse->stats;
     }
     p.b_shared = b_shared; p.out_stats = out_stats;
+    p.k_lo = 0; p.k_pass = 0; p.accumulate = 0;
     const int trc = bn_tail_args(tail, out_stats != nullptr ? out_stats : (fuse ? fuse->stats : nullptr), n_feat, &p.tail);
     if (trc != GNM_OK) return trc;
     p.dbg = g_tc_dbg_host;
     p.n_slabs = (n_feat + TC_SLAB - 1) / TC_SLAB;
-    p.kcores_max = ((n_max + 15) / 16) * 2;
+    p.kcores_max = (((ksplit ? TC_K_PASS : n_max) + 15) / 16) * 2;
     // B planes + staging + LUT (+ the z tiles of the fused relu / BatchNorm backward)
     const int smem = 24 * (p.kcores_max * 128 + 16) + TC_EPI_WARPS * TC_STG + 4096 + 1024 + (fuse ? TC_EPI_WARPS * TC_STG : 0);
     if (smem > smem_cap - 1024) return GNM_ERR_TOO_LARGE;
@@ -661,6 +682,20 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
     int var = (fuse ? TCV_FUSE : 0) | (aff_coef ? TCV_AFF : 0) | ((src_map || bias || out_stats || b_shared) ? TCV_MAP : 0) |
               (eps ? TCV_EPS : 0) | (mode != 0 ? TCV_AVG : 0);
     cudaError_t e;
+    if (ksplit) {
+        // pass 0 carries the self term and the bias, later passes add their columns' contribution to dst
+        for (int k_lo = 0; k_lo < n_max; k_lo += TC_K_PASS) {
+            p.k_lo = k_lo; p.k_pass = TC_K_PASS; p.accumulate = k_lo > 0;
+            if (k_lo > 0) { p.eps = nullptr; p.bias = nullptr; }
+            const int v2 = ((src_map || bias) ? TCV_MAP : 0) | (eps ? TCV_EPS : 0);
+            if (mode == 2) e = launch_variant<false, TCV_KSPLIT | TCV_AVG | TCV_MAP | TCV_EPS>(p, grid, smem, stream);
+            else if (v2 == 0) e = launch_variant<false, TCV_KSPLIT>(p, grid, smem, stream);
+            else if (v2 == TCV_EPS) e = launch_variant<false, TCV_KSPLIT | TCV_EPS>(p, grid, smem, stream);
+            else e = launch_variant<false, TCV_KSPLIT | TCV_MAP | TCV_EPS>(p, grid, smem, stream);
+            if (e != cudaSuccess) return (int)e;
+        }
+        return GNM_OK;
+    }
     if (p.dbg != nullptr) {
         e = var == 0 ? launch_variant<true, 0>(p, grid, smem, stream) : launch_variant<true, TCV_ALL>(p, grid, smem, stream);
         return e == cudaSuccess ? GNM_OK : (int)e;

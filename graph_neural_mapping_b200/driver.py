@@ -22,6 +22,7 @@ import torch
 
 from . import dist as _dist
 from . import engine as _engine
+from . import graphed as _graphed
 from . import ops as _ops
 
 
@@ -166,7 +167,7 @@ class _WholeStepPlan(object):
         if self.graph is None:
             g = torch.cuda.CUDAGraph()
             n0 = _ops.kernels_recorded()
-            with torch.cuda.graph(g):
+            with _graphed.quiet_capture(), torch.cuda.graph(g):
                 self.loss = self.body()
             self.launches = _ops.kernels_recorded() - n0     # libgnm kernels inside the graph (C-side counters)
             _ops.REPLAYED[0] -= self.launches                # capture records, replay launches

@@ -22,6 +22,26 @@ from . import engine as _engine
 from . import ops as _ops
 
 
+import contextlib
+import gc
+
+
+@contextlib.contextmanager
+def quiet_capture():
+    """Around a CUDA-graph capture: Python's cyclic garbage collector must not run inside it. Collecting an old plan
+    (a CUDAGraph with its private memory pool, pinned staging buffers) calls cudaGraphExecDestroy / cudaFree-class APIs,
+    which are not permitted while a stream is capturing and invalidate the capture ("operation not permitted when
+    stream is capturing" at capture_end, seen once in a long test process). Collect first, then hold the collector."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was_enabled:
+            gc.enable()
+
+
 class StepPlan(object):
     """Static buffers + captured graphs for one (B, N, flags) training-step shape."""
 
@@ -94,7 +114,7 @@ class StepPlan(object):
             g = torch.cuda.CUDAGraph()
             params = [p.detach() for p in _engine.flat_params(model)]
             n0 = _ops.kernels_recorded()
-            with torch.cuda.graph(g, pool=self.pool):
+            with quiet_capture(), torch.cuda.graph(g, pool=self.pool):
                 bs = self._structure()
                 g_f, d_logit, sv = _engine.run_forward(model, bs, self.neg_idx, True, True, None, params, self.comm)
             self.fwd_launches = _ops.kernels_recorded() - n0   # libgnm kernels inside the graph (C-side counters)
@@ -114,7 +134,7 @@ class StepPlan(object):
             self.dd_in.copy_(dd_logit)
             g = torch.cuda.CUDAGraph()
             n0 = _ops.kernels_recorded()
-            with torch.cuda.graph(g, pool=self.pool):
+            with quiet_capture(), torch.cuda.graph(g, pool=self.pool):
                 _, grads = _engine.run_backward(self.model, self.sv, self.params, self.dg_in, self.dd_in, False,
                                                 self.comm)
                 self.grad_shapes = [None if x is None else tuple(x.shape) for x in grads]

@@ -1,5 +1,5 @@
 """Micro-benchmark / ncu target for the neighbour-aggregation kernels at the benchmark shape
-(B graphs x N=400 nodes, F=64): python tests/probes/agg_bench.py [B] [iters] [impl ...]"""
+(B graphs x N nodes, F features): python tests/probes/agg_bench.py [B] [iters] [impl] [N] [F]"""
 import os
 import sys
 
@@ -13,12 +13,13 @@ from graph_neural_mapping_b200 import engine, ops, synth  # noqa: E402
 def main():
     b = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-    impls = [int(x) for x in sys.argv[3:]] or [2, 1, 0]
+    impls = [int(x) for x in sys.argv[3:4]] or [2, 1, 0]
+    n_nodes = int(sys.argv[4]) if len(sys.argv) > 4 else 400
     dev = torch.device("cuda")
-    graphs = synth.make_graphs_bulk(b, 400, 30, 128, seed0=0, device=dev)
+    graphs = synth.make_graphs_bulk(b, n_nodes, 30, 128, seed0=0, device=dev)
     store = engine.GraphStore(dev, add_self_loops=True)
     bs = store.assemble(graphs)
-    m, f = bs.n_rows, 64
+    m, f = bs.n_rows, (int(sys.argv[5]) if len(sys.argv) > 5 else 64)
     torch.manual_seed(0)
     src = torch.randn(m, f, device=dev)
     dst = torch.empty(m, f, device=dev)

@@ -356,8 +356,9 @@ def _bitmaps(rp_local, ci_local, no, counts):
 @pytest.mark.parametrize("mode,use_eps,use_map", [(0, True, False), (0, False, False), (1, True, False), (2, False, False),
                                                    (0, True, True)])
 def test_aggregate_dense_matches_csr_and_oracle(counts, f, mode, use_eps, use_map, impl):
-    if impl == 2 and max(counts) > 416:
-        pytest.skip("tcgen05 kernel holds graphs of <= 416 nodes (the dispatcher falls back to mma.sync)")
+    if impl == 2 and max(counts) > 416 and mode == 1:
+        pytest.skip("graphs above 416 nodes run the tcgen05 kernel in K-split passes; the forward average (a division of "
+                    "the accumulated total) stays on the mma.sync kernel")
     if len(counts) > 100 and (f != 64 or mode != 0):
         pytest.skip("the many-graph case (persistent CTAs wrap around) is run for F=64, sum pooling")
     rng = np.random.default_rng(len(counts) * 100 + f + mode)
