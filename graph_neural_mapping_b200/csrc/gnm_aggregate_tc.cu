@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     float* sm_zst = reinterpret_cast<float*>(tc_smem + (size_t)24 * b_ncore_stride + TC_EPI_WARPS * TC_STG + 4096);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
     for (int i = tid; i < 16 * 32; i += TC_THREADS) {
         const uint32_t e = (uint32_t)i >> 5;
         lut[i] = make_uint2(bits2_bf16x2(e), bits2_bf16x2(e >> 2));
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     tc_fence_after();
     const uint32_t tmem = s_tmem;
     const int n_items = p.n_graphs * p.n_slabs;
+    pdl_wait();          // set-up done (nothing above read global memory): now wait for the kernel in front of this one
 
     if (warp < TC_EPI_WARPS) {
         // ================================ epilogue: TMEM -> registers -> staging tile -> global ===========
@@ -610,8 +612,7 @@ cudaError_t launch_variant(const AggTcParams& p, int grid, int smem, cudaStream_
     cudaError_t e = cudaFuncSetAttribute(aggregate_tc_kernel<DBG, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     gnm_count_launch(GNM_K_AGG_TC);
-    aggregate_tc_kernel<DBG, VAR><<<grid, TC_THREADS, smem, stream>>>(p);
-    return cudaGetLastError();
+    return gnm_launch_pdl<AggTcParams>(aggregate_tc_kernel<DBG, VAR>, grid, TC_THREADS, smem, stream, p);
 }
 
 }  // namespace

@@ -20,6 +20,36 @@ enum GnmKernelFamily {
 };
 void gnm_count_launch(int family);     // gnm_dgi.cu
 
+// Programmatic dependent launch (PDL) for the persistent tcgen05 kernels: launched with the programmatic-stream-serialisation
+// attribute, a kernel's CTAs may start on SMs the PREVIOUS kernel of the stream has already vacated and run their set-up
+// (barrier init, tensor-memory allocation, weight planes, lookup tables) while its stragglers finish; pdl_wait() blocks
+// until that previous kernel has completed and flushed - it stands in front of the first access to anything a
+// predecessor may have produced. pdl_launch_dependents() at kernel start lets the NEXT kernel do the same to this one.
+// Contract for ABI users (gnm_set_pdl): a kernel's weight operands must not be written by the kernel immediately in
+// front of it in the stream (in a training step they are written once, by the optimiser, many kernels earlier).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+int gnm_pdl_enabled();                 // gnm_dgi.cu
+
+template <typename P>
+static inline cudaError_t gnm_launch_pdl(void (*kernel)(const P), int grid, int block, size_t smem, cudaStream_t st, const P& p) {
+    if (!gnm_pdl_enabled()) {
+        kernel<<<grid, block, smem, st>>>(p);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 static inline cudaStream_t gnm_cast_stream(gnm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __host__ __device__ static inline bool gnm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

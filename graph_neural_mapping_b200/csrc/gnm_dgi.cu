@@ -1,6 +1,8 @@
 // DGI discriminator scoring (reference: models/discriminator.py:19-38, models/graphcnn.py:233-246)
 // as a fused segmented reduction: nn.Bilinear(n_h, n_h, 1) is h^T W c + b = <h, u_g> + b with
 // u_g = W c_g computed once per graph, instead of ATen's _trilinear expansion over all M rows.
+#include <stdlib.h>
+
 #include "gnm_common.cuh"
 
 namespace {
@@ -314,6 +316,22 @@ extern "C" int gnm_stream_capture_status(gnm_stream_t stream, int* status) {
     cudaError_t e = cudaStreamIsCapturing(gnm_cast_stream(stream), &s);
     if (status) *status = (int)s;
     if (e != cudaSuccess) { cudaGetLastError(); if (status && e == cudaErrorStreamCaptureInvalidated) *status = 2; }
+    return GNM_OK;
+}
+
+// Off by default: measured on B200 at B = 1024 (whole step as one CUDA graph) it changes nothing - 3.69 ms with, 3.65 ms
+// without (gpurun_out/r2_bench_pdl{1,0}.json): graph replay already hides the launch latency and the persistent kernels'
+// tails are short. Kept as an opt-in (GNM_PDL=1 / gnm_set_pdl) for latency-bound small-batch use.
+static int g_pdl = -1;                  // -1: not decided yet (environment GNM_PDL, default off)
+int gnm_pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* e = getenv("GNM_PDL");
+        g_pdl = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return g_pdl;
+}
+extern "C" int gnm_set_pdl(int enabled) {
+    g_pdl = enabled ? 1 : 0;
     return GNM_OK;
 }
 

@@ -104,6 +104,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) linear_bwd_dx_tc_kernel(const L
     const int n_tiles = (p.n_rows + 127) >> 7;
     constexpr bool act = ACT;
 
+    // the B images fold the BatchNorm-backward coefficients, which come out of the tail of the kernel in front: wait first
+    pdl_launch_dependents();
+    pdl_wait();
     // ---- setup: B images. GEMM k = o (n_out), n = i (n_in); K-major core matrices: (n, k) -> (k/8)*1024 + (n/8)*128 + (n%8)*16 + (k%8)*2
     for (int e = tid; e < BT_F * BT_F / 2; e += BT_THREADS) {
         const int n = e >> 5, k = (e & 31) * 2;
@@ -431,6 +434,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) linear_wgrad_tc_kernel(const Wg
     const int n_chunks = (p.n_rows + WG_ROWS - 1) / WG_ROWS;
     constexpr bool act = ACT;
 
+    pdl_launch_dependents();
     if (tid < 3 * BT_F) s_sum[tid] = 0.f;
     if (tid == 0) {
         s_abort = 0;
@@ -446,6 +450,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) linear_wgrad_tc_kernel(const Wg
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+    pdl_wait();
 
     if (warp < WG_PROD_WARPS) {
         // ================================ producers ============================================================
@@ -678,7 +683,8 @@ int gnm_launch_linear_bwd_dx_tc(const float* dy, int64_t lddy, const float* z, i
         e = cudaFuncSetAttribute(linear_bwd_dx_tc_kernel<A, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM);       \
         if (e != cudaSuccess) return (int)e;                                                                                 \
         gnm_count_launch(GNM_K_LINEAR_BWD_DX_TC);                                                                            \
-        linear_bwd_dx_tc_kernel<A, F><<<grid, BT_THREADS, BT_SMEM, stream>>>(p);                                             \
+        e = gnm_launch_pdl<LinBwdTcParams>(linear_bwd_dx_tc_kernel<A, F>, grid, BT_THREADS, BT_SMEM, stream, p);             \
+        if (e != cudaSuccess) return (int)e;                                                                                 \
     } while (0)
     if (act && fast) GNM_BT_LAUNCH(true, true);
     else if (fast) GNM_BT_LAUNCH(false, true);
@@ -721,7 +727,8 @@ int gnm_launch_linear_wgrad_tc(const float* dy, int64_t lddy, const float* z, in
         e = cudaFuncSetAttribute(linear_wgrad_tc_kernel<A, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);       \
         if (e != cudaSuccess) return (int)e;                                                                                \
         gnm_count_launch(GNM_K_LINEAR_WGRAD_TC);                                                                            \
-        linear_wgrad_tc_kernel<A, F><<<grid, WG_THREADS, WG_SMEM, stream>>>(p);                                             \
+        e = gnm_launch_pdl<WgradTcParams>(linear_wgrad_tc_kernel<A, F>, grid, WG_THREADS, WG_SMEM, stream, p);              \
+        if (e != cudaSuccess) return (int)e;                                                                                \
     } while (0)
     if (act && fast) GNM_WG_LAUNCH(true, true);
     else if (fast) GNM_WG_LAUNCH(false, true);

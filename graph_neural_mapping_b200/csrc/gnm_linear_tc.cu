@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
     constexpr bool act = ACT;
 
     // ---- one-time setup: W planes (K-major core matrices), prologue constants, barriers, tensor memory
+    pdl_launch_dependents();
     for (int e = tid; e < LT_F * LT_F / 2; e += LT_THREADS) {
         const int n = e >> 5, k = (e & 31) * 2;                       // element pair (n, k), (n, k+1)
         float w0 = 0.f, w1 = 0.f;
@@ -89,6 +90,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
         *reinterpret_cast<uint32_t*>(sm_w + LT_W_PLANE + off) = m;
         *reinterpret_cast<uint32_t*>(sm_w + 2 * LT_W_PLANE + off) = l;
     }
+    // weights above, barriers / tensor memory below need nothing from the kernel in front; the BatchNorm affine of the
+    // prologue does (it comes out of that kernel's tail): wait here
+    pdl_wait();
     for (int k = tid; k < LT_F; k += LT_THREADS) {
         sm_sc[k] = (act && k < p.n_in) ? p.in_scale[k] : 1.f;
         sm_sc[LT_F + k] = (act && k < p.n_in) ? p.in_shift[k] : 0.f;
@@ -389,7 +393,8 @@ int gnm_launch_linear_tc(const float* x, int64_t ldx, int n_rows, int n_in, cons
         e = cudaFuncSetAttribute(linear_tc_kernel<A, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);        \
         if (e != cudaSuccess) return (int)e;                                                                           \
         gnm_count_launch(GNM_K_LINEAR_TC);                                                                             \
-        linear_tc_kernel<A, F><<<grid, LT_THREADS, LT_SMEM, stream>>>(p);                                              \
+        e = gnm_launch_pdl<LinTcParams>(linear_tc_kernel<A, F>, grid, LT_THREADS, LT_SMEM, stream, p);                  \
+        if (e != cudaSuccess) return (int)e;                                                                           \
     } while (0)
     if (act && fast) GNM_LT_LAUNCH(true, true);
     else if (fast) GNM_LT_LAUNCH(false, true);

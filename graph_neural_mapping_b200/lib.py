@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libgnm.so")
-ABI_VERSION = 21
+ABI_VERSION = 22
 
 _c_i32 = ctypes.c_int
 _c_i64 = ctypes.c_int64
@@ -25,6 +25,7 @@ SIGNATURES = {
     "gnm_set_device": [_c_i32],
     "gnm_device_info": [_p, _p, _p, _p],
     "gnm_launch_counts": [_p, _c_i32],
+    "gnm_set_pdl": [_c_i32],
     "gnm_stream_capture_status": [_p, _p],
     "gnm_csr_build": [_p, _c_i64, _p, _p, _c_i32, _c_i32, _c_i32, _c_i32, _p, _p, _p, _p],
     "gnm_csr_batch_gather": [_p, _p, _p, _p, _p, _c_i32, _p, _p, _p, _p],

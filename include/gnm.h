@@ -33,7 +33,7 @@ extern "C" {
 #define GNM_ERR_TOO_LARGE (-2)
 #define GNM_ERR_ALIGN (-3)
 
-#define GNM_ABI_VERSION 21
+#define GNM_ABI_VERSION 22
 
 typedef void* gnm_stream_t;
 
@@ -95,6 +95,13 @@ int gnm_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_o
  * 8 linear_wgrad (FFMA), 9 every other kernel. Returns the number of families (>= 0) or GNM_ERR_BAD_ARG.
  * Tests use it to prove WHICH kernel family a code path ran; bench.py to count launches. */
 int gnm_launch_counts(int64_t* out, int n);
+/* Programmatic dependent launch of the persistent tcgen05 kernels (aggregation, Linear forward / dX / dW): off by default
+ * (no measurable gain inside a CUDA-graph replay at B = 1024; environment GNM_PDL=1 or this call turn it on). When on, a
+ * kernel's CTAs may start on SMs the previous kernel of the stream has vacated and
+ * run their set-up - barriers, tensor-memory allocation, WEIGHT planes, lookup tables - before that kernel has finished;
+ * every access to activations, statistics or coefficients waits for its completion (griddepcontrol.wait). Contract: a
+ * call's weight operand must not be written by the kernel immediately in front of it in the stream. */
+int gnm_set_pdl(int enabled);
 /* Debugging aid for CUDA-graph capture: *status = 0 (stream not capturing), 1 (capturing), 2 (capture invalidated). */
 int gnm_stream_capture_status(gnm_stream_t stream, int* status);
 
