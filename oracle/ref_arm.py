@@ -1,4 +1,5 @@
-"""TEST / BASELINE INFRASTRUCTURE ONLY - loads the UNMODIFIED reference staged in `oracle/_ref/` (oracle/make_ref.py).
+"""TEST / BASELINE INFRASTRUCTURE ONLY - loads the UNMODIFIED reference staged in `oracle/_ref/` (oracle/make_ref.py:
+one archive of the six reference files + a sha256 manifest; unpacked here into a per-process temporary directory).
 
 Only tests/, __graft_entry__.smoke() and bench.py's `cpu_baseline` / `--impl reference` legs may import this module;
 the product (`graph_neural_mapping_b200/`, `models/`) never does.
@@ -11,31 +12,51 @@ Two things are offered:
     get_saliency_map / get_latent_space, main.py:19-96), imported with `models` resolving either to the reference's
     classes ("reference") or to the repo-root `models/` shim ("repo") - the drop-in claim of SURVEY 8(b), executed.
 """
+import atexit
 import hashlib
 import importlib
 import importlib.util
 import json
 import os
+import shutil
 import sys
+import tarfile
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF_DIR = os.path.join(HERE, "_ref")
+STAGE_DIR = os.path.join(HERE, "_ref")
 REPO = os.path.dirname(HERE)
+REF_DIR = None          # where the archive is unpacked (set by verify())
 
 
 def available():
-    return os.path.isfile(os.path.join(REF_DIR, "MANIFEST.json"))
+    if not os.path.isfile(os.path.join(STAGE_DIR, "MANIFEST.json")):
+        return False
+    with open(os.path.join(STAGE_DIR, "MANIFEST.json")) as f:
+        return os.path.isfile(os.path.join(STAGE_DIR, json.load(f).get("archive", "")))
 
 
 def verify():
-    """The staged files are byte-identical to what make_ref.py copied from /root/reference."""
-    with open(os.path.join(REF_DIR, "MANIFEST.json")) as f:
-        manifest = json.load(f)["files"]
+    """Unpack the staged archive (once per process) and check that every file is byte-identical to what make_ref.py
+    read from /root/reference."""
+    global REF_DIR
+    with open(os.path.join(STAGE_DIR, "MANIFEST.json")) as f:
+        meta = json.load(f)
+    manifest = meta["files"]
+    if REF_DIR is None:
+        d = tempfile.mkdtemp(prefix="gnm_ref_")
+        atexit.register(shutil.rmtree, d, True)
+        with tarfile.open(os.path.join(STAGE_DIR, meta["archive"]), "r:gz") as tar:
+            for m in tar.getmembers():
+                if m.name not in manifest or not m.isfile():
+                    raise RuntimeError("unexpected member %r in the staged reference archive" % m.name)
+            tar.extractall(d)
+        REF_DIR = d
     for rel, want in manifest.items():
         with open(os.path.join(REF_DIR, rel), "rb") as f:
             got = hashlib.sha256(f.read()).hexdigest()
         if got != want:
-            raise RuntimeError("oracle/_ref/%s does not match its manifest: the reference copy was edited" % rel)
+            raise RuntimeError("staged reference file %s does not match its manifest: the reference copy was edited" % rel)
     return sorted(manifest)
 
 
