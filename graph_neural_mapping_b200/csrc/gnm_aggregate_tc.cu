@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         // stores (a row-per-lane store costs 32 L1 wavefronts per instruction); the eps self term and the bias are
         // added during the copy-out, where the source rows are read coalesced as well.
         uint32_t acc_it = 0;
-        long long w_acc = 0;
+        long long w_acc = 0, c_drain = 0, c_copy = 0;
         const long long t_role = clock64();
         const float self_c = (kEps && p.eps) ? 1.f + __ldg(p.eps) : 0.f;
         const uint32_t my_slot = warp >> 2;
@@ -199,26 +199,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 const uint32_t slot = acc_it & 1, ph = (acc_it >> 1) & 1;
                 if (TC_EPI_WARPS == 8 && slot != my_slot) continue;
                 float ds_row = 0.f;
+                // DGI gradient of the shuffled rows (the first r_nneg rows of the batch, main.py's n_f[idx]): tiles holding
+                // such rows - a handful per launch, but all of them in the first CTAs' first graphs, where a synchronous
+                // load per row made those CTAs the critical path (+35 us per launch) - fetch them asynchronously into the
+                // output staging tile, and the drain below adds the accumulator on top
+                const bool neg_tile = fuse && p.r_dneg != nullptr && mt * 128 + q * 32 < n && n0 + mt * 128 + q * 32 < p.r_nneg;
                 if (fuse && mt * 128 + q * 32 < n) {
                     // the rows this warp will mask with arrive while it waits for the accumulator: z through cp.async
                     // into its second staging tile (two rows per instruction, coalesced), d_score one row per lane
                     const int zr0 = mt * 128 + q * 32;
                     float* zst = sm_zst + warp * (32 * TC_PITCH);
                     const uint32_t zst_u32 = smem_u32(zst);
+                    // lane -> (row pair member lane >> 4, float4 column lane & 15); rows advance by two per copy, addresses
+                    // by a constant step (no per-row 64-bit multiply)
+                    const int c4z = lane & 15;
+                    const int nvz = c4z * 4 < p.n_feat ? n - zr0 - (lane >> 4) : 0;      // copy i is in range iff 2 i < nvz
+                    const char* srcz = reinterpret_cast<const char*>(p.rz + (int64_t)(n0 + zr0 + (lane >> 4)) * p.ld_rz + c4z * 4);
+                    const int64_t stepz = 2 * p.ld_rz * (int64_t)sizeof(float);
+                    uint32_t dstz = zst_u32 + (uint32_t)(((lane >> 4) * TC_PITCH + c4z * 4) * 4);
+                    if (nvz >= 31) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstz), "l"(srcz) : "memory");
+                            srcz += stepz;
+                            dstz += 2 * TC_PITCH * 4;
+                        }
+                    } else {
 #pragma unroll 4
-                    for (int i = 0; i < 16; ++i) {
-                        const int rr = i * 2 + (lane >> 4), c4z = lane & 15;
-                        const bool okz = zr0 + rr < n && c4z * 4 < p.n_feat;
-                        const float* srcz = p.rz + (int64_t)(n0 + (okz ? zr0 + rr : 0)) * p.ld_rz + (okz ? c4z * 4 : 0);
-                        const uint32_t dstz = zst_u32 + (uint32_t)((rr * TC_PITCH + c4z * 4) * 4);
-                        const int nbytes = okz ? 16 : 0;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dstz), "l"(srcz), "r"(nbytes) : "memory");
+                        for (int i = 0; i < 16; ++i) {
+                            const bool okz = 2 * i < nvz;
+                            const int nbytes = okz ? 16 : 0;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dstz),
+                                         "l"(okz ? srcz : reinterpret_cast<const char*>(p.rz)), "r"(nbytes) : "memory");
+                            srcz += stepz;
+                            dstz += 2 * TC_PITCH * 4;
+                        }
+                    }
+                    if (neg_tile) {
+                        uint32_t dstn = smem_u32(stg) + (uint32_t)(((lane >> 4) * TC_PITCH + c4z * 4) * 4);
+#pragma unroll 4
+                        for (int i = 0; i < 16; ++i) {
+                            const int64_t gr_n = (int64_t)n0 + zr0 + 2 * i + (lane >> 4);
+                            const bool okn = 2 * i < nvz && gr_n < p.r_nneg;
+                            const int nbytes = okn ? 16 : 0;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dstn),
+                                         "l"(p.r_dneg + (okn ? gr_n * p.ld_dneg + c4z * 4 : 0)), "r"(nbytes) : "memory");
+                            dstn += 2 * TC_PITCH * 4;
+                        }
                     }
                     asm volatile("cp.async.commit_group;" ::: "memory");
                     if (p.r_dscore != nullptr && zr0 + lane < n) ds_row = __ldg(p.r_dscore + n0 + zr0 + lane);
                 }
                 if (!mbar_wait<32>(&acc_full[slot], ph, abort_flag, DBG ? &w_acc : nullptr)) break;
                 tc_fence_after();
+                const long long t_d0 = DBG ? clock64() : 0;
                 const int row0 = mt * 128 + q * 32;              // first row (within the graph) of this warp's slice
                 const int r = row0 + lane;
                 const int gr = n0 + (r < n ? r : 0);
@@ -226,6 +260,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 if (kAvg && p.mode == 1) deg = (float)(p.rowptr[gr + 1] - p.rowptr[gr]);
                 // a warp whose 32 rows all lie beyond the graph (the tail of the last row tile) has nothing to drain
                 const bool any_rows = row0 < n && have_k;
+                if (neg_tile) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                }
                 if (any_rows) {
 #pragma unroll 1
                     for (int c0 = 0; c0 < TC_SLAB; c0 += 16) {
@@ -245,6 +283,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) v[e] /= deg;
                             }
+                            if (kFuse && neg_tile) {
+                                const float4 a = *reinterpret_cast<const float4*>(stg + lane * TC_PITCH + c0 + j);
+                                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+                            }
                             *reinterpret_cast<float4*>(stg + lane * TC_PITCH + c0 + j) = make_float4(v[0], v[1], v[2], v[3]);
                         }
                     }
@@ -253,6 +295,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[slot]);       // accumulator drained: the MMA may reuse the slot
+                const long long t_d1 = DBG ? clock64() : 0;
+                if (DBG) c_drain += t_d1 - t_d0;
                 if (any_rows) {
                     const int c4 = lane & 15;
                     const int col = f0 + c4 * 4;
@@ -260,59 +304,97 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                     {
                         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (kMap && p.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-#pragma unroll 4
-                        for (int i = 0; i < 16; ++i) {
-                            const int rr = i * 2 + (lane >> 4);
-                            // d_score of row rr lives in lane rr: EVERY lane takes part in the shuffle (narrow layers
-                            // leave lanes without a column, tail tiles leave lanes without a row)
-                            const float ds = fuse ? __shfl_sync(GNM_FULL_MASK, ds_row, rr) : 0.f;
-                            if (!col_ok || row0 + rr >= n) continue;
-                            const int g2 = n0 + row0 + rr;
-                            float4 v = *reinterpret_cast<const float4*>(stg + rr * TC_PITCH + c4 * 4);
-                            if (kSplit && p.accumulate) {
-                                const float4 o = *reinterpret_cast<const float4*>(p.dst + (int64_t)g2 * p.ld_dst + col);
-                                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                            }
-                            if (kEps && p.eps) {
-                                const int64_t sr = (kMap && p.src_map) ? (int64_t)p.src_map[p.b_shared ? row0 + rr : g2] : (int64_t)g2;
-                                const float4 sv = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
-                                v.x = fmaf(self_c, sv.x, v.x); v.y = fmaf(self_c, sv.y, v.y);
-                                v.z = fmaf(self_c, sv.z, v.z); v.w = fmaf(self_c, sv.w, v.w);
-                            }
-                            if (kMap) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
-                            if (ostats) {
-                                rs1[0] += v.x; rs1[1] += v.y; rs1[2] += v.z; rs1[3] += v.w;
-                                rs2[0] = fmaf(v.x, v.x, rs2[0]); rs2[1] = fmaf(v.y, v.y, rs2[1]);
-                                rs2[2] = fmaf(v.z, v.z, rs2[2]); rs2[3] = fmaf(v.w, v.w, rs2[3]);
-                            }
-                            if (fuse) {
-                                // gnm_relu_bn_bwd_reduce on the fly: add the readout / DGI gradients of this row, mask by
-                                // the ReLU of the layer below, accumulate sum(dy) and sum(dy * xhat)
-                                const float4 zv = *reinterpret_cast<const float4*>(sm_zst + warp * (32 * TC_PITCH) + rr * TC_PITCH + c4 * 4);
-                                v.x += r_gp.x; v.y += r_gp.y; v.z += r_gp.z; v.w += r_gp.w;
-                                if (p.r_dscore != nullptr) {
-                                    v.x = fmaf(ds, r_uu.x, v.x); v.y = fmaf(ds, r_uu.y, v.y);
-                                    v.z = fmaf(ds, r_uu.z, v.z); v.w = fmaf(ds, r_uu.w, v.w);
+                        // Rows in batches of CB: every load of a batch (staging tile, z tile, dst / self / negative rows) is
+                        // issued before the first dependent instruction, so a batch pays one shared / global round trip
+                        // instead of one per row; row addresses advance by constant steps (two rows per iteration).
+                        constexpr int CB = 4;
+                        const int rsub = lane >> 4;
+                        const int nvalid = col_ok ? n - row0 - rsub : 0;          // row 2 i + rsub of the slice exists iff 2 i < nvalid
+                        const int64_t g20 = (int64_t)n0 + row0 + rsub;
+                        const bool acc_dst = kSplit && p.accumulate;
+                        const bool self_t = kEps && p.eps != nullptr;
+                        const bool self_map = kMap && p.src_map != nullptr;
+                        const bool dsc_t = fuse && p.r_dscore != nullptr;
+                        const float* stg_r = stg + rsub * TC_PITCH + c4 * 4;
+                        const float* z_r = kFuse ? sm_zst + warp * (32 * TC_PITCH) + rsub * TC_PITCH + c4 * 4 : nullptr;
+                        char* dptr = reinterpret_cast<char*>(p.dst + g20 * p.ld_dst + col);
+                        const int64_t dstep = 2 * p.ld_dst * (int64_t)sizeof(float);
+                        const char* sptr = reinterpret_cast<const char*>(p.src + g20 * p.ld_src + col);
+                        const int64_t sstep = 2 * p.ld_src * (int64_t)sizeof(float);
+#pragma unroll 1
+                        for (int i0 = 0; i0 < 16; i0 += CB) {
+                            float4 vv[CB], zz[CB], oo[CB], ss[CB];
+                            float dsv[CB];
+#pragma unroll
+                            for (int j = 0; j < CB; ++j) {
+                                const int i = i0 + j;
+                                const bool okr = 2 * i < nvalid;
+                                // d_score of row rr lives in lane rr: EVERY lane takes part in the shuffle (narrow layers
+                                // leave lanes without a column, tail tiles leave lanes without a row)
+                                if (kFuse) dsv[j] = dsc_t ? __shfl_sync(GNM_FULL_MASK, ds_row, 2 * i + rsub) : 0.f;
+                                vv[j] = *reinterpret_cast<const float4*>(stg_r + i * (2 * TC_PITCH));
+                                if (fuse) zz[j] = *reinterpret_cast<const float4*>(z_r + i * (2 * TC_PITCH));
+                                if (kSplit) {
+                                    oo[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (acc_dst && okr) oo[j] = *reinterpret_cast<const float4*>(dptr + j * dstep);
                                 }
-                                if (p.r_dneg != nullptr && g2 < p.r_nneg) {
-                                    const float4 dn = __ldg(reinterpret_cast<const float4*>(p.r_dneg + (int64_t)g2 * p.ld_dneg + col));
-                                    v.x += dn.x; v.y += dn.y; v.z += dn.z; v.w += dn.w;
+                                if (kEps) {
+                                    ss[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (self_t && okr) {
+                                        if (self_map) {
+                                            const int64_t sr = (int64_t)p.src_map[p.b_shared ? row0 + 2 * i + rsub : (int)g20 + 2 * i];
+                                            ss[j] = __ldg(reinterpret_cast<const float4*>(p.src + sr * p.ld_src + col));
+                                        } else {
+                                            ss[j] = __ldg(reinterpret_cast<const float4*>(sptr + j * sstep));
+                                        }
+                                    }
                                 }
-                                v.x = (fmaf(zv.x, r_sc.x, r_sh.x) > 0.f) ? v.x : 0.f;
-                                v.y = (fmaf(zv.y, r_sc.y, r_sh.y) > 0.f) ? v.y : 0.f;
-                                v.z = (fmaf(zv.z, r_sc.z, r_sh.z) > 0.f) ? v.z : 0.f;
-                                v.w = (fmaf(zv.w, r_sc.w, r_sh.w) > 0.f) ? v.w : 0.f;
-                                rs1[0] += v.x; rs1[1] += v.y; rs1[2] += v.z; rs1[3] += v.w;
-                                rs2[0] = fmaf(v.x, (zv.x - r_mu.x) * r_rs.x, rs2[0]);
-                                rs2[1] = fmaf(v.y, (zv.y - r_mu.y) * r_rs.y, rs2[1]);
-                                rs2[2] = fmaf(v.z, (zv.z - r_mu.z) * r_rs.z, rs2[2]);
-                                rs2[3] = fmaf(v.w, (zv.w - r_mu.w) * r_rs.w, rs2[3]);
                             }
-                            *reinterpret_cast<float4*>(p.dst + (int64_t)g2 * p.ld_dst + col) = v;
+#pragma unroll
+                            for (int j = 0; j < CB; ++j) {
+                                if (2 * (i0 + j) >= nvalid) continue;
+                                float4 v = vv[j];
+                                if (kSplit) { v.x += oo[j].x; v.y += oo[j].y; v.z += oo[j].z; v.w += oo[j].w; }
+                                if (kEps) {
+                                    v.x = fmaf(self_c, ss[j].x, v.x); v.y = fmaf(self_c, ss[j].y, v.y);
+                                    v.z = fmaf(self_c, ss[j].z, v.z); v.w = fmaf(self_c, ss[j].w, v.w);
+                                }
+                                if (kMap) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+                                if (ostats) {
+                                    rs1[0] += v.x; rs1[1] += v.y; rs1[2] += v.z; rs1[3] += v.w;
+                                    rs2[0] = fmaf(v.x, v.x, rs2[0]); rs2[1] = fmaf(v.y, v.y, rs2[1]);
+                                    rs2[2] = fmaf(v.z, v.z, rs2[2]); rs2[3] = fmaf(v.w, v.w, rs2[3]);
+                                }
+                                if (fuse) {
+                                    // gnm_relu_bn_bwd_reduce on the fly: add the readout / DGI gradients of this row, mask by
+                                    // the ReLU of the layer below, accumulate sum(dy) and sum(dy * (z - mean)) (the 1 / std
+                                    // factor of xhat is applied once, when the sums are folded)
+                                    const float4 zv = zz[j];
+                                    v.x += r_gp.x; v.y += r_gp.y; v.z += r_gp.z; v.w += r_gp.w;
+                                    if (dsc_t) {
+                                        const float ds = dsv[j];
+                                        v.x = fmaf(ds, r_uu.x, v.x); v.y = fmaf(ds, r_uu.y, v.y);
+                                        v.z = fmaf(ds, r_uu.z, v.z); v.w = fmaf(ds, r_uu.w, v.w);
+                                    }
+                                    v.x = (fmaf(zv.x, r_sc.x, r_sh.x) > 0.f) ? v.x : 0.f;
+                                    v.y = (fmaf(zv.y, r_sc.y, r_sh.y) > 0.f) ? v.y : 0.f;
+                                    v.z = (fmaf(zv.z, r_sc.z, r_sh.z) > 0.f) ? v.z : 0.f;
+                                    v.w = (fmaf(zv.w, r_sc.w, r_sh.w) > 0.f) ? v.w : 0.f;
+                                    rs1[0] += v.x; rs1[1] += v.y; rs1[2] += v.z; rs1[3] += v.w;
+                                    rs2[0] = fmaf(v.x, zv.x - r_mu.x, rs2[0]);
+                                    rs2[1] = fmaf(v.y, zv.y - r_mu.y, rs2[1]);
+                                    rs2[2] = fmaf(v.z, zv.z - r_mu.z, rs2[2]);
+                                    rs2[3] = fmaf(v.w, zv.w - r_mu.w, rs2[3]);
+                                }
+                                *reinterpret_cast<float4*>(dptr + j * dstep) = v;
+                            }
+                            dptr += CB * dstep;
+                            sptr += CB * sstep;
                         }
                     }
                     __syncwarp();
                 }
+                if (DBG) c_copy += clock64() - t_d1;
             }
         }
         double* const stats_out = ostats ? p.out_stats : (fuse ? p.r_stats : nullptr);
@@ -320,6 +402,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
             // lanes l and l ^ 16 hold the same columns: fold, park the warp's 2 x 64 partial sums in its staging tile,
             // add the epilogue warps in a fixed order, ONE fp64 atomic per column and CTA
             __syncwarp();
+            if (fuse) { rs2[0] *= r_rs.x; rs2[1] *= r_rs.y; rs2[2] *= r_rs.z; rs2[3] *= r_rs.w; }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 rs1[u] += __shfl_xor_sync(GNM_FULL_MASK, rs1[u], 16);
@@ -338,7 +421,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 if (c < p.n_feat) atomicAdd(&stats_out[(tid >> 6) * p.n_feat + c], (double)a);
             }
         }
-        if (DBG && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_role; p.dbg[blockIdx.x * 16 + 1] = w_acc; }
+        if (DBG && tid == 0) {
+            p.dbg[blockIdx.x * 16 + 0] = clock64() - t_role; p.dbg[blockIdx.x * 16 + 1] = w_acc;
+            p.dbg[blockIdx.x * 16 + 12] = c_drain; p.dbg[blockIdx.x * 16 + 13] = c_copy;
+        }
     } else if (warp == TC_MMA_WARP) {
         // ================================ MMA issue (one thread) ==========================================
         if (lane == 0) {
@@ -698,7 +784,8 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
         return GNM_OK;
     }
     if (p.dbg != nullptr) {
-        e = var == 0 ? launch_variant<true, 0>(p, grid, smem, stream) : launch_variant<true, TCV_ALL>(p, grid, smem, stream);
+        e = var == 0 ? launch_variant<true, 0>(p, grid, smem, stream)
+            : var == TCV_FUSE ? launch_variant<true, TCV_FUSE>(p, grid, smem, stream) : launch_variant<true, TCV_ALL>(p, grid, smem, stream);
         return e == cudaSuccess ? GNM_OK : (int)e;
     }
     switch (var) {

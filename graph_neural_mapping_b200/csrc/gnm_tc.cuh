@@ -28,21 +28,34 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // conversion warps need (ncu: 10-17% of all executed instructions in the row-GEMM kernels), hence BACKOFF_NS > 0
 // parks the warp with nanosleep between polls. The single MMA-issuing thread polls without back-off (its wake-up
 // latency is on the critical path). The clock / abort flag are only consulted every 64 polls.
+// GNM_MBAR_HINT_NS > 0: every poll is a try_wait WITH a suspend-time hint - the thread sleeps in hardware until the phase
+// completes or the hint expires and costs no issue slots meanwhile (without the hint try_wait came back after ~20 cycles:
+// 40 % of all warp instructions of the fused aggregation were polls, and the MMA thread's polls - no back-off - competed
+// with the epilogue / producer warps of its scheduler, profiles/r2_aggregate_tc_fused_lines.txt).
+#ifndef GNM_MBAR_HINT_NS
+#define GNM_MBAR_HINT_NS 2000
+#endif
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t done = 0;
+#if GNM_MBAR_HINT_NS > 0
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity), "r"((uint32_t)GNM_MBAR_HINT_NS) : "memory");
+#else
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+#endif
+    return done;
+}
 template <int BACKOFF_NS = 0>
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag,
                                           long long* waited = nullptr) {
     const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (done) return true;
+    if (mbar_try_wait(addr, parity)) return true;
     const long long t0 = clock64();
     int spins = 0;
     while (true) {
-        if (BACKOFF_NS > 0) __nanosleep(BACKOFF_NS);
-        asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
-                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (done) {
+        if (GNM_MBAR_HINT_NS == 0 && BACKOFF_NS > 0) __nanosleep(BACKOFF_NS);
+        if (mbar_try_wait(addr, parity)) {
             if (waited) *waited += clock64() - t0;
             return true;
         }

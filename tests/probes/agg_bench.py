@@ -27,7 +27,38 @@ def main():
     ops.aggregate(bs.rowptr, bs.colidx, src, None, ref, 0, None, None)
     alg_bytes = 4.0 * bs.nnz + 4.0 * (m + 1) + 8.0 * m * f
     for impl in impls:
-        if impl == 0:
+        if impl == 3:
+            # the backward pass's fused variant: aggregation -> + readout / DGI gradients -> ReLU mask of the layer below ->
+            # BatchNorm-backward sums, as the step calls it for the middle layers (no eps, no negative rows)
+            z = torch.randn(m, f, device=dev)
+            scale = torch.rand(f, device=dev) + 0.5
+            shift = torch.randn(f, device=dev) * 0.1
+            mean = torch.randn(f, device=dev) * 0.1
+            rstd = torch.rand(f, device=dev) + 0.5
+            d_pooled = torch.randn(bs.n_graphs, f, device=dev)
+            d_score = torch.randn(m, device=dev)
+            u = torch.randn(bs.n_graphs, f, device=dev)
+            stats = torch.zeros(2, f, dtype=torch.float64, device=dev)
+            # PROBE_STEP (bit mask): the extras of the training step's call, one by one: 1 = readout / DGI operands as
+            # column slices of [B, 5F] matrices, 2 = negative-row gradients for the first B rows, 4 = pool scale,
+            # 8 = BatchNorm-backward tail in the last CTA
+            flags = int(os.environ.get("PROBE_STEP", "0"))
+            d_neg, n_neg, ps, tail = None, 0, None, None
+            if flags & 1:
+                d_pooled = torch.randn(bs.n_graphs, 5 * f, device=dev)[:, f:2 * f]
+                u = torch.randn(bs.n_graphs, 5 * f, device=dev)[:, f:2 * f]
+            if flags & 2:
+                d_neg, n_neg = torch.randn(bs.n_graphs, 5 * f, device=dev)[:, f:2 * f], bs.n_graphs
+            if flags & 4:
+                ps = torch.ones(bs.n_graphs, device=dev)
+            if flags & 8:
+                coef = torch.empty(3, f, device=dev)
+                tail = ops.BnTail(ops.BnTail.BWD_COEFFS, float(m), scale, mean, rstd, coef=coef)
+            fn = lambda: ops.aggregate_dense_relu_bn_bwd(bs.bitmap_addr, bs.node_off, bs.rowptr, bs.n_graphs, bs.n_max, src, 0,
+                                                         None, z, scale, shift, mean, rstd, d_pooled, ps, d_score, u, d_neg, n_neg,
+                                                         dst, stats, tail)
+            name = "tcgen05 fused bwd"
+        elif impl == 0:
             fn = lambda: ops.aggregate(bs.rowptr, bs.colidx, src, None, dst, 0, None, None)
             name = "csr warp-per-row"
         else:
@@ -44,7 +75,7 @@ def main():
             ev[i + 1].record()
         torch.cuda.synchronize()
         ts = [ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(iters)]
-        if impl == 2:
+        if impl >= 2:
             from graph_neural_mapping_b200 import lib
             dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
             lib.load().gnm_aggregate_tc_set_debug(dbg.data_ptr())
@@ -53,7 +84,18 @@ def main():
             lib.load().gnm_aggregate_tc_set_debug(None)
             d = dbg.view(148, 16).double().mean(0).tolist()
             print("  tcgen05 role cycles (mean over CTAs): epilogue %.0f (waiting acc_full %.0f) | mma %.0f (waiting a_full %.0f, "
-                  "acc_empty %.0f) | producer %.0f (a_empty slow-path wait %.0f; A expand+store %.0f, a_empty wait call incl. fast path %.0f, syncwarp+arrive %.0f, B convert+store+next loads %.0f, tile head/tail (word loads, item switch) %.0f)" % tuple(d[:12]))
+                  "acc_empty %.0f) | producer %.0f (a_empty slow-path wait %.0f; A expand+store %.0f, a_empty wait call incl. fast path %.0f, syncwarp+arrive %.0f, B convert+store+next loads %.0f, tile head/tail (word loads, item switch) %.0f) | epilogue warp 0: drain %.0f, copy-out %.0f" % tuple(d[:14]))
+        if impl == 3:
+            want = ref + d_pooled.repeat_interleave(n_nodes, 0) + d_score[:, None] * u.repeat_interleave(n_nodes, 0)
+            if d_neg is not None:
+                want[:n_neg] += d_neg
+            want = torch.where(z * scale + shift > 0, want, torch.zeros_like(want))
+            err = float((dst - want).abs().max() / want.abs().max())
+            alg = alg_bytes + 4.0 * m * f
+            t = float(np.median(ts))
+            print("%-18s median %8.1f us  min %8.1f us  -> %7.1f GB/s algorithmic (%.3f of 6546)  max rel err %.2e  abort=%s"
+                  % (name, t, min(ts), alg / t / 1e3, alg / t / 1e3 / 6546.2, err, ops.aggregate_tc_status()))
+            continue
         err = float((dst - ref).abs().max() / ref.abs().max())
         t = float(np.median(ts))
         print("%-18s median %8.1f us  min %8.1f us  -> %7.1f GB/s algorithmic (%.3f of 6546)  max rel err vs csr %.2e  abort=%s"
