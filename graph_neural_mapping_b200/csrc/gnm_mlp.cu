@@ -360,7 +360,10 @@ bn_relu_readout_vec_kernel(const float* __restrict__ z, int64_t ldz, int n_feat,
 // ------------------------------------------------------------------------------------------
 // backward of relu(bn(z)), pass 1: assemble the incoming gradient, mask, reduce
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// DOUT: a per-row incoming gradient d_out exists (the unfused fallback); without it (the top layer of the training step) the
+// kernel keeps fewer rows' operands in registers and three CTAs fit an SM
+template <bool DOUT>
+__global__ void __launch_bounds__(256, DOUT ? 2 : 3)
 relu_bn_bwd_reduce_vec_kernel(const float* __restrict__ z, int64_t ldz, int n_feat, const float* __restrict__ scale,
                               const float* __restrict__ shift, const float* __restrict__ mean,
                               const float* __restrict__ rstd, const float* __restrict__ d_out, int64_t ld_dout,
@@ -394,31 +397,46 @@ relu_bn_bwd_reduce_vec_kernel(const float* __restrict__ z, int64_t ldz, int n_fe
             const float* q = u + (int64_t)g * ldu + f;
             uu = make_float4(q[0], q[1], q[2], q[3]);
         }
-#pragma unroll 2
-        for (int r = r0 + rr; r < r1; r += rpp) {
-            const float4 zv = ld_stream_f4(z + (int64_t)r * ldz + f);
-            float4 gr = gp;
-            if (d_out != nullptr) {
-                const float4 t = ld_stream_f4(d_out + (int64_t)r * ld_dout + f);
-                gr.x += t.x; gr.y += t.y; gr.z += t.z; gr.w += t.w;
+        // four rows per thread and iteration, every load issued before the first use (the rows of the shuffled-row gradient
+        // d_neg are the first n_neg rows of the batch: loaded one by one they made the CTAs of the first graphs the tail
+        // of the launch)
+        constexpr int UB = 4;
+        for (int rb = r0 + rr; rb < r1; rb += UB * rpp) {
+            float4 zv[UB], dv[UB], nv[UB];
+            float ds[UB];
+#pragma unroll
+            for (int k = 0; k < UB; ++k) {
+                const int r = rb + k * rpp;
+                const bool ok = r < r1;
+                zv[k] = nv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (DOUT) dv[k] = zv[k];
+                ds[k] = 0.f;
+                if (ok) {
+                    zv[k] = ld_stream_f4(z + (int64_t)r * ldz + f);
+                    if (DOUT) dv[k] = ld_stream_f4(d_out + (int64_t)r * ld_dout + f);
+                    if (d_score != nullptr) ds[k] = __ldg(d_score + r);
+                    if (d_neg != nullptr && r < n_neg) nv[k] = *reinterpret_cast<const float4*>(d_neg + (int64_t)r * ld_dneg + f);
+                }
             }
-            if (d_score != nullptr) {
-                const float ds = d_score[r];
-                gr.x = fmaf(ds, uu.x, gr.x); gr.y = fmaf(ds, uu.y, gr.y); gr.z = fmaf(ds, uu.z, gr.z); gr.w = fmaf(ds, uu.w, gr.w);
+#pragma unroll
+            for (int k = 0; k < UB; ++k) {
+                const int r = rb + k * rpp;
+                if (r >= r1) continue;
+                float4 gr = gp;
+                if (DOUT) { gr.x += dv[k].x; gr.y += dv[k].y; gr.z += dv[k].z; gr.w += dv[k].w; }
+                gr.x = fmaf(ds[k], uu.x, gr.x); gr.y = fmaf(ds[k], uu.y, gr.y);
+                gr.z = fmaf(ds[k], uu.z, gr.z); gr.w = fmaf(ds[k], uu.w, gr.w);
+                gr.x += nv[k].x; gr.y += nv[k].y; gr.z += nv[k].z; gr.w += nv[k].w;
+                float4 v;
+                v.x = (fmaf(zv[k].x, sc.x, sh.x) > 0.f) ? gr.x : 0.f;
+                v.y = (fmaf(zv[k].y, sc.y, sh.y) > 0.f) ? gr.y : 0.f;
+                v.z = (fmaf(zv[k].z, sc.z, sh.z) > 0.f) ? gr.z : 0.f;
+                v.w = (fmaf(zv[k].w, sc.w, sh.w) > 0.f) ? gr.w : 0.f;
+                *reinterpret_cast<float4*>(dy + (int64_t)r * lddy + f) = v;
+                s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+                s2.x = fmaf(v.x, (zv[k].x - mu.x) * rs.x, s2.x); s2.y = fmaf(v.y, (zv[k].y - mu.y) * rs.y, s2.y);
+                s2.z = fmaf(v.z, (zv[k].z - mu.z) * rs.z, s2.z); s2.w = fmaf(v.w, (zv[k].w - mu.w) * rs.w, s2.w);
             }
-            if (d_neg != nullptr && r < n_neg) {
-                const float* q = d_neg + (int64_t)r * ld_dneg + f;
-                gr.x += q[0]; gr.y += q[1]; gr.z += q[2]; gr.w += q[3];
-            }
-            float4 v;
-            v.x = (fmaf(zv.x, sc.x, sh.x) > 0.f) ? gr.x : 0.f;
-            v.y = (fmaf(zv.y, sc.y, sh.y) > 0.f) ? gr.y : 0.f;
-            v.z = (fmaf(zv.z, sc.z, sh.z) > 0.f) ? gr.z : 0.f;
-            v.w = (fmaf(zv.w, sc.w, sh.w) > 0.f) ? gr.w : 0.f;
-            *reinterpret_cast<float4*>(dy + (int64_t)r * lddy + f) = v;
-            s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
-            s2.x = fmaf(v.x, (zv.x - mu.x) * rs.x, s2.x); s2.y = fmaf(v.y, (zv.y - mu.y) * rs.y, s2.y);
-            s2.z = fmaf(v.z, (zv.z - mu.z) * rs.z, s2.z); s2.w = fmaf(v.w, (zv.w - mu.w) * rs.w, s2.w);
         }
     }
     red1[threadIdx.x] = s1;
@@ -658,16 +676,23 @@ extern "C" int gnm_relu_bn_bwd_reduce(const float* z, int64_t ldz, int n_rows, i
     if (d_score != nullptr && u == nullptr) return GNM_ERR_BAD_ARG;
     const bool vec = (n_feat % 4 == 0) && n_feat <= 1024 && (ldz % 4 == 0) && (lddy % 4 == 0) && gnm_aligned16(z) &&
                      gnm_aligned16(dy) && gnm_aligned16(scale) && gnm_aligned16(shift) && gnm_aligned16(mean) &&
-                     gnm_aligned16(rstd) && (d_out == nullptr || ((ld_dout % 4 == 0) && gnm_aligned16(d_out)));
+                     gnm_aligned16(rstd) && (d_out == nullptr || ((ld_dout % 4 == 0) && gnm_aligned16(d_out))) &&
+                     (d_neg == nullptr || ((ld_dneg % 4 == 0) && gnm_aligned16(d_neg)));
     BnTailDev td;
     const int trc = bn_tail_args(tail, stats, n_feat, &td);
     if (trc != GNM_OK) return trc;
     if (vec) {
         gnm_count_launch(GNM_K_OTHER);
-        const int grid = n_graphs < 148 * 4 ? n_graphs : 148 * 4;
-        relu_bn_bwd_reduce_vec_kernel<<<grid, 256, 0, gnm_cast_stream(stream)>>>(
-            z, ldz, n_feat, scale, shift, mean, rstd, d_out, ld_dout, d_pooled, ld_dpooled, pool_scale, d_score, u, ldu,
-            d_neg, ld_dneg, n_neg, node_off, n_graphs, dy, lddy, stats, td);
+        const int per_sm = d_out != nullptr ? 2 : 3;                 // resident CTAs per SM (launch bounds)
+        const int grid = n_graphs < 148 * per_sm ? n_graphs : 148 * per_sm;
+        if (d_out != nullptr)
+            relu_bn_bwd_reduce_vec_kernel<true><<<grid, 256, 0, gnm_cast_stream(stream)>>>(
+                z, ldz, n_feat, scale, shift, mean, rstd, d_out, ld_dout, d_pooled, ld_dpooled, pool_scale, d_score, u, ldu,
+                d_neg, ld_dneg, n_neg, node_off, n_graphs, dy, lddy, stats, td);
+        else
+            relu_bn_bwd_reduce_vec_kernel<false><<<grid, 256, 0, gnm_cast_stream(stream)>>>(
+                z, ldz, n_feat, scale, shift, mean, rstd, d_out, ld_dout, d_pooled, ld_dpooled, pool_scale, d_score, u, ldu,
+                d_neg, ld_dneg, n_neg, node_off, n_graphs, dy, lddy, stats, td);
         GNM_RETURN_IF_LAUNCH_FAILED();
         return GNM_OK;
     }
