@@ -16,7 +16,8 @@
 // kernel families counted by gnm_launch_counts (include/gnm.h); host-side, one increment per kernel enqueued
 enum GnmKernelFamily {
     GNM_K_AGG_CSR = 0, GNM_K_AGG_MMA_SYNC, GNM_K_AGG_TC, GNM_K_LINEAR_FFMA, GNM_K_LINEAR_TC, GNM_K_LINEAR_BWD_FFMA,
-    GNM_K_LINEAR_BWD_DX_TC, GNM_K_LINEAR_WGRAD_TC, GNM_K_LINEAR_WGRAD_FFMA, GNM_K_OTHER, GNM_K_FAMILIES
+    GNM_K_LINEAR_BWD_DX_TC, GNM_K_LINEAR_WGRAD_TC, GNM_K_LINEAR_WGRAD_FFMA, GNM_K_OTHER, GNM_K_LINEAR_BWD_ONEPASS_TC,
+    GNM_K_FAMILIES
 };
 void gnm_count_launch(int family);     // gnm_dgi.cu
 

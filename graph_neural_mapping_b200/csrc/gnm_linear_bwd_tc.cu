@@ -652,6 +652,434 @@ __global__ void __launch_bounds__(WG_THREADS, 1) linear_wgrad_tc_kernel(const Wg
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One-pass backward unit (64 x 64, aligned, dx requested): dX, dW, db and the ReLU mask / BatchNorm-backward reduction of
+// the unit below from ONE read of dy, z and x - 16 M F bytes instead of the 28 M F of the two kernels above.
+//   dz = cA*dy + cB*z + cC is formed in fp32 by the producers (one fma pair per element) and split ONCE into three exact
+//   bf16 planes; a = relu(x*in_scale + in_shift) (or x) likewise. The dz planes of a 128-row tile live in shared memory
+//   as 8 x 16-byte core matrices [8 rows][8 channels] and serve BOTH GEMMs through two descriptors over the same bytes:
+//     GEMM 1 (dX, per tile):  D1[row, i]  = sum_o dz[row, o] W[o, i]      A = dz, K-major  (M = 128 rows, K = 64 channels)
+//                             B = [W_hi | W_mid | W_lo] side by side (N = 192 / 128 / 64 for the hi / mid / lo plane of dz:
+//                             the six kept products in three MMAs per k-step; the three column groups are summed on drain)
+//     GEMM 2 (dW, whole CTA): D2[o, i]   += sum_row dz[row, o] a[row, i]  A = dz, MN-major (M = 128: hi channels | mid
+//                             channels; a second M = 128 MMA starting at the lo plane, of which only lanes 0-63 count),
+//                             B = [a_hi | a_mid | a_lo] (N = 192; 64 for lo), K = 16 rows per MMA, 32-row chunks.
+//   Tensor memory: D1 columns 0-191 (one slot: its drain is short and GEMM 1 of the next tile is a whole tile away),
+//   D2 columns 192-383 and 384-447, drained once per CTA.
+//   Roles: warps 0-3 epilogue (drain D1, + mask / reduction / store in a column layout, as in the dx kernel above),
+//   warps 4-11 producers (global -> cp.async landing ring, three 32-row chunks deep -> fma / relu -> split -> planes),
+//   warp 12 MMA issue. Barriers: full[4] (chunk c of the tile: a planes + dz planes written), b_empty[2] (a-plane ring),
+//   a_free (all MMAs of the tile retired: its dz planes may be overwritten), d1_full / d1_empty, done.
+constexpr int OP_A_CS = 16 * 128 + 16;             // bytes between 8-channel cores of a dz plane (128 rows, padded)
+constexpr int OP_A_PLANE = 8 * OP_A_CS;
+constexpr int OP_A_BYTES = 3 * OP_A_PLANE;
+constexpr int OP_B_CS = 4 * 128 + 16;              // bytes between 8-column cores of the a planes (32 rows, padded)
+constexpr int OP_B_SLOT = 24 * OP_B_CS;
+constexpr int OP_W_KCORE = 24 * 128;               // bytes between 8-channel k-cores of [W_hi | W_mid | W_lo]
+constexpr int OP_W_BYTES = 8 * OP_W_KCORE;
+constexpr int OP_EPI_WARPS = 4, OP_PROD_WARPS = 8;
+constexpr int OP_PT = OP_PROD_WARPS * 32;
+constexpr int OP_THREADS = (OP_EPI_WARPS + OP_PROD_WARPS + 1) * 32;
+constexpr int OP_MMA_WARP = OP_EPI_WARPS + OP_PROD_WARPS;
+constexpr int OP_DEPTH = 3;                        // landing ring: 32-row chunks requested ahead of their conversion
+constexpr int OP_LAND_CHUNK = 3 * 2 * OP_PT * 16;  // three streams x two rows per producer thread x 16 B
+constexpr int OP_OFF_A = OP_W_BYTES;
+constexpr int OP_OFF_B = OP_OFF_A + OP_A_BYTES;
+constexpr int OP_OFF_LAND = OP_OFF_B + 2 * OP_B_SLOT;
+constexpr int OP_OFF_OBUF = OP_OFF_LAND + OP_DEPTH * OP_LAND_CHUNK;
+constexpr int OP_OFF_X = OP_OFF_OBUF + OP_EPI_WARPS * BT_OSTG;
+constexpr int OP_OFF_C = OP_OFF_X + OP_EPI_WARPS * BT_STG;
+constexpr int OP_SMEM = OP_OFF_C + 4 * BT_F * 4;
+constexpr int OP_D2A = 192, OP_D2B = 384;
+static_assert(OP_SMEM <= 232448 - 512, "one-pass backward unit: shared memory");
+static_assert(128 * 65 * 4 <= OP_DEPTH * OP_LAND_CHUNK, "dW staging tile reuses the landing ring");
+
+struct LinBwd1Params {
+    const float* dy; int64_t lddy;
+    const float* z; int64_t ldz;
+    const float* coef;
+    const float* w; int64_t ldw;
+    const float* x; int64_t ldx;
+    const float* in_scale; const float* in_shift; const float* in_mean; const float* in_rstd;
+    float* dx; int64_t lddx;
+    float* dw; int64_t lddw; float* db;
+    double* stats_in;
+    int n_rows;
+    BnTailDev tail;
+};
+
+template <bool ACT>
+__global__ void __launch_bounds__(OP_THREADS, 1) linear_bwd_onepass_tc_kernel(const LinBwd1Params p) {
+    extern __shared__ __align__(1024) unsigned char op_smem[];
+    __shared__ __align__(8) uint64_t bars[4 + 2 + 4];
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_abort;
+    __shared__ float s_sum[BT_F];                                        // column sums of dz (db)
+    uint64_t* full = bars;                 // [4]
+    uint64_t* b_empty = bars + 4;          // [2]
+    uint64_t* a_free = bars + 6;
+    uint64_t* d1_full = bars + 7;
+    uint64_t* d1_empty = bars + 8;
+    uint64_t* done = bars + 9;
+    unsigned char* sm_w = op_smem;
+    unsigned char* sm_a = op_smem + OP_OFF_A;
+    unsigned char* sm_b = op_smem + OP_OFF_B;
+    unsigned char* sm_land = op_smem + OP_OFF_LAND;
+    float* sm_obuf = reinterpret_cast<float*>(op_smem + OP_OFF_OBUF);
+    float* sm_x = reinterpret_cast<float*>(op_smem + OP_OFF_X);
+    float* sm_c = reinterpret_cast<float*>(op_smem + OP_OFF_C);          // in_scale | in_shift | in_mean | in_rstd
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    volatile int* abort_flag = &s_abort;
+    const int n_tiles = (p.n_rows + 127) >> 7;
+    const int G = gridDim.x;
+
+    pdl_launch_dependents();
+    pdl_wait();
+    // ---- setup: [W_hi | W_mid | W_lo], K-major: (n' = plane * 64 + i, k = o) -> (k/8)*KCORE + (n'/8)*128 + (n'%8)*16 + (k%8)*2
+    for (int e = tid; e < BT_F * BT_F / 2; e += OP_THREADS) {
+        const int n = e >> 5, k = (e & 31) * 2;
+        const float w0 = p.w[(int64_t)k * p.ldw + n], w1 = p.w[(int64_t)(k + 1) * p.ldw + n];
+        uint32_t h, m, l;
+        split3x2(w0, w1, h, m, l);
+        const int off = (k >> 3) * OP_W_KCORE + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
+        *reinterpret_cast<uint32_t*>(sm_w + off) = h;
+        *reinterpret_cast<uint32_t*>(sm_w + 8 * 128 + off) = m;
+        *reinterpret_cast<uint32_t*>(sm_w + 16 * 128 + off) = l;
+    }
+    for (int i = tid; i < BT_F; i += OP_THREADS) {
+        sm_c[i] = ACT ? p.in_scale[i] : 1.f;
+        sm_c[BT_F + i] = ACT ? p.in_shift[i] : 0.f;
+        sm_c[2 * BT_F + i] = ACT ? p.in_mean[i] : 0.f;
+        sm_c[3 * BT_F + i] = ACT ? p.in_rstd[i] : 0.f;
+        s_sum[i] = 0.f;
+    }
+    if (tid == 0) {
+        s_abort = 0;
+        for (int i = 0; i < 4; ++i) mbar_init(&full[i], OP_PROD_WARPS);
+        for (int i = 0; i < 2; ++i) mbar_init(&b_empty[i], 1);
+        mbar_init(a_free, 1);
+        mbar_init(d1_full, 1);
+        mbar_init(d1_empty, OP_EPI_WARPS);
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == OP_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    if (warp < OP_EPI_WARPS) {
+        // ================================ epilogue: drain D1, mask / reduce / store =================================
+        float cs1[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, cs2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        const int q = warp;
+        float* stg = sm_x + warp * (32 * BT_PITCH);
+        float* obuf = sm_obuf + warp * (32 * BT_OPITCH);
+        const uint32_t stg_u32 = smem_u32(stg);
+        const int sub = lane >> 3, c4l = (lane & 7) * 4;
+        if (ACT && (int)blockIdx.x < n_tiles)
+            stage_rows_async(p.x, p.ldx, p.n_rows, BT_F, blockIdx.x * 128 + q * 32, stg, stg_u32, lane, true);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles && !*abort_flag; tile += G, ++it) {
+            if (!mbar_wait<32>(d1_full, it & 1, abort_flag)) break;
+            tc_fence_after();
+            const int row0 = tile * 128 + q * 32;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                for (int c0 = 0; c0 < 32; c0 += 16) {
+                    uint32_t g0[16], g1[16], g2[16];
+                    const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + hf * 32 + c0;
+                    tmem_ld16(ta, g0);
+                    tmem_ld16(ta + 64, g1);
+                    tmem_ld16(ta + 128, g2);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float v[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            v[e] = (__uint_as_float(g2[j + e]) + __uint_as_float(g1[j + e])) + __uint_as_float(g0[j + e]);
+                        *reinterpret_cast<float4*>(obuf + lane * BT_OPITCH + c0 + j) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                }
+                if (hf == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(d1_empty);               // D1 has left tensor memory
+                }
+                __syncwarp();
+                const int c = hf * 32 + c4l;
+                const float4 sc = *reinterpret_cast<const float4*>(sm_c + c);
+                const float4 sh = *reinterpret_cast<const float4*>(sm_c + BT_F + c);
+                const float4 mu = *reinterpret_cast<const float4*>(sm_c + 2 * BT_F + c);
+                const float4 rs = *reinterpret_cast<const float4*>(sm_c + 3 * BT_F + c);
+                const int nvalid = p.n_rows - row0 - sub;                  // row 4 i + sub is in range iff 4 i < nvalid
+                char* dstp = reinterpret_cast<char*>(p.dx + (int64_t)(row0 + sub) * p.lddx + c);
+                const int64_t dstep = 4 * p.lddx * (int64_t)sizeof(float);
+#pragma unroll
+                for (int i0 = 0; i0 < 8; i0 += 4) {
+                    float4 dd[4], xx[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        dd[i] = *reinterpret_cast<const float4*>(obuf + (4 * (i0 + i) + sub) * BT_OPITCH + c4l);
+                        if (ACT) xx[i] = *reinterpret_cast<const float4*>(stg + (4 * (i0 + i) + sub) * BT_PITCH + c);
+                    }
+#pragma unroll
+                    for (int i = i0; i < i0 + 4; ++i) {
+                        float4 d = dd[i - i0];
+                        const bool okr = 4 * i < nvalid;
+                        if (ACT) {
+                            const float4 xv = xx[i - i0];
+                            d.x = (okr && fmaf(xv.x, sc.x, sh.x) > 0.f) ? d.x : 0.f;
+                            d.y = (okr && fmaf(xv.y, sc.y, sh.y) > 0.f) ? d.y : 0.f;
+                            d.z = (okr && fmaf(xv.z, sc.z, sh.z) > 0.f) ? d.z : 0.f;
+                            d.w = (okr && fmaf(xv.w, sc.w, sh.w) > 0.f) ? d.w : 0.f;
+                            cs1[hf][0] += d.x; cs1[hf][1] += d.y; cs1[hf][2] += d.z; cs1[hf][3] += d.w;
+                            cs2[hf][0] = fmaf(d.x, (xv.x - mu.x) * rs.x, cs2[hf][0]);
+                            cs2[hf][1] = fmaf(d.y, (xv.y - mu.y) * rs.y, cs2[hf][1]);
+                            cs2[hf][2] = fmaf(d.z, (xv.z - mu.z) * rs.z, cs2[hf][2]);
+                            cs2[hf][3] = fmaf(d.w, (xv.w - mu.w) * rs.w, cs2[hf][3]);
+                        }
+                        if (okr) *reinterpret_cast<float4*>(dstp + i * dstep) = d;
+                    }
+                }
+                __syncwarp();                                           // the half tile is reused by the next half
+            }
+            if (ACT) {
+                const int next_tile = tile + G;
+                if (next_tile < n_tiles)
+                    stage_rows_async(p.x, p.ldx, p.n_rows, BT_F, next_tile * 128 + q * 32, stg, stg_u32, lane, true);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (ACT && p.stats_in != nullptr) {
+            __syncwarp();
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float a1 = cs1[hf][u], a2 = cs2[hf][u];
+                    a1 += __shfl_xor_sync(GNM_FULL_MASK, a1, 8);
+                    a2 += __shfl_xor_sync(GNM_FULL_MASK, a2, 8);
+                    a1 += __shfl_xor_sync(GNM_FULL_MASK, a1, 16);
+                    a2 += __shfl_xor_sync(GNM_FULL_MASK, a2, 16);
+                    if (lane < 8) {
+                        stg[hf * 32 + c4l + u] = a1;
+                        stg[BT_F + hf * 32 + c4l + u] = a2;
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(OP_EPI_WARPS * 32) : "memory");
+            if (tid < 2 * BT_F) {
+                float a = 0.f;
+#pragma unroll
+                for (int w = 0; w < OP_EPI_WARPS; ++w) a += sm_x[w * (32 * BT_PITCH) + tid];
+                atomicAdd(&p.stats_in[(tid >> 6) * BT_F + (tid & (BT_F - 1))], (double)a);
+            }
+        }
+    } else if (warp == OP_MMA_WARP) {
+        // ================================ MMA issue (one thread) ====================================================
+        if (lane == 0) {
+            const uint32_t id_k = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);      // A, B K-major
+            const uint32_t id_t = id_k | (1u << 15) | (1u << 16);                                           // A, B MN-major
+            const uint32_t n192 = (uint32_t)(192 >> 3) << 17, n128 = (uint32_t)(128 >> 3) << 17, n64 = (uint32_t)(64 >> 3) << 17;
+            const uint32_t a_base = smem_u32(sm_a), b_base = smem_u32(sm_b), w_base = smem_u32(sm_w);
+            uint32_t it = 0, cc = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < n_tiles && ok; tile += G, ++it) {
+                for (int c = 0; c < 4 && ok; ++c, ++cc) {
+                    if (!(ok = mbar_wait(&full[c], it & 1, abort_flag))) break;
+                    tc_fence_after();
+                    const uint32_t slot = cc & 1;
+                    // GEMM 2: rows c*32 .. c*32+31 of the tile (row cores 4 c ..), two k-steps of 16 rows
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint64_t a_hm = umma_desc(a_base + (uint32_t)((c * 4 + ks * 2) * 128), 128, OP_A_CS);
+                        const uint64_t a_lo = umma_desc(a_base + 2 * OP_A_PLANE + (uint32_t)((c * 4 + ks * 2) * 128), 128, OP_A_CS);
+                        const uint64_t b_d = umma_desc(b_base + slot * OP_B_SLOT + (uint32_t)(ks * 256), 128, OP_B_CS);
+                        const uint32_t acc = (cc | (uint32_t)ks) ? 1u : 0u;
+                        umma_ss(tmem + OP_D2A, a_hm, b_d, id_t | n192, acc);
+                        umma_ss(tmem + OP_D2B, a_lo, b_d, id_t | n64, acc);
+                    }
+                    umma_commit(&b_empty[slot]);
+                }
+                if (!ok) break;
+                if (!(ok = mbar_wait(d1_empty, (it & 1) ^ 1, abort_flag))) break;
+                tc_fence_after();
+                // GEMM 1: all 128 rows, four k-steps of 16 channels (two channel cores)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t a_h = umma_desc(a_base + (uint32_t)(ks * 2 * OP_A_CS), OP_A_CS, 128);
+                    const uint64_t pl = (uint64_t)(OP_A_PLANE >> 4);
+                    const uint64_t b_d = umma_desc(w_base + (uint32_t)(ks * 2 * OP_W_KCORE), OP_W_KCORE, 128);
+                    umma_ss(tmem, a_h, b_d, id_k | n192, ks ? 1u : 0u);
+                    umma_ss(tmem, a_h + pl, b_d, id_k | n128, 1u);
+                    umma_ss(tmem, a_h + 2 * pl, b_d, id_k | n64, 1u);
+                }
+                umma_commit(d1_full);
+                umma_commit(a_free);
+            }
+            if (ok) umma_commit(done);
+        }
+    } else {
+        // ================================ producers =================================================================
+        // thread -> float4 column c4 (fixed) and rows kr0, kr0 + 16 of every 32-row chunk, three streams; global ->
+        // landing ring with cp.async, OP_DEPTH - 1 chunks ahead; every thread reads back exactly what it requested
+        const int ptid = tid - OP_EPI_WARPS * 32;
+        const int c4 = ptid & 15, kr0 = ptid >> 4;
+        const float4 cA = *reinterpret_cast<const float4*>(p.coef + c4 * 4);
+        const float4 cB = *reinterpret_cast<const float4*>(p.coef + BT_F + c4 * 4);
+        const float4 cC = *reinterpret_cast<const float4*>(p.coef + 2 * BT_F + c4 * 4);
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ACT) {
+            sc = *reinterpret_cast<const float4*>(p.in_scale + c4 * 4);
+            sh = *reinterpret_cast<const float4*>(p.in_shift + c4 * 4);
+        }
+        float4 s_dz = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* my_land = reinterpret_cast<float4*>(sm_land) + ptid;      // slot (d, q) at my_land[(d * 6 + q) * OP_PT]
+        const uint32_t my_land_u32 = smem_u32(my_land);
+        const int n_chunks = ((int)blockIdx.x < n_tiles) ? ((n_tiles - 1 - (int)blockIdx.x) / G + 1) * 4 : 0;   // this CTA's
+        auto request_chunk = [&](int j, int d) {
+            if (j < n_chunks) {
+                const int r0 = ((int)blockIdx.x + (j >> 2) * G) * 128 + (j & 3) * 32 + kr0;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int r = r0 + 16 * u;
+                    const bool okr = r < p.n_rows;
+                    const int nbytes = okr ? 16 : 0;
+                    const int64_t rr = okr ? r : 0;
+                    const uint32_t dst = my_land_u32 + (uint32_t)((d * 6 + u * 3) * OP_PT * 16);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst),
+                                 "l"(p.dy + rr * p.lddy + c4 * 4), "r"(nbytes) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + OP_PT * 16),
+                                 "l"(p.z + rr * p.ldz + c4 * 4), "r"(nbytes) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 2 * OP_PT * 16),
+                                 "l"(p.x + rr * p.ldx + c4 * 4), "r"(nbytes) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");          // one group per slot, even when empty
+        };
+#pragma unroll
+        for (int d = 0; d < OP_DEPTH - 1; ++d) request_chunk(d, d);
+        bool ok = true;
+        for (int j = 0; j < n_chunks && ok; ++j) {
+            const int d = j % OP_DEPTH;
+            const int c = j & 3;
+            // slot (j + DEPTH - 1) % DEPTH was consumed by this thread in the previous iteration: safe to refill
+            request_chunk(j + OP_DEPTH - 1, (j + OP_DEPTH - 1) % OP_DEPTH);
+            asm volatile("cp.async.wait_group %0;" ::"n"(OP_DEPTH - 1) : "memory");
+            const int row_base = ((int)blockIdx.x + (j >> 2) * G) * 128 + c * 32 + kr0;
+            float4 vdz[2], va[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float4 g = my_land[(d * 6 + u * 3) * OP_PT];
+                const float4 zz = my_land[(d * 6 + u * 3 + 1) * OP_PT];
+                float4 a = my_land[(d * 6 + u * 3 + 2) * OP_PT];
+                const bool okr = row_base + 16 * u < p.n_rows;
+                float4 dz;
+                dz.x = okr ? fmaf(cA.x, g.x, fmaf(cB.x, zz.x, cC.x)) : 0.f;
+                dz.y = okr ? fmaf(cA.y, g.y, fmaf(cB.y, zz.y, cC.y)) : 0.f;
+                dz.z = okr ? fmaf(cA.z, g.z, fmaf(cB.z, zz.z, cC.z)) : 0.f;
+                dz.w = okr ? fmaf(cA.w, g.w, fmaf(cB.w, zz.w, cC.w)) : 0.f;
+                if (ACT) {
+                    a.x = okr ? fmaxf(fmaf(a.x, sc.x, sh.x), 0.f) : 0.f;
+                    a.y = okr ? fmaxf(fmaf(a.y, sc.y, sh.y), 0.f) : 0.f;
+                    a.z = okr ? fmaxf(fmaf(a.z, sc.z, sh.z), 0.f) : 0.f;
+                    a.w = okr ? fmaxf(fmaf(a.w, sc.w, sh.w), 0.f) : 0.f;
+                }
+                vdz[u] = dz;
+                va[u] = a;
+                s_dz.x += dz.x; s_dz.y += dz.y; s_dz.z += dz.z; s_dz.w += dz.w;
+            }
+            // a planes -> ring slot (free once GEMM 2 of the chunk two back has retired)
+            const uint32_t slot = (uint32_t)j & 1, bph = ((uint32_t)j >> 1) & 1;
+            if (!(ok = mbar_wait<32>(&b_empty[slot], bph ^ 1, abort_flag))) break;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int k = kr0 + 16 * u;
+                unsigned char* sb = sm_b + slot * OP_B_SLOT + (c4 >> 1) * OP_B_CS + (k >> 3) * 128 + (k & 7) * 16 + (c4 & 1) * 8;
+                uint32_t h0, m0, l0, h1, m1, l1;
+                split3x2(va[u].x, va[u].y, h0, m0, l0);
+                split3x2(va[u].z, va[u].w, h1, m1, l1);
+                *reinterpret_cast<uint2*>(sb) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(sb + 8 * OP_B_CS) = make_uint2(m0, m1);
+                *reinterpret_cast<uint2*>(sb + 16 * OP_B_CS) = make_uint2(l0, l1);
+            }
+            // dz planes -> the tile buffer (free once every MMA of the previous tile has retired)
+            if (c == 0 && !(ok = mbar_wait<32>(a_free, (((uint32_t)j >> 2) & 1) ^ 1, abort_flag))) break;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int k = c * 32 + kr0 + 16 * u;
+                unsigned char* sa = sm_a + (c4 >> 1) * OP_A_CS + (k >> 3) * 128 + (k & 7) * 16 + (c4 & 1) * 8;
+                uint32_t h0, m0, l0, h1, m1, l1;
+                split3x2(vdz[u].x, vdz[u].y, h0, m0, l0);
+                split3x2(vdz[u].z, vdz[u].w, h1, m1, l1);
+                *reinterpret_cast<uint2*>(sa) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(sa + OP_A_PLANE) = make_uint2(m0, m1);
+                *reinterpret_cast<uint2*>(sa + 2 * OP_A_PLANE) = make_uint2(l0, l1);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[c]);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        // column sums of dz: lanes l and l ^ 16 share c4 -> fold, one shared atomic per column and warp
+        float v[4] = {s_dz.x, s_dz.y, s_dz.z, s_dz.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] += __shfl_xor_sync(GNM_FULL_MASK, v[u], 16);
+        if (lane < 16) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) atomicAdd(&s_sum[c4 * 4 + u], v[u]);
+        }
+    }
+    // ================================ dW / db (once per CTA) ==========================================================
+    __syncwarp();
+    const bool fin = mbar_wait<64>(done, 0, abort_flag);
+    tc_fence_after();
+    __syncthreads();
+    float* tile = reinterpret_cast<float*>(sm_land);                     // [128][65] floats: the landing ring is free now
+    const bool have = (int)blockIdx.x < n_tiles;
+    if (fin && have && warp < 4) {
+        const int m = warp * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t g0[16], g1[16], g2[16], g3[16];
+            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + OP_D2A + c0;
+            tmem_ld16(ta, g0);
+            tmem_ld16(ta + 64, g1);
+            tmem_ld16(ta + 128, g2);
+            if (warp < 2) tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + OP_D2B + c0, g3);   // lo plane: lanes 0-63 only
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float t = (__uint_as_float(g2[j]) + __uint_as_float(g1[j])) + __uint_as_float(g0[j]);
+                if (warp < 2) t += __uint_as_float(g3[j]);
+                tile[m * 65 + c0 + j] = t;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (fin && have) {
+        for (int e = tid; e < BT_F * BT_F; e += OP_THREADS) {
+            const int o = e >> 6, i = e & 63;
+            atomicAdd(&p.dw[(int64_t)o * p.lddw + i], tile[o * 65 + i] + tile[(64 + o) * 65 + i]);
+        }
+        if (p.db != nullptr && tid < BT_F) atomicAdd(&p.db[tid], s_sum[tid]);
+    }
+    if (warp == OP_MMA_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+    if (ACT) bn_tail_run(p.tail);
+}
+
 }  // namespace
 
 int gnm_launch_linear_bwd_dx_tc(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* coef,
@@ -735,6 +1163,49 @@ int gnm_launch_linear_wgrad_tc(const float* dy, int64_t lddy, const float* z, in
     else if (act) GNM_WG_LAUNCH(true, false);
     else GNM_WG_LAUNCH(false, false);
 #undef GNM_WG_LAUNCH
+    e = cudaGetLastError();
+    return e == cudaSuccess ? GNM_OK : (int)e;
+}
+
+/* One-pass backward unit (see linear_bwd_onepass_tc_kernel). GNM_ERR_TOO_LARGE, nothing launched, unless the unit is 64 x 64,
+ * every matrix is 16-byte aligned with a leading dimension divisible by four, and dx and dw are requested. */
+int gnm_launch_linear_bwd_onepass_tc(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* coef,
+                                     const float* x, int64_t ldx, const float* in_scale, const float* in_shift,
+                                     const float* in_mean, const float* in_rstd, const float* w, int64_t ldw, float* dw,
+                                     int64_t lddw, float* dbias, float* dx, int64_t lddx, double* stats_in, int n_rows,
+                                     int n_out, int n_in, const gnm_bn_tail* tail, cudaStream_t stream) {
+    if (n_in != BT_F || n_out != BT_F || dx == nullptr || dw == nullptr || n_rows < 1) return GNM_ERR_TOO_LARGE;
+    if (((lddy | ldz | ldx | lddx) & 3) != 0 || !gnm_aligned16(dy) || !gnm_aligned16(z) || !gnm_aligned16(x) ||
+        !gnm_aligned16(dx) || !gnm_aligned16(coef))
+        return GNM_ERR_TOO_LARGE;
+    const bool act = in_scale != nullptr;
+    if (act && (!gnm_aligned16(in_scale) || !gnm_aligned16(in_shift))) return GNM_ERR_TOO_LARGE;
+    if (tail != nullptr && (stats_in == nullptr || !act)) return GNM_ERR_BAD_ARG;
+    int dev = 0, sms = 148, major = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) return GNM_ERR_TOO_LARGE;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    LinBwd1Params p;
+    p.dy = dy; p.lddy = lddy; p.z = z; p.ldz = ldz; p.coef = coef; p.w = w; p.ldw = ldw; p.x = x; p.ldx = ldx;
+    p.in_scale = in_scale; p.in_shift = in_shift; p.in_mean = in_mean; p.in_rstd = in_rstd; p.dx = dx; p.lddx = lddx;
+    p.dw = dw; p.lddw = lddw; p.db = dbias; p.stats_in = stats_in; p.n_rows = n_rows;
+    const int trc = bn_tail_args(tail, stats_in, n_in, &p.tail);
+    if (trc != GNM_OK) return trc;
+    const int tiles = (n_rows + 127) / 128;
+    const int grid = tiles < sms ? tiles : sms;
+    cudaError_t e;
+#define GNM_OP_LAUNCH(A)                                                                                                    \
+    do {                                                                                                                    \
+        e = cudaFuncSetAttribute(linear_bwd_onepass_tc_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, OP_SMEM);    \
+        if (e != cudaSuccess) return (int)e;                                                                                \
+        gnm_count_launch(GNM_K_LINEAR_BWD_ONEPASS_TC);                                                                      \
+        e = gnm_launch_pdl<LinBwd1Params>(linear_bwd_onepass_tc_kernel<A>, grid, OP_THREADS, OP_SMEM, stream, p);           \
+        if (e != cudaSuccess) return (int)e;                                                                                \
+    } while (0)
+    if (act) GNM_OP_LAUNCH(true);
+    else GNM_OP_LAUNCH(false);
+#undef GNM_OP_LAUNCH
     e = cudaGetLastError();
     return e == cudaSuccess ? GNM_OK : (int)e;
 }

@@ -528,12 +528,12 @@ bn_bwd_apply_kernel(const float* __restrict__ z, int64_t ldz, int n_rows, int n_
 int gnm_launch_linear_tc(const float* x, int64_t ldx, int n_rows, int n_in, const float* w, int64_t ldw, int w_is_kn,
                          const float* bias, const float* in_scale, const float* in_shift, float* y, int64_t ldy,
                          int n_out, double* col_stats, const gnm_bn_tail* tail, cudaStream_t stream);
-static int g_linear_impl = 0;     // 0 auto, 1 FFMA kernel, 2 tcgen05 kernel only (A/B switch, see gnm_set_linear_impl)
+static int g_linear_impl = 0;     // 0 auto, 1 FFMA kernel, 2 tcgen05 kernels only, 3 = 2 with the two-pass backward pair (A/B switch)
 
 int gnm_linear_impl_value() { return g_linear_impl; }
 
 extern "C" int gnm_set_linear_impl(int impl) {
-    if (impl < 0 || impl > 2) return GNM_ERR_BAD_ARG;
+    if (impl < 0 || impl > 3) return GNM_ERR_BAD_ARG;
     g_linear_impl = impl;
     return GNM_OK;
 }
@@ -546,10 +546,10 @@ extern "C" int gnm_linear(const float* x, int64_t ldx, int n_rows, int n_in, con
     if (!x || !w || !y) return GNM_ERR_BAD_ARG;
     if ((in_scale == nullptr) != (in_shift == nullptr)) return GNM_ERR_BAD_ARG;
     // large-M 64-wide layers go to the tensor cores; tiny problems are not worth a persistent 148-CTA launch
-    if (g_linear_impl != 1 && (g_linear_impl == 2 || n_rows >= 4096)) {
+    if (g_linear_impl != 1 && (g_linear_impl >= 2 || n_rows >= 4096)) {
         const int rc = gnm_launch_linear_tc(x, ldx, n_rows, n_in, w, ldw, w_is_kn, bias, in_scale, in_shift, y, ldy, n_out,
                                             col_stats, tail, gnm_cast_stream(stream));
-        if (rc == GNM_OK || g_linear_impl == 2 || rc != GNM_ERR_TOO_LARGE) return rc;
+        if (rc == GNM_OK || g_linear_impl >= 2 || rc != GNM_ERR_TOO_LARGE) return rc;
     }
     if (tail != nullptr) return GNM_ERR_TOO_LARGE;      // the FFMA kernel has no tail: nothing launched, call gnm_bn_finalize
     dim3 grid((n_rows + LBM - 1) / LBM, (n_out + LBN - 1) / LBN);

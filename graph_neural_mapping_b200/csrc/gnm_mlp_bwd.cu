@@ -280,7 +280,12 @@ int gnm_launch_linear_bwd_dx_tc(const float* dy, int64_t lddy, const float* z, i
 int gnm_launch_linear_wgrad_tc(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* coef,
                                const float* x, int64_t ldx, const float* in_scale, const float* in_shift, float* dw,
                                int64_t lddw, float* dbias, int n_rows, int n_out, int n_in, cudaStream_t stream);
-int gnm_linear_impl_value();     // gnm_mlp.cu: 0 auto, 1 FFMA only, 2 tcgen05 only
+int gnm_launch_linear_bwd_onepass_tc(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* coef,
+                                     const float* x, int64_t ldx, const float* in_scale, const float* in_shift,
+                                     const float* in_mean, const float* in_rstd, const float* w, int64_t ldw, float* dw,
+                                     int64_t lddw, float* dbias, float* dx, int64_t lddx, double* stats_in, int n_rows,
+                                     int n_out, int n_in, const gnm_bn_tail* tail, cudaStream_t stream);
+int gnm_linear_impl_value();     // gnm_mlp.cu: 0 auto, 1 FFMA only, 2 tcgen05 only, 3 tcgen05 two-pass pair only
 
 extern "C" int gnm_linear_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* coef,
                               const float* x, int64_t ldx, const float* in_scale, const float* in_shift,
@@ -300,16 +305,23 @@ extern "C" int gnm_linear_bwd(const float* dy, int64_t lddy, const float* z, int
     p.w = w; p.ldw = ldw; p.dw = dw; p.lddw = lddw; p.db = dbias; p.dx = dx; p.lddx = lddx; p.stats_in = stats_in;
     p.n_rows = n_rows; p.n_out = n_out; p.n_in = n_in;
     const int impl = gnm_linear_impl_value();
-    if (impl != 1 && (impl == 2 || n_rows >= 4096)) {
-        // two tensor-core passes over the rows (input gradient, then weight gradient)
-        int rc = GNM_OK;
+    if (impl != 1 && (impl >= 2 || n_rows >= 4096)) {
+        // one pass over dy, z, x when the unit is 64 x 64 and aligned ...
+        int rc = GNM_ERR_TOO_LARGE;
+        if (impl != 3 && dx != nullptr)
+            rc = gnm_launch_linear_bwd_onepass_tc(dy, lddy, z, ldz, coef, x, ldx, in_scale, in_shift, in_mean, in_rstd, w, ldw,
+                                                  dw, lddw, dbias, dx, lddx, stats_in, n_rows, n_out, n_in, tail,
+                                                  gnm_cast_stream(stream));
+        if (rc != GNM_ERR_TOO_LARGE) return rc;
+        // ... else two tensor-core passes over the rows (input gradient, then weight gradient)
+        rc = GNM_OK;
         if (dx != nullptr)
             rc = gnm_launch_linear_bwd_dx_tc(dy, lddy, z, ldz, coef, x, ldx, in_scale, in_shift, in_mean, in_rstd, w, ldw,
                                              dx, lddx, stats_in, n_rows, n_out, n_in, tail, gnm_cast_stream(stream));
         if (rc == GNM_OK)
             rc = gnm_launch_linear_wgrad_tc(dy, lddy, z, ldz, coef, x, ldx, in_scale, in_shift, dw, lddw, dbias, n_rows,
                                             n_out, n_in, gnm_cast_stream(stream));
-        if (rc == GNM_OK || impl == 2 || rc != GNM_ERR_TOO_LARGE) return rc;
+        if (rc == GNM_OK || impl >= 2 || rc != GNM_ERR_TOO_LARGE) return rc;
     }
     if (tail != nullptr) return GNM_ERR_TOO_LARGE;      // the fused FFMA kernel has no tail: nothing launched
     int dev = 0, sms = 148;

@@ -57,7 +57,7 @@ def device_info():
 
 
 KERNEL_FAMILIES = ("aggregate_csr", "aggregate_mma_sync", "aggregate_tc", "linear_ffma", "linear_tc", "linear_bwd_ffma",
-                   "linear_bwd_dx_tc", "linear_wgrad_tc", "linear_wgrad_ffma", "other")
+                   "linear_bwd_dx_tc", "linear_wgrad_tc", "linear_wgrad_ffma", "other", "linear_bwd_onepass_tc")
 
 
 def launch_counts():

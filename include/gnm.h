@@ -92,7 +92,7 @@ int gnm_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_o
  * (a kernel recorded during CUDA-graph capture counts once, its replays are the caller's to count). Families:
  * 0 aggregate (CSR warp-per-row), 1 aggregate (mma.sync dense blocks), 2 aggregate (tcgen05), 3 linear (FFMA),
  * 4 linear (tcgen05), 5 linear_bwd (fused FFMA), 6 linear_bwd dX (tcgen05), 7 linear_bwd dW (tcgen05),
- * 8 linear_wgrad (FFMA), 9 every other kernel. Returns the number of families (>= 0) or GNM_ERR_BAD_ARG.
+ * 8 linear_wgrad (FFMA), 9 every other kernel, 10 linear_bwd one-pass dX + dW (tcgen05). Returns the number of families (>= 0) or GNM_ERR_BAD_ARG.
  * Tests use it to prove WHICH kernel family a code path ran; bench.py to count launches. */
 int gnm_launch_counts(int64_t* out, int n);
 /* Programmatic dependent launch of the persistent tcgen05 kernels (aggregation, Linear forward / dX / dW): off by default
@@ -241,7 +241,8 @@ int gnm_linear(const float* x, int64_t ldx, int n_rows, int n_in,
 
 /* gnm_linear implementation switch (process-wide A/B aid; the only global setting of the library):
  * 0 = auto (tcgen05 kernel for n_in, n_out <= 64 and n_rows >= 4096, fp32 FFMA kernel otherwise), 1 = FFMA only,
- * 2 = tcgen05 only. The tcgen05 kernel keeps fp32-level accuracy by exact bf16x3 operand splits (six MMAs per k-step). */
+ * 2 = tcgen05 only, 3 = tcgen05 only with gnm_linear_bwd held to its two-pass kernel pair (without it a 64 x 64 aligned unit
+ * takes the one-pass kernel). The tcgen05 kernels keep fp32-level accuracy by exact bf16x3 operand splits (six products). */
 int gnm_set_linear_impl(int impl);
 
 /* Weight gradient: dw[o, i] += sum_m dz[m, o] * f(x[m, i]); dbias[o] += sum_m dz[m, o] (nullable).

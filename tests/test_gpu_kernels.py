@@ -673,7 +673,8 @@ def test_linear_bwd_fused(m, fo, fi, act, train):
                                      (129, 63, 37), (64 * 148 * 3 + 5, 64, 64)])
 @pytest.mark.parametrize("act,train", [(True, True), (False, True), (True, False)])
 def test_linear_bwd_tcgen05(m, fo, fi, act, train):
-    """Tensor-core backward unit (input-gradient kernel + weight-gradient kernel, bf16x3 exact splits) against the
+    """Tensor-core backward unit - the one-pass kernel (impl 2; 64 x 64 aligned units with dx) and the two-pass pair of an
+    input-gradient and a weight-gradient kernel (impl 3, and every other shape), bf16x3 exact splits - against the
     fp64 stand-in at the FFMA kernel's tolerance, and against the FFMA kernel itself."""
     torch.manual_seed(m + fo + fi)
     dy, z = torch.randn(m, fo, device=DEV), torch.randn(m, fo, device=DEV) * 2 + 0.5
@@ -689,8 +690,9 @@ def test_linear_bwd_tcgen05(m, fo, fi, act, train):
     irs = torch.rand(fi, device=DEV) + 0.5 if act else None
     outs = []
     try:
-        for impl in (2, 1):
+        for impl in (2, 3, 1):
             ops.set_linear_impl(impl)
+            before = ops.launch_counts()
             dw, db = torch.zeros(fo, fi, device=DEV), torch.zeros(fo, device=DEV)
             dx = torch.full((m, fi), float("nan"), device=DEV)
             st = torch.zeros(2 * fi, dtype=torch.float64, device=DEV) if act else None
@@ -698,6 +700,8 @@ def test_linear_bwd_tcgen05(m, fo, fi, act, train):
             dw2, db2 = torch.zeros(fo, fi, device=DEV), torch.zeros(fo, device=DEV)
             ops.linear_bwd(dy, z, coef, x, None, None, None, None, w, dw2, db2, None, None)
             outs.append((dw, db, dx, st, dw2, db2))
+            onepass = ops.launch_counts()["linear_bwd_onepass_tc"] - before["linear_bwd_onepass_tc"]
+            assert onepass == (1 if impl == 2 and fo == 64 and fi == 64 else 0), (impl, onepass)
     finally:
         ops.set_linear_impl(0)
     assert not ops.aggregate_tc_status(), "tcgen05 kernel hit a barrier timeout"
@@ -707,13 +711,14 @@ def test_linear_bwd_tcgen05(m, fo, fi, act, train):
     emul_ops.linear_bwd(c(dy), c(z), c(coef), c(x), c(isc), c(ish), c(imu), c(irs), c(w), dwr, dbr, dxr, str_)
     dwr2, dbr2 = torch.zeros(fo, fi), torch.zeros(fo)
     emul_ops.linear_bwd(c(dy), c(z), c(coef), c(x), None, None, None, None, c(w), dwr2, dbr2, None, None)
-    tc, ff = outs
+    tc, tc2, ff = outs
     if act:
         # the ReLU mask is discontinuous: entries whose pre-activation is within rounding of zero may legitimately
         # flip between the fp32 fmaf and the fp64 stand-in; they are compared against the FFMA kernel only
         edge = (x.double() * isc.double() + ish.double()).abs() < 1e-5
         assert int(edge.sum()) < 1e-4 * edge.numel() + 16
         tc[2][edge] = 0.0
+        tc2[2][edge] = 0.0
         dxr[edge.cpu()] = 0.0
         ff[2][edge] = 0.0
     assert_close(tc[2], dxr, TOL, "dx vs fp64")
@@ -723,8 +728,12 @@ def test_linear_bwd_tcgen05(m, fo, fi, act, train):
     assert_close(tc[5], dbr2, TOL, "db (no dx) vs fp64")
     assert_close(tc[2], ff[2], TOL, "dx vs FFMA")
     assert_close(tc[0], ff[0], TOL, "dw vs FFMA")
+    assert_close(tc2[2], dxr, TOL, "two-pass dx vs fp64")
+    assert_close(tc2[0], dwr, TOL, "two-pass dw vs fp64")
+    assert_close(tc2[1], dbr, TOL, "two-pass db vs fp64")
     if act:
         assert_close(tc[3], ff[3], 2e-5, "stats_in vs FFMA")
+        assert_close(tc2[3], ff[3], 2e-5, "two-pass stats_in vs FFMA")
         if not bool(edge.any()):
             assert_close(tc[3], str_, 2e-5, "stats_in vs fp64")
 
