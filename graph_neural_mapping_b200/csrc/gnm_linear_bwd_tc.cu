@@ -736,15 +736,33 @@ __global__ void __launch_bounds__(OP_THREADS, 1) linear_bwd_onepass_tc_kernel(co
     pdl_launch_dependents();
     pdl_wait();
     // ---- setup: [W_hi | W_mid | W_lo], K-major: (n' = plane * 64 + i, k = o) -> (k/8)*KCORE + (n'/8)*128 + (n'%8)*16 + (k%8)*2
-    for (int e = tid; e < BT_F * BT_F / 2; e += OP_THREADS) {
-        const int n = e >> 5, k = (e & 31) * 2;
-        const float w0 = p.w[(int64_t)k * p.ldw + n], w1 = p.w[(int64_t)(k + 1) * p.ldw + n];
-        uint32_t h, m, l;
-        split3x2(w0, w1, h, m, l);
-        const int off = (k >> 3) * OP_W_KCORE + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
-        *reinterpret_cast<uint32_t*>(sm_w + off) = h;
-        *reinterpret_cast<uint32_t*>(sm_w + 8 * 128 + off) = m;
-        *reinterpret_cast<uint32_t*>(sm_w + 16 * 128 + off) = l;
+    // (consecutive threads read consecutive i of two rows o, o + 1: coalesced; all loads of a thread are in flight
+    // before the first split - the set-up is one global round trip, not five)
+    {
+        constexpr int NP = (BT_F * BT_F / 2 + OP_THREADS - 1) / OP_THREADS;
+        float w0[NP], w1[NP];
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            const int e = tid + u * OP_THREADS;
+            const int n = e & 63, k = (e >> 6) * 2;
+            w0[u] = w1[u] = 0.f;
+            if (e < BT_F * BT_F / 2) {
+                w0[u] = __ldg(p.w + (int64_t)k * p.ldw + n);
+                w1[u] = __ldg(p.w + (int64_t)(k + 1) * p.ldw + n);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            const int e = tid + u * OP_THREADS;
+            if (e >= BT_F * BT_F / 2) break;
+            const int n = e & 63, k = (e >> 6) * 2;
+            uint32_t h, m, l;
+            split3x2(w0[u], w1[u], h, m, l);
+            const int off = (k >> 3) * OP_W_KCORE + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
+            *reinterpret_cast<uint32_t*>(sm_w + off) = h;
+            *reinterpret_cast<uint32_t*>(sm_w + 8 * 128 + off) = m;
+            *reinterpret_cast<uint32_t*>(sm_w + 16 * 128 + off) = l;
+        }
     }
     for (int i = tid; i < BT_F; i += OP_THREADS) {
         sm_c[i] = ACT ? p.in_scale[i] : 1.f;

@@ -76,19 +76,32 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcPar
 
     // ---- one-time setup: W planes (K-major core matrices), prologue constants, barriers, tensor memory
     pdl_launch_dependents();
-    for (int e = tid; e < LT_F * LT_F / 2; e += LT_THREADS) {
-        const int n = e >> 5, k = (e & 31) * 2;                       // element pair (n, k), (n, k+1)
-        float w0 = 0.f, w1 = 0.f;
-        if (n < p.n_out) {
-            if (k < p.n_in) w0 = p.w_is_kn ? p.w[(int64_t)k * p.ldw + n] : p.w[(int64_t)n * p.ldw + k];
-            if (k + 1 < p.n_in) w1 = p.w_is_kn ? p.w[(int64_t)(k + 1) * p.ldw + n] : p.w[(int64_t)n * p.ldw + k + 1];
+    // (every load of a thread is in flight before the first split: the set-up is one global round trip, not four)
+    {
+        constexpr int NP = (LT_F * LT_F / 2 + LT_THREADS - 1) / LT_THREADS;
+        float w0[NP], w1[NP];
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            const int e = tid + u * LT_THREADS;
+            const int n = e >> 5, k = (e & 31) * 2;                   // element pair (n, k), (n, k+1)
+            w0[u] = w1[u] = 0.f;
+            if (e < LT_F * LT_F / 2 && n < p.n_out) {
+                if (k < p.n_in) w0[u] = p.w_is_kn ? __ldg(p.w + (int64_t)k * p.ldw + n) : __ldg(p.w + (int64_t)n * p.ldw + k);
+                if (k + 1 < p.n_in) w1[u] = p.w_is_kn ? __ldg(p.w + (int64_t)(k + 1) * p.ldw + n) : __ldg(p.w + (int64_t)n * p.ldw + k + 1);
+            }
         }
-        uint32_t h, m, l;
-        split3x2(w0, w1, h, m, l);
-        const int off = (k >> 3) * LT_W_KCORE + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
-        *reinterpret_cast<uint32_t*>(sm_w + off) = h;
-        *reinterpret_cast<uint32_t*>(sm_w + LT_W_PLANE + off) = m;
-        *reinterpret_cast<uint32_t*>(sm_w + 2 * LT_W_PLANE + off) = l;
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            const int e = tid + u * LT_THREADS;
+            if (e >= LT_F * LT_F / 2) break;
+            const int n = e >> 5, k = (e & 31) * 2;
+            uint32_t h, m, l;
+            split3x2(w0[u], w1[u], h, m, l);
+            const int off = (k >> 3) * LT_W_KCORE + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
+            *reinterpret_cast<uint32_t*>(sm_w + off) = h;
+            *reinterpret_cast<uint32_t*>(sm_w + LT_W_PLANE + off) = m;
+            *reinterpret_cast<uint32_t*>(sm_w + 2 * LT_W_PLANE + off) = l;
+        }
     }
     // weights above, barriers / tensor memory below need nothing from the kernel in front; the BatchNorm affine of the
     // prologue does (it comes out of that kernel's tail): wait here

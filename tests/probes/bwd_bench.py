@@ -1,5 +1,6 @@
 """Micro-benchmark / ncu target for the backward unit at the benchmark shape (M = 409,600 rows, 64 -> 64).
-usage: bwd_bench.py [rows] [iters] [impl ...]   impl 2 = tcgen05 (dx kernel + wgrad kernel), 1 = fused FFMA kernel"""
+usage: bwd_bench.py [rows] [iters] [impl ...]   impl 2 = tcgen05 (one-pass kernel when dx is requested), 3 = tcgen05 two-pass
+pair (dx kernel + wgrad kernel), 1 = fused FFMA kernel"""
 import os, sys
 import numpy as np
 import torch
@@ -35,6 +36,6 @@ for impl in impls:
         t = float(np.median([ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(iters)]))
         nbytes = (16.0 if with_dx else 12.0) * m * 64          # dy, z, x read once (+ dx written)
         print("%-8s %-8s median %8.1f us -> %7.1f GB/s algorithmic (%.3f of 6546), abort=%s"
-              % ("tcgen05" if impl == 2 else "ffma", "dx+dw" if with_dx else "dw only", t, nbytes / t / 1e3,
+              % ({2: "tcgen05", 3: "tc-2pass"}.get(impl, "ffma"), "dx+dw" if with_dx else "dw only", t, nbytes / t / 1e3,
                  nbytes / t / 1e3 / 6546.2, ops.aggregate_tc_status()))
 ops.set_linear_impl(0)
