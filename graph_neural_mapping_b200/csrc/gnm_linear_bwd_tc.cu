@@ -915,6 +915,25 @@ __global__ void __launch_bounds__(OP_THREADS, 1) linear_bwd_onepass_tc_kernel(co
                 for (int c = 0; c < 4 && ok; ++c, ++cc) {
                     if (!(ok = mbar_wait(&full[c], it & 1, abort_flag))) break;
                     tc_fence_after();
+                    if (c == 3) {
+                        // GEMM 1: all 128 rows, four k-steps of 16 channels (two channel cores). Issued BEFORE the last
+                        // chunk's GEMM 2 so that a_free fires as early as possible: the producers then overwrite the dz
+                        // planes chunk by chunk from row 0, and reach the rows GEMM 2 of this chunk still reads only after
+                        // waiting for its a-plane slot (b_empty), i.e. after it has retired.
+                        if (!(ok = mbar_wait(d1_empty, (it & 1) ^ 1, abort_flag))) break;
+                        tc_fence_after();
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t a_h = umma_desc(a_base + (uint32_t)(ks * 2 * OP_A_CS), OP_A_CS, 128);
+                            const uint64_t pl = (uint64_t)(OP_A_PLANE >> 4);
+                            const uint64_t b_d = umma_desc(w_base + (uint32_t)(ks * 2 * OP_W_KCORE), OP_W_KCORE, 128);
+                            umma_ss(tmem, a_h, b_d, id_k | n192, ks ? 1u : 0u);
+                            umma_ss(tmem, a_h + pl, b_d, id_k | n128, 1u);
+                            umma_ss(tmem, a_h + 2 * pl, b_d, id_k | n64, 1u);
+                        }
+                        umma_commit(d1_full);
+                        umma_commit(a_free);
+                    }
                     const uint32_t slot = cc & 1;
                     // GEMM 2: rows c*32 .. c*32+31 of the tile (row cores 4 c ..), two k-steps of 16 rows
 #pragma unroll
@@ -929,20 +948,6 @@ __global__ void __launch_bounds__(OP_THREADS, 1) linear_bwd_onepass_tc_kernel(co
                     umma_commit(&b_empty[slot]);
                 }
                 if (!ok) break;
-                if (!(ok = mbar_wait(d1_empty, (it & 1) ^ 1, abort_flag))) break;
-                tc_fence_after();
-                // GEMM 1: all 128 rows, four k-steps of 16 channels (two channel cores)
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t a_h = umma_desc(a_base + (uint32_t)(ks * 2 * OP_A_CS), OP_A_CS, 128);
-                    const uint64_t pl = (uint64_t)(OP_A_PLANE >> 4);
-                    const uint64_t b_d = umma_desc(w_base + (uint32_t)(ks * 2 * OP_W_KCORE), OP_W_KCORE, 128);
-                    umma_ss(tmem, a_h, b_d, id_k | n192, ks ? 1u : 0u);
-                    umma_ss(tmem, a_h + pl, b_d, id_k | n128, 1u);
-                    umma_ss(tmem, a_h + 2 * pl, b_d, id_k | n64, 1u);
-                }
-                umma_commit(d1_full);
-                umma_commit(a_free);
             }
             if (ok) umma_commit(done);
         }
