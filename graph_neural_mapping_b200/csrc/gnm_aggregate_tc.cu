@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
     uint2* lut = reinterpret_cast<uint2*>(tc_smem + (size_t)24 * b_ncore_stride + TC_EPI_WARPS * TC_STG);
     // fused relu / BatchNorm backward only: one more tile per epilogue warp, the z rows of its slice (cp.async)
     float* sm_zst = reinterpret_cast<float*>(tc_smem + (size_t)24 * b_ncore_stride + TC_EPI_WARPS * TC_STG + 4096);
+    // affine variant only: landing area of the second stream's rows (cp.async, eight 16-byte slots per producer thread)
+    float4* sm_aff = reinterpret_cast<float4*>(tc_smem + (size_t)24 * b_ncore_stride + TC_EPI_WARPS * TC_STG + 4096 +
+                                               ((kFuse && p.rz != nullptr) ? TC_EPI_WARPS * TC_STG : 0));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     pdl_launch_dependents();
@@ -531,6 +534,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
         // affine variant: this thread's column never changes within a slab - its coefficients live in registers
         float4 aff_a = make_float4(0.f, 0.f, 0.f, 0.f), aff_b = aff_a, aff_c = aff_a;
         int aff_col = -1;
+        // The second stream (aff_z) lands in shared memory through cp.async and meets the first (registers, bq) only when
+        // the chunk is converted: forming cA*src + cB*z + cC right behind the loads made every chunk wait for DRAM
+        // (B fill 130 k of 292 k cycles per CTA, 164 us per launch against 96 us for the plain variant).
+        float4* my_aff = sm_aff + ptid;                      // slot u at my_aff[u * 256]
+        const uint32_t my_aff_u32 = smem_u32(my_aff);
+        const bool aff_on = kAff && p.aff_coef != nullptr;
         auto load_b = [&](const ItemP& q, int kc) {
             const int col = q.f0 + lb_c4 * 4;
             const bool ok0 = kc < q.n_kc && col < p.n_feat;
@@ -541,6 +550,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                 aff_c = __ldg(reinterpret_cast<const float4*>(p.aff_coef + 2 * p.n_feat + col));
                 aff_col = col;
             }
+            // a chunk that was requested but never converted (a group without a chunk in a one-chunk graph) must not
+            // race the new requests for the same landing slots
+            if (kAff && aff_on) asm volatile("cp.async.wait_group 0;" ::: "memory");
             const float* rowp = p.src + (int64_t)(q.n0 + k_lo + kbase) * p.ld_src + col;
             const float* zrow = kAff ? p.aff_z + (int64_t)(q.n0 + k_lo + kbase) * p.ld_aff_z + col : nullptr;
 #pragma unroll
@@ -554,19 +566,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                     } else {
                         v = __ldg(reinterpret_cast<const float4*>(rowp + (int64_t)(u * 8) * p.ld_src));
                     }
-                    if (kAff && p.aff_coef != nullptr) {
-                        const float4 zv = __ldg(reinterpret_cast<const float4*>(zrow + (int64_t)(u * 8) * p.ld_aff_z));
-                        v.x = fmaf(aff_a.x, v.x, fmaf(aff_b.x, zv.x, aff_c.x)); v.y = fmaf(aff_a.y, v.y, fmaf(aff_b.y, zv.y, aff_c.y));
-                        v.z = fmaf(aff_a.z, v.z, fmaf(aff_b.z, zv.z, aff_c.z)); v.w = fmaf(aff_a.w, v.w, fmaf(aff_b.w, zv.w, aff_c.w));
-                    }
-                    if (kAvg && p.mode == 2) {
+                    if (kAvg && p.mode == 2 && !aff_on) {
                         const int jr = q.n0 + k_lo + k;
                         const float w = 1.f / (float)(p.rowptr[jr + 1] - p.rowptr[jr]);
                         v.x *= w; v.y *= w; v.z *= w; v.w *= w;
                     }
                 }
+                if (kAff && aff_on) {
+                    const bool okz = ok0 && k < q.nk;
+                    const int nbytes = okz ? 16 : 0;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(my_aff_u32 + (uint32_t)(u * 256 * 16)),
+                                 "l"(okz ? zrow + (int64_t)(u * 8) * p.ld_aff_z : p.aff_z), "r"(nbytes) : "memory");
+                }
                 bq[u] = v;
             }
+            if (kAff && aff_on) asm volatile("cp.async.commit_group;" ::: "memory");
         };
         ItemP cur, nxt;
         fetch_item(blockIdx.x, cur);
@@ -626,6 +640,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) aggregate_tc_kernel(const AggTc
                         }
                         first_b = false;
                         const long long tb0 = DBG ? clock64() : 0;
+                        if (kAff && aff_on) {
+                            // the chunk's second stream has landed (one group per chunk and thread): h = cA*src + cB*z + cC
+                            asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int k = kc * TC_KC + lb_kr + u * 8;
+                                const float4 zv = my_aff[u * 256];
+                                float4 v = bq[u];
+                                v.x = fmaf(aff_a.x, v.x, fmaf(aff_b.x, zv.x, aff_c.x)); v.y = fmaf(aff_a.y, v.y, fmaf(aff_b.y, zv.y, aff_c.y));
+                                v.z = fmaf(aff_a.z, v.z, fmaf(aff_b.z, zv.z, aff_c.z)); v.w = fmaf(aff_a.w, v.w, fmaf(aff_b.w, zv.w, aff_c.w));
+                                if (k >= cur.nk || lb_c4 * 4 + cur.f0 >= p.n_feat) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (kAvg && p.mode == 2 && k < cur.nk) {
+                                    const int jr = cur.n0 + k_lo + k;
+                                    const float w = 1.f / (float)(p.rowptr[jr + 1] - p.rowptr[jr]);
+                                    v.x *= w; v.y *= w; v.z *= w; v.w *= w;
+                                }
+                                bq[u] = v;
+                            }
+                        }
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             const int k = kc * TC_KC + lb_kr + u * 8, c4 = lb_c4;
@@ -761,7 +794,8 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
     p.n_slabs = (n_feat + TC_SLAB - 1) / TC_SLAB;
     p.kcores_max = (((ksplit ? TC_K_PASS : n_max) + 15) / 16) * 2;
     // B planes + staging + LUT (+ the z tiles of the fused relu / BatchNorm backward)
-    const int smem = 24 * (p.kcores_max * 128 + 16) + TC_EPI_WARPS * TC_STG + 4096 + 1024 + (fuse ? TC_EPI_WARPS * TC_STG : 0);
+    const int smem = 24 * (p.kcores_max * 128 + 16) + TC_EPI_WARPS * TC_STG + 4096 + 1024 + (fuse ? TC_EPI_WARPS * TC_STG : 0) +
+                     (aff_coef ? TC_PROD_WARPS * 32 * 8 * 16 : 0);
     if (smem > smem_cap - 1024) return GNM_ERR_TOO_LARGE;
     const int64_t items = (int64_t)n_graphs * p.n_slabs;
     const int grid = (int)(items < sms ? items : sms);
@@ -785,7 +819,9 @@ int gnm_launch_aggregate_tc(const int64_t* bitmap_addr, const int32_t* node_off,
     }
     if (p.dbg != nullptr) {
         e = var == 0 ? launch_variant<true, 0>(p, grid, smem, stream)
-            : var == TCV_FUSE ? launch_variant<true, TCV_FUSE>(p, grid, smem, stream) : launch_variant<true, TCV_ALL>(p, grid, smem, stream);
+            : var == TCV_FUSE ? launch_variant<true, TCV_FUSE>(p, grid, smem, stream)
+            : var == TCV_MAP ? launch_variant<true, TCV_MAP>(p, grid, smem, stream)
+            : var == TCV_AFF ? launch_variant<true, TCV_AFF>(p, grid, smem, stream) : launch_variant<true, TCV_ALL>(p, grid, smem, stream);
         return e == cudaSuccess ? GNM_OK : (int)e;
     }
     switch (var) {

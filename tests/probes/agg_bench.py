@@ -58,6 +58,21 @@ def main():
                                                          None, z, scale, shift, mean, rstd, d_pooled, ps, d_score, u, d_neg, n_neg,
                                                          dst, stats, tail)
             name = "tcgen05 fused bwd"
+        elif impl == 4:
+            # layer 0: one 400 x F table shared by every graph (tags = arange), bias, BatchNorm statistics of the output
+            table = torch.randn(n_nodes, f, device=dev)
+            tags = torch.arange(n_nodes, dtype=torch.int32, device=dev)
+            bias = torch.randn(f, device=dev)
+            ostats = torch.zeros(2, f, dtype=torch.float64, device=dev)
+            fn = lambda: ops.aggregate_dense_table(bs.bitmap_addr, bs.node_off, bs.rowptr, bs.n_graphs, bs.n_max, table, tags, dst,
+                                                   0, None, bias, ostats)
+            name = "tcgen05 table"
+        elif impl == 5:
+            # layer-0 backward: rows = cA * dy + cB * z + cC formed on load (two streams)
+            z = torch.randn(m, f, device=dev)
+            coef = torch.randn(3, f, device=dev)
+            fn = lambda: ops.aggregate_dense_affine(bs.bitmap_addr, bs.node_off, bs.rowptr, bs.n_graphs, bs.n_max, src, z, coef, dst, 0)
+            name = "tcgen05 affine"
         elif impl == 0:
             fn = lambda: ops.aggregate(bs.rowptr, bs.colidx, src, None, dst, 0, None, None)
             name = "csr warp-per-row"
@@ -85,6 +100,18 @@ def main():
             d = dbg.view(148, 16).double().mean(0).tolist()
             print("  tcgen05 role cycles (mean over CTAs): epilogue %.0f (waiting acc_full %.0f) | mma %.0f (waiting a_full %.0f, "
                   "acc_empty %.0f) | producer %.0f (a_empty slow-path wait %.0f; A expand+store %.0f, a_empty wait call incl. fast path %.0f, syncwarp+arrive %.0f, B convert+store+next loads %.0f, tile head/tail (word loads, item switch) %.0f) | epilogue warp 0: drain %.0f, copy-out %.0f" % tuple(d[:14]))
+        if impl in (4, 5):
+            if impl == 4:
+                ops.aggregate(bs.rowptr, bs.colidx, table.repeat(bs.n_graphs, 1), None, ref, 0, None, None)
+                want, alg = ref + bias, alg_bytes - 4.0 * m * f
+            else:
+                ops.aggregate(bs.rowptr, bs.colidx, coef[0] * src + coef[1] * z + coef[2], None, ref, 0, None, None)
+                want, alg = ref, alg_bytes + 4.0 * m * f
+            err = float((dst - want).abs().max() / want.abs().max())
+            t = float(np.median(ts))
+            print("%-18s median %8.1f us  min %8.1f us  -> %7.1f GB/s algorithmic (%.3f of 6546)  max rel err %.2e  abort=%s"
+                  % (name, t, min(ts), alg / t / 1e3, alg / t / 1e3 / 6546.2, err, ops.aggregate_tc_status()))
+            continue
         if impl == 3:
             want = ref + d_pooled.repeat_interleave(n_nodes, 0) + d_score[:, None] * u.repeat_interleave(n_nodes, 0)
             if d_neg is not None:

@@ -491,7 +491,8 @@ def test_aggregate_dense_relu_bn_bwd(counts, f, mode, eps_on, terms):
 
 
 @pytest.mark.parametrize("counts,f,mode", [([12, 12, 12], 8, 0), ([400, 400, 400], 64, 0), ([37, 64, 5, 90, 1], 64, 0),
-                                           ([416, 129, 128, 400] * 40, 64, 0), ([48, 48], 12, 2), ([1000], 64, 0)])
+                                           ([400, 129, 128, 399] * 40, 64, 0), ([416, 129, 128, 400], 64, 0), ([48, 48], 12, 2),
+                                           ([1000], 64, 0)])
 def test_aggregate_dense_affine(counts, f, mode):
     """Aggregation of a BatchNorm-backward result folded into the row loads: Agg(cA*dy + cB*z + cC) must equal
     bn_bwd_apply followed by the aggregation, and the fp64 stand-in; batches the tcgen05 kernel cannot take return False
@@ -517,7 +518,7 @@ def test_aggregate_dense_affine(counts, f, mode):
     ops.bn_bwd_coeffs(stats, float(m), gamma, mean, rstd, coef)
     out = torch.full((m, f), float("nan"), device=DEV)
     launched = ops.aggregate_dense_affine(addr, no, rp, len(counts), max(counts), dy, z, coef, out, mode)
-    if max(counts) > 416:
+    if max(counts) > 400:                 # the second stream's landing area leaves shared memory for 400-node planes
         assert launched is False and bool(torch.isnan(out).all())
         return
     assert launched is True
