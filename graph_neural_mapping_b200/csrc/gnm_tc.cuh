@@ -31,7 +31,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // GNM_MBAR_HINT_NS > 0: every poll is a try_wait WITH a suspend-time hint - the thread sleeps in hardware until the phase
 // completes or the hint expires and costs no issue slots meanwhile (without the hint try_wait came back after ~20 cycles:
 // 40 % of all warp instructions of the fused aggregation were polls, and the MMA thread's polls - no back-off - competed
-// with the epilogue / producer warps of its scheduler, profiles/r2_aggregate_tc_fused_lines.txt).
+// with the epilogue / producer warps of its scheduler, profiles/r2_aggregate_tc_fused_before_lines.txt).
 #ifndef GNM_MBAR_HINT_NS
 #define GNM_MBAR_HINT_NS 2000
 #endif
