@@ -31,7 +31,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one aggregate_tc_kernel launch at B=1024, N=400, F=64
-# (ncu --set full, profiles/r1_aggregate_tcgen05_ncu.txt): 126.3 MB + 62.8 MB
+# (ncu --set full, profiles/r2_aggregate_tc_end_ncu.txt): 126.2 MB + 63.2 MB
 AGG_DRAM_TRAFFIC_BYTES = 189.0e6
 METRIC = "gin_train_graphs_per_sec_400roi"
 UNIT = "graphs/s"

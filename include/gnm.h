@@ -265,7 +265,9 @@ int gnm_bn_bwd_coeffs(double* stats, double count, const float* gamma, const flo
  *   dx[m,i] = (sum_o dz[m,o]*w[o,i]) * [a[m,i] > 0]                     (nullable; mask only with in_scale)
  *   stats_in[i] += sum_m dx[m,i];  stats_in[F_in+i] += sum_m dx[m,i]*(x[m,i]-in_mean[i])*in_rstd[i]   (nullable)
  * i.e. dx is already the ReLU-masked gradient at the previous unit's BatchNorm output and stats_in its
- * BatchNorm-backward reduction. */
+ * BatchNorm-backward reduction. Kernels: n_rows >= 4096 on sm_100 - a one-pass tcgen05 kernel (dy, z, x read once) when
+ * F_out = F_in = 64, dx is requested and every matrix is 16-byte aligned with a leading dimension divisible by four, else a
+ * tcgen05 input-gradient kernel followed by a weight-gradient kernel; the fused fp32 FFMA kernel otherwise. */
 int gnm_linear_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* coef,
                    const float* x, int64_t ldx, const float* in_scale, const float* in_shift,
                    const float* in_mean, const float* in_rstd, const float* w, int64_t ldw,
