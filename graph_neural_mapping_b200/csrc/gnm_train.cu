@@ -249,7 +249,65 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = k_begin; k0 < k_end; k0 += SG_K) {
+    // Interior tiles of aligned operands (every tile of the training step's three products): the next k slice's global
+    // loads are issued into registers BEFORE the current slice is multiplied - the unpipelined loop below pays one global
+    // round trip per 16-deep slice, 20 of them for K = 320, which was most of these kernels' 30-40 us.
+    const int t = threadIdx.x;
+    const int mode_a = (sak == 1 && (sam & 3) == 0) ? 0 : ((sam == 1 && (sak & 3) == 0 && !SIGMOID_A) ? 1 : -1);
+    const int mode_b = (sbk == 1 && (sbn & 3) == 0) ? 0 : ((sbn == 1 && (sbk & 3) == 0) ? 1 : -1);
+    const bool piped = mode_a >= 0 && mode_b >= 0 && m0 + SG_T <= m_tot && n0 + SG_T <= n_tot && k_begin < k_end &&
+                       ((k_end - k_begin) % SG_K) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+    if (piped) {
+        // mode 0: contiguous along k - thread -> row t >> 2, float4 (t & 3) along k; mode 1: contiguous along the row /
+        // column index - thread -> k = t >> 4, float4 (t & 15) along i
+        const float* pa = mode_a == 0 ? a + (int64_t)(m0 + (t >> 2)) * sam + (t & 3) * 4 : a + (int64_t)(t >> 4) * sak + m0 + (t & 15) * 4;
+        const float* pb = mode_b == 0 ? b + (int64_t)(n0 + (t >> 2)) * sbn + (t & 3) * 4 : b + (int64_t)(t >> 4) * sbk + n0 + (t & 15) * 4;
+        const int64_t step_a = mode_a == 0 ? SG_K : SG_K * sak, step_b = mode_b == 0 ? SG_K : SG_K * sbk;
+        pa += (int64_t)k_begin * (mode_a == 0 ? 1 : sak);
+        pb += (int64_t)k_begin * (mode_b == 0 ? 1 : sbk);
+        float4 ra = *reinterpret_cast<const float4*>(pa), rb = *reinterpret_cast<const float4*>(pb);
+        for (int k0 = k_begin; k0 < k_end; k0 += SG_K) {
+            if (SIGMOID_A) {
+                ra.x = 1.f / (1.f + expf(-ra.x)); ra.y = 1.f / (1.f + expf(-ra.y));
+                ra.z = 1.f / (1.f + expf(-ra.z)); ra.w = 1.f / (1.f + expf(-ra.w));
+                if (blockIdx.x == 0)            // mode_a == 0 here (the sigmoid variant has no mode 1)
+                    *reinterpret_cast<float4*>(a_out + (int64_t)(m0 + (t >> 2)) * lda_out + k0 + (t & 3) * 4) = ra;
+            }
+            if (mode_a == 0) {
+                const int i = t >> 2, k4 = (t & 3) * 4;
+                sa[k4][i] = ra.x; sa[k4 + 1][i] = ra.y; sa[k4 + 2][i] = ra.z; sa[k4 + 3][i] = ra.w;
+            } else {
+                *reinterpret_cast<float4*>(&sa[t >> 4][(t & 15) * 4]) = ra;
+            }
+            if (mode_b == 0) {
+                const int i = t >> 2, k4 = (t & 3) * 4;
+                sb[k4][i] = rb.x; sb[k4 + 1][i] = rb.y; sb[k4 + 2][i] = rb.z; sb[k4 + 3][i] = rb.w;
+            } else {
+                *reinterpret_cast<float4*>(&sb[t >> 4][(t & 15) * 4]) = rb;
+            }
+            __syncthreads();
+            if (k0 + SG_K < k_end) {
+                pa += step_a;
+                pb += step_b;
+                ra = *reinterpret_cast<const float4*>(pa);
+                rb = *reinterpret_cast<const float4*>(pb);
+            }
+#pragma unroll
+            for (int kk = 0; kk < SG_K; ++kk) {
+                float av[4], bv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) av[i] = sa[kk][ty + 16 * i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bv[j] = sb[kk][tx + 16 * j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+    for (int k0 = k_begin; k0 < k_end && !piped; k0 += SG_K) {
         sg_load_tile<SIGMOID_A>(sa, a, sam, sak, m0, k0, m_tot, k_end, a_out, lda_out, blockIdx.x == 0);
         sg_load_tile<false>(sb, b, sbn, sbk, n0, k0, n_tot, k_end, nullptr, 0, false);
         __syncthreads();
