@@ -527,6 +527,32 @@ def run_b200(args):
                                "what": "same call with the device graph cache DISABLED: every step ships the batch's "
                                        "int64 edge lists (what the reference does per step, graphcnn.py:195-206) and "
                                        "rebuilds CSR + bitmaps"}}
+        if trainer is not None:
+            # the same host inputs through this repo's own driver: Trainer.step(host graph list, host labels) stages the
+            # slot addresses / labels / permutation in pinned memory, copies them up and replays the whole-step graph;
+            # float(loss) reads the step's loss back (and synchronises) every step
+            def step_e2e_trainer():
+                sel = np.random.permutation(len(pool))[:B]
+                batch = [pool[i] for i in sel]
+                return float(trainer.step(batch, [g.label for g in batch]))
+            for _ in range(3):
+                step_e2e_trainer()
+            barrier()
+            h0 = trainer.h2d_bytes
+            n_tr = args.steps * inner
+            t0 = time.perf_counter()
+            for _ in range(n_tr):
+                step_e2e_trainer()
+            barrier()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            check_status("the Trainer end-to-end steps")
+            e2e["trainer"] = {"value": B * world * n_tr / float(tt.item()), "unit": UNIT,
+                              "h2d_bytes_per_step": int((trainer.h2d_bytes - h0) / n_tr), "d2h_bytes_per_step": 4,
+                              "what": "driver.Trainer.step(host S2VGraph list, host labels) + float(loss) every step: slot "
+                                      "addresses, labels and the DGI permutation go up from pinned memory each step, the "
+                                      "loss comes back each step (wall clock, max over ranks)"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
