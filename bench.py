@@ -193,10 +193,16 @@ class OpTimer(object):
         self.ops = ops
         self.orig = {}
         self.records = []
+        self.spin_cycles = 200000 if hasattr(torch.cuda, "_sleep") else 0       # ~0.1 ms of device time in FRONT of the events
 
     def _wrap(self, name, fn):
         def wrapped(*a, **k):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # Keep the GPU busy while the host gets from the start event to the kernel launch (event record + ctypes
+            # marshalling: 20-60 us for the many-argument entry points). On an idle GPU the start event would be stamped at
+            # once and that host time counted as kernel time (the step's first ops read 30-60 us too long that way).
+            if self.spin_cycles:
+                torch.cuda._sleep(self.spin_cycles)
             s.record()
             out = fn(*a, **k)
             e.record()

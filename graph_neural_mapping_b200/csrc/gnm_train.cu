@@ -294,11 +294,10 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict
             }
 #pragma unroll
             for (int kk = 0; kk < SG_K; ++kk) {
-                float av[4], bv[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) av[i] = sa[kk][ty + 16 * i];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) bv[j] = sb[kk][tx + 16 * j];
+                // four consecutive rows / columns per thread: one 128-bit shared-memory load per operand and k
+                const float4 a4 = *reinterpret_cast<const float4*>(&sa[kk][ty * 4]);
+                const float4 b4 = *reinterpret_cast<const float4*>(&sb[kk][tx * 4]);
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -313,11 +312,9 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < SG_K; ++kk) {
-            float av[4], bv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) av[i] = sa[kk][ty + 16 * i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bv[j] = sb[kk][tx + 16 * j];
+            const float4 a4 = *reinterpret_cast<const float4*>(&sa[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&sb[kk][tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -327,11 +324,11 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty + 16 * i;
+        const int m = m0 + ty * 4 + i;
         if (m >= m_tot) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx + 16 * j;
+            const int n = n0 + tx * 4 + j;
             if (n >= n_tot) continue;
             float v = acc[i][j];
             if (DSIG_EPI) {
