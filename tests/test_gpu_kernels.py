@@ -739,6 +739,54 @@ def test_linear_bwd_tcgen05(m, fo, fi, act, train):
             assert_close(tc[3], str_, 2e-5, "stats_in vs fp64")
 
 
+@pytest.mark.parametrize("m", [1, 100, 128, 129, 4096 + 31, 128 * 148 + 1])
+@pytest.mark.parametrize("act", [True, False])
+def test_linear_bwd_onepass_edges(m, act):
+    """The one-pass backward unit at its edges: fewer rows than one tile / fewer tiles than SMs / one tile more than SMs,
+    every operand a column slice of a wider matrix (leading dimension 192), dw a slice of a wider gradient buffer that
+    already holds values (the kernel ADDS), against the fp64 stand-in; untouched neighbours of the slices stay untouched."""
+    fo = fi = 64
+    torch.manual_seed(7 * m + act)
+    wide = lambda rows: torch.randn(rows, 3 * 64, device=DEV)
+    dy_w, z_w, x_w = wide(m), wide(m) * 2 + 0.5, wide(m)
+    dy, z, x = dy_w[:, 64:128], z_w[:, 64:128], x_w[:, 64:128]
+    w = torch.randn(fo, fi, device=DEV) * 0.3
+    coef = torch.randn(3, fo, device=DEV)
+    isc = torch.rand(fi, device=DEV) + 0.5 if act else None
+    ish = torch.randn(fi, device=DEV) if act else None
+    imu = torch.randn(fi, device=DEV) if act else None
+    irs = torch.rand(fi, device=DEV) + 0.5 if act else None
+    dx_w = torch.full((m, 3 * 64), 7.0, device=DEV)
+    dw_w = torch.randn(fo, 2 * fi, device=DEV)
+    dw0 = dw_w.clone()
+    db = torch.randn(fo, device=DEV)
+    db0 = db.clone()
+    st = torch.zeros(2 * fi, dtype=torch.float64, device=DEV) if act else None
+    try:
+        ops.set_linear_impl(2)
+        before = ops.launch_counts()["linear_bwd_onepass_tc"]
+        ops.linear_bwd(dy, z, coef, x, isc, ish, imu, irs, w, dw_w[:, fi:], db, dx_w[:, 64:128], st)
+        assert ops.launch_counts()["linear_bwd_onepass_tc"] == before + 1
+    finally:
+        ops.set_linear_impl(0)
+    assert not ops.aggregate_tc_status(), "tcgen05 kernel hit a barrier timeout"
+    c = lambda t: t.cpu().contiguous() if t is not None else None
+    dwr, dbr, dxr = torch.zeros(fo, fi), torch.zeros(fo), torch.empty(m, fi)
+    str_ = torch.zeros(2 * fi, dtype=torch.float64) if act else None
+    emul_ops.linear_bwd(c(dy), c(z), c(coef), c(x), c(isc), c(ish), c(imu), c(irs), c(w), dwr, dbr, dxr, str_)
+    dx = dx_w[:, 64:128].clone()
+    if act:
+        edge = (x.double() * isc.double() + ish.double()).abs() < 1e-5
+        dx[edge] = 0.0
+        dxr[edge.cpu()] = 0.0
+    assert_close(dx, dxr, TOL, "dx")
+    assert_close(dw_w[:, fi:] - dw0[:, fi:], dwr, TOL, "dw (added to the slice)")
+    assert_close(db - db0, dbr, TOL, "db (added)")
+    assert torch.equal(dw_w[:, :fi], dw0[:, :fi]) and bool((dx_w[:, :64] == 7.0).all()) and bool((dx_w[:, 128:] == 7.0).all())
+    if act and not bool(edge.any()):
+        assert_close(st, str_, 2e-5, "stats_in")
+
+
 @pytest.mark.parametrize("m,k,n", [(1, 1, 1), (37, 10, 8), (300, 64, 64), (5000, 64, 64), (129, 12, 12), (20000, 48, 64),
                                    (4097, 64, 33), (40000, 64, 64)])
 @pytest.mark.parametrize("kn,pro,stats", [(False, False, True), (False, True, True), (True, False, False), (True, True, True)])
