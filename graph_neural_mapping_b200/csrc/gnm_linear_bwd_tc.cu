@@ -708,6 +708,35 @@ struct LinBwd1Params {
     BnTailDev tail;
 };
 
+// the producers' arithmetic on one chunk: dz = cA*dy + cB*z + cC and a = relu(x*scale + shift) for this thread's two rows
+// (landing slots u*3 + {0, 1, 2} = dy, z, x), zero for rows past the end (CHECK), column sums of dz
+template <bool ACT, bool CHECK>
+__device__ __forceinline__ void op_rows(const float4* land, int row_base, int n_rows, const float4& cA, const float4& cB,
+                                        const float4& cC, const float4& sc, const float4& sh, float4 (&vdz)[2],
+                                        float4 (&va)[2], float4& s_dz) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const float4 g = land[(u * 3) * OP_PT];
+        const float4 zz = land[(u * 3 + 1) * OP_PT];
+        float4 a = land[(u * 3 + 2) * OP_PT];
+        const bool okr = !CHECK || row_base + 16 * u < n_rows;
+        float4 dz;
+        dz.x = okr ? fmaf(cA.x, g.x, fmaf(cB.x, zz.x, cC.x)) : 0.f;
+        dz.y = okr ? fmaf(cA.y, g.y, fmaf(cB.y, zz.y, cC.y)) : 0.f;
+        dz.z = okr ? fmaf(cA.z, g.z, fmaf(cB.z, zz.z, cC.z)) : 0.f;
+        dz.w = okr ? fmaf(cA.w, g.w, fmaf(cB.w, zz.w, cC.w)) : 0.f;
+        if (ACT) {
+            a.x = okr ? fmaxf(fmaf(a.x, sc.x, sh.x), 0.f) : 0.f;
+            a.y = okr ? fmaxf(fmaf(a.y, sc.y, sh.y), 0.f) : 0.f;
+            a.z = okr ? fmaxf(fmaf(a.z, sc.z, sh.z), 0.f) : 0.f;
+            a.w = okr ? fmaxf(fmaf(a.w, sc.w, sh.w), 0.f) : 0.f;
+        }
+        vdz[u] = dz;
+        va[u] = a;
+        s_dz.x += dz.x; s_dz.y += dz.y; s_dz.z += dz.z; s_dz.w += dz.w;
+    }
+}
+
 template <bool ACT>
 __global__ void __launch_bounds__(OP_THREADS, 1) linear_bwd_onepass_tc_kernel(const LinBwd1Params p) {
     extern __shared__ __align__(1024) unsigned char op_smem[];
@@ -1000,27 +1029,11 @@ __global__ void __launch_bounds__(OP_THREADS, 1) linear_bwd_onepass_tc_kernel(co
             asm volatile("cp.async.wait_group %0;" ::"n"(OP_DEPTH - 1) : "memory");
             const int row_base = ((int)blockIdx.x + (j >> 2) * G) * 128 + c * 32 + kr0;
             float4 vdz[2], va[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const float4 g = my_land[(d * 6 + u * 3) * OP_PT];
-                const float4 zz = my_land[(d * 6 + u * 3 + 1) * OP_PT];
-                float4 a = my_land[(d * 6 + u * 3 + 2) * OP_PT];
-                const bool okr = row_base + 16 * u < p.n_rows;
-                float4 dz;
-                dz.x = okr ? fmaf(cA.x, g.x, fmaf(cB.x, zz.x, cC.x)) : 0.f;
-                dz.y = okr ? fmaf(cA.y, g.y, fmaf(cB.y, zz.y, cC.y)) : 0.f;
-                dz.z = okr ? fmaf(cA.z, g.z, fmaf(cB.z, zz.z, cC.z)) : 0.f;
-                dz.w = okr ? fmaf(cA.w, g.w, fmaf(cB.w, zz.w, cC.w)) : 0.f;
-                if (ACT) {
-                    a.x = okr ? fmaxf(fmaf(a.x, sc.x, sh.x), 0.f) : 0.f;
-                    a.y = okr ? fmaxf(fmaf(a.y, sc.y, sh.y), 0.f) : 0.f;
-                    a.z = okr ? fmaxf(fmaf(a.z, sc.z, sh.z), 0.f) : 0.f;
-                    a.w = okr ? fmaxf(fmaf(a.w, sc.w, sh.w), 0.f) : 0.f;
-                }
-                vdz[u] = dz;
-                va[u] = a;
-                s_dz.x += dz.x; s_dz.y += dz.y; s_dz.z += dz.z; s_dz.w += dz.w;
-            }
+            // every chunk but the last of the matrix lies wholly inside it: no per-row range checks there
+            if (row_base - kr0 + 31 < p.n_rows)
+                op_rows<ACT, false>(my_land + (size_t)d * 6 * OP_PT, row_base, p.n_rows, cA, cB, cC, sc, sh, vdz, va, s_dz);
+            else
+                op_rows<ACT, true>(my_land + (size_t)d * 6 * OP_PT, row_base, p.n_rows, cA, cB, cC, sc, sh, vdz, va, s_dz);
             // a planes -> ring slot (free once GEMM 2 of the chunk two back has retired)
             const uint32_t slot = (uint32_t)j & 1, bph = ((uint32_t)j >> 1) & 1;
             if (!(ok = mbar_wait<32>(&b_empty[slot], bph ^ 1, abort_flag))) break;
